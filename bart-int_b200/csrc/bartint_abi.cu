@@ -1,0 +1,513 @@
+// C ABI of libbartint_cuda.so (see include/bartint.h for what each entry point replaces in the reference).
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <new>
+
+#include "common.cuh"
+
+namespace bartint {
+const char* get_error();
+
+static int check_device() {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        (void)cudaGetLastError();
+        set_error("no CUDA device available (%s): libbartint_cuda has no CPU path", e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+        return BARTINT_ERR_NODEVICE;
+    }
+    return BARTINT_OK;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    bool active = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) {
+            cudaSetDevice(dev);
+            active = true;
+        }
+    }
+    ~DeviceGuard() {
+        if (active) cudaSetDevice(prev);
+    }
+};
+
+static void free_device(DeviceForest& d) {
+    cudaFree(d.nodes); cudaFree(d.tree_off); cudaFree(d.tree_leaf_off); cudaFree(d.leaf_mu); cudaFree(d.cut_off);
+    cudaFree(d.cut_val); cudaFree(d.node_bit); cudaFree(d.group_tree_off); cudaFree(d.draw_group_off);
+    cudaFree(d.group_rec);
+    d = DeviceForest{};
+}
+
+static int finish_forest(bartint_forest* f, bartint_forest** out) {
+    int rc = forest_finish_host(f);
+    if (rc == BARTINT_OK) rc = check_device();
+    if (rc == BARTINT_OK) {
+        cudaError_t e = cudaGetDevice(&f->device);
+        if (e != cudaSuccess) rc = cuda_fail(e, "cudaGetDevice", __FILE__, __LINE__);
+    }
+    if (rc == BARTINT_OK) rc = forest_upload(f);
+    if (rc == BARTINT_OK) {
+        cudaError_t e = cudaEventCreate(&f->ev0);
+        if (e == cudaSuccess) e = cudaEventCreate(&f->ev1);
+        if (e != cudaSuccess) rc = cuda_fail(e, "cudaEventCreate", __FILE__, __LINE__);
+    }
+    if (rc != BARTINT_OK) {
+        bartint_forest_destroy(f);
+        return rc;
+    }
+    *out = f;
+    return BARTINT_OK;
+}
+
+static int check_cuts(int32_t d, const int32_t* cut_offsets, const double* cut_values) {
+    BI_REQUIRE(d >= 0, BARTINT_ERR_ARG, "d must be >= 0");
+    BI_REQUIRE(cut_offsets != nullptr, BARTINT_ERR_ARG, "cut_offsets is NULL");
+    BI_REQUIRE(cut_offsets[0] == 0, BARTINT_ERR_ARG, "cut_offsets[0] must be 0");
+    for (int32_t j = 0; j < d; ++j)
+        BI_REQUIRE(cut_offsets[j + 1] >= cut_offsets[j], BARTINT_ERR_ARG, "cut_offsets must be non-decreasing");
+    BI_REQUIRE(cut_offsets[d] == 0 || cut_values != nullptr, BARTINT_ERR_ARG, "cut_values is NULL");
+    return BARTINT_OK;
+}
+
+}  // namespace bartint
+
+using namespace bartint;
+
+extern "C" {
+
+int bartint_version(void) { return 100; }
+
+const char* bartint_last_error(void) { return bartint::get_error(); }
+
+int bartint_device_count(int* n_out) {
+    BI_REQUIRE(n_out != nullptr, BARTINT_ERR_ARG, "n_out is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); n = 0; }
+    *n_out = n;
+    return BARTINT_OK;
+}
+
+int bartint_set_device(int device) {
+    int rc = check_device();
+    if (rc) return rc;
+    BI_CUDA(cudaSetDevice(device));
+    return BARTINT_OK;
+}
+
+int bartint_forest_from_dbarts098(const char* const* tree_strings, const double* tree_fits, const double* x_train,
+                                  int64_t n, int32_t d, const int32_t* cut_offsets, const double* cut_values,
+                                  double y_min, double y_max, int32_t m, int32_t S, bartint_forest** out) {
+    BI_REQUIRE(out != nullptr, BARTINT_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    BI_REQUIRE(S >= 0 && m >= 0 && n >= 0, BARTINT_ERR_ARG, "S, m, n must be >= 0");
+    BI_REQUIRE((int64_t)S * m == 0 || tree_strings != nullptr, BARTINT_ERR_ARG, "tree_strings is NULL");
+    BI_REQUIRE((int64_t)S * m * n == 0 || tree_fits != nullptr, BARTINT_ERR_ARG, "tree_fits is NULL");
+    BI_REQUIRE(n * d == 0 || x_train != nullptr, BARTINT_ERR_ARG, "x_train is NULL");
+    int rc = check_cuts(d, cut_offsets, cut_values);
+    if (rc) return rc;
+    bartint_forest* f = new (std::nothrow) bartint_forest();
+    BI_REQUIRE(f != nullptr, BARTINT_ERR_NOMEM, "out of host memory");
+    f->S = S; f->m = m; f->d = d; f->y_min = y_min; f->y_max = y_max;
+    f->cut_off.assign(cut_offsets, cut_offsets + d + 1);
+    f->cut_val.assign(cut_values, cut_values + cut_offsets[d]);
+    rc = parse_dbarts_forest(tree_strings, tree_fits, x_train, n, d, cut_offsets, cut_values, m, S, f);
+    if (rc) { delete f; return rc; }
+    return finish_forest(f, out);
+}
+
+int bartint_forest_from_soa(int32_t S, int32_t m, int32_t d, const int64_t* tree_node_offset, const int32_t* split_var,
+                            const int32_t* split_cut_idx, const int32_t* left, const int32_t* right,
+                            const double* leaf_mu, const int32_t* cut_offsets, const double* cut_values, double y_min,
+                            double y_max, bartint_forest** out) {
+    BI_REQUIRE(out != nullptr, BARTINT_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    BI_REQUIRE(S >= 0 && m >= 0, BARTINT_ERR_ARG, "S and m must be >= 0");
+    BI_REQUIRE(tree_node_offset != nullptr, BARTINT_ERR_ARG, "tree_node_offset is NULL");
+    const bool has_nodes = (int64_t)S * m > 0;
+    BI_REQUIRE(!has_nodes || (split_var && split_cut_idx && left && right && leaf_mu), BARTINT_ERR_ARG,
+               "node arrays must not be NULL");
+    int rc = check_cuts(d, cut_offsets, cut_values);
+    if (rc) return rc;
+    bartint_forest* f = new (std::nothrow) bartint_forest();
+    BI_REQUIRE(f != nullptr, BARTINT_ERR_NOMEM, "out of host memory");
+    f->S = S; f->m = m; f->d = d; f->y_min = y_min; f->y_max = y_max;
+    f->cut_off.assign(cut_offsets, cut_offsets + d + 1);
+    f->cut_val.assign(cut_values, cut_values + cut_offsets[d]);
+    rc = canonicalise_soa(S, m, d, tree_node_offset, split_var, split_cut_idx, left, right, leaf_mu, f);
+    if (rc) { delete f; return rc; }
+    return finish_forest(f, out);
+}
+
+int bartint_forest_info(const bartint_forest* f, int64_t info[10]) {
+    BI_REQUIRE(f != nullptr && info != nullptr, BARTINT_ERR_ARG, "NULL argument");
+    info[0] = f->S; info[1] = f->m; info[2] = f->d; info[3] = f->n_nodes; info[4] = f->n_leaves;
+    info[5] = f->max_depth; info[6] = f->max_internal; info[7] = f->table_ok ? 1 : 0; info[8] = f->n_groups;
+    info[9] = f->nb;
+    return BARTINT_OK;
+}
+
+int bartint_forest_export_soa(const bartint_forest* f, int64_t* tree_node_offset, int32_t* split_var,
+                              int32_t* split_cut_idx, int32_t* left, int32_t* right, double* leaf_mu) {
+    BI_REQUIRE(f != nullptr, BARTINT_ERR_ARG, "forest is NULL");
+    const size_t nn = (size_t)f->n_nodes;
+    if (tree_node_offset) memcpy(tree_node_offset, f->tree_off.data(), f->tree_off.size() * sizeof(int64_t));
+    if (split_var && nn) memcpy(split_var, f->var.data(), nn * sizeof(int32_t));
+    if (split_cut_idx && nn) memcpy(split_cut_idx, f->cut.data(), nn * sizeof(int32_t));
+    if (left && nn) memcpy(left, f->left.data(), nn * sizeof(int32_t));
+    if (right && nn) memcpy(right, f->right.data(), nn * sizeof(int32_t));
+    if (leaf_mu && nn) memcpy(leaf_mu, f->mu.data(), nn * sizeof(double));
+    return BARTINT_OK;
+}
+
+void bartint_forest_destroy(bartint_forest* f) {
+    if (f == nullptr) return;
+    {
+        DeviceGuard g(f->device);
+        free_device(f->dev);
+        if (f->ev0) cudaEventDestroy(f->ev0);
+        if (f->ev1) cudaEventDestroy(f->ev1);
+        (void)cudaGetLastError();
+    }
+    delete f;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+static int make_points(const bartint_forest* f, int64_t N, int32_t d, bartint_points** out) {
+    BI_REQUIRE(f != nullptr && out != nullptr, BARTINT_ERR_ARG, "NULL argument");
+    *out = nullptr;
+    BI_REQUIRE(N >= 0, BARTINT_ERR_ARG, "N must be >= 0");
+    BI_REQUIRE(d == f->d, BARTINT_ERR_ARG, "point matrix has %d columns but the forest was fit on %d variables", d, f->d);
+    bartint_points* p = new (std::nothrow) bartint_points();
+    BI_REQUIRE(p != nullptr, BARTINT_ERR_NOMEM, "out of host memory");
+    p->device = f->device; p->N = N; p->d = d;
+    p->Npad = ((N + TK_TILE - 1) / TK_TILE) * TK_TILE;
+    if (p->Npad == 0) p->Npad = TK_TILE;
+    cudaError_t e = cudaMalloc((void**)&p->codes, (size_t)std::max(d, 1) * (size_t)p->Npad);
+    if (e != cudaSuccess) { delete p; return cuda_fail(e, "cudaMalloc(codes)", __FILE__, __LINE__); }
+    *out = p;
+    return BARTINT_OK;
+}
+
+int bartint_points_from_device(const bartint_forest* f, const double* dX, int64_t N, int32_t d, int64_t ld,
+                               void* stream, bartint_points** out) {
+    int rc = make_points(f, N, d, out);
+    if (rc) return rc;
+    BI_REQUIRE(N * d == 0 || dX != nullptr, BARTINT_ERR_ARG, "X is NULL");
+    BI_REQUIRE(ld >= N, BARTINT_ERR_ARG, "leading dimension smaller than N");
+    DeviceGuard g(f->device);
+    rc = launch_bin_points(dX, ld, N, d, f->dev.cut_off, f->dev.cut_val, f->max_cuts, (*out)->codes, (*out)->Npad,
+                           (cudaStream_t)stream);
+    if (rc) { bartint_points_destroy(*out); *out = nullptr; }
+    return rc;
+}
+
+int bartint_points_from_host(const bartint_forest* f, const double* X, int64_t N, int32_t d, bartint_points** out) {
+    BI_REQUIRE(f != nullptr && out != nullptr, BARTINT_ERR_ARG, "NULL argument");
+    *out = nullptr;
+    BI_REQUIRE(N >= 0 && (N * d == 0 || X != nullptr), BARTINT_ERR_ARG, "X is NULL or N < 0");
+    DeviceGuard g(f->device);
+    double* dX = nullptr;
+    const size_t bytes = (size_t)std::max<int64_t>(N * d, 1) * sizeof(double);
+    BI_CUDA(cudaMalloc((void**)&dX, bytes));
+    cudaError_t e = (N * d) ? cudaMemcpy(dX, X, (size_t)(N * d) * sizeof(double), cudaMemcpyHostToDevice) : cudaSuccess;
+    int rc = (e == cudaSuccess) ? bartint_points_from_device(f, dX, N, d, N, nullptr, out)
+                                : cuda_fail(e, "cudaMemcpy(X)", __FILE__, __LINE__);
+    if (rc == BARTINT_OK) {
+        e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { rc = cuda_fail(e, "bin_points", __FILE__, __LINE__); bartint_points_destroy(*out); *out = nullptr; }
+    }
+    cudaFree(dX);
+    return rc;
+}
+
+int64_t bartint_points_count(const bartint_points* p) { return p ? p->N : -1; }
+
+int bartint_points_codes(const bartint_points* p, uint8_t* codes_out) {
+    BI_REQUIRE(p != nullptr && (codes_out != nullptr || p->N * p->d == 0), BARTINT_ERR_ARG, "NULL argument");
+    DeviceGuard g(p->device);
+    BI_CUDA(cudaDeviceSynchronize());
+    if (p->N > 0 && p->d > 0)
+        BI_CUDA(cudaMemcpy2D(codes_out, (size_t)p->N, p->codes, (size_t)p->Npad, (size_t)p->N, (size_t)p->d,
+                             cudaMemcpyDeviceToHost));
+    return BARTINT_OK;
+}
+
+void bartint_points_destroy(bartint_points* p) {
+    if (p == nullptr) return;
+    {
+        DeviceGuard g(p->device);
+        cudaFree(p->codes);
+        (void)cudaGetLastError();
+    }
+    delete p;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+static int check_range(const bartint_forest* f, const bartint_points* p, int32_t draw_begin, int32_t draw_end) {
+    BI_REQUIRE(f != nullptr && p != nullptr, BARTINT_ERR_ARG, "NULL forest or points");
+    BI_REQUIRE(p->d == f->d && p->device == f->device, BARTINT_ERR_ARG, "points were not created for this forest");
+    BI_REQUIRE(0 <= draw_begin && draw_begin <= draw_end && draw_end <= f->S, BARTINT_ERR_ARG,
+               "draw range [%d, %d) outside [0, %d)", draw_begin, draw_end, f->S);
+    return BARTINT_OK;
+}
+
+// core: run the evaluation kernel + second-stage merges, everything on `st`, outputs on device (scaled units)
+static int eval_core(const bartint_forest* f, const bartint_points* p, uint32_t flags, int32_t draw_begin,
+                     int32_t draw_end, double* d_draw_sum, double* d_point_mean, double* d_point_m2,
+                     int32_t* d_leaf, double* d_full, double fp_scale, double fp_y0, int fp_scaled, cudaStream_t st) {
+    const int ndraws = draw_end - draw_begin;
+    f->last_launches = 0;
+    f->last_timed = false;
+    if (ndraws == 0) return BARTINT_OK;
+    const bool want_mom = d_point_mean != nullptr && d_point_m2 != nullptr;
+    if (d_leaf != nullptr) flags |= BARTINT_FORCE_WALK;
+    EvalPlan plan = make_plan(f, p, flags, draw_begin, draw_end, want_mom);
+    f->last_used_table = plan.use_table ? 1 : 0;
+    double *draw_part = nullptr, *pt_mean = nullptr, *pt_m2 = nullptr;
+    BI_CUDA(cudaMallocAsync((void**)&draw_part, sizeof(double) * (size_t)plan.n_tiles * (size_t)ndraws, st));
+    const bool direct_mom = want_mom && plan.n_chunks == 1;   // single chunk: the kernel writes the final moments
+    if (want_mom) {
+        if (direct_mom) { pt_mean = d_point_mean; pt_m2 = d_point_m2; }
+        else {
+            const size_t bytes = sizeof(double) * (size_t)plan.n_chunks * (size_t)std::max<int64_t>(p->N, 1);
+            BI_CUDA(cudaMallocAsync((void**)&pt_mean, bytes, st));
+            BI_CUDA(cudaMallocAsync((void**)&pt_m2, bytes, st));
+        }
+    }
+    BI_CUDA(cudaEventRecord(f->ev0, st));
+    int rc = plan.use_table ? launch_eval_table(f, p, plan, draw_part, pt_mean, pt_m2, d_full, fp_scale, fp_y0, fp_scaled, st)
+                            : launch_eval_walk(f, p, plan, draw_part, pt_mean, pt_m2, d_leaf, d_full, fp_scale, fp_y0, fp_scaled, st);
+    BI_CUDA(cudaEventRecord(f->ev1, st));
+    f->last_timed = true;
+    f->last_launches = 1;
+    if (rc == BARTINT_OK && d_draw_sum != nullptr) {
+        rc = launch_reduce_draw_parts(draw_part, plan.n_tiles, ndraws, d_draw_sum, st);
+        f->last_launches++;
+    }
+    if (rc == BARTINT_OK && want_mom && !direct_mom) {
+        rc = launch_merge_point_parts(pt_mean, pt_m2, plan.n_chunks, plan.chunk_draws, ndraws, p->N, d_point_mean,
+                                      d_point_m2, st);
+        f->last_launches++;
+    }
+    cudaFreeAsync(draw_part, st);
+    if (want_mom && !direct_mom) { cudaFreeAsync(pt_mean, st); cudaFreeAsync(pt_m2, st); }
+    return rc;
+}
+
+int bartint_eval_points_device(const bartint_forest* f, const bartint_points* p, uint32_t flags, int32_t draw_begin,
+                               int32_t draw_end, double* d_draw_sum, double* d_point_mean, double* d_point_m2,
+                               void* stream) {
+    int rc = check_range(f, p, draw_begin, draw_end);
+    if (rc) return rc;
+    BI_REQUIRE((d_point_mean == nullptr) == (d_point_m2 == nullptr), BARTINT_ERR_ARG,
+               "d_point_mean and d_point_m2 must both be given or both be NULL");
+    DeviceGuard g(f->device);
+    return eval_core(f, p, flags, draw_begin, draw_end, d_draw_sum, d_point_mean, d_point_m2, nullptr, nullptr, 1.0, 0.0,
+                     1, (cudaStream_t)stream);
+}
+
+int bartint_merge_moments_device(const bartint_forest* f, uint32_t flags, int32_t G, const int32_t* shard_draws,
+                                 const double* d_mean, const double* d_m2, int64_t N, const double* d_weights,
+                                 int64_t weights_len, double* d_point_mean_out, double* d_point_var_out, void* stream) {
+    BI_REQUIRE(f != nullptr && shard_draws != nullptr && G >= 1, BARTINT_ERR_ARG, "bad shard description");
+    BI_REQUIRE(N == 0 || (d_mean != nullptr && d_m2 != nullptr), BARTINT_ERR_ARG, "NULL moments");
+    BI_REQUIRE(d_weights == nullptr || weights_len == 1 || weights_len == N, BARTINT_ERR_ARG,
+               "weights must have length 1 or N");
+    DeviceGuard g(f->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    int32_t* d_counts = nullptr;
+    BI_CUDA(cudaMallocAsync((void**)&d_counts, sizeof(int32_t) * (size_t)G, st));
+    BI_CUDA(cudaMemcpyAsync(d_counts, shard_draws, sizeof(int32_t) * (size_t)G, cudaMemcpyHostToDevice, st));
+    const int scaled = (flags & BARTINT_SCALED_UNITS) ? 1 : 0;
+    int rc = launch_merge_shards(d_mean, d_m2, G, d_counts, N, f->y_max - f->y_min, f->y_min, scaled, d_weights,
+                                 weights_len, d_point_mean_out, d_point_var_out, st);
+    cudaFreeAsync(d_counts, st);
+    return rc;
+}
+
+int bartint_eval_points(const bartint_forest* f, const bartint_points* p, uint32_t flags, int32_t draw_begin,
+                        int32_t draw_end, const double* weights, int64_t weights_len, double* draw_mean,
+                        double* point_mean, double* point_var, double* full_pred) {
+    int rc = check_range(f, p, draw_begin, draw_end);
+    if (rc) return rc;
+    BI_REQUIRE(weights == nullptr || weights_len == 1 || weights_len == p->N, BARTINT_ERR_ARG,
+               "weights must have length 1 or N");
+    DeviceGuard g(f->device);
+    const int ndraws = draw_end - draw_begin;
+    const int64_t N = p->N;
+    const int scaled = (flags & BARTINT_SCALED_UNITS) ? 1 : 0;
+    const double scale = f->y_max - f->y_min, y0 = f->y_min;
+    cudaStream_t st = nullptr;
+    const bool want_mom = point_mean != nullptr || point_var != nullptr;
+    double *d_sum = nullptr, *d_mean = nullptr, *d_m2 = nullptr, *d_full = nullptr, *d_out = nullptr, *d_w = nullptr,
+           *d_omean = nullptr, *d_ovar = nullptr;
+    int32_t* d_cnt = nullptr;
+    rc = BARTINT_OK;
+    auto cleanup = [&]() {
+        cudaFree(d_sum); cudaFree(d_mean); cudaFree(d_m2); cudaFree(d_full); cudaFree(d_out); cudaFree(d_w);
+        cudaFree(d_omean); cudaFree(d_ovar); cudaFree(d_cnt);
+    };
+#define EP_CUDA(call)                                                             \
+    do {                                                                          \
+        cudaError_t _e = (call);                                                  \
+        if (_e != cudaSuccess) { cleanup(); return cuda_fail(_e, #call, __FILE__, __LINE__); } \
+    } while (0)
+    const size_t nb_draw = sizeof(double) * (size_t)std::max(ndraws, 1), nb_pt = sizeof(double) * (size_t)std::max<int64_t>(N, 1);
+    EP_CUDA(cudaMalloc((void**)&d_sum, nb_draw));
+    EP_CUDA(cudaMalloc((void**)&d_out, nb_draw));
+    if (want_mom) {
+        EP_CUDA(cudaMalloc((void**)&d_mean, nb_pt));
+        EP_CUDA(cudaMalloc((void**)&d_m2, nb_pt));
+        EP_CUDA(cudaMalloc((void**)&d_omean, nb_pt));
+        EP_CUDA(cudaMalloc((void**)&d_ovar, nb_pt));
+        EP_CUDA(cudaMalloc((void**)&d_cnt, sizeof(int32_t)));
+        if (weights != nullptr) {
+            EP_CUDA(cudaMalloc((void**)&d_w, sizeof(double) * (size_t)weights_len));
+            EP_CUDA(cudaMemcpy(d_w, weights, sizeof(double) * (size_t)weights_len, cudaMemcpyHostToDevice));
+        }
+    }
+    if (full_pred != nullptr && (int64_t)ndraws * N > 0)
+        EP_CUDA(cudaMalloc((void**)&d_full, sizeof(double) * (size_t)ndraws * (size_t)N));
+    rc = eval_core(f, p, flags, draw_begin, draw_end, d_sum, want_mom ? d_mean : nullptr, want_mom ? d_m2 : nullptr,
+                   nullptr, d_full, scale, y0, scaled, st);
+    if (rc == BARTINT_OK && draw_mean != nullptr && ndraws > 0)
+        rc = launch_finalize_draws(d_sum, ndraws, N, scale, y0, scaled, d_out, st);
+    if (rc == BARTINT_OK && want_mom && N > 0) {
+        if (ndraws == 0) {
+            // no draws: colMeans / colVars of a 0-row matrix are NaN
+            cleanup();
+            const double nan = std::numeric_limits<double>::quiet_NaN();
+            for (int64_t i = 0; i < N; ++i) { if (point_mean) point_mean[i] = nan; if (point_var) point_var[i] = nan; }
+            return BARTINT_OK;
+        }
+        EP_CUDA(cudaMemcpy(d_cnt, &ndraws, sizeof(int32_t), cudaMemcpyHostToDevice));
+        rc = launch_merge_shards(d_mean, d_m2, 1, d_cnt, N, scale, y0, scaled, d_w, weights_len, d_omean, d_ovar, st);
+    }
+    if (rc != BARTINT_OK) { cleanup(); return rc; }
+    EP_CUDA(cudaDeviceSynchronize());
+    if (draw_mean != nullptr && ndraws > 0) EP_CUDA(cudaMemcpy(draw_mean, d_out, sizeof(double) * (size_t)ndraws, cudaMemcpyDeviceToHost));
+    if (point_mean != nullptr && N > 0) EP_CUDA(cudaMemcpy(point_mean, d_omean, sizeof(double) * (size_t)N, cudaMemcpyDeviceToHost));
+    if (point_var != nullptr && N > 0) EP_CUDA(cudaMemcpy(point_var, d_ovar, sizeof(double) * (size_t)N, cudaMemcpyDeviceToHost));
+    if (d_full != nullptr) EP_CUDA(cudaMemcpy(full_pred, d_full, sizeof(double) * (size_t)ndraws * (size_t)N, cudaMemcpyDeviceToHost));
+    cleanup();
+#undef EP_CUDA
+    return BARTINT_OK;
+}
+
+int bartint_eval(const bartint_forest* f, const double* X, int64_t N, int32_t d, uint32_t flags, const double* weights,
+                 int64_t weights_len, double* draw_mean, double* point_mean, double* point_var, double* full_pred) {
+    BI_REQUIRE(f != nullptr, BARTINT_ERR_ARG, "forest is NULL");
+    bartint_points* p = nullptr;
+    int rc = bartint_points_from_host(f, X, N, d, &p);
+    if (rc) return rc;
+    rc = bartint_eval_points(f, p, flags, 0, f->S, weights, weights_len, draw_mean, point_mean, point_var, full_pred);
+    bartint_points_destroy(p);
+    return rc;
+}
+
+int bartint_leaf_indices(const bartint_forest* f, const bartint_points* p, int32_t draw_begin, int32_t draw_end,
+                         int32_t use_table_kernel, int32_t* out) {
+    int rc = check_range(f, p, draw_begin, draw_end);
+    if (rc) return rc;
+    const int64_t total = (int64_t)(draw_end - draw_begin) * f->m * p->N;
+    if (total == 0) return BARTINT_OK;
+    BI_REQUIRE(out != nullptr, BARTINT_ERR_ARG, "out is NULL");
+    BI_REQUIRE(!use_table_kernel || f->table_ok, BARTINT_ERR_UNSUPPORTED,
+               "the table kernel does not apply to this forest (deep trees, > 127 cuts or too many variables)");
+    DeviceGuard g(f->device);
+    int32_t* d_leaf = nullptr;
+    BI_CUDA(cudaMalloc((void**)&d_leaf, sizeof(int32_t) * (size_t)total));
+    if (use_table_kernel) {
+        rc = launch_table_leaf(f, p, draw_begin, draw_end, d_leaf, nullptr);
+    } else {
+        rc = eval_core(f, p, BARTINT_FORCE_WALK, draw_begin, draw_end, nullptr, nullptr, nullptr, d_leaf, nullptr, 1.0,
+                       0.0, 1, nullptr);
+    }
+    cudaError_t e = cudaDeviceSynchronize();
+    if (rc == BARTINT_OK && e != cudaSuccess) rc = cuda_fail(e, "leaf kernel", __FILE__, __LINE__);
+    if (rc == BARTINT_OK) {
+        e = cudaMemcpy(out, d_leaf, sizeof(int32_t) * (size_t)total, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemcpy(leaf)", __FILE__, __LINE__);
+    }
+    cudaFree(d_leaf);
+    return rc;
+}
+
+int bartint_exact_integrals(const bartint_forest* f, int32_t measure, const double* lo, const double* hi,
+                            int32_t n_draws_used, double* out) {
+    BI_REQUIRE(f != nullptr, BARTINT_ERR_ARG, "forest is NULL");
+    BI_REQUIRE(measure >= 0 && measure <= 2, BARTINT_ERR_ARG, "unknown measure %d", measure);
+    BI_REQUIRE((lo == nullptr) == (hi == nullptr), BARTINT_ERR_ARG, "lo and hi must both be given or both be NULL");
+    int n_draws = (n_draws_used <= 0 || n_draws_used > f->S) ? f->S : n_draws_used;
+    if (n_draws == 0) return BARTINT_OK;
+    BI_REQUIRE(out != nullptr, BARTINT_ERR_ARG, "out is NULL");
+    DeviceGuard g(f->device);
+    const int d = f->d;
+    std::vector<double> box((size_t)2 * std::max(d, 1));
+    for (int j = 0; j < d; ++j) {
+        box[(size_t)j] = lo ? lo[j] : 0.0;                                            // BARTInt.R:151
+        box[(size_t)d + j] = hi ? hi[j] : (measure == BARTINT_MEASURE_EXPONENTIAL ? INFINITY : 1.0);   // :153-155
+    }
+    double *d_box = nullptr, *d_out = nullptr;
+    BI_CUDA(cudaMalloc((void**)&d_box, sizeof(double) * box.size()));
+    cudaError_t e = cudaMalloc((void**)&d_out, sizeof(double) * (size_t)n_draws);
+    if (e == cudaSuccess) e = cudaMemcpy(d_box, box.data(), sizeof(double) * box.size(), cudaMemcpyHostToDevice);
+    int rc = e == cudaSuccess ? launch_exact_integrals(f, measure, d_box, d_box + d, n_draws, d_out, nullptr)
+                              : cuda_fail(e, "exact_integrals setup", __FILE__, __LINE__);
+    if (rc == BARTINT_OK) {
+        e = cudaMemcpy(out, d_out, sizeof(double) * (size_t)n_draws, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = cuda_fail(e, "exact_integrals", __FILE__, __LINE__);
+    }
+    cudaFree(d_box);
+    cudaFree(d_out);
+    return rc;
+}
+
+int bartint_finalize_integrals(const bartint_forest* f, const double* integrals_scaled, int32_t n, double* rescaled_out,
+                               double* mean_out, double* sd_out) {
+    BI_REQUIRE(f != nullptr && n >= 0, BARTINT_ERR_ARG, "bad arguments");
+    if (n == 0) {
+        if (mean_out) *mean_out = std::numeric_limits<double>::quiet_NaN();
+        if (sd_out) *sd_out = std::numeric_limits<double>::quiet_NaN();
+        return BARTINT_OK;
+    }
+    BI_REQUIRE(integrals_scaled != nullptr, BARTINT_ERR_ARG, "integrals is NULL");
+    DeviceGuard g(f->device);
+    double *d_in = nullptr, *d_res = nullptr, *d_ms = nullptr;
+    BI_CUDA(cudaMalloc((void**)&d_in, sizeof(double) * (size_t)(2 * n + 2)));
+    d_res = d_in + n;
+    d_ms = d_res + n;
+    cudaError_t e = cudaMemcpy(d_in, integrals_scaled, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice);
+    int rc = e == cudaSuccess ? launch_finalize_integrals(d_in, n, f->y_min, f->y_max, d_res, d_ms, nullptr)
+                              : cuda_fail(e, "finalize_integrals", __FILE__, __LINE__);
+    double ms[2] = {0, 0};
+    if (rc == BARTINT_OK) {
+        e = cudaMemcpy(ms, d_ms, sizeof(ms), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && rescaled_out) e = cudaMemcpy(rescaled_out, d_res, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = cuda_fail(e, "finalize_integrals", __FILE__, __LINE__);
+    }
+    cudaFree(d_in);
+    if (rc == BARTINT_OK) { if (mean_out) *mean_out = ms[0]; if (sd_out) *sd_out = ms[1]; }
+    return rc;
+}
+
+int bartint_last_eval_profile(const bartint_forest* f, float* kernel_ms, int32_t* n_launches, int32_t* used_table_kernel) {
+    BI_REQUIRE(f != nullptr, BARTINT_ERR_ARG, "forest is NULL");
+    if (n_launches) *n_launches = f->last_launches;
+    if (used_table_kernel) *used_table_kernel = f->last_used_table;
+    if (kernel_ms) {
+        *kernel_ms = 0.f;
+        if (f->last_timed) {
+            DeviceGuard g(f->device);
+            BI_CUDA(cudaEventSynchronize(f->ev1));
+            BI_CUDA(cudaEventElapsedTime(kernel_ms, f->ev0, f->ev1));
+        }
+    }
+    return BARTINT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,154 @@
+// Internal definitions shared by the translation units of libbartint_cuda.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/bartint.h"
+
+namespace bartint {
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing: no exceptions cross the C ABI; status code + thread-local message
+// ---------------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define BI_CUDA(call)                                                            \
+    do {                                                                         \
+        cudaError_t _e = (call);                                                 \
+        if (_e != cudaSuccess) return ::bartint::cuda_fail(_e, #call, __FILE__, __LINE__); \
+    } while (0)
+
+#define BI_REQUIRE(cond, code, ...)                  \
+    do {                                             \
+        if (!(cond)) {                               \
+            ::bartint::set_error(__VA_ARGS__);       \
+            return (code);                           \
+        }                                            \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// device forest layout
+// ---------------------------------------------------------------------------------------------
+// Walk kernel node record (8 B), nodes of a tree stored in pre-order (left child = self + 1):
+//   x = var | cut << 16   (var == 0xFFFF marks a leaf)
+//   y = internal: offset of the right child relative to this node;  leaf: leaf ordinal in the tree
+constexpr uint32_t LEAF_VAR = 0xFFFFu;
+
+// Table kernel ("predicate-byte + joint leaf table"): consecutive trees of one draw are packed into
+// groups whose internal nodes total <= NB.  One record per group, contiguous in HBM so a pipeline
+// stage is one 1-D bulk (TMA) copy:
+//   [ 16 B header | NB x {u32 code-row byte offset = var*TILE, u32 bias x4} | 2^NB doubles ]
+// Predicate of node j for 4 points at once: ((codes4 + bias4) & 0x80808080) with
+// bias = 127 - cut (codes <= 127), i.e. bit 7 of each byte = (code > cut) = "go right".
+// Table entry [idx] = sum over the group's trees of the leaf mu selected by predicate bits idx.
+constexpr int TK_THREADS = 256;        // threads per CTA
+constexpr int TK_Q = 2;                // point quads (4 points) per thread
+constexpr int TK_P = 4 * TK_Q;         // points per thread
+constexpr int TK_TILE = TK_THREADS * TK_P;   // 2048 points per CTA tile
+constexpr int TK_HDR = 16;
+constexpr uint32_t TK_FLAG_END_DRAW = 1u;
+// A tree with more than NB internal nodes cannot be indexed by NB predicate bits.  It gets a record of its own
+// of type WALK:  [ 16 B header | n_nodes x walk-node (8 B) | n_leaves doubles ]  and is walked per point inside the
+// same kernel (rare; the prior puts ~1e-4 of the trees there).  Header: {flags, first tree, n_trees | n_nodes, 0}.
+constexpr uint32_t TK_FLAG_WALK = 2u;
+__host__ __device__ constexpr int tk_rec_bytes(int nb) { return TK_HDR + nb * 8 + (8 << nb); }
+
+struct DeviceForest {
+    uint2* nodes = nullptr;            // n_nodes
+    int32_t* tree_off = nullptr;       // S*m+1
+    int32_t* tree_leaf_off = nullptr;  // S*m+1
+    double* leaf_mu = nullptr;         // n_leaves
+    int32_t* cut_off = nullptr;        // d+1
+    double* cut_val = nullptr;
+    // table path
+    uint8_t* node_bit = nullptr;       // n_nodes: predicate bit of an internal node within its group
+    int32_t* group_tree_off = nullptr; // n_groups+1: first tree (linear index) of each group
+    int32_t* draw_group_off = nullptr; // S+1: first group of each draw
+    uint8_t* group_rec = nullptr;      // n_groups * tk_rec_bytes(nb)
+};
+
+}  // namespace bartint
+
+struct bartint_forest {
+    int device = 0;
+    int32_t S = 0, m = 0, d = 0;
+    int64_t n_nodes = 0, n_leaves = 0;
+    int32_t max_depth = 0, max_internal = 0, max_cuts = 0;
+    double y_min = 0, y_max = 1;
+    // canonical (pre-order) host SoA
+    std::vector<int64_t> tree_off;
+    std::vector<int32_t> var, cut, left, right;
+    std::vector<double> mu;
+    std::vector<int32_t> cut_off;
+    std::vector<double> cut_val;
+    // table path
+    bool table_ok = false;
+    int nb = 0;
+    int64_t n_groups = 0;
+    std::vector<int32_t> draw_group_off;  // host copy, S+1
+    bartint::DeviceForest dev;
+    // profile of the last evaluation
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    mutable int last_launches = 0;
+    mutable int last_used_table = 0;
+    mutable bool last_timed = false;
+};
+
+struct bartint_points {
+    int device = 0;
+    int64_t N = 0, Npad = 0;
+    int32_t d = 0;
+    uint8_t* codes = nullptr;  // feature-major: codes[f * Npad + i], zero padded to Npad (multiple of TK_TILE)
+};
+
+namespace bartint {
+
+// host-side pieces (forest_host.cpp)
+int forest_finish_host(bartint_forest* f);      // validate canonical SoA, compute stats
+int forest_upload(bartint_forest* f);           // build device arrays (+ table groups)
+int parse_dbarts_forest(const char* const* tree_strings, const double* tree_fits, const double* x_train,
+                        int64_t n, int32_t d, const int32_t* cut_offsets, const double* cut_values,
+                        int32_t m, int32_t S, bartint_forest* f);
+int canonicalise_soa(int32_t S, int32_t m, int32_t d, const int64_t* tree_node_offset, const int32_t* split_var,
+                     const int32_t* split_cut_idx, const int32_t* left, const int32_t* right,
+                     const double* leaf_mu, bartint_forest* f);
+
+// kernel launchers (kernels_*.cu)
+int launch_bin_points(const double* dX, int64_t ld, int64_t N, int32_t d, const int32_t* d_cut_off,
+                      const double* d_cut_val, int max_cuts, uint8_t* codes, int64_t Npad, cudaStream_t st);
+int launch_build_tables(const bartint_forest* f, const uint2* d_desc, const uint32_t* d_hdr, cudaStream_t st);
+
+struct EvalPlan {
+    int32_t draw_begin, draw_end;
+    int n_tiles, n_chunks, chunk_draws;
+    bool use_table;
+};
+EvalPlan make_plan(const bartint_forest* f, const bartint_points* p, uint32_t flags, int32_t draw_begin,
+                   int32_t draw_end, bool want_moments);
+
+// draw_part: [n_tiles][ndraws]; pt_mean / pt_m2: [n_chunks][N] (may be null = no moments)
+int launch_eval_walk(const bartint_forest* f, const bartint_points* p, const EvalPlan& plan, double* draw_part,
+                     double* pt_mean, double* pt_m2, int32_t* leaf_out, double* full_pred, double fp_scale,
+                     double fp_y0, int fp_scaled, cudaStream_t st);
+int launch_eval_table(const bartint_forest* f, const bartint_points* p, const EvalPlan& plan, double* draw_part,
+                      double* pt_mean, double* pt_m2, double* full_pred, double fp_scale, double fp_y0,
+                      int fp_scaled, cudaStream_t st);
+int launch_table_leaf(const bartint_forest* f, const bartint_points* p, int32_t draw_begin, int32_t draw_end,
+                      int32_t* leaf_out, cudaStream_t st);
+int launch_reduce_draw_parts(const double* draw_part, int n_tiles, int ndraws, double* draw_sum, cudaStream_t st);
+int launch_merge_point_parts(const double* pt_mean, const double* pt_m2, int n_chunks, int chunk_draws, int ndraws,
+                             int64_t N, double* mean_out, double* m2_out, cudaStream_t st);
+int launch_merge_shards(const double* mean, const double* m2, int G, const int32_t* d_counts, int64_t N,
+                        double scale, double y0, int scaled, const double* w, int64_t wlen, double* mean_out,
+                        double* var_out, cudaStream_t st);
+int launch_finalize_draws(const double* draw_sum, int ndraws, int64_t N, double scale, double y0, int scaled,
+                          double* out, cudaStream_t st);
+int launch_exact_integrals(const bartint_forest* f, int measure, const double* d_lo, const double* d_hi,
+                           int n_draws, double* d_out, cudaStream_t st);
+int launch_finalize_integrals(const double* d_in, int n, double y_min, double y_max, double* d_rescaled,
+                              double* d_mean_sd, cudaStream_t st);
+
+}  // namespace bartint

@@ -1,0 +1,390 @@
+// Host side of the forest container: the dbarts 0.9-8 tree-state exporter (strings + savedTreeFits ->
+// SoA), SoA canonicalisation, table-group planning and the upload to HBM.
+//
+// Reference behaviour restated here (never copied): getTree(), src/BARTInt.R:92-133 --
+//   :110-111 savedTrees[treeNum, sampleNum] / savedTreeFits[, treeNum, sampleNum]
+//   :118-119 tokenisation gsub("\\.", "\\. ") + strsplit(" ") feeding dbarts:::buildTree
+//   :122-125 route the training rows, leaf mu = fit of a training row in that leaf
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+
+#include "common.cuh"
+
+namespace bartint {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+const char* get_error() { return g_err; }
+
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+    set_error("CUDA error %d (%s) at %s:%d in %s", (int)e, cudaGetErrorString(e), file, line, what);
+    // clear the sticky-less error state so later calls report their own failures
+    (void)cudaGetLastError();
+    return (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? BARTINT_ERR_NODEVICE : BARTINT_ERR_CUDA;
+}
+
+// ---------------------------------------------------------------------------------------------
+// string parser: tree := "." | VAR " " CUT " " tree tree   (pre-order, 0-based ints)
+// Accepts any run of spaces between tokens (the reference tokeniser inserts one after every '.').
+// Appends the tree's nodes in pre-order; child indices are relative to the tree's first node.
+// ---------------------------------------------------------------------------------------------
+struct TreeBuf {
+    std::vector<int32_t> var, cut, left, right;
+};
+
+static bool parse_int(const char*& p, int32_t& out) {
+    while (*p == ' ') ++p;
+    if (*p < '0' || *p > '9') return false;
+    int64_t v = 0;
+    while (*p >= '0' && *p <= '9') {
+        v = v * 10 + (*p - '0');
+        if (v > std::numeric_limits<int32_t>::max()) return false;
+        ++p;
+    }
+    out = (int32_t)v;
+    return true;
+}
+
+static int parse_tree_string(const char* s, TreeBuf& t) {
+    t.var.clear(); t.cut.clear(); t.left.clear(); t.right.clear();
+    const char* p = s;
+    // explicit stack of internal nodes still waiting for their right child
+    std::vector<int32_t> pending;
+    bool done = false;
+    while (!done) {
+        while (*p == ' ') ++p;
+        if (*p == '\0') return BARTINT_ERR_PARSE;
+        int32_t me = (int32_t)t.var.size();
+        if (*p == '.') {
+            ++p;
+            t.var.push_back(-1); t.cut.push_back(0); t.left.push_back(-1); t.right.push_back(-1);
+            // a finished subtree: it is the left child of the node above (already linked as me = parent+1)
+            // or the right child of the innermost pending node
+            while (true) {
+                if (pending.empty()) { done = true; break; }
+                int32_t par = pending.back();
+                if (t.right[par] == -2) {          // left subtree just completed -> next node is its right child
+                    t.right[par] = (int32_t)t.var.size();
+                    break;
+                }
+                pending.pop_back();                // right subtree completed -> this node is complete too
+            }
+        } else {
+            int32_t v, c;
+            if (!parse_int(p, v) || !parse_int(p, c)) return BARTINT_ERR_PARSE;
+            t.var.push_back(v); t.cut.push_back(c);
+            t.left.push_back(me + 1);
+            t.right.push_back(-2);                 // -2: waiting for the left subtree to finish
+            pending.push_back(me);
+        }
+    }
+    while (*p == ' ') ++p;
+    if (*p != '\0') return BARTINT_ERR_PARSE;     // tree$remainder must be empty
+    return BARTINT_OK;
+}
+
+static inline int bin_value(double x, const double* cuts, int nc) {
+    // #{k : x > cut[k]} for ascending cuts; NaN -> 0
+    int lo = 0, len = nc;
+    while (len > 0) {
+        int h = len >> 1;
+        bool r = cuts[lo + h] < x;
+        lo = r ? lo + h + 1 : lo;
+        len = r ? len - h - 1 : h;
+    }
+    return lo;
+}
+
+int parse_dbarts_forest(const char* const* tree_strings, const double* tree_fits, const double* x_train,
+                        int64_t n, int32_t d, const int32_t* cut_offsets, const double* cut_values,
+                        int32_t m, int32_t S, bartint_forest* f) {
+    const int64_t n_trees = (int64_t)S * m;
+    std::vector<TreeBuf> trees((size_t)n_trees);
+    int status = BARTINT_OK;
+    int64_t bad_tree = -1;
+#pragma omp parallel for schedule(static)
+    for (int64_t k = 0; k < n_trees; ++k) {
+        if (tree_strings[k] == nullptr || parse_tree_string(tree_strings[k], trees[(size_t)k]) != BARTINT_OK) {
+#pragma omp critical
+            { status = BARTINT_ERR_PARSE; bad_tree = k; }
+        }
+    }
+    if (status != BARTINT_OK) {
+        set_error("malformed dbarts tree string at tree %lld (draw %lld)", (long long)(bad_tree % m),
+                  (long long)(bad_tree / m));
+        return status;
+    }
+    // integer cut map of the training matrix (dbarts keeps x as cut indices internally)
+    std::vector<int32_t> codes((size_t)(n * d));
+    for (int32_t j = 0; j < d; ++j) {
+        const double* cuts = cut_values + cut_offsets[j];
+        int nc = cut_offsets[j + 1] - cut_offsets[j];
+        for (int64_t i = 0; i < n; ++i) codes[(size_t)(j * n + i)] = bin_value(x_train[j * n + i], cuts, nc);
+    }
+    f->tree_off.assign((size_t)n_trees + 1, 0);
+    for (int64_t k = 0; k < n_trees; ++k) f->tree_off[(size_t)k + 1] = f->tree_off[(size_t)k] + (int64_t)trees[(size_t)k].var.size();
+    const int64_t nn = f->tree_off[(size_t)n_trees];
+    f->var.resize((size_t)nn); f->cut.resize((size_t)nn); f->left.resize((size_t)nn); f->right.resize((size_t)nn);
+    f->mu.assign((size_t)nn, 0.0);
+    int bad = 0;
+#pragma omp parallel for schedule(static)
+    for (int64_t k = 0; k < n_trees; ++k) {
+        const TreeBuf& t = trees[(size_t)k];
+        const int64_t base = f->tree_off[(size_t)k];
+        const int32_t cnt = (int32_t)t.var.size();
+        int32_t n_leaf = 0;
+        for (int32_t a = 0; a < cnt; ++a) {
+            f->var[(size_t)(base + a)] = t.var[a]; f->cut[(size_t)(base + a)] = t.cut[a];
+            f->left[(size_t)(base + a)] = t.left[a]; f->right[(size_t)(base + a)] = t.right[a];
+            if (t.var[a] < 0) { ++n_leaf; f->mu[(size_t)(base + a)] = std::numeric_limits<double>::quiet_NaN(); }
+            else if (t.var[a] >= d || t.cut[a] >= cut_offsets[t.var[a] + 1] - cut_offsets[t.var[a]]) {
+#pragma omp atomic write
+                bad = 1;
+            }
+        }
+        if (bad) continue;
+        // leaf mu = fit of the first training row routed to the leaf (fillPlotInfoForNode)
+        const double* fits = tree_fits + (size_t)k * (size_t)n;   // [obs, tree, sample] column-major
+        int32_t found = 0;
+        std::vector<char> have((size_t)cnt, 0);
+        for (int64_t i = 0; i < n && found < n_leaf; ++i) {
+            int32_t a = 0;
+            while (t.var[a] >= 0) a = (codes[(size_t)(t.var[a] * n + i)] > t.cut[a]) ? t.right[a] : t.left[a];
+            if (!have[(size_t)a]) { f->mu[(size_t)(base + a)] = fits[i]; have[(size_t)a] = 1; ++found; }
+        }
+    }
+    if (bad) {
+        set_error("tree string references a variable or cut index outside the cut-point table");
+        return BARTINT_ERR_PARSE;
+    }
+    return BARTINT_OK;
+}
+
+int canonicalise_soa(int32_t S, int32_t m, int32_t d, const int64_t* off, const int32_t* var, const int32_t* cut,
+                     const int32_t* left, const int32_t* right, const double* mu, bartint_forest* f) {
+    const int64_t n_trees = (int64_t)S * m;
+    BI_REQUIRE(off[0] == 0, BARTINT_ERR_ARG, "tree_node_offset[0] must be 0");
+    for (int64_t k = 0; k < n_trees; ++k)
+        BI_REQUIRE(off[k + 1] > off[k], BARTINT_ERR_ARG, "tree %lld has no nodes", (long long)k);
+    const int64_t nn = off[n_trees];
+    f->tree_off.assign(off, off + n_trees + 1);
+    f->var.resize((size_t)nn); f->cut.resize((size_t)nn); f->left.resize((size_t)nn); f->right.resize((size_t)nn);
+    f->mu.resize((size_t)nn);
+    int bad = 0;
+#pragma omp parallel for schedule(static)
+    for (int64_t k = 0; k < n_trees; ++k) {
+        const int64_t base = off[k];
+        const int32_t cnt = (int32_t)(off[k + 1] - base);
+        // pre-order renumbering from the root (node 0 of the tree)
+        std::vector<int32_t> order; order.reserve(cnt);
+        std::vector<int32_t> newid((size_t)cnt, -1), stack;
+        stack.push_back(0);
+        bool ok = true;
+        while (!stack.empty() && ok) {
+            int32_t a = stack.back(); stack.pop_back();
+            if (a < 0 || a >= cnt || newid[a] != -1) { ok = false; break; }
+            newid[a] = (int32_t)order.size(); order.push_back(a);
+            if (var[base + a] >= 0) {
+                if (var[base + a] >= d) { ok = false; break; }
+                stack.push_back(right[base + a]);
+                stack.push_back(left[base + a]);
+            }
+        }
+        if (!ok || (int32_t)order.size() != cnt) {
+#pragma omp atomic write
+            bad = 1;
+            continue;
+        }
+        for (int32_t b = 0; b < cnt; ++b) {
+            int32_t a = order[b];
+            bool leaf = var[base + a] < 0;
+            f->var[(size_t)(base + b)] = leaf ? -1 : var[base + a];
+            f->cut[(size_t)(base + b)] = leaf ? 0 : cut[base + a];
+            f->left[(size_t)(base + b)] = leaf ? -1 : newid[left[base + a]];
+            f->right[(size_t)(base + b)] = leaf ? -1 : newid[right[base + a]];
+            f->mu[(size_t)(base + b)] = leaf ? mu[base + a] : 0.0;
+        }
+    }
+    BI_REQUIRE(!bad, BARTINT_ERR_ARG, "SoA forest is not a set of binary trees rooted at node 0 (bad child index, cycle, unreachable node or variable >= d)");
+    return BARTINT_OK;
+}
+
+int forest_finish_host(bartint_forest* f) {
+    const int64_t n_trees = (int64_t)f->S * f->m;
+    f->n_nodes = f->tree_off[(size_t)n_trees];
+    BI_REQUIRE(f->n_nodes < (int64_t)1 << 31, BARTINT_ERR_UNSUPPORTED, "forest has more than 2^31 nodes");
+    f->max_cuts = 0;
+    for (int32_t j = 0; j < f->d; ++j) {
+        int nc = f->cut_off[(size_t)j + 1] - f->cut_off[(size_t)j];
+        BI_REQUIRE(nc >= 0, BARTINT_ERR_ARG, "cut_offsets must be non-decreasing");
+        f->max_cuts = std::max(f->max_cuts, nc);
+        for (int k = 1; k < nc; ++k)
+            BI_REQUIRE(f->cut_val[(size_t)f->cut_off[(size_t)j] + k] >= f->cut_val[(size_t)f->cut_off[(size_t)j] + k - 1],
+                       BARTINT_ERR_ARG, "cut points of variable %d are not ascending", j);
+    }
+    BI_REQUIRE(f->max_cuts <= 255, BARTINT_ERR_UNSUPPORTED, "more than 255 cut points for one variable (codes are uint8)");
+    BI_REQUIRE(f->d < 65535, BARTINT_ERR_UNSUPPORTED, "more than 65534 variables");
+    int64_t n_leaves = 0;
+    int32_t max_depth = 0, max_internal = 0;
+    int bad = 0;
+#pragma omp parallel for schedule(static) reduction(+ : n_leaves) reduction(max : max_depth, max_internal)
+    for (int64_t k = 0; k < n_trees; ++k) {
+        const int64_t base = f->tree_off[(size_t)k];
+        const int32_t cnt = (int32_t)(f->tree_off[(size_t)k + 1] - base);
+        int32_t internal = 0;
+        // depth via pre-order scan with a stack of "subtree ends"
+        std::vector<int32_t> depth((size_t)cnt, 0);
+        for (int32_t a = 0; a < cnt; ++a) {
+            if (f->var[(size_t)(base + a)] >= 0) {
+                ++internal;
+                int32_t v = f->var[(size_t)(base + a)], c = f->cut[(size_t)(base + a)];
+                if (c < 0 || c >= f->cut_off[(size_t)v + 1] - f->cut_off[(size_t)v]) bad = 1;
+                depth[(size_t)f->left[(size_t)(base + a)]] = depth[(size_t)a] + 1;
+                depth[(size_t)f->right[(size_t)(base + a)]] = depth[(size_t)a] + 1;
+            } else {
+                ++n_leaves;
+            }
+            max_depth = std::max(max_depth, depth[(size_t)a]);
+        }
+        if (cnt != 2 * internal + 1) bad = 1;
+        max_internal = std::max(max_internal, internal);
+    }
+    BI_REQUIRE(!bad, BARTINT_ERR_ARG, "forest has a cut index outside its variable's cut-point list or a malformed tree");
+    f->n_leaves = n_leaves;
+    f->max_depth = max_depth;
+    f->max_internal = max_internal;
+    return BARTINT_OK;
+}
+
+template <typename T>
+static int upload(T** dptr, const std::vector<T>& h) {
+    size_t bytes = std::max<size_t>(h.size(), 1) * sizeof(T);
+    BI_CUDA(cudaMalloc((void**)dptr, bytes));
+    if (!h.empty()) BI_CUDA(cudaMemcpy(*dptr, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return BARTINT_OK;
+}
+
+static int table_bits_from_env() {
+    const char* e = getenv("BARTINT_TABLE_BITS");
+    int nb = e ? atoi(e) : 8;
+    if (nb < 4) nb = 4;
+    if (nb > 8) nb = 8;
+    return nb;
+}
+
+int forest_upload(bartint_forest* f) {
+    const int64_t n_trees = (int64_t)f->S * f->m;
+    const int64_t nn = f->n_nodes;
+    std::vector<uint2> nodes((size_t)nn);
+    std::vector<int32_t> tree_off((size_t)n_trees + 1), leaf_off((size_t)n_trees + 1, 0);
+    std::vector<double> leaf_mu((size_t)f->n_leaves);
+    for (int64_t k = 0; k <= n_trees; ++k) tree_off[(size_t)k] = (int32_t)f->tree_off[(size_t)k];
+    // leaf offsets (prefix sum), then fill
+    for (int64_t k = 0; k < n_trees; ++k) {
+        int32_t cnt = tree_off[(size_t)k + 1] - tree_off[(size_t)k];
+        leaf_off[(size_t)k + 1] = leaf_off[(size_t)k] + (cnt + 1) / 2;
+    }
+#pragma omp parallel for schedule(static)
+    for (int64_t k = 0; k < n_trees; ++k) {
+        const int32_t base = tree_off[(size_t)k], cnt = tree_off[(size_t)k + 1] - base;
+        int32_t ord = 0;
+        for (int32_t a = 0; a < cnt; ++a) {
+            const size_t g = (size_t)(base + a);
+            if (f->var[g] >= 0) {
+                nodes[g] = make_uint2((uint32_t)f->var[g] | ((uint32_t)f->cut[g] << 16), (uint32_t)(f->right[g] - a));
+            } else {
+                nodes[g] = make_uint2(LEAF_VAR, (uint32_t)ord);
+                leaf_mu[(size_t)leaf_off[(size_t)k] + ord] = f->mu[g];
+                ++ord;
+            }
+        }
+    }
+    int rc;
+    if ((rc = upload(&f->dev.nodes, nodes))) return rc;
+    if ((rc = upload(&f->dev.tree_off, tree_off))) return rc;
+    if ((rc = upload(&f->dev.tree_leaf_off, leaf_off))) return rc;
+    if ((rc = upload(&f->dev.leaf_mu, leaf_mu))) return rc;
+    if ((rc = upload(&f->dev.cut_off, f->cut_off))) return rc;
+    if ((rc = upload(&f->dev.cut_val, f->cut_val))) return rc;
+
+    // ---- table path planning: greedy packing of consecutive trees of a draw into <= NB predicate bits ----
+    f->nb = table_bits_from_env();
+    // a tree that does not fit NB predicate bits becomes a WALK record if its nodes + leaf values fit one record
+    const int walk_cap_leaves = (tk_rec_bytes(f->nb) - TK_HDR + 8) / 24;   // 8*(2K-1) + 8*K <= REC - HDR
+    f->table_ok = n_trees > 0 && (f->max_internal <= f->nb || f->max_internal + 1 <= walk_cap_leaves) &&
+                  f->max_cuts <= 127 && (int64_t)f->d * TK_TILE <= 160 * 1024;
+    f->n_groups = 0;
+    if (!f->table_ok) return BARTINT_OK;
+    const int NB = f->nb;
+    std::vector<int32_t> group_tree_off;   // first tree of each group
+    std::vector<uint32_t> hdr;             // flags per group
+    std::vector<uint2> desc;               // NB per group: {var*TILE, bias x4}
+    std::vector<uint8_t> node_bit((size_t)nn, 0);
+    f->draw_group_off.assign((size_t)f->S + 1, 0);
+    group_tree_off.reserve((size_t)(n_trees / 3 + f->S + 1));
+    for (int32_t s = 0; s < f->S; ++s) {
+        f->draw_group_off[(size_t)s] = (int32_t)group_tree_off.size();
+        int bits = NB + 1;   // force a new group at the start of a draw
+        for (int32_t t = 0; t < f->m; ++t) {
+            const int64_t k = (int64_t)s * f->m + t;
+            const int32_t base = tree_off[(size_t)k], cnt = tree_off[(size_t)k + 1] - base;
+            const int internal = (cnt - 1) / 2;
+            if (internal > NB) {               // WALK record holding just this tree
+                group_tree_off.push_back((int32_t)k);
+                hdr.push_back(TK_FLAG_WALK);
+                desc.resize(desc.size() + (size_t)NB, make_uint2(0u, 0u));
+                bits = NB + 1;                 // the next tree starts a fresh table group
+                continue;
+            }
+            if (bits + internal > NB) {
+                group_tree_off.push_back((int32_t)k);
+                hdr.push_back(0u);
+                desc.resize(desc.size() + (size_t)NB, make_uint2(0u, 0u));   // unused slots: bias 0 -> predicate 0
+                bits = 0;
+            }
+            uint2* gd = &desc[desc.size() - (size_t)NB];
+            for (int32_t a = 0; a < cnt; ++a) {
+                const size_t g = (size_t)(base + a);
+                if (f->var[g] >= 0) {
+                    node_bit[g] = (uint8_t)bits;
+                    uint32_t bias = (uint32_t)(127 - f->cut[g]);
+                    gd[bits] = make_uint2((uint32_t)f->var[g] * (uint32_t)TK_TILE, bias * 0x01010101u);
+                    ++bits;
+                }
+            }
+        }
+        hdr.back() |= TK_FLAG_END_DRAW;
+    }
+    f->draw_group_off[(size_t)f->S] = (int32_t)group_tree_off.size();
+    f->n_groups = (int64_t)group_tree_off.size();
+    group_tree_off.push_back((int32_t)n_trees);
+    // group g covers trees [group_tree_off[g], min(group_tree_off[g+1], end of its draw)) -- groups never span draws
+    if ((rc = upload(&f->dev.node_bit, node_bit))) return rc;
+    if ((rc = upload(&f->dev.group_tree_off, group_tree_off))) return rc;
+    if ((rc = upload(&f->dev.draw_group_off, f->draw_group_off))) return rc;
+    BI_CUDA(cudaMalloc((void**)&f->dev.group_rec, (size_t)f->n_groups * (size_t)tk_rec_bytes(NB) + 16));
+    uint2* d_desc = nullptr;
+    uint32_t* d_hdr = nullptr;
+    if ((rc = upload(&d_desc, desc))) return rc;
+    if ((rc = upload(&d_hdr, hdr))) { cudaFree(d_desc); return rc; }
+    rc = launch_build_tables(f, d_desc, d_hdr, 0);
+    cudaError_t e = cudaDeviceSynchronize();
+    cudaFree(d_desc);
+    cudaFree(d_hdr);
+    if (rc) return rc;
+    BI_CUDA(e);
+    return BARTINT_OK;
+}
+
+}  // namespace bartint

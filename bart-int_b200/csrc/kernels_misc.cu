@@ -1,0 +1,401 @@
+// K0 point binning, table builder, K2 exact leaf-probability integral, K3 merges/finalisation.
+#include <cmath>
+
+#include "common.cuh"
+
+namespace bartint {
+
+// ---------------------------------------------------------------------------------------------
+// K0  bin_points: code = #{k : x > cut[j][k]}  (dbarts' integer cut map of x.test).
+// HBM-bound streaming kernel: reads 8 B, writes 1 B per matrix element.  One thread = 4 consecutive
+// points of one variable -> one 32-bit word of the feature-major code array (the word the table
+// kernel's byte-SIMD compare consumes).  Grid: x over point quads, y over variables.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t bin_one(double x, const double* __restrict__ cuts, int nc) {
+    int lo = 0, len = nc;
+    while (len > 0) {
+        int h = len >> 1;
+        bool r = cuts[lo + h] < x;      // NaN: false -> code 0
+        lo = r ? lo + h + 1 : lo;
+        len = r ? len - h - 1 : h;
+    }
+    return (uint32_t)lo;
+}
+
+__global__ void __launch_bounds__(256) bin_points_kernel(const double* __restrict__ X, int64_t ld, int64_t N,
+                                                         const int32_t* __restrict__ cut_off,
+                                                         const double* __restrict__ cut_val,
+                                                         uint32_t* __restrict__ codes4, int64_t quads_per_row) {
+    __shared__ double s_cut[256];
+    const int j = blockIdx.y;
+    const int c0 = cut_off[j], nc = cut_off[j + 1] - c0;
+    for (int k = threadIdx.x; k < nc; k += blockDim.x) s_cut[k] = cut_val[c0 + k];
+    __syncthreads();
+    const double* __restrict__ col = X + (int64_t)j * ld;
+    const bool aligned16 = ((reinterpret_cast<uintptr_t>(col) & 15) == 0);
+    for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < quads_per_row;
+         w += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = w * 4;
+        double x0 = 0, x1 = 0, x2 = 0, x3 = 0;
+        uint32_t word = 0;
+        if (i + 3 < N) {
+            if (aligned16) {
+                double2 a = __ldg(reinterpret_cast<const double2*>(col + i));
+                double2 b = __ldg(reinterpret_cast<const double2*>(col + i + 2));
+                x0 = a.x; x1 = a.y; x2 = b.x; x3 = b.y;
+            } else {
+                x0 = __ldg(col + i); x1 = __ldg(col + i + 1); x2 = __ldg(col + i + 2); x3 = __ldg(col + i + 3);
+            }
+            word = bin_one(x0, s_cut, nc) | (bin_one(x1, s_cut, nc) << 8) | (bin_one(x2, s_cut, nc) << 16) |
+                   (bin_one(x3, s_cut, nc) << 24);
+        } else {
+            for (int k = 0; k < 4; ++k)
+                if (i + k < N) word |= bin_one(__ldg(col + i + k), s_cut, nc) << (8 * k);
+        }
+        codes4[(int64_t)j * quads_per_row + w] = word;   // padding quads (i >= N) are written as 0
+    }
+}
+
+int launch_bin_points(const double* dX, int64_t ld, int64_t N, int32_t d, const int32_t* d_cut_off,
+                      const double* d_cut_val, int max_cuts, uint8_t* codes, int64_t Npad, cudaStream_t st) {
+    (void)max_cuts;
+    if (d == 0 || Npad == 0) return BARTINT_OK;
+    const int64_t quads = Npad / 4;
+    int64_t bx = (quads + 255) / 256;
+    // a few waves of 148 SMs x 8 resident CTAs; grid-stride beyond that
+    const int64_t cap = (148 * 8 * 4 + d - 1) / d;
+    if (bx > cap) bx = cap;
+    if (bx < 1) bx = 1;
+    dim3 grid((unsigned)bx, (unsigned)d);
+    bin_points_kernel<<<grid, 256, 0, st>>>(dX, ld, N, d_cut_off, d_cut_val, reinterpret_cast<uint32_t*>(codes), quads);
+    BI_CUDA(cudaGetLastError());
+    return BARTINT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Table builder: one CTA per group, one thread per table entry.  Thread idx walks every tree of the
+// group taking "right" at an internal node iff its predicate bit is set in idx, and sums the leaf
+// values in tree order.  Threads < NB also copy the node descriptors; thread 0 writes the header.
+// ---------------------------------------------------------------------------------------------
+__global__ void build_tables_kernel(const uint2* __restrict__ nodes, const int32_t* __restrict__ tree_off,
+                                    const int32_t* __restrict__ tree_leaf_off, const double* __restrict__ leaf_mu,
+                                    const uint8_t* __restrict__ node_bit, const int32_t* __restrict__ group_tree_off,
+                                    const uint2* __restrict__ desc, const uint32_t* __restrict__ hdr, int nb,
+                                    uint8_t* __restrict__ rec_base) {
+    const int64_t g = blockIdx.x;
+    const uint32_t idx = threadIdx.x;
+    uint8_t* rec = rec_base + g * (int64_t)tk_rec_bytes(nb);
+    const int32_t tb = group_tree_off[g], te = group_tree_off[g + 1];
+    const uint32_t flags = hdr[g];
+    if (flags & TK_FLAG_WALK) {
+        // copy the single tree of this record: walk nodes, then its leaf values
+        const int32_t n0 = tree_off[tb], cnt = tree_off[tb + 1] - n0, l0 = tree_leaf_off[tb];
+        uint2* wn = reinterpret_cast<uint2*>(rec + TK_HDR);
+        double* wmu = reinterpret_cast<double*>(rec + TK_HDR + 8 * cnt);
+        for (int a = idx; a < cnt; a += blockDim.x) wn[a] = nodes[n0 + a];
+        for (int a = idx; a < (cnt + 1) / 2; a += blockDim.x) wmu[a] = leaf_mu[l0 + a];
+        if (idx == 0) *reinterpret_cast<uint4*>(rec) = make_uint4(flags, (uint32_t)tb, (uint32_t)cnt, 0u);
+        return;
+    }
+    double sum = 0.0;
+    for (int32_t k = tb; k < te; ++k) {
+        int32_t node = tree_off[k];
+        uint2 r = nodes[node];
+        while ((r.x & 0xFFFFu) != LEAF_VAR) {
+            const uint32_t bit = node_bit[node];
+            node += ((idx >> bit) & 1u) ? (int32_t)r.y : 1;
+            r = nodes[node];
+        }
+        sum += leaf_mu[tree_leaf_off[k] + (int32_t)r.y];
+    }
+    reinterpret_cast<double*>(rec + TK_HDR + nb * 8)[idx] = sum;
+    if ((int)idx < nb) reinterpret_cast<uint2*>(rec + TK_HDR)[idx] = desc[g * nb + idx];
+    if (idx == 0) {
+        uint4 h = make_uint4(flags, (uint32_t)tb, (uint32_t)(te - tb), 0u);
+        *reinterpret_cast<uint4*>(rec) = h;
+    }
+}
+
+int launch_build_tables(const bartint_forest* f, const uint2* d_desc, const uint32_t* d_hdr, cudaStream_t st) {
+    if (f->n_groups == 0) return BARTINT_OK;
+    build_tables_kernel<<<(unsigned)f->n_groups, 1u << f->nb, 0, st>>>(
+        f->dev.nodes, f->dev.tree_off, f->dev.tree_leaf_off, f->dev.leaf_mu, f->dev.node_bit, f->dev.group_tree_off,
+        d_desc, d_hdr, f->nb, f->dev.group_rec);
+    BI_CUDA(cudaGetLastError());
+    return BARTINT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3  deterministic second-stage reductions (fixed summation order, no floating-point atomics)
+// ---------------------------------------------------------------------------------------------
+__global__ void reduce_draw_parts_kernel(const double* __restrict__ part, int n_tiles, int ndraws,
+                                         double* __restrict__ out) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= ndraws) return;
+    double acc = 0.0;
+    for (int t = 0; t < n_tiles; ++t) acc += part[(int64_t)t * ndraws + s];
+    out[s] = acc;
+}
+
+int launch_reduce_draw_parts(const double* draw_part, int n_tiles, int ndraws, double* draw_sum, cudaStream_t st) {
+    if (ndraws == 0) return BARTINT_OK;
+    reduce_draw_parts_kernel<<<(ndraws + 127) / 128, 128, 0, st>>>(draw_part, n_tiles, ndraws, draw_sum);
+    BI_CUDA(cudaGetLastError());
+    return BARTINT_OK;
+}
+
+// Chan et al. pairwise merge of (n, mean, M2), applied in chunk order
+__device__ __forceinline__ void chan_merge(double& n, double& mean, double& m2, double nb, double meanb, double m2b) {
+    if (nb == 0.0) return;
+    if (n == 0.0) { n = nb; mean = meanb; m2 = m2b; return; }
+    const double tot = n + nb;
+    const double delta = meanb - mean;
+    mean = mean + delta * (nb / tot);
+    m2 = m2 + m2b + delta * delta * (n * nb / tot);
+    n = tot;
+}
+
+__global__ void merge_point_parts_kernel(const double* __restrict__ pt_mean, const double* __restrict__ pt_m2,
+                                         int n_chunks, int chunk_draws, int ndraws, int64_t N,
+                                         double* __restrict__ mean_out, double* __restrict__ m2_out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    double n = 0.0, mean = 0.0, m2 = 0.0;
+    for (int c = 0; c < n_chunks; ++c) {
+        int cnt = min(chunk_draws, ndraws - c * chunk_draws);
+        chan_merge(n, mean, m2, (double)cnt, pt_mean[(int64_t)c * N + i], pt_m2[(int64_t)c * N + i]);
+    }
+    mean_out[i] = mean;
+    m2_out[i] = m2;
+}
+
+int launch_merge_point_parts(const double* pt_mean, const double* pt_m2, int n_chunks, int chunk_draws, int ndraws,
+                             int64_t N, double* mean_out, double* m2_out, cudaStream_t st) {
+    if (N == 0) return BARTINT_OK;
+    merge_point_parts_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(pt_mean, pt_m2, n_chunks, chunk_draws,
+                                                                          ndraws, N, mean_out, m2_out);
+    BI_CUDA(cudaGetLastError());
+    return BARTINT_OK;
+}
+
+// merge G draw shards (other GPUs' partials, shard-major) and apply colVars * weights / colMeans scaling
+__global__ void merge_shards_kernel(const double* __restrict__ mean, const double* __restrict__ m2, int G,
+                                    const int32_t* __restrict__ counts, int64_t N, double scale, double y0, int scaled,
+                                    const double* __restrict__ w, int64_t wlen, double* __restrict__ mean_out,
+                                    double* __restrict__ var_out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    double n = 0.0, mu = 0.0, M2 = 0.0;
+    for (int g = 0; g < G; ++g) chan_merge(n, mu, M2, (double)counts[g], mean[(int64_t)g * N + i], m2[(int64_t)g * N + i]);
+    if (mean_out) mean_out[i] = scaled ? mu : scale * (mu + 0.5) + y0;
+    if (var_out) {
+        double v = M2 / (n - 1.0);                       // n == 1 -> 0/0 = NaN like colVars on one row
+        if (!scaled) v = v * scale * scale;
+        if (w) v *= (wlen == 1 ? w[0] : w[i]);
+        var_out[i] = v;
+    }
+}
+
+int launch_merge_shards(const double* mean, const double* m2, int G, const int32_t* d_counts, int64_t N, double scale,
+                        double y0, int scaled, const double* w, int64_t wlen, double* mean_out, double* var_out,
+                        cudaStream_t st) {
+    if (N == 0) return BARTINT_OK;
+    merge_shards_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(mean, m2, G, d_counts, N, scale, y0, scaled, w,
+                                                                     wlen, mean_out, var_out);
+    BI_CUDA(cudaGetLastError());
+    return BARTINT_OK;
+}
+
+// rowMeans(predict(model, X)):  (ymax - ymin) * (sum/N + 0.5) + ymin
+__global__ void finalize_draws_kernel(const double* __restrict__ draw_sum, int ndraws, double inv_n_is_div,
+                                      double scale, double y0, int scaled, double* __restrict__ out) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= ndraws) return;
+    const double mean = draw_sum[s] / inv_n_is_div;     // N == 0 -> 0/0 = NaN like rowMeans of a 0-column matrix
+    out[s] = scaled ? mean : scale * (mean + 0.5) + y0;
+}
+
+int launch_finalize_draws(const double* draw_sum, int ndraws, int64_t N, double scale, double y0, int scaled,
+                          double* out, cudaStream_t st) {
+    if (ndraws == 0) return BARTINT_OK;
+    finalize_draws_kernel<<<(ndraws + 127) / 128, 128, 0, st>>>(draw_sum, ndraws, (double)N, scale, y0, scaled, out);
+    BI_CUDA(cudaGetLastError());
+    return BARTINT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2  exact leaf-probability integral, one thread per tree (S*m trees, a few leaves each).
+// Restates fillProbabilityForNode (BARTInt.R:32-72) + terminalProbability (:10-30) + the leaf sum of
+// singleTreeSum (:165-173).  The box [lo, hi]^d lives in a per-thread column of a global scratch
+// (interleaved so that warp accesses to the same variable coalesce); the DFS stack keeps, per level,
+// what is needed to undo the box narrowing and the conditional probability of the child currently
+// being visited, so P(leaf) is multiplied leaf-first going up exactly like the reference.
+// ---------------------------------------------------------------------------------------------
+constexpr int K2_MAX_DEPTH = 64;
+
+__device__ __forceinline__ double pexp1(double q) {   // stats::pexp(q), rate 1
+    return q <= 0.0 ? 0.0 : -expm1(-q);
+}
+
+__device__ __forceinline__ void child_probs(int measure, double lo, double hi, double rule, double& pl, double& pr) {
+    if (measure == BARTINT_MEASURE_UNIFORM) {                       // :46-48
+        pl = (rule - lo) / (hi - lo);
+        pr = (hi - rule) / (hi - lo);
+    } else if (measure == BARTINT_MEASURE_GAUSSIAN_REFCOMPAT) {     // :49-52 (as written: quirk B3)
+        const double norm = normcdf(hi - 0.5) - normcdf(lo - 0.5);
+        pl = (normcdf(rule) - normcdf(lo)) / norm;
+        pr = 1.0 - pl;
+    } else {                                                        // :53-56
+        const double norm = pexp1(hi) - pexp1(lo);
+        pl = (pexp1(rule) - pexp1(lo)) / norm;
+        pr = 1.0 - pl;
+    }
+}
+
+__global__ void __launch_bounds__(128) exact_tree_integral_kernel(
+    const uint2* __restrict__ nodes, const int32_t* __restrict__ tree_off, const int32_t* __restrict__ tree_leaf_off,
+    const double* __restrict__ leaf_mu, const int32_t* __restrict__ cut_off, const double* __restrict__ cut_val,
+    int d, int64_t n_trees, int measure, const double* __restrict__ lo0, const double* __restrict__ hi0,
+    double* __restrict__ box, double* __restrict__ tree_int) {
+    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double* blo = box + tid;                       // blo[j * nthreads], bhi = blo + d * nthreads
+    double* bhi = box + (int64_t)d * nthreads + tid;
+    for (int j = 0; j < d; ++j) { blo[(int64_t)j * nthreads] = lo0[j]; bhi[(int64_t)j * nthreads] = hi0[j]; }
+
+    int32_t st_var[K2_MAX_DEPTH];
+    int32_t st_node[K2_MAX_DEPTH];
+    uint8_t st_phase[K2_MAX_DEPTH];
+    double st_rule[K2_MAX_DEPTH], st_old[K2_MAX_DEPTH], st_cp[K2_MAX_DEPTH], st_pr[K2_MAX_DEPTH];
+
+    for (int64_t k = tid; k < n_trees; k += nthreads) {
+        const int32_t base = tree_off[k];
+        const double* mu = leaf_mu + tree_leaf_off[k];
+        double total = 0.0;
+        int sp = 0;
+        int32_t node = base;
+        while (true) {
+            const uint2 r = nodes[node];
+            const uint32_t v = r.x & 0xFFFFu;
+            if (v != LEAF_VAR) {
+                const double rule = cut_val[cut_off[v] + (int)(r.x >> 16)];       // :45
+                const double lo = blo[(int64_t)v * nthreads], hi = bhi[(int64_t)v * nthreads];
+                double pl, pr;
+                child_probs(measure, lo, hi, rule, pl, pr);
+                st_var[sp] = (int32_t)v; st_node[sp] = node + (int32_t)r.y; st_phase[sp] = 0;
+                st_rule[sp] = rule; st_old[sp] = hi; st_cp[sp] = pl; st_pr[sp] = pr;
+                ++sp;
+                bhi[(int64_t)v * nthreads] = rule;                               // :62  leftCut = (lo, rule)
+                node = node + 1;
+                continue;
+            }
+            // leaf: P = prob(leaf) * prob(parent) * ... excluding the root (:22-27); stump -> 1 (:67-69)
+            double p = 1.0;
+            if (sp > 0) {
+                p = st_cp[sp - 1];
+                for (int a = sp - 2; a >= 0; --a) p = p * st_cp[a];
+            }
+            total = total + p * mu[r.y];                                          // :172
+            // backtrack to the innermost ancestor whose right subtree is still to visit
+            bool found = false;
+            while (sp > 0) {
+                const int a = sp - 1;
+                const int32_t v2 = st_var[a];
+                if (st_phase[a] == 0) {
+                    bhi[(int64_t)v2 * nthreads] = st_old[a];                      // restore hi
+                    st_old[a] = blo[(int64_t)v2 * nthreads];
+                    blo[(int64_t)v2 * nthreads] = st_rule[a];                     // :64  rightCut = (rule, hi)
+                    st_phase[a] = 1;
+                    st_cp[a] = st_pr[a];
+                    node = st_node[a];
+                    found = true;
+                    break;
+                }
+                blo[(int64_t)v2 * nthreads] = st_old[a];                          // restore lo
+                --sp;
+            }
+            if (!found) break;
+        }
+        tree_int[k] = total;
+    }
+}
+
+// posteriorSum (BARTInt.R:198): sum of the m single-tree sums of one draw, in tree order
+__global__ void draw_integral_kernel(const double* __restrict__ tree_int, int m, int n_draws, double* __restrict__ out) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_draws) return;
+    double acc = 0.0;
+    for (int t = 0; t < m; ++t) acc += tree_int[(int64_t)s * m + t];
+    out[s] = acc;
+}
+
+int launch_exact_integrals(const bartint_forest* f, int measure, const double* d_lo, const double* d_hi, int n_draws,
+                           double* d_out, cudaStream_t st) {
+    if (n_draws == 0) return BARTINT_OK;
+    BI_REQUIRE(f->max_depth <= K2_MAX_DEPTH, BARTINT_ERR_UNSUPPORTED,
+               "exact integral supports trees up to depth %d (forest has depth %d)", K2_MAX_DEPTH, f->max_depth);
+    const int64_t n_trees = (int64_t)n_draws * f->m;
+    int blocks = (int)std::min<int64_t>((n_trees + 127) / 128, 148 * 4);
+    const int64_t nthreads = (int64_t)blocks * 128;
+    double *box = nullptr, *tree_int = nullptr;
+    BI_CUDA(cudaMallocAsync((void**)&box, sizeof(double) * (size_t)(2 * std::max(f->d, 1)) * (size_t)nthreads, st));
+    BI_CUDA(cudaMallocAsync((void**)&tree_int, sizeof(double) * (size_t)n_trees, st));
+    exact_tree_integral_kernel<<<blocks, 128, 0, st>>>(f->dev.nodes, f->dev.tree_off, f->dev.tree_leaf_off,
+                                                       f->dev.leaf_mu, f->dev.cut_off, f->dev.cut_val, f->d, n_trees,
+                                                       measure, d_lo, d_hi, box, tree_int);
+    BI_CUDA(cudaGetLastError());
+    draw_integral_kernel<<<(n_draws + 127) / 128, 128, 0, st>>>(tree_int, f->m, n_draws, d_out);
+    BI_CUDA(cudaGetLastError());
+    BI_CUDA(cudaFreeAsync(box, st));
+    BI_CUDA(cudaFreeAsync(tree_int, st));
+    return BARTINT_OK;
+}
+
+// BARTInt.R:260-262: rescale, mean, sd (n-1).  One CTA; fixed-order tree reduction in shared memory.
+__global__ void __launch_bounds__(256) finalize_integrals_kernel(const double* __restrict__ in, int n, double y_min,
+                                                                 double y_max, double* __restrict__ rescaled,
+                                                                 double* __restrict__ mean_sd) {
+    __shared__ double s_red[256];
+    __shared__ double s_mean;
+    const int t = threadIdx.x;
+    double acc = 0.0;
+    for (int i = t; i < n; i += 256) {
+        const double v = (in[i] + 0.5) * (y_max - y_min) + y_min;     // :260
+        if (rescaled) rescaled[i] = v;
+        acc += v;
+    }
+    s_red[t] = acc;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if (t < w) s_red[t] += s_red[t + w];
+        __syncthreads();
+    }
+    if (t == 0) s_mean = s_red[0] / (double)n;                        // :261
+    __syncthreads();
+    const double mean = s_mean;
+    acc = 0.0;
+    for (int i = t; i < n; i += 256) {
+        const double v = (in[i] + 0.5) * (y_max - y_min) + y_min;
+        acc += (v - mean) * (v - mean);
+    }
+    __syncthreads();
+    s_red[t] = acc;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if (t < w) s_red[t] += s_red[t + w];
+        __syncthreads();
+    }
+    if (t == 0) {
+        mean_sd[0] = mean;
+        mean_sd[1] = sqrt(s_red[0] / (double)(n - 1));                 // :262  (n == 1 -> NaN like R)
+    }
+}
+
+int launch_finalize_integrals(const double* d_in, int n, double y_min, double y_max, double* d_rescaled,
+                              double* d_mean_sd, cudaStream_t st) {
+    finalize_integrals_kernel<<<1, 256, 0, st>>>(d_in, n, y_min, y_max, d_rescaled, d_mean_sd);
+    BI_CUDA(cudaGetLastError());
+    return BARTINT_OK;
+}
+
+}  // namespace bartint

@@ -1,0 +1,327 @@
+"""Forest / Points handles over the C ABI, and the FlatForest (SoA) host container.
+
+Vocabulary follows the reference: a *forest* is a dbarts posterior of S draws x m trees
+(`model$fit$state[[1]]@savedTrees`, BARTInt.R:110); *points* are rows of the matrix handed to
+`predict(model, X)` (BARTInt.R:312); *cut points* are `dbarts:::createCutPoints` (BARTInt.R:108).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _lib
+
+
+class BartIntError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"bartint {_lib.STATUS_NAMES.get(status, status)}: {message}")
+        self.status = status
+
+
+def _check(status: int) -> None:
+    if status != 0:
+        raise BartIntError(status, _lib.load().bartint_last_error().decode("utf-8", "replace"))
+
+
+def _p(arr, ctype):
+    return None if arr is None else arr.ctypes.data_as(C.POINTER(ctype))
+
+
+@dataclass
+class FlatForest:
+    """Flattened posterior (SoA).  Tree (draw s, tree t) is at linear index t + s*m.
+
+    var == -1 marks a leaf; left/right are node indices relative to the tree's first node;
+    mu is the leaf value in dbarts' scaled response units.
+    """
+    S: int
+    m: int
+    d: int
+    tree_offset: np.ndarray
+    var: np.ndarray
+    cut: np.ndarray
+    left: np.ndarray
+    right: np.ndarray
+    mu: np.ndarray
+    cut_offsets: np.ndarray
+    cut_values: np.ndarray
+    y_min: float = -0.5
+    y_max: float = 0.5
+    meta: dict = field(default_factory=dict)
+
+    def __post_init__(self):
+        self.tree_offset = np.ascontiguousarray(self.tree_offset, np.int64)
+        for k in ("var", "cut", "left", "right", "cut_offsets"):
+            setattr(self, k, np.ascontiguousarray(getattr(self, k), np.int32))
+        self.mu = np.ascontiguousarray(self.mu, np.float64)
+        self.cut_values = np.ascontiguousarray(self.cut_values, np.float64)
+
+    @property
+    def n_trees(self) -> int:
+        return self.S * self.m
+
+    @property
+    def n_nodes(self) -> int:
+        return int(self.tree_offset[-1])
+
+    def cut_lists(self):
+        return [self.cut_values[self.cut_offsets[j]:self.cut_offsets[j + 1]] for j in range(self.d)]
+
+    def slice_draws(self, lo: int, hi: int) -> "FlatForest":
+        """Sub-forest of draws [lo, hi) (used for draw-sharding across GPUs)."""
+        a, b = int(self.tree_offset[lo * self.m]), int(self.tree_offset[hi * self.m])
+        return FlatForest(hi - lo, self.m, self.d, self.tree_offset[lo * self.m:hi * self.m + 1] - a,
+                          self.var[a:b], self.cut[a:b], self.left[a:b], self.right[a:b], self.mu[a:b],
+                          self.cut_offsets, self.cut_values, self.y_min, self.y_max, dict(self.meta))
+
+    # ---- dbarts 0.9-8 wire format, for exporter tests and synthetic "models" ----
+    def tree_string(self, k: int) -> str:
+        """Pre-order string of tree k: tree := "." | VAR " " CUT " " tree tree (0-based ints)."""
+        a = int(self.tree_offset[k])
+        out = []
+        stack = [0]
+        while stack:
+            node = stack.pop()
+            if self.var[a + node] < 0:
+                out.append(".")
+            else:
+                out.append(f"{int(self.var[a + node])} {int(self.cut[a + node])} ")
+                stack.append(int(self.right[a + node]))
+                stack.append(int(self.left[a + node]))
+        return "".join(out)
+
+    def to_dbarts_state(self, x_train: np.ndarray):
+        """(savedTrees [m, S] of str, savedTreeFits [n, m, S]) as dbarts would hold them for this forest:
+        the fit of training row i under tree (t, s) is the mu of the leaf the row falls in."""
+        x_train = np.asarray(x_train, np.float64)
+        n = x_train.shape[0]
+        strings = np.empty((self.m, self.S), dtype=object)
+        fits = np.zeros((n, self.m, self.S))
+        cl = self.cut_lists()
+        rows = np.arange(n)
+        for s in range(self.S):
+            for t in range(self.m):
+                k = t + s * self.m
+                strings[t, s] = self.tree_string(k)
+                a, b = int(self.tree_offset[k]), int(self.tree_offset[k + 1])
+                var, cut, left, right = self.var[a:b], self.cut[a:b], self.left[a:b], self.right[a:b]
+                node = np.zeros(n, np.int64)
+                for _ in range(b - a):
+                    v = var[node]
+                    internal = v >= 0
+                    if not internal.any():
+                        break
+                    vi = np.where(internal, v, 0)
+                    cv = np.array([cl[p][q] for p, q in zip(vi, np.where(internal, cut[node], 0))])
+                    node = np.where(internal, np.where(x_train[rows, vi] > cv, right[node], left[node]), node)
+                fits[:, t, s] = self.mu[a + node]
+        return strings, fits
+
+
+class Points:
+    """A point set binned to cut-point codes, resident in HBM (dbarts' integer cut map of x.test)."""
+
+    def __init__(self, forest: "Forest", handle: int, N: int):
+        self._forest = forest
+        self._h = C.c_void_p(handle)
+        self.N = N
+
+    def codes(self) -> np.ndarray:
+        """(N, d) uint8 codes: #{k : x > cut[j][k]} (for the bit-exactness tests)."""
+        out = np.zeros((self._forest.d, self.N), np.uint8)
+        _check(_lib.load().bartint_points_codes(self._h, _p(out, C.c_uint8)))
+        return out.T.copy()
+
+    def close(self):
+        if self._h:
+            _lib.load().bartint_points_destroy(self._h)
+            self._h = C.c_void_p(None)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Forest:
+    """A flattened posterior resident in HBM."""
+
+    def __init__(self, handle: int):
+        self._h = C.c_void_p(handle)
+        info = (C.c_int64 * 10)()
+        _check(_lib.load().bartint_forest_info(self._h, info))
+        (self.S, self.m, self.d, self.n_nodes, self.n_leaves, self.max_depth, self.max_internal, tk, self.n_groups,
+         self.table_bits) = [int(v) for v in info]
+        self.table_kernel_ok = bool(tk)
+        self.y_min = self.y_max = None
+
+    # ---- constructors ----
+    @classmethod
+    def from_soa(cls, ff: FlatForest) -> "Forest":
+        lib = _lib.load()
+        h = C.c_void_p()
+        _check(lib.bartint_forest_from_soa(ff.S, ff.m, ff.d, _p(ff.tree_offset, C.c_int64), _p(ff.var, C.c_int32),
+                                           _p(ff.cut, C.c_int32), _p(ff.left, C.c_int32), _p(ff.right, C.c_int32),
+                                           _p(ff.mu, C.c_double), _p(ff.cut_offsets, C.c_int32),
+                                           _p(ff.cut_values, C.c_double), float(ff.y_min), float(ff.y_max),
+                                           C.byref(h)))
+        f = cls(h.value)
+        f.y_min, f.y_max = float(ff.y_min), float(ff.y_max)
+        return f
+
+    @classmethod
+    def from_dbarts(cls, tree_strings, tree_fits, x_train, cut_lists, y_min, y_max) -> "Forest":
+        """Exporter: dbarts 0.9-8 saved state -> HBM forest (getTree, BARTInt.R:92-133, for all trees).
+
+        tree_strings [m, S] (R: savedTrees[treeNum, sampleNum]); tree_fits [n, m, S]; x_train [n, d].
+        """
+        lib = _lib.load()
+        tree_strings = np.asarray(tree_strings, dtype=object)
+        m, S = tree_strings.shape
+        x_train = np.asarray(x_train, np.float64)
+        n, d = x_train.shape
+        fits = np.asfortranarray(np.asarray(tree_fits, np.float64).reshape(n, m, S))
+        xt = np.asfortranarray(x_train)
+        enc = [str(tree_strings[k % m, k // m]).encode("ascii") for k in range(m * S)]
+        arr = (C.c_char_p * max(len(enc), 1))(*enc)
+        cut_offsets = np.zeros(d + 1, np.int32)
+        cut_offsets[1:] = np.cumsum([len(c) for c in cut_lists])
+        cut_values = (np.concatenate([np.asarray(c, np.float64) for c in cut_lists]) if d else np.zeros(0))
+        cut_values = np.ascontiguousarray(cut_values)
+        h = C.c_void_p()
+        _check(lib.bartint_forest_from_dbarts098(arr, _p(fits, C.c_double), _p(xt, C.c_double), n, d,
+                                                 _p(cut_offsets, C.c_int32), _p(cut_values, C.c_double),
+                                                 float(y_min), float(y_max), m, S, C.byref(h)))
+        f = cls(h.value)
+        f.y_min, f.y_max = float(y_min), float(y_max)
+        f._cut_offsets, f._cut_values = cut_offsets, cut_values
+        return f
+
+    def export_soa(self) -> dict:
+        n = self.n_nodes
+        off = np.zeros(self.S * self.m + 1, np.int64)
+        var, cut, left, right = (np.zeros(n, np.int32) for _ in range(4))
+        mu = np.zeros(n)
+        _check(_lib.load().bartint_forest_export_soa(self._h, _p(off, C.c_int64), _p(var, C.c_int32),
+                                                     _p(cut, C.c_int32), _p(left, C.c_int32), _p(right, C.c_int32),
+                                                     _p(mu, C.c_double)))
+        return dict(tree_offset=off, var=var, cut=cut, left=left, right=right, mu=mu)
+
+    # ---- points ----
+    def points(self, X) -> Points:
+        """Bin a host matrix (N x d, any layout) on the device."""
+        X = np.asarray(X, np.float64)
+        if X.ndim == 1:
+            X = X.reshape(-1, self.d) if self.d else X.reshape(-1, 0)
+        N, d = X.shape
+        Xf = np.asfortranarray(X)
+        h = C.c_void_p()
+        _check(_lib.load().bartint_points_from_host(self._h, _p(Xf, C.c_double), N, d, C.byref(h)))
+        return Points(self, h.value, N)
+
+    def points_from_device(self, dptr: int, N: int, ld: int | None = None, stream: int = 0) -> Points:
+        """Bin a column-major N x d fp64 matrix that already lives in HBM (dptr = device address)."""
+        h = C.c_void_p()
+        _check(_lib.load().bartint_points_from_device(self._h, C.c_void_p(dptr), N, self.d, ld or N,
+                                                      C.c_void_p(stream), C.byref(h)))
+        return Points(self, h.value, N)
+
+    # ---- evaluation ----
+    def eval(self, pts, weights=None, want=("draw_mean", "point_mean", "point_var"), scaled=False, draws=None,
+             force_walk=False) -> dict:
+        """predict + colVars*weights + rowMeans (+ the full S x N matrix when asked), fused on the device."""
+        own = not isinstance(pts, Points)
+        if own:
+            pts = self.points(pts)
+        try:
+            lo, hi = (0, self.S) if draws is None else draws
+            nd = hi - lo
+            out = {}
+            if "draw_mean" in want:
+                out["draw_mean"] = np.zeros(nd)
+            if "point_mean" in want:
+                out["point_mean"] = np.zeros(pts.N)
+            if "point_var" in want:
+                out["point_var"] = np.zeros(pts.N)
+            if "full_pred" in want:
+                out["full_pred"] = np.zeros((nd, pts.N), order="F")
+            w = None
+            if weights is not None:
+                w = np.ascontiguousarray(np.asarray(weights, np.float64).ravel())
+            flags = (_lib.BARTINT_SCALED_UNITS if scaled else 0) | (_lib.BARTINT_FORCE_WALK if force_walk else 0)
+            _check(_lib.load().bartint_eval_points(
+                self._h, pts._h, flags, lo, hi, _p(w, C.c_double), 0 if w is None else w.size,
+                _p(out.get("draw_mean"), C.c_double), _p(out.get("point_mean"), C.c_double),
+                _p(out.get("point_var"), C.c_double), _p(out.get("full_pred"), C.c_double)))
+            return out
+        finally:
+            if own:
+                pts.close()
+
+    def eval_device(self, pts: Points, d_draw_sum: int = 0, d_point_mean: int = 0, d_point_m2: int = 0, draws=None,
+                    stream: int = 0, force_walk: bool = False) -> None:
+        """Asynchronous evaluation writing raw scaled-unit partials to device addresses (0 = not wanted)."""
+        lo, hi = (0, self.S) if draws is None else draws
+        _check(_lib.load().bartint_eval_points_device(
+            self._h, pts._h, _lib.BARTINT_FORCE_WALK if force_walk else 0, lo, hi, C.c_void_p(d_draw_sum or None),
+            C.c_void_p(d_point_mean or None), C.c_void_p(d_point_m2 or None), C.c_void_p(stream)))
+
+    def merge_moments_device(self, shard_draws, d_mean: int, d_m2: int, N: int, d_weights: int, weights_len: int,
+                             d_mean_out: int, d_var_out: int, scaled=False, stream: int = 0) -> None:
+        sd = np.ascontiguousarray(shard_draws, np.int32)
+        _check(_lib.load().bartint_merge_moments_device(
+            self._h, _lib.BARTINT_SCALED_UNITS if scaled else 0, sd.size, _p(sd, C.c_int32), C.c_void_p(d_mean),
+            C.c_void_p(d_m2), N, C.c_void_p(d_weights or None), weights_len, C.c_void_p(d_mean_out or None),
+            C.c_void_p(d_var_out or None), C.c_void_p(stream)))
+
+    def last_eval_profile(self) -> dict:
+        ms, nl, tk = C.c_float(), C.c_int32(), C.c_int32()
+        _check(_lib.load().bartint_last_eval_profile(self._h, C.byref(ms), C.byref(nl), C.byref(tk)))
+        return {"kernel_ms": ms.value, "launches": nl.value, "table_kernel": bool(tk.value)}
+
+    def leaf_indices(self, pts, draws=None, use_table_kernel=False) -> np.ndarray:
+        """Leaf ordinals, shape (ndraws*m, N), row t + (s - lo)*m."""
+        own = not isinstance(pts, Points)
+        if own:
+            pts = self.points(pts)
+        try:
+            lo, hi = (0, self.S) if draws is None else draws
+            out = np.zeros(((hi - lo) * self.m, pts.N), np.int32)
+            _check(_lib.load().bartint_leaf_indices(self._h, pts._h, lo, hi, int(use_table_kernel),
+                                                    _p(out, C.c_int32)))
+            return out
+        finally:
+            if own:
+                pts.close()
+
+    # ---- exact integral ----
+    def exact_integrals(self, measure="uniform", n_draws_used=None, lo=None, hi=None) -> np.ndarray:
+        n = self.S if not n_draws_used or n_draws_used > self.S else int(n_draws_used)
+        out = np.zeros(n)
+        lo_a = None if lo is None else np.ascontiguousarray(np.broadcast_to(np.asarray(lo, np.float64), (self.d,)))
+        hi_a = None if hi is None else np.ascontiguousarray(np.broadcast_to(np.asarray(hi, np.float64), (self.d,)))
+        _check(_lib.load().bartint_exact_integrals(self._h, _lib.MEASURES[measure], _p(lo_a, C.c_double),
+                                                   _p(hi_a, C.c_double), n, _p(out, C.c_double)))
+        return out
+
+    def finalize_integrals(self, integrals_scaled):
+        x = np.ascontiguousarray(integrals_scaled, np.float64)
+        res = np.zeros_like(x)
+        mean, sd = C.c_double(), C.c_double()
+        _check(_lib.load().bartint_finalize_integrals(self._h, _p(x, C.c_double), x.size, _p(res, C.c_double),
+                                                      C.byref(mean), C.byref(sd)))
+        return res, mean.value, sd.value
+
+    def close(self):
+        if self._h:
+            _lib.load().bartint_forest_destroy(self._h)
+            self._h = C.c_void_p(None)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

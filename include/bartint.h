@@ -1,0 +1,182 @@
+/*
+ * bartint.h -- C ABI of libbartint_cuda.so, the B200 (sm_100a) implementation of the BART-Int
+ * posterior-evaluation hot path.
+ *
+ * The reference (ImperialCollegeLondon/BART-Int) has no FFI layer: the path sits behind plain R
+ * calls.  Every entry point below states the reference R expression(s) it replaces (file:line under
+ * /root/reference).  INTEGRATION.md shows the .Call shim a maintainer adds on the R side.
+ *
+ * Conventions
+ *   - plain C, all buffers caller-owned, nothing retained after return, no exceptions/longjmp
+ *     across the boundary: every function returns a bartint_status (0 = OK) and
+ *     bartint_last_error() gives the thread-local message;
+ *   - matrices use R layout: column-major double, 32-bit ints;
+ *   - "scaled units" are dbarts' internal response units  y' = (y - y_min)/(y_max - y_min) - 0.5;
+ *     "original units" are what predict() returns:  (y_max - y_min) * (sum_t mu + 0.5) + y_min;
+ *   - tree (draw s, tree t) has linear index  t + s*m  == R's savedTrees[t+1, s+1];
+ *   - functions ending in _device take DEVICE pointers and a cudaStream_t (passed as void*) and
+ *     are asynchronous on that stream; all others take HOST pointers and block;
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point returns
+ *     BARTINT_ERR_NODEVICE.
+ */
+#ifndef BARTINT_H
+#define BARTINT_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bartint_forest bartint_forest; /* flattened posterior (S draws x m trees) resident in HBM */
+typedef struct bartint_points bartint_points; /* point set binned to cut-point codes, resident in HBM   */
+
+typedef enum {
+    BARTINT_OK = 0,
+    BARTINT_ERR_ARG = 1,         /* NULL / bad sizes / inconsistent arrays              */
+    BARTINT_ERR_PARSE = 2,       /* malformed dbarts tree string                        */
+    BARTINT_ERR_CUDA = 3,        /* CUDA runtime error (message has the cudaError text)  */
+    BARTINT_ERR_UNSUPPORTED = 4, /* e.g. more than 255 cut points for one variable       */
+    BARTINT_ERR_NOMEM = 5,
+    BARTINT_ERR_NODEVICE = 6     /* no CUDA device visible: there is no CPU path         */
+} bartint_status;
+
+/* integration measures of fillProbabilityForNode, src/BARTInt.R:46-57 */
+typedef enum {
+    BARTINT_MEASURE_UNIFORM = 0,            /* :46-48  box [0,1]^d                                    */
+    BARTINT_MEASURE_GAUSSIAN_REFCOMPAT = 1, /* :49-52  exactly as written (quirk B3), box [0,1]^d     */
+    BARTINT_MEASURE_EXPONENTIAL = 2         /* :53-56  box [0,Inf)^d (:153-155)                        */
+} bartint_measure;
+
+/* flags for bartint_eval* */
+#define BARTINT_SCALED_UNITS 0x1u  /* outputs stay in dbarts scaled units (no y rescale)            */
+#define BARTINT_FORCE_WALK   0x2u  /* use the generic node-walk kernel even if the table kernel fits */
+
+int bartint_version(void);
+const char* bartint_last_error(void);
+int bartint_device_count(int* n_out);
+int bartint_set_device(int device);       /* forests/points are created on the current device */
+
+/* ---------------------------------------------------------------------------------------------
+ * Tree-state exporter.  Replaces getTree() (src/BARTInt.R:92-133) applied to every (tree, draw):
+ *   treeString <- sampler$state[[1]]@savedTrees[treeNum, sampleNum]            (:110)
+ *   treeFits   <- sampler$state[[1]]@savedTreeFits[, treeNum, sampleNum]       (:111)
+ *   dbarts:::buildTree(strsplit(gsub("\\.", "\\. ", treeString), " "))          (:118-119)
+ *   dbarts:::fillObservationsForNode / fillPlotInfoForNode  (leaf mu from fits) (:123-125)
+ *   cutPoints <- dbarts:::createCutPoints(sampler)                              (:108)
+ * tree_strings[t + s*m] is the dbarts 0.9-8 pre-order string ("0 49 .1 20 ..");
+ * tree_fits is n x m x S column-major (scaled units); x_train is n x d column-major;
+ * cut_values[cut_offsets[j] .. cut_offsets[j+1]) are variable j's ascending cut points.
+ * ------------------------------------------------------------------------------------------- */
+int bartint_forest_from_dbarts098(const char* const* tree_strings, const double* tree_fits,
+                                  const double* x_train, int64_t n, int32_t d,
+                                  const int32_t* cut_offsets, const double* cut_values,
+                                  double y_min, double y_max, int32_t m, int32_t S,
+                                  bartint_forest** out);
+
+/* Pre-flattened SoA forest (what the exporter produces; also the synthetic generator's format).
+ * split_var = -1 marks a leaf; left/right are node indices relative to the tree's first node. */
+int bartint_forest_from_soa(int32_t S, int32_t m, int32_t d, const int64_t* tree_node_offset,
+                            const int32_t* split_var, const int32_t* split_cut_idx,
+                            const int32_t* left, const int32_t* right, const double* leaf_mu,
+                            const int32_t* cut_offsets, const double* cut_values,
+                            double y_min, double y_max, bartint_forest** out);
+
+/* info[0..9] = S, m, d, n_nodes, n_leaves, max_depth, max_internal_nodes_per_tree,
+ *              table_kernel_ok (0/1), n_table_groups, table_bits */
+int bartint_forest_info(const bartint_forest* f, int64_t info[10]);
+/* read the canonical (pre-order) flattening back; arrays sized from info[3] */
+int bartint_forest_export_soa(const bartint_forest* f, int64_t* tree_node_offset, int32_t* split_var,
+                              int32_t* split_cut_idx, int32_t* left, int32_t* right, double* leaf_mu);
+void bartint_forest_destroy(bartint_forest* f);
+
+/* ---------------------------------------------------------------------------------------------
+ * Point sets.  Replaces dbarts' integer cut map of x.test inside predict()
+ * (call sites src/BARTInt.R:312,380; src/survey_design/bartMean.R:47,74):
+ *   code[i][j] = #{k : X[i,j] > cut[j][k]}    (NaN -> 0), so  "right iff x > cut"  <=>  code > cut index.
+ * X is N x d column-major with leading dimension ld >= N.
+ * ------------------------------------------------------------------------------------------- */
+int bartint_points_from_host(const bartint_forest* f, const double* X, int64_t N, int32_t d,
+                             bartint_points** out);
+int bartint_points_from_device(const bartint_forest* f, const double* dX, int64_t N, int32_t d,
+                               int64_t ld, void* stream, bartint_points** out);
+int64_t bartint_points_count(const bartint_points* p);
+int bartint_points_codes(const bartint_points* p, uint8_t* codes_out /* N x d column-major */);
+void bartint_points_destroy(bartint_points* p);
+
+/* ---------------------------------------------------------------------------------------------
+ * Ensemble evaluation + fused reductions over draws [draw_begin, draw_end).  Replaces
+ *   fValues <- predict(model, X)                      BARTInt.R:312,380; bartMean.R:47,74
+ *   colVars(fValues) * weights                        BARTInt.R:314,386; bartMean.R:50
+ *   rowMeans(pred)                                    bartMean.R:76,82
+ * without materialising the S x N matrix unless full_pred is requested.  Any output may be NULL.
+ *   draw_mean [draw_end-draw_begin]  rowMeans(predict(model, X))
+ *   point_mean[N]                    colMeans(predict(model, X))
+ *   point_var [N]                    colVars(predict(model, X)) * weights   (n-1; NaN if one draw)
+ *   full_pred [(draw_end-draw_begin) x N] column-major, rows = draws (what predict() returns)
+ * weights: NULL (=1), or weights_len == 1 (scalar), or weights_len == N.
+ * ------------------------------------------------------------------------------------------- */
+int bartint_eval_points(const bartint_forest* f, const bartint_points* p, uint32_t flags,
+                        int32_t draw_begin, int32_t draw_end,
+                        const double* weights, int64_t weights_len,
+                        double* draw_mean, double* point_mean, double* point_var, double* full_pred);
+
+/* one-shot convenience: bin + evaluate all draws */
+int bartint_eval(const bartint_forest* f, const double* X, int64_t N, int32_t d, uint32_t flags,
+                 const double* weights, int64_t weights_len,
+                 double* draw_mean, double* point_mean, double* point_var, double* full_pred);
+
+/* Device-resident variant used by the multi-GPU host layer and the benchmark: raw partials in
+ * SCALED units, written to device memory, asynchronous on `stream`.
+ *   d_draw_sum[draw_end-draw_begin]  sum_i sum_t mu            (divide by N, rescale = rowMeans)
+ *   d_point_mean[N], d_point_m2[N]   mean and sum of squared deviations over the draw range of
+ *                                    sum_t mu  (Chan-mergeable across draw shards)            */
+int bartint_eval_points_device(const bartint_forest* f, const bartint_points* p, uint32_t flags,
+                               int32_t draw_begin, int32_t draw_end,
+                               double* d_draw_sum, double* d_point_mean, double* d_point_m2,
+                               void* stream);
+
+/* Chan merge of G draw-shards' per-point moments (device pointers, shard-major [g*N + i]);
+ * then  var = M2/(n-1) * scale^2 * weight  and  mean = y0 + scale*(0.5 + mean)  with
+ * scale = y_max - y_min, y0 = y_min (or scale = 1, y0 = -0.5 for BARTINT_SCALED_UNITS).     */
+int bartint_merge_moments_device(const bartint_forest* f, uint32_t flags, int32_t G,
+                                 const int32_t* shard_draws /* host, G */,
+                                 const double* d_mean, const double* d_m2, int64_t N,
+                                 const double* d_weights, int64_t weights_len,
+                                 double* d_point_mean_out, double* d_point_var_out, void* stream);
+
+/* Leaf ordinals (leaves numbered 0..K-1 left-to-right in pre-order) reached by
+ * every point in every tree of the draw range: out[(t + (s-draw_begin)*m) * N + i].  The
+ * "bit-exact against dbarts routing" check reads this.  use_table_kernel != 0 decodes the
+ * ordinals from the table kernel's predicate bits instead of the node-walk kernel.          */
+int bartint_leaf_indices(const bartint_forest* f, const bartint_points* p,
+                         int32_t draw_begin, int32_t draw_end, int32_t use_table_kernel,
+                         int32_t* out);
+
+/* ---------------------------------------------------------------------------------------------
+ * Exact leaf-probability integral.  Replaces sampleIntegrals(model, dim, measure)
+ * (src/BARTInt.R:204-223 -> posteriorSum :177-201 -> singleTreeSum :135-175 ->
+ * fillProbabilityForNode :32-72, terminalProbability :10-30).
+ * out[s], s < n_draws_used, in SCALED units (the caller rescales, BARTInt.R:260).
+ * lo/hi: NULL for the reference's box ([0,1]^d, or [0,Inf)^d for the exponential measure).
+ * The reference only ever uses draws 1..ntree (quirk B1): pass n_draws_used = min(m, S) for
+ * bug-compatible output, S (or <= 0) for all draws.
+ * ------------------------------------------------------------------------------------------- */
+int bartint_exact_integrals(const bartint_forest* f, int32_t measure, const double* lo, const double* hi,
+                            int32_t n_draws_used, double* out);
+
+/* BARTInt.R:260-262 / 290-292:  integrals <- (integrals+0.5)*(ymax-ymin)+ymin; mean; sd (n-1).
+ * Runs on the device the forest lives on. rescaled_out may be NULL. */
+int bartint_finalize_integrals(const bartint_forest* f, const double* integrals_scaled, int32_t n,
+                               double* rescaled_out, double* mean_out, double* sd_out);
+
+/* Timing of the last bartint_eval_points* call on this forest: milliseconds spent in the dominant
+ * evaluation kernel (CUDA events on the launching stream) and number of kernels launched.
+ * Only valid after the stream has been synchronised. */
+int bartint_last_eval_profile(const bartint_forest* f, float* kernel_ms, int32_t* n_launches,
+                              int32_t* used_table_kernel);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BARTINT_H */

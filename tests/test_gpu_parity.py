@@ -1,0 +1,254 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): leaf indices and cut codes BIT-EXACT; integrals, means and variances
+within 1e-6 relative (we assert much tighter: the arithmetic is fp64 end to end, differences come only
+from summation order).
+"""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import oracle_np as onp
+from bartint_b200 import Forest, synth, api
+from bartint_testlib import kat_forest
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-6            # the north-star tolerance
+TIGHT = 1e-11          # what fp64 accumulation should actually give
+
+
+def _assert_close(got, want, tol=TIGHT, scale=None, msg=""):
+    got, want = np.asarray(got, float), np.asarray(want, float)
+    assert got.shape == want.shape, msg
+    nan = np.isnan(want)
+    assert np.array_equal(np.isnan(got), nan), msg
+    s = np.maximum(np.abs(want[~nan]), 1e-300) if scale is None else scale
+    err = np.abs(got[~nan] - want[~nan]) / s
+    assert err.size == 0 or err.max() <= tol, f"{msg}: max rel err {err.max():.3e}"
+
+
+def test_kats_cuda(kats):
+    for k in kats:
+        ff = kat_forest(k)
+        X = np.array(k["X"], dtype=float)
+        f = Forest.from_soa(ff)
+        for table in ([False, True] if f.table_kernel_ok else [False]):
+            assert np.array_equal(f.leaf_indices(X, use_table_kernel=table), np.array(k["leaf"])), (k["name"], table)
+        for walk in (False, True):
+            out = f.eval(X, want=("full_pred", "draw_mean", "point_var"), force_walk=walk)
+            _assert_close(out["full_pred"], k["predict"], 1e-15, msg=k["name"])
+            if "col_vars" in k:
+                _assert_close(out["point_var"], k["col_vars"], 1e-13, msg=k["name"])
+                _assert_close(out["draw_mean"], k["row_means"], 1e-14, msg=k["name"])
+        for measure, want in k["integrals"].items():
+            _assert_close(f.exact_integrals(measure), want, 1e-14, scale=1.0, msg=f"{k['name']} {measure}")
+        f.close()
+
+
+def test_codes_bit_exact(small_case):
+    ff, _, _, X = small_case
+    Xe = X.copy()
+    cl = ff.cut_lists()
+    Xe[0, 0] = cl[0][10]; Xe[1, 0] = np.nextafter(cl[0][10], np.inf); Xe[2, 1] = -5.0; Xe[3, 1] = 9.0
+    Xe[4, 2] = np.nan; Xe[5, 3] = cl[3][0]; Xe[6, 3] = cl[3][-1]; Xe[7, 3] = np.nextafter(cl[3][-1], np.inf)
+    Xe[8, :] = np.inf; Xe[9, :] = -np.inf
+    f = Forest.from_soa(ff)
+    pts = f.points(Xe)
+    assert np.array_equal(pts.codes().astype(np.int32), onp.bin_points(Xe, ff.cut_offsets, ff.cut_values))
+    pts.close(); f.close()
+
+
+@pytest.mark.parametrize("table", [False, True])
+def test_leaf_indices_bit_exact(small_case, table):
+    ff, _, _, X = small_case
+    f = Forest.from_soa(ff)
+    if table and not f.table_kernel_ok:
+        pytest.skip("table kernel not applicable")
+    got = f.leaf_indices(X, use_table_kernel=table)
+    want = onp.leaf_ordinals(ff, X)
+    assert got.shape == want.shape and np.array_equal(got, want)
+    f.close()
+
+
+@pytest.mark.parametrize("walk", [False, True])
+def test_predict_and_reductions(small_case, walk):
+    ff, _, _, X = small_case
+    f = Forest.from_soa(ff)
+    w = np.random.default_rng(1).random(X.shape[0])
+    out = f.eval(X, weights=w, want=("full_pred", "draw_mean", "point_mean", "point_var"), force_walk=walk)
+    P = onp.predict(ff, X)
+    _assert_close(out["full_pred"], P, 1e-13, msg="predict")
+    _assert_close(out["draw_mean"], onp.row_means(P), 1e-13, msg="rowMeans")
+    _assert_close(out["point_mean"], P.mean(axis=0), 1e-12, msg="colMeans")
+    _assert_close(out["point_var"], onp.col_vars(P) * w, 1e-10, msg="colVars*weights")
+    sc = f.eval(X, want=("full_pred",), scaled=True, force_walk=walk)
+    _assert_close(sc["full_pred"], onp.tree_sums(ff, X), 1e-13, scale=1.0, msg="scaled units")
+    f.close()
+
+
+@pytest.mark.parametrize("bits", [4, 5, 6, 7, 8])
+def test_table_bits_variants(small_case, bits, monkeypatch):
+    ff, _, _, X = small_case
+    monkeypatch.setenv("BARTINT_TABLE_BITS", str(bits))
+    f = Forest.from_soa(ff)
+    assert f.table_bits == bits
+    if not f.table_kernel_ok:
+        pytest.skip("forest does not fit")
+    out = f.eval(X, want=("draw_mean", "point_var"))
+    P = onp.predict(ff, X)
+    _assert_close(out["draw_mean"], onp.row_means(P), 1e-13)
+    _assert_close(out["point_var"], onp.col_vars(P), 1e-10)
+    assert np.array_equal(f.leaf_indices(X, use_table_kernel=True), onp.leaf_ordinals(ff, X))
+    assert f.last_eval_profile()["table_kernel"]
+    f.close()
+
+
+@pytest.mark.parametrize("kind", ["stumps", "left_chain", "right_chain", "same_var", "balanced", "edge_cuts"])
+def test_adversarial_forests(kind):
+    ff = synth.adversarial_forest(kind, 5, 7, 3, numcut=100, seed=2, depth=11)
+    rng = np.random.default_rng(6)
+    X = rng.random((700, 3))
+    X[:50] = np.round(X[:50] * 101) / 101          # many exact ties with the cut grid
+    f = Forest.from_soa(ff)
+    assert np.array_equal(f.leaf_indices(X), onp.leaf_ordinals(ff, X))
+    if f.table_kernel_ok:
+        assert np.array_equal(f.leaf_indices(X, use_table_kernel=True), onp.leaf_ordinals(ff, X))
+    P = onp.predict(ff, X)
+    for walk in (False, True):
+        out = f.eval(X, want=("draw_mean", "point_var", "full_pred"), force_walk=walk)
+        _assert_close(out["full_pred"], P, 1e-13, msg=kind)
+        _assert_close(out["draw_mean"], onp.row_means(P), 1e-13, msg=kind)
+        _assert_close(out["point_var"], onp.col_vars(P), 1e-9, scale=np.maximum(onp.col_vars(P), 1e-12), msg=kind)
+    _assert_close(f.exact_integrals("uniform"), onp.sample_integrals(ff, "uniform"), 1e-13, scale=1.0, msg=kind)
+    f.close()
+
+
+@pytest.mark.parametrize("measure", ["uniform", "gaussian", "exponential"])
+def test_exact_integrals(small_case, measure):
+    ff, *_ = small_case
+    f = Forest.from_soa(ff)
+    want = onp.sample_integrals(ff, measure)
+    _assert_close(f.exact_integrals(measure), want, 1e-12, scale=np.maximum(np.abs(want), 1e-3), msg=measure)
+    # reference quirk B1: only the first min(m, S) draws
+    n = min(ff.m, ff.S)
+    _assert_close(f.exact_integrals(measure, n_draws_used=n), want[:n], 1e-12, scale=np.maximum(np.abs(want[:n]), 1e-3))
+    res, mean, sd = f.finalize_integrals(want)
+    r0, m0, s0 = onp.finalize_integrals(want, ff.y_min, ff.y_max)
+    _assert_close(res, r0, 1e-14)
+    assert abs(mean - m0) <= 1e-13 * max(1, abs(m0)) and abs(sd - s0) <= 1e-12 * max(1e-3, abs(s0))
+    f.close()
+
+
+def test_exporter_matches_oracle_gettree(small_case):
+    ff, x_train, *_ = small_case
+    strings, fits = ff.to_dbarts_state(x_train)
+    f = Forest.from_dbarts(strings, fits, x_train, ff.cut_lists(), ff.y_min, ff.y_max)
+    got = f.export_soa()
+    want = onp.forest_from_dbarts(strings, fits, x_train, ff.cut_lists(), ff.y_min, ff.y_max)
+    for key in ("tree_offset", "var", "cut", "left", "right", "mu"):
+        assert np.array_equal(got[key], np.asarray(want[key])), key
+    f.close()
+
+
+def test_edge_shapes():
+    rng = np.random.default_rng(2)
+    x_train = rng.random((15, 1))
+    # d = 1, S = 1 (variance NaN like R), m = 1, C = 1
+    ff = synth.prior_forest(3, 1, 1, x_train)
+    f = Forest.from_soa(ff)
+    X = rng.random((1, 1))
+    out = f.eval(X, want=("draw_mean", "point_mean", "point_var", "full_pred"))
+    P = onp.predict(ff, X)
+    _assert_close(out["full_pred"], P, 1e-14)
+    assert math.isnan(out["point_var"][0])
+    # empty point set: rowMeans of a 0-column matrix is NaN
+    out = f.eval(np.zeros((0, 1)), want=("draw_mean",))
+    assert np.isnan(out["draw_mean"]).all()
+    f.close()
+    # ragged: N not a multiple of anything, draw sub-range
+    ff = synth.prior_forest(4, 9, 5, rng.random((20, 2)))
+    f = Forest.from_soa(ff)
+    X = rng.random((2049 * 2 + 1, 2))
+    P = onp.predict(ff, X)
+    for walk in (False, True):
+        out = f.eval(X, want=("draw_mean", "point_var"), draws=(2, 7), force_walk=walk)
+        _assert_close(out["draw_mean"], onp.row_means(P[2:7]), 1e-13)
+        _assert_close(out["point_var"], onp.col_vars(P[2:7]), 1e-10, scale=np.maximum(onp.col_vars(P[2:7]), 1e-12))
+    f.close()
+
+
+def test_deep_tree_inside_table_kernel():
+    """A tree with more than NB internal nodes becomes a WALK record inside the table kernel."""
+    rng = np.random.default_rng(3)
+    cut_lists = [np.linspace(0, 1, 102)[1:-1]] * 2
+    deep = synth.adversarial_forest("left_chain", 1, 1, 2, seed=5, depth=14)
+    a = synth.prior_forest(6, 4, 6, rng.random((25, 2)), cut_lists=cut_lists)
+    # splice the deep tree in as tree 2 of draw 1
+    trees = []
+    for k in range(a.S * a.m):
+        src, kk = (deep, 0) if k == 1 * a.m + 2 else (a, k)
+        lo, hi = src.tree_offset[kk], src.tree_offset[kk + 1]
+        trees.append((src.var[lo:hi], src.cut[lo:hi], src.left[lo:hi], src.right[lo:hi], src.mu[lo:hi]))
+    off = np.concatenate([[0], np.cumsum([len(t[0]) for t in trees])])
+    ff = synth.FlatForest(a.S, a.m, 2, off, *(np.concatenate([t[i] for t in trees]) for i in range(5)),
+                          a.cut_offsets, a.cut_values, 0.0, 2.0)
+    f = Forest.from_soa(ff)
+    assert f.table_kernel_ok and f.max_internal > f.table_bits
+    X = rng.random((5000, 2))
+    P = onp.predict(ff, X)
+    out = f.eval(X, want=("draw_mean", "point_var", "full_pred"))
+    assert f.last_eval_profile()["table_kernel"]
+    _assert_close(out["full_pred"], P, 1e-13)
+    _assert_close(out["draw_mean"], onp.row_means(P), 1e-13)
+    assert np.array_equal(f.leaf_indices(X, use_table_kernel=True), onp.leaf_ordinals(ff, X))
+    f.close()
+
+
+def test_api_drop_in_semantics(small_case):
+    """sampleIntegrals / predict / colVars*weights / rowMeans through the R-interface mirror."""
+    ff, x_train, y_train, X = small_case
+    model = api.model_from_flat(ff, x_train, y_train)
+    got = api.sampleIntegrals(model, ff.d, "uniform")                 # bug-compatible: first min(m, S) draws
+    want = onp.sample_integrals(ff, "uniform", n_draws_used=min(ff.m, ff.S))
+    _assert_close(got, want, 1e-12, scale=np.maximum(np.abs(want), 1e-3))
+    Xc = X[:100]
+    P = onp.predict(ff, Xc)
+    _assert_close(api.predict(model, Xc), P, 1e-13)
+    _assert_close(api.bartint_candidate_var(model, Xc, 1.0), onp.col_vars(P), 1e-10)
+    _assert_close(api.bartint_draw_means(model, Xc), onp.row_means(P), 1e-13)
+    model.close()
+
+
+def test_sequential_design_loop_runs():
+    rng = np.random.default_rng(0)
+    trainX = rng.random((20, 1))
+    out = api.mainBARTInt(1, 2, lambda x: np.exp(-np.abs(x - 0.5).sum(axis=1)), trainX,
+                          np.exp(-np.abs(trainX - 0.5).sum(axis=1)), sequential=True, measure="uniform",
+                          bart=lambda X, y, **kw: api.synthetic_bart(X, y, **{**kw, "ndpost": kw["ndpost"] // 50}))
+    assert out["meanValueBART"].shape == (2,) and np.isfinite(out["meanValueBART"]).all()
+    assert out["trainData"].shape == (21, 2)
+    out["model"].close()
+
+
+def test_full_size_properties_cfg2_shape():
+    """BASELINE cfg-2-shaped run at reduced S (size-independent properties): linearity of the per-draw
+    sum in the point set, MC mean within 5 sigma of the exact integral, table == walk kernel."""
+    cfg = synth.CONFIGS[2]
+    x_train, y_train = synth.make_design(2)
+    ff = synth.prior_forest(2002, 64, cfg["m"], x_train, y_train)
+    f = Forest.from_soa(ff)
+    X = synth.make_points(2, 200_000)
+    a = f.eval(X, want=("draw_mean",), scaled=True)["draw_mean"]
+    b = f.eval(X, want=("draw_mean",), scaled=True, force_walk=True)["draw_mean"]
+    _assert_close(a, b, 1e-12, scale=np.maximum(np.abs(b), 1e-3), msg="table vs walk")
+    h1 = f.eval(X[:120_001], want=("draw_mean",), scaled=True)["draw_mean"]
+    h2 = f.eval(X[120_001:], want=("draw_mean",), scaled=True)["draw_mean"]
+    _assert_close((h1 * 120_001 + h2 * (200_000 - 120_001)) / 200_000, a, 1e-12, scale=np.maximum(np.abs(a), 1e-3),
+                  msg="additivity over point shards")
+    exact = f.exact_integrals("uniform")
+    # the cut grid spans the training range, a subset of [0,1]^d, so MC over U[0,1]^d estimates the same integral
+    sd = np.sqrt(f.eval(X[:20000], want=("full_pred",), scaled=True)["full_pred"].var(axis=1, ddof=1) / 200_000)
+    assert (np.abs(a - exact) <= 6 * sd + 1e-9).all()
+    f.close()
