@@ -80,6 +80,8 @@ extern "C" {
 
 int bartint_version(void) { return 100; }
 
+int64_t bartint_kernel_launch_count(void) { return (int64_t)bartint::launch_count(); }
+
 const char* bartint_last_error(void) { return bartint::get_error(); }
 
 int bartint_device_count(int* n_out) {
@@ -176,7 +178,7 @@ void bartint_forest_destroy(bartint_forest* f) {
 }
 
 // ------------------------------------------------------------------------------------------------------------
-static int make_points(const bartint_forest* f, int64_t N, int32_t d, bartint_points** out) {
+static int make_points(const bartint_forest* f, int64_t N, int32_t d, cudaStream_t st, bartint_points** out) {
     BI_REQUIRE(f != nullptr && out != nullptr, BARTINT_ERR_ARG, "NULL argument");
     *out = nullptr;
     BI_REQUIRE(N >= 0, BARTINT_ERR_ARG, "N must be >= 0");
@@ -186,18 +188,20 @@ static int make_points(const bartint_forest* f, int64_t N, int32_t d, bartint_po
     p->device = f->device; p->N = N; p->d = d;
     p->Npad = ((N + TK_TILE - 1) / TK_TILE) * TK_TILE;
     if (p->Npad == 0) p->Npad = TK_TILE;
-    cudaError_t e = cudaMalloc((void**)&p->codes, (size_t)std::max(d, 1) * (size_t)p->Npad);
-    if (e != cudaSuccess) { delete p; return cuda_fail(e, "cudaMalloc(codes)", __FILE__, __LINE__); }
+    p->stream = st;
+    DeviceGuard g(f->device);
+    cudaError_t e = cudaMallocAsync((void**)&p->codes, (size_t)std::max(d, 1) * (size_t)p->Npad, st);
+    if (e != cudaSuccess) { delete p; return cuda_fail(e, "cudaMallocAsync(codes)", __FILE__, __LINE__); }
     *out = p;
     return BARTINT_OK;
 }
 
 int bartint_points_from_device(const bartint_forest* f, const double* dX, int64_t N, int32_t d, int64_t ld,
                                void* stream, bartint_points** out) {
-    int rc = make_points(f, N, d, out);
-    if (rc) return rc;
     BI_REQUIRE(N * d == 0 || dX != nullptr, BARTINT_ERR_ARG, "X is NULL");
     BI_REQUIRE(ld >= N, BARTINT_ERR_ARG, "leading dimension smaller than N");
+    int rc = make_points(f, N, d, (cudaStream_t)stream, out);
+    if (rc) return rc;
     DeviceGuard g(f->device);
     rc = launch_bin_points(dX, ld, N, d, f->dev.cut_off, f->dev.cut_val, f->max_cuts, (*out)->codes, (*out)->Npad,
                            (cudaStream_t)stream);
@@ -240,7 +244,7 @@ void bartint_points_destroy(bartint_points* p) {
     if (p == nullptr) return;
     {
         DeviceGuard g(p->device);
-        cudaFree(p->codes);
+        if (p->codes) cudaFreeAsync(p->codes, p->stream);
         (void)cudaGetLastError();
     }
     delete p;
@@ -434,6 +438,43 @@ int bartint_leaf_indices(const bartint_forest* f, const bartint_points* p, int32
         if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemcpy(leaf)", __FILE__, __LINE__);
     }
     cudaFree(d_leaf);
+    return rc;
+}
+
+int bartint_exact_integrals_device(const bartint_forest* f, int32_t measure, const double* lo, const double* hi,
+                                   int32_t n_draws_used, double* d_out, double* d_rescaled, double* d_mean_sd,
+                                   void* stream) {
+    BI_REQUIRE(f != nullptr, BARTINT_ERR_ARG, "forest is NULL");
+    BI_REQUIRE(measure >= 0 && measure <= 2, BARTINT_ERR_ARG, "unknown measure %d", measure);
+    BI_REQUIRE((lo == nullptr) == (hi == nullptr), BARTINT_ERR_ARG, "lo and hi must both be given or both be NULL");
+    const int n_draws = (n_draws_used <= 0 || n_draws_used > f->S) ? f->S : n_draws_used;
+    if (n_draws == 0) return BARTINT_OK;
+    BI_REQUIRE(d_out != nullptr, BARTINT_ERR_ARG, "d_out is NULL");
+    DeviceGuard g(f->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    double* d_box = nullptr;
+    if (lo != nullptr && f->d > 0) {
+        BI_CUDA(cudaMallocAsync((void**)&d_box, sizeof(double) * 2 * (size_t)f->d, st));
+        BI_CUDA(cudaMemcpyAsync(d_box, lo, sizeof(double) * (size_t)f->d, cudaMemcpyHostToDevice, st));
+        BI_CUDA(cudaMemcpyAsync(d_box + f->d, hi, sizeof(double) * (size_t)f->d, cudaMemcpyHostToDevice, st));
+    }
+    int rc = launch_exact_integrals(f, measure, d_box, d_box ? d_box + f->d : nullptr, n_draws, d_out, st);
+    if (d_box) cudaFreeAsync(d_box, st);
+    if (rc == BARTINT_OK && d_mean_sd != nullptr)
+        rc = launch_finalize_integrals(d_out, n_draws, f->y_min, f->y_max, d_rescaled, d_mean_sd, st);
+    return rc;
+}
+
+int bartint_finalize_draws_device(const bartint_forest* f, uint32_t flags, const double* d_draw_sum, int32_t ndraws,
+                                  int64_t n_points, double* d_draw_mean, double* d_mean_var, void* stream) {
+    BI_REQUIRE(f != nullptr && ndraws >= 0, BARTINT_ERR_ARG, "bad arguments");
+    if (ndraws == 0) return BARTINT_OK;
+    BI_REQUIRE(d_draw_sum != nullptr && d_draw_mean != nullptr, BARTINT_ERR_ARG, "NULL device pointer");
+    DeviceGuard g(f->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int scaled = (flags & BARTINT_SCALED_UNITS) ? 1 : 0;
+    int rc = launch_finalize_draws(d_draw_sum, ndraws, n_points, f->y_max - f->y_min, f->y_min, scaled, d_draw_mean, st);
+    if (rc == BARTINT_OK && d_mean_var != nullptr) rc = launch_draw_summary(d_draw_mean, ndraws, d_mean_var, st);
     return rc;
 }
 

@@ -13,6 +13,8 @@ namespace bartint {
 // error plumbing: no exceptions cross the C ABI; status code + thread-local message
 // ---------------------------------------------------------------------------------------------
 void set_error(const char* fmt, ...);
+void count_launch(int n = 1);          // every kernel launch of the library goes through this counter
+long long launch_count();
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 
 #define BI_CUDA(call)                                                            \
@@ -54,7 +56,8 @@ constexpr uint32_t TK_FLAG_END_DRAW = 1u;
 // of type WALK:  [ 16 B header | n_nodes x walk-node (8 B) | n_leaves doubles ]  and is walked per point inside the
 // same kernel (rare; the prior puts ~1e-4 of the trees there).  Header: {flags, first tree, n_trees | n_nodes, 0}.
 constexpr uint32_t TK_FLAG_WALK = 2u;
-__host__ __device__ constexpr int tk_rec_bytes(int nb) { return TK_HDR + nb * 8 + (8 << nb); }
+__host__ __device__ constexpr int tk_tbl_off(int nb) { return TK_HDR + ((nb * 8 + 15) & ~15); }   // 16 B aligned
+__host__ __device__ constexpr int tk_rec_bytes(int nb) { return tk_tbl_off(nb) + (8 << nb); }       // multiple of 16
 
 struct DeviceForest {
     uint2* nodes = nullptr;            // n_nodes
@@ -101,6 +104,7 @@ struct bartint_points {
     int device = 0;
     int64_t N = 0, Npad = 0;
     int32_t d = 0;
+    cudaStream_t stream = nullptr;   // stream the code buffer was allocated on (stream-ordered allocator)
     uint8_t* codes = nullptr;  // feature-major: codes[f * Npad + i], zero padded to Npad (multiple of TK_TILE)
 };
 
@@ -148,6 +152,7 @@ int launch_finalize_draws(const double* draw_sum, int ndraws, int64_t N, double 
                           double* out, cudaStream_t st);
 int launch_exact_integrals(const bartint_forest* f, int measure, const double* d_lo, const double* d_hi,
                            int n_draws, double* d_out, cudaStream_t st);
+int launch_draw_summary(const double* d_draw_mean, int ndraws, double* d_mean_var, cudaStream_t st);
 int launch_finalize_integrals(const double* d_in, int n, double y_min, double y_max, double* d_rescaled,
                               double* d_mean_sd, cudaStream_t st);
 

@@ -6,6 +6,7 @@
 //   :118-119 tokenisation gsub("\\.", "\\. ") + strsplit(" ") feeding dbarts:::buildTree
 //   :122-125 route the training rows, leaf mu = fit of a training row in that leaf
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -26,6 +27,10 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 const char* get_error() { return g_err; }
+
+static std::atomic<long long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
     set_error("CUDA error %d (%s) at %s:%d in %s", (int)e, cudaGetErrorString(e), file, line, what);

@@ -164,16 +164,11 @@ int launch_eval_walk(const bartint_forest* f, const bartint_points* p, const Eva
                      double* pt_mean, double* pt_m2, int32_t* leaf_out, double* full_pred, double fp_scale,
                      double fp_y0, int fp_scaled, cudaStream_t st) {
     dim3 grid((unsigned)plan.n_tiles, (unsigned)plan.n_chunks);
-    if (pt_mean != nullptr)
-        eval_walk_kernel<true><<<grid, WK_THREADS, 0, st>>>(
-            f->dev.nodes, f->dev.tree_off, f->dev.tree_leaf_off, f->dev.leaf_mu, p->codes, p->Npad, p->N, f->m,
-            plan.draw_begin, plan.draw_end, plan.chunk_draws, draw_part, pt_mean, pt_m2, leaf_out, full_pred, fp_scale,
-            fp_y0, fp_scaled);
-    else
-        eval_walk_kernel<false><<<grid, WK_THREADS, 0, st>>>(
-            f->dev.nodes, f->dev.tree_off, f->dev.tree_leaf_off, f->dev.leaf_mu, p->codes, p->Npad, p->N, f->m,
-            plan.draw_begin, plan.draw_end, plan.chunk_draws, draw_part, pt_mean, pt_m2, leaf_out, full_pred, fp_scale,
-            fp_y0, fp_scaled);
+    auto kern = pt_mean != nullptr ? eval_walk_kernel<true> : eval_walk_kernel<false>;
+    kern<<<grid, WK_THREADS, 0, st>>>(f->dev.nodes, f->dev.tree_off, f->dev.tree_leaf_off, f->dev.leaf_mu, p->codes,
+                                      p->Npad, p->N, f->m, plan.draw_begin, plan.draw_end, plan.chunk_draws, draw_part,
+                                      pt_mean, pt_m2, leaf_out, full_pred, fp_scale, fp_y0, fp_scaled);
+    count_launch();
     BI_CUDA(cudaGetLastError());
     return BARTINT_OK;
 }
@@ -287,7 +282,7 @@ __global__ void __launch_bounds__(TK_THREADS, 2) eval_table_kernel(const TablePa
             const unsigned char* rec = stage + g * REC;
             const uint32_t flags = *reinterpret_cast<const uint32_t*>(rec);
             const uint2* __restrict__ desc = reinterpret_cast<const uint2*>(rec + TK_HDR);
-            const double* __restrict__ tbl = reinterpret_cast<const double*>(rec + TK_HDR + NB * 8);
+            const double* __restrict__ tbl = reinterpret_cast<const double*>(rec + tk_tbl_off(NB));
             if (flags & TK_FLAG_WALK) {
                 // rare: a tree too deep for NB predicate bits, walked per point from its record in shared memory
                 const uint2* __restrict__ wn = reinterpret_cast<const uint2*>(rec + TK_HDR);
@@ -397,6 +392,7 @@ static int launch_table_inst(const TableParams& prm, dim3 grid, cudaStream_t st)
         configured_smem = 227 * 1024;
     }
     kern<<<grid, TK_THREADS, smem, st>>>(prm);
+    count_launch();
     BI_CUDA(cudaGetLastError());
     return BARTINT_OK;
 }
@@ -508,6 +504,7 @@ int launch_table_leaf(const bartint_forest* f, const bartint_points* p, int32_t 
     table_leaf_kernel<<<grid, 256, 0, st>>>(f->dev.group_rec, f->nb, f->dev.draw_group_off, f->dev.nodes,
                                             f->dev.tree_off, f->dev.node_bit, p->codes, p->Npad, p->N, f->m,
                                             draw_begin, draw_end, leaf_out);
+    count_launch();
     BI_CUDA(cudaGetLastError());
     return BARTINT_OK;
 }

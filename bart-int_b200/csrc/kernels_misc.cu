@@ -68,6 +68,7 @@ int launch_bin_points(const double* dX, int64_t ld, int64_t N, int32_t d, const 
     if (bx < 1) bx = 1;
     dim3 grid((unsigned)bx, (unsigned)d);
     bin_points_kernel<<<grid, 256, 0, st>>>(dX, ld, N, d_cut_off, d_cut_val, reinterpret_cast<uint32_t*>(codes), quads);
+    count_launch();
     BI_CUDA(cudaGetLastError());
     return BARTINT_OK;
 }
@@ -108,7 +109,7 @@ __global__ void build_tables_kernel(const uint2* __restrict__ nodes, const int32
         }
         sum += leaf_mu[tree_leaf_off[k] + (int32_t)r.y];
     }
-    reinterpret_cast<double*>(rec + TK_HDR + nb * 8)[idx] = sum;
+    reinterpret_cast<double*>(rec + tk_tbl_off(nb))[idx] = sum;
     if ((int)idx < nb) reinterpret_cast<uint2*>(rec + TK_HDR)[idx] = desc[g * nb + idx];
     if (idx == 0) {
         uint4 h = make_uint4(flags, (uint32_t)tb, (uint32_t)(te - tb), 0u);
@@ -121,6 +122,7 @@ int launch_build_tables(const bartint_forest* f, const uint2* d_desc, const uint
     build_tables_kernel<<<(unsigned)f->n_groups, 1u << f->nb, 0, st>>>(
         f->dev.nodes, f->dev.tree_off, f->dev.tree_leaf_off, f->dev.leaf_mu, f->dev.node_bit, f->dev.group_tree_off,
         d_desc, d_hdr, f->nb, f->dev.group_rec);
+    count_launch();
     BI_CUDA(cudaGetLastError());
     return BARTINT_OK;
 }
@@ -140,6 +142,7 @@ __global__ void reduce_draw_parts_kernel(const double* __restrict__ part, int n_
 int launch_reduce_draw_parts(const double* draw_part, int n_tiles, int ndraws, double* draw_sum, cudaStream_t st) {
     if (ndraws == 0) return BARTINT_OK;
     reduce_draw_parts_kernel<<<(ndraws + 127) / 128, 128, 0, st>>>(draw_part, n_tiles, ndraws, draw_sum);
+    count_launch();
     BI_CUDA(cudaGetLastError());
     return BARTINT_OK;
 }
@@ -174,6 +177,7 @@ int launch_merge_point_parts(const double* pt_mean, const double* pt_m2, int n_c
     if (N == 0) return BARTINT_OK;
     merge_point_parts_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(pt_mean, pt_m2, n_chunks, chunk_draws,
                                                                           ndraws, N, mean_out, m2_out);
+    count_launch();
     BI_CUDA(cudaGetLastError());
     return BARTINT_OK;
 }
@@ -202,6 +206,7 @@ int launch_merge_shards(const double* mean, const double* m2, int G, const int32
     if (N == 0) return BARTINT_OK;
     merge_shards_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(mean, m2, G, d_counts, N, scale, y0, scaled, w,
                                                                      wlen, mean_out, var_out);
+    count_launch();
     BI_CUDA(cudaGetLastError());
     return BARTINT_OK;
 }
@@ -219,6 +224,7 @@ int launch_finalize_draws(const double* draw_sum, int ndraws, int64_t N, double 
                           double* out, cudaStream_t st) {
     if (ndraws == 0) return BARTINT_OK;
     finalize_draws_kernel<<<(ndraws + 127) / 128, 128, 0, st>>>(draw_sum, ndraws, (double)N, scale, y0, scaled, out);
+    count_launch();
     BI_CUDA(cudaGetLastError());
     return BARTINT_OK;
 }
@@ -261,7 +267,10 @@ __global__ void __launch_bounds__(128) exact_tree_integral_kernel(
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     double* blo = box + tid;                       // blo[j * nthreads], bhi = blo + d * nthreads
     double* bhi = box + (int64_t)d * nthreads + tid;
-    for (int j = 0; j < d; ++j) { blo[(int64_t)j * nthreads] = lo0[j]; bhi[(int64_t)j * nthreads] = hi0[j]; }
+    for (int j = 0; j < d; ++j) {   // default box: [0,1]^d, or [0,Inf)^d for the exponential measure (BARTInt.R:151-155)
+        blo[(int64_t)j * nthreads] = lo0 ? lo0[j] : 0.0;
+        bhi[(int64_t)j * nthreads] = hi0 ? hi0[j] : (measure == BARTINT_MEASURE_EXPONENTIAL ? INFINITY : 1.0);
+    }
 
     int32_t st_var[K2_MAX_DEPTH];
     int32_t st_node[K2_MAX_DEPTH];
@@ -343,8 +352,10 @@ int launch_exact_integrals(const bartint_forest* f, int measure, const double* d
     exact_tree_integral_kernel<<<blocks, 128, 0, st>>>(f->dev.nodes, f->dev.tree_off, f->dev.tree_leaf_off,
                                                        f->dev.leaf_mu, f->dev.cut_off, f->dev.cut_val, f->d, n_trees,
                                                        measure, d_lo, d_hi, box, tree_int);
+    count_launch();
     BI_CUDA(cudaGetLastError());
     draw_integral_kernel<<<(n_draws + 127) / 128, 128, 0, st>>>(tree_int, f->m, n_draws, d_out);
+    count_launch();
     BI_CUDA(cudaGetLastError());
     BI_CUDA(cudaFreeAsync(box, st));
     BI_CUDA(cudaFreeAsync(tree_int, st));
@@ -391,9 +402,45 @@ __global__ void __launch_bounds__(256) finalize_integrals_kernel(const double* _
     }
 }
 
+// bartMean.R:80,82: mean(pred) (= mean of the row means, all rows have equal length) and the variance of the row means
+__global__ void __launch_bounds__(256) draw_summary_kernel(const double* __restrict__ rm, int n, double* __restrict__ out) {
+    __shared__ double s_red[256];
+    __shared__ double s_mean;
+    const int t = threadIdx.x;
+    double acc = 0.0;
+    for (int i = t; i < n; i += 256) acc += rm[i];
+    s_red[t] = acc;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if (t < w) s_red[t] += s_red[t + w];
+        __syncthreads();
+    }
+    if (t == 0) s_mean = s_red[0] / (double)n;
+    __syncthreads();
+    const double mean = s_mean;
+    acc = 0.0;
+    for (int i = t; i < n; i += 256) acc += (rm[i] - mean) * (rm[i] - mean);
+    __syncthreads();
+    s_red[t] = acc;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if (t < w) s_red[t] += s_red[t + w];
+        __syncthreads();
+    }
+    if (t == 0) { out[0] = mean; out[1] = s_red[0] / (double)(n - 1); }
+}
+
+int launch_draw_summary(const double* d_draw_mean, int ndraws, double* d_mean_var, cudaStream_t st) {
+    draw_summary_kernel<<<1, 256, 0, st>>>(d_draw_mean, ndraws, d_mean_var);
+    count_launch();
+    BI_CUDA(cudaGetLastError());
+    return BARTINT_OK;
+}
+
 int launch_finalize_integrals(const double* d_in, int n, double y_min, double y_max, double* d_rescaled,
                               double* d_mean_sd, cudaStream_t st) {
     finalize_integrals_kernel<<<1, 256, 0, st>>>(d_in, n, y_min, y_max, d_rescaled, d_mean_sd);
+    count_launch();
     BI_CUDA(cudaGetLastError());
     return BARTINT_OK;
 }

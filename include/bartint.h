@@ -136,6 +136,13 @@ int bartint_eval_points_device(const bartint_forest* f, const bartint_points* p,
                                double* d_draw_sum, double* d_point_mean, double* d_point_m2,
                                void* stream);
 
+/* rowMeans + the survey estimator's summary (bartMean.R:76,80,82), asynchronous, device pointers:
+ *   d_draw_mean[ndraws] = rowMeans(pred) = (ymax-ymin)*(d_draw_sum/n_points + 0.5) + ymin
+ *   d_mean_var[2]       = { mean(pred), sum((rowMeans - mean)^2)/(ndraws-1) }   (a VARIANCE, quirk B6)
+ * d_draw_sum holds sum_i sum_t mu over n_points points (e.g. the all-reduced sums of all point shards). */
+int bartint_finalize_draws_device(const bartint_forest* f, uint32_t flags, const double* d_draw_sum, int32_t ndraws,
+                                  int64_t n_points, double* d_draw_mean, double* d_mean_var, void* stream);
+
 /* Chan merge of G draw-shards' per-point moments (device pointers, shard-major [g*N + i]);
  * then  var = M2/(n-1) * scale^2 * weight  and  mean = y0 + scale*(0.5 + mean)  with
  * scale = y_max - y_min, y0 = y_min (or scale = 1, y0 = -0.5 for BARTINT_SCALED_UNITS).     */
@@ -165,6 +172,13 @@ int bartint_leaf_indices(const bartint_forest* f, const bartint_points* p,
 int bartint_exact_integrals(const bartint_forest* f, int32_t measure, const double* lo, const double* hi,
                             int32_t n_draws_used, double* out);
 
+/* Asynchronous device variant: d_out[n_draws] scaled integrals; if d_rescaled / d_mean_sd are non-NULL the
+ * finalisation of BARTInt.R:260-262 is fused behind it (d_rescaled[n_draws], d_mean_sd[2] = {mean, sd}).
+ * lo/hi are HOST pointers (d doubles each) or NULL for the reference's box. */
+int bartint_exact_integrals_device(const bartint_forest* f, int32_t measure, const double* lo, const double* hi,
+                                   int32_t n_draws_used, double* d_out, double* d_rescaled, double* d_mean_sd,
+                                   void* stream);
+
 /* BARTInt.R:260-262 / 290-292:  integrals <- (integrals+0.5)*(ymax-ymin)+ymin; mean; sd (n-1).
  * Runs on the device the forest lives on. rescaled_out may be NULL. */
 int bartint_finalize_integrals(const bartint_forest* f, const double* integrals_scaled, int32_t n,
@@ -175,6 +189,10 @@ int bartint_finalize_integrals(const bartint_forest* f, const double* integrals_
  * Only valid after the stream has been synchronised. */
 int bartint_last_eval_profile(const bartint_forest* f, float* kernel_ms, int32_t* n_launches,
                               int32_t* used_table_kernel);
+
+/* Number of CUDA kernels this library has launched in this process so far (all devices, all streams).
+ * bench.py reports the difference across its timed region as "gpu_launches". */
+int64_t bartint_kernel_launch_count(void);
 
 #ifdef __cplusplus
 }
