@@ -97,26 +97,26 @@ class FlatForest:
         the fit of training row i under tree (t, s) is the mu of the leaf the row falls in."""
         x_train = np.asarray(x_train, np.float64)
         n = x_train.shape[0]
+        K = self.n_trees
         strings = np.empty((self.m, self.S), dtype=object)
-        fits = np.zeros((n, self.m, self.S))
-        cl = self.cut_lists()
-        rows = np.arange(n)
-        for s in range(self.S):
-            for t in range(self.m):
-                k = t + s * self.m
-                strings[t, s] = self.tree_string(k)
-                a, b = int(self.tree_offset[k]), int(self.tree_offset[k + 1])
-                var, cut, left, right = self.var[a:b], self.cut[a:b], self.left[a:b], self.right[a:b]
-                node = np.zeros(n, np.int64)
-                for _ in range(b - a):
-                    v = var[node]
-                    internal = v >= 0
-                    if not internal.any():
-                        break
-                    vi = np.where(internal, v, 0)
-                    cv = np.array([cl[p][q] for p, q in zip(vi, np.where(internal, cut[node], 0))])
-                    node = np.where(internal, np.where(x_train[rows, vi] > cv, right[node], left[node]), node)
-                fits[:, t, s] = self.mu[a + node]
+        for k in range(K):
+            strings[k % self.m, k // self.m] = self.tree_string(k)
+        # route every training row through every tree at once on the integer cut map (x > cut  <=>  code > cut index)
+        codes = np.zeros((n, max(self.d, 1)), np.int32)
+        for j, cuts in enumerate(self.cut_lists()):
+            codes[:, j] = np.where(np.isnan(x_train[:, j]), 0, np.searchsorted(cuts, x_train[:, j], side="left"))
+        base = self.tree_offset[:-1, None]
+        node = np.broadcast_to(base, (K, n)).copy()
+        rows = np.arange(n)[None, :]
+        while True:
+            v = self.var[node]
+            internal = v >= 0
+            if not internal.any():
+                break
+            go_right = codes[rows, np.where(internal, v, 0)] > self.cut[node]
+            nxt = np.where(go_right, self.right[node], self.left[node]) + base
+            node = np.where(internal, nxt, node)
+        fits = self.mu[node].reshape(self.S, self.m, n).transpose(2, 1, 0).copy()
         return strings, fits
 
 
@@ -276,6 +276,20 @@ class Forest:
             self._h, _lib.BARTINT_SCALED_UNITS if scaled else 0, sd.size, _p(sd, C.c_int32), C.c_void_p(d_mean),
             C.c_void_p(d_m2), N, C.c_void_p(d_weights or None), weights_len, C.c_void_p(d_mean_out or None),
             C.c_void_p(d_var_out or None), C.c_void_p(stream)))
+
+    def finalize_draws_device(self, d_draw_sum: int, ndraws: int, n_points: int, d_draw_mean: int, d_mean_var: int = 0,
+                              scaled=False, stream: int = 0) -> None:
+        """rowMeans + {mean(pred), variance of row means} (bartMean.R:76,80,82) from per-draw sums, on device."""
+        _check(_lib.load().bartint_finalize_draws_device(
+            self._h, _lib.BARTINT_SCALED_UNITS if scaled else 0, C.c_void_p(d_draw_sum), ndraws, n_points,
+            C.c_void_p(d_draw_mean), C.c_void_p(d_mean_var or None), C.c_void_p(stream)))
+
+    def exact_integrals_device(self, d_out: int, measure="uniform", n_draws_used=None, d_rescaled: int = 0,
+                               d_mean_sd: int = 0, stream: int = 0) -> None:
+        """sampleIntegrals (+ the BARTInt.R:260-262 finalisation when d_mean_sd is given), asynchronous."""
+        _check(_lib.load().bartint_exact_integrals_device(
+            self._h, _lib.MEASURES[measure], None, None, int(n_draws_used or 0), C.c_void_p(d_out),
+            C.c_void_p(d_rescaled or None), C.c_void_p(d_mean_sd or None), C.c_void_p(stream)))
 
     def last_eval_profile(self) -> dict:
         ms, nl, tk = C.c_float(), C.c_int32(), C.c_int32()

@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""Benchmark of the BART-Int posterior-evaluation hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+Workload (config.workload): BASELINE.json configs[1] -- Genz Gaussian-peak d=10, 50 trees x 1000 draws,
+1e6 uniform MC points (+ the C=100 sequential-design candidates).  One *step* is one sequential-design
+pass of the hot path over a fresh posterior that is already resident in HBM:
+    exact leaf-volume integrals of all S draws + their mean/sd        (sampleIntegrals, BARTInt.R:259-262)
+    candidates: bin -> ensemble evaluation -> colVars * weights       (BARTInt.R:312-314)
+    MC points : bin -> ensemble evaluation -> rowMeans -> mean/var    (bartMean.R:74-82 estimator)
+metric = tree-evals/s = S*m*(N + C) per step / device time.  N > 1 ranks: weak scaling, the MC points are
+sharded (1e6 per GPU, all-gathered per-draw sums) and the candidate evaluation is sharded over draws
+(all-gathered moments, Chan merge).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "tree-evals/sec (draws x trees x points)"
+UNIT = "tree-evals/s"
+CFG = 2
+
+
+def workload(args):
+    from bartint_b200 import synth
+    c = dict(synth.CONFIGS[CFG])
+    if args.points:
+        c["N"] = args.points
+    if args.draws:
+        c["S"] = args.draws
+    return c
+
+
+def config_json(c, extra=None):
+    out = {"workload": c["name"], "d": c["d"], "trees": c["m"], "draws": c["S"], "mc_points_per_gpu": c["N"],
+           "candidates": c["C"], "measure": c["measure"], "cutpoints_per_variable": 100,
+           "l2": "flushed between steps (512 MiB memset outside the per-step event pairs)"}
+    out.update(extra or {})
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU implementation of the path = the C restatement (oracle port),
+# all host threads, a bounded sample of the same workload per step
+# ---------------------------------------------------------------------------------------------
+def cpu_sample_run(ff, X, nthreads, budget_s, oc):
+    """Time the CPU port on as many of X's rows as fit the time budget.  Returns (evals/s, rows used, seconds)."""
+    probe = min(len(X), 2000)
+    t0 = time.perf_counter()
+    oc.predict_reduce(ff, X[:probe], nthreads=nthreads, want=("draw_mean",))
+    rate = ff.S * ff.m * probe / max(time.perf_counter() - t0, 1e-9)
+    rows = int(min(len(X), max(probe, budget_s * rate / (ff.S * ff.m))))
+    t0 = time.perf_counter()
+    oc.predict_reduce(ff, X[:rows], nthreads=nthreads, want=("draw_mean",))
+    dt = time.perf_counter() - t0
+    return ff.S * ff.m * rows / dt, rows, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from bartint_b200 import synth
+    from oracle import oracle_c as oc
+    c = workload(args)
+    x_train, y_train = synth.make_design(CFG)
+    ff = synth.prior_forest(2000, c["S"], c["m"], x_train, y_train)
+    nthreads = oc.max_threads()
+    rows = min(c["N"], 20000 * max(1, nthreads // 4))
+    X = synth.make_points(CFG, rows)
+    Xc = synth.make_points(CFG, c["C"], seed=777)
+
+    def step():
+        oc.exact_integrals(ff, "uniform", nthreads=nthreads)
+        oc.predict_reduce(ff, Xc, nthreads=nthreads, want=("point_var",))
+        oc.predict_reduce(ff, X, nthreads=nthreads, want=("draw_mean",))
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    evals = ff.S * ff.m * (rows + c["C"]) * args.steps
+    value = evals / dt
+    sample = f"{rows} of {c['N']} MC points + {c['C']} candidates, all {c['S']} draws, per step"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_json(c, {"reference_note": "R/dbarts cannot run here (no R); this is the C restatement of "
+                                  "the dbarts predict loop + sampleIntegrals arithmetic (oracle/oracle_c.c), OpenMP over draws"}),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthreads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for name, v in zip(names, r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        busy = sorted(sm)[len(sm) // 2:] if sm else []       # upper half = samples under load
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from bartint_b200 import Forest, synth, _lib
+    from bartint_b200 import dist as bdist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    c = workload(args)
+    S, m, d, N, C = c["S"], c["m"], c["d"], c["N"], c["C"]
+    n_total = N * world
+
+    # ---- inputs (synthetic, seeded): posteriors of two consecutive design steps, MC points, candidates ----
+    x_train, y_train = synth.make_design(CFG)
+    flats = [synth.prior_forest(2000 + it, S, m, x_train, y_train) for it in range(2)]
+    forests = [Forest.from_soa(ff) for ff in flats]
+    assert all(f.table_kernel_ok for f in forests), "table kernel must apply to the benchmark forest"
+    X_host = torch.from_numpy(np.asfortranarray(synth.make_points(CFG, N, seed=12345 + rank)).T.copy()).pin_memory()  # [d, N]
+    Xc_host = torch.from_numpy(np.asfortranarray(synth.make_points(CFG, C, seed=777)).T.copy()).pin_memory()
+    dX, dXc = X_host.to(dev), Xc_host.to(dev)
+    st = torch.cuda.current_stream().cuda_stream
+    d_int = torch.empty(S, dtype=torch.float64, device=dev)
+    d_int_res = torch.empty(S, dtype=torch.float64, device=dev)
+    d_int_ms = torch.empty(2, dtype=torch.float64, device=dev)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    results = {}
+
+    def step(i):
+        f = forests[i % len(forests)]
+        f.exact_integrals_device(d_int.data_ptr(), "uniform", d_rescaled=d_int_res.data_ptr(),
+                                 d_mean_sd=d_int_ms.data_ptr(), stream=st)                       # sampleIntegrals + :260-262
+        pc = f.points_from_device(dXc.data_ptr(), C, stream=st)
+        var = bdist.draw_sharded_candidate_var(f, pc, None, stream=st)                             # :312-314
+        pm = f.points_from_device(dX.data_ptr(), N, stream=st)
+        dm, mv = bdist.point_sharded_draw_means(f, pm, stream=st)                                  # bartMean.R:74-82
+        pc.close(); pm.close()
+        results.update(var=var, draw_mean=dm, mean_var=mv, forest=f)
+
+    for i in range(args.warmup):
+        step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kernel_ms = []
+    launches0 = lib.bartint_kernel_launch_count()
+    torch.cuda.synchronize()
+    for i in range(args.steps):
+        flush.zero_()                                   # evict the previous step's data from the 126 MB L2
+        ev[i][0].record()
+        step(i)
+        ev[i][1].record()
+        ev[i][1].synchronize()
+        kernel_ms.append(results["forest"].last_eval_profile()["kernel_ms"])    # the MC-point evaluation kernel
+    torch.cuda.synchronize()
+    launches = lib.bartint_kernel_launch_count() - launches0
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    t_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in ev)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(t_ms.item())
+    evals_per_step = S * m * (n_total + C)
+    value = evals_per_step * args.steps / (total_ms * 1e-3)
+
+    # ---- K0 (binning) on its own: the HBM-bound kernel of the path ----
+    k0_ms = []
+    for _ in range(5):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        p = forests[0].points_from_device(dX.data_ptr(), N, stream=st)
+        b.record(); b.synchronize()
+        k0_ms.append(a.elapsed_time(b))
+        p.close()
+
+    # ---- end to end through the reference-facing call: dbarts wire format + host matrices in, host results out ----
+    e2e = None
+    if not args.no_e2e:
+        strings, fits = flats[0].to_dbarts_state(x_train)
+        cut_lists = flats[0].cut_lists()
+        Xn = X_host.numpy().T          # N x d view, column-major (pinned)
+        Xcn = Xc_host.numpy().T
+        e2e_steps = max(1, min(args.steps, 3))
+        times = []
+        h2d = d2h = 0
+        for k in range(e2e_steps + 1):
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            f = Forest.from_dbarts(strings, fits, x_train, cut_lists, flats[0].y_min, flats[0].y_max)   # exporter + H2D
+            integ = f.exact_integrals("uniform")
+            _, imean, isd = f.finalize_integrals(integ)
+            var = f.eval(Xcn, weights=np.ones(1), want=("point_var",))["point_var"]
+            dmean = f.eval(Xn, want=("draw_mean",))["draw_mean"]
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            if k > 0:
+                times.append(dt)
+            h2d = Xn.nbytes + Xcn.nbytes + f.n_nodes * 9 + f.n_leaves * 8 + f.n_groups * 8 * (f.table_bits + 1) + S * m * 8
+            d2h = integ.nbytes * 2 + var.nbytes + dmean.nbytes + 16
+            f.close()
+        t_e2e = torch.tensor([float(np.mean(times))], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+        e2e = {"value": S * m * (n_total + C) / float(t_e2e.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "s_per_step": float(t_e2e.item()), "steps": e2e_steps,
+               "includes": "dbarts-0.9-8 string/fit exporter, forest H2D + table build, X H2D (pinned), binning, "
+                           "evaluation, D2H of integrals, candidate variances and per-draw means"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (MC-point ensemble evaluation) ----
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json (measured)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
+    k1_ms = float(np.mean(kernel_ms))
+    alg_bytes = N * d * 1 + S * m * 26 + 8 * S            # uint8 codes + compact forest + per-draw sums
+    evals_k1 = S * m * N
+    sm_mhz = (clocks or {}).get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
+    # on-chip ceiling of the table kernel: shared-memory wavefronts and issue slots per (group, point)
+    f0 = forests[0]
+    trees_per_group = S * m / max(f0.n_groups, 1)
+    nb = f0.table_bits
+    # ideal shared-memory wavefronts per warp per group (conflict-free): nb/2 descriptor LDS.128 + nb*Q code LDS.32
+    # + P table LDS.64 (2 wavefronts each) + 1 header; a warp-group covers 32*P (group, point) pairs
+    wf = nb / 2.0 + nb * 2.0 + 8 * 2.0 + 1.0
+    lsu_bound = 148 * sm_mhz * 1e6 * (32 * 8) * trees_per_group / wf
+    roofline = {
+        "kernel": "eval_table_kernel (MC points)", "bound": "hbm", "achieved": alg_bytes / (k1_ms * 1e-3) / 1e9,
+        "peak": hbm_peak, "unit": "GB/s", "frac": alg_bytes / (k1_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+        "peak_source": peak_src, "alg_bytes_per_launch": alg_bytes, "alg_bytes_per_eval": alg_bytes / evals_k1,
+        "kernel_ms": k1_ms, "evals_per_s_kernel": evals_k1 / (k1_ms * 1e-3),
+        "note": "The path is NOT HBM-bound (SURVEY 8d): compulsory traffic is ~2e-4 B per tree-eval, so the HBM "
+                "fraction is tiny by construction; the binding resources are shared-memory wavefronts and issue slots.",
+        "equiv_stream_gbs": 32.0 * evals_k1 / (k1_ms * 1e-3) / 1e9,
+        "hbm_fraction_equiv_stream": 32.0 * evals_k1 / (k1_ms * 1e-3) / 1e9 / hbm_peak,
+        "smem_bound_evals_per_s": lsu_bound, "smem_bound_fraction": evals_k1 / (k1_ms * 1e-3) / lsu_bound,
+        "sm_clock_mhz": sm_mhz, "trees_per_group": trees_per_group, "table_bits": nb,
+    }
+    k0 = float(np.median(k0_ms))
+    roofline_k0 = {"kernel": "bin_points_kernel", "bound": "hbm", "achieved": 9.0 * N * d / (k0 * 1e-3) / 1e9,
+                   "peak": hbm_peak, "unit": "GB/s", "frac": 9.0 * N * d / (k0 * 1e-3) / 1e9 / hbm_peak,
+                   "traffic": None, "kernel_ms": k0, "alg_bytes_per_launch": 9 * N * d, "peak_source": peak_src}
+
+    # ---- CPU baseline beside it (oracle port, bounded sample, this box's host cores) ----
+    cpu = None
+    if not args.no_cpu and world == 1:
+        from oracle import oracle_c as oc
+        nthreads = oc.max_threads()
+        rate, rows, secs = cpu_sample_run(flats[0], X_host.numpy().T, nthreads, args.cpu_budget, oc)
+        rate1, rows1, _ = cpu_sample_run(flats[0], X_host.numpy().T, 1, min(args.cpu_budget, 5.0), oc)
+        cpu = {"value": rate, "unit": UNIT, "cores": nthreads, "kind": "port",
+               "sample": f"{rows} of {N} MC points x all {S} draws x {m} trees ({secs:.1f} s), OpenMP over draws",
+               "single_thread_value": rate1}
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": config_json(c, {"mc_points_total": n_total,
+                                                                       "parallelism": f"points x{world} (MC), draws x{world} (candidates)"}),
+        "s_per_sequential_design_step": total_ms / args.steps / 1e3,
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "roofline_k0": roofline_k0,
+        "cpu_baseline": cpu,
+        "results_check": {"integral_mean": float(d_int_ms[0].item()), "integral_sd": float(d_int_ms[1].item()),
+                          "mc_mean": float(results["mean_var"][0].item()),
+                          "argmax_candidate": int(torch.argmax(results["var"]).item())},
+    }
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--points", type=int, default=0, help="override MC points per GPU (testing)")
+    ap.add_argument("--draws", type=int, default=0, help="override posterior draws (testing)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for the cpu_baseline sample")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
