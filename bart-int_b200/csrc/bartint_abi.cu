@@ -48,7 +48,17 @@ static int finish_forest(bartint_forest* f, bartint_forest** out) {
         cudaError_t e = cudaGetDevice(&f->device);
         if (e != cudaSuccess) rc = cuda_fail(e, "cudaGetDevice", __FILE__, __LINE__);
     }
-    if (rc == BARTINT_OK) rc = forest_upload(f);
+    if (rc == BARTINT_OK) {
+        // keep freed blocks of the stream-ordered allocator cached across synchronisations (temporaries are
+        // allocated per call with cudaMallocAsync; the default threshold 0 would hand them back to the driver)
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, f->device) == cudaSuccess) {
+            uint64_t keep = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        (void)cudaGetLastError();
+        rc = forest_upload(f);
+    }
     if (rc == BARTINT_OK) {
         cudaError_t e = cudaEventCreate(&f->ev0);
         if (e == cudaSuccess) e = cudaEventCreate(&f->ev1);
@@ -186,8 +196,8 @@ static int make_points(const bartint_forest* f, int64_t N, int32_t d, cudaStream
     bartint_points* p = new (std::nothrow) bartint_points();
     BI_REQUIRE(p != nullptr, BARTINT_ERR_NOMEM, "out of host memory");
     p->device = f->device; p->N = N; p->d = d;
-    p->Npad = ((N + TK_TILE - 1) / TK_TILE) * TK_TILE;
-    if (p->Npad == 0) p->Npad = TK_TILE;
+    p->Npad = ((N + TK_NPAD - 1) / TK_NPAD) * TK_NPAD;
+    if (p->Npad == 0) p->Npad = TK_NPAD;
     p->stream = st;
     DeviceGuard g(f->device);
     cudaError_t e = cudaMallocAsync((void**)&p->codes, (size_t)std::max(d, 1) * (size_t)p->Npad, st);
@@ -269,7 +279,7 @@ static int eval_core(const bartint_forest* f, const bartint_points* p, uint32_t 
     if (ndraws == 0) return BARTINT_OK;
     const bool want_mom = d_point_mean != nullptr && d_point_m2 != nullptr;
     if (d_leaf != nullptr) flags |= BARTINT_FORCE_WALK;
-    EvalPlan plan = make_plan(f, p, flags, draw_begin, draw_end, want_mom);
+    EvalPlan plan = make_plan(f, p, flags, draw_begin, draw_end, want_mom, d_full != nullptr);
     f->last_used_table = plan.use_table ? 1 : 0;
     double *draw_part = nullptr, *pt_mean = nullptr, *pt_m2 = nullptr;
     BI_CUDA(cudaMallocAsync((void**)&draw_part, sizeof(double) * (size_t)plan.n_tiles * (size_t)ndraws, st));

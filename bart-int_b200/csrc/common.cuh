@@ -42,19 +42,18 @@ constexpr uint32_t LEAF_VAR = 0xFFFFu;
 // Table kernel ("predicate-byte + joint leaf table"): consecutive trees of one draw are packed into
 // groups whose internal nodes total <= NB.  One record per group, contiguous in HBM so a pipeline
 // stage is one 1-D bulk (TMA) copy:
-//   [ 16 B header | NB x {u32 code-row byte offset = var*TILE, u32 bias x4} | 2^NB doubles ]
+//   [ 16 B header | NB x {u32 variable, u32 bias x4} (padded to 16 B) | 2^NB doubles ]
 // Predicate of node j for 4 points at once: ((codes4 + bias4) & 0x80808080) with
 // bias = 127 - cut (codes <= 127), i.e. bit 7 of each byte = (code > cut) = "go right".
 // Table entry [idx] = sum over the group's trees of the leaf mu selected by predicate bits idx.
 constexpr int TK_THREADS = 256;        // threads per CTA
-constexpr int TK_Q = 2;                // point quads (4 points) per thread
-constexpr int TK_P = 4 * TK_Q;         // points per thread
-constexpr int TK_TILE = TK_THREADS * TK_P;   // 2048 points per CTA tile
+constexpr int TK_NPAD = TK_THREADS * 16;   // code rows are zero padded to a multiple of the largest CTA tile (4096 points)
+constexpr int TK_TILE_MIN = TK_THREADS * 8;   // smallest CTA tile (2 quads per thread)
 constexpr int TK_HDR = 16;
 constexpr uint32_t TK_FLAG_END_DRAW = 1u;
 // A tree with more than NB internal nodes cannot be indexed by NB predicate bits.  It gets a record of its own
-// of type WALK:  [ 16 B header | n_nodes x walk-node (8 B) | n_leaves doubles ]  and is walked per point inside the
-// same kernel (rare; the prior puts ~1e-4 of the trees there).  Header: {flags, first tree, n_trees | n_nodes, 0}.
+// of type WALK (header only) and is walked per point from the global node array inside the same kernel (rare; the
+// prior puts ~1e-4 of the trees there).  Header: {flags, first tree, number of trees, 0}.
 constexpr uint32_t TK_FLAG_WALK = 2u;
 __host__ __device__ constexpr int tk_tbl_off(int nb) { return TK_HDR + ((nb * 8 + 15) & ~15); }   // 16 B aligned
 __host__ __device__ constexpr int tk_rec_bytes(int nb) { return tk_tbl_off(nb) + (8 << nb); }       // multiple of 16
@@ -105,7 +104,7 @@ struct bartint_points {
     int64_t N = 0, Npad = 0;
     int32_t d = 0;
     cudaStream_t stream = nullptr;   // stream the code buffer was allocated on (stream-ordered allocator)
-    uint8_t* codes = nullptr;  // feature-major: codes[f * Npad + i], zero padded to Npad (multiple of TK_TILE)
+    uint8_t* codes = nullptr;  // feature-major: codes[f * Npad + i], zero padded to Npad (multiple of TK_NPAD)
 };
 
 namespace bartint {
@@ -128,10 +127,11 @@ int launch_build_tables(const bartint_forest* f, const uint2* d_desc, const uint
 struct EvalPlan {
     int32_t draw_begin, draw_end;
     int n_tiles, n_chunks, chunk_draws;
+    int tile;          // points per CTA
     bool use_table;
 };
 EvalPlan make_plan(const bartint_forest* f, const bartint_points* p, uint32_t flags, int32_t draw_begin,
-                   int32_t draw_end, bool want_moments);
+                   int32_t draw_end, bool want_moments, bool want_full);
 
 // draw_part: [n_tiles][ndraws]; pt_mean / pt_m2: [n_chunks][N] (may be null = no moments)
 int launch_eval_walk(const bartint_forest* f, const bartint_points* p, const EvalPlan& plan, double* draw_part,

@@ -325,10 +325,8 @@ int forest_upload(bartint_forest* f) {
 
     // ---- table path planning: greedy packing of consecutive trees of a draw into <= NB predicate bits ----
     f->nb = table_bits_from_env();
-    // a tree that does not fit NB predicate bits becomes a WALK record if its nodes + leaf values fit one record
-    const int walk_cap_leaves = (tk_rec_bytes(f->nb) - TK_HDR + 8) / 24;   // 8*(2K-1) + 8*K <= REC - HDR
-    f->table_ok = n_trees > 0 && (f->max_internal <= f->nb || f->max_internal + 1 <= walk_cap_leaves) &&
-                  f->max_cuts <= 127 && (int64_t)f->d * TK_TILE <= 160 * 1024;
+    // the table kernel needs 7-bit codes (byte-SIMD compare) and the code rows of one CTA tile in shared memory
+    f->table_ok = n_trees > 0 && f->max_cuts <= 127 && (int64_t)f->d * TK_TILE_MIN <= 160 * 1024;
     f->n_groups = 0;
     if (!f->table_ok) return BARTINT_OK;
     const int NB = f->nb;
@@ -364,7 +362,7 @@ int forest_upload(bartint_forest* f) {
                 if (f->var[g] >= 0) {
                     node_bit[g] = (uint8_t)bits;
                     uint32_t bias = (uint32_t)(127 - f->cut[g]);
-                    gd[bits] = make_uint2((uint32_t)f->var[g] * (uint32_t)TK_TILE, bias * 0x01010101u);
+                    gd[bits] = make_uint2((uint32_t)f->var[g], bias * 0x01010101u);
                     ++bits;
                 }
             }

@@ -10,8 +10,8 @@
 //                      mbarrier ring; points = uint8 cut codes, 4 per 32-bit word, feature-major
 //                      in shared memory; node test = one byte-SIMD add for 4 points; leaf values of
 //                      a whole group = one fp64 table lookup per point.
-//   eval_walk_kernel   generic fallback (any tree depth / up to 255 cuts): per-lane node walk from
-//                      L1/L2, also the producer of leaf ordinals for the bit-exactness check.
+//   eval_walk_kernel   generic fallback (up to 255 cuts, any number of variables): per-lane node walk
+//                      from L1/L2, also the producer of leaf ordinals for the bit-exactness check.
 #include <algorithm>
 
 #include "common.cuh"
@@ -27,7 +27,6 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
@@ -63,47 +62,10 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// work decomposition
-// ---------------------------------------------------------------------------------------------
-constexpr int WK_THREADS = 256;   // walk kernel: one point per thread
-
-EvalPlan make_plan(const bartint_forest* f, const bartint_points* p, uint32_t flags, int32_t draw_begin,
-                   int32_t draw_end, bool want_moments) {
-    (void)want_moments;
-    EvalPlan pl{};
-    pl.draw_begin = draw_begin;
-    pl.draw_end = draw_end;
-    const int ndraws = draw_end - draw_begin;
-    pl.use_table = f->table_ok && !(flags & BARTINT_FORCE_WALK) && p->d <= f->d;
-    const int tile = pl.use_table ? TK_TILE : WK_THREADS;
-    pl.n_tiles = (int)((p->N + tile - 1) / tile);
-    if (pl.n_tiles < 1) pl.n_tiles = 1;
-    // CTAs resident at once: 148 SMs x 2 (table kernel) or x 8 (walk kernel).  Split the draw range into chunks so
-    // the grid is several full waves; the tail wave then costs little.  Chunks only add tiny second-stage merges.
-    const int resident = 148 * (pl.use_table ? 2 : 8);
-    int best_chunks = 1;
-    double best_eff = -1.0;
-    const int max_chunks = std::max(1, std::min(ndraws, pl.use_table ? 64 : 16));
-    for (int c = 1; c <= max_chunks; ++c) {
-        const int cd = (ndraws + c - 1) / c;
-        const int real_c = (ndraws + cd - 1) / cd;
-        if (real_c != c) continue;
-        const double ctas = (double)pl.n_tiles * c;
-        const double waves = ctas / resident;
-        double eff = waves / std::ceil(waves);
-        // each extra chunk re-loads the tile's codes and re-fills the pipeline: mild preference for few chunks
-        eff -= 0.002 * c;
-        if (cd < 4 && c > 1) continue;
-        if (eff > best_eff + 1e-9) { best_eff = eff; best_chunks = c; }
-    }
-    pl.n_chunks = best_chunks;
-    pl.chunk_draws = std::max(1, (ndraws + best_chunks - 1) / best_chunks);
-    return pl;
-}
-
-// ---------------------------------------------------------------------------------------------
 // generic walk kernel
 // ---------------------------------------------------------------------------------------------
+constexpr int WK_THREADS = 256;   // one point per thread
+
 template <bool MOMENTS>
 __global__ void __launch_bounds__(WK_THREADS) eval_walk_kernel(
     const uint2* __restrict__ nodes, const int32_t* __restrict__ tree_off, const int32_t* __restrict__ tree_leaf_off,
@@ -176,21 +138,49 @@ int launch_eval_walk(const bartint_forest* f, const bartint_points* p, const Eva
 // ---------------------------------------------------------------------------------------------
 // table kernel
 // ---------------------------------------------------------------------------------------------
-constexpr int TK_GS = 8;       // groups per pipeline stage
-constexpr int TK_NSTAGE = 3;   // stages in flight
-
-// Predicate bytes of one group for one quad word stream.  After the NB steps, byte k of A holds, in its
-// top NB bits, the predicates of nodes 0..NB-1 for point k of the quad (node j at bit 8-NB+j).
-// SHARED by the evaluation kernel and the leaf-decoding kernel so the bit-exactness check exercises
-// exactly the compare the fast path uses.
-__device__ __forceinline__ uint32_t pred_step(uint32_t A, uint32_t codes4, uint32_t bias4) {
-    return (A >> 1) | ((codes4 + bias4) & 0x80808080u);
+constexpr int TK_NSTAGE = 3;                  // pipeline stages in flight
+constexpr int TK_STAGE_TARGET = 12 * 1024;    // bytes of group records per stage (one bulk copy)
+__host__ __device__ constexpr int tk_groups_per_stage(int nb) {
+    return TK_STAGE_TARGET / tk_rec_bytes(nb) < 4 ? 4 : TK_STAGE_TARGET / tk_rec_bytes(nb);
 }
+
+// Predicate bits of one group, 4 points per word.  The byte-wise sum codes + (127 - cut) carries into bit 7 of a
+// byte iff code > cut ("go right"); PRMT with the sign-replicating selector turns bit 7 into a full byte mask and
+// one LOP3 deposits it at the node's bit position.  Bit of node j inside each byte: tk_bit0(NB) + j, chosen so that
+// for NB <= 5 the byte IS the table offset idx * 8.  SHARED by the evaluation kernel and the leaf-decoding kernel
+// so the bit-exactness check exercises exactly the compare the fast path uses.
+__host__ __device__ constexpr int tk_bit0(int nb) { return nb <= 5 ? 3 : 8 - nb; }
+
+__device__ __forceinline__ uint32_t pred_mask4(uint32_t codes4, uint32_t bias4) {
+    // per byte: 0xFF if (code + bias) >= 128 else 0x00.  Selector nibbles 8..B = "replicate the sign bit of byte
+    // 0..3" -- only reachable through PTX prmt (__byte_perm masks the selector to 3 bits).
+    uint32_t m;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(m) : "r"(codes4 + bias4), "r"(0u), "r"(0xBA98u));
+    return m;
+}
+template <int NB>
+__device__ __forceinline__ uint32_t pred_step(uint32_t A, uint32_t codes4, uint32_t bias4, int j) {
+    return A | (pred_mask4(codes4, bias4) & ((1u << (tk_bit0(NB) + j)) * 0x01010101u));
+}
+// byte offset into the group's table for point k (0..3) of the quad
+template <int NB>
+__device__ __forceinline__ uint32_t table_offset(uint32_t A, int k) {
+    const uint32_t byte = __byte_perm(A, 0u, 0x4440u | (uint32_t)k);
+    if constexpr (NB <= 5) return byte;             // bits [3, 3+NB): idx * 8
+    else return byte << (NB - 5);                   // bits [8-NB, 8): idx << (8-NB)  ->  idx * 8
+}
+template <int NB>
+__device__ __forceinline__ uint32_t table_index(uint32_t A, int k) { return table_offset<NB>(A, k) >> 3; }
 
 struct TableParams {
     const uint8_t* group_rec;
     const int32_t* draw_group_off;
     const uint8_t* codes;
+    // global walk arrays for the rare WALK records (trees with more than NB internal nodes)
+    const uint2* nodes;
+    const int32_t* tree_off;
+    const int32_t* tree_leaf_off;
+    const double* leaf_mu;
     int64_t Npad, N;
     int d;
     int draw_begin, draw_end, chunk_draws;
@@ -202,25 +192,27 @@ struct TableParams {
     int fp_scaled;
 };
 
-template <int NB>
-__host__ __device__ constexpr int tk_stage_bytes() { return TK_GS * tk_rec_bytes(NB); }
-
-template <int NB>
+template <int NB, int Q>
 size_t tk_smem_bytes(int d) {
-    return (size_t)d * TK_TILE + (size_t)TK_NSTAGE * tk_stage_bytes<NB>() + 2 * TK_GS * (TK_THREADS / 32) * sizeof(double) +
-           (TK_NSTAGE + 1) * sizeof(uint64_t);
+    constexpr int GS = tk_groups_per_stage(NB);
+    return (size_t)d * (TK_THREADS * 4 * Q) + (size_t)TK_NSTAGE * GS * tk_rec_bytes(NB) +
+           2 * GS * (TK_THREADS / 32) * sizeof(double) + (TK_NSTAGE + 1) * sizeof(uint64_t);
 }
 
-template <int NB, bool MOMENTS, bool FULL>
-__global__ void __launch_bounds__(TK_THREADS, 2) eval_table_kernel(const TableParams prm) {
+// Q = point quads per thread: the CTA tile is TK_THREADS * 4 * Q points
+template <int NB, int Q, bool MOMENTS, bool FULL>
+__global__ void __launch_bounds__(TK_THREADS, (MOMENTS || Q > 2) ? 2 : 3) eval_table_kernel(const TableParams prm) {
     extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int P = 4 * Q;
+    constexpr int TILE = TK_THREADS * P;
     constexpr int REC = tk_rec_bytes(NB);
-    constexpr int STAGE = tk_stage_bytes<NB>();
+    constexpr int GS = tk_groups_per_stage(NB);
+    constexpr int STAGE = GS * REC;
     constexpr int NWARP = TK_THREADS / 32;
-    unsigned char* s_codes = smem;                                        // d rows of TK_TILE code bytes
-    unsigned char* s_stage = smem + (size_t)prm.d * TK_TILE;              // TK_NSTAGE stage buffers
-    double* s_wsum = reinterpret_cast<double*>(s_stage + TK_NSTAGE * STAGE);   // [2][TK_GS][NWARP]
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_wsum + 2 * TK_GS * NWARP); // [TK_NSTAGE] full + [1] codes
+    unsigned char* s_codes = smem;                                        // d rows of TILE code bytes
+    unsigned char* s_stage = smem + (size_t)prm.d * TILE;                 // TK_NSTAGE stage buffers
+    double* s_wsum = reinterpret_cast<double*>(s_stage + TK_NSTAGE * STAGE);   // [2][GS][NWARP]
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_wsum + 2 * GS * NWARP);    // [TK_NSTAGE] full + [1] codes
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile = blockIdx.x, chunk = blockIdx.y;
@@ -229,7 +221,7 @@ __global__ void __launch_bounds__(TK_THREADS, 2) eval_table_kernel(const TablePa
     const int s1 = min(s0 + prm.chunk_draws, prm.draw_end);
     const int g0 = prm.draw_group_off[s0], g1 = prm.draw_group_off[s1];
     const int n_groups = g1 - g0;
-    const int n_stages = (n_groups + TK_GS - 1) / TK_GS;
+    const int n_stages = (n_groups + GS - 1) / GS;
     const unsigned char* __restrict__ rec_g = prm.group_rec + (int64_t)g0 * REC;
 
     if (tid == 0) {
@@ -240,95 +232,93 @@ __global__ void __launch_bounds__(TK_THREADS, 2) eval_table_kernel(const TablePa
     __syncthreads();
     if (tid == 0) {
         // this tile's codes: one bulk copy per variable row
-        mbar_expect_tx(&s_bar[TK_NSTAGE], (uint32_t)prm.d * TK_TILE);
+        mbar_expect_tx(&s_bar[TK_NSTAGE], (uint32_t)prm.d * TILE);
         for (int j = 0; j < prm.d; ++j)
-            bulk_g2s(s_codes + (size_t)j * TK_TILE, prm.codes + (int64_t)j * prm.Npad + (int64_t)tile * TK_TILE, TK_TILE,
+            bulk_g2s(s_codes + (size_t)j * TILE, prm.codes + (int64_t)j * prm.Npad + (int64_t)tile * TILE, TILE,
                      &s_bar[TK_NSTAGE]);
         for (int k = 0; k < TK_NSTAGE && k < n_stages; ++k) {
-            const int ng = min(TK_GS, n_groups - k * TK_GS);
+            const int ng = min(GS, n_groups - k * GS);
             mbar_expect_tx(&s_bar[k], (uint32_t)(ng * REC));
             bulk_g2s(s_stage + k * STAGE, rec_g + (int64_t)k * STAGE, (uint32_t)(ng * REC), &s_bar[k]);
         }
     }
 
-    // validity of this thread's 8 points: quad q covers tile points (q*THREADS + tid)*4 .. +3
+    // validity of this thread's points: quad q covers tile points (q*THREADS + tid)*4 .. +3
     uint32_t vmask = 0;
-    const int64_t tile_base = (int64_t)tile * TK_TILE;
+    const int64_t tile_base = (int64_t)tile * TILE;
 #pragma unroll
-    for (int q = 0; q < TK_Q; ++q)
+    for (int q = 0; q < Q; ++q)
 #pragma unroll
         for (int k = 0; k < 4; ++k)
             if (tile_base + (int64_t)(q * TK_THREADS + tid) * 4 + k < prm.N) vmask |= 1u << (q * 4 + k);
 
-    double acc[TK_P];
-    double piv[MOMENTS ? TK_P : 1], S1[MOMENTS ? TK_P : 1], S2[MOMENTS ? TK_P : 1];
+    double acc[P];
+    double piv[MOMENTS ? P : 1], S1[MOMENTS ? P : 1], S2[MOMENTS ? P : 1];
 #pragma unroll
-    for (int p = 0; p < TK_P; ++p) acc[p] = 0.0;
+    for (int p = 0; p < P; ++p) acc[p] = 0.0;
 #pragma unroll
-    for (int p = 0; p < (MOMENTS ? TK_P : 1); ++p) { piv[p] = 0.0; S1[p] = 0.0; S2[p] = 0.0; }
+    for (int p = 0; p < (MOMENTS ? P : 1); ++p) { piv[p] = 0.0; S1[p] = 0.0; S2[p] = 0.0; }
 
     mbar_wait(&s_bar[TK_NSTAGE], 0);
-    const uint32_t* __restrict__ my_codes = reinterpret_cast<const uint32_t*>(s_codes) + tid;
+    const unsigned char* __restrict__ my_codes = s_codes + tid * 4;
 
     int draws_done = 0;   // uniform across the CTA
     for (int k = 0; k < n_stages; ++k) {
         const int b = k % TK_NSTAGE;
         mbar_wait(&s_bar[b], (uint32_t)((k / TK_NSTAGE) & 1));
-        const int ng = min(TK_GS, n_groups - k * TK_GS);
+        const int ng = min(GS, n_groups - k * GS);
         const unsigned char* stage = s_stage + b * STAGE;
         const int par = k & 1;
         const int stage_first_draw = draws_done;
+#pragma unroll 1
         for (int g = 0; g < ng; ++g) {
             const unsigned char* rec = stage + g * REC;
             const uint32_t flags = *reinterpret_cast<const uint32_t*>(rec);
-            const uint2* __restrict__ desc = reinterpret_cast<const uint2*>(rec + TK_HDR);
-            const double* __restrict__ tbl = reinterpret_cast<const double*>(rec + tk_tbl_off(NB));
             if (flags & TK_FLAG_WALK) {
-                // rare: a tree too deep for NB predicate bits, walked per point from its record in shared memory
-                const uint2* __restrict__ wn = reinterpret_cast<const uint2*>(rec + TK_HDR);
-                const uint32_t wcnt = reinterpret_cast<const uint32_t*>(rec)[2];
-                const double* __restrict__ wmu = reinterpret_cast<const double*>(rec + TK_HDR + 8 * wcnt);
+                // rare: a tree with more than NB internal nodes, walked per point from global memory (L1/L2)
+                const int64_t kt = reinterpret_cast<const uint32_t*>(rec)[1];
+                const uint2* __restrict__ wn = prm.nodes + prm.tree_off[kt];
+                const double* __restrict__ wmu = prm.leaf_mu + prm.tree_leaf_off[kt];
 #pragma unroll 1
-                for (int p = 0; p < TK_P; ++p) {
+                for (int p = 0; p < P; ++p) {
                     const uint32_t bo = (uint32_t)(((p >> 2) * TK_THREADS + tid) * 4 + (p & 3));
                     uint32_t node = 0;
                     uint2 r = wn[0];
                     while ((r.x & 0xFFFFu) != LEAF_VAR) {
-                        const uint32_t c = s_codes[(r.x & 0xFFFFu) * TK_TILE + bo];
+                        const uint32_t c = s_codes[(r.x & 0xFFFFu) * TILE + bo];
                         node += (c > (r.x >> 16)) ? r.y : 1u;
                         r = wn[node];
                     }
                     const double v = wmu[r.y];
 #pragma unroll
-                    for (int pp = 0; pp < TK_P; ++pp)
+                    for (int pp = 0; pp < P; ++pp)
                         if (pp == p) acc[pp] += v;      // keeps acc[] in registers (no dynamic indexing)
                 }
             } else {
-                uint32_t A[TK_Q];
+                const uint2* __restrict__ desc = reinterpret_cast<const uint2*>(rec + TK_HDR);
+                const unsigned char* __restrict__ tbl = rec + tk_tbl_off(NB);
+                uint32_t A[Q];
 #pragma unroll
-                for (int q = 0; q < TK_Q; ++q) A[q] = 0u;
+                for (int q = 0; q < Q; ++q) A[q] = 0u;
 #pragma unroll
                 for (int j = 0; j < NB; ++j) {
-                    const uint2 dj = desc[j];                                    // warp-uniform: smem broadcast
-                    const uint32_t* __restrict__ row = reinterpret_cast<const uint32_t*>(
-                        reinterpret_cast<const unsigned char*>(my_codes) + dj.x);
+                    const uint2 dj = desc[j];                                    // {variable, bias x4}: smem broadcast
+                    const uint32_t* __restrict__ row = reinterpret_cast<const uint32_t*>(my_codes + dj.x * TILE);
 #pragma unroll
-                    for (int q = 0; q < TK_Q; ++q) A[q] = pred_step(A[q], row[q * TK_THREADS], dj.y);
+                    for (int q = 0; q < Q; ++q) A[q] = pred_step<NB>(A[q], row[q * TK_THREADS], dj.y, j);
                 }
 #pragma unroll
-                for (int q = 0; q < TK_Q; ++q)
+                for (int q = 0; q < Q; ++q)
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {
-                        const uint32_t idx = (A[q] >> (8 * kk + 8 - NB)) & ((1u << NB) - 1u);
-                        acc[q * 4 + kk] += tbl[idx];
-                    }
+                    for (int kk = 0; kk < 4; ++kk)
+                        acc[q * 4 + kk] += *reinterpret_cast<const double*>(tbl + table_offset<NB>(A[q], kk));
             }
             if (flags & TK_FLAG_END_DRAW) {
                 // ---- draw epilogue: fold f_s(x) into the per-point moments and the per-draw sum ----
                 const int s = s0 + draws_done;
                 double dsum = 0.0;
 #pragma unroll
-                for (int p = 0; p < TK_P; ++p) {
+                for (int p = 0; p < P; ++p) {
                     const double fv = acc[p];
                     acc[p] = 0.0;
                     dsum += ((vmask >> p) & 1u) ? fv : 0.0;
@@ -347,14 +337,14 @@ __global__ void __launch_bounds__(TK_THREADS, 2) eval_table_kernel(const TablePa
                     }
                 }
                 dsum = warp_sum(dsum);
-                if (lane == 0) s_wsum[(par * TK_GS + (draws_done - stage_first_draw)) * NWARP + warp] = dsum;
+                if (lane == 0) s_wsum[(par * GS + (draws_done - stage_first_draw)) * NWARP + warp] = dsum;
                 ++draws_done;
             }
         }
         __syncthreads();   // every thread is done with stage buffer b and has published its warp sums
         if (tid == 0 && k + TK_NSTAGE < n_stages) {
             const int kn = k + TK_NSTAGE;
-            const int ngn = min(TK_GS, n_groups - kn * TK_GS);
+            const int ngn = min(GS, n_groups - kn * GS);
             mbar_expect_tx(&s_bar[b], (uint32_t)(ngn * REC));
             bulk_g2s(s_stage + b * STAGE, rec_g + (int64_t)kn * STAGE, (uint32_t)(ngn * REC), &s_bar[b]);
         }
@@ -362,7 +352,7 @@ __global__ void __launch_bounds__(TK_THREADS, 2) eval_table_kernel(const TablePa
         if (tid < done_here) {
             double tot = 0.0;
 #pragma unroll
-            for (int w = 0; w < NWARP; ++w) tot += s_wsum[(par * TK_GS + tid) * NWARP + w];
+            for (int w = 0; w < NWARP; ++w) tot += s_wsum[(par * GS + tid) * NWARP + w];
             prm.draw_part[(int64_t)tile * ndraws + (s0 - prm.draw_begin + stage_first_draw + tid)] = tot;
         }
     }
@@ -370,7 +360,7 @@ __global__ void __launch_bounds__(TK_THREADS, 2) eval_table_kernel(const TablePa
     if (MOMENTS) {
         const double n = (double)(s1 - s0);
 #pragma unroll
-        for (int p = 0; p < TK_P; ++p) {
+        for (int p = 0; p < P; ++p) {
             if ((vmask >> p) & 1u) {
                 const int64_t i = tile_base + (int64_t)((p >> 2) * TK_THREADS + tid) * 4 + (p & 3);
                 prm.pt_mean[(int64_t)chunk * prm.N + i] = piv[p] + S1[p] / n;
@@ -380,30 +370,91 @@ __global__ void __launch_bounds__(TK_THREADS, 2) eval_table_kernel(const TablePa
     }
 }
 
-template <int NB, bool MOMENTS, bool FULL>
-static int launch_table_inst(const TableParams& prm, dim3 grid, cudaStream_t st) {
-    static bool configured = false;
-    const size_t smem = tk_smem_bytes<NB>(prm.d);
-    auto kern = eval_table_kernel<NB, MOMENTS, FULL>;
-    static size_t configured_smem = 0;
-    if (!configured || smem > configured_smem) {
-        BI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        configured = true;
-        configured_smem = 227 * 1024;
-    }
-    kern<<<grid, TK_THREADS, smem, st>>>(prm);
-    count_launch();
-    BI_CUDA(cudaGetLastError());
-    return BARTINT_OK;
+// ---- instantiation table -----------------------------------------------------------------------------------
+typedef void (*table_kernel_t)(const TableParams);
+
+template <int NB, int Q>
+static table_kernel_t pick_kernel(bool mom, bool full) {
+    if (mom && full) return eval_table_kernel<NB, Q, true, true>;
+    if (mom) return eval_table_kernel<NB, Q, true, false>;
+    if (full) return eval_table_kernel<NB, Q, false, true>;
+    return eval_table_kernel<NB, Q, false, false>;
 }
 
+struct TableConfig {
+    table_kernel_t kern = nullptr;
+    size_t smem = 0;
+    int q = 2, tile = 0;
+};
+
 template <int NB>
-static int launch_table_nb(const TableParams& prm, dim3 grid, cudaStream_t st) {
-    const bool mom = prm.pt_mean != nullptr, full = prm.full_pred != nullptr;
-    if (mom && full) return launch_table_inst<NB, true, true>(prm, grid, st);
-    if (mom) return launch_table_inst<NB, true, false>(prm, grid, st);
-    if (full) return launch_table_inst<NB, false, true>(prm, grid, st);
-    return launch_table_inst<NB, false, false>(prm, grid, st);
+static TableConfig table_config_nb(int d, bool mom, bool full) {
+    TableConfig c;
+    // 16 points per thread when only per-draw sums are wanted (few live registers) and the codes tile stays small
+    const bool wide = !mom && !full && tk_smem_bytes<NB, 4>(d) <= 112 * 1024;
+    c.q = wide ? 4 : 2;
+    c.tile = TK_THREADS * 4 * c.q;
+    c.smem = wide ? tk_smem_bytes<NB, 4>(d) : tk_smem_bytes<NB, 2>(d);
+    c.kern = wide ? pick_kernel<NB, 4>(mom, full) : pick_kernel<NB, 2>(mom, full);
+    return c;
+}
+
+static TableConfig table_config(int nb, int d, bool mom, bool full) {
+    switch (nb) {
+        case 4: return table_config_nb<4>(d, mom, full);
+        case 5: return table_config_nb<5>(d, mom, full);
+        case 6: return table_config_nb<6>(d, mom, full);
+        case 7: return table_config_nb<7>(d, mom, full);
+        default: return table_config_nb<8>(d, mom, full);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// work decomposition
+// ---------------------------------------------------------------------------------------------
+EvalPlan make_plan(const bartint_forest* f, const bartint_points* p, uint32_t flags, int32_t draw_begin,
+                   int32_t draw_end, bool want_moments, bool want_full) {
+    EvalPlan pl{};
+    pl.draw_begin = draw_begin;
+    pl.draw_end = draw_end;
+    const int ndraws = draw_end - draw_begin;
+    pl.use_table = f->table_ok && !(flags & BARTINT_FORCE_WALK);
+    int resident_per_sm = 8;
+    pl.tile = WK_THREADS;
+    if (pl.use_table) {
+        TableConfig c = table_config(f->nb, p->d, want_moments, want_full);
+        pl.tile = c.tile;
+        cudaFuncSetAttribute(c.kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
+        int nblk = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, c.kern, TK_THREADS, c.smem) != cudaSuccess || nblk < 1) {
+            (void)cudaGetLastError();
+            nblk = 1;
+        }
+        resident_per_sm = nblk;
+    }
+    pl.n_tiles = (int)((p->N + pl.tile - 1) / pl.tile);
+    if (pl.n_tiles < 1) pl.n_tiles = 1;
+    int n_sm = 148;
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, f->device);
+    // Split the draw range into chunks so that the grid is a whole number of full waves of resident CTAs (the tail
+    // wave then costs little).  Chunks only add tiny second-stage merges.
+    const int resident = n_sm * resident_per_sm;
+    int best_chunks = 1;
+    double best_eff = -1.0;
+    const int max_chunks = std::max(1, std::min(ndraws, pl.use_table ? 96 : 16));
+    for (int c = 1; c <= max_chunks; ++c) {
+        const int cd = (ndraws + c - 1) / c;
+        const int real_c = (ndraws + cd - 1) / cd;
+        if (real_c != c) continue;
+        if (cd < 4 && c > 1) continue;
+        const double waves = (double)pl.n_tiles * c / resident;
+        // each extra chunk re-loads the tile's codes and re-fills the pipeline: mild preference for few chunks
+        const double eff = waves / std::ceil(waves) - 0.002 * c;
+        if (eff > best_eff + 1e-9) { best_eff = eff; best_chunks = c; }
+    }
+    pl.n_chunks = best_chunks;
+    pl.chunk_draws = std::max(1, (ndraws + best_chunks - 1) / best_chunks);
+    return pl;
 }
 
 int launch_eval_table(const bartint_forest* f, const bartint_points* p, const EvalPlan& plan, double* draw_part,
@@ -413,6 +464,10 @@ int launch_eval_table(const bartint_forest* f, const bartint_points* p, const Ev
     prm.group_rec = f->dev.group_rec;
     prm.draw_group_off = f->dev.draw_group_off;
     prm.codes = p->codes;
+    prm.nodes = f->dev.nodes;
+    prm.tree_off = f->dev.tree_off;
+    prm.tree_leaf_off = f->dev.tree_leaf_off;
+    prm.leaf_mu = f->dev.leaf_mu;
     prm.Npad = p->Npad;
     prm.N = p->N;
     prm.d = p->d;
@@ -426,35 +481,34 @@ int launch_eval_table(const bartint_forest* f, const bartint_points* p, const Ev
     prm.fp_scale = fp_scale;
     prm.fp_y0 = fp_y0;
     prm.fp_scaled = fp_scaled;
+    const TableConfig c = table_config(f->nb, p->d, pt_mean != nullptr, full_pred != nullptr);
+    BI_REQUIRE(c.tile == plan.tile, BARTINT_ERR_ARG, "internal: plan/launch tile mismatch");
+    BI_CUDA(cudaFuncSetAttribute(c.kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
     dim3 grid((unsigned)plan.n_tiles, (unsigned)plan.n_chunks);
-    switch (f->nb) {
-        case 4: return launch_table_nb<4>(prm, grid, st);
-        case 5: return launch_table_nb<5>(prm, grid, st);
-        case 6: return launch_table_nb<6>(prm, grid, st);
-        case 7: return launch_table_nb<7>(prm, grid, st);
-        case 8: return launch_table_nb<8>(prm, grid, st);
-    }
-    set_error("unsupported table bits %d", f->nb);
-    return BARTINT_ERR_UNSUPPORTED;
+    c.kern<<<grid, TK_THREADS, c.smem, st>>>(prm);
+    count_launch();
+    BI_CUDA(cudaGetLastError());
+    return BARTINT_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
 // Leaf ordinals decoded from the table kernel's predicate bytes (bit-exactness check of the fast
-// path's compare).  One thread per (point quad, group): recompute A with pred_step from the same
-// code words and descriptors, then walk each tree of the group with the predicate bits.
+// path's compare).  One thread per (point quad, group): recompute the predicate bytes with pred_step
+// from the same code words and descriptors, then walk each tree of the group with the predicate bits.
 // ---------------------------------------------------------------------------------------------
+template <int NB>
 __global__ void __launch_bounds__(256) table_leaf_kernel(
-    const uint8_t* __restrict__ group_rec, int nb, const int32_t* __restrict__ draw_group_off,
+    const uint8_t* __restrict__ group_rec, const int32_t* __restrict__ draw_group_off,
     const uint2* __restrict__ nodes, const int32_t* __restrict__ tree_off, const uint8_t* __restrict__ node_bit,
     const uint8_t* __restrict__ codes, int64_t Npad, int64_t N, int m, int draw_begin, int draw_end,
     int32_t* __restrict__ leaf_out) {
     const int64_t quad = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int g = draw_group_off[draw_begin] + blockIdx.y;
     if (g >= draw_group_off[draw_end] || quad * 4 >= N) return;
-    const uint8_t* rec = group_rec + (int64_t)g * tk_rec_bytes(nb);
+    const uint8_t* rec = group_rec + (int64_t)g * tk_rec_bytes(NB);
     const uint4 h = *reinterpret_cast<const uint4*>(rec);
     if (h.x & TK_FLAG_WALK) {
-        const uint2* wn = reinterpret_cast<const uint2*>(rec + TK_HDR);
+        const uint2* wn = nodes + tree_off[h.y];
         for (int kk = 0; kk < 4; ++kk) {
             const int64_t i = quad * 4 + kk;
             if (i >= N) break;
@@ -471,16 +525,17 @@ __global__ void __launch_bounds__(256) table_leaf_kernel(
     }
     const uint2* desc = reinterpret_cast<const uint2*>(rec + TK_HDR);
     uint32_t A = 0;
-    for (int j = 0; j < nb; ++j) {
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
         const uint2 dj = desc[j];
-        const int64_t var = dj.x / TK_TILE;
-        const uint32_t c4 = *reinterpret_cast<const uint32_t*>(codes + var * Npad + quad * 4);
-        A = pred_step(A, c4, dj.y);
+        const uint32_t c4 = *reinterpret_cast<const uint32_t*>(codes + (int64_t)dj.x * Npad + quad * 4);
+        A = pred_step<NB>(A, c4, dj.y, j);
     }
     for (int kk = 0; kk < 4; ++kk) {
         const int64_t i = quad * 4 + kk;
         if (i >= N) break;
-        const uint32_t idx = (A >> (8 * kk + 8 - nb)) & ((1u << nb) - 1u);
+        const uint32_t idx = kk == 0 ? table_index<NB>(A, 0) : kk == 1 ? table_index<NB>(A, 1)
+                           : kk == 2 ? table_index<NB>(A, 2) : table_index<NB>(A, 3);
         for (uint32_t t = 0; t < h.z; ++t) {
             const int64_t k = (int64_t)h.y + t;
             int32_t node = tree_off[k];
@@ -501,9 +556,17 @@ int launch_table_leaf(const bartint_forest* f, const bartint_points* p, int32_t 
     const int64_t quads = (p->N + 3) / 4;
     BI_REQUIRE(n_groups <= 65535, BARTINT_ERR_UNSUPPORTED, "leaf decoding limited to 65535 groups per call");
     dim3 grid((unsigned)((quads + 255) / 256), (unsigned)n_groups);
-    table_leaf_kernel<<<grid, 256, 0, st>>>(f->dev.group_rec, f->nb, f->dev.draw_group_off, f->dev.nodes,
-                                            f->dev.tree_off, f->dev.node_bit, p->codes, p->Npad, p->N, f->m,
-                                            draw_begin, draw_end, leaf_out);
+#define LEAF_CASE(NBV)                                                                                              \
+    case NBV:                                                                                                       \
+        table_leaf_kernel<NBV><<<grid, 256, 0, st>>>(f->dev.group_rec, f->dev.draw_group_off, f->dev.nodes,         \
+                                                     f->dev.tree_off, f->dev.node_bit, p->codes, p->Npad, p->N,     \
+                                                     f->m, draw_begin, draw_end, leaf_out);                         \
+        break;
+    switch (f->nb) {
+        LEAF_CASE(4) LEAF_CASE(5) LEAF_CASE(6) LEAF_CASE(7) LEAF_CASE(8)
+        default: set_error("unsupported table bits %d", f->nb); return BARTINT_ERR_UNSUPPORTED;
+    }
+#undef LEAF_CASE
     count_launch();
     BI_CUDA(cudaGetLastError());
     return BARTINT_OK;

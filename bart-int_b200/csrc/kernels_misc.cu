@@ -89,13 +89,8 @@ __global__ void build_tables_kernel(const uint2* __restrict__ nodes, const int32
     const int32_t tb = group_tree_off[g], te = group_tree_off[g + 1];
     const uint32_t flags = hdr[g];
     if (flags & TK_FLAG_WALK) {
-        // copy the single tree of this record: walk nodes, then its leaf values
-        const int32_t n0 = tree_off[tb], cnt = tree_off[tb + 1] - n0, l0 = tree_leaf_off[tb];
-        uint2* wn = reinterpret_cast<uint2*>(rec + TK_HDR);
-        double* wmu = reinterpret_cast<double*>(rec + TK_HDR + 8 * cnt);
-        for (int a = idx; a < cnt; a += blockDim.x) wn[a] = nodes[n0 + a];
-        for (int a = idx; a < (cnt + 1) / 2; a += blockDim.x) wmu[a] = leaf_mu[l0 + a];
-        if (idx == 0) *reinterpret_cast<uint4*>(rec) = make_uint4(flags, (uint32_t)tb, (uint32_t)cnt, 0u);
+        // header only: the evaluation kernel walks this tree from the global node array
+        if (idx == 0) *reinterpret_cast<uint4*>(rec) = make_uint4(flags, (uint32_t)tb, (uint32_t)(te - tb), 0u);
         return;
     }
     double sum = 0.0;
