@@ -282,7 +282,7 @@ static int upload(T** dptr, const std::vector<T>& h) {
 
 static int table_bits_from_env() {
     const char* e = getenv("BARTINT_TABLE_BITS");
-    int nb = e ? atoi(e) : 8;
+    int nb = e ? atoi(e) : 5;
     if (nb < 4) nb = 4;
     if (nb > 8) nb = 8;
     return nb;

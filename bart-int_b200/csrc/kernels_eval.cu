@@ -13,6 +13,7 @@
 //   eval_walk_kernel   generic fallback (up to 255 cuts, any number of variables): per-lane node walk
 //                      from L1/L2, also the producer of leaf ordinals for the bit-exactness check.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -192,23 +193,23 @@ struct TableParams {
     int fp_scaled;
 };
 
-template <int NB, int Q>
+template <int NB, int Q, int T>
 size_t tk_smem_bytes(int d) {
     constexpr int GS = tk_groups_per_stage(NB);
-    return (size_t)d * (TK_THREADS * 4 * Q) + (size_t)TK_NSTAGE * GS * tk_rec_bytes(NB) +
-           2 * GS * (TK_THREADS / 32) * sizeof(double) + (TK_NSTAGE + 1) * sizeof(uint64_t);
+    return (size_t)d * (T * 4 * Q) + (size_t)TK_NSTAGE * GS * tk_rec_bytes(NB) + 2 * GS * (T / 32) * sizeof(double) +
+           (TK_NSTAGE + 1) * sizeof(uint64_t);
 }
 
-// Q = point quads per thread: the CTA tile is TK_THREADS * 4 * Q points
-template <int NB, int Q, bool MOMENTS, bool FULL>
-__global__ void __launch_bounds__(TK_THREADS, (MOMENTS || Q > 2) ? 2 : 3) eval_table_kernel(const TableParams prm) {
+// Q = point quads per thread, T = threads per CTA: the CTA tile is T * 4 * Q points
+template <int NB, int Q, int T, bool MOMENTS, bool FULL>
+__global__ void __launch_bounds__(T, (T > 256) ? 2 : ((MOMENTS || Q > 2) ? 2 : 3)) eval_table_kernel(const TableParams prm) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int P = 4 * Q;
-    constexpr int TILE = TK_THREADS * P;
+    constexpr int TILE = T * P;
     constexpr int REC = tk_rec_bytes(NB);
     constexpr int GS = tk_groups_per_stage(NB);
     constexpr int STAGE = GS * REC;
-    constexpr int NWARP = TK_THREADS / 32;
+    constexpr int NWARP = T / 32;
     unsigned char* s_codes = smem;                                        // d rows of TILE code bytes
     unsigned char* s_stage = smem + (size_t)prm.d * TILE;                 // TK_NSTAGE stage buffers
     double* s_wsum = reinterpret_cast<double*>(s_stage + TK_NSTAGE * STAGE);   // [2][GS][NWARP]
@@ -250,7 +251,7 @@ __global__ void __launch_bounds__(TK_THREADS, (MOMENTS || Q > 2) ? 2 : 3) eval_t
     for (int q = 0; q < Q; ++q)
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-            if (tile_base + (int64_t)(q * TK_THREADS + tid) * 4 + k < prm.N) vmask |= 1u << (q * 4 + k);
+            if (tile_base + (int64_t)(q * T + tid) * 4 + k < prm.N) vmask |= 1u << (q * 4 + k);
 
     double acc[P];
     double piv[MOMENTS ? P : 1], S1[MOMENTS ? P : 1], S2[MOMENTS ? P : 1];
@@ -274,6 +275,7 @@ __global__ void __launch_bounds__(TK_THREADS, (MOMENTS || Q > 2) ? 2 : 3) eval_t
         for (int g = 0; g < ng; ++g) {
             const unsigned char* rec = stage + g * REC;
             const uint32_t flags = *reinterpret_cast<const uint32_t*>(rec);
+            const uint2* __restrict__ cur_desc = reinterpret_cast<const uint2*>(rec + TK_HDR);   // smem broadcast loads
             if (flags & TK_FLAG_WALK) {
                 // rare: a tree with more than NB internal nodes, walked per point from global memory (L1/L2)
                 const int64_t kt = reinterpret_cast<const uint32_t*>(rec)[1];
@@ -281,7 +283,7 @@ __global__ void __launch_bounds__(TK_THREADS, (MOMENTS || Q > 2) ? 2 : 3) eval_t
                 const double* __restrict__ wmu = prm.leaf_mu + prm.tree_leaf_off[kt];
 #pragma unroll 1
                 for (int p = 0; p < P; ++p) {
-                    const uint32_t bo = (uint32_t)(((p >> 2) * TK_THREADS + tid) * 4 + (p & 3));
+                    const uint32_t bo = (uint32_t)(((p >> 2) * T + tid) * 4 + (p & 3));
                     uint32_t node = 0;
                     uint2 r = wn[0];
                     while ((r.x & 0xFFFFu) != LEAF_VAR) {
@@ -295,17 +297,16 @@ __global__ void __launch_bounds__(TK_THREADS, (MOMENTS || Q > 2) ? 2 : 3) eval_t
                         if (pp == p) acc[pp] += v;      // keeps acc[] in registers (no dynamic indexing)
                 }
             } else {
-                const uint2* __restrict__ desc = reinterpret_cast<const uint2*>(rec + TK_HDR);
                 const unsigned char* __restrict__ tbl = rec + tk_tbl_off(NB);
                 uint32_t A[Q];
 #pragma unroll
                 for (int q = 0; q < Q; ++q) A[q] = 0u;
 #pragma unroll
                 for (int j = 0; j < NB; ++j) {
-                    const uint2 dj = desc[j];                                    // {variable, bias x4}: smem broadcast
+                    const uint2 dj = cur_desc[j];                                // {variable, bias x4}
                     const uint32_t* __restrict__ row = reinterpret_cast<const uint32_t*>(my_codes + dj.x * TILE);
 #pragma unroll
-                    for (int q = 0; q < Q; ++q) A[q] = pred_step<NB>(A[q], row[q * TK_THREADS], dj.y, j);
+                    for (int q = 0; q < Q; ++q) A[q] = pred_step<NB>(A[q], row[q * T], dj.y, j);
                 }
 #pragma unroll
                 for (int q = 0; q < Q; ++q)
@@ -330,7 +331,7 @@ __global__ void __launch_bounds__(TK_THREADS, (MOMENTS || Q > 2) ? 2 : 3) eval_t
                     }
                     if (FULL) {
                         if ((vmask >> p) & 1u) {
-                            const int64_t i = tile_base + (int64_t)((p >> 2) * TK_THREADS + tid) * 4 + (p & 3);
+                            const int64_t i = tile_base + (int64_t)((p >> 2) * T + tid) * 4 + (p & 3);
                             prm.full_pred[(int64_t)(s - prm.draw_begin) + (int64_t)ndraws * i] =
                                 prm.fp_scaled ? fv : prm.fp_scale * (fv + 0.5) + prm.fp_y0;
                         }
@@ -362,7 +363,7 @@ __global__ void __launch_bounds__(TK_THREADS, (MOMENTS || Q > 2) ? 2 : 3) eval_t
 #pragma unroll
         for (int p = 0; p < P; ++p) {
             if ((vmask >> p) & 1u) {
-                const int64_t i = tile_base + (int64_t)((p >> 2) * TK_THREADS + tid) * 4 + (p & 3);
+                const int64_t i = tile_base + (int64_t)((p >> 2) * T + tid) * 4 + (p & 3);
                 prm.pt_mean[(int64_t)chunk * prm.N + i] = piv[p] + S1[p] / n;
                 prm.pt_m2[(int64_t)chunk * prm.N + i] = S2[p] - S1[p] * S1[p] / n;
             }
@@ -373,30 +374,42 @@ __global__ void __launch_bounds__(TK_THREADS, (MOMENTS || Q > 2) ? 2 : 3) eval_t
 // ---- instantiation table -----------------------------------------------------------------------------------
 typedef void (*table_kernel_t)(const TableParams);
 
-template <int NB, int Q>
+template <int NB, int Q, int T>
 static table_kernel_t pick_kernel(bool mom, bool full) {
-    if (mom && full) return eval_table_kernel<NB, Q, true, true>;
-    if (mom) return eval_table_kernel<NB, Q, true, false>;
-    if (full) return eval_table_kernel<NB, Q, false, true>;
-    return eval_table_kernel<NB, Q, false, false>;
+    if (mom && full) return eval_table_kernel<NB, Q, T, true, true>;
+    if (mom) return eval_table_kernel<NB, Q, T, true, false>;
+    if (full) return eval_table_kernel<NB, Q, T, false, true>;
+    return eval_table_kernel<NB, Q, T, false, false>;
 }
 
 struct TableConfig {
     table_kernel_t kern = nullptr;
     size_t smem = 0;
-    int q = 2, tile = 0;
+    int q = 2, threads = 256, tile = 0;
 };
+
+template <int NB, int Q, int T>
+static TableConfig make_config(bool mom, bool full, int d) {
+    TableConfig c;
+    c.q = Q; c.threads = T; c.tile = T * 4 * Q;
+    c.smem = tk_smem_bytes<NB, Q, T>(d);
+    c.kern = pick_kernel<NB, Q, T>(mom, full);
+    return c;
+}
 
 template <int NB>
 static TableConfig table_config_nb(int d, bool mom, bool full) {
-    TableConfig c;
-    // 16 points per thread when only per-draw sums are wanted (few live registers) and the codes tile stays small
-    const bool wide = !mom && !full && tk_smem_bytes<NB, 4>(d) <= 112 * 1024;
-    c.q = wide ? 4 : 2;
-    c.tile = TK_THREADS * 4 * c.q;
-    c.smem = wide ? tk_smem_bytes<NB, 4>(d) : tk_smem_bytes<NB, 2>(d);
-    c.kern = wide ? pick_kernel<NB, 4>(mom, full) : pick_kernel<NB, 2>(mom, full);
-    return c;
+    // shapes: (Q quads/thread, T threads).  Per-draw-sum-only evaluations keep few live registers and take the wide
+    // shapes; per-point moments / full output keep 8 points per thread.  BARTINT_TK_SHAPE overrides (tuning).
+    int shape = (!mom && !full) ? 1 : 0;                       // 0: q2 t256   1: q4 t256   2: q2 t512
+    if (const char* e = getenv("BARTINT_TK_SHAPE")) { if (!mom && !full) shape = atoi(e); }
+    if (shape == 1 && tk_smem_bytes<NB, 4, 256>(d) > 112 * 1024) shape = 0;
+    if (shape == 2 && tk_smem_bytes<NB, 2, 512>(d) > 112 * 1024) shape = 0;
+    switch (shape) {
+        case 1: return make_config<NB, 4, 256>(mom, full, d);
+        case 2: return make_config<NB, 2, 512>(mom, full, d);
+        default: return make_config<NB, 2, 256>(mom, full, d);
+    }
 }
 
 static TableConfig table_config(int nb, int d, bool mom, bool full) {
@@ -426,7 +439,7 @@ EvalPlan make_plan(const bartint_forest* f, const bartint_points* p, uint32_t fl
         pl.tile = c.tile;
         cudaFuncSetAttribute(c.kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
         int nblk = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, c.kern, TK_THREADS, c.smem) != cudaSuccess || nblk < 1) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, c.kern, c.threads, c.smem) != cudaSuccess || nblk < 1) {
             (void)cudaGetLastError();
             nblk = 1;
         }
@@ -485,7 +498,7 @@ int launch_eval_table(const bartint_forest* f, const bartint_points* p, const Ev
     BI_REQUIRE(c.tile == plan.tile, BARTINT_ERR_ARG, "internal: plan/launch tile mismatch");
     BI_CUDA(cudaFuncSetAttribute(c.kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
     dim3 grid((unsigned)plan.n_tiles, (unsigned)plan.n_chunks);
-    c.kern<<<grid, TK_THREADS, c.smem, st>>>(prm);
+    c.kern<<<grid, c.threads, c.smem, st>>>(prm);
     count_launch();
     BI_CUDA(cudaGetLastError());
     return BARTINT_OK;
