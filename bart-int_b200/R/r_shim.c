@@ -1,0 +1,93 @@
+/*
+ * r_shim.c -- .Call glue between R and libbartint_cuda.so (include/bartint.h).
+ *
+ * SOURCE ONLY: this image has no R (no Rinternals.h / libR.so), so the shim is not built or tested here;
+ * everything it calls is exercised through the same C ABI by the ctypes tests.  On an R box:
+ *     R CMD SHLIB r_shim.c -I<repo>/include -L<repo>/bart-int_b200 -lbartint_cuda -o bartint_r.so
+ *
+ * R objects are read in place (column-major doubles, CHARSXP strings) -- no conversion, nothing retained.
+ * Every non-zero status becomes an R error carrying bartint_last_error().
+ */
+#include <R.h>
+#include <Rinternals.h>
+#include <stdint.h>
+#include <stdlib.h>
+
+#include "bartint.h"
+
+static void check(int status) {
+    if (status != BARTINT_OK) Rf_error("bartint: %s", bartint_last_error());
+}
+
+static void forest_finalizer(SEXP ptr) {
+    bartint_forest* f = (bartint_forest*)R_ExternalPtrAddr(ptr);
+    if (f) { bartint_forest_destroy(f); R_ClearExternalPtr(ptr); }
+}
+
+static bartint_forest* forest_of(SEXP ptr) {
+    bartint_forest* f = (bartint_forest*)R_ExternalPtrAddr(ptr);
+    if (!f) Rf_error("bartint: forest handle was already released");
+    return f;
+}
+
+/* .Call("bartint_R_forest", savedTrees (chr m x S), savedTreeFits (dbl n x m x S), x (dbl n x d),
+ *       cutPoints (list of d numeric), ymin, ymax)  -> external pointer
+ * Replaces getTree() for every (tree, draw): src/BARTInt.R:92-133. */
+SEXP bartint_R_forest(SEXP trees, SEXP fits, SEXP x, SEXP cuts, SEXP ymin, SEXP ymax) {
+    SEXP dim = Rf_getAttrib(trees, R_DimSymbol);
+    const int m = INTEGER(dim)[0], S = INTEGER(dim)[1];
+    SEXP xdim = Rf_getAttrib(x, R_DimSymbol);
+    const int64_t n = INTEGER(xdim)[0];
+    const int d = INTEGER(xdim)[1];
+    const char** strs = (const char**)R_alloc((size_t)m * S, sizeof(char*));
+    for (R_xlen_t k = 0; k < (R_xlen_t)m * S; ++k) strs[k] = CHAR(STRING_ELT(trees, k));   /* [tree, sample] col-major */
+    int32_t* off = (int32_t*)R_alloc((size_t)d + 1, sizeof(int32_t));
+    off[0] = 0;
+    for (int j = 0; j < d; ++j) off[j + 1] = off[j] + (int32_t)XLENGTH(VECTOR_ELT(cuts, j));
+    double* vals = (double*)R_alloc((size_t)off[d] + 1, sizeof(double));
+    for (int j = 0; j < d; ++j) {
+        const double* c = REAL(VECTOR_ELT(cuts, j));
+        for (int k = 0; k < off[j + 1] - off[j]; ++k) vals[off[j] + k] = c[k];
+    }
+    bartint_forest* f = NULL;
+    check(bartint_forest_from_dbarts098(strs, REAL(fits), REAL(x), n, d, off, vals, Rf_asReal(ymin), Rf_asReal(ymax),
+                                        m, S, &f));
+    SEXP ptr = PROTECT(R_MakeExternalPtr(f, R_NilValue, R_NilValue));
+    R_RegisterCFinalizerEx(ptr, forest_finalizer, TRUE);
+    UNPROTECT(1);
+    return ptr;
+}
+
+/* sampleIntegrals(model, dim, measure): src/BARTInt.R:204-223.  n_draws_used <= 0 -> all draws. */
+SEXP bartint_R_exact_integrals(SEXP ptr, SEXP measure, SEXP n_draws_used) {
+    bartint_forest* f = forest_of(ptr);
+    int64_t info[10];
+    check(bartint_forest_info(f, info));
+    int n = Rf_asInteger(n_draws_used);
+    if (n <= 0 || n > info[0]) n = (int)info[0];
+    SEXP out = PROTECT(Rf_allocVector(REALSXP, n));
+    check(bartint_exact_integrals(f, Rf_asInteger(measure), NULL, NULL, n, REAL(out)));
+    UNPROTECT(1);
+    return out;
+}
+
+/* what: bit 1 = rowMeans, bit 2 = colVars * weights, bit 4 = full S x N matrix (predict).
+ * Replaces predict(model, X) / colVars / rowMeans: BARTInt.R:312-314, bartMean.R:47-50,74-82. */
+SEXP bartint_R_eval(SEXP ptr, SEXP x, SEXP weights, SEXP what) {
+    bartint_forest* f = forest_of(ptr);
+    int64_t info[10];
+    check(bartint_forest_info(f, info));
+    SEXP xdim = Rf_getAttrib(x, R_DimSymbol);
+    const int64_t N = INTEGER(xdim)[0];
+    const int d = INTEGER(xdim)[1], S = (int)info[0], w = Rf_asInteger(what);
+    SEXP rm = PROTECT((w & 1) ? Rf_allocVector(REALSXP, S) : R_NilValue);
+    SEXP cv = PROTECT((w & 2) ? Rf_allocVector(REALSXP, N) : R_NilValue);
+    SEXP full = PROTECT((w & 4) ? Rf_allocMatrix(REALSXP, S, (int)N) : R_NilValue);
+    const int has_w = !Rf_isNull(weights);
+    check(bartint_eval(f, REAL(x), N, d, 0u, has_w ? REAL(weights) : NULL, has_w ? XLENGTH(weights) : 0,
+                       (w & 1) ? REAL(rm) : NULL, NULL, (w & 2) ? REAL(cv) : NULL, (w & 4) ? REAL(full) : NULL));
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 3));
+    SET_VECTOR_ELT(out, 0, rm); SET_VECTOR_ELT(out, 1, cv); SET_VECTOR_ELT(out, 2, full);
+    UNPROTECT(4);
+    return out;
+}

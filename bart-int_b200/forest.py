@@ -116,8 +116,21 @@ class FlatForest:
             go_right = codes[rows, np.where(internal, v, 0)] > self.cut[node]
             nxt = np.where(go_right, self.right[node], self.left[node]) + base
             node = np.where(internal, nxt, node)
-        fits = self.mu[node].reshape(self.S, self.m, n).transpose(2, 1, 0).copy()
+        # [n, m, S] in R's column-major layout (n fastest) == C-ordered (S, m, n): a transposed view, no copy
+        fits = self.mu[node].reshape(self.S, self.m, n).transpose(2, 1, 0)
         return strings, fits
+
+
+class WireStrings:
+    """savedTrees as the C ABI takes them: an array of K = m*S C strings in R's column-major order (tree index
+    fastest).  R already holds its character matrix this way (CHARSXP pointers), so the .Call shim passes them
+    without conversion; on the Python side the encoding is done once per model and cached here."""
+
+    def __init__(self, tree_strings):
+        tree_strings = np.asarray(tree_strings, dtype=object)
+        self.m, self.S = tree_strings.shape
+        self._enc = [str(v).encode("ascii") for v in tree_strings.T.ravel()]     # index t + s*m
+        self.array = (C.c_char_p * max(len(self._enc), 1))(*self._enc)
 
 
 class Points:
@@ -179,14 +192,14 @@ class Forest:
         tree_strings [m, S] (R: savedTrees[treeNum, sampleNum]); tree_fits [n, m, S]; x_train [n, d].
         """
         lib = _lib.load()
-        tree_strings = np.asarray(tree_strings, dtype=object)
-        m, S = tree_strings.shape
+        wire = tree_strings if isinstance(tree_strings, WireStrings) else WireStrings(tree_strings)
+        m, S, arr = wire.m, wire.S, wire.array
         x_train = np.asarray(x_train, np.float64)
         n, d = x_train.shape
-        fits = np.asfortranarray(np.asarray(tree_fits, np.float64).reshape(n, m, S))
+        fits = np.asarray(tree_fits, np.float64).reshape(n, m, S)
+        if not fits.flags["F_CONTIGUOUS"]:
+            fits = np.asfortranarray(fits)          # R arrays are column-major already; numpy ones may need a copy
         xt = np.asfortranarray(x_train)
-        enc = [str(tree_strings[k % m, k // m]).encode("ascii") for k in range(m * S)]
-        arr = (C.c_char_p * max(len(enc), 1))(*enc)
         cut_offsets = np.zeros(d + 1, np.int32)
         cut_offsets[1:] = np.cumsum([len(c) for c in cut_lists])
         cut_values = (np.concatenate([np.asarray(c, np.float64) for c in cut_lists]) if d else np.zeros(0))

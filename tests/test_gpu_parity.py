@@ -252,3 +252,34 @@ def test_full_size_properties_cfg2_shape():
     sd = np.sqrt(f.eval(X[:20000], want=("full_pred",), scaled=True)["full_pred"].var(axis=1, ddof=1) / 200_000)
     assert (np.abs(a - exact) <= 6 * sd + 1e-9).all()
     f.close()
+
+
+def test_dist_wrappers_single_rank(small_case):
+    """The production multi-GPU wrappers (device tensors, async ABI) at world size 1 == the host API."""
+    import torch
+    from bartint_b200 import dist as bdist
+    ff, _, _, X = small_case
+    f = Forest.from_soa(ff)
+    dX = torch.from_numpy(np.asfortranarray(X).T.copy()).cuda()          # [d, N] == N x d column-major
+    pts = f.points_from_device(dX.data_ptr(), X.shape[0])
+    dm, mv = bdist.point_sharded_draw_means(f, pts)
+    w = torch.rand(X.shape[0], dtype=torch.float64, device="cuda")
+    var = bdist.draw_sharded_candidate_var(f, pts, w)
+    torch.cuda.synchronize()
+    P = onp.predict(ff, X)
+    rm = onp.row_means(P)
+    _assert_close(dm.cpu().numpy(), rm, 1e-13)
+    _assert_close(mv.cpu().numpy(), [rm.mean(), rm.var(ddof=1)], 1e-11)
+    _assert_close(var.cpu().numpy(), onp.col_vars(P) * w.cpu().numpy(), 1e-10)
+    # async exact integral + fused finalisation
+    d_int = torch.empty(ff.S, dtype=torch.float64, device="cuda")
+    d_res = torch.empty(ff.S, dtype=torch.float64, device="cuda")
+    d_ms = torch.empty(2, dtype=torch.float64, device="cuda")
+    f.exact_integrals_device(d_int.data_ptr(), "uniform", d_rescaled=d_res.data_ptr(), d_mean_sd=d_ms.data_ptr())
+    torch.cuda.synchronize()
+    want = onp.sample_integrals(ff, "uniform")
+    r0, m0, s0 = onp.finalize_integrals(want, ff.y_min, ff.y_max)
+    _assert_close(d_int.cpu().numpy(), want, 1e-12, scale=np.maximum(np.abs(want), 1e-3))
+    _assert_close(d_res.cpu().numpy(), r0, 1e-13)
+    _assert_close(d_ms.cpu().numpy(), [m0, s0], 1e-11)
+    pts.close(); f.close()
