@@ -97,7 +97,7 @@ def run_reference(args):
     evals = ff.S * ff.m * (rows + c["C"]) * args.steps
     value = evals / dt
     sample = f"{rows} of {c['N']} MC points + {c['C']} candidates, all {c['S']} draws, per step"
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -122,7 +122,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -199,14 +199,14 @@ def run_ours(args):
         pc.close(); pm.close()
         results.update(var=var, draw_mean=dm, mean_var=mv, forest=f)
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()          # samples from warm-up to the end of the timed region
     for i in range(args.warmup):
         step(i)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     kernel_ms = []
     launches0 = lib.bartint_kernel_launch_count()
@@ -343,12 +343,25 @@ def run_ours(args):
                           "mc_mean": float(results["mean_var"][0].item()),
                           "argmax_candidate": int(torch.argmax(results["var"]).item())},
     }
-    print(json.dumps(out))
+    emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: str) -> None:
+    """Print the ONE result line on the real stdout (fd 1 is pointed at stderr for the rest of the run so that
+    library chatter such as NCCL's version banner cannot pollute it)."""
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (line + "\n").encode())
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
