@@ -336,6 +336,28 @@ int forest_upload(bartint_forest* f) {
     std::vector<uint8_t> node_bit((size_t)nn, 0);
     f->draw_group_off.assign((size_t)f->S + 1, 0);
     group_tree_off.reserve((size_t)(n_trees / 3 + f->S + 1));
+    // Bit order inside a group: table lookups of lanes whose indices differ only in a HIGH bit hit the same bank pair
+    // (a 2^NB x 8 B table wraps the 32 banks 2^(NB-4) times), lookups with equal indices are a broadcast.  The
+    // predicates least likely to differ between points -- cuts nearest the edge of their variable's cut grid -- are
+    // therefore given the highest bits.  Pure layout choice: the builder and the kernels read node_bit / desc.
+    std::vector<int64_t> gnodes;           // nodes of the group being filled
+    auto close_group = [&]() {
+        if (gnodes.empty()) return;
+        auto extremeness = [&](int64_t g) {
+            const int v = f->var[(size_t)g];
+            const double nc = (double)(f->cut_off[(size_t)v + 1] - f->cut_off[(size_t)v]);
+            return std::fabs(2.0 * (f->cut[(size_t)g] + 1.0) / (nc + 1.0) - 1.0);
+        };
+        std::stable_sort(gnodes.begin(), gnodes.end(),
+                         [&](int64_t a, int64_t b2) { return extremeness(a) < extremeness(b2); });
+        uint2* gd = &desc[desc.size() - (size_t)NB];
+        for (size_t b2 = 0; b2 < gnodes.size(); ++b2) {
+            const size_t g = (size_t)gnodes[b2];
+            node_bit[g] = (uint8_t)b2;
+            gd[b2] = make_uint2((uint32_t)f->var[g], (uint32_t)(127 - f->cut[g]) * 0x01010101u);
+        }
+        gnodes.clear();
+    };
     for (int32_t s = 0; s < f->S; ++s) {
         f->draw_group_off[(size_t)s] = (int32_t)group_tree_off.size();
         int bits = NB + 1;   // force a new group at the start of a draw
@@ -344,6 +366,7 @@ int forest_upload(bartint_forest* f) {
             const int32_t base = tree_off[(size_t)k], cnt = tree_off[(size_t)k + 1] - base;
             const int internal = (cnt - 1) / 2;
             if (internal > NB) {               // WALK record holding just this tree
+                close_group();
                 group_tree_off.push_back((int32_t)k);
                 hdr.push_back(TK_FLAG_WALK);
                 desc.resize(desc.size() + (size_t)NB, make_uint2(0u, 0u));
@@ -351,22 +374,17 @@ int forest_upload(bartint_forest* f) {
                 continue;
             }
             if (bits + internal > NB) {
+                close_group();
                 group_tree_off.push_back((int32_t)k);
                 hdr.push_back(0u);
                 desc.resize(desc.size() + (size_t)NB, make_uint2(0u, 0u));   // unused slots: bias 0 -> predicate 0
                 bits = 0;
             }
-            uint2* gd = &desc[desc.size() - (size_t)NB];
-            for (int32_t a = 0; a < cnt; ++a) {
-                const size_t g = (size_t)(base + a);
-                if (f->var[g] >= 0) {
-                    node_bit[g] = (uint8_t)bits;
-                    uint32_t bias = (uint32_t)(127 - f->cut[g]);
-                    gd[bits] = make_uint2((uint32_t)f->var[g], bias * 0x01010101u);
-                    ++bits;
-                }
-            }
+            for (int32_t a = 0; a < cnt; ++a)
+                if (f->var[(size_t)(base + a)] >= 0) gnodes.push_back((int64_t)base + a);
+            bits += internal;
         }
+        close_group();
         hdr.back() |= TK_FLAG_END_DRAW;
     }
     f->draw_group_off[(size_t)f->S] = (int32_t)group_tree_off.size();

@@ -141,8 +141,9 @@ int launch_eval_walk(const bartint_forest* f, const bartint_points* p, const Eva
 // ---------------------------------------------------------------------------------------------
 constexpr int TK_NSTAGE = 3;                  // pipeline stages in flight
 constexpr int TK_STAGE_TARGET = 12 * 1024;    // bytes of group records per stage (one bulk copy)
-__host__ __device__ constexpr int tk_groups_per_stage(int nb) {
-    return TK_STAGE_TARGET / tk_rec_bytes(nb) < 4 ? 4 : TK_STAGE_TARGET / tk_rec_bytes(nb);
+__host__ __device__ constexpr int tk_groups_per_stage(int nb) {   // 4..64 (the per-stage flag masks are 64-bit)
+    return TK_STAGE_TARGET / tk_rec_bytes(nb) < 4 ? 4
+           : (TK_STAGE_TARGET / tk_rec_bytes(nb) > 64 ? 64 : TK_STAGE_TARGET / tk_rec_bytes(nb));
 }
 
 // Predicate bits of one group, 4 points per word.  The byte-wise sum codes + (127 - cut) carries into bit 7 of a
@@ -271,30 +272,48 @@ __global__ void __launch_bounds__(T, (T > 256) ? 2 : ((MOMENTS || Q > 2) ? 2 : 3
         const unsigned char* stage = s_stage + b * STAGE;
         const int par = k & 1;
         const int stage_first_draw = draws_done;
+        // the stage's group flags as two warp-uniform bit masks (one strided load + ballots per stage instead of a
+        // dependent header load + branch per group)
+        unsigned long long walk_mask = 0ull, end_mask = 0ull;
+#pragma unroll
+        for (int base = 0; base < GS; base += 32) {
+            const int gl = base + lane;
+            const uint32_t fl = gl < ng ? *reinterpret_cast<const uint32_t*>(stage + gl * REC) : 0u;
+            walk_mask |= (unsigned long long)__ballot_sync(0xffffffffu, (fl & TK_FLAG_WALK) != 0u) << base;
+            end_mask |= (unsigned long long)__ballot_sync(0xffffffffu, (fl & TK_FLAG_END_DRAW) != 0u) << base;
+        }
 #pragma unroll 1
         for (int g = 0; g < ng; ++g) {
             const unsigned char* rec = stage + g * REC;
-            const uint32_t flags = *reinterpret_cast<const uint32_t*>(rec);
             const uint2* __restrict__ cur_desc = reinterpret_cast<const uint2*>(rec + TK_HDR);   // smem broadcast loads
-            if (flags & TK_FLAG_WALK) {
+            if ((walk_mask >> g) & 1ull) {
                 // rare: a tree with more than NB internal nodes, walked per point from global memory (L1/L2)
                 const int64_t kt = reinterpret_cast<const uint32_t*>(rec)[1];
                 const uint2* __restrict__ wn = prm.nodes + prm.tree_off[kt];
                 const double* __restrict__ wmu = prm.leaf_mu + prm.tree_leaf_off[kt];
-#pragma unroll 1
-                for (int p = 0; p < P; ++p) {
-                    const uint32_t bo = (uint32_t)(((p >> 2) * T + tid) * 4 + (p & 3));
-                    uint32_t node = 0;
-                    uint2 r = wn[0];
-                    while ((r.x & 0xFFFFu) != LEAF_VAR) {
-                        const uint32_t c = s_codes[(r.x & 0xFFFFu) * TILE + bo];
-                        node += (c > (r.x >> 16)) ? r.y : 1u;
-                        r = wn[node];
-                    }
-                    const double v = wmu[r.y];
 #pragma unroll
-                    for (int pp = 0; pp < P; ++pp)
-                        if (pp == p) acc[pp] += v;      // keeps acc[] in registers (no dynamic indexing)
+                for (int q = 0; q < Q; ++q) {
+                    // the 4 points of a quad advance in lock-step (independent chains -> memory-level parallelism)
+                    uint32_t node[4] = {0u, 0u, 0u, 0u};
+                    uint2 r[4];
+                    const uint32_t bo = (uint32_t)((q * T + tid) * 4);
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) r[kk] = wn[0];
+                    bool any = (r[0].x & 0xFFFFu) != LEAF_VAR;
+                    while (any) {
+                        any = false;
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) {
+                            if ((r[kk].x & 0xFFFFu) != LEAF_VAR) {
+                                const uint32_t c = s_codes[(r[kk].x & 0xFFFFu) * TILE + bo + kk];
+                                node[kk] += (c > (r[kk].x >> 16)) ? r[kk].y : 1u;
+                                r[kk] = wn[node[kk]];
+                                any |= (r[kk].x & 0xFFFFu) != LEAF_VAR;
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) acc[q * 4 + kk] += wmu[r[kk].y];
                 }
             } else {
                 const unsigned char* __restrict__ tbl = rec + tk_tbl_off(NB);
@@ -314,7 +333,7 @@ __global__ void __launch_bounds__(T, (T > 256) ? 2 : ((MOMENTS || Q > 2) ? 2 : 3
                     for (int kk = 0; kk < 4; ++kk)
                         acc[q * 4 + kk] += *reinterpret_cast<const double*>(tbl + table_offset<NB>(A[q], kk));
             }
-            if (flags & TK_FLAG_END_DRAW) {
+            if ((end_mask >> g) & 1ull) {
                 // ---- draw epilogue: fold f_s(x) into the per-point moments and the per-draw sum ----
                 const int s = s0 + draws_done;
                 double dsum = 0.0;
