@@ -11,11 +11,22 @@ namespace bartint {
 // points of one variable -> one 32-bit word of the feature-major code array (the word the table
 // kernel's byte-SIMD compare consumes).  Grid: x over point quads, y over variables.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t bin_one(double x, const double* __restrict__ cuts, int nc) {
-    int lo = 0, len = nc;
+// Guess-and-verify: the answer is ALWAYS decided by comparisons against the real cut values (exact for any ascending
+// cut list); the affine guess only makes the common case two probes on (near-)uniform grids such as dbarts'
+// usequants=FALSE cut points, instead of the 7 dependent probes of a binary search (which made the kernel
+// instruction/shared-memory bound rather than HBM bound).  `cuts` is sentinel padded: cuts[-1] = -inf, cuts[nc] = +inf,
+// so  k is correct  <=>  cuts[k-1] < x  &&  !(cuts[k] < x).
+__device__ __forceinline__ uint32_t bin_one(double x, const double* __restrict__ cuts, int nc, double c0, double inv_step) {
+    const double g = fma(x - c0, inv_step, 1.0);          // uniform grid: #{k : cut[k] < x} = floor((x - c0)/step) + 1
+    int k = __double2int_rd(fmin(fmax(g, 0.0), (double)nc));   // NaN -> fmax/fmin return the non-NaN bound -> 0
+    const bool up = cuts[k] < x, lo_ok = cuts[k - 1] < x;
+    if (lo_ok && !up) return (uint32_t)k;                 // common case: guess was right
+    if (up && !(cuts[k + 1 > nc ? nc : k + 1] < x)) return (uint32_t)(k + 1);
+    if (!lo_ok && k >= 2 && cuts[k - 2] < x) return (uint32_t)(k - 1);
+    int lo = 0, len = nc;                                 // irregular grid / NaN: plain lower-bound search
     while (len > 0) {
         int h = len >> 1;
-        bool r = cuts[lo + h] < x;      // NaN: false -> code 0
+        bool r = cuts[lo + h] < x;
         lo = r ? lo + h + 1 : lo;
         len = r ? len - h - 1 : h;
     }
@@ -26,19 +37,24 @@ __global__ void __launch_bounds__(256) bin_points_kernel(const double* __restric
                                                          const int32_t* __restrict__ cut_off,
                                                          const double* __restrict__ cut_val,
                                                          uint32_t* __restrict__ codes4, int64_t quads_per_row) {
-    __shared__ double s_cut[256];
+    __shared__ double s_cut_pad[258];
+    double* s_cut = s_cut_pad + 1;
     const int j = blockIdx.y;
-    const int c0 = cut_off[j], nc = cut_off[j + 1] - c0;
-    for (int k = threadIdx.x; k < nc; k += blockDim.x) s_cut[k] = cut_val[c0 + k];
+    const int c0i = cut_off[j], nc = cut_off[j + 1] - c0i;
+    for (int k = threadIdx.x; k < nc; k += blockDim.x) s_cut[k] = cut_val[c0i + k];
+    if (threadIdx.x == 0) { s_cut[-1] = -INFINITY; s_cut[nc] = INFINITY; }
     __syncthreads();
+    const double c0 = nc > 0 ? s_cut[0] : 0.0;
+    const double span = nc > 1 ? s_cut[nc - 1] - s_cut[0] : 0.0;
+    const double inv_step = span > 0.0 ? (double)(nc - 1) / span : 0.0;
     const double* __restrict__ col = X + (int64_t)j * ld;
     const bool aligned16 = ((reinterpret_cast<uintptr_t>(col) & 15) == 0);
     for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < quads_per_row;
          w += (int64_t)gridDim.x * blockDim.x) {
         const int64_t i = w * 4;
-        double x0 = 0, x1 = 0, x2 = 0, x3 = 0;
         uint32_t word = 0;
         if (i + 3 < N) {
+            double x0, x1, x2, x3;
             if (aligned16) {
                 double2 a = __ldg(reinterpret_cast<const double2*>(col + i));
                 double2 b = __ldg(reinterpret_cast<const double2*>(col + i + 2));
@@ -46,11 +62,11 @@ __global__ void __launch_bounds__(256) bin_points_kernel(const double* __restric
             } else {
                 x0 = __ldg(col + i); x1 = __ldg(col + i + 1); x2 = __ldg(col + i + 2); x3 = __ldg(col + i + 3);
             }
-            word = bin_one(x0, s_cut, nc) | (bin_one(x1, s_cut, nc) << 8) | (bin_one(x2, s_cut, nc) << 16) |
-                   (bin_one(x3, s_cut, nc) << 24);
+            word = bin_one(x0, s_cut, nc, c0, inv_step) | (bin_one(x1, s_cut, nc, c0, inv_step) << 8) |
+                   (bin_one(x2, s_cut, nc, c0, inv_step) << 16) | (bin_one(x3, s_cut, nc, c0, inv_step) << 24);
         } else {
             for (int k = 0; k < 4; ++k)
-                if (i + k < N) word |= bin_one(__ldg(col + i + k), s_cut, nc) << (8 * k);
+                if (i + k < N) word |= bin_one(__ldg(col + i + k), s_cut, nc, c0, inv_step) << (8 * k);
         }
         codes4[(int64_t)j * quads_per_row + w] = word;   // padding quads (i >= N) are written as 0
     }

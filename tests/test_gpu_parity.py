@@ -283,3 +283,19 @@ def test_dist_wrappers_single_rank(small_case):
     _assert_close(d_res.cpu().numpy(), r0, 1e-13)
     _assert_close(d_ms.cpu().numpy(), [m0, s0], 1e-11)
     pts.close(); f.close()
+
+
+def test_codes_irregular_cut_grid():
+    """K0's affine guess must never change the answer: quantile-like, clustered and duplicated cut points."""
+    rng = np.random.default_rng(9)
+    cuts = [np.sort(rng.beta(0.3, 0.3, 100)), np.sort(np.concatenate([rng.normal(0.2, 1e-3, 60), rng.random(40)])),
+            np.sort(np.repeat(rng.random(25), 4)), np.array([0.5])]
+    ff = synth.forest_from_trees([(j, 0, 0.1, -0.1) for j in range(4)], 1, 4, cuts)
+    X = rng.random((50001, 4))
+    X[:100, 0] = cuts[0]; X[100:200, 1] = cuts[1]; X[200:300, 2] = cuts[2]          # exact ties with every cut
+    X[300:400, 0] = np.nextafter(cuts[0], np.inf); X[400:500, 1] = np.nextafter(cuts[1], -np.inf)
+    X[500] = np.nan; X[501] = np.inf; X[502] = -np.inf; X[503] = 1e300; X[504] = -1e300
+    f = Forest.from_soa(ff)
+    pts = f.points(X)
+    assert np.array_equal(pts.codes().astype(np.int32), onp.bin_points(X, ff.cut_offsets, ff.cut_values))
+    pts.close(); f.close()
