@@ -35,9 +35,10 @@ struct DeviceGuard {
 };
 
 static void free_device(DeviceForest& d) {
-    cudaFree(d.nodes); cudaFree(d.tree_off); cudaFree(d.tree_leaf_off); cudaFree(d.leaf_mu); cudaFree(d.cut_off);
-    cudaFree(d.cut_val); cudaFree(d.node_bit); cudaFree(d.group_tree_off); cudaFree(d.draw_group_off);
-    cudaFree(d.group_rec);
+    void* ptrs[] = {d.nodes, d.tree_off, d.tree_leaf_off, d.leaf_mu, d.cut_off, d.cut_val, d.node_bit, d.group_tree_off,
+                    d.draw_group_off, d.group_rec};
+    for (void* q : ptrs)
+        if (q) cudaFreeAsync(q, nullptr);      // ordered after every kernel already enqueued on the default stream
     d = DeviceForest{};
 }
 
@@ -62,6 +63,7 @@ static int finish_forest(bartint_forest* f, bartint_forest** out) {
     if (rc == BARTINT_OK) {
         cudaError_t e = cudaEventCreate(&f->ev0);
         if (e == cudaSuccess) e = cudaEventCreate(&f->ev1);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&f->ev_last, cudaEventDisableTiming);
         if (e != cudaSuccess) rc = cuda_fail(e, "cudaEventCreate", __FILE__, __LINE__);
     }
     if (rc != BARTINT_OK) {
@@ -179,9 +181,12 @@ void bartint_forest_destroy(bartint_forest* f) {
     if (f == nullptr) return;
     {
         DeviceGuard g(f->device);
+        // the buffers are freed in default-stream order: make that stream wait for evaluations on other streams
+        if (f->ev_last && f->ev_last_set) cudaStreamWaitEvent(nullptr, f->ev_last, 0);
         free_device(f->dev);
         if (f->ev0) cudaEventDestroy(f->ev0);
         if (f->ev1) cudaEventDestroy(f->ev1);
+        if (f->ev_last) cudaEventDestroy(f->ev_last);
         (void)cudaGetLastError();
     }
     delete f;
@@ -226,7 +231,7 @@ int bartint_points_from_host(const bartint_forest* f, const double* X, int64_t N
     DeviceGuard g(f->device);
     double* dX = nullptr;
     const size_t bytes = (size_t)std::max<int64_t>(N * d, 1) * sizeof(double);
-    BI_CUDA(cudaMalloc((void**)&dX, bytes));
+    BI_CUDA(cudaMallocAsync((void**)&dX, bytes, nullptr));
     cudaError_t e = (N * d) ? cudaMemcpy(dX, X, (size_t)(N * d) * sizeof(double), cudaMemcpyHostToDevice) : cudaSuccess;
     int rc = (e == cudaSuccess) ? bartint_points_from_device(f, dX, N, d, N, nullptr, out)
                                 : cuda_fail(e, "cudaMemcpy(X)", __FILE__, __LINE__);
@@ -234,7 +239,7 @@ int bartint_points_from_host(const bartint_forest* f, const double* X, int64_t N
         e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { rc = cuda_fail(e, "bin_points", __FILE__, __LINE__); bartint_points_destroy(*out); *out = nullptr; }
     }
-    cudaFree(dX);
+    cudaFreeAsync(dX, nullptr);
     return rc;
 }
 
@@ -309,6 +314,7 @@ static int eval_core(const bartint_forest* f, const bartint_points* p, uint32_t 
     }
     cudaFreeAsync(draw_part, st);
     if (want_mom && !direct_mom) { cudaFreeAsync(pt_mean, st); cudaFreeAsync(pt_m2, st); }
+    if (cudaEventRecord(f->ev_last, st) == cudaSuccess) f->ev_last_set = true;
     return rc;
 }
 
@@ -362,8 +368,8 @@ int bartint_eval_points(const bartint_forest* f, const bartint_points* p, uint32
     int32_t* d_cnt = nullptr;
     rc = BARTINT_OK;
     auto cleanup = [&]() {
-        cudaFree(d_sum); cudaFree(d_mean); cudaFree(d_m2); cudaFree(d_full); cudaFree(d_out); cudaFree(d_w);
-        cudaFree(d_omean); cudaFree(d_ovar); cudaFree(d_cnt);
+        cudaFreeAsync(d_sum, nullptr); cudaFreeAsync(d_mean, nullptr); cudaFree(d_m2); cudaFreeAsync(d_full, nullptr); cudaFreeAsync(d_out, nullptr); cudaFreeAsync(d_w, nullptr);
+        cudaFreeAsync(d_omean, nullptr); cudaFreeAsync(d_ovar, nullptr); cudaFreeAsync(d_cnt, nullptr);
     };
 #define EP_CUDA(call)                                                             \
     do {                                                                          \
@@ -371,21 +377,21 @@ int bartint_eval_points(const bartint_forest* f, const bartint_points* p, uint32
         if (_e != cudaSuccess) { cleanup(); return cuda_fail(_e, #call, __FILE__, __LINE__); } \
     } while (0)
     const size_t nb_draw = sizeof(double) * (size_t)std::max(ndraws, 1), nb_pt = sizeof(double) * (size_t)std::max<int64_t>(N, 1);
-    EP_CUDA(cudaMalloc((void**)&d_sum, nb_draw));
-    EP_CUDA(cudaMalloc((void**)&d_out, nb_draw));
+    EP_CUDA(cudaMallocAsync((void**)&d_sum, nb_draw, nullptr));
+    EP_CUDA(cudaMallocAsync((void**)&d_out, nb_draw, nullptr));
     if (want_mom) {
-        EP_CUDA(cudaMalloc((void**)&d_mean, nb_pt));
-        EP_CUDA(cudaMalloc((void**)&d_m2, nb_pt));
-        EP_CUDA(cudaMalloc((void**)&d_omean, nb_pt));
-        EP_CUDA(cudaMalloc((void**)&d_ovar, nb_pt));
-        EP_CUDA(cudaMalloc((void**)&d_cnt, sizeof(int32_t)));
+        EP_CUDA(cudaMallocAsync((void**)&d_mean, nb_pt, nullptr));
+        EP_CUDA(cudaMallocAsync((void**)&d_m2, nb_pt, nullptr));
+        EP_CUDA(cudaMallocAsync((void**)&d_omean, nb_pt, nullptr));
+        EP_CUDA(cudaMallocAsync((void**)&d_ovar, nb_pt, nullptr));
+        EP_CUDA(cudaMallocAsync((void**)&d_cnt, sizeof(int32_t), nullptr));
         if (weights != nullptr) {
-            EP_CUDA(cudaMalloc((void**)&d_w, sizeof(double) * (size_t)weights_len));
+            EP_CUDA(cudaMallocAsync((void**)&d_w, sizeof(double) * (size_t)weights_len, nullptr));
             EP_CUDA(cudaMemcpy(d_w, weights, sizeof(double) * (size_t)weights_len, cudaMemcpyHostToDevice));
         }
     }
     if (full_pred != nullptr && (int64_t)ndraws * N > 0)
-        EP_CUDA(cudaMalloc((void**)&d_full, sizeof(double) * (size_t)ndraws * (size_t)N));
+        EP_CUDA(cudaMallocAsync((void**)&d_full, sizeof(double) * (size_t)ndraws * (size_t)N, nullptr));
     rc = eval_core(f, p, flags, draw_begin, draw_end, d_sum, want_mom ? d_mean : nullptr, want_mom ? d_m2 : nullptr,
                    nullptr, d_full, scale, y0, scaled, st);
     if (rc == BARTINT_OK && draw_mean != nullptr && ndraws > 0)
@@ -434,7 +440,7 @@ int bartint_leaf_indices(const bartint_forest* f, const bartint_points* p, int32
                "the table kernel does not apply to this forest (deep trees, > 127 cuts or too many variables)");
     DeviceGuard g(f->device);
     int32_t* d_leaf = nullptr;
-    BI_CUDA(cudaMalloc((void**)&d_leaf, sizeof(int32_t) * (size_t)total));
+    BI_CUDA(cudaMallocAsync((void**)&d_leaf, sizeof(int32_t) * (size_t)total, nullptr));
     if (use_table_kernel) {
         rc = launch_table_leaf(f, p, draw_begin, draw_end, d_leaf, nullptr);
     } else {
@@ -447,7 +453,7 @@ int bartint_leaf_indices(const bartint_forest* f, const bartint_points* p, int32
         e = cudaMemcpy(out, d_leaf, sizeof(int32_t) * (size_t)total, cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemcpy(leaf)", __FILE__, __LINE__);
     }
-    cudaFree(d_leaf);
+    cudaFreeAsync(d_leaf, nullptr);
     return rc;
 }
 
@@ -504,8 +510,8 @@ int bartint_exact_integrals(const bartint_forest* f, int32_t measure, const doub
         box[(size_t)d + j] = hi ? hi[j] : (measure == BARTINT_MEASURE_EXPONENTIAL ? INFINITY : 1.0);   // :153-155
     }
     double *d_box = nullptr, *d_out = nullptr;
-    BI_CUDA(cudaMalloc((void**)&d_box, sizeof(double) * box.size()));
-    cudaError_t e = cudaMalloc((void**)&d_out, sizeof(double) * (size_t)n_draws);
+    BI_CUDA(cudaMallocAsync((void**)&d_box, sizeof(double) * box.size(), nullptr));
+    cudaError_t e = cudaMallocAsync((void**)&d_out, sizeof(double) * (size_t)n_draws, nullptr);
     if (e == cudaSuccess) e = cudaMemcpy(d_box, box.data(), sizeof(double) * box.size(), cudaMemcpyHostToDevice);
     int rc = e == cudaSuccess ? launch_exact_integrals(f, measure, d_box, d_box + d, n_draws, d_out, nullptr)
                               : cuda_fail(e, "exact_integrals setup", __FILE__, __LINE__);
@@ -513,8 +519,8 @@ int bartint_exact_integrals(const bartint_forest* f, int32_t measure, const doub
         e = cudaMemcpy(out, d_out, sizeof(double) * (size_t)n_draws, cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) rc = cuda_fail(e, "exact_integrals", __FILE__, __LINE__);
     }
-    cudaFree(d_box);
-    cudaFree(d_out);
+    cudaFreeAsync(d_box, nullptr);
+    cudaFreeAsync(d_out, nullptr);
     return rc;
 }
 
@@ -529,7 +535,7 @@ int bartint_finalize_integrals(const bartint_forest* f, const double* integrals_
     BI_REQUIRE(integrals_scaled != nullptr, BARTINT_ERR_ARG, "integrals is NULL");
     DeviceGuard g(f->device);
     double *d_in = nullptr, *d_res = nullptr, *d_ms = nullptr;
-    BI_CUDA(cudaMalloc((void**)&d_in, sizeof(double) * (size_t)(2 * n + 2)));
+    BI_CUDA(cudaMallocAsync((void**)&d_in, sizeof(double) * (size_t)(2 * n + 2), nullptr));
     d_res = d_in + n;
     d_ms = d_res + n;
     cudaError_t e = cudaMemcpy(d_in, integrals_scaled, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice);
@@ -541,7 +547,7 @@ int bartint_finalize_integrals(const bartint_forest* f, const double* integrals_
         if (e == cudaSuccess && rescaled_out) e = cudaMemcpy(rescaled_out, d_res, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) rc = cuda_fail(e, "finalize_integrals", __FILE__, __LINE__);
     }
-    cudaFree(d_in);
+    cudaFreeAsync(d_in, nullptr);
     if (rc == BARTINT_OK) { if (mean_out) *mean_out = ms[0]; if (sd_out) *sd_out = ms[1]; }
     return rc;
 }

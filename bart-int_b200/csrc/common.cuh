@@ -94,6 +94,8 @@ struct bartint_forest {
     bartint::DeviceForest dev;
     // profile of the last evaluation
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev_last = nullptr;     // end of the last evaluation enqueued on a caller stream (ordering for destroy)
+    mutable bool ev_last_set = false;
     mutable int last_launches = 0;
     mutable int last_used_table = 0;
     mutable bool last_timed = false;

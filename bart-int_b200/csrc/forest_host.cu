@@ -44,10 +44,6 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
 // Accepts any run of spaces between tokens (the reference tokeniser inserts one after every '.').
 // Appends the tree's nodes in pre-order; child indices are relative to the tree's first node.
 // ---------------------------------------------------------------------------------------------
-struct TreeBuf {
-    std::vector<int32_t> var, cut, left, right;
-};
-
 static bool parse_int(const char*& p, int32_t& out) {
     while (*p == ' ') ++p;
     if (*p < '0' || *p > '9') return false;
@@ -61,26 +57,28 @@ static bool parse_int(const char*& p, int32_t& out) {
     return true;
 }
 
-static int parse_tree_string(const char* s, TreeBuf& t) {
-    t.var.clear(); t.cut.clear(); t.left.clear(); t.right.clear();
+// Parses one tree string straight into the SoA slices of its tree (capacity `cap` nodes, known from the count of
+// '.' characters).  `pending` is a scratch stack of internal nodes still waiting for their right child.
+static int parse_tree_string(const char* s, int32_t cap, int32_t* var, int32_t* cut, int32_t* left, int32_t* right,
+                             std::vector<int32_t>& pending) {
     const char* p = s;
-    // explicit stack of internal nodes still waiting for their right child
-    std::vector<int32_t> pending;
+    pending.clear();
+    int32_t n = 0;
     bool done = false;
     while (!done) {
         while (*p == ' ') ++p;
-        if (*p == '\0') return BARTINT_ERR_PARSE;
-        int32_t me = (int32_t)t.var.size();
+        if (*p == '\0' || n >= cap) return BARTINT_ERR_PARSE;
+        const int32_t me = n++;
         if (*p == '.') {
             ++p;
-            t.var.push_back(-1); t.cut.push_back(0); t.left.push_back(-1); t.right.push_back(-1);
-            // a finished subtree: it is the left child of the node above (already linked as me = parent+1)
-            // or the right child of the innermost pending node
+            var[me] = -1; cut[me] = 0; left[me] = -1; right[me] = -1;
+            // a finished subtree: the left child of the node above (already linked as parent+1), or the right child of
+            // the innermost pending node
             while (true) {
                 if (pending.empty()) { done = true; break; }
-                int32_t par = pending.back();
-                if (t.right[par] == -2) {          // left subtree just completed -> next node is its right child
-                    t.right[par] = (int32_t)t.var.size();
+                const int32_t par = pending.back();
+                if (right[par] == -2) {            // left subtree just completed -> the next node is its right child
+                    right[par] = n;
                     break;
                 }
                 pending.pop_back();                // right subtree completed -> this node is complete too
@@ -88,14 +86,13 @@ static int parse_tree_string(const char* s, TreeBuf& t) {
         } else {
             int32_t v, c;
             if (!parse_int(p, v) || !parse_int(p, c)) return BARTINT_ERR_PARSE;
-            t.var.push_back(v); t.cut.push_back(c);
-            t.left.push_back(me + 1);
-            t.right.push_back(-2);                 // -2: waiting for the left subtree to finish
+            var[me] = v; cut[me] = c; left[me] = me + 1;
+            right[me] = -2;                        // -2: waiting for the left subtree to finish
             pending.push_back(me);
         }
     }
     while (*p == ' ') ++p;
-    if (*p != '\0') return BARTINT_ERR_PARSE;     // tree$remainder must be empty
+    if (*p != '\0' || n != cap) return BARTINT_ERR_PARSE;     // tree$remainder must be empty
     return BARTINT_OK;
 }
 
@@ -115,61 +112,82 @@ int parse_dbarts_forest(const char* const* tree_strings, const double* tree_fits
                         int64_t n, int32_t d, const int32_t* cut_offsets, const double* cut_values,
                         int32_t m, int32_t S, bartint_forest* f) {
     const int64_t n_trees = (int64_t)S * m;
-    std::vector<TreeBuf> trees((size_t)n_trees);
-    int status = BARTINT_OK;
+    // pass 1: a tree with K leaves ('.' characters) has 2K-1 nodes -> node offsets by prefix sum
+    f->tree_off.assign((size_t)n_trees + 1, 0);
     int64_t bad_tree = -1;
 #pragma omp parallel for schedule(static)
     for (int64_t k = 0; k < n_trees; ++k) {
-        if (tree_strings[k] == nullptr || parse_tree_string(tree_strings[k], trees[(size_t)k]) != BARTINT_OK) {
+        int64_t dots = 0;
+        if (tree_strings[k] != nullptr)
+            for (const char* p = tree_strings[k]; *p; ++p) dots += (*p == '.');
+        if (dots == 0) {
 #pragma omp critical
-            { status = BARTINT_ERR_PARSE; bad_tree = k; }
+            bad_tree = k;
         }
+        f->tree_off[(size_t)k + 1] = 2 * dots - 1;
     }
-    if (status != BARTINT_OK) {
-        set_error("malformed dbarts tree string at tree %lld (draw %lld)", (long long)(bad_tree % m),
-                  (long long)(bad_tree / m));
-        return status;
-    }
+    if (bad_tree < 0)
+        for (int64_t k = 0; k < n_trees; ++k) f->tree_off[(size_t)k + 1] += f->tree_off[(size_t)k];
     // integer cut map of the training matrix (dbarts keeps x as cut indices internally)
     std::vector<int32_t> codes((size_t)(n * d));
+#pragma omp parallel for schedule(static)
     for (int32_t j = 0; j < d; ++j) {
         const double* cuts = cut_values + cut_offsets[j];
-        int nc = cut_offsets[j + 1] - cut_offsets[j];
+        const int nc = cut_offsets[j + 1] - cut_offsets[j];
         for (int64_t i = 0; i < n; ++i) codes[(size_t)(j * n + i)] = bin_value(x_train[j * n + i], cuts, nc);
     }
-    f->tree_off.assign((size_t)n_trees + 1, 0);
-    for (int64_t k = 0; k < n_trees; ++k) f->tree_off[(size_t)k + 1] = f->tree_off[(size_t)k] + (int64_t)trees[(size_t)k].var.size();
-    const int64_t nn = f->tree_off[(size_t)n_trees];
+    const int64_t nn = bad_tree < 0 ? f->tree_off[(size_t)n_trees] : 0;
     f->var.resize((size_t)nn); f->cut.resize((size_t)nn); f->left.resize((size_t)nn); f->right.resize((size_t)nn);
-    f->mu.assign((size_t)nn, 0.0);
-    int bad = 0;
-#pragma omp parallel for schedule(static)
-    for (int64_t k = 0; k < n_trees; ++k) {
-        const TreeBuf& t = trees[(size_t)k];
-        const int64_t base = f->tree_off[(size_t)k];
-        const int32_t cnt = (int32_t)t.var.size();
-        int32_t n_leaf = 0;
-        for (int32_t a = 0; a < cnt; ++a) {
-            f->var[(size_t)(base + a)] = t.var[a]; f->cut[(size_t)(base + a)] = t.cut[a];
-            f->left[(size_t)(base + a)] = t.left[a]; f->right[(size_t)(base + a)] = t.right[a];
-            if (t.var[a] < 0) { ++n_leaf; f->mu[(size_t)(base + a)] = std::numeric_limits<double>::quiet_NaN(); }
-            else if (t.var[a] >= d || t.cut[a] >= cut_offsets[t.var[a] + 1] - cut_offsets[t.var[a]]) {
+    f->mu.resize((size_t)nn);
+    int bad_ref = 0;
+    // pass 2: parse in place, then recover the leaf values
+#pragma omp parallel
+    {
+        std::vector<int32_t> pending;
+        std::vector<char> have;
+#pragma omp for schedule(static)
+        for (int64_t k = 0; k < n_trees; ++k) {
+            if (bad_tree >= 0) continue;
+            const int64_t base = f->tree_off[(size_t)k];
+            const int32_t cnt = (int32_t)(f->tree_off[(size_t)k + 1] - base);
+            int32_t* var = f->var.data() + base;
+            int32_t* cut = f->cut.data() + base;
+            int32_t* left = f->left.data() + base;
+            int32_t* right = f->right.data() + base;
+            double* mu = f->mu.data() + base;
+            if (parse_tree_string(tree_strings[k], cnt, var, cut, left, right, pending) != BARTINT_OK) {
+#pragma omp critical
+                bad_tree = k;
+                continue;
+            }
+            bool ok = true;
+            for (int32_t a = 0; a < cnt; ++a) {
+                mu[a] = var[a] < 0 ? std::numeric_limits<double>::quiet_NaN() : 0.0;
+                if (var[a] >= 0 && (var[a] >= d || cut[a] >= cut_offsets[var[a] + 1] - cut_offsets[var[a]])) ok = false;
+            }
+            if (!ok) {
 #pragma omp atomic write
-                bad = 1;
+                bad_ref = 1;
+                continue;
+            }
+            // leaf mu = fit of the first training row routed to the leaf (fillPlotInfoForNode, BARTInt.R:125)
+            const double* fits = tree_fits + (size_t)k * (size_t)n;   // [obs, tree, sample] column-major
+            const int32_t n_leaf = (cnt + 1) / 2;
+            have.assign((size_t)cnt, 0);
+            int32_t found = 0;
+            for (int64_t i = 0; i < n && found < n_leaf; ++i) {
+                int32_t a = 0;
+                while (var[a] >= 0) a = (codes[(size_t)(var[a] * n + i)] > cut[a]) ? right[a] : left[a];
+                if (!have[(size_t)a]) { mu[a] = fits[i]; have[(size_t)a] = 1; ++found; }
             }
         }
-        if (bad) continue;
-        // leaf mu = fit of the first training row routed to the leaf (fillPlotInfoForNode)
-        const double* fits = tree_fits + (size_t)k * (size_t)n;   // [obs, tree, sample] column-major
-        int32_t found = 0;
-        std::vector<char> have((size_t)cnt, 0);
-        for (int64_t i = 0; i < n && found < n_leaf; ++i) {
-            int32_t a = 0;
-            while (t.var[a] >= 0) a = (codes[(size_t)(t.var[a] * n + i)] > t.cut[a]) ? t.right[a] : t.left[a];
-            if (!have[(size_t)a]) { f->mu[(size_t)(base + a)] = fits[i]; have[(size_t)a] = 1; ++found; }
-        }
     }
-    if (bad) {
+    if (bad_tree >= 0) {
+        set_error("malformed dbarts tree string at tree %lld (draw %lld)", (long long)(bad_tree % m),
+                  (long long)(bad_tree / m));
+        return BARTINT_ERR_PARSE;
+    }
+    if (bad_ref) {
         set_error("tree string references a variable or cut index outside the cut-point table");
         return BARTINT_ERR_PARSE;
     }
@@ -275,8 +293,9 @@ int forest_finish_host(bartint_forest* f) {
 template <typename T>
 static int upload(T** dptr, const std::vector<T>& h) {
     size_t bytes = std::max<size_t>(h.size(), 1) * sizeof(T);
-    BI_CUDA(cudaMalloc((void**)dptr, bytes));
-    if (!h.empty()) BI_CUDA(cudaMemcpy(*dptr, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    // stream-ordered allocator on the default stream: cached blocks make a per-step forest rebuild cheap
+    BI_CUDA(cudaMallocAsync((void**)dptr, bytes, nullptr));
+    if (!h.empty()) BI_CUDA(cudaMemcpyAsync(*dptr, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, nullptr));
     return BARTINT_OK;
 }
 
@@ -328,7 +347,10 @@ int forest_upload(bartint_forest* f) {
     // the table kernel needs 7-bit codes (byte-SIMD compare) and the code rows of one CTA tile in shared memory
     f->table_ok = n_trees > 0 && f->max_cuts <= 127 && (int64_t)f->d * TK_TILE_MIN <= 160 * 1024;
     f->n_groups = 0;
-    if (!f->table_ok) return BARTINT_OK;
+    if (!f->table_ok) {
+        BI_CUDA(cudaStreamSynchronize(nullptr));
+        return BARTINT_OK;
+    }
     const int NB = f->nb;
     std::vector<int32_t> group_tree_off;   // first tree of each group
     std::vector<uint32_t> hdr;             // flags per group
@@ -394,15 +416,15 @@ int forest_upload(bartint_forest* f) {
     if ((rc = upload(&f->dev.node_bit, node_bit))) return rc;
     if ((rc = upload(&f->dev.group_tree_off, group_tree_off))) return rc;
     if ((rc = upload(&f->dev.draw_group_off, f->draw_group_off))) return rc;
-    BI_CUDA(cudaMalloc((void**)&f->dev.group_rec, (size_t)f->n_groups * (size_t)tk_rec_bytes(NB) + 16));
+    BI_CUDA(cudaMallocAsync((void**)&f->dev.group_rec, (size_t)f->n_groups * (size_t)tk_rec_bytes(NB) + 16, nullptr));
     uint2* d_desc = nullptr;
     uint32_t* d_hdr = nullptr;
     if ((rc = upload(&d_desc, desc))) return rc;
-    if ((rc = upload(&d_hdr, hdr))) { cudaFree(d_desc); return rc; }
+    if ((rc = upload(&d_hdr, hdr))) { cudaFreeAsync(d_desc, nullptr); return rc; }
     rc = launch_build_tables(f, d_desc, d_hdr, 0);
-    cudaError_t e = cudaDeviceSynchronize();
-    cudaFree(d_desc);
-    cudaFree(d_hdr);
+    cudaFreeAsync(d_desc, nullptr);
+    cudaFreeAsync(d_hdr, nullptr);
+    cudaError_t e = cudaStreamSynchronize(nullptr);   // host vectors (pageable) must outlive the copies; surface build errors here
     if (rc) return rc;
     BI_CUDA(e);
     return BARTINT_OK;
