@@ -55,7 +55,7 @@ SIGNATURES = {
     "bartint_finalize_draws_device": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p,
                                                 C.c_void_p, C.c_void_p]),
     "bartint_finalize_integrals": (C.c_int, [C.c_void_p, c_double_p, C.c_int32, c_double_p, c_double_p, c_double_p]),
-    "bartint_last_eval_profile": (C.c_int, [C.c_void_p, c_float_p, c_int32_p, c_int32_p]),
+    "bartint_last_eval_profile": (C.c_int, [C.c_void_p, C.c_int32, c_float_p, c_int32_p, c_int32_p]),
     "bartint_kernel_launch_count": (C.c_int64, []),
 }
 

@@ -61,8 +61,11 @@ static int finish_forest(bartint_forest* f, bartint_forest** out) {
         rc = forest_upload(f);
     }
     if (rc == BARTINT_OK) {
-        cudaError_t e = cudaEventCreate(&f->ev0);
-        if (e == cudaSuccess) e = cudaEventCreate(&f->ev1);
+        cudaError_t e = cudaSuccess;
+        for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
+            e = cudaEventCreate(&f->ev0[k]);
+            if (e == cudaSuccess) e = cudaEventCreate(&f->ev1[k]);
+        }
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&f->ev_last, cudaEventDisableTiming);
         if (e != cudaSuccess) rc = cuda_fail(e, "cudaEventCreate", __FILE__, __LINE__);
     }
@@ -184,8 +187,10 @@ void bartint_forest_destroy(bartint_forest* f) {
         // the buffers are freed in default-stream order: make that stream wait for evaluations on other streams
         if (f->ev_last && f->ev_last_set) cudaStreamWaitEvent(nullptr, f->ev_last, 0);
         free_device(f->dev);
-        if (f->ev0) cudaEventDestroy(f->ev0);
-        if (f->ev1) cudaEventDestroy(f->ev1);
+        for (int k = 0; k < 2; ++k) {
+            if (f->ev0[k]) cudaEventDestroy(f->ev0[k]);
+            if (f->ev1[k]) cudaEventDestroy(f->ev1[k]);
+        }
         if (f->ev_last) cudaEventDestroy(f->ev_last);
         (void)cudaGetLastError();
     }
@@ -279,13 +284,14 @@ static int eval_core(const bartint_forest* f, const bartint_points* p, uint32_t 
                      int32_t draw_end, double* d_draw_sum, double* d_point_mean, double* d_point_m2,
                      int32_t* d_leaf, double* d_full, double fp_scale, double fp_y0, int fp_scaled, cudaStream_t st) {
     const int ndraws = draw_end - draw_begin;
-    f->last_launches = 0;
-    f->last_timed = false;
+    const int slot = (d_point_mean != nullptr || d_full != nullptr || d_leaf != nullptr) ? 1 : 0;
+    f->last_launches[slot] = 0;
+    f->last_timed[slot] = false;
     if (ndraws == 0) return BARTINT_OK;
     const bool want_mom = d_point_mean != nullptr && d_point_m2 != nullptr;
     if (d_leaf != nullptr) flags |= BARTINT_FORCE_WALK;
     EvalPlan plan = make_plan(f, p, flags, draw_begin, draw_end, want_mom, d_full != nullptr);
-    f->last_used_table = plan.use_table ? 1 : 0;
+    f->last_used_table[slot] = plan.use_table ? 1 : 0;
     double *draw_part = nullptr, *pt_mean = nullptr, *pt_m2 = nullptr;
     BI_CUDA(cudaMallocAsync((void**)&draw_part, sizeof(double) * (size_t)plan.n_tiles * (size_t)ndraws, st));
     const bool direct_mom = want_mom && plan.n_chunks == 1;   // single chunk: the kernel writes the final moments
@@ -297,20 +303,20 @@ static int eval_core(const bartint_forest* f, const bartint_points* p, uint32_t 
             BI_CUDA(cudaMallocAsync((void**)&pt_m2, bytes, st));
         }
     }
-    BI_CUDA(cudaEventRecord(f->ev0, st));
+    BI_CUDA(cudaEventRecord(f->ev0[slot], st));
     int rc = plan.use_table ? launch_eval_table(f, p, plan, draw_part, pt_mean, pt_m2, d_full, fp_scale, fp_y0, fp_scaled, st)
                             : launch_eval_walk(f, p, plan, draw_part, pt_mean, pt_m2, d_leaf, d_full, fp_scale, fp_y0, fp_scaled, st);
-    BI_CUDA(cudaEventRecord(f->ev1, st));
-    f->last_timed = true;
-    f->last_launches = 1;
+    BI_CUDA(cudaEventRecord(f->ev1[slot], st));
+    f->last_timed[slot] = true;
+    f->last_launches[slot] = 1;
     if (rc == BARTINT_OK && d_draw_sum != nullptr) {
         rc = launch_reduce_draw_parts(draw_part, plan.n_tiles, ndraws, d_draw_sum, st);
-        f->last_launches++;
+        f->last_launches[slot]++;
     }
     if (rc == BARTINT_OK && want_mom && !direct_mom) {
         rc = launch_merge_point_parts(pt_mean, pt_m2, plan.n_chunks, plan.chunk_draws, ndraws, p->N, d_point_mean,
                                       d_point_m2, st);
-        f->last_launches++;
+        f->last_launches[slot]++;
     }
     cudaFreeAsync(draw_part, st);
     if (want_mom && !direct_mom) { cudaFreeAsync(pt_mean, st); cudaFreeAsync(pt_m2, st); }
@@ -552,16 +558,18 @@ int bartint_finalize_integrals(const bartint_forest* f, const double* integrals_
     return rc;
 }
 
-int bartint_last_eval_profile(const bartint_forest* f, float* kernel_ms, int32_t* n_launches, int32_t* used_table_kernel) {
+int bartint_last_eval_profile(const bartint_forest* f, int32_t with_moments, float* kernel_ms, int32_t* n_launches,
+                              int32_t* used_table_kernel) {
     BI_REQUIRE(f != nullptr, BARTINT_ERR_ARG, "forest is NULL");
-    if (n_launches) *n_launches = f->last_launches;
-    if (used_table_kernel) *used_table_kernel = f->last_used_table;
+    const int slot = with_moments ? 1 : 0;
+    if (n_launches) *n_launches = f->last_launches[slot];
+    if (used_table_kernel) *used_table_kernel = f->last_used_table[slot];
     if (kernel_ms) {
         *kernel_ms = 0.f;
-        if (f->last_timed) {
+        if (f->last_timed[slot]) {
             DeviceGuard g(f->device);
-            BI_CUDA(cudaEventSynchronize(f->ev1));
-            BI_CUDA(cudaEventElapsedTime(kernel_ms, f->ev0, f->ev1));
+            BI_CUDA(cudaEventSynchronize(f->ev1[slot]));
+            BI_CUDA(cudaEventElapsedTime(kernel_ms, f->ev0[slot], f->ev1[slot]));
         }
     }
     return BARTINT_OK;

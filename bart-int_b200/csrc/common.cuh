@@ -93,12 +93,13 @@ struct bartint_forest {
     std::vector<int32_t> draw_group_off;  // host copy, S+1
     bartint::DeviceForest dev;
     // profile of the last evaluation
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // slot 0: evaluations producing per-draw sums only; slot 1: evaluations with per-point moments / full output
+    cudaEvent_t ev0[2] = {nullptr, nullptr}, ev1[2] = {nullptr, nullptr};
     cudaEvent_t ev_last = nullptr;     // end of the last evaluation enqueued on a caller stream (ordering for destroy)
     mutable bool ev_last_set = false;
-    mutable int last_launches = 0;
-    mutable int last_used_table = 0;
-    mutable bool last_timed = false;
+    mutable int last_launches[2] = {0, 0};
+    mutable int last_used_table[2] = {0, 0};
+    mutable bool last_timed[2] = {false, false};
 };
 
 struct bartint_points {

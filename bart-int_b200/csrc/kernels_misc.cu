@@ -141,18 +141,29 @@ int launch_build_tables(const bartint_forest* f, const uint2* d_desc, const uint
 // ---------------------------------------------------------------------------------------------
 // K3  deterministic second-stage reductions (fixed summation order, no floating-point atomics)
 // ---------------------------------------------------------------------------------------------
-__global__ void reduce_draw_parts_kernel(const double* __restrict__ part, int n_tiles, int ndraws,
-                                         double* __restrict__ out) {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= ndraws) return;
+// CTA = 32 draws x 8 tile slices: slice y adds tiles y, y+8, ... (independent loads in flight), then the 8 slice
+// sums are added in slice order.  The summation tree depends only on (n_tiles), never on the launch shape.
+__global__ void __launch_bounds__(256) reduce_draw_parts_kernel(const double* __restrict__ part, int n_tiles, int ndraws,
+                                                                double* __restrict__ out) {
+    __shared__ double s_part[8][33];
+    const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
+    const int s = blockIdx.x * 32 + x;
     double acc = 0.0;
-    for (int t = 0; t < n_tiles; ++t) acc += part[(int64_t)t * ndraws + s];
-    out[s] = acc;
+    if (s < ndraws)
+        for (int t = y; t < n_tiles; t += 8) acc += part[(int64_t)t * ndraws + s];
+    s_part[y][x] = acc;
+    __syncthreads();
+    if (y == 0 && s < ndraws) {
+        double tot = s_part[0][x];
+#pragma unroll
+        for (int k = 1; k < 8; ++k) tot += s_part[k][x];
+        out[s] = tot;
+    }
 }
 
 int launch_reduce_draw_parts(const double* draw_part, int n_tiles, int ndraws, double* draw_sum, cudaStream_t st) {
     if (ndraws == 0) return BARTINT_OK;
-    reduce_draw_parts_kernel<<<(ndraws + 127) / 128, 128, 0, st>>>(draw_part, n_tiles, ndraws, draw_sum);
+    reduce_draw_parts_kernel<<<(ndraws + 31) / 32, 256, 0, st>>>(draw_part, n_tiles, ndraws, draw_sum);
     count_launch();
     BI_CUDA(cudaGetLastError());
     return BARTINT_OK;

@@ -51,19 +51,30 @@ def ordered_sum(rows: torch.Tensor) -> torch.Tensor:
     return acc
 
 
-def allreduce_draw_sums(local_sums: torch.Tensor, n_local: int, group=None) -> tuple[torch.Tensor, int]:
-    """Point-sharded exchange: per-draw sums of every rank's points -> (total sums, total point count)."""
+def allreduce_draw_sums(local_sums: torch.Tensor, n_local: int, group=None, n_total: int | None = None):
+    """Point-sharded exchange: per-draw sums of every rank's points -> (total sums, total point count).
+
+    Pass n_total when the caller knows the global point count: gathering it costs a device->host sync, which would
+    stall the launch queue behind the evaluation kernel."""
     rows = all_gather_rows(local_sums, group)
-    counts = all_gather_rows(torch.tensor([n_local], dtype=torch.int64, device=local_sums.device), group)
-    return ordered_sum(rows), int(counts.sum().item())
+    if n_total is None:
+        rank, world = world_info(group)
+        if world == 1:
+            n_total = n_local
+        else:
+            counts = all_gather_rows(torch.tensor([n_local], dtype=torch.int64, device=local_sums.device), group)
+            n_total = int(counts.sum().item())
+    return (ordered_sum(rows) if rows.shape[0] > 1 else rows[0]), n_total
 
 
-def gather_moments(local_mean: torch.Tensor, local_m2: torch.Tensor, n_local_draws: int, group=None):
+def gather_moments(local_mean: torch.Tensor, local_m2: torch.Tensor, n_local_draws: int, group=None, counts=None):
     """Draw-sharded exchange: (draw counts per rank, means [world, C], M2s [world, C])."""
     means = all_gather_rows(local_mean, group)
     m2s = all_gather_rows(local_m2, group)
-    counts = all_gather_rows(torch.tensor([n_local_draws], dtype=torch.int32, device=local_mean.device), group)
-    return counts.flatten().cpu().numpy().astype(np.int32), means, m2s
+    if counts is None:
+        c = all_gather_rows(torch.tensor([n_local_draws], dtype=torch.int32, device=local_mean.device), group)
+        counts = c.flatten().cpu().numpy().astype(np.int32)          # device->host sync; pass counts to avoid it
+    return np.asarray(counts, np.int32), means, m2s
 
 
 def chan_merge_np(counts, means, m2s):
@@ -89,13 +100,13 @@ def chan_merge_np(counts, means, m2s):
 # ---------------------------------------------------------------------------------------------
 # production wrappers (CUDA tensors + libbartint_cuda)
 # ---------------------------------------------------------------------------------------------
-def point_sharded_draw_means(forest, pts_local, group=None, scaled=False, stream=None):
+def point_sharded_draw_means(forest, pts_local, group=None, scaled=False, stream=None, n_total=None):
     """rowMeans(predict(model, X)) with X's rows sharded across ranks.  Returns (draw_mean[S], mean_var[2]) on device."""
     dev = torch.device("cuda", torch.cuda.current_device())
     st = torch.cuda.current_stream().cuda_stream if stream is None else stream
     sums = torch.empty(forest.S, dtype=torch.float64, device=dev)
     forest.eval_device(pts_local, d_draw_sum=sums.data_ptr(), stream=st)
-    total, n_total = allreduce_draw_sums(sums, pts_local.N, group)
+    total, n_total = allreduce_draw_sums(sums, pts_local.N, group, n_total)
     out = torch.empty(forest.S, dtype=torch.float64, device=dev)
     mv = torch.empty(2, dtype=torch.float64, device=dev)
     forest.finalize_draws_device(total.data_ptr(), forest.S, n_total, out.data_ptr(), mv.data_ptr(), scaled=scaled, stream=st)
@@ -113,7 +124,8 @@ def draw_sharded_candidate_var(forest, pts, weights=None, group=None, scaled=Fal
     m2 = torch.zeros(pts.N, dtype=torch.float64, device=dev)
     if hi > lo:
         forest.eval_device(pts, d_point_mean=mean.data_ptr(), d_point_m2=m2.data_ptr(), draws=(lo, hi), stream=st)
-    counts, means, m2s = gather_moments(mean, m2, hi - lo, group)
+    shard_counts = [shard_range(forest.S, world, r)[1] - shard_range(forest.S, world, r)[0] for r in range(world)]
+    counts, means, m2s = gather_moments(mean, m2, hi - lo, group, counts=shard_counts)
     var = torch.empty(pts.N, dtype=torch.float64, device=dev)
     w_ptr, w_len = (0, 0) if weights is None else (weights.data_ptr(), weights.numel())
     forest.merge_moments_device(counts, means.data_ptr(), m2s.data_ptr(), pts.N, w_ptr, w_len, 0, var.data_ptr(),

@@ -304,9 +304,10 @@ class Forest:
             self._h, _lib.MEASURES[measure], None, None, int(n_draws_used or 0), C.c_void_p(d_out),
             C.c_void_p(d_rescaled or None), C.c_void_p(d_mean_sd or None), C.c_void_p(stream)))
 
-    def last_eval_profile(self) -> dict:
+    def last_eval_profile(self, with_moments: bool = False) -> dict:
+        """Timing of the last evaluation of the given kind (per-draw sums only / with per-point outputs)."""
         ms, nl, tk = C.c_float(), C.c_int32(), C.c_int32()
-        _check(_lib.load().bartint_last_eval_profile(self._h, C.byref(ms), C.byref(nl), C.byref(tk)))
+        _check(_lib.load().bartint_last_eval_profile(self._h, int(with_moments), C.byref(ms), C.byref(nl), C.byref(tk)))
         return {"kernel_ms": ms.value, "launches": nl.value, "table_kernel": bool(tk.value)}
 
     def leaf_indices(self, pts, draws=None, use_table_kernel=False) -> np.ndarray:

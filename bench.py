@@ -188,15 +188,24 @@ def run_ours(args):
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
     results = {}
 
+    side = torch.cuda.Stream(device=dev)
+    main = torch.cuda.current_stream()
+
     def step(i):
         f = forests[i % len(forests)]
-        f.exact_integrals_device(d_int.data_ptr(), "uniform", d_rescaled=d_int_res.data_ptr(),
-                                 d_mean_sd=d_int_ms.data_ptr(), stream=st)                       # sampleIntegrals + :260-262
-        pc = f.points_from_device(dXc.data_ptr(), C, stream=st)
-        var = bdist.draw_sharded_candidate_var(f, pc, None, stream=st)                             # :312-314
+        # the large MC evaluation is enqueued first; the small chains (exact integral; candidates) follow on a side
+        # stream so neither their kernels nor their host-side launch work sit in front of it
+        side.wait_stream(main)
         pm = f.points_from_device(dX.data_ptr(), N, stream=st)
-        dm, mv = bdist.point_sharded_draw_means(f, pm, stream=st)                                  # bartMean.R:74-82
-        pc.close(); pm.close()
+        dm, mv = bdist.point_sharded_draw_means(f, pm, stream=st, n_total=n_total)                                  # bartMean.R:74-82
+        pm.close()
+        with torch.cuda.stream(side):
+            f.exact_integrals_device(d_int.data_ptr(), "uniform", d_rescaled=d_int_res.data_ptr(),
+                                     d_mean_sd=d_int_ms.data_ptr(), stream=side.cuda_stream)    # sampleIntegrals + :260-262
+            pc = f.points_from_device(dXc.data_ptr(), C, stream=side.cuda_stream)
+            var = bdist.draw_sharded_candidate_var(f, pc, None)                                  # :312-314
+            pc.close()
+        main.wait_stream(side)
         results.update(var=var, draw_mean=dm, mean_var=mv, forest=f)
 
     sampler = ClockSampler(local_rank)

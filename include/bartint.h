@@ -184,10 +184,11 @@ int bartint_exact_integrals_device(const bartint_forest* f, int32_t measure, con
 int bartint_finalize_integrals(const bartint_forest* f, const double* integrals_scaled, int32_t n,
                                double* rescaled_out, double* mean_out, double* sd_out);
 
-/* Timing of the last bartint_eval_points* call on this forest: milliseconds spent in the dominant
- * evaluation kernel (CUDA events on the launching stream) and number of kernels launched.
- * Only valid after the stream has been synchronised. */
-int bartint_last_eval_profile(const bartint_forest* f, float* kernel_ms, int32_t* n_launches,
+/* Timing of the last evaluation on this forest: milliseconds spent in the evaluation kernel (CUDA events on
+ * the launching stream), kernels launched, and which kernel ran.  Two slots are kept: with_moments = 0 for the
+ * last evaluation that produced per-draw sums only, 1 for the last one with per-point moments / full / leaf
+ * output.  Blocks until that kernel has finished. */
+int bartint_last_eval_profile(const bartint_forest* f, int32_t with_moments, float* kernel_ms, int32_t* n_launches,
                               int32_t* used_table_kernel);
 
 /* Number of CUDA kernels this library has launched in this process so far (all devices, all streams).

@@ -101,7 +101,7 @@ def test_table_bits_variants(small_case, bits, monkeypatch):
     _assert_close(out["draw_mean"], onp.row_means(P), 1e-13)
     _assert_close(out["point_var"], onp.col_vars(P), 1e-10)
     assert np.array_equal(f.leaf_indices(X, use_table_kernel=True), onp.leaf_ordinals(ff, X))
-    assert f.last_eval_profile()["table_kernel"]
+    assert f.last_eval_profile(True)["table_kernel"]
     f.close()
 
 
@@ -199,7 +199,7 @@ def test_deep_tree_inside_table_kernel():
     X = rng.random((5000, 2))
     P = onp.predict(ff, X)
     out = f.eval(X, want=("draw_mean", "point_var", "full_pred"))
-    assert f.last_eval_profile()["table_kernel"]
+    assert f.last_eval_profile(True)["table_kernel"]
     _assert_close(out["full_pred"], P, 1e-13)
     _assert_close(out["draw_mean"], onp.row_means(P), 1e-13)
     assert np.array_equal(f.leaf_indices(X, use_table_kernel=True), onp.leaf_ordinals(ff, X))

@@ -58,10 +58,10 @@ def run(cfg, scale):
         f.eval_device(pts, d_draw_sum=sums.data_ptr(), d_point_mean=mean.data_ptr() if want_mom else 0,
                       d_point_m2=m2.data_ptr() if want_mom else 0, stream=st)
         b.record(); b.synchronize()
-        times.append(a.elapsed_time(b)); kms.append(f.last_eval_profile()["kernel_ms"])
+        times.append(a.elapsed_time(b)); kms.append(f.last_eval_profile(want_mom)["kernel_ms"])
         if it < 2:
             pts.close()
-    prof = f.last_eval_profile()
+    prof = f.last_eval_profile(want_mom)
     # parity properties
     n_sub = min(N, 20000)
     sub = f.points_from_device(dX.data_ptr(), n_sub, ld=N, stream=st)
