@@ -37,6 +37,8 @@ SIGNATURES = {
     "bartint_points_from_host": (C.c_int, [C.c_void_p, c_double_p, C.c_int64, C.c_int32, handle_p]),
     "bartint_points_from_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p,
                                              handle_p]),
+    "bartint_points_generate": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_int64, C.c_void_p, C.c_void_p,
+                                          handle_p]),
     "bartint_points_count": (C.c_int64, [C.c_void_p]),
     "bartint_points_codes": (C.c_int, [C.c_void_p, c_uint8_p]),
     "bartint_points_destroy": (None, [C.c_void_p]),
@@ -61,7 +63,7 @@ SIGNATURES = {
 
 BARTINT_SCALED_UNITS = 0x1
 BARTINT_FORCE_WALK = 0x2
-MEASURES = {"uniform": 0, "gaussian": 1, "exponential": 2}
+MEASURES = {"uniform": 0, "gaussian": 1, "exponential": 2, "gaussian_correct": 3}
 STATUS_NAMES = {0: "OK", 1: "ERR_ARG", 2: "ERR_PARSE", 3: "ERR_CUDA", 4: "ERR_UNSUPPORTED", 5: "ERR_NOMEM",
                 6: "ERR_NODEVICE"}
 

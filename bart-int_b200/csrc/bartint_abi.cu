@@ -248,6 +248,21 @@ int bartint_points_from_host(const bartint_forest* f, const double* X, int64_t N
     return rc;
 }
 
+int bartint_points_generate(const bartint_forest* f, int32_t measure, int64_t N, uint64_t seed, int64_t first_index,
+                            double* dX_out, void* stream, bartint_points** out) {
+    BI_REQUIRE(f != nullptr && out != nullptr, BARTINT_ERR_ARG, "NULL argument");
+    *out = nullptr;
+    BI_REQUIRE(measure >= 0 && measure <= 3, BARTINT_ERR_ARG, "unknown measure %d", measure);
+    BI_REQUIRE(N >= 0 && first_index >= 0, BARTINT_ERR_ARG, "N and first_index must be >= 0");
+    int rc = make_points(f, N, f->d, (cudaStream_t)stream, out);
+    if (rc) return rc;
+    DeviceGuard g(f->device);
+    rc = launch_generate_points(measure, N, first_index, seed, f->d, f->dev.cut_off, f->dev.cut_val, (*out)->codes,
+                                (*out)->Npad, dX_out, (cudaStream_t)stream);
+    if (rc) { bartint_points_destroy(*out); *out = nullptr; }
+    return rc;
+}
+
 int64_t bartint_points_count(const bartint_points* p) { return p ? p->N : -1; }
 
 int bartint_points_codes(const bartint_points* p, uint8_t* codes_out) {
@@ -467,7 +482,7 @@ int bartint_exact_integrals_device(const bartint_forest* f, int32_t measure, con
                                    int32_t n_draws_used, double* d_out, double* d_rescaled, double* d_mean_sd,
                                    void* stream) {
     BI_REQUIRE(f != nullptr, BARTINT_ERR_ARG, "forest is NULL");
-    BI_REQUIRE(measure >= 0 && measure <= 2, BARTINT_ERR_ARG, "unknown measure %d", measure);
+    BI_REQUIRE(measure >= 0 && measure <= 3, BARTINT_ERR_ARG, "unknown measure %d", measure);
     BI_REQUIRE((lo == nullptr) == (hi == nullptr), BARTINT_ERR_ARG, "lo and hi must both be given or both be NULL");
     const int n_draws = (n_draws_used <= 0 || n_draws_used > f->S) ? f->S : n_draws_used;
     if (n_draws == 0) return BARTINT_OK;
@@ -503,7 +518,7 @@ int bartint_finalize_draws_device(const bartint_forest* f, uint32_t flags, const
 int bartint_exact_integrals(const bartint_forest* f, int32_t measure, const double* lo, const double* hi,
                             int32_t n_draws_used, double* out) {
     BI_REQUIRE(f != nullptr, BARTINT_ERR_ARG, "forest is NULL");
-    BI_REQUIRE(measure >= 0 && measure <= 2, BARTINT_ERR_ARG, "unknown measure %d", measure);
+    BI_REQUIRE(measure >= 0 && measure <= 3, BARTINT_ERR_ARG, "unknown measure %d", measure);
     BI_REQUIRE((lo == nullptr) == (hi == nullptr), BARTINT_ERR_ARG, "lo and hi must both be given or both be NULL");
     int n_draws = (n_draws_used <= 0 || n_draws_used > f->S) ? f->S : n_draws_used;
     if (n_draws == 0) return BARTINT_OK;

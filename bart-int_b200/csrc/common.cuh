@@ -125,6 +125,9 @@ int canonicalise_soa(int32_t S, int32_t m, int32_t d, const int64_t* tree_node_o
 // kernel launchers (kernels_*.cu)
 int launch_bin_points(const double* dX, int64_t ld, int64_t N, int32_t d, const int32_t* d_cut_off,
                       const double* d_cut_val, int max_cuts, uint8_t* codes, int64_t Npad, cudaStream_t st);
+int launch_generate_points(int measure, int64_t N, int64_t first_index, uint64_t seed, int32_t d,
+                           const int32_t* d_cut_off, const double* d_cut_val, uint8_t* codes, int64_t Npad,
+                           double* x_out, cudaStream_t st);
 int launch_build_tables(const bartint_forest* f, const uint2* d_desc, const uint32_t* d_hdr, cudaStream_t st);
 
 struct EvalPlan {

@@ -90,6 +90,86 @@ int launch_bin_points(const double* dX, int64_t ld, int64_t N, int32_t d, const 
 }
 
 // ---------------------------------------------------------------------------------------------
+// K0g  generate_points: Monte Carlo points drawn ON THE DEVICE from the integration measure and binned on the fly, so
+// the N x d fp64 matrix never exists in HBM.  Counter-based Philox4x32-10: element (point i,
+// variable j) uses counter (i_lo, i_hi, j, 0) and key (seed_lo, seed_hi) -> the stream does not depend on the launch
+// shape or on how points are sharded across GPUs (a shard passes the global index of its first point).
+//   uniform      x = u                                   (runif, BARTInt.R:301)
+//   gaussian     x = 0.5 + Phi^-1(Phi(-.5) + u (Phi(.5) - Phi(-.5)))   N(0.5,1) truncated to [0,1] (rtnorm, :304)
+//   exponential  x = -log1p(-u)                          (rexp, :307)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t& o0, uint32_t& o1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    o0 = c0; o1 = c1;
+}
+
+__device__ __forceinline__ double draw_from_measure(int measure, uint32_t w0, uint32_t w1) {
+    const double u = ((double)(w0 >> 5) * 67108864.0 + (double)(w1 >> 6)) * (1.0 / 9007199254740992.0);   // 53-bit [0,1)
+    if (measure == BARTINT_MEASURE_UNIFORM) return u;
+    if (measure == BARTINT_MEASURE_EXPONENTIAL) return -log1p(-u);
+    const double plo = 0.30853753872598690, phi = 0.69146246127401310;     // Phi(-0.5), Phi(0.5)
+    return 0.5 + normcdfinv(plo + (phi - plo) * u);
+}
+
+__global__ void __launch_bounds__(256) generate_points_kernel(int measure, int64_t N, int64_t first_index, uint32_t k0,
+                                                              uint32_t k1, const int32_t* __restrict__ cut_off,
+                                                              const double* __restrict__ cut_val,
+                                                              uint32_t* __restrict__ codes4, int64_t quads_per_row,
+                                                              double* __restrict__ x_out) {
+    __shared__ double s_cut_pad[258];
+    double* s_cut = s_cut_pad + 1;
+    const int j = blockIdx.y;
+    const int c0i = cut_off[j], nc = cut_off[j + 1] - c0i;
+    for (int k = threadIdx.x; k < nc; k += blockDim.x) s_cut[k] = cut_val[c0i + k];
+    if (threadIdx.x == 0) { s_cut[-1] = -INFINITY; s_cut[nc] = INFINITY; }
+    __syncthreads();
+    const double c0 = nc > 0 ? s_cut[0] : 0.0;
+    const double span = nc > 1 ? s_cut[nc - 1] - s_cut[0] : 0.0;
+    const double inv_step = span > 0.0 ? (double)(nc - 1) / span : 0.0;
+    for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < quads_per_row;
+         w += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t word = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int64_t i = w * 4 + k;
+            if (i < N) {
+                const uint64_t gi = (uint64_t)(first_index + i);
+                uint32_t r0, r1;
+                philox4x32_10((uint32_t)gi, (uint32_t)(gi >> 32), (uint32_t)j, 0u, k0, k1, r0, r1);
+                const double x = draw_from_measure(measure, r0, r1);
+                if (x_out != nullptr) x_out[(int64_t)j * N + i] = x;
+                word |= bin_one(x, s_cut, nc, c0, inv_step) << (8 * k);
+            }
+        }
+        codes4[(int64_t)j * quads_per_row + w] = word;
+    }
+}
+
+int launch_generate_points(int measure, int64_t N, int64_t first_index, uint64_t seed, int32_t d,
+                           const int32_t* d_cut_off, const double* d_cut_val, uint8_t* codes, int64_t Npad,
+                           double* x_out, cudaStream_t st) {
+    if (d == 0 || Npad == 0) return BARTINT_OK;
+    const int64_t quads = Npad / 4;
+    int64_t bx = (quads + 255) / 256;
+    const int64_t cap = (148 * 8 * 4 + d - 1) / d;
+    if (bx > cap) bx = cap;
+    if (bx < 1) bx = 1;
+    dim3 grid((unsigned)bx, (unsigned)d);
+    generate_points_kernel<<<grid, 256, 0, st>>>(measure, N, first_index, (uint32_t)seed, (uint32_t)(seed >> 32), d_cut_off,
+                                                 d_cut_val, reinterpret_cast<uint32_t*>(codes), quads, x_out);
+    count_launch();
+    BI_CUDA(cudaGetLastError());
+    return BARTINT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Table builder: one CTA per group, one thread per table entry.  Thread idx walks every tree of the
 // group taking "right" at an internal node iff its predicate bit is set in idx, and sums the leaf
 // values in tree order.  Threads < NB also copy the node descriptors; thread 0 writes the header.
@@ -273,6 +353,10 @@ __device__ __forceinline__ void child_probs(int measure, double lo, double hi, d
         const double norm = normcdf(hi - 0.5) - normcdf(lo - 0.5);
         pl = (normcdf(rule) - normcdf(lo)) / norm;
         pr = 1.0 - pl;
+    } else if (measure == BARTINT_MEASURE_GAUSSIAN) {               // corrected: the N(0.5, 1) mass on both sides
+        const double norm = normcdf(hi - 0.5) - normcdf(lo - 0.5);
+        pl = (normcdf(rule - 0.5) - normcdf(lo - 0.5)) / norm;
+        pr = (normcdf(hi - 0.5) - normcdf(rule - 0.5)) / norm;
     } else {                                                        // :53-56
         const double norm = pexp1(hi) - pexp1(lo);
         pl = (pexp1(rule) - pexp1(lo)) / norm;

@@ -242,6 +242,14 @@ class Forest:
                                                       C.c_void_p(stream), C.byref(h)))
         return Points(self, h.value, N)
 
+    def generate_points(self, measure: str, N: int, seed: int, first_index: int = 0, d_x_out: int = 0,
+                        stream: int = 0) -> Points:
+        """Draw N points from the integration measure on the device (Philox4x32-10) and bin them on the fly."""
+        h = C.c_void_p()
+        _check(_lib.load().bartint_points_generate(self._h, _lib.MEASURES[measure], N, seed, first_index,
+                                                   C.c_void_p(d_x_out or None), C.c_void_p(stream), C.byref(h)))
+        return Points(self, h.value, N)
+
     # ---- evaluation ----
     def eval(self, pts, weights=None, want=("draw_mean", "point_mean", "point_var"), scaled=False, draws=None,
              force_walk=False) -> dict:

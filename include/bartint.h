@@ -45,7 +45,9 @@ typedef enum {
 typedef enum {
     BARTINT_MEASURE_UNIFORM = 0,            /* :46-48  box [0,1]^d                                    */
     BARTINT_MEASURE_GAUSSIAN_REFCOMPAT = 1, /* :49-52  exactly as written (quirk B3), box [0,1]^d     */
-    BARTINT_MEASURE_EXPONENTIAL = 2         /* :53-56  box [0,Inf)^d (:153-155)                        */
+    BARTINT_MEASURE_EXPONENTIAL = 2,        /* :53-56  box [0,Inf)^d (:153-155)                        */
+    BARTINT_MEASURE_GAUSSIAN = 3            /* corrected :49-52: N(0.5,1) truncated to the box, both masses with mean 0.5
+                                               (NOT what the reference computes)  */
 } bartint_measure;
 
 /* flags for bartint_eval* */
@@ -100,6 +102,15 @@ int bartint_points_from_host(const bartint_forest* f, const double* X, int64_t N
                              bartint_points** out);
 int bartint_points_from_device(const bartint_forest* f, const double* dX, int64_t N, int32_t d,
                                int64_t ld, void* stream, bartint_points** out);
+/* Monte Carlo points drawn ON THE DEVICE from the integration measure and binned on the fly (the N x d fp64 matrix is
+ * never materialised).  Replaces the reference's host-side sampling of the measure --
+ * runif / rtnorm(mean=.5, lower=0, upper=1) / rexp at src/BARTInt.R:301,304,307 -- when the points are only needed
+ * for the ensemble evaluation.  Counter-based Philox4x32-10: element (point i, variable j) depends only on
+ * (seed, first_index + i, j), so shards of one point set can be generated independently on different GPUs.
+ * measure: UNIFORM, GAUSSIAN / GAUSSIAN_REFCOMPAT (both: N(0.5,1) truncated to [0,1]), EXPONENTIAL.
+ * dX_out: optional device buffer (N x d column-major) receiving the generated values (tests), or NULL. */
+int bartint_points_generate(const bartint_forest* f, int32_t measure, int64_t N, uint64_t seed, int64_t first_index,
+                            double* dX_out, void* stream, bartint_points** out);
 int64_t bartint_points_count(const bartint_points* p);
 int bartint_points_codes(const bartint_points* p, uint8_t* codes_out /* N x d column-major */);
 void bartint_points_destroy(bartint_points* p);

@@ -179,6 +179,9 @@ static void fill_prob(tree_ctx* c, int32_t k, double* box /* [2*d]: lo then hi *
         else if (c->measure == 1) {
             const double norm = pnorm_(hi - 0.5) - pnorm_(lo - 0.5);
             pl = (pnorm_(rule) - pnorm_(lo)) / norm; pr = 1.0 - pl;
+        } else if (c->measure == 3) {   /* corrected gaussian (not the reference): both masses about mean 0.5 */
+            const double norm = pnorm_(hi - 0.5) - pnorm_(lo - 0.5);
+            pl = (pnorm_(rule - 0.5) - pnorm_(lo - 0.5)) / norm; pr = (pnorm_(hi - 0.5) - pnorm_(rule - 0.5)) / norm;
         } else {
             const double norm = pexp_(hi) - pexp_(lo);
             pl = (pexp_(rule) - pexp_(lo)) / norm; pr = 1.0 - pl;

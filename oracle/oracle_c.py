@@ -69,7 +69,7 @@ def exact_integrals(forest, measure="uniform", n_draws=None, nthreads=1, lo=None
     f = as_ns(forest)
     n = f.S if n_draws is None else int(n_draws)
     out = np.zeros(n)
-    code = {"uniform": 0, "gaussian": 1, "exponential": 2}[measure]
+    code = {"uniform": 0, "gaussian": 1, "exponential": 2, "gaussian_correct": 3}[measure]
     lo_a = None if lo is None else np.ascontiguousarray(np.broadcast_to(np.asarray(lo, np.float64), (f.d,)))
     hi_a = None if hi is None else np.ascontiguousarray(np.broadcast_to(np.asarray(hi, np.float64), (f.d,)))
     load().oracle_exact_integrals(*_forest_args(f), C.c_int32(code), _p(lo_a), _p(hi_a), C.c_int32(n),

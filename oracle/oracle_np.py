@@ -387,6 +387,10 @@ def single_tree_sum(var, cut, left, right, mu, cut_lists, d, measure, lo=None, h
                     norm = _pmvnorm1(lo_v, hi_v, mean=0.5)
                     pl = _div(_pmvnorm1(lo_v, rule, mean=0.0), norm)
                     pr = 1.0 - pl
+                elif measure == "gaussian_correct":                        # NOT the reference: both masses about mean 0.5
+                    norm = _pmvnorm1(lo_v, hi_v, mean=0.5)
+                    pl = _div(_pmvnorm1(lo_v, rule, mean=0.5), norm)
+                    pr = _div(_pmvnorm1(rule, hi_v, mean=0.5), norm)
                 elif measure == "exponential":                             # :53-56
                     norm = _pexp(hi_v) - _pexp(lo_v)
                     pl = _div(_pexp(rule) - _pexp(lo_v), norm)
@@ -461,3 +465,39 @@ def leaf_probabilities(var, cut, left, right, cut_lists, d, measure="uniform"):
             mu = np.zeros(len(var)); mu[k] = 1.0
             probs.append(single_tree_sum(var, cut, left, right, mu, cut_lists, d, measure))
     return np.array(probs)
+
+
+# --------------------------------------------------------------------------------------
+# 8f item 2: on-device sampling of the integration measure -- restatement of the generator
+# (Philox4x32-10, Salmon et al. 2011; the measure transforms of BARTInt.R:301,304,307)
+# --------------------------------------------------------------------------------------
+
+def philox4x32_10(c0, c1, c2, c3, k0, k1):
+    """Vectorised Philox4x32-10 on uint32 arrays; returns the first two output words."""
+    M0, M1, W0, W1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), 0x9E3779B9, 0xBB67AE85
+    c0, c1, c2, c3 = (np.asarray(c, np.uint64) for c in np.broadcast_arrays(c0, c1, c2, c3))
+    k0, k1 = int(k0), int(k1)
+    mask = np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0, p1 = M0 * c0, M1 * c2
+        hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & mask, p1 >> np.uint64(32), p1 & mask
+        c0, c1, c2, c3 = hi1 ^ c1 ^ np.uint64(k0), lo1, hi0 ^ c3 ^ np.uint64(k1), lo0
+        k0, k1 = (k0 + W0) & 0xFFFFFFFF, (k1 + W1) & 0xFFFFFFFF
+    return c0.astype(np.uint32), c1.astype(np.uint32)
+
+
+def generate_points(measure, N, d, seed, first_index=0):
+    """(N, d) float64 points exactly as generate_points_kernel draws them (uniform: bit-exact; the gaussian and
+    exponential transforms go through libm / scipy and may differ from the device in the last ulp)."""
+    i = (np.arange(N, dtype=np.uint64) + np.uint64(first_index))[:, None]
+    j = np.arange(d, dtype=np.uint64)[None, :]
+    w0, w1 = philox4x32_10(i & np.uint64(0xFFFFFFFF), i >> np.uint64(32), j, np.uint64(0),
+                           seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    u = ((w0 >> np.uint32(5)).astype(np.float64) * 67108864.0 + (w1 >> np.uint32(6)).astype(np.float64)) / 9007199254740992.0
+    if measure == "uniform":
+        return u
+    if measure == "exponential":
+        return -np.log1p(-u)
+    from scipy.special import ndtri
+    plo, phi = 0.30853753872598690, 0.69146246127401310
+    return 0.5 + ndtri(plo + (phi - plo) * u)

@@ -125,7 +125,7 @@ def test_adversarial_forests(kind):
     f.close()
 
 
-@pytest.mark.parametrize("measure", ["uniform", "gaussian", "exponential"])
+@pytest.mark.parametrize("measure", ["uniform", "gaussian", "exponential", "gaussian_correct"])
 def test_exact_integrals(small_case, measure):
     ff, *_ = small_case
     f = Forest.from_soa(ff)
@@ -299,3 +299,38 @@ def test_codes_irregular_cut_grid():
     pts = f.points(X)
     assert np.array_equal(pts.codes().astype(np.int32), onp.bin_points(X, ff.cut_offsets, ff.cut_values))
     pts.close(); f.close()
+
+
+@pytest.mark.parametrize("measure", ["uniform", "gaussian", "exponential"])
+def test_device_point_generation(small_case, measure):
+    """Philox points drawn on the device: values match the oracle's restatement of the generator, codes are the
+    exact cut map of those values, shards reproduce the unsharded stream, and the MC estimate built on them agrees
+    with the exact integral of the same measure."""
+    import torch
+    ff, *_ = small_case
+    f = Forest.from_soa(ff)
+    N, seed = 20001, 0x1234_5678_9ABC_DEF0
+    dX = torch.empty((ff.d, N), dtype=torch.float64, device="cuda")
+    pts = f.generate_points(measure, N, seed, d_x_out=dX.data_ptr())
+    torch.cuda.synchronize()
+    X = dX.cpu().numpy().T
+    want = onp.generate_points(measure, N, ff.d, seed)
+    if measure == "uniform":
+        assert np.array_equal(X, want)                                  # bit-exact
+    else:
+        np.testing.assert_allclose(X, want, rtol=1e-13, atol=1e-15)     # libm vs CUDA math: last-ulp differences
+    assert np.array_equal(pts.codes().astype(np.int32), onp.bin_points(X, ff.cut_offsets, ff.cut_values))
+    # two shards == one stream
+    a = f.generate_points(measure, 12000, seed); b = f.generate_points(measure, N - 12000, seed, first_index=12000)
+    assert np.array_equal(np.vstack([a.codes(), b.codes()]), pts.codes())
+    # MC on generated points vs the exact integral of the same measure
+    exact_name = {"uniform": "uniform", "gaussian": "gaussian_correct", "exponential": "exponential"}[measure]
+    exact = f.exact_integrals(exact_name)
+    F = onp.tree_sums(ff, X)
+    mc = f.eval(pts, want=("draw_mean",), scaled=True)["draw_mean"]
+    _assert_close(mc, F.mean(axis=1), 1e-12, scale=np.maximum(np.abs(F.mean(axis=1)), 1e-3))
+    se = F.std(axis=1, ddof=1) / math.sqrt(N)
+    assert (np.abs(mc - exact) <= 5 * se + 1e-12).all()
+    for p in (pts, a, b):
+        p.close()
+    f.close()

@@ -130,3 +130,34 @@ def test_survey_integral_consistency(seed, d, S, m):
         assert abs(variance - P.mean(axis=1).var(ddof=1)) < 1e-12
     else:
         assert math.isnan(variance)
+
+
+def test_corrected_gaussian_measure_is_a_probability_and_matches_mc(small_case):
+    """'gaussian_correct' (not the reference's as-written branch): leaf masses sum to one and the
+    exact integral agrees with Monte Carlo under N(0.5, 1) truncated to [0, 1]^d."""
+    ff, *_ = small_case
+    f = onp.as_ns(ff)
+    cl = onp.cut_lists_of(f)
+    for k in range(0, f.S * f.m, 5):
+        a, b = f.tree_offset[k], f.tree_offset[k + 1]
+        p = onp.leaf_probabilities(f.var[a:b], f.cut[a:b], f.left[a:b], f.right[a:b], cl, f.d, "gaussian_correct")
+        assert abs(p.sum() - 1.0) < 1e-12 and (p >= -1e-15).all()
+    rng = np.random.default_rng(3)
+    X = synth.sample_measure(rng, "gaussian", 40000, ff.d)
+    F = onp.tree_sums(ff, X)
+    exact = onp.sample_integrals(ff, "gaussian_correct")
+    se = F.std(axis=1, ddof=1) / math.sqrt(X.shape[0])
+    assert (np.abs(F.mean(axis=1) - exact) <= 5 * se + 1e-12).all()
+    from oracle import oracle_c as oc
+    np.testing.assert_allclose(oc.exact_integrals(ff, "gaussian_correct"), exact, rtol=1e-13, atol=1e-15)
+
+
+def test_philox_known_answers():
+    """Random123 kat_vectors for philox4x32-10 (first two output words) pin the generator's restatement."""
+    u = np.uint64
+    for ctr, key, want in [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d)),
+                           ((0xffffffff,) * 4, (0xffffffff, 0xffffffff), (0x408f276d, 0x41c83b0e)),
+                           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+                            (0xd16cfe09, 0x94fdcceb))]:
+        a, b = onp.philox4x32_10(u(ctr[0]), u(ctr[1]), u(ctr[2]), u(ctr[3]), key[0], key[1])
+        assert (int(a), int(b)) == want
