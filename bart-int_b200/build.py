@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libbartint_cuda.so")
 SYNTH_LIB = os.path.join(HERE, "libbartint_synth.so")
 
-CUDA_SOURCES = ["bartint_abi.cu", "forest_host.cu", "kernels_eval.cu", "kernels_misc.cu"]
+CUDA_SOURCES = ["bartint_abi.cu", "forest_host.cu", "kernels_eval.cu", "kernels_gather.cu", "kernels_misc.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC,-fopenmp,-O3", "-shared", "-lgomp",
@@ -38,7 +38,8 @@ def _stale(target: str, sources: list[str]) -> bool:
 
 def build_cuda(force: bool = False, verbose: bool = False, extra: list[str] | None = None) -> str:
     srcs = [os.path.join(CSRC, s) for s in CUDA_SOURCES]
-    deps = srcs + [os.path.join(CSRC, "common.cuh"), os.path.join(HERE, "..", "include", "bartint.h")]
+    deps = srcs + [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "pipeline.cuh"),
+                   os.path.join(HERE, "..", "include", "bartint.h")]
     if force or _stale(LIB, deps):
         cmd = [_nvcc(), *NVCC_FLAGS, *(extra or []), "-o", LIB, *srcs]
         if verbose:

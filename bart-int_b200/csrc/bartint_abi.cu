@@ -211,7 +211,13 @@ static int make_points(const bartint_forest* f, int64_t N, int32_t d, cudaStream
     p->stream = st;
     DeviceGuard g(f->device);
     cudaError_t e = cudaMallocAsync((void**)&p->codes, (size_t)std::max(d, 1) * (size_t)p->Npad, st);
-    if (e != cudaSuccess) { delete p; return cuda_fail(e, "cudaMallocAsync(codes)", __FILE__, __LINE__); }
+    if (e == cudaSuccess && f->gather)      // the gather kernel reads point-major packed codes (16 B per point)
+        e = cudaMallocAsync((void**)&p->codes_pm, sizeof(uint4) * (size_t)p->Npad, st);
+    if (e != cudaSuccess) {
+        if (p->codes) cudaFreeAsync(p->codes, st);
+        delete p;
+        return cuda_fail(e, "cudaMallocAsync(codes)", __FILE__, __LINE__);
+    }
     *out = p;
     return BARTINT_OK;
 }
@@ -225,6 +231,8 @@ int bartint_points_from_device(const bartint_forest* f, const double* dX, int64_
     DeviceGuard g(f->device);
     rc = launch_bin_points(dX, ld, N, d, f->dev.cut_off, f->dev.cut_val, f->max_cuts, (*out)->codes, (*out)->Npad,
                            (cudaStream_t)stream);
+    if (rc == BARTINT_OK && (*out)->codes_pm)
+        rc = launch_repack_codes((*out)->codes, (*out)->Npad, d, (*out)->codes_pm, (cudaStream_t)stream);
     if (rc) { bartint_points_destroy(*out); *out = nullptr; }
     return rc;
 }
@@ -259,6 +267,8 @@ int bartint_points_generate(const bartint_forest* f, int32_t measure, int64_t N,
     DeviceGuard g(f->device);
     rc = launch_generate_points(measure, N, first_index, seed, f->d, f->dev.cut_off, f->dev.cut_val, (*out)->codes,
                                 (*out)->Npad, dX_out, (cudaStream_t)stream);
+    if (rc == BARTINT_OK && (*out)->codes_pm)
+        rc = launch_repack_codes((*out)->codes, (*out)->Npad, f->d, (*out)->codes_pm, (cudaStream_t)stream);
     if (rc) { bartint_points_destroy(*out); *out = nullptr; }
     return rc;
 }
@@ -280,6 +290,7 @@ void bartint_points_destroy(bartint_points* p) {
     {
         DeviceGuard g(p->device);
         if (p->codes) cudaFreeAsync(p->codes, p->stream);
+        if (p->codes_pm) cudaFreeAsync(p->codes_pm, p->stream);
         (void)cudaGetLastError();
     }
     delete p;
@@ -319,8 +330,9 @@ static int eval_core(const bartint_forest* f, const bartint_points* p, uint32_t 
         }
     }
     BI_CUDA(cudaEventRecord(f->ev0[slot], st));
-    int rc = plan.use_table ? launch_eval_table(f, p, plan, draw_part, pt_mean, pt_m2, d_full, fp_scale, fp_y0, fp_scaled, st)
-                            : launch_eval_walk(f, p, plan, draw_part, pt_mean, pt_m2, d_leaf, d_full, fp_scale, fp_y0, fp_scaled, st);
+    int rc = plan.use_gather ? launch_eval_gather(f, p, plan, draw_part, pt_mean, pt_m2, d_full, fp_scale, fp_y0, fp_scaled, st)
+             : plan.use_table ? launch_eval_table(f, p, plan, draw_part, pt_mean, pt_m2, d_full, fp_scale, fp_y0, fp_scaled, st)
+                              : launch_eval_walk(f, p, plan, draw_part, pt_mean, pt_m2, d_leaf, d_full, fp_scale, fp_y0, fp_scaled, st);
     BI_CUDA(cudaEventRecord(f->ev1[slot], st));
     f->last_timed[slot] = true;
     f->last_launches[slot] = 1;
@@ -463,7 +475,8 @@ int bartint_leaf_indices(const bartint_forest* f, const bartint_points* p, int32
     int32_t* d_leaf = nullptr;
     BI_CUDA(cudaMallocAsync((void**)&d_leaf, sizeof(int32_t) * (size_t)total, nullptr));
     if (use_table_kernel) {
-        rc = launch_table_leaf(f, p, draw_begin, draw_end, d_leaf, nullptr);
+        rc = f->gather ? launch_gather_leaf(f, p, draw_begin, draw_end, d_leaf, nullptr)
+                       : launch_table_leaf(f, p, draw_begin, draw_end, d_leaf, nullptr);
     } else {
         rc = eval_core(f, p, BARTINT_FORCE_WALK, draw_begin, draw_end, nullptr, nullptr, nullptr, d_leaf, nullptr, 1.0,
                        0.0, 1, nullptr);

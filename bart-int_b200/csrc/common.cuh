@@ -58,6 +58,17 @@ constexpr uint32_t TK_FLAG_WALK = 2u;
 __host__ __device__ constexpr int tk_tbl_off(int nb) { return TK_HDR + ((nb * 8 + 15) & ~15); }   // 16 B aligned
 __host__ __device__ constexpr int tk_rec_bytes(int nb) { return tk_tbl_off(nb) + (8 << nb); }       // multiple of 16
 
+// Gather kernel (d <= 16, NB <= 5): the thread keeps each point's codes PACKED IN REGISTERS (point-major, 4 codes per
+// word, R = 2..4 words per point) and one PRMT with a per-group selector gathers the codes of up to 4 nodes of one
+// point; byte-wise add of the biases, sign-replicating PRMT and one IDP.4A against the per-slot weights -(8 << bit)
+// give the table byte offset directly.  Two rounds per group: round 0 gathers from words (0,1) = variables 0..7,
+// round 1 from words (R-2,R-1) = variables 4(R-2) .. 4(R-2)+7.  No code loads from shared memory at all.
+//   record: [ 16 B header | selA|selB<<16, biasA, biasB, wA, wB, 0, 0, 0 | 2^NB doubles ]
+constexpr int TG_DESC = 32;
+__host__ __device__ constexpr int tg_tbl_off() { return TK_HDR + TG_DESC; }
+__host__ __device__ constexpr int tg_rec_bytes(int nb) { return tg_tbl_off() + (8 << nb); }
+__host__ __device__ constexpr int tg_regs_for(int d) { return d <= 8 ? 2 : (d <= 12 ? 3 : 4); }
+
 struct DeviceForest {
     uint2* nodes = nullptr;            // n_nodes
     int32_t* tree_off = nullptr;       // S*m+1
@@ -87,7 +98,9 @@ struct bartint_forest {
     std::vector<int32_t> cut_off;
     std::vector<double> cut_val;
     // table path
-    bool table_ok = false;
+    bool table_ok = false;             // a fast (table or gather) kernel applies
+    bool gather = false;               // group records are in the gather format (else table format)
+    int g_regs = 0;                    // gather: code words per point
     int nb = 0;
     int64_t n_groups = 0;
     std::vector<int32_t> draw_group_off;  // host copy, S+1
@@ -108,6 +121,7 @@ struct bartint_points {
     int32_t d = 0;
     cudaStream_t stream = nullptr;   // stream the code buffer was allocated on (stream-ordered allocator)
     uint8_t* codes = nullptr;  // feature-major: codes[f * Npad + i], zero padded to Npad (multiple of TK_NPAD)
+    uint4* codes_pm = nullptr; // point-major packed codes (16 B per point) for the gather kernel; built with the codes
 };
 
 namespace bartint {
@@ -128,13 +142,25 @@ int launch_bin_points(const double* dX, int64_t ld, int64_t N, int32_t d, const 
 int launch_generate_points(int measure, int64_t N, int64_t first_index, uint64_t seed, int32_t d,
                            const int32_t* d_cut_off, const double* d_cut_val, uint8_t* codes, int64_t Npad,
                            double* x_out, cudaStream_t st);
-int launch_build_tables(const bartint_forest* f, const uint2* d_desc, const uint32_t* d_hdr, cudaStream_t st);
+struct EvalPlan;
+int launch_build_tables(const bartint_forest* f, const uint32_t* d_desc, int desc_words, const uint32_t* d_hdr,
+                        cudaStream_t st);
+int launch_repack_codes(const uint8_t* codes, int64_t Npad, int d, uint4* codes_pm, cudaStream_t st);
+int launch_eval_gather(const bartint_forest* f, const bartint_points* p, const EvalPlan& plan, double* draw_part,
+                       double* pt_mean, double* pt_m2, double* full_pred, double fp_scale, double fp_y0,
+                       int fp_scaled, cudaStream_t st);
+int launch_gather_leaf(const bartint_forest* f, const bartint_points* p, int32_t draw_begin, int32_t draw_end,
+                       int32_t* leaf_out, cudaStream_t st);
+int gather_resident_ctas(const bartint_forest* f, bool mom, bool full);   // occupancy query for make_plan
+inline int fast_rec_bytes(const bartint_forest* f) { return f->gather ? tg_rec_bytes(f->nb) : tk_rec_bytes(f->nb); }
+inline int fast_tbl_off(const bartint_forest* f) { return f->gather ? tg_tbl_off() : tk_tbl_off(f->nb); }
 
 struct EvalPlan {
     int32_t draw_begin, draw_end;
     int n_tiles, n_chunks, chunk_draws;
     int tile;          // points per CTA
-    bool use_table;
+    bool use_table;    // a fast kernel (table or gather format) is used, else the walk kernel
+    bool use_gather;   // ... and it is the gather kernel
 };
 EvalPlan make_plan(const bartint_forest* f, const bartint_points* p, uint32_t flags, int32_t draw_begin,
                    int32_t draw_end, bool want_moments, bool want_full);

@@ -342,19 +342,25 @@ int forest_upload(bartint_forest* f) {
     if ((rc = upload(&f->dev.cut_off, f->cut_off))) return rc;
     if ((rc = upload(&f->dev.cut_val, f->cut_val))) return rc;
 
-    // ---- table path planning: greedy packing of consecutive trees of a draw into <= NB predicate bits ----
+    // ---- fast-path planning: greedy packing of consecutive trees of a draw into groups of <= NB predicate bits ----
     f->nb = table_bits_from_env();
-    // the table kernel needs 7-bit codes (byte-SIMD compare) and the code rows of one CTA tile in shared memory
+    // both fast kernels need 7-bit codes (byte-wise compare); the table kernel keeps the code rows of one CTA tile in
+    // shared memory, the gather kernel keeps a point's codes in <= 4 registers
     f->table_ok = n_trees > 0 && f->max_cuts <= 127 && (int64_t)f->d * TK_TILE_MIN <= 160 * 1024;
+    const char* kenv = getenv("BARTINT_KERNEL");
+    f->gather = f->table_ok && f->d <= 16 && f->d >= 1 && !(kenv && strcmp(kenv, "table") == 0);
+    if (f->gather && f->nb > 5) f->nb = 5;                 // slot weights -(8 << bit) must fit a signed byte
+    f->g_regs = tg_regs_for(f->d);
     f->n_groups = 0;
     if (!f->table_ok) {
         BI_CUDA(cudaStreamSynchronize(nullptr));
         return BARTINT_OK;
     }
     const int NB = f->nb;
+    const int DW = f->gather ? TG_DESC / 4 : 2 * NB;       // descriptor words per group
     std::vector<int32_t> group_tree_off;   // first tree of each group
     std::vector<uint32_t> hdr;             // flags per group
-    std::vector<uint2> desc;               // NB per group: {var*TILE, bias x4}
+    std::vector<uint32_t> desc;            // DW words per group
     std::vector<uint8_t> node_bit((size_t)nn, 0);
     f->draw_group_off.assign((size_t)f->S + 1, 0);
     group_tree_off.reserve((size_t)(n_trees / 3 + f->S + 1));
@@ -362,23 +368,76 @@ int forest_upload(bartint_forest* f) {
     // (a 2^NB x 8 B table wraps the 32 banks 2^(NB-4) times), lookups with equal indices are a broadcast.  The
     // predicates least likely to differ between points -- cuts nearest the edge of their variable's cut grid -- are
     // therefore given the highest bits.  Pure layout choice: the builder and the kernels read node_bit / desc.
-    std::vector<int64_t> gnodes;           // nodes of the group being filled
+    auto extremeness = [&](int64_t g) {
+        const int v = f->var[(size_t)g];
+        const double nc = (double)(f->cut_off[(size_t)v + 1] - f->cut_off[(size_t)v]);
+        return std::fabs(2.0 * (f->cut[(size_t)g] + 1.0) / (nc + 1.0) - 1.0);
+    };
+    // gather format: round 0 can address variables [0, 8), round 1 variables [base1, base1 + 8); 4 slots per round
+    const int base1 = 4 * (f->g_regs - 2);
+    struct Slot { int64_t node; int round, pos; };
+    std::vector<int64_t> gnodes;           // nodes of the group being filled (table format)
+    std::vector<Slot> gslots;              // nodes + their slots (gather format)
+    int used[2] = {0, 0};
     auto close_group = [&]() {
-        if (gnodes.empty()) return;
-        auto extremeness = [&](int64_t g) {
-            const int v = f->var[(size_t)g];
-            const double nc = (double)(f->cut_off[(size_t)v + 1] - f->cut_off[(size_t)v]);
-            return std::fabs(2.0 * (f->cut[(size_t)g] + 1.0) / (nc + 1.0) - 1.0);
-        };
-        std::stable_sort(gnodes.begin(), gnodes.end(),
-                         [&](int64_t a, int64_t b2) { return extremeness(a) < extremeness(b2); });
-        uint2* gd = &desc[desc.size() - (size_t)NB];
-        for (size_t b2 = 0; b2 < gnodes.size(); ++b2) {
-            const size_t g = (size_t)gnodes[b2];
-            node_bit[g] = (uint8_t)b2;
-            gd[b2] = make_uint2((uint32_t)f->var[g], (uint32_t)(127 - f->cut[g]) * 0x01010101u);
+        uint32_t* gd = desc.empty() ? nullptr : &desc[desc.size() - (size_t)DW];
+        if (!f->gather) {
+            if (gnodes.empty()) return;
+            std::stable_sort(gnodes.begin(), gnodes.end(),
+                             [&](int64_t a, int64_t b2) { return extremeness(a) < extremeness(b2); });
+            for (size_t b2 = 0; b2 < gnodes.size(); ++b2) {
+                const size_t g = (size_t)gnodes[b2];
+                node_bit[g] = (uint8_t)b2;
+                gd[2 * b2] = (uint32_t)f->var[g];
+                gd[2 * b2 + 1] = (uint32_t)(127 - f->cut[g]) * 0x01010101u;
+            }
+            gnodes.clear();
+            return;
         }
-        gnodes.clear();
+        if (gslots.empty()) { used[0] = used[1] = 0; return; }
+        std::stable_sort(gslots.begin(), gslots.end(),
+                         [&](const Slot& a, const Slot& b2) { return extremeness(a.node) < extremeness(b2.node); });
+        uint32_t sel[2] = {0, 0}, bias[2] = {0, 0}, wgt[2] = {0, 0};
+        for (size_t b2 = 0; b2 < gslots.size(); ++b2) {
+            const Slot& sl = gslots[b2];
+            const size_t g = (size_t)sl.node;
+            node_bit[g] = (uint8_t)b2;
+            const uint32_t byte_in_bank = (uint32_t)(f->var[g] - (sl.round ? base1 : 0));       // 0..7
+            sel[sl.round] |= byte_in_bank << (4 * sl.pos);
+            bias[sl.round] |= (uint32_t)(127 - f->cut[g]) << (8 * sl.pos);
+            wgt[sl.round] |= ((uint32_t)(-(8 << b2)) & 0xFFu) << (8 * sl.pos);                // signed byte -(8 << bit)
+        }
+        gd[0] = sel[0] | (sel[1] << 16); gd[1] = bias[0]; gd[2] = bias[1]; gd[3] = wgt[0]; gd[4] = wgt[1];
+        gslots.clear();
+        used[0] = used[1] = 0;
+    };
+    // try to place the internal nodes of tree [base, base+cnt) into the open gather group; all or nothing
+    auto place_tree = [&](int32_t base, int32_t cnt, int bits) -> bool {
+        const size_t mark = gslots.size();
+        int u[2] = {used[0], used[1]};
+        int nbits = bits;
+        for (int32_t a = 0; a < cnt; ++a) {
+            const size_t g = (size_t)(base + a);
+            if (f->var[g] < 0) continue;
+            const int v = f->var[g];
+            const bool in0 = v < 8, in1 = v >= base1 && v < base1 + 8;
+            int r = -1;
+            if (in0 && in1) r = (u[0] <= u[1]) ? 0 : 1;      // variable reachable from both rounds: take the emptier one
+            else if (in0) r = 0;
+            else if (in1) r = 1;
+            if (r >= 0 && u[r] >= 4) r = (r == 0 ? (in1 && u[1] < 4 ? 1 : -1) : (in0 && u[0] < 4 ? 0 : -1));
+            if (r < 0 || nbits >= NB) { gslots.resize(mark); return false; }
+            gslots.push_back(Slot{(int64_t)g, r, u[r]});
+            ++u[r];
+            ++nbits;
+        }
+        used[0] = u[0]; used[1] = u[1];
+        return true;
+    };
+    auto open_group = [&](int64_t k, uint32_t flags) {
+        group_tree_off.push_back((int32_t)k);
+        hdr.push_back(flags);
+        desc.resize(desc.size() + (size_t)DW, 0u);           // unused slots: bias 0 -> predicate 0, weight 0
     };
     for (int32_t s = 0; s < f->S; ++s) {
         f->draw_group_off[(size_t)s] = (int32_t)group_tree_off.size();
@@ -387,23 +446,30 @@ int forest_upload(bartint_forest* f) {
             const int64_t k = (int64_t)s * f->m + t;
             const int32_t base = tree_off[(size_t)k], cnt = tree_off[(size_t)k + 1] - base;
             const int internal = (cnt - 1) / 2;
-            if (internal > NB) {               // WALK record holding just this tree
+            bool placed = false;
+            if (internal <= NB) {
+                if (!f->gather) {
+                    if (bits + internal > NB) { close_group(); open_group(k, 0u); bits = 0; }
+                    for (int32_t a = 0; a < cnt; ++a)
+                        if (f->var[(size_t)(base + a)] >= 0) gnodes.push_back((int64_t)base + a);
+                    placed = true;
+                } else {
+                    if (bits <= NB && bits + internal <= NB && place_tree(base, cnt, bits)) placed = true;
+                    else {
+                        close_group(); open_group(k, 0u); bits = 0;
+                        placed = place_tree(base, cnt, 0);
+                        if (!placed) {                       // does not fit even an empty group -> WALK record
+                            group_tree_off.pop_back(); hdr.pop_back(); desc.resize(desc.size() - (size_t)DW);
+                        }
+                    }
+                }
+            }
+            if (!placed) {                                   // WALK record holding just this tree
                 close_group();
-                group_tree_off.push_back((int32_t)k);
-                hdr.push_back(TK_FLAG_WALK);
-                desc.resize(desc.size() + (size_t)NB, make_uint2(0u, 0u));
-                bits = NB + 1;                 // the next tree starts a fresh table group
+                open_group(k, TK_FLAG_WALK);
+                bits = NB + 1;                               // the next tree starts a fresh group
                 continue;
             }
-            if (bits + internal > NB) {
-                close_group();
-                group_tree_off.push_back((int32_t)k);
-                hdr.push_back(0u);
-                desc.resize(desc.size() + (size_t)NB, make_uint2(0u, 0u));   // unused slots: bias 0 -> predicate 0
-                bits = 0;
-            }
-            for (int32_t a = 0; a < cnt; ++a)
-                if (f->var[(size_t)(base + a)] >= 0) gnodes.push_back((int64_t)base + a);
             bits += internal;
         }
         close_group();
@@ -412,16 +478,16 @@ int forest_upload(bartint_forest* f) {
     f->draw_group_off[(size_t)f->S] = (int32_t)group_tree_off.size();
     f->n_groups = (int64_t)group_tree_off.size();
     group_tree_off.push_back((int32_t)n_trees);
-    // group g covers trees [group_tree_off[g], min(group_tree_off[g+1], end of its draw)) -- groups never span draws
+    // group g covers trees [group_tree_off[g], group_tree_off[g+1]) -- groups never span draws
     if ((rc = upload(&f->dev.node_bit, node_bit))) return rc;
     if ((rc = upload(&f->dev.group_tree_off, group_tree_off))) return rc;
     if ((rc = upload(&f->dev.draw_group_off, f->draw_group_off))) return rc;
-    BI_CUDA(cudaMallocAsync((void**)&f->dev.group_rec, (size_t)f->n_groups * (size_t)tk_rec_bytes(NB) + 16, nullptr));
-    uint2* d_desc = nullptr;
+    BI_CUDA(cudaMallocAsync((void**)&f->dev.group_rec, (size_t)f->n_groups * (size_t)fast_rec_bytes(f) + 16, nullptr));
+    uint32_t* d_desc = nullptr;
     uint32_t* d_hdr = nullptr;
     if ((rc = upload(&d_desc, desc))) return rc;
     if ((rc = upload(&d_hdr, hdr))) { cudaFreeAsync(d_desc, nullptr); return rc; }
-    rc = launch_build_tables(f, d_desc, d_hdr, 0);
+    rc = launch_build_tables(f, d_desc, DW, d_hdr, 0);
     cudaFreeAsync(d_desc, nullptr);
     cudaFreeAsync(d_hdr, nullptr);
     cudaError_t e = cudaStreamSynchronize(nullptr);   // host vectors (pageable) must outlive the copies; surface build errors here

@@ -177,11 +177,11 @@ int launch_generate_points(int measure, int64_t N, int64_t first_index, uint64_t
 __global__ void build_tables_kernel(const uint2* __restrict__ nodes, const int32_t* __restrict__ tree_off,
                                     const int32_t* __restrict__ tree_leaf_off, const double* __restrict__ leaf_mu,
                                     const uint8_t* __restrict__ node_bit, const int32_t* __restrict__ group_tree_off,
-                                    const uint2* __restrict__ desc, const uint32_t* __restrict__ hdr, int nb,
-                                    uint8_t* __restrict__ rec_base) {
+                                    const uint32_t* __restrict__ desc, int desc_words, const uint32_t* __restrict__ hdr,
+                                    int rec_bytes, int tbl_off, uint8_t* __restrict__ rec_base) {
     const int64_t g = blockIdx.x;
     const uint32_t idx = threadIdx.x;
-    uint8_t* rec = rec_base + g * (int64_t)tk_rec_bytes(nb);
+    uint8_t* rec = rec_base + g * (int64_t)rec_bytes;
     const int32_t tb = group_tree_off[g], te = group_tree_off[g + 1];
     const uint32_t flags = hdr[g];
     if (flags & TK_FLAG_WALK) {
@@ -200,19 +200,20 @@ __global__ void build_tables_kernel(const uint2* __restrict__ nodes, const int32
         }
         sum += leaf_mu[tree_leaf_off[k] + (int32_t)r.y];
     }
-    reinterpret_cast<double*>(rec + tk_tbl_off(nb))[idx] = sum;
-    if ((int)idx < nb) reinterpret_cast<uint2*>(rec + TK_HDR)[idx] = desc[g * nb + idx];
+    reinterpret_cast<double*>(rec + tbl_off)[idx] = sum;
+    if ((int)idx < desc_words) reinterpret_cast<uint32_t*>(rec + TK_HDR)[idx] = desc[g * desc_words + idx];
     if (idx == 0) {
         uint4 h = make_uint4(flags, (uint32_t)tb, (uint32_t)(te - tb), 0u);
         *reinterpret_cast<uint4*>(rec) = h;
     }
 }
 
-int launch_build_tables(const bartint_forest* f, const uint2* d_desc, const uint32_t* d_hdr, cudaStream_t st) {
+int launch_build_tables(const bartint_forest* f, const uint32_t* d_desc, int desc_words, const uint32_t* d_hdr,
+                        cudaStream_t st) {
     if (f->n_groups == 0) return BARTINT_OK;
     build_tables_kernel<<<(unsigned)f->n_groups, 1u << f->nb, 0, st>>>(
         f->dev.nodes, f->dev.tree_off, f->dev.tree_leaf_off, f->dev.leaf_mu, f->dev.node_bit, f->dev.group_tree_off,
-        d_desc, d_hdr, f->nb, f->dev.group_rec);
+        d_desc, desc_words, d_hdr, fast_rec_bytes(f), fast_tbl_off(f), f->dev.group_rec);
     count_launch();
     BI_CUDA(cudaGetLastError());
     return BARTINT_OK;

@@ -15,6 +15,14 @@ from bartint_testlib import kat_forest
 
 pytestmark = pytest.mark.gpu
 
+@pytest.fixture(params=["gather", "table"], autouse=True)
+def kernel_kind(request, monkeypatch):
+    """Every parity test runs against both fast kernels: the register-gather kernel (default for d <= 16) and the
+    shared-memory table kernel (forced with BARTINT_KERNEL=table; the default for d > 16)."""
+    monkeypatch.setenv("BARTINT_KERNEL", request.param)
+    return request.param
+
+
 RTOL = 1e-6            # the north-star tolerance
 TIGHT = 1e-11          # what fp64 accumulation should actually give
 
@@ -89,11 +97,11 @@ def test_predict_and_reductions(small_case, walk):
 
 
 @pytest.mark.parametrize("bits", [4, 5, 6, 7, 8])
-def test_table_bits_variants(small_case, bits, monkeypatch):
+def test_table_bits_variants(small_case, bits, monkeypatch, kernel_kind):
     ff, _, _, X = small_case
     monkeypatch.setenv("BARTINT_TABLE_BITS", str(bits))
     f = Forest.from_soa(ff)
-    assert f.table_bits == bits
+    assert f.table_bits == (min(bits, 5) if kernel_kind == "gather" else bits)
     if not f.table_kernel_ok:
         pytest.skip("forest does not fit")
     out = f.eval(X, want=("draw_mean", "point_var"))
@@ -333,4 +341,23 @@ def test_device_point_generation(small_case, measure):
     assert (np.abs(mc - exact) <= 5 * se + 1e-12).all()
     for p in (pts, a, b):
         p.close()
+    f.close()
+
+
+@pytest.mark.parametrize("d", [1, 5, 8, 9, 12, 13, 16, 17, 24])
+def test_dimension_sweep_both_kernels(d, kernel_kind):
+    """The gather kernel's register layouts (2, 3, 4 code words per point) and the table kernel beyond 16 variables."""
+    rng = np.random.default_rng(100 + d)
+    x_train = rng.random((50, d))
+    ff = synth.prior_forest(d, 7, 11, x_train, rng.normal(size=50))
+    X = rng.random((4500, d))
+    f = Forest.from_soa(ff)
+    P = onp.predict(ff, X)
+    out = f.eval(X, want=("draw_mean", "point_var", "full_pred"))
+    assert f.last_eval_profile(True)["table_kernel"]
+    span = ff.y_max - ff.y_min                 # the response is N(0,1): predictions cross zero, so scale by the range
+    _assert_close(out["full_pred"], P, 1e-13, scale=span)
+    _assert_close(out["draw_mean"], onp.row_means(P), 1e-13, scale=span)
+    _assert_close(out["point_var"], onp.col_vars(P), 1e-9, scale=np.maximum(onp.col_vars(P), 1e-12))
+    assert np.array_equal(f.leaf_indices(X[:600], use_table_kernel=True), onp.leaf_ordinals(ff, X[:600]))
     f.close()
