@@ -149,8 +149,23 @@ __global__ void __launch_bounds__(TG_THREADS, MOMENTS ? 2 : 3) eval_gather_kerne
             walk_mask |= (unsigned long long)__ballot_sync(0xffffffffu, (fl & TK_FLAG_WALK) != 0u) << base;
             end_mask |= (unsigned long long)__ballot_sync(0xffffffffu, (fl & TK_FLAG_END_DRAW) != 0u) << base;
         }
+        // plain groups (no flag) run in a tight loop; the next flagged group is found with one ffs on the masks
+        auto table_group = [&](const unsigned char* rec) {
+            const uint4 da = *reinterpret_cast<const uint4*>(rec + TK_HDR);            // smem broadcast loads
+            const uint32_t d4 = *reinterpret_cast<const uint32_t*>(rec + TK_HDR + 16);
+            const unsigned char* __restrict__ tbl = rec + tg_tbl_off();
+#pragma unroll
+            for (int p = 0; p < P; ++p)
+                acc[p] += *reinterpret_cast<const double*>(tbl + gather_offset<R>(creg[p], da.x, da.y, da.z, da.w, d4));
+        };
+        int g = 0;
 #pragma unroll 1
-        for (int g = 0; g < ng; ++g) {
+        while (g < ng) {
+            const unsigned long long special = (walk_mask | end_mask) >> g;
+            const int g_stop = special ? min(ng, g + __ffsll((long long)special) - 1) : ng;
+#pragma unroll 1
+            for (; g < g_stop; ++g) table_group(stage + g * REC);
+            if (g >= ng) break;
             const unsigned char* rec = stage + g * REC;
             if ((walk_mask >> g) & 1ull) {
                 // rare: a tree that does not fit a group, walked per point from global memory (L1/L2)
@@ -168,12 +183,7 @@ __global__ void __launch_bounds__(TG_THREADS, MOMENTS ? 2 : 3) eval_gather_kerne
                     acc[p] += wmu[r.y];
                 }
             } else {
-                const uint4 da = *reinterpret_cast<const uint4*>(rec + TK_HDR);            // smem broadcast loads
-                const uint32_t d4 = *reinterpret_cast<const uint32_t*>(rec + TK_HDR + 16);
-                const unsigned char* __restrict__ tbl = rec + tg_tbl_off();
-#pragma unroll
-                for (int p = 0; p < P; ++p)
-                    acc[p] += *reinterpret_cast<const double*>(tbl + gather_offset<R>(creg[p], da.x, da.y, da.z, da.w, d4));
+                table_group(rec);
             }
             if ((end_mask >> g) & 1ull) {
                 // ---- draw epilogue: fold f_s(x) into the per-point moments and the per-draw sum ----
@@ -202,6 +212,7 @@ __global__ void __launch_bounds__(TG_THREADS, MOMENTS ? 2 : 3) eval_gather_kerne
                 if (lane == 0) s_wsum[(par * GS + (draws_done - stage_first_draw)) * NWARP + warp] = dsum;
                 ++draws_done;
             }
+            ++g;
         }
         __syncthreads();   // every thread is done with stage buffer b and has published its warp sums
         if (tid == 0 && k + TK_NSTAGE < n_stages) {
