@@ -214,10 +214,35 @@ __global__ void __launch_bounds__(T, (T > 256) ? 2 : ((MOMENTS || Q > 2) ? 2 : 3
             walk_mask |= (unsigned long long)__ballot_sync(0xffffffffu, (fl & TK_FLAG_WALK) != 0u) << base;
             end_mask |= (unsigned long long)__ballot_sync(0xffffffffu, (fl & TK_FLAG_END_DRAW) != 0u) << base;
         }
-#pragma unroll 1
-        for (int g = 0; g < ng; ++g) {
-            const unsigned char* rec = stage + g * REC;
+        // plain groups (no flag) run in a tight loop; the next flagged group is found with one ffs on the masks
+        auto table_group = [&](const unsigned char* rec) {
             const uint2* __restrict__ cur_desc = reinterpret_cast<const uint2*>(rec + TK_HDR);   // smem broadcast loads
+            const unsigned char* __restrict__ tbl = rec + tk_tbl_off(NB);
+            uint32_t A[Q];
+#pragma unroll
+            for (int q = 0; q < Q; ++q) A[q] = 0u;
+#pragma unroll
+            for (int j = 0; j < NB; ++j) {
+                const uint2 dj = cur_desc[j];                                // {variable, bias x4}
+                const uint32_t* __restrict__ row = reinterpret_cast<const uint32_t*>(my_codes + dj.x * TILE);
+#pragma unroll
+                for (int q = 0; q < Q; ++q) A[q] = pred_step<NB>(A[q], row[q * T], dj.y, j);
+            }
+#pragma unroll
+            for (int q = 0; q < Q; ++q)
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                    acc[q * 4 + kk] += *reinterpret_cast<const double*>(tbl + table_offset<NB>(A[q], kk));
+        };
+        int g = 0;
+#pragma unroll 1
+        while (g < ng) {
+            const unsigned long long special = (walk_mask | end_mask) >> g;
+            const int g_stop = special ? min(ng, g + __ffsll((long long)special) - 1) : ng;
+#pragma unroll 1
+            for (; g < g_stop; ++g) table_group(stage + g * REC);
+            if (g >= ng) break;
+            const unsigned char* rec = stage + g * REC;
             if ((walk_mask >> g) & 1ull) {
                 // rare: a tree with more than NB internal nodes, walked per point from global memory (L1/L2)
                 const int64_t kt = reinterpret_cast<const uint32_t*>(rec)[1];
@@ -248,22 +273,7 @@ __global__ void __launch_bounds__(T, (T > 256) ? 2 : ((MOMENTS || Q > 2) ? 2 : 3
                     for (int kk = 0; kk < 4; ++kk) acc[q * 4 + kk] += wmu[r[kk].y];
                 }
             } else {
-                const unsigned char* __restrict__ tbl = rec + tk_tbl_off(NB);
-                uint32_t A[Q];
-#pragma unroll
-                for (int q = 0; q < Q; ++q) A[q] = 0u;
-#pragma unroll
-                for (int j = 0; j < NB; ++j) {
-                    const uint2 dj = cur_desc[j];                                // {variable, bias x4}
-                    const uint32_t* __restrict__ row = reinterpret_cast<const uint32_t*>(my_codes + dj.x * TILE);
-#pragma unroll
-                    for (int q = 0; q < Q; ++q) A[q] = pred_step<NB>(A[q], row[q * T], dj.y, j);
-                }
-#pragma unroll
-                for (int q = 0; q < Q; ++q)
-#pragma unroll
-                    for (int kk = 0; kk < 4; ++kk)
-                        acc[q * 4 + kk] += *reinterpret_cast<const double*>(tbl + table_offset<NB>(A[q], kk));
+                table_group(rec);
             }
             if ((end_mask >> g) & 1ull) {
                 // ---- draw epilogue: fold f_s(x) into the per-point moments and the per-draw sum ----
@@ -292,6 +302,7 @@ __global__ void __launch_bounds__(T, (T > 256) ? 2 : ((MOMENTS || Q > 2) ? 2 : 3
                 if (lane == 0) s_wsum[(par * GS + (draws_done - stage_first_draw)) * NWARP + warp] = dsum;
                 ++draws_done;
             }
+            ++g;
         }
         __syncthreads();   // every thread is done with stage buffer b and has published its warp sums
         if (tid == 0 && k + TK_NSTAGE < n_stages) {
