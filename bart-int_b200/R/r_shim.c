@@ -61,7 +61,7 @@ SEXP bartint_R_forest(SEXP trees, SEXP fits, SEXP x, SEXP cuts, SEXP ymin, SEXP 
 /* sampleIntegrals(model, dim, measure): src/BARTInt.R:204-223.  n_draws_used <= 0 -> all draws. */
 SEXP bartint_R_exact_integrals(SEXP ptr, SEXP measure, SEXP n_draws_used) {
     bartint_forest* f = forest_of(ptr);
-    int64_t info[10];
+    int64_t info[12];
     check(bartint_forest_info(f, info));
     int n = Rf_asInteger(n_draws_used);
     if (n <= 0 || n > info[0]) n = (int)info[0];
@@ -75,7 +75,7 @@ SEXP bartint_R_exact_integrals(SEXP ptr, SEXP measure, SEXP n_draws_used) {
  * Replaces predict(model, X) / colVars / rowMeans: BARTInt.R:312-314, bartMean.R:47-50,74-82. */
 SEXP bartint_R_eval(SEXP ptr, SEXP x, SEXP weights, SEXP what) {
     bartint_forest* f = forest_of(ptr);
-    int64_t info[10];
+    int64_t info[12];
     check(bartint_forest_info(f, info));
     SEXP xdim = Rf_getAttrib(x, R_DimSymbol);
     const int64_t N = INTEGER(xdim)[0];

@@ -159,11 +159,13 @@ int bartint_forest_from_soa(int32_t S, int32_t m, int32_t d, const int64_t* tree
     return finish_forest(f, out);
 }
 
-int bartint_forest_info(const bartint_forest* f, int64_t info[10]) {
+int bartint_forest_info(const bartint_forest* f, int64_t info[12]) {
     BI_REQUIRE(f != nullptr && info != nullptr, BARTINT_ERR_ARG, "NULL argument");
     info[0] = f->S; info[1] = f->m; info[2] = f->d; info[3] = f->n_nodes; info[4] = f->n_leaves;
     info[5] = f->max_depth; info[6] = f->max_internal; info[7] = f->table_ok ? 1 : 0; info[8] = f->n_groups;
     info[9] = f->nb;
+    info[10] = f->table_ok ? (f->gather ? 2 : 1) : 0;
+    info[11] = f->gather ? f->g_regs : 0;
     return BARTINT_OK;
 }
 
@@ -231,6 +233,7 @@ int bartint_points_from_device(const bartint_forest* f, const double* dX, int64_
     DeviceGuard g(f->device);
     rc = launch_bin_points(dX, ld, N, d, f->dev.cut_off, f->dev.cut_val, f->max_cuts, (*out)->codes, (*out)->Npad,
                            (cudaStream_t)stream);
+    // (a one-pass kernel writing both layouts was tried and was slower: its 1-byte feature-major stores are 32 B per warp)
     if (rc == BARTINT_OK && (*out)->codes_pm)
         rc = launch_repack_codes((*out)->codes, (*out)->Npad, d, (*out)->codes_pm, (cudaStream_t)stream);
     if (rc) { bartint_points_destroy(*out); *out = nullptr; }

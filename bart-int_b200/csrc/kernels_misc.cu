@@ -261,15 +261,31 @@ __device__ __forceinline__ void chan_merge(double& n, double& mean, double& m2, 
     n = tot;
 }
 
-__global__ void merge_point_parts_kernel(const double* __restrict__ pt_mean, const double* __restrict__ pt_m2,
-                                         int n_chunks, int chunk_draws, int ndraws, int64_t N,
-                                         double* __restrict__ mean_out, double* __restrict__ m2_out) {
+// Chan merge of the draw chunks in chunk order.  The merge weights nb/tot and n*nb/tot depend only on the chunk sizes,
+// so they are computed once per CTA (shared memory); the per-point dependent chain is then 4 fp64 ops per chunk with
+// no division, and the loads of later chunks are in flight while earlier ones are merged.
+__global__ void __launch_bounds__(256) merge_point_parts_kernel(const double* __restrict__ pt_mean,
+                                                                const double* __restrict__ pt_m2, int n_chunks,
+                                                                int chunk_draws, int ndraws, int64_t N,
+                                                                double* __restrict__ mean_out, double* __restrict__ m2_out) {
+    extern __shared__ double s_w[];          // [2][n_chunks]: w1 = nb/tot, w2 = n*nb/tot  (n = draws merged so far)
+    for (int c = threadIdx.x; c < n_chunks; c += blockDim.x) {
+        const double n = (double)min(c * chunk_draws, ndraws);
+        const double nb = (double)min(chunk_draws, ndraws - c * chunk_draws);
+        const double tot = n + nb;
+        s_w[c] = nb / tot;
+        s_w[n_chunks + c] = n * nb / tot;
+    }
+    __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
-    double n = 0.0, mean = 0.0, m2 = 0.0;
-    for (int c = 0; c < n_chunks; ++c) {
-        int cnt = min(chunk_draws, ndraws - c * chunk_draws);
-        chan_merge(n, mean, m2, (double)cnt, pt_mean[(int64_t)c * N + i], pt_m2[(int64_t)c * N + i]);
+    double mean = pt_mean[i], m2 = pt_m2[i];             // chunk 0
+#pragma unroll 4
+    for (int c = 1; c < n_chunks; ++c) {
+        const double mb = pt_mean[(int64_t)c * N + i], m2b = pt_m2[(int64_t)c * N + i];
+        const double delta = mb - mean;
+        mean = fma(delta, s_w[c], mean);
+        m2 = fma(delta * delta, s_w[n_chunks + c], m2 + m2b);
     }
     mean_out[i] = mean;
     m2_out[i] = m2;
@@ -278,8 +294,8 @@ __global__ void merge_point_parts_kernel(const double* __restrict__ pt_mean, con
 int launch_merge_point_parts(const double* pt_mean, const double* pt_m2, int n_chunks, int chunk_draws, int ndraws,
                              int64_t N, double* mean_out, double* m2_out, cudaStream_t st) {
     if (N == 0) return BARTINT_OK;
-    merge_point_parts_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(pt_mean, pt_m2, n_chunks, chunk_draws,
-                                                                          ndraws, N, mean_out, m2_out);
+    merge_point_parts_kernel<<<(unsigned)((N + 255) / 256), 256, 2 * sizeof(double) * (size_t)n_chunks, st>>>(
+        pt_mean, pt_m2, n_chunks, chunk_draws, ndraws, N, mean_out, m2_out);
     count_launch();
     BI_CUDA(cudaGetLastError());
     return BARTINT_OK;

@@ -164,11 +164,12 @@ class Forest:
 
     def __init__(self, handle: int):
         self._h = C.c_void_p(handle)
-        info = (C.c_int64 * 10)()
+        info = (C.c_int64 * 12)()
         _check(_lib.load().bartint_forest_info(self._h, info))
         (self.S, self.m, self.d, self.n_nodes, self.n_leaves, self.max_depth, self.max_internal, tk, self.n_groups,
-         self.table_bits) = [int(v) for v in info]
-        self.table_kernel_ok = bool(tk)
+         self.table_bits, kind, self.gather_words) = [int(v) for v in info]
+        self.table_kernel_ok = bool(tk)                                  # a fast kernel (table or gather) applies
+        self.fast_kernel = {0: "none", 1: "table", 2: "gather"}[kind]
         self.y_min = self.y_max = None
 
     # ---- constructors ----

@@ -304,30 +304,54 @@ def run_ours(args):
     alg_bytes = N * d * 1 + S * m * 26 + 8 * S            # uint8 codes + compact forest + per-draw sums
     evals_k1 = S * m * N
     sm_mhz = (clocks or {}).get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
-    # on-chip ceiling of the table kernel: shared-memory wavefronts and issue slots per (group, point)
+    # on-chip ceilings of the evaluation kernel: per warp and group, a warp covers 32 * P
+    # (group, point) pairs.  Shared-memory pipe: 1 wavefront / clk / SM.  Issue: 4 warp-instructions / clk / SM.
     f0 = forests[0]
     trees_per_group = S * m / max(f0.n_groups, 1)
     nb = f0.table_bits
-    # ideal shared-memory wavefronts per warp per group (conflict-free): nb/2 descriptor LDS.128 + nb*Q code LDS.32
-    # + P table LDS.64 (2 wavefronts each) + 1 header; a warp-group covers 32*P (group, point) pairs
-    wf = nb / 2.0 + nb * 2.0 + 8 * 2.0 + 1.0
-    lsu_bound = 148 * sm_mhz * 1e6 * (32 * 8) * trees_per_group / wf
+    if f0.fast_kernel == "gather":
+        pts = 8                                          # points per thread
+        wavefronts = pts * 2.0 + 2.0                     # P table LDS.64 (2 wavefronts each, conflict-free) + 2 descriptor loads
+        instrs = pts * 10.0 + 2.0 + 5.0                  # (PRMT, IADD, PRMT, IDP) x 2 rounds + LDS + DADD per point; descriptors; loop
+    else:
+        pts = 16
+        wavefronts = nb / 2.0 + nb * 4.0 + pts * 2.0     # descriptor LDS.128 + code LDS.32 per (node, quad) + table LDS.64
+        instrs = nb * (2.0 + 4 * 4.0) + pts * 3.0 + nb / 2.0 + 5.0
+    per_warp = 32 * pts * trees_per_group                # tree-evals per warp-group
+    lsu_bound = 148 * sm_mhz * 1e6 * per_warp / wavefronts
+    issue_bound = 148 * sm_mhz * 1e6 * per_warp / (instrs / 4.0)
+    onchip_bound = min(lsu_bound, issue_bound)
     roofline = {
-        "kernel": "eval_table_kernel (MC points)", "bound": "hbm", "achieved": alg_bytes / (k1_ms * 1e-3) / 1e9,
+        "kernel": f"eval_{f0.fast_kernel}_kernel (MC points)", "bound": "hbm", "achieved": alg_bytes / (k1_ms * 1e-3) / 1e9,
         "peak": hbm_peak, "unit": "GB/s", "frac": alg_bytes / (k1_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
         "peak_source": peak_src, "alg_bytes_per_launch": alg_bytes, "alg_bytes_per_eval": alg_bytes / evals_k1,
         "kernel_ms": k1_ms, "evals_per_s_kernel": evals_k1 / (k1_ms * 1e-3),
         "note": "The path is NOT HBM-bound (SURVEY 8d): compulsory traffic is ~2e-4 B per tree-eval, so the HBM "
-                "fraction is tiny by construction; the binding resources are shared-memory wavefronts and issue slots.",
+                "fraction is tiny by construction; the binding resources are issue slots and shared-memory wavefronts "
+                "(onchip_* fields; model in DESIGN.md section 3).",
         "equiv_stream_gbs": 32.0 * evals_k1 / (k1_ms * 1e-3) / 1e9,
         "hbm_fraction_equiv_stream": 32.0 * evals_k1 / (k1_ms * 1e-3) / 1e9 / hbm_peak,
-        "smem_bound_evals_per_s": lsu_bound, "smem_bound_fraction": evals_k1 / (k1_ms * 1e-3) / lsu_bound,
-        "sm_clock_mhz": sm_mhz, "trees_per_group": trees_per_group, "table_bits": nb,
+        "smem_bound_evals_per_s": lsu_bound, "issue_bound_evals_per_s": issue_bound,
+        "onchip_bound_evals_per_s": onchip_bound, "onchip_bound_fraction": evals_k1 / (k1_ms * 1e-3) / onchip_bound,
+        "smem_bound_fraction": evals_k1 / (k1_ms * 1e-3) / lsu_bound,
+        "sm_clock_mhz": sm_mhz, "trees_per_group": trees_per_group, "table_bits": nb, "fast_kernel": f0.fast_kernel,
     }
+    # DRAM traffic per launch from the committed ncu --set full captures (profiles/ncu_traffic.json), same workload
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    except Exception:
+        traffic = {}
+    if not args.points and not args.draws:
+        roofline["traffic"] = traffic.get(f"eval_{f0.fast_kernel}_kernel")
     k0 = float(np.median(k0_ms))
-    roofline_k0 = {"kernel": "bin_points_kernel", "bound": "hbm", "achieved": 9.0 * N * d / (k0 * 1e-3) / 1e9,
-                   "peak": hbm_peak, "unit": "GB/s", "frac": 9.0 * N * d / (k0 * 1e-3) / 1e9 / hbm_peak,
-                   "traffic": None, "kernel_ms": k0, "alg_bytes_per_launch": 9 * N * d, "peak_source": peak_src}
+    pm = f0.fast_kernel == "gather"                       # + repack_codes_kernel: codes -> 16 B packed record per point
+    k0_name = "bin_points_kernel+repack_codes_kernel" if pm else "bin_points_kernel"
+    k0_bytes = 9 * N * d + ((N * d + 16 * N) if pm else 0)   # fp64 in, uint8 out (+ re-read codes, packed layout out)
+    roofline_k0 = {"kernel": k0_name, "bound": "hbm", "achieved": k0_bytes / (k0 * 1e-3) / 1e9,
+                   "peak": hbm_peak, "unit": "GB/s", "frac": k0_bytes / (k0 * 1e-3) / 1e9 / hbm_peak,
+                   "traffic": traffic.get("bin_points_kernel") if not args.points else None, "kernel_ms": k0,
+                   "alg_bytes_per_launch": k0_bytes, "peak_source": peak_src,
+                   "note": "timed with events around the whole points_from_device call (allocation + launch gap included)"}
 
     # ---- CPU baseline beside it (oracle port, bounded sample, this box's host cores) ----
     cpu = None

@@ -84,9 +84,10 @@ int bartint_forest_from_soa(int32_t S, int32_t m, int32_t d, const int64_t* tree
                             const int32_t* cut_offsets, const double* cut_values,
                             double y_min, double y_max, bartint_forest** out);
 
-/* info[0..9] = S, m, d, n_nodes, n_leaves, max_depth, max_internal_nodes_per_tree,
- *              table_kernel_ok (0/1), n_table_groups, table_bits */
-int bartint_forest_info(const bartint_forest* f, int64_t info[10]);
+/* info[0..11] = S, m, d, n_nodes, n_leaves, max_depth, max_internal_nodes_per_tree,
+ *               fast_kernel_ok (0/1), n_groups, table_bits, fast kernel kind (0 none, 1 table, 2 gather),
+ *               gather code words per point */
+int bartint_forest_info(const bartint_forest* f, int64_t info[12]);
 /* read the canonical (pre-order) flattening back; arrays sized from info[3] */
 int bartint_forest_export_soa(const bartint_forest* f, int64_t* tree_node_offset, int32_t* split_var,
                               int32_t* split_cut_idx, int32_t* left, int32_t* right, double* leaf_mu);
