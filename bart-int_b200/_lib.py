@@ -50,6 +50,7 @@ SIGNATURES = {
                                              C.c_void_p, C.c_void_p, C.c_void_p]),
     "bartint_merge_moments_device": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int32, c_int32_p, C.c_void_p, C.c_void_p,
                                                C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bartint_argmax_ties_device": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "bartint_leaf_indices": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, c_int32_p]),
     "bartint_exact_integrals": (C.c_int, [C.c_void_p, C.c_int32, c_double_p, c_double_p, C.c_int32, c_double_p]),
     "bartint_exact_integrals_device": (C.c_int, [C.c_void_p, C.c_int32, c_double_p, c_double_p, C.c_int32, C.c_void_p,

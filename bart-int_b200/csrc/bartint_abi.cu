@@ -385,6 +385,11 @@ int bartint_merge_moments_device(const bartint_forest* f, uint32_t flags, int32_
     return rc;
 }
 
+int bartint_argmax_ties_device(const double* d_values, int64_t n, int64_t* d_out, void* stream) {
+    BI_REQUIRE(d_out != nullptr && n >= 0 && (n == 0 || d_values != nullptr), BARTINT_ERR_ARG, "bad arguments");
+    return launch_argmax_ties(d_values, n, d_out, (cudaStream_t)stream);
+}
+
 int bartint_eval_points(const bartint_forest* f, const bartint_points* p, uint32_t flags, int32_t draw_begin,
                         int32_t draw_end, const double* weights, int64_t weights_len, double* draw_mean,
                         double* point_mean, double* point_var, double* full_pred) {

@@ -560,6 +560,54 @@ int launch_draw_summary(const double* d_draw_mean, int ndraws, double* d_mean_va
     return BARTINT_OK;
 }
 
+// which(var == max(var)) (BARTInt.R:315,387; bartMean.R:51): index of the first maximum and the number of ties.  One CTA;
+// any NaN makes the result {-1, 0} (R: max() is NaN and the tie set is empty).
+__global__ void __launch_bounds__(256) argmax_ties_kernel(const double* __restrict__ v, int64_t n, int64_t* __restrict__ out) {
+    __shared__ double s_max[256];
+    __shared__ long long s_idx[256];
+    __shared__ long long s_cnt[256];
+    __shared__ int s_nan;
+    const int t = threadIdx.x;
+    if (t == 0) s_nan = 0;
+    __syncthreads();
+    double best = -INFINITY;
+    long long bi = -1;
+    for (int64_t i = t; i < n; i += 256) {
+        const double x = v[i];
+        if (x != x) s_nan = 1;
+        if (x > best || bi < 0) { best = x; bi = i; }
+    }
+    s_max[t] = best; s_idx[t] = bi;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if (t < w && s_idx[t + w] >= 0 &&
+            (s_idx[t] < 0 || s_max[t + w] > s_max[t] || (s_max[t + w] == s_max[t] && s_idx[t + w] < s_idx[t]))) {
+            s_max[t] = s_max[t + w]; s_idx[t] = s_idx[t + w];
+        }
+        __syncthreads();
+    }
+    const double m = s_max[0];
+    long long cnt = 0;
+    for (int64_t i = t; i < n; i += 256) cnt += (v[i] == m);
+    s_cnt[t] = cnt;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if (t < w) s_cnt[t] += s_cnt[t + w];
+        __syncthreads();
+    }
+    if (t == 0) {
+        out[0] = (s_nan || n == 0) ? -1 : s_idx[0];
+        out[1] = (s_nan || n == 0) ? 0 : s_cnt[0];
+    }
+}
+
+int launch_argmax_ties(const double* d_v, int64_t n, int64_t* d_out, cudaStream_t st) {
+    argmax_ties_kernel<<<1, 256, 0, st>>>(d_v, n, d_out);
+    count_launch();
+    BI_CUDA(cudaGetLastError());
+    return BARTINT_OK;
+}
+
 int launch_finalize_integrals(const double* d_in, int n, double y_min, double y_max, double* d_rescaled,
                               double* d_mean_sd, cudaStream_t st) {
     finalize_integrals_kernel<<<1, 256, 0, st>>>(d_in, n, y_min, y_max, d_rescaled, d_mean_sd);

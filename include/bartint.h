@@ -155,6 +155,11 @@ int bartint_eval_points_device(const bartint_forest* f, const bartint_points* p,
 int bartint_finalize_draws_device(const bartint_forest* f, uint32_t flags, const double* d_draw_sum, int32_t ndraws,
                                   int64_t n_points, double* d_draw_mean, double* d_mean_var, void* stream);
 
+/* which(var == max(var)) on the device (src/BARTInt.R:315,387; bartMean.R:51): d_out[0] = 0-based index of the
+ * first maximum, d_out[1] = number of elements equal to it; {-1, 0} if any value is NaN or n == 0.  The random tie
+ * break -- and R's sample(scalar) quirk, SURVEY App. B2 -- stay with the caller. */
+int bartint_argmax_ties_device(const double* d_values, int64_t n, int64_t* d_out, void* stream);
+
 /* Chan merge of G draw-shards' per-point moments (device pointers, shard-major [g*N + i]);
  * then  var = M2/(n-1) * scale^2 * weight  and  mean = y0 + scale*(0.5 + mean)  with
  * scale = y_max - y_min, y0 = y_min (or scale = 1, y0 = -0.5 for BARTINT_SCALED_UNITS).     */

@@ -361,3 +361,60 @@ def test_dimension_sweep_both_kernels(d, kernel_kind):
     _assert_close(out["point_var"], onp.col_vars(P), 1e-9, scale=np.maximum(onp.col_vars(P), 1e-12))
     assert np.array_equal(f.leaf_indices(X[:600], use_table_kernel=True), onp.leaf_ordinals(ff, X[:600]))
     f.close()
+
+
+def test_argmax_ties_device():
+    import ctypes as C
+    import torch
+    from bartint_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(1)
+    for case in range(6):
+        v = rng.random(1000 + case)
+        if case == 1:
+            v[[5, 700, 333]] = 2.0                    # ties
+        if case == 2:
+            v[17] = np.nan
+        if case == 3:
+            v[:] = 0.25                               # everything ties
+        if case == 4:
+            v = -rng.random(7) - 5.0                  # all negative, short
+        t = torch.from_numpy(v).cuda()
+        out = torch.zeros(2, dtype=torch.int64, device="cuda")
+        assert lib.bartint_argmax_ties_device(C.c_void_p(t.data_ptr()), v.size, C.c_void_p(out.data_ptr()), None) == 0
+        idx, ties = out.cpu().tolist()
+        if np.isnan(v).any():
+            assert (idx, ties) == (-1, 0)
+        else:
+            which = np.nonzero(v == v.max())[0]       # R: which(var == max(var))
+            assert idx == which[0] and ties == len(which)
+
+
+def test_random_shapes_property(kernel_kind):
+    """Seeded sweep over ragged shapes: S, m, d, N, draw sub-ranges, weights -- CUDA == oracle every time."""
+    rng = np.random.default_rng(2024)
+    for trial in range(12):
+        d = int(rng.integers(1, 21)); S = int(rng.integers(1, 9)); m = int(rng.integers(1, 13))
+        N = int(rng.choice([1, 3, 31, 257, 2047, 2048, 2049, 4097, 6000]))
+        x_train = rng.random((int(rng.integers(2, 60)), d))
+        ff = synth.prior_forest(int(rng.integers(1 << 30)), S, m, x_train, rng.normal(size=len(x_train)),
+                                numcut=int(rng.choice([1, 2, 7, 100, 127])))
+        X = rng.random((N, d)) * 1.4 - 0.2
+        f = Forest.from_soa(ff)
+        lo = int(rng.integers(0, S)); hi = int(rng.integers(lo + 1, S + 1))
+        w = rng.random(N)
+        out = f.eval(X, weights=w, want=("draw_mean", "point_mean", "point_var"), draws=(lo, hi))
+        P = onp.predict(ff, X)[lo:hi]
+        span = max(ff.y_max - ff.y_min, 1e-300)
+        _assert_close(out["draw_mean"], onp.row_means(P), 1e-12, scale=span, msg=f"trial {trial}")
+        _assert_close(out["point_mean"], P.mean(axis=0), 1e-12, scale=span, msg=f"trial {trial}")
+        if hi - lo > 1:
+            _assert_close(out["point_var"], onp.col_vars(P) * w, 1e-9,
+                          scale=np.maximum(onp.col_vars(P) * w, 1e-12 * span ** 2), msg=f"trial {trial}")
+        else:
+            assert np.isnan(out["point_var"]).all()
+        assert np.array_equal(f.leaf_indices(X, draws=(lo, hi)), onp.leaf_ordinals(ff, X)[lo * m:hi * m])
+        if f.table_kernel_ok:
+            assert np.array_equal(f.leaf_indices(X, draws=(lo, hi), use_table_kernel=True),
+                                  onp.leaf_ordinals(ff, X)[lo * m:hi * m])
+        f.close()
