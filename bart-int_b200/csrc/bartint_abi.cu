@@ -459,14 +459,107 @@ int bartint_eval_points(const bartint_forest* f, const bartint_points* p, uint32
     return BARTINT_OK;
 }
 
+// One-shot host-buffer evaluation.  Large matrices are processed as a pipeline over row blocks: the host->device copy
+// of block k+1 (copy stream) overlaps the binning + evaluation of block k (compute stream); per-block draw sums are
+// added in block order, per-point outputs land at their offsets.  Results do not depend on the block count up to the
+// fp64 summation order of the per-draw sums (fixed by N alone).
 int bartint_eval(const bartint_forest* f, const double* X, int64_t N, int32_t d, uint32_t flags, const double* weights,
                  int64_t weights_len, double* draw_mean, double* point_mean, double* point_var, double* full_pred) {
     BI_REQUIRE(f != nullptr, BARTINT_ERR_ARG, "forest is NULL");
-    bartint_points* p = nullptr;
-    int rc = bartint_points_from_host(f, X, N, d, &p);
-    if (rc) return rc;
-    rc = bartint_eval_points(f, p, flags, 0, f->S, weights, weights_len, draw_mean, point_mean, point_var, full_pred);
-    bartint_points_destroy(p);
+    BI_REQUIRE(N >= 0 && (N * d == 0 || X != nullptr), BARTINT_ERR_ARG, "X is NULL or N < 0");
+    BI_REQUIRE(d == f->d, BARTINT_ERR_ARG, "point matrix has %d columns but the forest was fit on %d variables", d, f->d);
+    constexpr int64_t kMinPipelined = 1 << 18;
+    if (N < kMinPipelined || full_pred != nullptr || f->S == 0) {      // small / full-matrix requests: single shot
+        bartint_points* p = nullptr;
+        int rc = bartint_points_from_host(f, X, N, d, &p);
+        if (rc) return rc;
+        rc = bartint_eval_points(f, p, flags, 0, f->S, weights, weights_len, draw_mean, point_mean, point_var, full_pred);
+        bartint_points_destroy(p);
+        return rc;
+    }
+    BI_REQUIRE(weights == nullptr || weights_len == 1 || weights_len == N, BARTINT_ERR_ARG,
+               "weights must have length 1 or N");
+    DeviceGuard g(f->device);
+    const int S = f->S;
+    const int scaled = (flags & BARTINT_SCALED_UNITS) ? 1 : 0;
+    const double scale = f->y_max - f->y_min, y0 = f->y_min;
+    const bool want_mom = point_mean != nullptr || point_var != nullptr;
+    const int K = 4;                                                   // row blocks
+    const int64_t blk = (((N + K - 1) / K + TK_NPAD - 1) / TK_NPAD) * TK_NPAD;
+    const int nblk = (int)((N + blk - 1) / blk);
+    cudaStream_t cs = nullptr, xs = nullptr;       // compute, copy
+    cudaEvent_t copied[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr};
+    double *dX[2] = {nullptr, nullptr}, *d_sums = nullptr, *d_sum = nullptr, *d_out = nullptr, *d_mean = nullptr,
+           *d_m2 = nullptr, *d_omean = nullptr, *d_ovar = nullptr, *d_w = nullptr;
+    int32_t* d_cnt = nullptr;
+    bartint_points* pts[2] = {nullptr, nullptr};
+    int rc = BARTINT_OK;
+    cudaError_t e = cudaSuccess;
+    auto ok = [&](cudaError_t err) { if (e == cudaSuccess && err != cudaSuccess) e = err; return e == cudaSuccess; };
+    ok(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+    ok(cudaStreamCreateWithFlags(&xs, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; ++k) {
+        ok(cudaEventCreateWithFlags(&copied[k], cudaEventDisableTiming));
+        ok(cudaEventCreateWithFlags(&consumed[k], cudaEventDisableTiming));
+        ok(cudaMallocAsync((void**)&dX[k], sizeof(double) * (size_t)blk * (size_t)d, cs));
+    }
+    ok(cudaMallocAsync((void**)&d_sums, sizeof(double) * (size_t)nblk * (size_t)S, cs));
+    ok(cudaMallocAsync((void**)&d_sum, sizeof(double) * (size_t)S, cs));
+    ok(cudaMallocAsync((void**)&d_out, sizeof(double) * (size_t)S, cs));
+    if (want_mom) {
+        ok(cudaMallocAsync((void**)&d_mean, sizeof(double) * (size_t)N, cs));
+        ok(cudaMallocAsync((void**)&d_m2, sizeof(double) * (size_t)N, cs));
+        ok(cudaMallocAsync((void**)&d_omean, sizeof(double) * (size_t)N, cs));
+        ok(cudaMallocAsync((void**)&d_ovar, sizeof(double) * (size_t)N, cs));
+        ok(cudaMallocAsync((void**)&d_cnt, sizeof(int32_t), cs));
+        if (weights != nullptr) {
+            ok(cudaMallocAsync((void**)&d_w, sizeof(double) * (size_t)weights_len, cs));
+            ok(cudaMemcpyAsync(d_w, weights, sizeof(double) * (size_t)weights_len, cudaMemcpyHostToDevice, cs));
+        }
+        ok(cudaMemcpyAsync(d_cnt, &S, sizeof(int32_t), cudaMemcpyHostToDevice, cs));
+    }
+    ok(cudaStreamSynchronize(cs));                 // buffers exist before the copy stream touches them
+    for (int k = 0; k < nblk && e == cudaSuccess && rc == BARTINT_OK; ++k) {
+        const int b = k & 1;
+        const int64_t r0 = (int64_t)k * blk, rows = std::min<int64_t>(blk, N - r0);
+        if (k >= 2) ok(cudaStreamWaitEvent(xs, consumed[b], 0));       // block k-2 has been binned out of dX[b]
+        ok(cudaMemcpy2DAsync(dX[b], sizeof(double) * (size_t)rows, X + r0, sizeof(double) * (size_t)N,
+                             sizeof(double) * (size_t)rows, (size_t)d, cudaMemcpyHostToDevice, xs));
+        ok(cudaEventRecord(copied[b], xs));
+        ok(cudaStreamWaitEvent(cs, copied[b], 0));
+        if (pts[b]) { bartint_points_destroy(pts[b]); pts[b] = nullptr; }
+        if (e != cudaSuccess) break;
+        rc = bartint_points_from_device(f, dX[b], rows, d, rows, cs, &pts[b]);
+        ok(cudaEventRecord(consumed[b], cs));
+        if (rc == BARTINT_OK)
+            rc = eval_core(f, pts[b], flags, 0, S, d_sums + (size_t)k * S, want_mom ? d_mean + r0 : nullptr,
+                           want_mom ? d_m2 + r0 : nullptr, nullptr, nullptr, scale, y0, scaled, cs);
+    }
+    if (e == cudaSuccess && rc == BARTINT_OK) rc = launch_reduce_draw_parts(d_sums, nblk, S, d_sum, cs);
+    if (e == cudaSuccess && rc == BARTINT_OK && draw_mean != nullptr)
+        rc = launch_finalize_draws(d_sum, S, N, scale, y0, scaled, d_out, cs);
+    if (e == cudaSuccess && rc == BARTINT_OK && want_mom)
+        rc = launch_merge_shards(d_mean, d_m2, 1, d_cnt, N, scale, y0, scaled, d_w, weights_len, d_omean, d_ovar, cs);
+    if (e == cudaSuccess && rc == BARTINT_OK) {
+        if (draw_mean) ok(cudaMemcpyAsync(draw_mean, d_out, sizeof(double) * (size_t)S, cudaMemcpyDeviceToHost, cs));
+        if (point_mean) ok(cudaMemcpyAsync(point_mean, d_omean, sizeof(double) * (size_t)N, cudaMemcpyDeviceToHost, cs));
+        if (point_var) ok(cudaMemcpyAsync(point_var, d_ovar, sizeof(double) * (size_t)N, cudaMemcpyDeviceToHost, cs));
+    }
+    if (cs) ok(cudaStreamSynchronize(cs));
+    if (xs) cudaStreamSynchronize(xs);
+    for (int k = 0; k < 2; ++k) {
+        if (pts[k]) bartint_points_destroy(pts[k]);
+        if (dX[k]) cudaFreeAsync(dX[k], cs);
+        if (copied[k]) cudaEventDestroy(copied[k]);
+        if (consumed[k]) cudaEventDestroy(consumed[k]);
+    }
+    double* tmp[] = {d_sums, d_sum, d_out, d_mean, d_m2, d_omean, d_ovar, d_w};
+    for (double* q : tmp)
+        if (q) cudaFreeAsync(q, cs);
+    if (d_cnt) cudaFreeAsync(d_cnt, cs);
+    if (cs) { cudaStreamSynchronize(cs); cudaStreamDestroy(cs); }
+    if (xs) cudaStreamDestroy(xs);
+    if (rc == BARTINT_OK && e != cudaSuccess) rc = cuda_fail(e, "bartint_eval pipeline", __FILE__, __LINE__);
     return rc;
 }
 

@@ -13,12 +13,31 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <ctime>
 
 #include "common.cuh"
 
 namespace bartint {
 
 static thread_local char g_err[512] = "";
+
+// BARTINT_TIMING=1: print the phases of forest construction to stderr (host wall clock)
+struct PhaseTimer {
+    bool on;
+    double t0;
+    static double now() {
+        timespec ts;
+        clock_gettime(CLOCK_MONOTONIC, &ts);
+        return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+    }
+    PhaseTimer() : on(getenv("BARTINT_TIMING") != nullptr), t0(now()) {}
+    void lap(const char* what) {
+        if (!on) return;
+        const double t = now();
+        fprintf(stderr, "[bartint] %-28s %8.3f ms\n", what, t - t0);
+        t0 = t;
+    }
+};
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -112,6 +131,7 @@ int parse_dbarts_forest(const char* const* tree_strings, const double* tree_fits
                         int64_t n, int32_t d, const int32_t* cut_offsets, const double* cut_values,
                         int32_t m, int32_t S, bartint_forest* f) {
     const int64_t n_trees = (int64_t)S * m;
+    PhaseTimer pt;
     // pass 1: a tree with K leaves ('.' characters) has 2K-1 nodes -> node offsets by prefix sum
     f->tree_off.assign((size_t)n_trees + 1, 0);
     int64_t bad_tree = -1;
@@ -140,6 +160,7 @@ int parse_dbarts_forest(const char* const* tree_strings, const double* tree_fits
     f->var.resize((size_t)nn); f->cut.resize((size_t)nn); f->left.resize((size_t)nn); f->right.resize((size_t)nn);
     f->mu.resize((size_t)nn);
     int bad_ref = 0;
+    pt.lap("exporter: count + cut map");
     // pass 2: parse in place, then recover the leaf values
 #pragma omp parallel
     {
@@ -182,6 +203,7 @@ int parse_dbarts_forest(const char* const* tree_strings, const double* tree_fits
             }
         }
     }
+    pt.lap("exporter: parse + leaf mu");
     if (bad_tree >= 0) {
         set_error("malformed dbarts tree string at tree %lld (draw %lld)", (long long)(bad_tree % m),
                   (long long)(bad_tree / m));
@@ -244,6 +266,7 @@ int canonicalise_soa(int32_t S, int32_t m, int32_t d, const int64_t* off, const 
 }
 
 int forest_finish_host(bartint_forest* f) {
+    PhaseTimer pt;
     const int64_t n_trees = (int64_t)f->S * f->m;
     f->n_nodes = f->tree_off[(size_t)n_trees];
     BI_REQUIRE(f->n_nodes < (int64_t)1 << 31, BARTINT_ERR_UNSUPPORTED, "forest has more than 2^31 nodes");
@@ -287,6 +310,7 @@ int forest_finish_host(bartint_forest* f) {
     f->n_leaves = n_leaves;
     f->max_depth = max_depth;
     f->max_internal = max_internal;
+    pt.lap("validate + stats");
     return BARTINT_OK;
 }
 
@@ -308,6 +332,7 @@ static int table_bits_from_env() {
 }
 
 int forest_upload(bartint_forest* f) {
+    PhaseTimer pt;
     const int64_t n_trees = (int64_t)f->S * f->m;
     const int64_t nn = f->n_nodes;
     std::vector<uint2> nodes((size_t)nn);
@@ -335,6 +360,7 @@ int forest_upload(bartint_forest* f) {
         }
     }
     int rc;
+    pt.lap("upload: pack walk form");
     if ((rc = upload(&f->dev.nodes, nodes))) return rc;
     if ((rc = upload(&f->dev.tree_off, tree_off))) return rc;
     if ((rc = upload(&f->dev.tree_leaf_off, leaf_off))) return rc;
@@ -342,6 +368,7 @@ int forest_upload(bartint_forest* f) {
     if ((rc = upload(&f->dev.cut_off, f->cut_off))) return rc;
     if ((rc = upload(&f->dev.cut_val, f->cut_val))) return rc;
 
+    pt.lap("upload: H2D walk form");
     // ---- fast-path planning: greedy packing of consecutive trees of a draw into groups of <= NB predicate bits ----
     f->nb = table_bits_from_env();
     // both fast kernels need 7-bit codes (byte-wise compare); the table kernel keeps the code rows of one CTA tile in
@@ -358,12 +385,7 @@ int forest_upload(bartint_forest* f) {
     }
     const int NB = f->nb;
     const int DW = f->gather ? TG_DESC / 4 : 2 * NB;       // descriptor words per group
-    std::vector<int32_t> group_tree_off;   // first tree of each group
-    std::vector<uint32_t> hdr;             // flags per group
-    std::vector<uint32_t> desc;            // DW words per group
     std::vector<uint8_t> node_bit((size_t)nn, 0);
-    f->draw_group_off.assign((size_t)f->S + 1, 0);
-    group_tree_off.reserve((size_t)(n_trees / 3 + f->S + 1));
     // Bit order inside a group: table lookups of lanes whose indices differ only in a HIGH bit hit the same bank pair
     // (a 2^NB x 8 B table wraps the 32 banks 2^(NB-4) times), lookups with equal indices are a broadcast.  The
     // predicates least likely to differ between points -- cuts nearest the edge of their variable's cut grid -- are
@@ -376,71 +398,82 @@ int forest_upload(bartint_forest* f) {
     // gather format: round 0 can address variables [0, 8), round 1 variables [base1, base1 + 8); 4 slots per round
     const int base1 = 4 * (f->g_regs - 2);
     struct Slot { int64_t node; int round, pos; };
-    std::vector<int64_t> gnodes;           // nodes of the group being filled (table format)
-    std::vector<Slot> gslots;              // nodes + their slots (gather format)
-    int used[2] = {0, 0};
-    auto close_group = [&]() {
-        uint32_t* gd = desc.empty() ? nullptr : &desc[desc.size() - (size_t)DW];
-        if (!f->gather) {
-            if (gnodes.empty()) return;
-            std::stable_sort(gnodes.begin(), gnodes.end(),
-                             [&](int64_t a, int64_t b2) { return extremeness(a) < extremeness(b2); });
-            for (size_t b2 = 0; b2 < gnodes.size(); ++b2) {
-                const size_t g = (size_t)gnodes[b2];
-                node_bit[g] = (uint8_t)b2;
-                gd[2 * b2] = (uint32_t)f->var[g];
-                gd[2 * b2 + 1] = (uint32_t)(127 - f->cut[g]) * 0x01010101u;
-            }
-            gnodes.clear();
-            return;
-        }
-        if (gslots.empty()) { used[0] = used[1] = 0; return; }
-        std::stable_sort(gslots.begin(), gslots.end(),
-                         [&](const Slot& a, const Slot& b2) { return extremeness(a.node) < extremeness(b2.node); });
-        uint32_t sel[2] = {0, 0}, bias[2] = {0, 0}, wgt[2] = {0, 0};
-        for (size_t b2 = 0; b2 < gslots.size(); ++b2) {
-            const Slot& sl = gslots[b2];
-            const size_t g = (size_t)sl.node;
-            node_bit[g] = (uint8_t)b2;
-            const uint32_t byte_in_bank = (uint32_t)(f->var[g] - (sl.round ? base1 : 0));       // 0..7
-            sel[sl.round] |= byte_in_bank << (4 * sl.pos);
-            bias[sl.round] |= (uint32_t)(127 - f->cut[g]) << (8 * sl.pos);
-            wgt[sl.round] |= ((uint32_t)(-(8 << b2)) & 0xFFu) << (8 * sl.pos);                // signed byte -(8 << bit)
-        }
-        gd[0] = sel[0] | (sel[1] << 16); gd[1] = bias[0]; gd[2] = bias[1]; gd[3] = wgt[0]; gd[4] = wgt[1];
-        gslots.clear();
-        used[0] = used[1] = 0;
+    // draws are independent: each is planned on its own (OpenMP) into a DrawPlan, then the plans are concatenated
+    struct DrawPlan {
+        std::vector<int32_t> group_tree_off;   // first tree of each group of the draw
+        std::vector<uint32_t> hdr;             // flags per group
+        std::vector<uint32_t> desc;            // DW words per group
     };
-    // try to place the internal nodes of tree [base, base+cnt) into the open gather group; all or nothing
-    auto place_tree = [&](int32_t base, int32_t cnt, int bits) -> bool {
-        const size_t mark = gslots.size();
-        int u[2] = {used[0], used[1]};
-        int nbits = bits;
-        for (int32_t a = 0; a < cnt; ++a) {
-            const size_t g = (size_t)(base + a);
-            if (f->var[g] < 0) continue;
-            const int v = f->var[g];
-            const bool in0 = v < 8, in1 = v >= base1 && v < base1 + 8;
-            int r = -1;
-            if (in0 && in1) r = (u[0] <= u[1]) ? 0 : 1;      // variable reachable from both rounds: take the emptier one
-            else if (in0) r = 0;
-            else if (in1) r = 1;
-            if (r >= 0 && u[r] >= 4) r = (r == 0 ? (in1 && u[1] < 4 ? 1 : -1) : (in0 && u[0] < 4 ? 0 : -1));
-            if (r < 0 || nbits >= NB) { gslots.resize(mark); return false; }
-            gslots.push_back(Slot{(int64_t)g, r, u[r]});
-            ++u[r];
-            ++nbits;
-        }
-        used[0] = u[0]; used[1] = u[1];
-        return true;
-    };
-    auto open_group = [&](int64_t k, uint32_t flags) {
-        group_tree_off.push_back((int32_t)k);
-        hdr.push_back(flags);
-        desc.resize(desc.size() + (size_t)DW, 0u);           // unused slots: bias 0 -> predicate 0, weight 0
-    };
+    std::vector<DrawPlan> plans((size_t)f->S);
+#pragma omp parallel for schedule(static)
     for (int32_t s = 0; s < f->S; ++s) {
-        f->draw_group_off[(size_t)s] = (int32_t)group_tree_off.size();
+        std::vector<int32_t>& group_tree_off = plans[(size_t)s].group_tree_off;
+        std::vector<uint32_t>& hdr = plans[(size_t)s].hdr;
+        std::vector<uint32_t>& desc = plans[(size_t)s].desc;
+        std::vector<int64_t> gnodes;           // nodes of the group being filled (table format)
+        std::vector<Slot> gslots;              // nodes + their slots (gather format)
+        int used[2] = {0, 0};
+        auto close_group = [&]() {
+            uint32_t* gd = desc.empty() ? nullptr : &desc[desc.size() - (size_t)DW];
+            if (!f->gather) {
+                if (gnodes.empty()) return;
+                std::stable_sort(gnodes.begin(), gnodes.end(),
+                                 [&](int64_t a, int64_t b2) { return extremeness(a) < extremeness(b2); });
+                for (size_t b2 = 0; b2 < gnodes.size(); ++b2) {
+                    const size_t g = (size_t)gnodes[b2];
+                    node_bit[g] = (uint8_t)b2;
+                    gd[2 * b2] = (uint32_t)f->var[g];
+                    gd[2 * b2 + 1] = (uint32_t)(127 - f->cut[g]) * 0x01010101u;
+                }
+                gnodes.clear();
+                return;
+            }
+            if (gslots.empty()) { used[0] = used[1] = 0; return; }
+            std::stable_sort(gslots.begin(), gslots.end(),
+                             [&](const Slot& a, const Slot& b2) { return extremeness(a.node) < extremeness(b2.node); });
+            uint32_t sel[2] = {0, 0}, bias[2] = {0, 0}, wgt[2] = {0, 0};
+            for (size_t b2 = 0; b2 < gslots.size(); ++b2) {
+                const Slot& sl = gslots[b2];
+                const size_t g = (size_t)sl.node;
+                node_bit[g] = (uint8_t)b2;
+                const uint32_t byte_in_bank = (uint32_t)(f->var[g] - (sl.round ? base1 : 0));       // 0..7
+                sel[sl.round] |= byte_in_bank << (4 * sl.pos);
+                bias[sl.round] |= (uint32_t)(127 - f->cut[g]) << (8 * sl.pos);
+                wgt[sl.round] |= ((uint32_t)(-(8 << b2)) & 0xFFu) << (8 * sl.pos);                // signed byte -(8 << bit)
+            }
+            gd[0] = sel[0] | (sel[1] << 16); gd[1] = bias[0]; gd[2] = bias[1]; gd[3] = wgt[0]; gd[4] = wgt[1];
+            gslots.clear();
+            used[0] = used[1] = 0;
+        };
+        // try to place the internal nodes of tree [base, base+cnt) into the open gather group; all or nothing
+        auto place_tree = [&](int32_t base, int32_t cnt, int bits) -> bool {
+            const size_t mark = gslots.size();
+            int u[2] = {used[0], used[1]};
+            int nbits = bits;
+            for (int32_t a = 0; a < cnt; ++a) {
+                const size_t g = (size_t)(base + a);
+                if (f->var[g] < 0) continue;
+                const int v = f->var[g];
+                const bool in0 = v < 8, in1 = v >= base1 && v < base1 + 8;
+                int r = -1;
+                if (in0 && in1) r = (u[0] <= u[1]) ? 0 : 1;      // variable reachable from both rounds: take the emptier one
+                else if (in0) r = 0;
+                else if (in1) r = 1;
+                if (r >= 0 && u[r] >= 4) r = (r == 0 ? (in1 && u[1] < 4 ? 1 : -1) : (in0 && u[0] < 4 ? 0 : -1));
+                if (r < 0 || nbits >= NB) { gslots.resize(mark); return false; }
+                gslots.push_back(Slot{(int64_t)g, r, u[r]});
+                ++u[r];
+                ++nbits;
+            }
+            used[0] = u[0]; used[1] = u[1];
+            return true;
+        };
+        auto open_group = [&](int64_t k, uint32_t flags) {
+            group_tree_off.push_back((int32_t)k);
+            hdr.push_back(flags);
+            desc.resize(desc.size() + (size_t)DW, 0u);           // unused slots: bias 0 -> predicate 0, weight 0
+        };
+
         int bits = NB + 1;   // force a new group at the start of a draw
         for (int32_t t = 0; t < f->m; ++t) {
             const int64_t k = (int64_t)s * f->m + t;
@@ -475,10 +508,25 @@ int forest_upload(bartint_forest* f) {
         close_group();
         hdr.back() |= TK_FLAG_END_DRAW;
     }
-    f->draw_group_off[(size_t)f->S] = (int32_t)group_tree_off.size();
+    // concatenate the per-draw plans
+    f->draw_group_off.assign((size_t)f->S + 1, 0);
+    for (int32_t s = 0; s < f->S; ++s)
+        f->draw_group_off[(size_t)s + 1] = f->draw_group_off[(size_t)s] + (int32_t)plans[(size_t)s].hdr.size();
+    const size_t n_groups_total = (size_t)f->draw_group_off[(size_t)f->S];
+    std::vector<int32_t> group_tree_off(n_groups_total);
+    std::vector<uint32_t> hdr(n_groups_total), desc(n_groups_total * (size_t)DW);
+#pragma omp parallel for schedule(static)
+    for (int32_t s = 0; s < f->S; ++s) {
+        const size_t g0 = (size_t)f->draw_group_off[(size_t)s];
+        const DrawPlan& pl = plans[(size_t)s];
+        std::copy(pl.group_tree_off.begin(), pl.group_tree_off.end(), group_tree_off.begin() + g0);
+        std::copy(pl.hdr.begin(), pl.hdr.end(), hdr.begin() + g0);
+        std::copy(pl.desc.begin(), pl.desc.end(), desc.begin() + g0 * (size_t)DW);
+    }
     f->n_groups = (int64_t)group_tree_off.size();
     group_tree_off.push_back((int32_t)n_trees);
     // group g covers trees [group_tree_off[g], group_tree_off[g+1]) -- groups never span draws
+    pt.lap("upload: group planner");
     if ((rc = upload(&f->dev.node_bit, node_bit))) return rc;
     if ((rc = upload(&f->dev.group_tree_off, group_tree_off))) return rc;
     if ((rc = upload(&f->dev.draw_group_off, f->draw_group_off))) return rc;
@@ -491,6 +539,7 @@ int forest_upload(bartint_forest* f) {
     cudaFreeAsync(d_desc, nullptr);
     cudaFreeAsync(d_hdr, nullptr);
     cudaError_t e = cudaStreamSynchronize(nullptr);   // host vectors (pageable) must outlive the copies; surface build errors here
+    pt.lap("upload: H2D groups + build tables");
     if (rc) return rc;
     BI_CUDA(e);
     return BARTINT_OK;

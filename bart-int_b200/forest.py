@@ -254,30 +254,45 @@ class Forest:
     # ---- evaluation ----
     def eval(self, pts, weights=None, want=("draw_mean", "point_mean", "point_var"), scaled=False, draws=None,
              force_walk=False) -> dict:
-        """predict + colVars*weights + rowMeans (+ the full S x N matrix when asked), fused on the device."""
-        own = not isinstance(pts, Points)
+        """predict + colVars*weights + rowMeans (+ the full S x N matrix when asked), fused on the device.
+
+        `pts` is either a Points handle (codes resident in HBM) or a host matrix (N x d): the latter goes through the
+        one-shot `bartint_eval`, which pipelines host->device copies against the evaluation for large N."""
+        lo, hi = (0, self.S) if draws is None else draws
+        nd = hi - lo
+        host = not isinstance(pts, Points)
+        if host:
+            X = np.asarray(pts, np.float64)
+            if X.ndim == 1:
+                X = X.reshape(-1, self.d) if self.d else X.reshape(-1, 0)
+            X = np.asfortranarray(X)
+            N = X.shape[0]
+        else:
+            N = pts.N
+        out = {}
+        if "draw_mean" in want:
+            out["draw_mean"] = np.zeros(nd)
+        if "point_mean" in want:
+            out["point_mean"] = np.zeros(N)
+        if "point_var" in want:
+            out["point_var"] = np.zeros(N)
+        if "full_pred" in want:
+            out["full_pred"] = np.zeros((nd, N), order="F")
+        w = None
+        if weights is not None:
+            w = np.ascontiguousarray(np.asarray(weights, np.float64).ravel())
+        flags = (_lib.BARTINT_SCALED_UNITS if scaled else 0) | (_lib.BARTINT_FORCE_WALK if force_walk else 0)
+        outs = (_p(out.get("draw_mean"), C.c_double), _p(out.get("point_mean"), C.c_double),
+                _p(out.get("point_var"), C.c_double), _p(out.get("full_pred"), C.c_double))
+        wargs = (_p(w, C.c_double), 0 if w is None else w.size)
+        if host and draws is None:
+            _check(_lib.load().bartint_eval(self._h, _p(X, C.c_double), N, X.shape[1], flags, *wargs, *outs))
+            return out
+        own = host
         if own:
-            pts = self.points(pts)
+            pts = self.points(X)
         try:
-            lo, hi = (0, self.S) if draws is None else draws
-            nd = hi - lo
-            out = {}
-            if "draw_mean" in want:
-                out["draw_mean"] = np.zeros(nd)
-            if "point_mean" in want:
-                out["point_mean"] = np.zeros(pts.N)
-            if "point_var" in want:
-                out["point_var"] = np.zeros(pts.N)
-            if "full_pred" in want:
-                out["full_pred"] = np.zeros((nd, pts.N), order="F")
-            w = None
-            if weights is not None:
-                w = np.ascontiguousarray(np.asarray(weights, np.float64).ravel())
-            flags = (_lib.BARTINT_SCALED_UNITS if scaled else 0) | (_lib.BARTINT_FORCE_WALK if force_walk else 0)
-            _check(_lib.load().bartint_eval_points(
-                self._h, pts._h, flags, lo, hi, _p(w, C.c_double), 0 if w is None else w.size,
-                _p(out.get("draw_mean"), C.c_double), _p(out.get("point_mean"), C.c_double),
-                _p(out.get("point_var"), C.c_double), _p(out.get("full_pred"), C.c_double)))
+            _check(_lib.load().bartint_eval_points(self._h, pts._h, flags, lo, hi, *wargs, *outs))
             return out
         finally:
             if own:

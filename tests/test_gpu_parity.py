@@ -418,3 +418,25 @@ def test_random_shapes_property(kernel_kind):
             assert np.array_equal(f.leaf_indices(X, draws=(lo, hi), use_table_kernel=True),
                                   onp.leaf_ordinals(ff, X)[lo * m:hi * m])
         f.close()
+
+
+def test_pipelined_host_eval_matches_point_handle_path():
+    """bartint_eval (host matrix, row-block pipeline above 2^18 points) == points handle + bartint_eval_points."""
+    rng = np.random.default_rng(77)
+    x_train = rng.random((60, 6))
+    ff = synth.prior_forest(12, 9, 10, x_train, rng.normal(size=60))
+    N = (1 << 18) + 12345
+    X = rng.random((N, 6))
+    w = rng.random(N)
+    f = Forest.from_soa(ff)
+    a = f.eval(X, weights=w, want=("draw_mean", "point_mean", "point_var"))            # one-shot, pipelined
+    pts = f.points(X)
+    b = f.eval(pts, weights=w, want=("draw_mean", "point_mean", "point_var"))          # resident codes
+    span = ff.y_max - ff.y_min
+    _assert_close(a["draw_mean"], b["draw_mean"], 1e-13, scale=span)
+    assert np.array_equal(a["point_mean"], b["point_mean"]) and np.array_equal(a["point_var"], b["point_var"])
+    sub = slice(0, N, 997)
+    P = onp.predict(ff, X[sub])
+    _assert_close(a["point_mean"][sub], P.mean(axis=0), 1e-12, scale=span)
+    _assert_close(a["point_var"][sub], onp.col_vars(P) * w[sub], 1e-9, scale=np.maximum(onp.col_vars(P) * w[sub], 1e-12))
+    pts.close(); f.close()
