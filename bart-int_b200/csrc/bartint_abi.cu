@@ -240,6 +240,57 @@ int bartint_points_from_device(const bartint_forest* f, const double* dX, int64_
     return rc;
 }
 
+struct bartint_staged {
+    int device = 0;
+    int64_t N = 0;
+    int32_t d = 0;
+    double* dX = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t done = nullptr;
+};
+
+int bartint_stage_matrix(const double* X, int64_t N, int32_t d, int device, bartint_staged** out) {
+    BI_REQUIRE(out != nullptr, BARTINT_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    BI_REQUIRE(N >= 0 && d >= 0 && (N * d == 0 || X != nullptr), BARTINT_ERR_ARG, "X is NULL or bad shape");
+    int rc = check_device();
+    if (rc) return rc;
+    DeviceGuard g(device);
+    bartint_staged* s = new (std::nothrow) bartint_staged();
+    BI_REQUIRE(s != nullptr, BARTINT_ERR_NOMEM, "out of host memory");
+    s->device = device; s->N = N; s->d = d;
+    cudaError_t e = cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->done, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaMallocAsync((void**)&s->dX, sizeof(double) * (size_t)std::max<int64_t>(N * d, 1), s->copy_stream);
+    if (e == cudaSuccess && N * d > 0)
+        e = cudaMemcpyAsync(s->dX, X, sizeof(double) * (size_t)(N * d), cudaMemcpyHostToDevice, s->copy_stream);
+    if (e == cudaSuccess) e = cudaEventRecord(s->done, s->copy_stream);
+    if (e != cudaSuccess) { bartint_staged_free(s); return cuda_fail(e, "bartint_stage_matrix", __FILE__, __LINE__); }
+    *out = s;
+    return BARTINT_OK;
+}
+
+int bartint_staged_points(const bartint_forest* f, const bartint_staged* s, void* stream, bartint_points** out) {
+    BI_REQUIRE(f != nullptr && s != nullptr && out != nullptr, BARTINT_ERR_ARG, "NULL argument");
+    BI_REQUIRE(s->device == f->device, BARTINT_ERR_ARG, "matrix was staged on another device than the forest's");
+    DeviceGuard g(f->device);
+    BI_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, s->done, 0));
+    return bartint_points_from_device(f, s->dX, s->N, s->d, s->N, stream, out);
+}
+
+void bartint_staged_free(bartint_staged* s) {
+    if (s == nullptr) return;
+    {
+        DeviceGuard g(s->device);
+        if (s->copy_stream) cudaStreamSynchronize(s->copy_stream);
+        if (s->dX) cudaFree(s->dX);            // synchronous: a consumer stream may still be binning from it
+        if (s->done) cudaEventDestroy(s->done);
+        if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
+        (void)cudaGetLastError();
+    }
+    delete s;
+}
+
 int bartint_points_from_host(const bartint_forest* f, const double* X, int64_t N, int32_t d, bartint_points** out) {
     BI_REQUIRE(f != nullptr && out != nullptr, BARTINT_ERR_ARG, "NULL argument");
     *out = nullptr;

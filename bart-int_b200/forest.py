@@ -133,6 +133,35 @@ class WireStrings:
         self.array = (C.c_char_p * max(len(self._enc), 1))(*self._enc)
 
 
+class StagedMatrix:
+    """A host matrix on its way to the device (asynchronous copy started at construction), independent of any forest:
+    the candidate matrix / fullData exist before the model is fitted, so their transfer can overlap the export."""
+
+    def __init__(self, X, device: int = 0):
+        X = np.asarray(X, np.float64)
+        self._X = np.asfortranarray(X)          # keep the host buffer alive until the copy has been consumed
+        self.N, self.d = self._X.shape
+        h = C.c_void_p()
+        _check(_lib.load().bartint_stage_matrix(_p(self._X, C.c_double), self.N, self.d, device, C.byref(h)))
+        self._h = h
+
+    def points(self, forest: "Forest", stream: int = 0) -> "Points":
+        h = C.c_void_p()
+        _check(_lib.load().bartint_staged_points(forest._h, self._h, C.c_void_p(stream), C.byref(h)))
+        return Points(forest, h.value, self.N)
+
+    def close(self):
+        if self._h:
+            _lib.load().bartint_staged_free(self._h)
+            self._h = C.c_void_p(None)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Points:
     """A point set binned to cut-point codes, resident in HBM (dbarts' integer cut map of x.test)."""
 

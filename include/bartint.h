@@ -99,6 +99,15 @@ void bartint_forest_destroy(bartint_forest* f);
  *   code[i][j] = #{k : X[i,j] > cut[j][k]}    (NaN -> 0), so  "right iff x > cut"  <=>  code > cut index.
  * X is N x d column-major with leading dimension ld >= N.
  * ------------------------------------------------------------------------------------------- */
+/* Staging of a host matrix that does not depend on the fitted model (the candidate matrix / fullData of
+ * bartMean.R:26 exist before bart() returns): starts the host->device copy on an internal copy stream and returns at
+ * once, so the transfer overlaps the exporter's CPU work.  bartint_staged_points() then bins it for a forest (waits
+ * for the copy on `stream`); the staging buffer is released by bartint_staged_free().  device = CUDA device index. */
+typedef struct bartint_staged bartint_staged;
+int bartint_stage_matrix(const double* X, int64_t N, int32_t d, int device, bartint_staged** out);
+int bartint_staged_points(const bartint_forest* f, const bartint_staged* s, void* stream, bartint_points** out);
+void bartint_staged_free(bartint_staged* s);
+
 int bartint_points_from_host(const bartint_forest* f, const double* X, int64_t N, int32_t d,
                              bartint_points** out);
 int bartint_points_from_device(const bartint_forest* f, const double* dX, int64_t N, int32_t d,

@@ -440,3 +440,15 @@ def test_pipelined_host_eval_matches_point_handle_path():
     _assert_close(a["point_mean"][sub], P.mean(axis=0), 1e-12, scale=span)
     _assert_close(a["point_var"][sub], onp.col_vars(P) * w[sub], 1e-9, scale=np.maximum(onp.col_vars(P) * w[sub], 1e-12))
     pts.close(); f.close()
+
+
+def test_staged_matrix_path(small_case):
+    from bartint_b200 import StagedMatrix
+    ff, _, _, X = small_case
+    st = StagedMatrix(X)                    # copy starts before the forest exists
+    f = Forest.from_soa(ff)
+    pts = st.points(f)
+    assert np.array_equal(pts.codes().astype(np.int32), onp.bin_points(X, ff.cut_offsets, ff.cut_values))
+    out = f.eval(pts, want=("draw_mean",))
+    _assert_close(out["draw_mean"], onp.row_means(onp.predict(ff, X)), 1e-13, scale=ff.y_max - ff.y_min)
+    pts.close(); st.close(); f.close()
