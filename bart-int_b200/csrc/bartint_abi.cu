@@ -35,7 +35,7 @@ struct DeviceGuard {
 };
 
 static void free_device(DeviceForest& d) {
-    void* ptrs[] = {d.nodes, d.tree_off, d.tree_leaf_off, d.leaf_mu, d.cut_off, d.cut_val, d.node_bit, d.group_tree_off,
+    void* ptrs[] = {d.nodes, d.tree_off, d.tree_leaf_off, d.leaf_mu, d.cut_off, d.cut_val, d.node_bit, d.tree_perm, d.group_tree_off,
                     d.draw_group_off, d.group_rec};
     for (void* q : ptrs)
         if (q) cudaFreeAsync(q, nullptr);      // ordered after every kernel already enqueued on the default stream

@@ -55,6 +55,9 @@ constexpr uint32_t TK_FLAG_END_DRAW = 1u;
 // of type WALK (header only) and is walked per point from the global node array inside the same kernel (rare; the
 // prior puts ~1e-4 of the trees there).  Header: {flags, first tree, number of trees, 0}.
 constexpr uint32_t TK_FLAG_WALK = 2u;
+// gather format only: the record holds ONE joint 2^NB table over two gather rounds; unflagged gather records are DUAL
+// (two independent 16-entry tables: trees [first, first+split) -> table 1, the rest -> table 2; header.w = split).
+constexpr uint32_t TK_FLAG_JOINT = 4u;
 __host__ __device__ constexpr int tk_tbl_off(int nb) { return TK_HDR + ((nb * 8 + 15) & ~15); }   // 16 B aligned
 __host__ __device__ constexpr int tk_rec_bytes(int nb) { return tk_tbl_off(nb) + (8 << nb); }       // multiple of 16
 
@@ -63,10 +66,11 @@ __host__ __device__ constexpr int tk_rec_bytes(int nb) { return tk_tbl_off(nb) +
 // point; byte-wise add of the biases, sign-replicating PRMT and one IDP.4A against the per-slot weights -(8 << bit)
 // give the table byte offset directly.  Two rounds per group: round 0 gathers from words (0,1) = variables 0..7,
 // round 1 from words (R-2,R-1) = variables 4(R-2) .. 4(R-2)+7.  No code loads from shared memory at all.
-//   record: [ 16 B header | selA|selB<<16, biasA, biasB, wA, wB, 0, 0, 0 | 2^NB doubles ]
+//   record: [ 16 B header | selA|selB<<16, biasA, biasB, wA, wB, pairsel, 0, 0 | 32 doubles (2^NB if larger) ]
+//   DUAL records (default) use the table area as two 16-entry tables, one per round; JOINT records as one 2^NB table.
 constexpr int TG_DESC = 32;
 __host__ __device__ constexpr int tg_tbl_off() { return TK_HDR + TG_DESC; }
-__host__ __device__ constexpr int tg_rec_bytes(int nb) { return tg_tbl_off() + (8 << nb); }
+__host__ __device__ constexpr int tg_rec_bytes(int nb) { return tg_tbl_off() + ((8 << nb) < 256 ? 256 : (8 << nb)); }
 __host__ __device__ constexpr int tg_regs_for(int d) { return d <= 8 ? 2 : (d <= 12 ? 3 : 4); }
 
 struct DeviceForest {
@@ -78,7 +82,8 @@ struct DeviceForest {
     double* cut_val = nullptr;
     // table path
     uint8_t* node_bit = nullptr;       // n_nodes: predicate bit of an internal node within its group
-    int32_t* group_tree_off = nullptr; // n_groups+1: first tree (linear index) of each group
+    int32_t* tree_perm = nullptr;      // S*m: permuted position -> tree id (gather planner packs trees; else identity)
+    int32_t* group_tree_off = nullptr; // n_groups+1: first (permuted) tree position of each group
     int32_t* draw_group_off = nullptr; // S+1: first group of each draw
     uint8_t* group_rec = nullptr;      // n_groups * tk_rec_bytes(nb)
 };
@@ -144,7 +149,7 @@ int launch_generate_points(int measure, int64_t N, int64_t first_index, uint64_t
                            double* x_out, cudaStream_t st);
 struct EvalPlan;
 int launch_build_tables(const bartint_forest* f, const uint32_t* d_desc, int desc_words, const uint32_t* d_hdr,
-                        cudaStream_t st);
+                        const uint32_t* d_split, cudaStream_t st);
 int launch_repack_codes(const uint8_t* codes, int64_t Npad, int d, uint4* codes_pm, cudaStream_t st);
 int launch_eval_gather(const bartint_forest* f, const bartint_points* p, const EvalPlan& plan, double* draw_part,
                        double* pt_mean, double* pt_m2, double* full_pred, double fp_scale, double fp_y0,

@@ -402,23 +402,39 @@ int forest_upload(bartint_forest* f) {
     struct DrawPlan {
         std::vector<int32_t> group_tree_off;   // first tree of each group of the draw
         std::vector<uint32_t> hdr;             // flags per group
+        std::vector<uint32_t> split;           // gather DUAL records: number of trees in table 1
         std::vector<uint32_t> desc;            // DW words per group
     };
+    std::vector<int32_t> tree_perm((size_t)n_trees);           // permuted position -> tree id (identity: table format)
+    for (int64_t k = 0; k < n_trees; ++k) tree_perm[(size_t)k] = (int32_t)k;
     std::vector<DrawPlan> plans((size_t)f->S);
 #pragma omp parallel for schedule(static)
     for (int32_t s = 0; s < f->S; ++s) {
         std::vector<int32_t>& group_tree_off = plans[(size_t)s].group_tree_off;
         std::vector<uint32_t>& hdr = plans[(size_t)s].hdr;
+        std::vector<uint32_t>& split = plans[(size_t)s].split;
         std::vector<uint32_t>& desc = plans[(size_t)s].desc;
-        std::vector<int64_t> gnodes;           // nodes of the group being filled (table format)
-        std::vector<Slot> gslots;              // nodes + their slots (gather format)
-        int used[2] = {0, 0};
-        auto close_group = [&]() {
-            uint32_t* gd = desc.empty() ? nullptr : &desc[desc.size() - (size_t)DW];
-            if (!f->gather) {
+        auto open_group = [&](int64_t k, uint32_t flags) {
+            group_tree_off.push_back((int32_t)k);
+            hdr.push_back(flags);
+            split.push_back(0u);
+            desc.resize(desc.size() + (size_t)DW, 0u);           // unused slots: bias 0 -> predicate 0, weight 0
+        };
+        auto internal_nodes = [&](int64_t k, std::vector<int64_t>& out) {
+            out.clear();
+            const int32_t base = tree_off[(size_t)k], cnt = tree_off[(size_t)k + 1] - base;
+            for (int32_t a = 0; a < cnt; ++a)
+                if (f->var[(size_t)(base + a)] >= 0) out.push_back((int64_t)base + a);
+        };
+
+        if (!f->gather) {
+            // ---------------- table format: up to NB nodes per group, any variables ----------------
+            std::vector<int64_t> gnodes, tn;
+            auto close_group = [&]() {
                 if (gnodes.empty()) return;
                 std::stable_sort(gnodes.begin(), gnodes.end(),
                                  [&](int64_t a, int64_t b2) { return extremeness(a) < extremeness(b2); });
+                uint32_t* gd = &desc[desc.size() - (size_t)DW];
                 for (size_t b2 = 0; b2 < gnodes.size(); ++b2) {
                     const size_t g = (size_t)gnodes[b2];
                     node_bit[g] = (uint8_t)b2;
@@ -426,9 +442,138 @@ int forest_upload(bartint_forest* f) {
                     gd[2 * b2 + 1] = (uint32_t)(127 - f->cut[g]) * 0x01010101u;
                 }
                 gnodes.clear();
-                return;
+            };
+            int bits = NB + 1;   // force a new group at the start of a draw
+            for (int32_t t = 0; t < f->m; ++t) {
+                const int64_t k = (int64_t)s * f->m + t;
+                internal_nodes(k, tn);
+                const int internal = (int)tn.size();
+                if (internal > NB) {                             // WALK record holding just this tree
+                    close_group();
+                    open_group(k, TK_FLAG_WALK);
+                    bits = NB + 1;
+                    continue;
+                }
+                if (bits + internal > NB) { close_group(); open_group(k, 0u); bits = 0; }
+                gnodes.insert(gnodes.end(), tn.begin(), tn.end());
+                bits += internal;
             }
-            if (gslots.empty()) { used[0] = used[1] = 0; return; }
+            close_group();
+            hdr.back() |= TK_FLAG_END_DRAW;
+            continue;
+        }
+
+        // ---------------- gather format ----------------
+        // DUAL record (the common kind): two independent 16-entry tables.  Table 1 holds trees whose <= 4 nodes use
+        // variables of code words (0,1); table 2 trees whose nodes use words (R-2,R-1) [pairsel 0] or (0,R-1)
+        // [pairsel 1].  One PRMT gather + one IDP.4A per table and point.  The trees of a draw may be summed in any
+        // order, so they are bin-packed into the tables (first-fit decreasing) and the draw's trees are PERMUTED:
+        // record g covers permuted positions [group_tree_off[g], group_tree_off[g+1]), tree_perm maps to tree ids.
+        // JOINT record: one 2^NB table over two gather rounds, for trees that fit no DUAL table.  WALK: no table.
+        const int R = f->g_regs;
+        struct Bin { int type; int nodes; std::vector<int32_t> trees; };   // type 0: pair (0,1); 1: (R-2,R-1); 2: (0,R-1)
+        std::vector<Bin> bins;
+        std::vector<int32_t> stumps, joint_trees, walk_trees;
+        std::vector<int64_t> tn;
+        std::vector<std::pair<int, int32_t>> order;      // (node count, tree) for first-fit decreasing
+        auto type_ok = [&](int type, int32_t t) {
+            internal_nodes((int64_t)s * f->m + t, tn);
+            for (int64_t g : tn) {
+                const int reg = f->var[(size_t)g] >> 2;
+                const bool ok = R == 2 ? true
+                                : type == 0 ? reg <= 1
+                                : type == 1 ? (reg == R - 2 || reg == R - 1)
+                                            : (reg == 0 || reg == R - 1);
+                if (!ok) return false;
+            }
+            return true;
+        };
+        for (int32_t t = 0; t < f->m; ++t) {
+            internal_nodes((int64_t)s * f->m + t, tn);
+            if (tn.empty()) stumps.push_back(t);
+            else order.emplace_back((int)tn.size(), t);
+        }
+        std::stable_sort(order.begin(), order.end(), [](const auto& a, const auto& b2) { return a.first > b2.first; });
+        int n_side[2] = {0, 0};                           // bins feeding table 1 / table 2
+        for (const auto& kt : order) {
+            const int k = kt.first;
+            const int32_t t = kt.second;
+            const int n_types = R == 2 ? 2 : 3;           // R == 2: both tables read words (0,1); type 1 = "table 2"
+            bool ok[3] = {false, false, false};
+            bool any = false;
+            if (k <= 4)
+                for (int ty = 0; ty < n_types; ++ty) { ok[ty] = type_ok(ty, t); any = any || ok[ty]; }
+            if (!any) {
+                internal_nodes((int64_t)s * f->m + t, tn);
+                (k <= NB ? joint_trees : walk_trees).push_back(t);
+                continue;
+            }
+            // best fit among open bins of a compatible type; else open a bin on the emptier side
+            int best = -1;
+            for (size_t bi = 0; bi < bins.size(); ++bi)
+                if (ok[bins[bi].type] && bins[bi].nodes + k <= 4 && (best < 0 || bins[bi].nodes > bins[(size_t)best].nodes))
+                    best = (int)bi;
+            if (best < 0) {
+                int ty = -1;
+                for (int c = 0; c < n_types; ++c) {
+                    if (!ok[c]) continue;
+                    const int side = c == 0 ? 0 : 1;
+                    if (ty < 0 || n_side[side] < n_side[ty == 0 ? 0 : 1]) ty = c;
+                }
+                bins.push_back(Bin{ty, 0, {}});
+                ++n_side[ty == 0 ? 0 : 1];
+                best = (int)bins.size() - 1;
+            }
+            bins[(size_t)best].nodes += k;
+            bins[(size_t)best].trees.push_back(t);
+        }
+        // emit: pair every table-1 bin with a table-2 bin
+        std::vector<int> side1, side2;
+        for (size_t bi = 0; bi < bins.size(); ++bi) (bins[bi].type == 0 ? side1 : side2).push_back((int)bi);
+        int32_t* perm = tree_perm.data() + (size_t)s * f->m;
+        int32_t pos = 0;                                  // next permuted position inside the draw
+        auto byte_of = [&](int type, int v) {            // byte index of variable v inside the table's register pair
+            if (R == 2 || type == 0) return v;
+            if (type == 1) return v - base1;
+            return v < 4 ? v : v - base1;
+        };
+        auto emit_table = [&](const Bin* bin, int table, uint32_t* gd) {
+            if (bin == nullptr) return;
+            uint32_t sel = 0, bias = 0, wgt = 0;
+            int n = 0;
+            for (int32_t t : bin->trees) {
+                perm[pos++] = (int32_t)((int64_t)s * f->m + t);
+                internal_nodes((int64_t)s * f->m + t, tn);
+                for (int64_t gi : tn) {
+                    const size_t g = (size_t)gi;
+                    node_bit[g] = (uint8_t)n;
+                    sel |= (uint32_t)byte_of(bin->type, f->var[g]) << (4 * n);
+                    bias |= (uint32_t)(127 - f->cut[g]) << (8 * n);
+                    wgt |= ((uint32_t)(-(8 << n)) & 0xFFu) << (8 * n);
+                    ++n;
+                }
+            }
+            if (table == 0) { gd[0] |= sel; gd[1] = bias; gd[3] = wgt; }
+            else { gd[0] |= sel << 16; gd[2] = bias; gd[4] = wgt; gd[5] = bin->type == 2 ? 1u : 0u; }
+        };
+        const size_t n_dual = std::max(side1.size(), side2.size());
+        for (size_t r = 0; r < n_dual || (r == 0 && !stumps.empty() && joint_trees.empty() && walk_trees.empty()); ++r) {
+            open_group((int64_t)s * f->m + pos, 0u);
+            uint32_t* gd = &desc[desc.size() - (size_t)DW];
+            const int32_t start = pos;
+            if (r == 0)                                   // stumps only add a constant: all into the first table 1
+                for (int32_t t : stumps) perm[pos++] = (int32_t)((int64_t)s * f->m + t);
+            emit_table(r < side1.size() ? &bins[(size_t)side1[r]] : nullptr, 0, gd);
+            split.back() = (uint32_t)(pos - start);
+            emit_table(r < side2.size() ? &bins[(size_t)side2[r]] : nullptr, 1, gd);
+            if (r == 0) stumps.clear();
+        }
+        // JOINT records: greedy packing of the remaining small trees, two rounds of <= 4 slots, <= NB bits
+        std::vector<Slot> gslots;
+        int used[2] = {0, 0}, jbits = 0;
+        bool jopen = false;
+        auto close_joint = [&]() {
+            if (!jopen) return;
             std::stable_sort(gslots.begin(), gslots.end(),
                              [&](const Slot& a, const Slot& b2) { return extremeness(a.node) < extremeness(b2.node); });
             uint32_t sel[2] = {0, 0}, bias[2] = {0, 0}, wgt[2] = {0, 0};
@@ -436,76 +581,59 @@ int forest_upload(bartint_forest* f) {
                 const Slot& sl = gslots[b2];
                 const size_t g = (size_t)sl.node;
                 node_bit[g] = (uint8_t)b2;
-                const uint32_t byte_in_bank = (uint32_t)(f->var[g] - (sl.round ? base1 : 0));       // 0..7
-                sel[sl.round] |= byte_in_bank << (4 * sl.pos);
+                sel[sl.round] |= (uint32_t)(f->var[g] - (sl.round ? base1 : 0)) << (4 * sl.pos);
                 bias[sl.round] |= (uint32_t)(127 - f->cut[g]) << (8 * sl.pos);
-                wgt[sl.round] |= ((uint32_t)(-(8 << b2)) & 0xFFu) << (8 * sl.pos);                // signed byte -(8 << bit)
+                wgt[sl.round] |= ((uint32_t)(-(8 << b2)) & 0xFFu) << (8 * sl.pos);
             }
+            uint32_t* gd = &desc[desc.size() - (size_t)DW];
             gd[0] = sel[0] | (sel[1] << 16); gd[1] = bias[0]; gd[2] = bias[1]; gd[3] = wgt[0]; gd[4] = wgt[1];
             gslots.clear();
-            used[0] = used[1] = 0;
+            used[0] = used[1] = 0; jbits = 0;
+            jopen = false;
         };
-        // try to place the internal nodes of tree [base, base+cnt) into the open gather group; all or nothing
-        auto place_tree = [&](int32_t base, int32_t cnt, int bits) -> bool {
+        auto place_joint = [&]() -> bool {               // nodes in tn; all or nothing
             const size_t mark = gslots.size();
             int u[2] = {used[0], used[1]};
-            int nbits = bits;
-            for (int32_t a = 0; a < cnt; ++a) {
-                const size_t g = (size_t)(base + a);
-                if (f->var[g] < 0) continue;
-                const int v = f->var[g];
+            int nbits = jbits;
+            for (int64_t gi : tn) {
+                const int v = f->var[(size_t)gi];
                 const bool in0 = v < 8, in1 = v >= base1 && v < base1 + 8;
                 int r = -1;
-                if (in0 && in1) r = (u[0] <= u[1]) ? 0 : 1;      // variable reachable from both rounds: take the emptier one
+                if (in0 && in1) r = (u[0] <= u[1]) ? 0 : 1;
                 else if (in0) r = 0;
                 else if (in1) r = 1;
                 if (r >= 0 && u[r] >= 4) r = (r == 0 ? (in1 && u[1] < 4 ? 1 : -1) : (in0 && u[0] < 4 ? 0 : -1));
                 if (r < 0 || nbits >= NB) { gslots.resize(mark); return false; }
-                gslots.push_back(Slot{(int64_t)g, r, u[r]});
+                gslots.push_back(Slot{gi, r, u[r]});
                 ++u[r];
                 ++nbits;
             }
-            used[0] = u[0]; used[1] = u[1];
+            used[0] = u[0]; used[1] = u[1]; jbits = nbits;
             return true;
         };
-        auto open_group = [&](int64_t k, uint32_t flags) {
-            group_tree_off.push_back((int32_t)k);
-            hdr.push_back(flags);
-            desc.resize(desc.size() + (size_t)DW, 0u);           // unused slots: bias 0 -> predicate 0, weight 0
-        };
-
-        int bits = NB + 1;   // force a new group at the start of a draw
-        for (int32_t t = 0; t < f->m; ++t) {
-            const int64_t k = (int64_t)s * f->m + t;
-            const int32_t base = tree_off[(size_t)k], cnt = tree_off[(size_t)k + 1] - base;
-            const int internal = (cnt - 1) / 2;
-            bool placed = false;
-            if (internal <= NB) {
-                if (!f->gather) {
-                    if (bits + internal > NB) { close_group(); open_group(k, 0u); bits = 0; }
-                    for (int32_t a = 0; a < cnt; ++a)
-                        if (f->var[(size_t)(base + a)] >= 0) gnodes.push_back((int64_t)base + a);
-                    placed = true;
-                } else {
-                    if (bits <= NB && bits + internal <= NB && place_tree(base, cnt, bits)) placed = true;
-                    else {
-                        close_group(); open_group(k, 0u); bits = 0;
-                        placed = place_tree(base, cnt, 0);
-                        if (!placed) {                       // does not fit even an empty group -> WALK record
-                            group_tree_off.pop_back(); hdr.pop_back(); desc.resize(desc.size() - (size_t)DW);
-                        }
-                    }
-                }
+        for (int32_t t : joint_trees) {
+            internal_nodes((int64_t)s * f->m + t, tn);
+            if (jopen && place_joint()) { perm[pos++] = (int32_t)((int64_t)s * f->m + t); continue; }
+            close_joint();
+            if (place_joint()) {
+                open_group((int64_t)s * f->m + pos, TK_FLAG_JOINT);
+                jopen = true;
+                if (!stumps.empty()) { for (int32_t st : stumps) perm[pos++] = (int32_t)((int64_t)s * f->m + st); stumps.clear(); }
+                perm[pos++] = (int32_t)((int64_t)s * f->m + t);
+            } else {
+                walk_trees.push_back(t);                  // cannot be slotted (e.g. 5 nodes on variables of one round)
             }
-            if (!placed) {                                   // WALK record holding just this tree
-                close_group();
-                open_group(k, TK_FLAG_WALK);
-                bits = NB + 1;                               // the next tree starts a fresh group
-                continue;
-            }
-            bits += internal;
         }
-        close_group();
+        close_joint();
+        for (int32_t t : walk_trees) {                    // one header-only record per tree, walked from global memory
+            open_group((int64_t)s * f->m + pos, TK_FLAG_WALK);
+            perm[pos++] = (int32_t)((int64_t)s * f->m + t);
+        }
+        if (!stumps.empty()) {                            // a draw made only of stumps and WALK trees
+            open_group((int64_t)s * f->m + pos, 0u);
+            for (int32_t t : stumps) perm[pos++] = (int32_t)((int64_t)s * f->m + t);
+            split.back() = (uint32_t)stumps.size();
+        }
         hdr.back() |= TK_FLAG_END_DRAW;
     }
     // concatenate the per-draw plans
@@ -514,13 +642,14 @@ int forest_upload(bartint_forest* f) {
         f->draw_group_off[(size_t)s + 1] = f->draw_group_off[(size_t)s] + (int32_t)plans[(size_t)s].hdr.size();
     const size_t n_groups_total = (size_t)f->draw_group_off[(size_t)f->S];
     std::vector<int32_t> group_tree_off(n_groups_total);
-    std::vector<uint32_t> hdr(n_groups_total), desc(n_groups_total * (size_t)DW);
+    std::vector<uint32_t> hdr(n_groups_total), split(n_groups_total), desc(n_groups_total * (size_t)DW);
 #pragma omp parallel for schedule(static)
     for (int32_t s = 0; s < f->S; ++s) {
         const size_t g0 = (size_t)f->draw_group_off[(size_t)s];
         const DrawPlan& pl = plans[(size_t)s];
         std::copy(pl.group_tree_off.begin(), pl.group_tree_off.end(), group_tree_off.begin() + g0);
         std::copy(pl.hdr.begin(), pl.hdr.end(), hdr.begin() + g0);
+        std::copy(pl.split.begin(), pl.split.end(), split.begin() + g0);
         std::copy(pl.desc.begin(), pl.desc.end(), desc.begin() + g0 * (size_t)DW);
     }
     f->n_groups = (int64_t)group_tree_off.size();
@@ -528,16 +657,18 @@ int forest_upload(bartint_forest* f) {
     // group g covers trees [group_tree_off[g], group_tree_off[g+1]) -- groups never span draws
     pt.lap("upload: group planner");
     if ((rc = upload(&f->dev.node_bit, node_bit))) return rc;
+    if ((rc = upload(&f->dev.tree_perm, tree_perm))) return rc;
     if ((rc = upload(&f->dev.group_tree_off, group_tree_off))) return rc;
     if ((rc = upload(&f->dev.draw_group_off, f->draw_group_off))) return rc;
     BI_CUDA(cudaMallocAsync((void**)&f->dev.group_rec, (size_t)f->n_groups * (size_t)fast_rec_bytes(f) + 16, nullptr));
-    uint32_t* d_desc = nullptr;
-    uint32_t* d_hdr = nullptr;
+    uint32_t *d_desc = nullptr, *d_hdr = nullptr, *d_split = nullptr;
     if ((rc = upload(&d_desc, desc))) return rc;
     if ((rc = upload(&d_hdr, hdr))) { cudaFreeAsync(d_desc, nullptr); return rc; }
-    rc = launch_build_tables(f, d_desc, DW, d_hdr, 0);
+    if ((rc = upload(&d_split, split))) { cudaFreeAsync(d_desc, nullptr); cudaFreeAsync(d_hdr, nullptr); return rc; }
+    rc = launch_build_tables(f, d_desc, DW, d_hdr, d_split, 0);
     cudaFreeAsync(d_desc, nullptr);
     cudaFreeAsync(d_hdr, nullptr);
+    cudaFreeAsync(d_split, nullptr);
     cudaError_t e = cudaStreamSynchronize(nullptr);   // host vectors (pageable) must outlive the copies; surface build errors here
     pt.lap("upload: H2D groups + build tables");
     if (rc) return rc;

@@ -61,6 +61,18 @@ __device__ __forceinline__ uint32_t gather_offset(const uint32_t (&c)[R], uint32
     return (uint32_t)o;
 }
 
+// DUAL record: two independent 16-entry tables.  Table 1 gathers from code words (0,1); table 2 from (R-2,R-1) or,
+// with pairsel, (0,R-1).  Returns both byte offsets (table 2's already includes its +128).
+template <int R>
+__device__ __forceinline__ void dual_offsets(const uint32_t (&c)[R], uint32_t d0, uint32_t d1, uint32_t d2, uint32_t d3,
+                                             uint32_t d4, uint32_t pairsel, uint32_t& o1, uint32_t& o2) {
+    const uint32_t lo = (R == 2) ? c[0] : (pairsel ? c[0] : c[R - 2]);
+    const uint32_t gA = __byte_perm(c[0], c[1], d0);
+    const uint32_t gB = __byte_perm(lo, c[R - 1], d0 >> 16);
+    o1 = (uint32_t)__dp4a((int)sign_mask4(gA + d1), (int)d3, 0);
+    o2 = (uint32_t)__dp4a((int)sign_mask4(gB + d2), (int)d4, 128);
+}
+
 template <int R>
 __device__ __forceinline__ uint32_t code_of(const uint32_t (&c)[R], uint32_t var) {   // WALK records: one code by variable
     uint32_t lo = c[0], hi = c[1];
@@ -141,17 +153,30 @@ __global__ void __launch_bounds__(TG_THREADS, MOMENTS ? 2 : 3) eval_gather_kerne
         const int par = k & 1;
         const int stage_first_draw = draws_done;
         // the stage's group flags as two warp-uniform bit masks
-        unsigned long long walk_mask = 0ull, end_mask = 0ull;
+        unsigned long long walk_mask = 0ull, end_mask = 0ull, joint_mask = 0ull;
 #pragma unroll
         for (int base = 0; base < GS; base += 32) {
             const int gl = base + lane;
             const uint32_t fl = gl < ng ? *reinterpret_cast<const uint32_t*>(stage + gl * REC) : 0u;
             walk_mask |= (unsigned long long)__ballot_sync(0xffffffffu, (fl & TK_FLAG_WALK) != 0u) << base;
             end_mask |= (unsigned long long)__ballot_sync(0xffffffffu, (fl & TK_FLAG_END_DRAW) != 0u) << base;
+            joint_mask |= (unsigned long long)__ballot_sync(0xffffffffu, (fl & TK_FLAG_JOINT) != 0u) << base;
         }
-        // plain groups (no flag) run in a tight loop; the next flagged group is found with one ffs on the masks
-        auto table_group = [&](const unsigned char* rec) {
+        // DUAL records without a flag (the bulk) run in a tight loop; the next flagged record is found with one ffs
+        auto dual_group = [&](const unsigned char* rec) {
             const uint4 da = *reinterpret_cast<const uint4*>(rec + TK_HDR);            // smem broadcast loads
+            const uint2 db = *reinterpret_cast<const uint2*>(rec + TK_HDR + 16);
+            const unsigned char* __restrict__ tbl = rec + tg_tbl_off();
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                uint32_t o1, o2;
+                dual_offsets<R>(creg[p], da.x, da.y, da.z, da.w, db.x, db.y, o1, o2);
+                acc[p] += *reinterpret_cast<const double*>(tbl + o1);
+                acc[p] += *reinterpret_cast<const double*>(tbl + o2);
+            }
+        };
+        auto joint_group = [&](const unsigned char* rec) {
+            const uint4 da = *reinterpret_cast<const uint4*>(rec + TK_HDR);
             const uint32_t d4 = *reinterpret_cast<const uint32_t*>(rec + TK_HDR + 16);
             const unsigned char* __restrict__ tbl = rec + tg_tbl_off();
 #pragma unroll
@@ -161,10 +186,10 @@ __global__ void __launch_bounds__(TG_THREADS, MOMENTS ? 2 : 3) eval_gather_kerne
         int g = 0;
 #pragma unroll 1
         while (g < ng) {
-            const unsigned long long special = (walk_mask | end_mask) >> g;
+            const unsigned long long special = (walk_mask | end_mask | joint_mask) >> g;
             const int g_stop = special ? min(ng, g + __ffsll((long long)special) - 1) : ng;
 #pragma unroll 1
-            for (; g < g_stop; ++g) table_group(stage + g * REC);
+            for (; g < g_stop; ++g) dual_group(stage + g * REC);
             if (g >= ng) break;
             const unsigned char* rec = stage + g * REC;
             if ((walk_mask >> g) & 1ull) {
@@ -182,8 +207,10 @@ __global__ void __launch_bounds__(TG_THREADS, MOMENTS ? 2 : 3) eval_gather_kerne
                     }
                     acc[p] += wmu[r.y];
                 }
+            } else if ((joint_mask >> g) & 1ull) {
+                joint_group(rec);
             } else {
-                table_group(rec);
+                dual_group(rec);
             }
             if ((end_mask >> g) & 1ull) {
                 // ---- draw epilogue: fold f_s(x) into the per-point moments and the per-draw sum ----
@@ -327,7 +354,8 @@ template <int R>
 __global__ void __launch_bounds__(256) gather_leaf_kernel(
     const uint8_t* __restrict__ group_rec, int nb, const int32_t* __restrict__ draw_group_off,
     const uint2* __restrict__ nodes, const int32_t* __restrict__ tree_off, const uint8_t* __restrict__ node_bit,
-    const uint4* __restrict__ codes_pm, int64_t N, int m, int draw_begin, int draw_end, int32_t* __restrict__ leaf_out) {
+    const int32_t* __restrict__ tree_perm, const uint4* __restrict__ codes_pm, int64_t N, int m, int draw_begin,
+    int draw_end, int32_t* __restrict__ leaf_out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int g = draw_group_off[draw_begin] + blockIdx.y;
     if (g >= draw_group_off[draw_end] || i >= N) return;
@@ -350,9 +378,18 @@ __global__ void __launch_bounds__(256) gather_leaf_kernel(
         return;
     }
     const uint32_t* dw = reinterpret_cast<const uint32_t*>(rec + TK_HDR);
-    const uint32_t idx = gather_offset<R>(c, dw[0], dw[1], dw[2], dw[3], dw[4]) >> 3;
+    uint32_t idx1, idx2;
+    if (h.x & TK_FLAG_JOINT) {
+        idx1 = idx2 = gather_offset<R>(c, dw[0], dw[1], dw[2], dw[3], dw[4]) >> 3;
+    } else {
+        uint32_t o1, o2;
+        dual_offsets<R>(c, dw[0], dw[1], dw[2], dw[3], dw[4], dw[5], o1, o2);
+        idx1 = o1 >> 3;
+        idx2 = (o2 - 128u) >> 3;
+    }
     for (uint32_t t = 0; t < h.z; ++t) {
-        const int64_t k = (int64_t)h.y + t;
+        const uint32_t idx = (h.x & TK_FLAG_JOINT) || t < h.w ? idx1 : idx2;
+        const int64_t k = tree_perm[(int64_t)h.y + t];
         int32_t node = tree_off[k];
         uint2 r = nodes[node];
         while ((r.x & 0xFFFFu) != LEAF_VAR) {
@@ -373,14 +410,14 @@ int launch_gather_leaf(const bartint_forest* f, const bartint_points* p, int32_t
 #define GL_CASE(RV)                                                                                                \
     case RV:                                                                                                       \
         gather_leaf_kernel<RV><<<grid, 256, 0, st>>>(f->dev.group_rec, f->nb, f->dev.draw_group_off, f->dev.nodes, \
-                                                     f->dev.tree_off, f->dev.node_bit, p->codes_pm, p->N, f->m,    \
-                                                     draw_begin, draw_end, leaf_out);                              \
+                                                     f->dev.tree_off, f->dev.node_bit, f->dev.tree_perm, p->codes_pm, p->N, \
+                                                     f->m, draw_begin, draw_end, leaf_out);                        \
         break;
     switch (f->g_regs) {
         GL_CASE(2) GL_CASE(3)
         default: gather_leaf_kernel<4><<<grid, 256, 0, st>>>(f->dev.group_rec, f->nb, f->dev.draw_group_off, f->dev.nodes,
-                                                             f->dev.tree_off, f->dev.node_bit, p->codes_pm, p->N, f->m,
-                                                             draw_begin, draw_end, leaf_out);
+                                                             f->dev.tree_off, f->dev.node_bit, f->dev.tree_perm, p->codes_pm,
+                                                             p->N, f->m, draw_begin, draw_end, leaf_out);
     }
 #undef GL_CASE
     count_launch();

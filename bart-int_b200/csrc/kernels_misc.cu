@@ -1,4 +1,5 @@
 // K0 point binning, table builder, K2 exact leaf-probability integral, K3 merges/finalisation.
+#include <algorithm>
 #include <cmath>
 
 #include "common.cuh"
@@ -176,21 +177,35 @@ int launch_generate_points(int measure, int64_t N, int64_t first_index, uint64_t
 // ---------------------------------------------------------------------------------------------
 __global__ void build_tables_kernel(const uint2* __restrict__ nodes, const int32_t* __restrict__ tree_off,
                                     const int32_t* __restrict__ tree_leaf_off, const double* __restrict__ leaf_mu,
-                                    const uint8_t* __restrict__ node_bit, const int32_t* __restrict__ group_tree_off,
-                                    const uint32_t* __restrict__ desc, int desc_words, const uint32_t* __restrict__ hdr,
-                                    int rec_bytes, int tbl_off, uint8_t* __restrict__ rec_base) {
+                                    const uint8_t* __restrict__ node_bit, const int32_t* __restrict__ tree_perm,
+                                    const int32_t* __restrict__ group_tree_off, const uint32_t* __restrict__ desc,
+                                    int desc_words, const uint32_t* __restrict__ hdr, const uint32_t* __restrict__ split,
+                                    int gather, int nb, int rec_bytes, int tbl_off, uint8_t* __restrict__ rec_base) {
     const int64_t g = blockIdx.x;
-    const uint32_t idx = threadIdx.x;
+    const uint32_t tid = threadIdx.x;
     uint8_t* rec = rec_base + g * (int64_t)rec_bytes;
     const int32_t tb = group_tree_off[g], te = group_tree_off[g + 1];
     const uint32_t flags = hdr[g];
-    if (flags & TK_FLAG_WALK) {
-        // header only: the evaluation kernel walks this tree from the global node array
-        if (idx == 0) *reinterpret_cast<uint4*>(rec) = make_uint4(flags, (uint32_t)tb, (uint32_t)(te - tb), 0u);
+    const uint32_t sp = split[g];
+    // header: {flags, first permuted tree position (WALK: the tree id itself), number of trees, trees in table 1}
+    if (tid == 0)
+        *reinterpret_cast<uint4*>(rec) = make_uint4(flags, (flags & TK_FLAG_WALK) ? (uint32_t)tree_perm[tb] : (uint32_t)tb,
+                                                    (uint32_t)(te - tb), sp);
+    if (flags & TK_FLAG_WALK) return;       // header only: the evaluation kernel walks this tree from the global arrays
+    if ((int)tid < desc_words) reinterpret_cast<uint32_t*>(rec + TK_HDR)[tid] = desc[g * desc_words + tid];
+    // which table entry / which trees this thread sums
+    int32_t k0 = tb, k1 = te;
+    uint32_t idx = tid;
+    if (gather && !(flags & TK_FLAG_JOINT)) {           // DUAL record: two 16-entry tables
+        if (tid >= 32) return;
+        idx = tid & 15u;
+        if (tid < 16) k1 = tb + (int32_t)sp; else k0 = tb + (int32_t)sp;
+    } else if (tid >= (1u << nb)) {
         return;
     }
     double sum = 0.0;
-    for (int32_t k = tb; k < te; ++k) {
+    for (int32_t kp = k0; kp < k1; ++kp) {
+        const int32_t k = tree_perm[kp];
         int32_t node = tree_off[k];
         uint2 r = nodes[node];
         while ((r.x & 0xFFFFu) != LEAF_VAR) {
@@ -200,20 +215,17 @@ __global__ void build_tables_kernel(const uint2* __restrict__ nodes, const int32
         }
         sum += leaf_mu[tree_leaf_off[k] + (int32_t)r.y];
     }
-    reinterpret_cast<double*>(rec + tbl_off)[idx] = sum;
-    if ((int)idx < desc_words) reinterpret_cast<uint32_t*>(rec + TK_HDR)[idx] = desc[g * desc_words + idx];
-    if (idx == 0) {
-        uint4 h = make_uint4(flags, (uint32_t)tb, (uint32_t)(te - tb), 0u);
-        *reinterpret_cast<uint4*>(rec) = h;
-    }
+    reinterpret_cast<double*>(rec + tbl_off)[tid] = sum;      // DUAL: entries 0..15 = table 1, 16..31 = table 2
 }
 
 int launch_build_tables(const bartint_forest* f, const uint32_t* d_desc, int desc_words, const uint32_t* d_hdr,
-                        cudaStream_t st) {
+                        const uint32_t* d_split, cudaStream_t st) {
     if (f->n_groups == 0) return BARTINT_OK;
-    build_tables_kernel<<<(unsigned)f->n_groups, 1u << f->nb, 0, st>>>(
-        f->dev.nodes, f->dev.tree_off, f->dev.tree_leaf_off, f->dev.leaf_mu, f->dev.node_bit, f->dev.group_tree_off,
-        d_desc, desc_words, d_hdr, fast_rec_bytes(f), fast_tbl_off(f), f->dev.group_rec);
+    const unsigned threads = std::max(32u, 1u << f->nb);
+    build_tables_kernel<<<(unsigned)f->n_groups, threads, 0, st>>>(
+        f->dev.nodes, f->dev.tree_off, f->dev.tree_leaf_off, f->dev.leaf_mu, f->dev.node_bit, f->dev.tree_perm,
+        f->dev.group_tree_off, d_desc, desc_words, d_hdr, d_split, f->gather ? 1 : 0, f->nb, fast_rec_bytes(f), fast_tbl_off(f),
+        f->dev.group_rec);
     count_launch();
     BI_CUDA(cudaGetLastError());
     return BARTINT_OK;
