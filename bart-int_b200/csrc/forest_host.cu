@@ -465,108 +465,127 @@ int forest_upload(bartint_forest* f) {
 
         // ---------------- gather format ----------------
         // DUAL record (the common kind): two independent 16-entry tables.  Table 1 holds trees whose <= 4 nodes use
-        // variables of code words (0,1); table 2 trees whose nodes use words (R-2,R-1) [pairsel 0] or (0,R-1)
-        // [pairsel 1].  One PRMT gather + one IDP.4A per table and point.  The trees of a draw may be summed in any
-        // order, so they are bin-packed into the tables (first-fit decreasing) and the draw's trees are PERMUTED:
-        // record g covers permuted positions [group_tree_off[g], group_tree_off[g+1]), tree_perm maps to tree ids.
-        // JOINT record: one 2^NB table over two gather rounds, for trees that fit no DUAL table.  WALK: no table.
+        // variables of code words (0,1); table 2 gathers from words (R-2,R-1) [pairsel 0], (0,R-1) [pairsel 1] or,
+        // with one more PRMT per point, (0,1,R-1) [pairsel 2].  One PRMT gather + one IDP.4A per table and point.
+        // The trees of a draw may be summed in any order, so they are bin-packed into the tables and the draw's
+        // trees are PERMUTED: record g covers permuted positions [group_tree_off[g], group_tree_off[g+1]), tree_perm
+        // maps to tree ids.  Packing: for K = ceil(nodes / 8), K + 1, ... try to fit every tree into K table-1 bins
+        // and K table-2 bins (largest trees first; fullest bin that takes the tree, never widening a table-2 bin to
+        // three words when a narrower home exists); the first K that fits is almost always the lower bound.
+        // JOINT record: one 2^NB table over two gather rounds, for 5-node trees.  WALK: no table.
         const int R = f->g_regs;
-        struct Bin { int type; int nodes; std::vector<int32_t> trees; };   // type 0: pair (0,1); 1: (R-2,R-1); 2: (0,R-1)
-        std::vector<Bin> bins;
+        const unsigned last = 1u << (R - 1);
+        const unsigned m_side1 = 3u, m_pair0 = (1u << (R - 2)) | last, m_pair1 = 1u | last, m_triple = 3u | last;
+        auto within = [](unsigned regs, unsigned mask) { return (regs & ~mask) == 0u; };
+        auto pair_ok = [&](unsigned regs) { return within(regs, m_pair0) || within(regs, m_pair1); };
+        auto side2_ok = [&](unsigned regs) { return pair_ok(regs) || within(regs, m_triple); };
+        struct Item { int k; unsigned regs; int flex; int32_t tree; };
+        struct Bin { int nodes = 0; unsigned regs = 0; std::vector<int32_t> trees; };
+        std::vector<Item> items;
+        std::vector<Bin> bins1, bins2;
         std::vector<int32_t> stumps, joint_trees, walk_trees;
         std::vector<int64_t> tn;
-        std::vector<std::pair<int, int32_t>> order;      // (node count, tree) for first-fit decreasing
-        auto type_ok = [&](int type, int32_t t) {
+        int dual_nodes = 0;
+        for (int32_t t = 0; t < f->m; ++t) {
             internal_nodes((int64_t)s * f->m + t, tn);
-            for (int64_t g : tn) {
-                const int reg = f->var[(size_t)g] >> 2;
-                const bool ok = R == 2 ? true
-                                : type == 0 ? reg <= 1
-                                : type == 1 ? (reg == R - 2 || reg == R - 1)
-                                            : (reg == 0 || reg == R - 1);
-                if (!ok) return false;
+            if (tn.empty()) { stumps.push_back(t); continue; }
+            unsigned regs = 0;
+            for (int64_t g : tn) regs |= 1u << (f->var[(size_t)g] >> 2);
+            const int k = (int)tn.size();
+            if (k <= 4 && (within(regs, m_side1) || side2_ok(regs))) {
+                items.push_back(Item{k, regs, (int)within(regs, m_side1) + (int)pair_ok(regs), t});
+                dual_nodes += k;
+            } else {
+                (k <= NB ? joint_trees : walk_trees).push_back(t);
+            }
+        }
+        std::stable_sort(items.begin(), items.end(),
+                         [](const Item& a, const Item& b2) { return a.k != b2.k ? a.k > b2.k : a.flex < b2.flex; });
+        auto try_pack = [&](int K) -> bool {
+            bins1.assign((size_t)K, Bin{});
+            bins2.assign((size_t)K, Bin{});
+            for (const Item& it : items) {
+                Bin* best = nullptr;
+                int best_key = 0;                         // lower is better: widening << 8 | (4 - fill) << 1 | side 2
+                if (within(it.regs, m_side1))
+                    for (Bin& b : bins1) {
+                        if (b.nodes + it.k > 4) continue;
+                        const int key = (4 - b.nodes) << 1;
+                        if (best == nullptr || key < best_key) { best = &b; best_key = key; }
+                    }
+                for (Bin& b : bins2) {
+                    const unsigned u = b.regs | it.regs;
+                    if (b.nodes + it.k > 4 || !side2_ok(u)) continue;
+                    const int widen = (!pair_ok(u) && pair_ok(b.regs)) ? 1 : 0;
+                    const int key = (widen << 8) | ((4 - b.nodes) << 1) | 1;
+                    if (best == nullptr || key < best_key) { best = &b; best_key = key; }
+                }
+                if (best == nullptr) return false;
+                best->nodes += it.k;
+                best->regs |= it.regs;
+                best->trees.push_back(it.tree);
             }
             return true;
         };
-        for (int32_t t = 0; t < f->m; ++t) {
-            internal_nodes((int64_t)s * f->m + t, tn);
-            if (tn.empty()) stumps.push_back(t);
-            else order.emplace_back((int)tn.size(), t);
-        }
-        std::stable_sort(order.begin(), order.end(), [](const auto& a, const auto& b2) { return a.first > b2.first; });
-        int n_side[2] = {0, 0};                           // bins feeding table 1 / table 2
-        for (const auto& kt : order) {
-            const int k = kt.first;
-            const int32_t t = kt.second;
-            const int n_types = R == 2 ? 2 : 3;           // R == 2: both tables read words (0,1); type 1 = "table 2"
-            bool ok[3] = {false, false, false};
-            bool any = false;
-            if (k <= 4)
-                for (int ty = 0; ty < n_types; ++ty) { ok[ty] = type_ok(ty, t); any = any || ok[ty]; }
-            if (!any) {
-                internal_nodes((int64_t)s * f->m + t, tn);
-                (k <= NB ? joint_trees : walk_trees).push_back(t);
-                continue;
-            }
-            // best fit among open bins of a compatible type; else open a bin on the emptier side
-            int best = -1;
-            for (size_t bi = 0; bi < bins.size(); ++bi)
-                if (ok[bins[bi].type] && bins[bi].nodes + k <= 4 && (best < 0 || bins[bi].nodes > bins[(size_t)best].nodes))
-                    best = (int)bi;
-            if (best < 0) {
-                int ty = -1;
-                for (int c = 0; c < n_types; ++c) {
-                    if (!ok[c]) continue;
-                    const int side = c == 0 ? 0 : 1;
-                    if (ty < 0 || n_side[side] < n_side[ty == 0 ? 0 : 1]) ty = c;
-                }
-                bins.push_back(Bin{ty, 0, {}});
-                ++n_side[ty == 0 ? 0 : 1];
-                best = (int)bins.size() - 1;
-            }
-            bins[(size_t)best].nodes += k;
-            bins[(size_t)best].trees.push_back(t);
-        }
-        // emit: pair every table-1 bin with a table-2 bin
-        std::vector<int> side1, side2;
-        for (size_t bi = 0; bi < bins.size(); ++bi) (bins[bi].type == 0 ? side1 : side2).push_back((int)bi);
+        int K = (dual_nodes + 7) / 8;
+        while (!try_pack(K)) ++K;                         // K = number of trees always fits
         int32_t* perm = tree_perm.data() + (size_t)s * f->m;
         int32_t pos = 0;                                  // next permuted position inside the draw
-        auto byte_of = [&](int type, int v) {            // byte index of variable v inside the table's register pair
-            if (R == 2 || type == 0) return v;
-            if (type == 1) return v - base1;
-            return v < 4 ? v : v - base1;
-        };
-        auto emit_table = [&](const Bin* bin, int table, uint32_t* gd) {
-            if (bin == nullptr) return;
-            uint32_t sel = 0, bias = 0, wgt = 0;
+        auto emit_table = [&](const Bin& bin, int table, uint32_t* gd) {
+            if (bin.trees.empty()) return;
+            const int ps = table == 0 ? -1 : within(bin.regs, m_pair0) ? 0 : within(bin.regs, m_pair1) ? 1 : 2;
+            uint32_t sel = 0, sel_t = 0, bias = 0, wgt = 0;
             int n = 0;
-            for (int32_t t : bin->trees) {
+            for (int32_t t : bin.trees) {
                 perm[pos++] = (int32_t)((int64_t)s * f->m + t);
                 internal_nodes((int64_t)s * f->m + t, tn);
                 for (int64_t gi : tn) {
                     const size_t g = (size_t)gi;
+                    const int v = f->var[g];
+                    // byte of variable v inside the table's gather operands (see dual_offsets in kernels_gather.cu)
+                    int byte = v;                                                   // table 1: words (0,1)
+                    if (ps == 0) byte = v - base1;                                  // words (R-2,R-1)
+                    else if (ps == 1) byte = v < 4 ? v : v - base1;                 // words (0,R-1)
+                    else if (ps == 2) {                                             // (PRMT(w0,w1,sel_t), R-1)
+                        if (v < 8) { sel_t |= (uint32_t)v << (4 * n); byte = n; }
+                        else byte = v - base1;
+                    }
                     node_bit[g] = (uint8_t)n;
-                    sel |= (uint32_t)byte_of(bin->type, f->var[g]) << (4 * n);
+                    sel |= (uint32_t)byte << (4 * n);
                     bias |= (uint32_t)(127 - f->cut[g]) << (8 * n);
                     wgt |= ((uint32_t)(-(8 << n)) & 0xFFu) << (8 * n);
                     ++n;
                 }
             }
             if (table == 0) { gd[0] |= sel; gd[1] = bias; gd[3] = wgt; }
-            else { gd[0] |= sel << 16; gd[2] = bias; gd[4] = wgt; gd[5] = bin->type == 2 ? 1u : 0u; }
+            else { gd[0] |= sel << 16; gd[2] = bias; gd[4] = wgt; gd[5] = (uint32_t)ps; gd[6] = sel_t; }
         };
-        const size_t n_dual = std::max(side1.size(), side2.size());
-        for (size_t r = 0; r < n_dual || (r == 0 && !stumps.empty() && joint_trees.empty() && walk_trees.empty()); ++r) {
+        // emit, sorted by table-2 kind so the kernel's per-record variant branch changes rarely
+        std::vector<int> rec_order;
+        for (int r = 0; r < K; ++r)
+            if (!bins1[(size_t)r].trees.empty() || !bins2[(size_t)r].trees.empty()) rec_order.push_back(r);
+        auto kind_of = [&](int r) {
+            const Bin& b = bins2[(size_t)r];
+            return b.trees.empty() || within(b.regs, m_pair0) ? 0 : within(b.regs, m_pair1) ? 1 : 2;
+        };
+        std::stable_sort(rec_order.begin(), rec_order.end(), [&](int a, int b2) { return kind_of(a) < kind_of(b2); });
+        if (rec_order.empty() && !stumps.empty() && joint_trees.empty() && walk_trees.empty()) {
+            bins1.assign(1, Bin{});
+            bins2.assign(1, Bin{});
+            rec_order.push_back(0);                       // a draw of stumps only: one record holding the constant
+        }
+        for (size_t q = 0; q < rec_order.size(); ++q) {
+            const int r = rec_order[q];
             open_group((int64_t)s * f->m + pos, 0u);
             uint32_t* gd = &desc[desc.size() - (size_t)DW];
             const int32_t start = pos;
-            if (r == 0)                                   // stumps only add a constant: all into the first table 1
+            if (q == 0) {                                 // stumps only add a constant: all into the first table 1
                 for (int32_t t : stumps) perm[pos++] = (int32_t)((int64_t)s * f->m + t);
-            emit_table(r < side1.size() ? &bins[(size_t)side1[r]] : nullptr, 0, gd);
+                stumps.clear();
+            }
+            emit_table(bins1[(size_t)r], 0, gd);
             split.back() = (uint32_t)(pos - start);
-            emit_table(r < side2.size() ? &bins[(size_t)side2[r]] : nullptr, 1, gd);
-            if (r == 0) stumps.clear();
+            emit_table(bins2[(size_t)r], 1, gd);
         }
         // JOINT records: greedy packing of the remaining small trees, two rounds of <= 4 slots, <= NB bits
         std::vector<Slot> gslots;

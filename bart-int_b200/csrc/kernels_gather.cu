@@ -12,6 +12,7 @@
 // Branch-free, warp-uniform, and the only shared-memory traffic left is the table lookup + 2 descriptor loads.
 #include <algorithm>
 #include <cstdlib>
+#include <type_traits>
 
 #include "pipeline.cuh"
 
@@ -61,12 +62,13 @@ __device__ __forceinline__ uint32_t gather_offset(const uint32_t (&c)[R], uint32
     return (uint32_t)o;
 }
 
-// DUAL record: two independent 16-entry tables.  Table 1 gathers from code words (0,1); table 2 from (R-2,R-1) or,
-// with pairsel, (0,R-1).  Returns both byte offsets (table 2's already includes its +128).
-template <int R>
+// DUAL record: two independent 16-entry tables.  Table 1 gathers from code words (0,1); table 2 from (R-2,R-1)
+// [V = 0], (0,R-1) [V = 1] or (PRMT(w0,w1,sel_t), R-1) [V = 2: any three words, one more PRMT].  V is a property of
+// the record (warp-uniform branch outside the point loop).  Returns both byte offsets (table 2's includes its +128).
+template <int R, int V>
 __device__ __forceinline__ void dual_offsets(const uint32_t (&c)[R], uint32_t d0, uint32_t d1, uint32_t d2, uint32_t d3,
-                                             uint32_t d4, uint32_t pairsel, uint32_t& o1, uint32_t& o2) {
-    const uint32_t lo = (R == 2) ? c[0] : (pairsel ? c[0] : c[R - 2]);
+                                             uint32_t d4, uint32_t sel_t, uint32_t& o1, uint32_t& o2) {
+    const uint32_t lo = (R == 2 || V == 1) ? c[0] : (V == 0) ? c[R - 2] : __byte_perm(c[0], c[1], sel_t);
     const uint32_t gA = __byte_perm(c[0], c[1], d0);
     const uint32_t gB = __byte_perm(lo, c[R - 1], d0 >> 16);
     o1 = (uint32_t)__dp4a((int)sign_mask4(gA + d1), (int)d3, 0);
@@ -163,17 +165,22 @@ __global__ void __launch_bounds__(TG_THREADS, MOMENTS ? 2 : 3) eval_gather_kerne
             joint_mask |= (unsigned long long)__ballot_sync(0xffffffffu, (fl & TK_FLAG_JOINT) != 0u) << base;
         }
         // DUAL records without a flag (the bulk) run in a tight loop; the next flagged record is found with one ffs
-        auto dual_group = [&](const unsigned char* rec) {
-            const uint4 da = *reinterpret_cast<const uint4*>(rec + TK_HDR);            // smem broadcast loads
-            const uint2 db = *reinterpret_cast<const uint2*>(rec + TK_HDR + 16);
-            const unsigned char* __restrict__ tbl = rec + tg_tbl_off();
+        auto dual_points = [&](auto variant, const uint4& da, const uint4& db, const unsigned char* __restrict__ tbl) {
 #pragma unroll
             for (int p = 0; p < P; ++p) {
                 uint32_t o1, o2;
-                dual_offsets<R>(creg[p], da.x, da.y, da.z, da.w, db.x, db.y, o1, o2);
+                dual_offsets<R, decltype(variant)::value>(creg[p], da.x, da.y, da.z, da.w, db.x, db.z, o1, o2);
                 acc[p] += *reinterpret_cast<const double*>(tbl + o1);
                 acc[p] += *reinterpret_cast<const double*>(tbl + o2);
             }
+        };
+        auto dual_group = [&](const unsigned char* rec) {
+            const uint4 da = *reinterpret_cast<const uint4*>(rec + TK_HDR);            // smem broadcast loads
+            const uint4 db = *reinterpret_cast<const uint4*>(rec + TK_HDR + 16);       // wB, table-2 kind, sel_t, -
+            const unsigned char* __restrict__ tbl = rec + tg_tbl_off();
+            if (R == 2 || db.y == 0u) dual_points(std::integral_constant<int, 0>{}, da, db, tbl);
+            else if (db.y == 1u) dual_points(std::integral_constant<int, 1>{}, da, db, tbl);
+            else dual_points(std::integral_constant<int, 2>{}, da, db, tbl);
         };
         auto joint_group = [&](const unsigned char* rec) {
             const uint4 da = *reinterpret_cast<const uint4*>(rec + TK_HDR);
@@ -383,7 +390,9 @@ __global__ void __launch_bounds__(256) gather_leaf_kernel(
         idx1 = idx2 = gather_offset<R>(c, dw[0], dw[1], dw[2], dw[3], dw[4]) >> 3;
     } else {
         uint32_t o1, o2;
-        dual_offsets<R>(c, dw[0], dw[1], dw[2], dw[3], dw[4], dw[5], o1, o2);
+        if (R == 2 || dw[5] == 0u) dual_offsets<R, 0>(c, dw[0], dw[1], dw[2], dw[3], dw[4], dw[6], o1, o2);
+        else if (dw[5] == 1u) dual_offsets<R, 1>(c, dw[0], dw[1], dw[2], dw[3], dw[4], dw[6], o1, o2);
+        else dual_offsets<R, 2>(c, dw[0], dw[1], dw[2], dw[3], dw[4], dw[6], o1, o2);
         idx1 = o1 >> 3;
         idx2 = (o2 - 128u) >> 3;
     }
