@@ -233,7 +233,9 @@ int bartint_points_from_device(const bartint_forest* f, const double* dX, int64_
     DeviceGuard g(f->device);
     rc = launch_bin_points(dX, ld, N, d, f->dev.cut_off, f->dev.cut_val, f->max_cuts, (*out)->codes, (*out)->Npad,
                            (cudaStream_t)stream);
-    // (a one-pass kernel writing both layouts was tried and was slower: its 1-byte feature-major stores are 32 B per warp)
+    // (one-pass kernels writing both layouts were tried twice -- one point per thread, then four with a PRMT byte
+    //  transpose -- and were slower at every size (tools/k0_sweep.py: 1.39 vs 1.28 ms at 5e7 points): binning is bound
+    //  by its shared-memory cut-table probes, and the pass over all variables leaves fewer, fatter threads)
     if (rc == BARTINT_OK && (*out)->codes_pm)
         rc = launch_repack_codes((*out)->codes, (*out)->Npad, d, (*out)->codes_pm, (cudaStream_t)stream);
     if (rc) { bartint_points_destroy(*out); *out = nullptr; }

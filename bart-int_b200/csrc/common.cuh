@@ -156,6 +156,7 @@ int launch_eval_gather(const bartint_forest* f, const bartint_points* p, const E
                        int fp_scaled, cudaStream_t st);
 int launch_gather_leaf(const bartint_forest* f, const bartint_points* p, int32_t draw_begin, int32_t draw_end,
                        int32_t* leaf_out, cudaStream_t st);
+int gather_tile(bool mom, bool full);
 int gather_resident_ctas(const bartint_forest* f, bool mom, bool full);   // occupancy query for make_plan
 inline int fast_rec_bytes(const bartint_forest* f) { return f->gather ? tg_rec_bytes(f->nb) : tk_rec_bytes(f->nb); }
 inline int fast_tbl_off(const bartint_forest* f) { return f->gather ? tg_tbl_off() : tk_tbl_off(f->nb); }

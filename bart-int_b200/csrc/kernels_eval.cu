@@ -398,7 +398,7 @@ EvalPlan make_plan(const bartint_forest* f, const bartint_points* p, uint32_t fl
     int resident_per_sm = 8;
     pl.tile = WK_THREADS;
     if (pl.use_gather) {
-        pl.tile = 2048;
+        pl.tile = gather_tile(want_moments, want_full);
         resident_per_sm = gather_resident_ctas(f, want_moments, want_full);
     } else if (pl.use_table) {
         TableConfig c = table_config(f->nb, p->d, want_moments, want_full);

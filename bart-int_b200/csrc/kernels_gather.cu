@@ -19,8 +19,7 @@
 namespace bartint {
 
 constexpr int TG_THREADS = 256;
-constexpr int TG_P = 8;                          // points per thread
-constexpr int TG_TILE = TG_THREADS * TG_P;       // 2048 points per CTA
+constexpr int TG_P = 8;                          // points per thread (16 in the sums-only kernel, see gather_tile)
 
 // ---------------------------------------------------------------------------------------------
 // point-major packed codes: codes_pm[i] = 16 bytes, byte j = code of variable j (0 beyond d)
@@ -89,10 +88,10 @@ size_t tg_smem_bytes() {
            (TK_NSTAGE + 1) * sizeof(uint64_t);
 }
 
-template <int NB, int R, bool MOMENTS, bool FULL>
-__global__ void __launch_bounds__(TG_THREADS, MOMENTS ? 2 : 3) eval_gather_kernel(const TableParams prm) {
+template <int NB, int R, bool MOMENTS, bool FULL, int P = TG_P>
+__global__ void __launch_bounds__(TG_THREADS, P > 8 ? 2 : MOMENTS ? 2 : 3) eval_gather_kernel(const TableParams prm) {
     extern __shared__ __align__(128) unsigned char smem[];
-    constexpr int P = TG_P, T = TG_THREADS, TILE = TG_TILE;
+    constexpr int T = TG_THREADS, TILE = TG_THREADS * P;
     constexpr int REC = tg_rec_bytes(NB);
     constexpr int GS = groups_per_stage(REC);
     constexpr int STAGE = GS * REC;
@@ -277,6 +276,15 @@ __global__ void __launch_bounds__(TG_THREADS, MOMENTS ? 2 : 3) eval_gather_kerne
     }
 }
 
+// points per thread: 16 for the sums-only kernel (the Monte Carlo path: 2 CTAs x 256 threads x 128 registers per SM;
+// halves the per-record descriptor/loop overhead per point, 5.76 -> 5.56 ms at cfg 2), 8 when per-point moments or
+// the full matrix are wanted (their extra accumulators do not fit 16 points).  BARTINT_GATHER_P=8 forces 8.
+int gather_points_per_thread(bool mom, bool full) {
+    static const bool p8 = [] { const char* e = std::getenv("BARTINT_GATHER_P"); return e && std::atoi(e) == 8; }();
+    return (!p8 && !mom && !full) ? 16 : TG_P;
+}
+int gather_tile(bool mom, bool full) { return TG_THREADS * gather_points_per_thread(mom, full); }
+
 // ---- instantiation table -----------------------------------------------------------------------------------
 typedef void (*gather_kernel_t)(const TableParams);
 
@@ -285,6 +293,7 @@ static gather_kernel_t pick_gather(bool mom, bool full) {
     if (mom && full) return eval_gather_kernel<NB, R, true, true>;
     if (mom) return eval_gather_kernel<NB, R, true, false>;
     if (full) return eval_gather_kernel<NB, R, false, true>;
+    if (gather_points_per_thread(mom, full) == 16) return eval_gather_kernel<NB, R, false, false, 16>;
     return eval_gather_kernel<NB, R, false, false>;
 }
 
@@ -319,7 +328,8 @@ int launch_eval_gather(const bartint_forest* f, const bartint_points* p, const E
                        double* pt_mean, double* pt_m2, double* full_pred, double fp_scale, double fp_y0, int fp_scaled,
                        cudaStream_t st) {
     BI_REQUIRE(p->codes_pm != nullptr, BARTINT_ERR_ARG, "internal: points have no packed codes for the gather kernel");
-    BI_REQUIRE(plan.tile == TG_TILE, BARTINT_ERR_ARG, "internal: plan/launch tile mismatch");
+    BI_REQUIRE(plan.tile == gather_tile(pt_mean != nullptr, full_pred != nullptr), BARTINT_ERR_ARG,
+               "internal: plan/launch tile mismatch");
     TableParams prm{};
     prm.group_rec = f->dev.group_rec;
     prm.draw_group_off = f->dev.draw_group_off;

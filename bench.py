@@ -316,9 +316,10 @@ def run_ours(args):
     trees_per_group = S * m / max(f0.n_groups, 1)
     nb = f0.table_bits
     if f0.fast_kernel == "gather":
-        pts = 8                                          # points per thread
-        wavefronts = pts * 2.0 + 2.0                     # P table LDS.64 (2 wavefronts each, conflict-free) + 2 descriptor loads
-        instrs = pts * 10.0 + 2.0 + 5.0                  # (PRMT, IADD, PRMT, IDP) x 2 rounds + LDS + DADD per point; descriptors; loop
+        pts = 16                                         # points per thread (sums-only kernel of the MC path)
+        # DUAL record: two 16-entry fp64 tables per record and point
+        wavefronts = pts * 2 * 2.0 + 2.0                 # 2 table LDS.64 per point (2 wavefronts each, conflict-free) + 2 descriptor loads
+        instrs = pts * 12.0 + 2.0 + 7.0                  # (PRMT, IADD, PRMT, IDP, LDS, DADD) per table and point; descriptors; loop
     else:
         pts = 16
         wavefronts = nb / 2.0 + nb * 4.0 + pts * 2.0     # descriptor LDS.128 + code LDS.32 per (node, quad) + table LDS.64
