@@ -11,6 +11,9 @@ bartint_measure_code <- c(uniform = 0L, gaussian = 1L, exponential = 2L)
 
 # export the dbarts 0.9-8 sampler state once per fitted model (cached on the model object's environment)
 bartint_forest <- function(model) {
+  if (!is.null(model$treedraws))      # a BART::wbart / pbart fit (README.md:202: "swap the BART package")
+    return(.Call("bartint_R_forest_wbart", model$treedraws$trees, model$treedraws$cutpoints,
+                 if (is.null(model$offset)) 0 else model$offset))
   fit <- model$fit
   if (!fit$control@keepTrees) stop("bartint needs bart(..., keeptrees = TRUE)")
   key <- "bartint_handle"

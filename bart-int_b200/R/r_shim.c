@@ -58,6 +58,27 @@ SEXP bartint_R_forest(SEXP trees, SEXP fits, SEXP x, SEXP cuts, SEXP ymin, SEXP 
     return ptr;
 }
 
+/* .Call("bartint_R_forest_wbart", fit$treedraws$trees (chr 1), fit$treedraws$cutpoints (list of p numeric),
+ *       fit$offset)  -> external pointer.   For fits made with BART::wbart / pbart instead of dbarts
+ * (the reference's README.md:202 invites swapping the BART package); routing follows tree::bn (left iff x < cut). */
+SEXP bartint_R_forest_wbart(SEXP trees, SEXP cuts, SEXP offset) {
+    const int d = (int)XLENGTH(cuts);
+    int32_t* off = (int32_t*)R_alloc((size_t)d + 1, sizeof(int32_t));
+    off[0] = 0;
+    for (int j = 0; j < d; ++j) off[j + 1] = off[j] + (int32_t)XLENGTH(VECTOR_ELT(cuts, j));
+    double* vals = (double*)R_alloc((size_t)off[d] + 1, sizeof(double));
+    for (int j = 0; j < d; ++j) {
+        const double* c = REAL(VECTOR_ELT(cuts, j));
+        for (int k = 0; k < off[j + 1] - off[j]; ++k) vals[off[j] + k] = c[k];
+    }
+    bartint_forest* f = NULL;
+    check(bartint_forest_from_wbart(CHAR(STRING_ELT(trees, 0)), 0, d, off, vals, Rf_asReal(offset), &f));
+    SEXP ptr = PROTECT(R_MakeExternalPtr(f, R_NilValue, R_NilValue));
+    R_RegisterCFinalizerEx(ptr, forest_finalizer, TRUE);
+    UNPROTECT(1);
+    return ptr;
+}
+
 /* sampleIntegrals(model, dim, measure): src/BARTInt.R:204-223.  n_draws_used <= 0 -> all draws. */
 SEXP bartint_R_exact_integrals(SEXP ptr, SEXP measure, SEXP n_draws_used) {
     bartint_forest* f = forest_of(ptr);

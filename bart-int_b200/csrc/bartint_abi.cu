@@ -140,8 +140,39 @@ int bartint_forest_from_soa(int32_t S, int32_t m, int32_t d, const int64_t* tree
                             const int32_t* split_cut_idx, const int32_t* left, const int32_t* right,
                             const double* leaf_mu, const int32_t* cut_offsets, const double* cut_values, double y_min,
                             double y_max, bartint_forest** out) {
+    return bartint_forest_from_soa_routed(S, m, d, tree_node_offset, split_var, split_cut_idx, left, right, leaf_mu,
+                                          cut_offsets, cut_values, y_min, y_max, BARTINT_ROUTE_DBARTS, out);
+}
+
+int bartint_forest_from_wbart(const char* trees_text, int64_t text_len, int32_t d, const int32_t* cut_offsets,
+                              const double* cut_values, double offset, bartint_forest** out) {
     BI_REQUIRE(out != nullptr, BARTINT_ERR_ARG, "out is NULL");
     *out = nullptr;
+    BI_REQUIRE(trees_text != nullptr, BARTINT_ERR_ARG, "trees_text is NULL");
+    if (text_len <= 0) text_len = (int64_t)std::strlen(trees_text);
+    BI_REQUIRE(trees_text[text_len] == '\0', BARTINT_ERR_ARG, "trees_text must be NUL terminated at text_len");
+    int rc = check_cuts(d, cut_offsets, cut_values);
+    if (rc) return rc;
+    bartint_forest* f = new (std::nothrow) bartint_forest();
+    BI_REQUIRE(f != nullptr, BARTINT_ERR_NOMEM, "out of host memory");
+    f->d = d; f->y_min = offset - 0.5; f->y_max = offset + 0.5; f->route = BARTINT_ROUTE_BART;
+    f->cut_off.assign(cut_offsets, cut_offsets + d + 1);
+    f->cut_val.assign(cut_values, cut_values + cut_offsets[d]);
+    rc = parse_wbart_forest(trees_text, text_len, d, f);
+    if (rc) { delete f; return rc; }
+    return finish_forest(f, out);
+}
+
+int bartint_forest_route(const bartint_forest* f) { return f ? f->route : -1; }
+
+int bartint_forest_from_soa_routed(int32_t S, int32_t m, int32_t d, const int64_t* tree_node_offset,
+                                   const int32_t* split_var, const int32_t* split_cut_idx, const int32_t* left,
+                                   const int32_t* right, const double* leaf_mu, const int32_t* cut_offsets,
+                                   const double* cut_values, double y_min, double y_max, int32_t route,
+                                   bartint_forest** out) {
+    BI_REQUIRE(out != nullptr, BARTINT_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    BI_REQUIRE(route == BARTINT_ROUTE_DBARTS || route == BARTINT_ROUTE_BART, BARTINT_ERR_ARG, "unknown routing rule %d", route);
     BI_REQUIRE(S >= 0 && m >= 0, BARTINT_ERR_ARG, "S and m must be >= 0");
     BI_REQUIRE(tree_node_offset != nullptr, BARTINT_ERR_ARG, "tree_node_offset is NULL");
     const bool has_nodes = (int64_t)S * m > 0;
@@ -151,7 +182,7 @@ int bartint_forest_from_soa(int32_t S, int32_t m, int32_t d, const int64_t* tree
     if (rc) return rc;
     bartint_forest* f = new (std::nothrow) bartint_forest();
     BI_REQUIRE(f != nullptr, BARTINT_ERR_NOMEM, "out of host memory");
-    f->S = S; f->m = m; f->d = d; f->y_min = y_min; f->y_max = y_max;
+    f->S = S; f->m = m; f->d = d; f->y_min = y_min; f->y_max = y_max; f->route = route;
     f->cut_off.assign(cut_offsets, cut_offsets + d + 1);
     f->cut_val.assign(cut_values, cut_values + cut_offsets[d]);
     rc = canonicalise_soa(S, m, d, tree_node_offset, split_var, split_cut_idx, left, right, leaf_mu, f);
@@ -231,8 +262,8 @@ int bartint_points_from_device(const bartint_forest* f, const double* dX, int64_
     int rc = make_points(f, N, d, (cudaStream_t)stream, out);
     if (rc) return rc;
     DeviceGuard g(f->device);
-    rc = launch_bin_points(dX, ld, N, d, f->dev.cut_off, f->dev.cut_val, f->max_cuts, (*out)->codes, (*out)->Npad,
-                           (cudaStream_t)stream);
+    rc = launch_bin_points(dX, ld, N, d, f->dev.cut_off, f->dev.cut_val, f->max_cuts, f->route, (*out)->codes,
+                           (*out)->Npad, (cudaStream_t)stream);
     // (one-pass kernels writing both layouts were tried twice -- one point per thread, then four with a PRMT byte
     //  transpose -- and were slower at every size (tools/k0_sweep.py: 1.39 vs 1.28 ms at 5e7 points): binning is bound
     //  by its shared-memory cut-table probes, and the pass over all variables leaves fewer, fatter threads)
@@ -321,8 +352,8 @@ int bartint_points_generate(const bartint_forest* f, int32_t measure, int64_t N,
     int rc = make_points(f, N, f->d, (cudaStream_t)stream, out);
     if (rc) return rc;
     DeviceGuard g(f->device);
-    rc = launch_generate_points(measure, N, first_index, seed, f->d, f->dev.cut_off, f->dev.cut_val, (*out)->codes,
-                                (*out)->Npad, dX_out, (cudaStream_t)stream);
+    rc = launch_generate_points(measure, N, first_index, seed, f->d, f->dev.cut_off, f->dev.cut_val, f->route,
+                                (*out)->codes, (*out)->Npad, dX_out, (cudaStream_t)stream);
     if (rc == BARTINT_OK && (*out)->codes_pm)
         rc = launch_repack_codes((*out)->codes, (*out)->Npad, f->d, (*out)->codes_pm, (cudaStream_t)stream);
     if (rc) { bartint_points_destroy(*out); *out = nullptr; }

@@ -96,6 +96,7 @@ struct bartint_forest {
     int64_t n_nodes = 0, n_leaves = 0;
     int32_t max_depth = 0, max_internal = 0, max_cuts = 0;
     double y_min = 0, y_max = 1;
+    int route = 0;             // BARTINT_ROUTE_DBARTS (left iff x <= cut) or BARTINT_ROUTE_BART (left iff x < cut)
     // canonical (pre-order) host SoA
     std::vector<int64_t> tree_off;
     std::vector<int32_t> var, cut, left, right;
@@ -137,15 +138,16 @@ int forest_upload(bartint_forest* f);           // build device arrays (+ table 
 int parse_dbarts_forest(const char* const* tree_strings, const double* tree_fits, const double* x_train,
                         int64_t n, int32_t d, const int32_t* cut_offsets, const double* cut_values,
                         int32_t m, int32_t S, bartint_forest* f);
+int parse_wbart_forest(const char* text, int64_t len, int32_t d, bartint_forest* f);
 int canonicalise_soa(int32_t S, int32_t m, int32_t d, const int64_t* tree_node_offset, const int32_t* split_var,
                      const int32_t* split_cut_idx, const int32_t* left, const int32_t* right,
                      const double* leaf_mu, bartint_forest* f);
 
 // kernel launchers (kernels_*.cu)
 int launch_bin_points(const double* dX, int64_t ld, int64_t N, int32_t d, const int32_t* d_cut_off,
-                      const double* d_cut_val, int max_cuts, uint8_t* codes, int64_t Npad, cudaStream_t st);
+                      const double* d_cut_val, int max_cuts, int route, uint8_t* codes, int64_t Npad, cudaStream_t st);
 int launch_generate_points(int measure, int64_t N, int64_t first_index, uint64_t seed, int32_t d,
-                           const int32_t* d_cut_off, const double* d_cut_val, uint8_t* codes, int64_t Npad,
+                           const int32_t* d_cut_off, const double* d_cut_val, int route, uint8_t* codes, int64_t Npad,
                            double* x_out, cudaStream_t st);
 struct EvalPlan;
 int launch_build_tables(const bartint_forest* f, const uint32_t* d_desc, int desc_words, const uint32_t* d_hdr,

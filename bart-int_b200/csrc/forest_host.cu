@@ -216,6 +216,144 @@ int parse_dbarts_forest(const char* const* tree_strings, const double* tree_fits
     return BARTINT_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// BART::wbart / pbart `treedraws$trees` text:
+//   "ndpost ntree p\n"  then per draw, per tree:  "nnodes\n"  followed by nnodes lines  "nid var cut theta\n"
+// (tree.cpp operator<<: nodes as tree::getnodes lists them).  nid = heap index (root 1, children 2 nid, 2 nid + 1);
+// a node is internal iff its left child is listed; var / cut 0-based; theta = leaf value.
+// Pass 1 (sequential) finds every tree's node lines by counting newlines; pass 2 (OpenMP over trees) parses the
+// lines and emits the canonical pre-order SoA.
+// ---------------------------------------------------------------------------------------------
+static bool parse_i64(const char*& p, const char* end, int64_t& out) {
+    while (p < end && (*p == ' ' || *p == '\t' || *p == '\r' || *p == '\n')) ++p;
+    if (p >= end || *p < '0' || *p > '9') return false;
+    int64_t v = 0;
+    while (p < end && *p >= '0' && *p <= '9') {
+        if (v > (std::numeric_limits<int64_t>::max() - 9) / 10) return false;
+        v = v * 10 + (*p - '0');
+        ++p;
+    }
+    out = v;
+    return true;
+}
+
+int parse_wbart_forest(const char* text, int64_t len, int32_t d, bartint_forest* f) {
+    const char* p = text;
+    const char* end = text + len;
+    int64_t S64 = 0, m64 = 0, p64 = 0;
+    BI_REQUIRE(parse_i64(p, end, S64) && parse_i64(p, end, m64) && parse_i64(p, end, p64), BARTINT_ERR_PARSE,
+               "treedraws text does not start with \"ndpost ntree p\"");
+    BI_REQUIRE(S64 <= 1 << 24 && m64 <= 1 << 24 && S64 * m64 <= (int64_t)1 << 31, BARTINT_ERR_PARSE,
+               "implausible treedraws header (%lld draws x %lld trees)", (long long)S64, (long long)m64);
+    BI_REQUIRE(p64 == d, BARTINT_ERR_ARG, "treedraws header says p = %lld but d = %d cut-point lists were given",
+               (long long)p64, d);
+    f->S = (int32_t)S64; f->m = (int32_t)m64;
+    const int64_t n_trees = S64 * m64;
+    // pass 1: locate each tree's node lines
+    std::vector<const char*> first_line((size_t)n_trees);
+    f->tree_off.assign((size_t)n_trees + 1, 0);
+    for (int64_t k = 0; k < n_trees; ++k) {
+        int64_t nn = 0;
+        BI_REQUIRE(parse_i64(p, end, nn) && nn >= 1 && nn < (int64_t)1 << 30, BARTINT_ERR_PARSE,
+                   "tree %lld: missing or bad node count", (long long)k);
+        const char* nl = (const char*)memchr(p, '\n', (size_t)(end - p));
+        BI_REQUIRE(nl != nullptr, BARTINT_ERR_PARSE, "tree %lld: text ends after the node count", (long long)k);
+        p = nl + 1;
+        first_line[(size_t)k] = p;
+        for (int64_t q = 0; q < nn; ++q) {
+            nl = (const char*)memchr(p, '\n', (size_t)(end - p));
+            if (nl == nullptr) {
+                BI_REQUIRE(q == nn - 1 && p < end, BARTINT_ERR_PARSE, "tree %lld: %lld node lines announced, text ends after %lld",
+                           (long long)k, (long long)nn, (long long)q);
+                p = end;
+            } else {
+                p = nl + 1;
+            }
+        }
+        f->tree_off[(size_t)k + 1] = f->tree_off[(size_t)k] + nn;
+    }
+    while (p < end && (*p == ' ' || *p == '\t' || *p == '\r' || *p == '\n' || *p == '\0')) ++p;
+    BI_REQUIRE(p == end, BARTINT_ERR_PARSE, "trailing text after the last tree");
+    const int64_t nn_total = f->tree_off[(size_t)n_trees];
+    f->var.resize((size_t)nn_total); f->cut.resize((size_t)nn_total); f->left.resize((size_t)nn_total);
+    f->right.resize((size_t)nn_total); f->mu.resize((size_t)nn_total);
+    // pass 2: parse + heap ids -> pre-order
+    int64_t bad_tree = -1;
+#pragma omp parallel
+    {
+        struct Node { uint64_t nid; int32_t var, cut; double theta; };
+        std::vector<Node> nodes;
+        std::vector<std::pair<int64_t, int32_t>> stack;      // (index into nodes, parent slot or -1 - (parent slot) for right)
+#pragma omp for schedule(static)
+        for (int64_t k = 0; k < n_trees; ++k) {
+            const int64_t base = f->tree_off[(size_t)k];
+            const int32_t nn = (int32_t)(f->tree_off[(size_t)k + 1] - base);
+            const char* q = first_line[(size_t)k];
+            nodes.clear();
+            bool ok = true;
+            for (int32_t a = 0; a < nn && ok; ++a) {
+                int64_t nid = 0, v = 0, c = 0;
+                ok = parse_i64(q, end, nid) && parse_i64(q, end, v) && parse_i64(q, end, c) && nid >= 1;
+                if (!ok) break;
+                while (q < end && (*q == ' ' || *q == '\t')) ++q;
+                char* after = nullptr;
+                const double th = strtod(q, &after);           // text is NUL terminated (ABI contract)
+                ok = after != q && after <= end;
+                q = after;
+                nodes.push_back(Node{(uint64_t)nid, (int32_t)std::min<int64_t>(v, INT32_MAX), (int32_t)std::min<int64_t>(c, INT32_MAX), th});
+            }
+            if (ok) {
+                std::sort(nodes.begin(), nodes.end(), [](const Node& x, const Node& y) { return x.nid < y.nid; });
+                for (int32_t a = 1; a < nn; ++a) ok = ok && nodes[(size_t)a].nid != nodes[(size_t)a - 1].nid;
+            }
+            auto find = [&](uint64_t nid) -> int64_t {
+                auto it = std::lower_bound(nodes.begin(), nodes.end(), nid, [](const Node& x, uint64_t id) { return x.nid < id; });
+                return (it != nodes.end() && it->nid == nid) ? (int64_t)(it - nodes.begin()) : -1;
+            };
+            int32_t emitted = 0;
+            if (ok) {
+                const int64_t root = find(1);
+                ok = root >= 0;
+                stack.clear();
+                if (ok) stack.emplace_back(root, INT32_MIN);
+                while (!stack.empty() && ok) {
+                    const int64_t a = stack.back().first;
+                    const int32_t link = stack.back().second;
+                    stack.pop_back();
+                    const int32_t me = emitted++;
+                    if (link != INT32_MIN && link < 0) f->right[(size_t)(base + (-1 - link))] = me;   // right child of that slot
+                    const Node& nd = nodes[(size_t)a];
+                    const int64_t l = nd.nid <= (UINT64_MAX >> 1) ? find(2 * nd.nid) : -1;
+                    if (l >= 0) {
+                        const int64_t r = find(2 * nd.nid + 1);
+                        ok = r >= 0 && nd.var >= 0 && nd.var < d &&
+                             nd.cut < f->cut_off[(size_t)nd.var + 1] - f->cut_off[(size_t)nd.var];
+                        if (!ok) break;
+                        f->var[(size_t)(base + me)] = nd.var; f->cut[(size_t)(base + me)] = nd.cut;
+                        f->left[(size_t)(base + me)] = me + 1; f->right[(size_t)(base + me)] = -1;
+                        f->mu[(size_t)(base + me)] = 0.0;
+                        stack.emplace_back(r, -1 - me);
+                        stack.emplace_back(l, me);
+                    } else {
+                        f->var[(size_t)(base + me)] = -1; f->cut[(size_t)(base + me)] = 0;
+                        f->left[(size_t)(base + me)] = -1; f->right[(size_t)(base + me)] = -1;
+                        f->mu[(size_t)(base + me)] = nd.theta;
+                    }
+                }
+                ok = ok && emitted == nn;                     // every listed node reachable from the root
+            }
+            if (!ok) {
+#pragma omp critical
+                if (bad_tree < 0 || k < bad_tree) bad_tree = k;
+            }
+        }
+    }
+    BI_REQUIRE(bad_tree < 0, BARTINT_ERR_PARSE,
+               "tree %lld (draw %lld, tree %lld): malformed node lines, missing root/child, unreachable node, or a split outside the cut-point lists",
+               (long long)bad_tree, (long long)(bad_tree / std::max<int64_t>(m64, 1)), (long long)(bad_tree % std::max<int64_t>(m64, 1)));
+    return BARTINT_OK;
+}
+
 int canonicalise_soa(int32_t S, int32_t m, int32_t d, const int64_t* off, const int32_t* var, const int32_t* cut,
                      const int32_t* left, const int32_t* right, const double* mu, bartint_forest* f) {
     const int64_t n_trees = (int64_t)S * m;

@@ -17,23 +17,31 @@ namespace bartint {
 // usequants=FALSE cut points, instead of the 7 dependent probes of a binary search (which made the kernel
 // instruction/shared-memory bound rather than HBM bound).  `cuts` is sentinel padded: cuts[-1] = -inf, cuts[nc] = +inf,
 // so  k is correct  <=>  cuts[k-1] < x  &&  !(cuts[k] < x).
+// INC = false (dbarts):      code = #{k : cut[k] <  x}, NaN -> 0   ("right iff x >  cut"  <=>  code > cut index)
+// INC = true  (BART::wbart):  code = #{k : cut[k] <= x}, NaN -> nc  ("right iff x >= cut", tree::bn's "x < c -> left")
+template <bool INC>
+__device__ __forceinline__ bool cut_below(double c, double x) { return INC ? c <= x : c < x; }
+
+template <bool INC>
 __device__ __forceinline__ uint32_t bin_one(double x, const double* __restrict__ cuts, int nc, double c0, double inv_step) {
+    if (INC && x != x) return (uint32_t)nc;               // NaN: every "x < c" is false -> always right
     const double g = fma(x - c0, inv_step, 1.0);          // uniform grid: #{k : cut[k] < x} = floor((x - c0)/step) + 1
     int k = __double2int_rd(fmin(fmax(g, 0.0), (double)nc));   // NaN -> fmax/fmin return the non-NaN bound -> 0
-    const bool up = cuts[k] < x, lo_ok = cuts[k - 1] < x;
+    const bool up = cut_below<INC>(cuts[k], x), lo_ok = cut_below<INC>(cuts[k - 1], x);
     if (lo_ok && !up) return (uint32_t)k;                 // common case: guess was right
-    if (up && !(cuts[k + 1 > nc ? nc : k + 1] < x)) return (uint32_t)(k + 1);
-    if (!lo_ok && k >= 2 && cuts[k - 2] < x) return (uint32_t)(k - 1);
-    int lo = 0, len = nc;                                 // irregular grid / NaN: plain lower-bound search
+    if (up && !cut_below<INC>(cuts[k + 1 > nc ? nc : k + 1], x)) return (uint32_t)(k + 1);
+    if (!lo_ok && k >= 2 && cut_below<INC>(cuts[k - 2], x)) return (uint32_t)(k - 1);
+    int lo = 0, len = nc;                                 // irregular grid / NaN / infinities: plain lower-bound search
     while (len > 0) {
         int h = len >> 1;
-        bool r = cuts[lo + h] < x;
+        bool r = cut_below<INC>(cuts[lo + h], x);
         lo = r ? lo + h + 1 : lo;
         len = r ? len - h - 1 : h;
     }
     return (uint32_t)lo;
 }
 
+template <bool INC>
 __global__ void __launch_bounds__(256) bin_points_kernel(const double* __restrict__ X, int64_t ld, int64_t N,
                                                          const int32_t* __restrict__ cut_off,
                                                          const double* __restrict__ cut_val,
@@ -63,18 +71,18 @@ __global__ void __launch_bounds__(256) bin_points_kernel(const double* __restric
             } else {
                 x0 = __ldg(col + i); x1 = __ldg(col + i + 1); x2 = __ldg(col + i + 2); x3 = __ldg(col + i + 3);
             }
-            word = bin_one(x0, s_cut, nc, c0, inv_step) | (bin_one(x1, s_cut, nc, c0, inv_step) << 8) |
-                   (bin_one(x2, s_cut, nc, c0, inv_step) << 16) | (bin_one(x3, s_cut, nc, c0, inv_step) << 24);
+            word = bin_one<INC>(x0, s_cut, nc, c0, inv_step) | (bin_one<INC>(x1, s_cut, nc, c0, inv_step) << 8) |
+                   (bin_one<INC>(x2, s_cut, nc, c0, inv_step) << 16) | (bin_one<INC>(x3, s_cut, nc, c0, inv_step) << 24);
         } else {
             for (int k = 0; k < 4; ++k)
-                if (i + k < N) word |= bin_one(__ldg(col + i + k), s_cut, nc, c0, inv_step) << (8 * k);
+                if (i + k < N) word |= bin_one<INC>(__ldg(col + i + k), s_cut, nc, c0, inv_step) << (8 * k);
         }
         codes4[(int64_t)j * quads_per_row + w] = word;   // padding quads (i >= N) are written as 0
     }
 }
 
 int launch_bin_points(const double* dX, int64_t ld, int64_t N, int32_t d, const int32_t* d_cut_off,
-                      const double* d_cut_val, int max_cuts, uint8_t* codes, int64_t Npad, cudaStream_t st) {
+                      const double* d_cut_val, int max_cuts, int route, uint8_t* codes, int64_t Npad, cudaStream_t st) {
     (void)max_cuts;
     if (d == 0 || Npad == 0) return BARTINT_OK;
     const int64_t quads = Npad / 4;
@@ -84,7 +92,8 @@ int launch_bin_points(const double* dX, int64_t ld, int64_t N, int32_t d, const 
     if (bx > cap) bx = cap;
     if (bx < 1) bx = 1;
     dim3 grid((unsigned)bx, (unsigned)d);
-    bin_points_kernel<<<grid, 256, 0, st>>>(dX, ld, N, d_cut_off, d_cut_val, reinterpret_cast<uint32_t*>(codes), quads);
+    auto kern = route == BARTINT_ROUTE_BART ? bin_points_kernel<true> : bin_points_kernel<false>;
+    kern<<<grid, 256, 0, st>>>(dX, ld, N, d_cut_off, d_cut_val, reinterpret_cast<uint32_t*>(codes), quads);
     count_launch();
     BI_CUDA(cudaGetLastError());
     return BARTINT_OK;
@@ -119,6 +128,7 @@ __device__ __forceinline__ double draw_from_measure(int measure, uint32_t w0, ui
     return 0.5 + normcdfinv(plo + (phi - plo) * u);
 }
 
+template <bool INC>
 __global__ void __launch_bounds__(256) generate_points_kernel(int measure, int64_t N, int64_t first_index, uint32_t k0,
                                                               uint32_t k1, const int32_t* __restrict__ cut_off,
                                                               const double* __restrict__ cut_val,
@@ -146,7 +156,7 @@ __global__ void __launch_bounds__(256) generate_points_kernel(int measure, int64
                 philox4x32_10((uint32_t)gi, (uint32_t)(gi >> 32), (uint32_t)j, 0u, k0, k1, r0, r1);
                 const double x = draw_from_measure(measure, r0, r1);
                 if (x_out != nullptr) x_out[(int64_t)j * N + i] = x;
-                word |= bin_one(x, s_cut, nc, c0, inv_step) << (8 * k);
+                word |= bin_one<INC>(x, s_cut, nc, c0, inv_step) << (8 * k);
             }
         }
         codes4[(int64_t)j * quads_per_row + w] = word;
@@ -154,7 +164,7 @@ __global__ void __launch_bounds__(256) generate_points_kernel(int measure, int64
 }
 
 int launch_generate_points(int measure, int64_t N, int64_t first_index, uint64_t seed, int32_t d,
-                           const int32_t* d_cut_off, const double* d_cut_val, uint8_t* codes, int64_t Npad,
+                           const int32_t* d_cut_off, const double* d_cut_val, int route, uint8_t* codes, int64_t Npad,
                            double* x_out, cudaStream_t st) {
     if (d == 0 || Npad == 0) return BARTINT_OK;
     const int64_t quads = Npad / 4;
@@ -163,8 +173,9 @@ int launch_generate_points(int measure, int64_t N, int64_t first_index, uint64_t
     if (bx > cap) bx = cap;
     if (bx < 1) bx = 1;
     dim3 grid((unsigned)bx, (unsigned)d);
-    generate_points_kernel<<<grid, 256, 0, st>>>(measure, N, first_index, (uint32_t)seed, (uint32_t)(seed >> 32), d_cut_off,
-                                                 d_cut_val, reinterpret_cast<uint32_t*>(codes), quads, x_out);
+    auto kern = route == BARTINT_ROUTE_BART ? generate_points_kernel<true> : generate_points_kernel<false>;
+    kern<<<grid, 256, 0, st>>>(measure, N, first_index, (uint32_t)seed, (uint32_t)(seed >> 32), d_cut_off, d_cut_val,
+                               reinterpret_cast<uint32_t*>(codes), quads, x_out);
     count_launch();
     BI_CUDA(cudaGetLastError());
     return BARTINT_OK;

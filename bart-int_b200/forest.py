@@ -50,6 +50,7 @@ class FlatForest:
     y_min: float = -0.5
     y_max: float = 0.5
     meta: dict = field(default_factory=dict)
+    route: int = 0      # 0: dbarts "left iff x <= cut"; 1: BART::wbart "left iff x < cut" (include/bartint.h)
 
     def __post_init__(self):
         self.tree_offset = np.ascontiguousarray(self.tree_offset, np.int64)
@@ -74,7 +75,7 @@ class FlatForest:
         a, b = int(self.tree_offset[lo * self.m]), int(self.tree_offset[hi * self.m])
         return FlatForest(hi - lo, self.m, self.d, self.tree_offset[lo * self.m:hi * self.m + 1] - a,
                           self.var[a:b], self.cut[a:b], self.left[a:b], self.right[a:b], self.mu[a:b],
-                          self.cut_offsets, self.cut_values, self.y_min, self.y_max, dict(self.meta))
+                          self.cut_offsets, self.cut_values, self.y_min, self.y_max, dict(self.meta), self.route)
 
     # ---- dbarts 0.9-8 wire format, for exporter tests and synthetic "models" ----
     def tree_string(self, k: int) -> str:
@@ -91,6 +92,24 @@ class FlatForest:
                 stack.append(int(self.right[a + node]))
                 stack.append(int(self.left[a + node]))
         return "".join(out)
+
+    def to_wbart_text(self) -> str:
+        """The forest as BART::wbart's ``treedraws$trees`` text: "ndpost ntree p", then per tree the node count and one
+        line "nid var cut theta" per node in pre-order (heap ids: root 1, children 2 nid / 2 nid + 1)."""
+        out = [f"{self.S} {self.m} {self.d}"]
+        for k in range(self.n_trees):
+            a, b = int(self.tree_offset[k]), int(self.tree_offset[k + 1])
+            out.append(str(b - a))
+            stack = [(0, 1)]
+            while stack:
+                node, nid = stack.pop()
+                if self.var[a + node] >= 0:
+                    out.append(f"{nid} {int(self.var[a + node])} {int(self.cut[a + node])} 0")
+                    stack.append((int(self.right[a + node]), 2 * nid + 1))
+                    stack.append((int(self.left[a + node]), 2 * nid))
+                else:
+                    out.append(f"{nid} 0 0 {float(self.mu[a + node])!r}")
+        return "\n".join(out) + "\n"
 
     def to_dbarts_state(self, x_train: np.ndarray):
         """(savedTrees [m, S] of str, savedTreeFits [n, m, S]) as dbarts would hold them for this forest:
@@ -199,6 +218,7 @@ class Forest:
          self.table_bits, kind, self.gather_words) = [int(v) for v in info]
         self.table_kernel_ok = bool(tk)                                  # a fast kernel (table or gather) applies
         self.fast_kernel = {0: "none", 1: "table", 2: "gather"}[kind]
+        self.route = int(_lib.load().bartint_forest_route(self._h))
         self.y_min = self.y_max = None
 
     # ---- constructors ----
@@ -206,13 +226,30 @@ class Forest:
     def from_soa(cls, ff: FlatForest) -> "Forest":
         lib = _lib.load()
         h = C.c_void_p()
-        _check(lib.bartint_forest_from_soa(ff.S, ff.m, ff.d, _p(ff.tree_offset, C.c_int64), _p(ff.var, C.c_int32),
-                                           _p(ff.cut, C.c_int32), _p(ff.left, C.c_int32), _p(ff.right, C.c_int32),
-                                           _p(ff.mu, C.c_double), _p(ff.cut_offsets, C.c_int32),
-                                           _p(ff.cut_values, C.c_double), float(ff.y_min), float(ff.y_max),
-                                           C.byref(h)))
+        _check(lib.bartint_forest_from_soa_routed(
+            ff.S, ff.m, ff.d, _p(ff.tree_offset, C.c_int64), _p(ff.var, C.c_int32), _p(ff.cut, C.c_int32),
+            _p(ff.left, C.c_int32), _p(ff.right, C.c_int32), _p(ff.mu, C.c_double), _p(ff.cut_offsets, C.c_int32),
+            _p(ff.cut_values, C.c_double), float(ff.y_min), float(ff.y_max), int(getattr(ff, "route", 0)), C.byref(h)))
         f = cls(h.value)
         f.y_min, f.y_max = float(ff.y_min), float(ff.y_max)
+        return f
+
+    @classmethod
+    def from_wbart(cls, trees_text, cut_lists, offset: float = 0.0) -> "Forest":
+        """Exporter for BART::wbart / pbart fits: ``fit$treedraws$trees`` (text), ``fit$treedraws$cutpoints`` and
+        ``fit$offset``.  Routing follows tree::bn (left iff x < cut); predictions are offset + sum of leaf values."""
+        lib = _lib.load()
+        text = trees_text.encode() if isinstance(trees_text, str) else bytes(trees_text)
+        d = len(cut_lists)
+        cut_offsets = np.zeros(d + 1, np.int32)
+        cut_offsets[1:] = np.cumsum([len(c) for c in cut_lists])
+        cut_values = (np.concatenate([np.asarray(c, np.float64) for c in cut_lists]) if d else np.zeros(0))
+        cut_values = np.ascontiguousarray(cut_values)
+        h = C.c_void_p()
+        _check(lib.bartint_forest_from_wbart(text, len(text), d, _p(cut_offsets, C.c_int32), _p(cut_values, C.c_double),
+                                             float(offset), C.byref(h)))
+        f = cls(h.value)
+        f.y_min, f.y_max = float(offset) - 0.5, float(offset) + 0.5
         return f
 
     @classmethod

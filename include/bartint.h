@@ -84,6 +84,29 @@ int bartint_forest_from_soa(int32_t S, int32_t m, int32_t d, const int64_t* tree
                             const int32_t* cut_offsets, const double* cut_values,
                             double y_min, double y_max, bartint_forest** out);
 
+/* Routing rule of a split node (x = the point's value of the split variable, c = the cut point):
+ *   DBARTS  left iff x <= c, NaN -> left    (dbarts; what the reference's predict() does)
+ *   BART    left iff x <  c, NaN -> right   (BART::wbart / pbart, tree::bn)
+ * The rule only changes how points are binned (code = #{k : x > cut_k} vs #{k : x >= cut_k}); the evaluation
+ * kernels work on codes and are shared. */
+#define BARTINT_ROUTE_DBARTS 0
+#define BARTINT_ROUTE_BART   1
+int bartint_forest_from_soa_routed(int32_t S, int32_t m, int32_t d, const int64_t* tree_node_offset,
+                                   const int32_t* split_var, const int32_t* split_cut_idx, const int32_t* left,
+                                   const int32_t* right, const double* leaf_mu, const int32_t* cut_offsets,
+                                   const double* cut_values, double y_min, double y_max, int32_t route,
+                                   bartint_forest** out);
+int bartint_forest_route(const bartint_forest* f);
+
+/* Exporter for BART::wbart / pbart fits (the reference's README.md:202 invites swapping
+ * the BART package).  trees_text = fit$treedraws$trees, a NUL-terminated string: "ndpost ntree p\n", then draw by
+ * draw and tree by tree a line with the node count followed by one line "nid var cut theta" per node (heap node ids:
+ * root 1, children 2 nid and 2 nid + 1; var and cut 0-based; theta = leaf value).  cut_values / cut_offsets flatten
+ * fit$treedraws$cutpoints.  offset = fit$offset (wbart: mean(y.train)): predict.wbart = offset + sum_t theta, which
+ * the library expresses as y_min = offset - 0.5, y_max = offset + 0.5 of the dbarts rescale.  text_len <= 0: strlen. */
+int bartint_forest_from_wbart(const char* trees_text, int64_t text_len, int32_t d, const int32_t* cut_offsets,
+                              const double* cut_values, double offset, bartint_forest** out);
+
 /* info[0..11] = S, m, d, n_nodes, n_leaves, max_depth, max_internal_nodes_per_tree,
  *               fast_kernel_ok (0/1), n_groups, table_bits, fast kernel kind (0 none, 1 table, 2 gather),
  *               gather code words per point */

@@ -32,7 +32,10 @@ typedef struct {
     const int32_t* cut_offsets;
     const double* cut_values;
     double y_min, y_max;
+    int32_t route;   /* 0: dbarts, right iff x > cut (NaN -> left); 1: BART::wbart tree::bn, left iff x < cut (NaN -> right) */
 } forest_t;
+
+static inline int go_right(int32_t route, double x, double c) { return route ? !(x < c) : (x > c); }
 
 int oracle_max_threads(void) {
 #ifdef _OPENMP
@@ -55,7 +58,7 @@ static void tree_predict_add(const forest_t* f, int64_t k, const double* X, int6
         int32_t node = 0;
         while (var[node] >= 0) {
             const double c = f->cut_values[f->cut_offsets[var[node]] + cut[node]];
-            node = (X[(int64_t)var[node] * N + i] > c) ? right[node] : left[node];   /* NaN -> left */
+            node = go_right(f->route, X[(int64_t)var[node] * N + i], c) ? right[node] : left[node];
         }
         acc[i] += mu[node];
     }
@@ -66,9 +69,9 @@ static void tree_predict_add(const forest_t* f, int64_t k, const double* X, int6
 void oracle_predict_reduce(int32_t S, int32_t m, int32_t d, const int64_t* tree_offset, const int32_t* var,
                            const int32_t* cut, const int32_t* left, const int32_t* right, const double* mu,
                            const int32_t* cut_offsets, const double* cut_values, double y_min, double y_max,
-                           const double* X, int64_t N, int32_t nthreads, double* draw_mean, double* point_mean,
-                           double* point_var, double* full) {
-    forest_t f = {S, m, d, tree_offset, var, cut, left, right, mu, cut_offsets, cut_values, y_min, y_max};
+                           int32_t route, const double* X, int64_t N, int32_t nthreads, double* draw_mean,
+                           double* point_mean, double* point_var, double* full) {
+    forest_t f = {S, m, d, tree_offset, var, cut, left, right, mu, cut_offsets, cut_values, y_min, y_max, route};
     const int want_pt = point_mean != NULL || point_var != NULL;
     if (nthreads < 1) nthreads = 1;
     /* per-thread Welford state over the draws it owns, merged afterwards in thread order */
@@ -128,7 +131,7 @@ void oracle_predict_reduce(int32_t S, int32_t m, int32_t d, const int64_t* tree_
 
 void oracle_leaf_ordinals(int32_t S, int32_t m, const int64_t* tree_offset, const int32_t* var, const int32_t* cut,
                           const int32_t* left, const int32_t* right, const int32_t* cut_offsets,
-                          const double* cut_values, const double* X, int64_t N, int32_t* out) {
+                          const double* cut_values, int32_t route, const double* X, int64_t N, int32_t* out) {
 #pragma omp parallel for schedule(static)
     for (int64_t k = 0; k < (int64_t)S * m; ++k) {
         const int64_t a = tree_offset[k];
@@ -146,7 +149,7 @@ void oracle_leaf_ordinals(int32_t S, int32_t m, const int64_t* tree_offset, cons
             int32_t node = 0;
             while (var[a + node] >= 0) {
                 const double c = cut_values[cut_offsets[var[a + node]] + cut[a + node]];
-                node = (X[(int64_t)var[a + node] * N + i] > c) ? right[a + node] : left[a + node];
+                node = go_right(route, X[(int64_t)var[a + node] * N + i], c) ? right[a + node] : left[a + node];
             }
             out[k * N + i] = ordinal[node];
         }

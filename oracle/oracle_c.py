@@ -50,7 +50,8 @@ def predict_reduce(forest, X, nthreads=1, want=("draw_mean", "point_mean", "poin
         out["point_var"] = np.zeros(N)
     if "full_pred" in want:
         out["full_pred"] = np.zeros((f.S, N), order="F")
-    load().oracle_predict_reduce(*_forest_args(f), C.c_double(f.y_min), C.c_double(f.y_max), _p(X), C.c_int64(N),
+    load().oracle_predict_reduce(*_forest_args(f), C.c_double(f.y_min), C.c_double(f.y_max), C.c_int32(f.route), _p(X),
+                                 C.c_int64(N),
                                  C.c_int32(nthreads), _p(out.get("draw_mean")), _p(out.get("point_mean")),
                                  _p(out.get("point_var")), _p(out.get("full_pred")))
     return out
@@ -61,7 +62,8 @@ def leaf_ordinals(forest, X):
     X = np.asfortranarray(np.asarray(X, np.float64))
     out = np.zeros((f.S * f.m, X.shape[0]), np.int32)
     load().oracle_leaf_ordinals(C.c_int32(f.S), C.c_int32(f.m), _p(f.tree_offset), _p(f.var), _p(f.cut), _p(f.left),
-                                _p(f.right), _p(f.cut_offsets), _p(f.cut_values), _p(X), C.c_int64(X.shape[0]), _p(out))
+                                _p(f.right), _p(f.cut_offsets), _p(f.cut_values), C.c_int32(f.route), _p(X), C.c_int64(X.shape[0]),
+                                _p(out))
     return out
 
 

@@ -34,6 +34,7 @@ Forest container used throughout ("flat forest"): any object/dict exposing
     mu           float64[nodes]  leaf value in dbarts' scaled units (0 for internal nodes)
     cut_offsets  int32[d+1], cut_values float64[cut_offsets[d]]   ascending per variable
     y_min, y_max float           range of the training response
+    route        int (optional)  0 = dbarts rule "left iff x <= cut" (default); 1 = BART::wbart rule "left iff x < cut"
 """
 from __future__ import annotations
 
@@ -43,6 +44,8 @@ from types import SimpleNamespace
 import numpy as np
 
 LD = np.longdouble  # 80-bit on x86-64: what R's LDOUBLE is on the reference's platforms
+ROUTE_DBARTS = 0    # left iff x <= cut; NaN compares false -> left  [dbarts-mem]
+ROUTE_BART = 1      # left iff x <  cut; NaN compares false -> right [BART-mem: tree::bn, "if(x[v] < xi[v][c]) left"]
 
 
 def _get(forest, name):
@@ -59,6 +62,10 @@ def as_ns(forest) -> SimpleNamespace:
     ns.mu = np.ascontiguousarray(_get(forest, "mu"), dtype=np.float64)
     ns.cut_values = np.ascontiguousarray(_get(forest, "cut_values"), dtype=np.float64)
     ns.y_min, ns.y_max = float(_get(forest, "y_min")), float(_get(forest, "y_max"))
+    try:
+        ns.route = int(_get(forest, "route"))
+    except (KeyError, AttributeError):
+        ns.route = ROUTE_DBARTS
     return ns
 
 
@@ -176,10 +183,11 @@ def forest_from_dbarts(tree_strings, tree_fits, x_train, cut_lists, y_min, y_max
 # a1  predict(model, X): dbarts C++ predict [dbarts-mem], call sites BARTInt.R:312,380; bartMean.R:47,74
 # --------------------------------------------------------------------------------------
 
-def bin_points(X, cut_offsets, cut_values):
+def bin_points(X, cut_offsets, cut_values, route=ROUTE_DBARTS):
     """dbarts' integer cut map of a test matrix [dbarts-mem]:  b = #{k : x > cut[j][k]}.
 
     Right iff b > splitIndex0  <=>  x > cut[j][splitIndex0] for ascending cuts.  NaN -> 0.
+    route = ROUTE_BART: b = #{k : x >= cut[j][k]} (right iff x >= cut), NaN -> number of cuts (always right).
     """
     X = np.asarray(X, np.float64)
     N, d = X.shape
@@ -187,8 +195,12 @@ def bin_points(X, cut_offsets, cut_values):
     for j in range(d):
         cuts = cut_values[cut_offsets[j]:cut_offsets[j + 1]]
         col = X[:, j]
-        b = np.searchsorted(cuts, col, side="left")  # number of cuts strictly below x
-        codes[:, j] = np.where(np.isnan(col), 0, b)
+        if route == ROUTE_BART:
+            b = np.searchsorted(cuts, col, side="right")  # number of cuts <= x
+            codes[:, j] = np.where(np.isnan(col), len(cuts), b)
+        else:
+            b = np.searchsorted(cuts, col, side="left")  # number of cuts strictly below x
+            codes[:, j] = np.where(np.isnan(col), 0, b)
     return codes
 
 
@@ -213,7 +225,7 @@ def leaf_nodes(forest, X):
                 break
             vi = np.where(internal, v, 0)
             cv = f.cut_values[f.cut_offsets[vi] + np.where(internal, cut[node], 0)]
-            go_right = X[rows, vi] > cv
+            go_right = ~(X[rows, vi] < cv) if f.route == ROUTE_BART else X[rows, vi] > cv
             node = np.where(internal, np.where(go_right, right[node], left[node]), node)
         out[k] = node
     return out
@@ -465,6 +477,90 @@ def leaf_probabilities(var, cut, left, right, cut_lists, d, measure="uniform"):
             mu = np.zeros(len(var)); mu[k] = 1.0
             probs.append(single_tree_sum(var, cut, left, right, mu, cut_lists, d, measure))
     return np.array(probs)
+
+
+# --------------------------------------------------------------------------------------
+# BART::wbart / pbart tree draws (reference README.md:202 invites swapping BART packages)
+# --------------------------------------------------------------------------------------
+
+def forest_from_wbart(trees_text, cut_lists, offset=0.0):
+    """Flat forest from BART::wbart's ``fit$treedraws`` [BART-mem].
+
+    ``trees_text`` = treedraws$trees: first line "ndpost ntree p"; then, draw by draw and tree by tree, a line with
+    the node count followed by one line "nid var cut theta" per node (tree.cpp operator<<).  nid is the heap index
+    (root 1, children 2*nid and 2*nid+1); a node is internal iff its left child is listed; var and cut are 0-based,
+    cut indexes ``treedraws$cutpoints[[var+1]]``; theta is the leaf value (ignored on internal nodes).
+    Routing (tree::bn): left iff x[var] < cutpoints[var][cut].  predict.wbart = offset + sum_t theta with
+    offset = fit$offset = mean(y.train); expressed with the dbarts rescale (ymax - ymin) * (sum + 0.5) + ymin by
+    setting ymin = offset - 0.5, ymax = offset + 0.5.
+    """
+    tok = trees_text.split()
+    S, m, d = int(tok[0]), int(tok[1]), int(tok[2])
+    if d != len(cut_lists):
+        raise ValueError("treedraws header says p = %d but %d cut-point lists were given" % (d, len(cut_lists)))
+    pos = 3
+    tree_offset = [0]
+    var, cut, left, right, mu = [], [], [], [], []
+    for _ in range(S * m):
+        nn = int(tok[pos]); pos += 1
+        nodes = {}
+        for _k in range(nn):
+            nid, v, c, th = int(tok[pos]), int(tok[pos + 1]), int(tok[pos + 2]), float(tok[pos + 3])
+            pos += 4
+            nodes[nid] = (v, c, th)
+        if 1 not in nodes:
+            raise ValueError("tree without a root node")
+        base = len(var)
+        stack = [(1, -1, False)]          # (nid, parent slot, is right child): pre-order, left child first
+        while stack:
+            nid, parent, is_right = stack.pop()
+            slot = len(var) - base
+            if parent >= 0:
+                (right if is_right else left)[base + parent] = slot
+            v, c, th = nodes[nid]
+            if 2 * nid in nodes:
+                if 2 * nid + 1 not in nodes:
+                    raise ValueError("node %d has a left child but no right child" % nid)
+                if not (0 <= v < d) or not (0 <= c < len(cut_lists[v])):
+                    raise ValueError("split (%d, %d) outside the cut-point lists" % (v, c))
+                var.append(v); cut.append(c); left.append(-1); right.append(-1); mu.append(0.0)
+                stack.append((2 * nid + 1, slot, True))
+                stack.append((2 * nid, slot, False))
+            else:
+                var.append(-1); cut.append(0); left.append(-1); right.append(-1); mu.append(th)
+        if len(var) - base != nn:
+            raise ValueError("unreachable nodes in a tree")
+        tree_offset.append(len(var))
+    if pos != len(tok):
+        raise ValueError("trailing tokens after the last tree")
+    cut_offsets = np.zeros(d + 1, np.int32)
+    for j in range(d):
+        cut_offsets[j + 1] = cut_offsets[j] + len(cut_lists[j])
+    cut_values = np.concatenate([np.asarray(c, np.float64) for c in cut_lists]) if d else np.zeros(0)
+    return SimpleNamespace(S=S, m=m, d=d, tree_offset=np.array(tree_offset, np.int64), var=np.array(var, np.int32),
+                           cut=np.array(cut, np.int32), left=np.array(left, np.int32), right=np.array(right, np.int32),
+                           mu=np.array(mu, np.float64), cut_offsets=cut_offsets, cut_values=cut_values,
+                           y_min=float(offset) - 0.5, y_max=float(offset) + 0.5, route=ROUTE_BART)
+
+
+def wbart_trees_text(forest) -> str:
+    """Inverse of forest_from_wbart: writes a flat forest in the treedraws$trees text format (heap node ids, nodes in
+    pre-order as tree::getnodes lists them; theta of internal nodes written as 0)."""
+    f = as_ns(forest)
+    out = ["%d %d %d" % (f.S, f.m, f.d)]
+    for k in range(f.S * f.m):
+        a, b = int(f.tree_offset[k]), int(f.tree_offset[k + 1])
+        out.append(str(b - a))
+        stack = [(0, 1)]
+        while stack:
+            node, nid = stack.pop()
+            if f.var[a + node] >= 0:
+                out.append("%d %d %d 0" % (nid, f.var[a + node], f.cut[a + node]))
+                stack.append((int(f.right[a + node]), 2 * nid + 1))
+                stack.append((int(f.left[a + node]), 2 * nid))
+            else:
+                out.append("%d 0 0 %r" % (nid, float(f.mu[a + node])))
+    return "\n".join(out) + "\n"
 
 
 # --------------------------------------------------------------------------------------
