@@ -10,7 +10,8 @@ Layout
   synth.py         synthetic posteriors and Genz-shaped data for tests and the benchmark
   R/               the .Call shim sources a BART-Int maintainer adds (not buildable here: no R)
 """
-from .forest import FlatForest, Forest, Points, StagedMatrix, WireStrings, BartIntError  # noqa: F401
+from .forest import (FlatForest, Forest, Points, StagedMatrix, WireStrings, BartIntError,  # noqa: F401
+                     design_step_dbarts)
 from . import api, synth  # noqa: F401
 
-__all__ = ["FlatForest", "Forest", "Points", "StagedMatrix", "WireStrings", "BartIntError", "api", "synth"]
+__all__ = ["FlatForest", "Forest", "Points", "StagedMatrix", "WireStrings", "BartIntError", "design_step_dbarts", "api", "synth"]

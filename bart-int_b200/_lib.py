@@ -30,6 +30,11 @@ SIGNATURES = {
     "bartint_forest_from_soa": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, c_int64_p, c_int32_p, c_int32_p, c_int32_p,
                                           c_int32_p, c_double_p, c_int32_p, c_double_p, C.c_double, C.c_double,
                                           handle_p]),
+    "bartint_set_host_threads": (C.c_int, [C.c_int]),
+    "bartint_design_step_dbarts098": (C.c_int, [C.c_void_p, c_double_p, c_double_p, C.c_int64, C.c_int32, c_int32_p,
+                                                c_double_p, C.c_double, C.c_double, C.c_int32, C.c_int32, C.c_void_p,
+                                                C.c_void_p, c_double_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
+                                                c_double_p, c_double_p, c_double_p, c_double_p, c_double_p]),
     "bartint_forest_from_soa_routed": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, c_int64_p, c_int32_p, c_int32_p,
                                                  c_int32_p, c_int32_p, c_double_p, c_int32_p, c_double_p, C.c_double,
                                                  C.c_double, C.c_int32, handle_p]),

@@ -1,8 +1,14 @@
 // C ABI of libbartint_cuda.so (see include/bartint.h for what each entry point replaces in the reference).
 #include <cmath>
 #include <cstring>
+#include <ctime>
+#include <cstdio>
 #include <limits>
 #include <new>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 #include "common.cuh"
 
@@ -108,6 +114,16 @@ int bartint_device_count(int* n_out) {
     return BARTINT_OK;
 }
 
+int bartint_set_host_threads(int n) {
+#ifdef _OPENMP
+    omp_set_num_threads(n > 0 ? n : omp_get_num_procs());
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
+}
+
 int bartint_set_device(int device) {
     int rc = check_device();
     if (rc) return rc;
@@ -115,9 +131,22 @@ int bartint_set_device(int device) {
     return BARTINT_OK;
 }
 
+static int forest_from_dbarts_impl(const char* const* tree_strings, const double* tree_fits, const double* x_train,
+                                   int64_t n, int32_t d, const int32_t* cut_offsets, const double* cut_values,
+                                   double y_min, double y_max, int32_t m, int32_t S, bool defer_upload_sync,
+                                   bartint_forest** out);
+
 int bartint_forest_from_dbarts098(const char* const* tree_strings, const double* tree_fits, const double* x_train,
                                   int64_t n, int32_t d, const int32_t* cut_offsets, const double* cut_values,
                                   double y_min, double y_max, int32_t m, int32_t S, bartint_forest** out) {
+    return forest_from_dbarts_impl(tree_strings, tree_fits, x_train, n, d, cut_offsets, cut_values, y_min, y_max, m, S,
+                                   false, out);
+}
+
+static int forest_from_dbarts_impl(const char* const* tree_strings, const double* tree_fits, const double* x_train,
+                                   int64_t n, int32_t d, const int32_t* cut_offsets, const double* cut_values,
+                                   double y_min, double y_max, int32_t m, int32_t S, bool defer_upload_sync,
+                                   bartint_forest** out) {
     BI_REQUIRE(out != nullptr, BARTINT_ERR_ARG, "out is NULL");
     *out = nullptr;
     BI_REQUIRE(S >= 0 && m >= 0 && n >= 0, BARTINT_ERR_ARG, "S, m, n must be >= 0");
@@ -129,6 +158,7 @@ int bartint_forest_from_dbarts098(const char* const* tree_strings, const double*
     bartint_forest* f = new (std::nothrow) bartint_forest();
     BI_REQUIRE(f != nullptr, BARTINT_ERR_NOMEM, "out of host memory");
     f->S = S; f->m = m; f->d = d; f->y_min = y_min; f->y_max = y_max;
+    f->defer_upload_sync = defer_upload_sync;
     f->cut_off.assign(cut_offsets, cut_offsets + d + 1);
     f->cut_val.assign(cut_values, cut_values + cut_offsets[d]);
     rc = parse_dbarts_forest(tree_strings, tree_fits, x_train, n, d, cut_offsets, cut_values, m, S, f);
@@ -785,6 +815,153 @@ int bartint_last_eval_profile(const bartint_forest* f, int32_t with_moments, flo
             BI_CUDA(cudaEventElapsedTime(kernel_ms, f->ev0[slot], f->ev1[slot]));
         }
     }
+    return BARTINT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// One sequential-design step, fused and pipelined over chunks of draws ("the step on either side"):
+// while the GPU evaluates the draws of chunk g, the host exports chunk g+1 (string parser, leaf mu, group planner,
+// H2D, table build).  Everything the device does is enqueued on one private non-blocking stream; the exporter keeps
+// using the default stream, which does not synchronise with it.
+// ------------------------------------------------------------------------------------------------------------
+int bartint_design_step_dbarts098(const char* const* tree_strings, const double* tree_fits, const double* x_train,
+                                  int64_t n, int32_t d, const int32_t* cut_offsets, const double* cut_values,
+                                  double y_min, double y_max, int32_t m, int32_t S, const bartint_staged* mc,
+                                  const bartint_staged* cand, const double* weights, int64_t weights_len,
+                                  int32_t measure, int32_t n_draws_integral, int32_t n_chunks, double* integrals_scaled,
+                                  double* integral_mean_sd, double* cand_var, double* draw_mean, double* draw_mean_var) {
+    BI_REQUIRE(S >= 1 && m >= 1, BARTINT_ERR_ARG, "S and m must be >= 1");
+    BI_REQUIRE(tree_strings != nullptr && tree_fits != nullptr, BARTINT_ERR_ARG, "NULL dbarts state");
+    BI_REQUIRE(measure >= 0 && measure <= 3, BARTINT_ERR_ARG, "unknown measure %d", measure);
+    BI_REQUIRE(mc == nullptr || mc->d == d, BARTINT_ERR_ARG, "MC point matrix has %d columns, the model %d", mc ? mc->d : 0, d);
+    BI_REQUIRE(cand == nullptr || cand->d == d, BARTINT_ERR_ARG, "candidate matrix has %d columns, the model %d", cand ? cand->d : 0, d);
+    BI_REQUIRE(mc == nullptr || cand == nullptr || mc->device == cand->device, BARTINT_ERR_ARG, "matrices staged on different devices");
+    const int64_t C = cand ? cand->N : 0, N = mc ? mc->N : 0;
+    BI_REQUIRE(weights == nullptr || weights_len == 1 || weights_len == C, BARTINT_ERR_ARG, "weights must have length 1 or C");
+    BI_REQUIRE(cand_var == nullptr || cand != nullptr, BARTINT_ERR_ARG, "cand_var wanted but no candidate matrix");
+    BI_REQUIRE((draw_mean == nullptr && draw_mean_var == nullptr) || mc != nullptr, BARTINT_ERR_ARG, "draw means wanted but no MC matrix");
+    int rc = check_device();
+    if (rc) return rc;
+    const int device = mc ? mc->device : cand ? cand->device : -1;
+    int cur = 0;
+    BI_CUDA(cudaGetDevice(&cur));
+    DeviceGuard guard(device >= 0 ? device : cur);
+
+    int G = n_chunks > 0 ? n_chunks : (S >= 256 ? 4 : 1);
+    G = std::min(G, S);
+    const int n_int = (n_draws_integral <= 0 || n_draws_integral > S) ? S : n_draws_integral;
+    const bool want_int = integrals_scaled != nullptr || integral_mean_sd != nullptr;
+    const bool want_cand = cand_var != nullptr && C > 0;
+    const bool want_mc = (draw_mean != nullptr || draw_mean_var != nullptr) && N > 0;
+
+    cudaStream_t st = nullptr;
+    cudaEvent_t built = nullptr;
+    std::vector<bartint_forest*> forests;
+    bartint_points *pm = nullptr, *pc = nullptr;
+    double* d_buf = nullptr;
+    int32_t* d_counts = nullptr;
+    auto cleanup = [&]() {
+        if (st) cudaStreamSynchronize(st);
+        cudaStreamSynchronize(nullptr);
+        if (built) cudaEventDestroy(built);
+        if (pm) bartint_points_destroy(pm);
+        if (pc) bartint_points_destroy(pc);
+        if (d_buf) cudaFreeAsync(d_buf, nullptr);
+        if (d_counts) cudaFreeAsync(d_counts, nullptr);
+        for (bartint_forest* f : forests) bartint_forest_destroy(f);
+        if (st) cudaStreamDestroy(st);
+        (void)cudaGetLastError();
+    };
+#define DS_CUDA(call)                                                                       \
+    do {                                                                                    \
+        cudaError_t _e = (call);                                                            \
+        if (_e != cudaSuccess) { cleanup(); return cuda_fail(_e, #call, __FILE__, __LINE__); } \
+    } while (0)
+#define DS_RC(call)                                    \
+    do {                                               \
+        rc = (call);                                   \
+        if (rc != BARTINT_OK) { cleanup(); return rc; } \
+    } while (0)
+    DS_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    DS_CUDA(cudaEventCreateWithFlags(&built, cudaEventDisableTiming));
+    // one device buffer: integrals S | rescaled S | mean,sd 2 | draw sums S | draw means S | mean,var 2 |
+    //                    candidate means G*C | candidate M2 G*C | candidate var C | weights max(len,1)
+    const size_t nS = (size_t)S, nC = (size_t)std::max<int64_t>(C, 1);
+    const size_t total = 4 * nS + 4 + 2 * (size_t)G * nC + nC + (size_t)std::max<int64_t>(weights_len, 1);
+    DS_CUDA(cudaMallocAsync((void**)&d_buf, sizeof(double) * total, st));
+    double* d_int = d_buf;
+    double* d_int_res = d_int + nS;
+    double* d_int_ms = d_int_res + nS;
+    double* d_sum = d_int_ms + 2;
+    double* d_dmean = d_sum + nS;
+    double* d_mv = d_dmean + nS;
+    double* d_cmean = d_mv + 2;
+    double* d_cm2 = d_cmean + (size_t)G * nC;
+    double* d_cvar = d_cm2 + (size_t)G * nC;
+    double* d_w = d_cvar + nC;
+    if (weights != nullptr && want_cand)
+        DS_CUDA(cudaMemcpyAsync(d_w, weights, sizeof(double) * (size_t)weights_len, cudaMemcpyHostToDevice, st));
+    std::vector<int32_t> counts((size_t)G);
+
+    static const bool timing = [] { const char* e = std::getenv("BARTINT_TIMING"); return e && e[0] == '1'; }();
+    std::vector<double> t_cpu;
+    auto now_ms = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return 1e3 * (double)ts.tv_sec + 1e-6 * (double)ts.tv_nsec; };
+    const double t_begin = now_ms();
+    for (int g = 0; g < G; ++g) {
+        const int32_t s0 = (int32_t)((int64_t)S * g / G), s1 = (int32_t)((int64_t)S * (g + 1) / G);
+        counts[(size_t)g] = s1 - s0;
+        bartint_forest* f = nullptr;
+        if (timing) t_cpu.push_back(now_ms() - t_begin);
+        DS_RC(forest_from_dbarts_impl(tree_strings + (size_t)s0 * (size_t)m, tree_fits + (size_t)s0 * (size_t)m * (size_t)n,
+                                      x_train, n, d, cut_offsets, cut_values, y_min, y_max, m, s1 - s0, true, &f));
+        forests.push_back(f);
+        // the sub-forest's copies and table build are still in flight on the default stream: order `st` after them
+        DS_CUDA(cudaEventRecord(built, nullptr));
+        DS_CUDA(cudaStreamWaitEvent(st, built, 0));
+        if (g == 0) {            // the cut points are the same for every chunk: bin once against the first sub-forest
+            if (want_mc) DS_RC(bartint_staged_points(f, mc, st, &pm));
+            if (want_cand) DS_RC(bartint_staged_points(f, cand, st, &pc));
+        }
+        if (want_int && s0 < n_int)
+            DS_RC(launch_exact_integrals(f, measure, nullptr, nullptr, std::min(s1, n_int) - s0, d_int + s0, st));
+        if (want_cand)
+            DS_RC(eval_core(f, pc, 0u, 0, s1 - s0, nullptr, d_cmean + (size_t)g * nC, d_cm2 + (size_t)g * nC, nullptr, nullptr,
+                            1.0, 0.0, 1, st));
+        if (want_mc)
+            DS_RC(eval_core(f, pm, 0u, 0, s1 - s0, d_sum + s0, nullptr, nullptr, nullptr, nullptr, 1.0, 0.0, 1, st));
+        if (timing) t_cpu.push_back(now_ms() - t_begin);
+    }
+    const double scale = y_max - y_min;
+    if (want_int) DS_RC(launch_finalize_integrals(d_int, n_int, y_min, y_max, d_int_res, d_int_ms, st));
+    if (want_cand) {
+        DS_CUDA(cudaMallocAsync((void**)&d_counts, sizeof(int32_t) * (size_t)G, st));
+        DS_CUDA(cudaMemcpyAsync(d_counts, counts.data(), sizeof(int32_t) * (size_t)G, cudaMemcpyHostToDevice, st));
+        DS_RC(launch_merge_shards(d_cmean, d_cm2, G, d_counts, C, scale, y_min, 0, weights ? d_w : nullptr, weights_len,
+                                  nullptr, d_cvar, st));
+    }
+    if (want_mc) {
+        DS_RC(launch_finalize_draws(d_sum, S, N, scale, y_min, 0, d_dmean, st));
+        DS_RC(launch_draw_summary(d_dmean, S, d_mv, st));
+    }
+    if (integrals_scaled) DS_CUDA(cudaMemcpyAsync(integrals_scaled, d_int, sizeof(double) * (size_t)n_int, cudaMemcpyDeviceToHost, st));
+    if (integral_mean_sd) DS_CUDA(cudaMemcpyAsync(integral_mean_sd, d_int_ms, sizeof(double) * 2, cudaMemcpyDeviceToHost, st));
+    if (want_cand) DS_CUDA(cudaMemcpyAsync(cand_var, d_cvar, sizeof(double) * (size_t)C, cudaMemcpyDeviceToHost, st));
+    if (want_mc && draw_mean) DS_CUDA(cudaMemcpyAsync(draw_mean, d_dmean, sizeof(double) * nS, cudaMemcpyDeviceToHost, st));
+    if (want_mc && draw_mean_var) DS_CUDA(cudaMemcpyAsync(draw_mean_var, d_mv, sizeof(double) * 2, cudaMemcpyDeviceToHost, st));
+    DS_CUDA(cudaStreamSynchronize(st));
+    if (timing) {
+        fprintf(stderr, "[bartint] design step: %d chunks, total %.3f ms\n", G, now_ms() - t_begin);
+        for (int g = 0; g < G; ++g) {
+            float k_ms = 0.f, gap = 0.f;
+            if (want_mc) cudaEventElapsedTime(&k_ms, forests[(size_t)g]->ev0[0], forests[(size_t)g]->ev1[0]);
+            if (want_mc && g > 0) cudaEventElapsedTime(&gap, forests[(size_t)g - 1]->ev1[0], forests[(size_t)g]->ev0[0]);
+            fprintf(stderr, "[bartint]   chunk %d: host export %.3f -> %.3f ms, enqueue done %.3f ms; MC kernel %.3f ms, GPU gap before it %.3f ms\n",
+                    g, t_cpu[(size_t)2 * g], t_cpu[(size_t)2 * g + 1], t_cpu[(size_t)2 * g + 1], k_ms, gap);
+        }
+    }
+    cleanup();
+#undef DS_CUDA
+#undef DS_RC
     return BARTINT_OK;
 }
 

@@ -104,6 +104,7 @@ struct bartint_forest {
     std::vector<int32_t> cut_off;
     std::vector<double> cut_val;
     // table path
+    bool defer_upload_sync = false;    // forest_upload leaves its default-stream work in flight (pipelined design step)
     bool table_ok = false;             // a fast (table or gather) kernel applies
     bool gather = false;               // group records are in the gather format (else table format)
     int g_regs = 0;                    // gather: code words per point

@@ -826,7 +826,10 @@ int forest_upload(bartint_forest* f) {
     cudaFreeAsync(d_desc, nullptr);
     cudaFreeAsync(d_hdr, nullptr);
     cudaFreeAsync(d_split, nullptr);
-    cudaError_t e = cudaStreamSynchronize(nullptr);   // host vectors (pageable) must outlive the copies; surface build errors here
+    // Surface copy / build errors here.  (Not needed for the host vectors: a cudaMemcpyAsync from pageable memory
+    // returns once the source has been staged.)  The pipelined design step defers this wait: it orders its own
+    // stream after the default stream with an event and lets the host run ahead to the next chunk of draws.
+    cudaError_t e = f->defer_upload_sync ? cudaSuccess : cudaStreamSynchronize(nullptr);
     pt.lap("upload: H2D groups + build tables");
     if (rc) return rc;
     BI_CUDA(e);

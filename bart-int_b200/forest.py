@@ -443,3 +443,48 @@ class Forest:
             self.close()
         except Exception:
             pass
+
+
+def design_step_dbarts(tree_strings, tree_fits, x_train, cut_lists, y_min, y_max, mc=None, candidates=None,
+                       weights=None, measure="uniform", n_draws_integral=None, n_chunks=0,
+                       want=("integrals", "integral_mean_sd", "cand_var", "draw_mean", "draw_mean_var")) -> dict:
+    """One sequential-design step in one ABI call (bartint_design_step_dbarts098): exact integrals + their mean/sd
+    (BARTInt.R:259-262), per-candidate variance (BARTInt.R:312-314) and per-draw means over the MC / population points
+    (bartMean.R:74-82), with the exporter pipelined against the evaluation kernels over chunks of draws.
+
+    mc / candidates: StagedMatrix (start their host->device copies before calling) or None.
+    """
+    lib = _lib.load()
+    wire = tree_strings if isinstance(tree_strings, WireStrings) else WireStrings(tree_strings)
+    m, S = wire.m, wire.S
+    x_train = np.asarray(x_train, np.float64)
+    n, d = x_train.shape
+    fits = np.asarray(tree_fits, np.float64).reshape(n, m, S)
+    if not fits.flags["F_CONTIGUOUS"]:
+        fits = np.asfortranarray(fits)
+    xt = np.asfortranarray(x_train)
+    cut_offsets = np.zeros(d + 1, np.int32)
+    cut_offsets[1:] = np.cumsum([len(c) for c in cut_lists])
+    cut_values = np.ascontiguousarray(np.concatenate([np.asarray(c, np.float64) for c in cut_lists]) if d else np.zeros(0))
+    n_int = S if not n_draws_integral else min(int(n_draws_integral), S)
+    C_ = candidates.N if candidates is not None else 0
+    out = {}
+    if "integrals" in want:
+        out["integrals"] = np.zeros(n_int)
+    if "integral_mean_sd" in want:
+        out["integral_mean_sd"] = np.zeros(2)
+    if "cand_var" in want and candidates is not None:
+        out["cand_var"] = np.zeros(C_)
+    if "draw_mean" in want and mc is not None:
+        out["draw_mean"] = np.zeros(S)
+    if "draw_mean_var" in want and mc is not None:
+        out["draw_mean_var"] = np.zeros(2)
+    w = None if weights is None else np.ascontiguousarray(np.atleast_1d(np.asarray(weights, np.float64)))
+    _check(lib.bartint_design_step_dbarts098(
+        wire.array, _p(fits, C.c_double), _p(xt, C.c_double), n, d, _p(cut_offsets, C.c_int32), _p(cut_values, C.c_double),
+        float(y_min), float(y_max), m, S, mc._h if mc is not None else None,
+        candidates._h if candidates is not None else None, _p(w, C.c_double) if w is not None else None,
+        0 if w is None else len(w), _lib.MEASURES[measure], 0 if not n_draws_integral else int(n_draws_integral),
+        int(n_chunks), *(_p(out[k], C.c_double) if k in out else None
+                         for k in ("integrals", "integral_mean_sd", "cand_var", "draw_mean", "draw_mean_var"))))
+    return out

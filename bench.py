@@ -169,6 +169,10 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
+    # torchrun pins OMP_NUM_THREADS=1 per rank, which would make the exporter (host C++, OpenMP) serial: give every
+    # rank its share of the host cores instead
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+    host_threads = int(lib.bartint_set_host_threads(max(1, (os.cpu_count() or 1) // max(local_world, 1))))
     c = workload(args)
     S, m, d, N, C = c["S"], c["m"], c["d"], c["N"], c["C"]
     n_total = N * world
@@ -253,7 +257,7 @@ def run_ours(args):
     # ---- end to end through the reference-facing call: dbarts wire format + host matrices in, host results out ----
     e2e = None
     if not args.no_e2e:
-        from bartint_b200 import StagedMatrix, WireStrings
+        from bartint_b200 import StagedMatrix, WireStrings, design_step_dbarts
         strings, fits = flats[0].to_dbarts_state(x_train)
         strings = WireStrings(strings)      # R holds savedTrees as C strings already; marshal once, outside the timing
         cut_lists = flats[0].cut_lists()
@@ -270,25 +274,32 @@ def run_ours(args):
             # the point matrices do not depend on the fitted model: their H2D copies are started first and overlap
             # the exporter's CPU work (bartint_stage_matrix); everything goes through the host-buffer C ABI
             sx, sxc = StagedMatrix(Xn, local_rank), StagedMatrix(Xcn, local_rank)
-            f = Forest.from_dbarts(strings, fits, x_train, cut_lists, flats[0].y_min, flats[0].y_max)   # exporter + H2D
-            integ = f.exact_integrals("uniform")
-            _, imean, isd = f.finalize_integrals(integ)
-            pc, pm = sxc.points(f), sx.points(f)
-            var = f.eval(pc, weights=np.ones(1), want=("point_var",))["point_var"]
-            dmean = f.eval(pm, want=("draw_mean",))["draw_mean"]
-            torch.cuda.synchronize()
+            if args.e2e_separate:        # the same step as separate ABI calls (exporter, then the evaluations)
+                f = Forest.from_dbarts(strings, fits, x_train, cut_lists, flats[0].y_min, flats[0].y_max)   # exporter + H2D
+                integ = f.exact_integrals("uniform")
+                _, imean, isd = f.finalize_integrals(integ)
+                pc, pm = sxc.points(f), sx.points(f)
+                var = f.eval(pc, weights=np.ones(1), want=("point_var",))["point_var"]
+                dmean = f.eval(pm, want=("draw_mean",))["draw_mean"]
+                torch.cuda.synchronize()
+                pc.close(); pm.close(); f.close()
+            else:                        # one call: bartint_design_step_dbarts098 (exporter pipelined against the kernels)
+                o = design_step_dbarts(strings, fits, x_train, cut_lists, flats[0].y_min, flats[0].y_max, mc=sx,
+                                       candidates=sxc, weights=1.0, measure="uniform")
+                integ, var, dmean = o["integrals"], o["cand_var"], o["draw_mean"]
             dt = time.perf_counter() - t0
-            pc.close(); pm.close(); sx.close(); sxc.close()
+            sx.close(); sxc.close()
             if k > 0:
                 times.append(dt)
-            h2d = Xn.nbytes + Xcn.nbytes + f.n_nodes * 9 + f.n_leaves * 8 + f.n_groups * 8 * (f.table_bits + 1) + S * m * 8
-            d2h = integ.nbytes * 2 + var.nbytes + dmean.nbytes + 16
-            f.close()
+            f0 = forests[0]
+            h2d = Xn.nbytes + Xcn.nbytes + f0.n_nodes * 9 + f0.n_leaves * 8 + f0.n_groups * 8 * (f0.table_bits + 1) + S * m * 8
+            d2h = integ.nbytes * 2 + var.nbytes + dmean.nbytes + 32
         t_e2e = torch.tensor([float(np.mean(times))], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
         e2e = {"value": S * m * (n_total + C) / float(t_e2e.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "s_per_step": float(t_e2e.item()), "steps": e2e_steps,
+               "call": "separate ABI calls" if args.e2e_separate else "bartint_design_step_dbarts098 (one call, draw-chunk pipeline)",
                "includes": "X / candidate H2D from pinned memory (started first, overlapping the exporter), dbarts-0.9-8 "
                            "string/fit exporter, forest H2D + table build, binning, exact integrals, evaluation, D2H of "
                            "integrals, candidate variances and per-draw means"}
@@ -375,7 +386,8 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "config": config_json(c, {"mc_points_total": n_total,
-                                                                       "parallelism": f"points x{world} (MC), draws x{world} (candidates)"}),
+                                                                       "parallelism": f"points x{world} (MC), draws x{world} (candidates)",
+                                                                       "host_threads_per_rank": host_threads}),
         "s_per_sequential_design_step": total_ms / args.steps / 1e3,
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "roofline_k0": roofline_k0,
         "cpu_baseline": cpu,
@@ -410,6 +422,8 @@ def main():
     ap.add_argument("--points", type=int, default=0, help="override MC points per GPU (testing)")
     ap.add_argument("--draws", type=int, default=0, help="override posterior draws (testing)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-separate", action="store_true",
+                    help="time the end-to-end step as separate ABI calls instead of the fused bartint_design_step call")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for the cpu_baseline sample")
     args = ap.parse_args()

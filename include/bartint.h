@@ -58,6 +58,10 @@ int bartint_version(void);
 const char* bartint_last_error(void);
 int bartint_device_count(int* n_out);
 int bartint_set_device(int device);       /* forests/points are created on the current device */
+/* Host threads used by the exporter / group planner (OpenMP).  n <= 0: one per host core.  Returns the number in
+ * effect.  Launchers that pin OMP_NUM_THREADS=1 per rank (torchrun) make the exporter serial unless this is called;
+ * a multi-rank host should pass cores / ranks-per-node. */
+int bartint_set_host_threads(int n);
 
 /* ---------------------------------------------------------------------------------------------
  * Tree-state exporter.  Replaces getTree() (src/BARTInt.R:92-133) applied to every (tree, draw):
@@ -243,6 +247,29 @@ int bartint_last_eval_profile(const bartint_forest* f, int32_t with_moments, flo
 /* Number of CUDA kernels this library has launched in this process so far (all devices, all streams).
  * bench.py reports the difference across its timed region as "gpu_launches". */
 int64_t bartint_kernel_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * One sequential-design step in ONE call.  Replaces the body of the reference's loop
+ *   sampleIntegrals(model, dim, measure); rescale, mean, sd                     BARTInt.R:259-262 / 289-292
+ *   colVars(predict(model, candidateSet)) * weights                            BARTInt.R:312-314
+ *   rowMeans(predict(model, X)); mean; variance of the row means               bartMean.R:74-82
+ * given the dbarts state as bartint_forest_from_dbarts098 takes it and two matrices staged with
+ * bartint_stage_matrix (either may be NULL).  The draws are processed in n_chunks chunks (<= 0: automatic): while
+ * the GPU evaluates one chunk, the host exports the next, so the exporter's CPU time hides behind the kernels.
+ * Results are identical to the separate calls up to the summation order of the Chan merge across chunks.
+ *   integrals_scaled [n_draws_integral or S]  per-draw exact integrals, dbarts scaled units (sampleIntegrals' value)
+ *   integral_mean_sd [2]                      mean and sd of the rescaled integrals          (BARTInt.R:260-262)
+ *   cand_var         [C]                      colVars(predict(model, candidates)) * weights
+ *   draw_mean        [S]                      rowMeans(predict(model, X_mc)), original units
+ *   draw_mean_var    [2]                      mean(draw_mean), var(draw_mean)                 (bartMean.R:80-82)
+ * Any output may be NULL.  n_draws_integral <= 0: all draws (the reference uses the first ntree, quirk B1).
+ * ------------------------------------------------------------------------------------------- */
+int bartint_design_step_dbarts098(const char* const* tree_strings, const double* tree_fits, const double* x_train,
+                                  int64_t n, int32_t d, const int32_t* cut_offsets, const double* cut_values,
+                                  double y_min, double y_max, int32_t m, int32_t S, const bartint_staged* mc,
+                                  const bartint_staged* cand, const double* weights, int64_t weights_len,
+                                  int32_t measure, int32_t n_draws_integral, int32_t n_chunks, double* integrals_scaled,
+                                  double* integral_mean_sd, double* cand_var, double* draw_mean, double* draw_mean_var);
 
 #ifdef __cplusplus
 }
