@@ -310,7 +310,38 @@ struct bartint_staged {
     double* dX = nullptr;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t done = nullptr;
+    // large matrices travel in row blocks (multiples of 4096 rows), each with its own event, so a consumer can start
+    // on the first rows while the rest is still on the bus (bartint_design_step_dbarts098)
+    int n_blocks = 1;
+    int64_t block_rows = 0;
+    cudaEvent_t block_done[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    // Only block 0 is put on the bus at once: copies queue FIFO on the copy engine, and the first forest upload of a
+    // design step must not wait behind the whole matrix.  The other blocks are submitted by staged_submit_rest()
+    // (first consumer, or the design step right after its first forest upload).  The host matrix stays caller-owned
+    // and must remain valid until the staged matrix has been consumed or freed.
+    const double* host_X = nullptr;
+    int submitted = 1;
 };
+
+static cudaError_t staged_submit_block(bartint_staged* s, int b) {
+    const int64_t r0 = (int64_t)b * s->block_rows, rows = std::min(s->block_rows, s->N - r0);
+    cudaError_t e = cudaSuccess;
+    if (rows > 0)
+        e = cudaMemcpy2DAsync(s->dX + r0, sizeof(double) * (size_t)s->N, s->host_X + r0, sizeof(double) * (size_t)s->N,
+                              sizeof(double) * (size_t)rows, (size_t)s->d, cudaMemcpyHostToDevice, s->copy_stream);
+    if (e == cudaSuccess) e = cudaEventRecord(s->block_done[b], s->copy_stream);
+    return e;
+}
+
+static cudaError_t staged_submit_rest(const bartint_staged* cs) {
+    bartint_staged* s = const_cast<bartint_staged*>(cs);      // the handle is logically const for its consumers
+    cudaError_t e = cudaSuccess;
+    if (s->submitted >= s->n_blocks) return e;
+    for (int b = s->submitted; b < s->n_blocks && e == cudaSuccess; ++b) e = staged_submit_block(s, b);
+    s->submitted = s->n_blocks;
+    if (e == cudaSuccess) e = cudaEventRecord(s->done, s->copy_stream);
+    return e;
+}
 
 int bartint_stage_matrix(const double* X, int64_t N, int32_t d, int device, bartint_staged** out) {
     BI_REQUIRE(out != nullptr, BARTINT_ERR_ARG, "out is NULL");
@@ -325,8 +356,19 @@ int bartint_stage_matrix(const double* X, int64_t N, int32_t d, int device, bart
     cudaError_t e = cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->done, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMallocAsync((void**)&s->dX, sizeof(double) * (size_t)std::max<int64_t>(N * d, 1), s->copy_stream);
-    if (e == cudaSuccess && N * d > 0)
-        e = cudaMemcpyAsync(s->dX, X, sizeof(double) * (size_t)(N * d), cudaMemcpyHostToDevice, s->copy_stream);
+    if (e == cudaSuccess && N * d > 0) {
+        if (N >= (int64_t)1 << 18) {      // 4 row blocks: column-major, so each block is a d-row 2-D copy
+            s->n_blocks = 4;
+            s->block_rows = ((N + 3) / 4 + TK_NPAD - 1) / TK_NPAD * TK_NPAD;
+            s->host_X = X;
+            for (int b = 0; b < s->n_blocks && e == cudaSuccess; ++b)
+                e = cudaEventCreateWithFlags(&s->block_done[b], cudaEventDisableTiming);
+            if (e == cudaSuccess) e = staged_submit_block(s, 0);
+            s->submitted = 1;
+        } else {
+            e = cudaMemcpyAsync(s->dX, X, sizeof(double) * (size_t)(N * d), cudaMemcpyHostToDevice, s->copy_stream);
+        }
+    }
     if (e == cudaSuccess) e = cudaEventRecord(s->done, s->copy_stream);
     if (e != cudaSuccess) { bartint_staged_free(s); return cuda_fail(e, "bartint_stage_matrix", __FILE__, __LINE__); }
     *out = s;
@@ -337,6 +379,7 @@ int bartint_staged_points(const bartint_forest* f, const bartint_staged* s, void
     BI_REQUIRE(f != nullptr && s != nullptr && out != nullptr, BARTINT_ERR_ARG, "NULL argument");
     BI_REQUIRE(s->device == f->device, BARTINT_ERR_ARG, "matrix was staged on another device than the forest's");
     DeviceGuard g(f->device);
+    BI_CUDA(staged_submit_rest(s));
     BI_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, s->done, 0));
     return bartint_points_from_device(f, s->dX, s->N, s->d, s->N, stream, out);
 }
@@ -348,6 +391,8 @@ void bartint_staged_free(bartint_staged* s) {
         if (s->copy_stream) cudaStreamSynchronize(s->copy_stream);
         if (s->dX) cudaFree(s->dX);            // synchronous: a consumer stream may still be binning from it
         if (s->done) cudaEventDestroy(s->done);
+        for (cudaEvent_t ev : s->block_done)
+            if (ev) cudaEventDestroy(ev);
         if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
         (void)cudaGetLastError();
     }
@@ -858,7 +903,7 @@ int bartint_design_step_dbarts098(const char* const* tree_strings, const double*
     cudaEvent_t built = nullptr;
     std::vector<bartint_forest*> forests;
     bartint_points *pm = nullptr, *pc = nullptr;
-    double* d_buf = nullptr;
+    double *d_buf = nullptr, *d_block_part = nullptr;
     int32_t* d_counts = nullptr;
     auto cleanup = [&]() {
         if (st) cudaStreamSynchronize(st);
@@ -867,6 +912,7 @@ int bartint_design_step_dbarts098(const char* const* tree_strings, const double*
         if (pm) bartint_points_destroy(pm);
         if (pc) bartint_points_destroy(pc);
         if (d_buf) cudaFreeAsync(d_buf, nullptr);
+        if (d_block_part) cudaFreeAsync(d_block_part, nullptr);
         if (d_counts) cudaFreeAsync(d_counts, nullptr);
         for (bartint_forest* f : forests) bartint_forest_destroy(f);
         if (st) cudaStreamDestroy(st);
@@ -918,16 +964,46 @@ int bartint_design_step_dbarts098(const char* const* tree_strings, const double*
         // the sub-forest's copies and table build are still in flight on the default stream: order `st` after them
         DS_CUDA(cudaEventRecord(built, nullptr));
         DS_CUDA(cudaStreamWaitEvent(st, built, 0));
+        if (g == 0 && mc != nullptr) DS_CUDA(staged_submit_rest(mc));   // the first forest is on the bus: now the rest of X
+        bool mc_done = false;
         if (g == 0) {            // the cut points are the same for every chunk: bin once against the first sub-forest
-            if (want_mc) DS_RC(bartint_staged_points(f, mc, st, &pm));
             if (want_cand) DS_RC(bartint_staged_points(f, cand, st, &pc));
+            if (want_mc && mc->n_blocks > 1) {
+                // The MC matrix arrives in row blocks: bin each block as it lands and evaluate the FIRST chunk of draws
+                // on it right away (a view of the point set), so the bus transfer hides behind the kernels as well.
+                DS_RC(make_points(f, N, d, st, &pm));
+                const int B = mc->n_blocks;
+                DS_CUDA(cudaMallocAsync((void**)&d_block_part, sizeof(double) * (size_t)B * (size_t)(s1 - s0), st));
+                int used = 0;
+                for (int b = 0; b < B; ++b) {
+                    const int64_t r0 = (int64_t)b * mc->block_rows, rows = std::min(mc->block_rows, N - r0);
+                    if (rows <= 0) break;
+                    const int64_t rows_padded = (b == B - 1 || r0 + mc->block_rows >= N) ? pm->Npad - r0 : mc->block_rows;
+                    DS_CUDA(cudaStreamWaitEvent(st, mc->block_done[b], 0));
+                    DS_RC(launch_bin_points(mc->dX + r0, N, rows, d, f->dev.cut_off, f->dev.cut_val, f->max_cuts, f->route,
+                                            pm->codes + r0, pm->Npad, st, rows_padded));
+                    if (pm->codes_pm)
+                        DS_RC(launch_repack_codes(pm->codes + r0, pm->Npad, d, pm->codes_pm + r0, st, rows_padded));
+                    bartint_points view = *pm;                       // shallow: same buffers, rows [r0, r0 + rows)
+                    view.codes = pm->codes + r0;
+                    view.codes_pm = pm->codes_pm ? pm->codes_pm + r0 : nullptr;
+                    view.N = rows;
+                    DS_RC(eval_core(f, &view, 0u, 0, s1 - s0, d_block_part + (size_t)used * (size_t)(s1 - s0), nullptr, nullptr,
+                                    nullptr, nullptr, 1.0, 0.0, 1, st));
+                    ++used;
+                }
+                DS_RC(launch_reduce_draw_parts(d_block_part, used, s1 - s0, d_sum + s0, st));   // fixed block order
+                mc_done = true;
+            } else if (want_mc) {
+                DS_RC(bartint_staged_points(f, mc, st, &pm));
+            }
         }
         if (want_int && s0 < n_int)
             DS_RC(launch_exact_integrals(f, measure, nullptr, nullptr, std::min(s1, n_int) - s0, d_int + s0, st));
         if (want_cand)
             DS_RC(eval_core(f, pc, 0u, 0, s1 - s0, nullptr, d_cmean + (size_t)g * nC, d_cm2 + (size_t)g * nC, nullptr, nullptr,
                             1.0, 0.0, 1, st));
-        if (want_mc)
+        if (want_mc && !mc_done)
             DS_RC(eval_core(f, pm, 0u, 0, s1 - s0, d_sum + s0, nullptr, nullptr, nullptr, nullptr, 1.0, 0.0, 1, st));
         if (timing) t_cpu.push_back(now_ms() - t_begin);
     }

@@ -146,14 +146,15 @@ int canonicalise_soa(int32_t S, int32_t m, int32_t d, const int64_t* tree_node_o
 
 // kernel launchers (kernels_*.cu)
 int launch_bin_points(const double* dX, int64_t ld, int64_t N, int32_t d, const int32_t* d_cut_off,
-                      const double* d_cut_val, int max_cuts, int route, uint8_t* codes, int64_t Npad, cudaStream_t st);
+                      const double* d_cut_val, int max_cuts, int route, uint8_t* codes, int64_t Npad, cudaStream_t st,
+                      int64_t rows_padded = 0);
 int launch_generate_points(int measure, int64_t N, int64_t first_index, uint64_t seed, int32_t d,
                            const int32_t* d_cut_off, const double* d_cut_val, int route, uint8_t* codes, int64_t Npad,
                            double* x_out, cudaStream_t st);
 struct EvalPlan;
 int launch_build_tables(const bartint_forest* f, const uint32_t* d_desc, int desc_words, const uint32_t* d_hdr,
                         const uint32_t* d_split, cudaStream_t st);
-int launch_repack_codes(const uint8_t* codes, int64_t Npad, int d, uint4* codes_pm, cudaStream_t st);
+int launch_repack_codes(const uint8_t* codes, int64_t Npad, int d, uint4* codes_pm, cudaStream_t st, int64_t rows = 0);
 int launch_eval_gather(const bartint_forest* f, const bartint_points* p, const EvalPlan& plan, double* draw_part,
                        double* pt_mean, double* pt_m2, double* full_pred, double fp_scale, double fp_y0,
                        int fp_scaled, cudaStream_t st);

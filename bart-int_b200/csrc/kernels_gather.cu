@@ -25,17 +25,18 @@ constexpr int TG_P = 8;                          // points per thread (16 in the
 // point-major packed codes: codes_pm[i] = 16 bytes, byte j = code of variable j (0 beyond d)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) repack_codes_kernel(const uint8_t* __restrict__ codes, int64_t Npad, int d,
-                                                           uint4* __restrict__ codes_pm) {
+                                                           uint4* __restrict__ codes_pm, int64_t rows) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= Npad) return;
+    if (i >= rows) return;
     uint32_t w[4] = {0u, 0u, 0u, 0u};
     for (int j = 0; j < d; ++j) w[j >> 2] |= (uint32_t)codes[(int64_t)j * Npad + i] << (8 * (j & 3));
     codes_pm[i] = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-int launch_repack_codes(const uint8_t* codes, int64_t Npad, int d, uint4* codes_pm, cudaStream_t st) {
+int launch_repack_codes(const uint8_t* codes, int64_t Npad, int d, uint4* codes_pm, cudaStream_t st, int64_t rows) {
     if (Npad == 0) return BARTINT_OK;
-    repack_codes_kernel<<<(unsigned)((Npad + 255) / 256), 256, 0, st>>>(codes, Npad, d, codes_pm);
+    if (rows <= 0) rows = Npad;          // rows > 0: a row block (codes / codes_pm point at its first row; stride Npad)
+    repack_codes_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(codes, Npad, d, codes_pm, rows);
     count_launch();
     BI_CUDA(cudaGetLastError());
     return BARTINT_OK;

@@ -75,7 +75,8 @@ template <bool INC>
 __global__ void __launch_bounds__(256) bin_points_kernel(const double* __restrict__ X, int64_t ld, int64_t N,
                                                          const int32_t* __restrict__ cut_off,
                                                          const double* __restrict__ cut_val,
-                                                         uint32_t* __restrict__ codes4, int64_t quads_per_row) {
+                                                         uint32_t* __restrict__ codes4, int64_t quads_per_row,
+                                                         int64_t n_quads) {
     __shared__ double s_cut_pad[258];
     __shared__ float2 s_pair[257];
     double* s_cut = s_cut_pad + 1;
@@ -88,7 +89,8 @@ __global__ void __launch_bounds__(256) bin_points_kernel(const double* __restric
     const double inv_step = span > 0.0 ? (double)(nc - 1) / span : 0.0;
     const double* __restrict__ col = X + (int64_t)j * ld;
     const bool aligned16 = ((reinterpret_cast<uintptr_t>(col) & 15) == 0);
-    for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < quads_per_row;
+    // quads_per_row = stride of the code rows; n_quads = words this launch writes (a row block of a larger point set)
+    for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_quads;
          w += (int64_t)gridDim.x * blockDim.x) {
         const int64_t i = w * 4;
         uint32_t word = 0;
@@ -114,10 +116,13 @@ __global__ void __launch_bounds__(256) bin_points_kernel(const double* __restric
 }
 
 int launch_bin_points(const double* dX, int64_t ld, int64_t N, int32_t d, const int32_t* d_cut_off,
-                      const double* d_cut_val, int max_cuts, int route, uint8_t* codes, int64_t Npad, cudaStream_t st) {
+                      const double* d_cut_val, int max_cuts, int route, uint8_t* codes, int64_t Npad, cudaStream_t st,
+                      int64_t rows_padded) {
     (void)max_cuts;
     if (d == 0 || Npad == 0) return BARTINT_OK;
-    const int64_t quads = Npad / 4;
+    // rows_padded > 0: bin a row block -- `codes` points at the block's first row inside code rows of stride Npad, and
+    // rows_padded (a multiple of 4, >= N) rows are written (zeros beyond N)
+    const int64_t quads = (rows_padded > 0 ? rows_padded : Npad) / 4;
     int64_t bx = (quads + 255) / 256;
     // a few waves of 148 SMs x 8 resident CTAs; grid-stride beyond that
     const int64_t cap = (148 * 8 * 4 + d - 1) / d;
@@ -125,7 +130,7 @@ int launch_bin_points(const double* dX, int64_t ld, int64_t N, int32_t d, const 
     if (bx < 1) bx = 1;
     dim3 grid((unsigned)bx, (unsigned)d);
     auto kern = route == BARTINT_ROUTE_BART ? bin_points_kernel<true> : bin_points_kernel<false>;
-    kern<<<grid, 256, 0, st>>>(dX, ld, N, d_cut_off, d_cut_val, reinterpret_cast<uint32_t*>(codes), quads);
+    kern<<<grid, 256, 0, st>>>(dX, ld, N, d_cut_off, d_cut_val, reinterpret_cast<uint32_t*>(codes), Npad / 4, quads);
     count_launch();
     BI_CUDA(cudaGetLastError());
     return BARTINT_OK;

@@ -129,7 +129,11 @@ void bartint_forest_destroy(bartint_forest* f);
 /* Staging of a host matrix that does not depend on the fitted model (the candidate matrix / fullData of
  * bartMean.R:26 exist before bart() returns): starts the host->device copy on an internal copy stream and returns at
  * once, so the transfer overlaps the exporter's CPU work.  bartint_staged_points() then bins it for a forest (waits
- * for the copy on `stream`); the staging buffer is released by bartint_staged_free().  device = CUDA device index. */
+ * for the copy on `stream`); the staging buffer is released by bartint_staged_free().  device = CUDA device index.
+ * Matrices of >= 2^18 rows travel in four row blocks, of which only the first is put on the bus at once (copies queue
+ * first-in first-out on the copy engine and a forest upload must not wait behind the whole matrix); the rest follows
+ * when the first consumer asks for the data.  X therefore has to stay valid until the staged matrix has been consumed
+ * (bartint_staged_points / bartint_design_step_dbarts098 returned) or freed. */
 typedef struct bartint_staged bartint_staged;
 int bartint_stage_matrix(const double* X, int64_t N, int32_t d, int device, bartint_staged** out);
 int bartint_staged_points(const bartint_forest* f, const bartint_staged* s, void* stream, bartint_points** out);
