@@ -54,3 +54,21 @@ bartint_draw_means <- function(model, X) {
 #   bartMean.R:74-82        pred <- predict(model, fullData); rowMeans(pred); mean(pred)
 #                        -> rm <- bartint_draw_means(model, fullData); meanValue[i] <- mean(rm);
 #                           standardDeviation[i] <- sum((rm - meanValue[i])^2) / (length(rm) - 1)
+
+# One library call for the body of the sequential loop (src/BARTInt.R:259-262 + 312-314; with X also
+# src/survey_design/bartMean.R:74-82): exact integrals (scaled units) + their rescaled mean/sd, per-candidate
+# variance * weights, per-draw means.  The export of the saved trees is pipelined against the kernels.
+bartint_design_step <- function(model, candidateSet = NULL, weights = NULL, measure = "uniform", X = NULL,
+                                all_draws = FALSE) {
+  fit <- model$fit
+  state <- fit$state[[1]]
+  y <- fit$data@y
+  n_used <- if (all_draws) 0L else dim(state@treeFits)[2]
+  r <- .Call("bartint_R_design_step", state@savedTrees, state@savedTreeFits, fit$data@x,
+             dbarts:::createCutPoints(fit), min(y), max(y),
+             if (is.null(candidateSet)) NULL else as.matrix(candidateSet) + 0,
+             if (is.null(weights)) NULL else as.double(weights),
+             if (is.null(X)) NULL else as.matrix(X) + 0, bartint_measure_code[[measure]], as.integer(n_used))
+  names(r) <- c("integrals", "integral_mean_sd", "cand_var", "draw_mean", "draw_mean_var")
+  r
+}

@@ -112,3 +112,58 @@ SEXP bartint_R_eval(SEXP ptr, SEXP x, SEXP weights, SEXP what) {
     UNPROTECT(4);
     return out;
 }
+
+/* .Call("bartint_R_design_step", savedTrees, savedTreeFits, x, cutPoints, ymin, ymax, candidates (dbl C x d or NULL),
+ *       weights (dbl, length 1 or C, or NULL), X (dbl N x d or NULL), measure, n_draws_integral)
+ * -> list(integrals, integral_mean_sd, cand_var, draw_mean, draw_mean_var).   One library call for the body of the
+ * sequential loop (BARTInt.R:259-262 + 312-314; with X also bartMean.R:74-82): the export of the saved trees is
+ * pipelined against the evaluation kernels, so no forest handle is kept. */
+SEXP bartint_R_design_step(SEXP trees, SEXP fits, SEXP x, SEXP cuts, SEXP ymin, SEXP ymax, SEXP cand, SEXP weights,
+                           SEXP X, SEXP measure, SEXP n_draws_integral) {
+    SEXP dim = Rf_getAttrib(trees, R_DimSymbol);
+    const int m = INTEGER(dim)[0], S = INTEGER(dim)[1];
+    SEXP xdim = Rf_getAttrib(x, R_DimSymbol);
+    const int64_t n = INTEGER(xdim)[0];
+    const int d = INTEGER(xdim)[1];
+    const char** strs = (const char**)R_alloc((size_t)m * S, sizeof(char*));
+    for (R_xlen_t k = 0; k < (R_xlen_t)m * S; ++k) strs[k] = CHAR(STRING_ELT(trees, k));
+    int32_t* off = (int32_t*)R_alloc((size_t)d + 1, sizeof(int32_t));
+    off[0] = 0;
+    for (int j = 0; j < d; ++j) off[j + 1] = off[j] + (int32_t)XLENGTH(VECTOR_ELT(cuts, j));
+    double* vals = (double*)R_alloc((size_t)off[d] + 1, sizeof(double));
+    for (int j = 0; j < d; ++j) {
+        const double* c = REAL(VECTOR_ELT(cuts, j));
+        for (int k = 0; k < off[j + 1] - off[j]; ++k) vals[off[j] + k] = c[k];
+    }
+    int device = 0;
+    bartint_staged *sc = NULL, *sx = NULL;
+    int64_t C = 0;
+    if (!Rf_isNull(cand)) {
+        C = INTEGER(Rf_getAttrib(cand, R_DimSymbol))[0];
+        check(bartint_stage_matrix(REAL(cand), C, d, device, &sc));
+    }
+    if (!Rf_isNull(X)) {
+        const int rc = bartint_stage_matrix(REAL(X), INTEGER(Rf_getAttrib(X, R_DimSymbol))[0], d, device, &sx);
+        if (rc != BARTINT_OK) { bartint_staged_free(sc); check(rc); }
+    }
+    int n_int = Rf_asInteger(n_draws_integral);
+    if (n_int <= 0 || n_int > S) n_int = S;
+    SEXP integ = PROTECT(Rf_allocVector(REALSXP, n_int));
+    SEXP ims = PROTECT(Rf_allocVector(REALSXP, 2));
+    SEXP cv = PROTECT(sc ? Rf_allocVector(REALSXP, C) : R_NilValue);
+    SEXP dm = PROTECT(sx ? Rf_allocVector(REALSXP, S) : R_NilValue);
+    SEXP dmv = PROTECT(sx ? Rf_allocVector(REALSXP, 2) : R_NilValue);
+    const int has_w = !Rf_isNull(weights);
+    const int rc = bartint_design_step_dbarts098(strs, REAL(fits), REAL(x), n, d, off, vals, Rf_asReal(ymin), Rf_asReal(ymax),
+                                                 m, S, sx, sc, has_w ? REAL(weights) : NULL, has_w ? XLENGTH(weights) : 0,
+                                                 Rf_asInteger(measure), n_int, 0, REAL(integ), REAL(ims),
+                                                 sc ? REAL(cv) : NULL, sx ? REAL(dm) : NULL, sx ? REAL(dmv) : NULL);
+    bartint_staged_free(sc);
+    bartint_staged_free(sx);
+    if (rc != BARTINT_OK) { UNPROTECT(5); check(rc); }
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 5));
+    SET_VECTOR_ELT(out, 0, integ); SET_VECTOR_ELT(out, 1, ims); SET_VECTOR_ELT(out, 2, cv);
+    SET_VECTOR_ELT(out, 3, dm); SET_VECTOR_ELT(out, 4, dmv);
+    UNPROTECT(6);
+    return out;
+}

@@ -16,6 +16,7 @@ there is no CPU path here.
   BARTInt(...) :225, BART_posterior(...) :329,    BARTInt, BART_posterior, mainBARTInt
   mainBARTInt(...) :398
   computeBART(...)             bartMean.R:16      computeBART
+  (loop body :259-262 + :312-314 in one call)     bartint_design_step(model, candidateSet, weights, measure)
 """
 from __future__ import annotations
 
@@ -123,6 +124,27 @@ def bartint_candidate_var(model: BartModel, X, weights=1.0) -> np.ndarray:
 def bartint_draw_means(model: BartModel, X) -> np.ndarray:
     """rowMeans(predict(model, X)) without materialising the S x N matrix (bartMean.R:74-76)."""
     return model.forest().eval(X, want=("draw_mean",))["draw_mean"]
+
+
+def bartint_design_step(model: BartModel, candidateSet=None, weights=1.0, measure="uniform", X=None,
+                        all_draws: bool = False) -> dict:
+    """One sequential-design step in one library call (bartint_design_step_dbarts098): what BARTInt.R:259-262 and
+    :312-314 (and, when X is given, bartMean.R:74-82) compute from a freshly fitted model, with the tree export
+    pipelined against the evaluation.  Returns the per-draw integrals in scaled units (`integrals`, the value of
+    sampleIntegrals -- first ntree draws unless all_draws, quirk B1), `integral_mean_sd` (rescaled, :260-262),
+    `cand_var` (= colVars(predict(model, candidateSet)) * weights) and `draw_mean` / `draw_mean_var`."""
+    from .forest import StagedMatrix, design_step_dbarts
+    fit = model.fit
+    sc = StagedMatrix(candidateSet) if candidateSet is not None else None
+    sx = StagedMatrix(X) if X is not None else None
+    try:
+        return design_step_dbarts(fit.saved_trees, fit.saved_tree_fits, fit.x, fit.cut_points, model.y_min, model.y_max,
+                                  mc=sx, candidates=sc, weights=weights, measure=measure,
+                                  n_draws_integral=None if all_draws else min(fit.n_tree, fit.n_draws))
+    finally:
+        for h in (sc, sx):
+            if h is not None:
+                h.close()
 
 
 def r_sample_one(v: np.ndarray, rng) -> int:

@@ -82,3 +82,22 @@ def test_design_step_errors():
     with pytest.raises(BartIntError):
         design_step_dbarts(WireStrings(strings), fits, x_train, ff.cut_lists(), ff.y_min, ff.y_max, mc=wrong_d)
     wrong_d.close(); cand.close()
+
+
+def test_api_design_step_matches_drop_in_functions():
+    from bartint_b200 import api
+    rng = np.random.default_rng(21)
+    x = rng.random((60, 3))
+    y = synth.genz_gaussian(x)
+    model = api.synthetic_bart(x, y, ndpost=400, keepevery=1, ntree=20, seed=4)
+    cand = rng.random((100, 3))
+    w = rng.random(100)
+    step = api.bartint_design_step(model, cand, w, "uniform")
+    integ = api.sampleIntegrals(model, 3, "uniform")                      # first ntree draws (quirk B1)
+    assert step["integrals"].shape == integ.shape and np.array_equal(step["integrals"], integ)
+    resc = (integ + 0.5) * (model.y_max - model.y_min) + model.y_min       # BARTInt.R:260-262
+    assert abs(step["integral_mean_sd"][0] - resc.mean()) <= 1e-12 * (model.y_max - model.y_min)
+    assert abs(step["integral_mean_sd"][1] - resc.std(ddof=1)) <= 1e-10 * resc.std(ddof=1)
+    var = api.bartint_candidate_var(model, cand, w)
+    assert np.max(np.abs(step["cand_var"] - var)) <= 1e-10 * np.max(var)
+    model.close()
