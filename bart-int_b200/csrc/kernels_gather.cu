@@ -165,22 +165,25 @@ __global__ void __launch_bounds__(TG_THREADS, P > 8 ? 2 : MOMENTS ? 2 : 3) eval_
             joint_mask |= (unsigned long long)__ballot_sync(0xffffffffu, (fl & TK_FLAG_JOINT) != 0u) << base;
         }
         // DUAL records without a flag (the bulk) run in a tight loop; the next flagged record is found with one ffs
-        auto dual_points = [&](auto variant, const uint4& da, const uint4& db, const unsigned char* __restrict__ tbl) {
+        auto dual_points = [&](auto variant, const uint4& da, uint32_t wB, uint32_t sel_t,
+                               const unsigned char* __restrict__ tbl) {
 #pragma unroll
             for (int p = 0; p < P; ++p) {
                 uint32_t o1, o2;
-                dual_offsets<R, decltype(variant)::value>(creg[p], da.x, da.y, da.z, da.w, db.x, db.z, o1, o2);
+                dual_offsets<R, decltype(variant)::value>(creg[p], da.x, da.y, da.z, da.w, wB, sel_t, o1, o2);
                 acc[p] += *reinterpret_cast<const double*>(tbl + o1);
                 acc[p] += *reinterpret_cast<const double*>(tbl + o2);
             }
         };
         auto dual_group = [&](const unsigned char* rec) {
-            const uint4 da = *reinterpret_cast<const uint4*>(rec + TK_HDR);            // smem broadcast loads
-            const uint4 db = *reinterpret_cast<const uint4*>(rec + TK_HDR + 16);       // wB, table-2 kind, sel_t, -
+            // smem broadcast loads: 16 + 8 bytes (a broadcast LDS.128 costs 2 wavefronts, an LDS.64 one); sel_t is
+            // fetched only by the three-word kind
+            const uint4 da = *reinterpret_cast<const uint4*>(rec + TK_HDR);
+            const uint2 db = *reinterpret_cast<const uint2*>(rec + TK_HDR + 16);       // wB, table-2 kind
             const unsigned char* __restrict__ tbl = rec + tg_tbl_off();
-            if (R == 2 || db.y == 0u) dual_points(std::integral_constant<int, 0>{}, da, db, tbl);
-            else if (db.y == 1u) dual_points(std::integral_constant<int, 1>{}, da, db, tbl);
-            else dual_points(std::integral_constant<int, 2>{}, da, db, tbl);
+            if (R == 2 || db.y == 0u) dual_points(std::integral_constant<int, 0>{}, da, db.x, 0u, tbl);
+            else if (db.y == 1u) dual_points(std::integral_constant<int, 1>{}, da, db.x, 0u, tbl);
+            else dual_points(std::integral_constant<int, 2>{}, da, db.x, *reinterpret_cast<const uint32_t*>(rec + TK_HDR + 24), tbl);
         };
         auto joint_group = [&](const unsigned char* rec) {
             const uint4 da = *reinterpret_cast<const uint4*>(rec + TK_HDR);

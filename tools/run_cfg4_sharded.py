@@ -34,6 +34,8 @@ def main():
     c = synth.CONFIGS[4]
     x_train, y_train = synth.make_design(4)
     ff = synth.prior_forest(4000, c["S"], c["m"], x_train, y_train)
+    from bartint_b200 import _lib
+    _lib.load().bartint_set_host_threads(max(1, (os.cpu_count() or 1) // max(world, 1)))    # torchrun pins OMP to 1
     f = Forest.from_soa(ff)
     S = ff.S
     lo, hi = bdist.shard_range(n_total, world, rank)
@@ -65,18 +67,19 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     total2 = run(2)
     torch.cuda.synchronize()
-    scale = ff.y_max - ff.y_min
-    draw_mean = scale * (total / n_total + 0.5) + ff.y_min            # rowMeans(predict(model, X)), bartMean.R:76
-    draw_mean2 = scale * (total2 / n_total + 0.5) + ff.y_min
-    same = float((draw_mean - draw_mean2).abs().max() / scale)
+    # dbarts' scaled units (the synthetic rare-event response is constant, so the original-unit range is degenerate)
+    draw_mean = total / n_total                                        # rowMeans(predict(model, X)) before the y rescale
+    draw_mean2 = total2 / n_total
+    same = float((draw_mean - draw_mean2).abs().max())
     if rank == 0:
         t = float(ms.item()) * 1e-3
         print(json.dumps({"cfg": 4, "workload": c["name"], "n_gpus": world, "points_total": n_total,
                           "points_per_gpu": hi - lo, "draws": S, "trees": ff.m, "tree_evals": S * ff.m * n_total,
                           "s": t, "evals_per_s": S * ff.m * n_total / t,
                           "includes": "on-device Philox generation + binning of the shard, ensemble evaluation, all-gather of per-draw sums",
-                          "integral_mean": float(draw_mean.mean()), "integral_sd": float(draw_mean.std(unbiased=True)),
-                          "max_rel_diff_vs_two_piece_generation": same}), flush=True)
+                          "integral_mean_scaled_units": float(draw_mean.mean()),
+                          "integral_sd_scaled_units": float(draw_mean.std(unbiased=True)),
+                          "max_abs_diff_vs_two_piece_generation": same}), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
