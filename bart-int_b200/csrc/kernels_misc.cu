@@ -42,21 +42,20 @@ __device__ __forceinline__ uint32_t bin_one(double x, const double* __restrict__
 }
 
 // Single-precision screen in front of bin_one: pair[k] = {float_ru(cuts[k-1]), float_rd(cuts[k])}, one 8-byte probe
-// instead of two.  With xd = float_rd(x) <= x <= xu = float_ru(x):
-//     pair[k].x <  xd  =>  cuts[k-1] <  x          xu <= pair[k].y  =>  !(cuts[k] <  x)      (dbarts rule)
-//     pair[k].x <= xd  =>  cuts[k-1] <= x          xu <  pair[k].y  =>  !(cuts[k] <= x)      (BART rule)
-// so a passed screen PROVES the guess; anything else (x within a float ulp of a cut, wrong guess, NaN, irregular grid)
-// takes the exact fp64 path.  Halves the shared-memory bytes per element -- ncu had the cut-table probes at 70 % of
-// the L1/shared pipe with 55 % bank-conflict replays, ahead of HBM.
+// instead of two, and the guess itself in fp32.  With xn = float_rn(x):  |x - xn| <= ulp/2, so x lies strictly between
+// the float neighbours of xn, and for floats U < xn < D:
+//     U <= prev(xn) < x   =>  cuts[k-1] <= U < x          x < next(xn) <= D  =>  x < D <= cuts[k]
+// i.e. a passed screen PROVES cuts[k-1] < x < cuts[k], which decides the code under both routing rules.  Anything
+// else (x within a float ulp of a cut or exactly on it, wrong guess, NaN, +-Inf, irregular grid) takes the exact fp64
+// path.  ncu before the screen: cut-table probes at 70 % of the L1/shared pipe with 55 % bank-conflict replays,
+// ahead of HBM; with two-sided fp64 guess arithmetic the kernel was then issue-bound (78 %), hence the fp32 guess.
 template <bool INC>
 __device__ __forceinline__ uint32_t bin_screened(double x, const float2* __restrict__ pair, const double* __restrict__ cuts,
-                                                 int nc, double c0, double inv_step) {
-    const double g = fma(x - c0, inv_step, 1.0);
-    const int k = __double2int_rd(fmin(fmax(g, 0.0), (double)nc));
+                                                 int nc, double c0, double inv_step, float c0f, float invf) {
+    const float xn = __double2float_rn(x);
+    const int k = min(max(__float2int_rd(fmaf(xn - c0f, invf, 1.0f)), 0), nc);     // NaN -> 0
     const float2 pr = pair[k];
-    const float xd = __double2float_rd(x), xu = __double2float_ru(x);
-    const bool ok = INC ? (pr.x <= xd && xu < pr.y) : (pr.x < xd && xu <= pr.y);
-    if (ok) return (uint32_t)k;
+    if (pr.x < xn && xn < pr.y) return (uint32_t)k;
     return bin_one<INC>(x, cuts, nc, c0, inv_step);
 }
 
@@ -87,6 +86,7 @@ __global__ void __launch_bounds__(256) bin_points_kernel(const double* __restric
     const double c0 = nc > 0 ? s_cut[0] : 0.0;
     const double span = nc > 1 ? s_cut[nc - 1] - s_cut[0] : 0.0;
     const double inv_step = span > 0.0 ? (double)(nc - 1) / span : 0.0;
+    const float c0f = (float)c0, invf = (float)inv_step;
     const double* __restrict__ col = X + (int64_t)j * ld;
     const bool aligned16 = ((reinterpret_cast<uintptr_t>(col) & 15) == 0);
     // quads_per_row = stride of the code rows; n_quads = words this launch writes (a row block of a larger point set)
@@ -103,13 +103,13 @@ __global__ void __launch_bounds__(256) bin_points_kernel(const double* __restric
             } else {
                 x0 = __ldg(col + i); x1 = __ldg(col + i + 1); x2 = __ldg(col + i + 2); x3 = __ldg(col + i + 3);
             }
-            word = bin_screened<INC>(x0, s_pair, s_cut, nc, c0, inv_step) |
-                   (bin_screened<INC>(x1, s_pair, s_cut, nc, c0, inv_step) << 8) |
-                   (bin_screened<INC>(x2, s_pair, s_cut, nc, c0, inv_step) << 16) |
-                   (bin_screened<INC>(x3, s_pair, s_cut, nc, c0, inv_step) << 24);
+            word = bin_screened<INC>(x0, s_pair, s_cut, nc, c0, inv_step, c0f, invf) |
+                   (bin_screened<INC>(x1, s_pair, s_cut, nc, c0, inv_step, c0f, invf) << 8) |
+                   (bin_screened<INC>(x2, s_pair, s_cut, nc, c0, inv_step, c0f, invf) << 16) |
+                   (bin_screened<INC>(x3, s_pair, s_cut, nc, c0, inv_step, c0f, invf) << 24);
         } else {
             for (int k = 0; k < 4; ++k)
-                if (i + k < N) word |= bin_screened<INC>(__ldg(col + i + k), s_pair, s_cut, nc, c0, inv_step) << (8 * k);
+                if (i + k < N) word |= bin_screened<INC>(__ldg(col + i + k), s_pair, s_cut, nc, c0, inv_step, c0f, invf) << (8 * k);
         }
         codes4[(int64_t)j * quads_per_row + w] = word;   // padding quads (i >= N) are written as 0
     }
@@ -181,6 +181,7 @@ __global__ void __launch_bounds__(256) generate_points_kernel(int measure, int64
     const double c0 = nc > 0 ? s_cut[0] : 0.0;
     const double span = nc > 1 ? s_cut[nc - 1] - s_cut[0] : 0.0;
     const double inv_step = span > 0.0 ? (double)(nc - 1) / span : 0.0;
+    const float c0f = (float)c0, invf = (float)inv_step;
     for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < quads_per_row;
          w += (int64_t)gridDim.x * blockDim.x) {
         uint32_t word = 0;
@@ -193,7 +194,7 @@ __global__ void __launch_bounds__(256) generate_points_kernel(int measure, int64
                 philox4x32_10((uint32_t)gi, (uint32_t)(gi >> 32), (uint32_t)j, 0u, k0, k1, r0, r1);
                 const double x = draw_from_measure(measure, r0, r1);
                 if (x_out != nullptr) x_out[(int64_t)j * N + i] = x;
-                word |= bin_screened<INC>(x, s_pair, s_cut, nc, c0, inv_step) << (8 * k);
+                word |= bin_screened<INC>(x, s_pair, s_cut, nc, c0, inv_step, c0f, invf) << (8 * k);
             }
         }
         codes4[(int64_t)j * quads_per_row + w] = word;

@@ -101,3 +101,25 @@ def test_api_design_step_matches_drop_in_functions():
     var = api.bartint_candidate_var(model, cand, w)
     assert np.max(np.abs(step["cand_var"] - var)) <= 1e-10 * np.max(var)
     model.close()
+
+
+@pytest.mark.parametrize("N", [262144, 300001])
+def test_design_step_row_block_path(N):
+    """>= 2^18 rows: the matrix is staged in four row blocks and the first chunk of draws is evaluated block by block on
+    views of the point set (ragged last block included)."""
+    ff, x_train, strings, fits, _, Xc, w = _case(S=24, m=6, d=5, N=10, C=50, seed=17)
+    rng = np.random.default_rng(N)
+    X = rng.random((N, 5))
+    X[::1000, 2] = np.nan
+    mc, cand = StagedMatrix(X), StagedMatrix(Xc)
+    out = design_step_dbarts(WireStrings(strings), fits, x_train, ff.cut_lists(), ff.y_min, ff.y_max, mc=mc, candidates=cand,
+                             weights=w, n_chunks=3)
+    # the staged handle stays usable for an ordinary consumer afterwards
+    f = Forest.from_soa(ff)
+    pts = mc.points(f)
+    sep = f.eval(pts, want=("draw_mean",))["draw_mean"]
+    pts.close(); f.close(); mc.close(); cand.close()
+    ref = oc.predict_reduce(ff, X, nthreads=oc.max_threads(), want=("draw_mean",))["draw_mean"]
+    scale = ff.y_max - ff.y_min
+    assert np.max(np.abs(out["draw_mean"] - ref)) <= 1e-12 * scale
+    assert np.max(np.abs(out["draw_mean"] - sep)) <= 1e-13 * scale

@@ -191,3 +191,36 @@ def test_wbart_device_point_generation(measure):
 def test_wbart_rejects_malformed(bad):
     with pytest.raises(BartIntError):
         Forest.from_wbart(bad, KAT_CUTS, 0.0)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# The C++ text parser runs before the library touches the device, so its verdicts are testable on a CPU-only box:
+# malformed text -> BARTINT_ERR_PARSE (2) / _ARG (1); well-formed text -> accepted (a forest on a GPU box, else
+# BARTINT_ERR_NODEVICE (6): there is no CPU path).
+# ------------------------------------------------------------------------------------------------------------
+def _from_wbart_status(text, cuts, offset=0.0):
+    try:
+        f = Forest.from_wbart(text, cuts, offset)
+    except BartIntError as e:
+        return e.status
+    f.close()
+    return 0
+
+
+def test_wbart_cpp_parser_verdicts():
+    from bartint_testlib import has_gpu
+    accepted = 0 if has_gpu() else 6
+    assert _from_wbart_status(KAT_TEXT, KAT_CUTS) == accepted
+    assert _from_wbart_status(KAT_TEXT.replace("\n", "\r\n"), KAT_CUTS) == accepted          # CRLF line ends
+    assert _from_wbart_status(KAT_TEXT.rstrip("\n"), KAT_CUTS) == accepted                    # no final newline
+    assert _from_wbart_status("1 1 2\n1\n1 0 0 -1.5e-3\n", KAT_CUTS) == accepted              # exponent notation
+    rng = np.random.default_rng(2)
+    ff = synth.prior_forest(2, 5, 7, rng.random((30, 3)), None)
+    assert _from_wbart_status(ff.to_wbart_text(), ff.cut_lists()) == accepted
+    for bad in ["", "1 1 2\n2\n1 0 0 0\n2 0 0 1.0\n", "1 1 2\n3\n1 5 0 0\n2 0 0 1\n3 0 0 2\n",
+                "1 1 2\n3\n1 0 9 0\n2 0 0 1\n3 0 0 2\n", "1 1 2\n1\n2 0 0 1.0\n", "1 1 2\n2\n1 0 0 1.0\n4 0 0 1.0\n",
+                "1 1 2\n1\n1 0 0 1.0\nextra\n", "1 2 2\n1\n1 0 0 1.0\n", "1 1 2\n1\n1 0 0 abc\n", "1 1 2\n0\n",
+                "1 1 2\n2\n1 0 0 1.0\n1 0 0 2.0\n", "-1 1 2\n1\n1 0 0 1.0\n"]:
+        assert _from_wbart_status(bad, KAT_CUTS) == 2, repr(bad)
+    assert _from_wbart_status("1 1 3\n1\n1 0 0 1.0\n", KAT_CUTS) == 1                         # p != number of cut lists
+    assert _from_wbart_status("1 1\n1\n1 0 0 0.5\n", KAT_CUTS) == 1                            # header one token short -> p mismatch
