@@ -903,19 +903,24 @@ int bartint_design_step_dbarts098(const char* const* tree_strings, const double*
     cudaEvent_t built = nullptr;
     std::vector<bartint_forest*> forests;
     bartint_points *pm = nullptr, *pc = nullptr;
-    double *d_buf = nullptr, *d_block_part = nullptr;
+    double* d_buf = nullptr;
     int32_t* d_counts = nullptr;
+    cudaStream_t bst[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t bev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ready = nullptr;
+    bartint_points views[8];
+    int n_bst = 0;
     auto cleanup = [&]() {
+        for (int b = 0; b < 8; ++b)
+            if (bst[b]) cudaStreamSynchronize(bst[b]);
         if (st) cudaStreamSynchronize(st);
         cudaStreamSynchronize(nullptr);
-        if (built) cudaEventDestroy(built);
+        // (streams and events belong to the per-thread StepResources cache)
         if (pm) bartint_points_destroy(pm);
         if (pc) bartint_points_destroy(pc);
         if (d_buf) cudaFreeAsync(d_buf, nullptr);
-        if (d_block_part) cudaFreeAsync(d_block_part, nullptr);
         if (d_counts) cudaFreeAsync(d_counts, nullptr);
         for (bartint_forest* f : forests) bartint_forest_destroy(f);
-        if (st) cudaStreamDestroy(st);
         (void)cudaGetLastError();
     };
 #define DS_CUDA(call)                                                                       \
@@ -928,12 +933,36 @@ int bartint_design_step_dbarts098(const char* const* tree_strings, const double*
         rc = (call);                                   \
         if (rc != BARTINT_OK) { cleanup(); return rc; } \
     } while (0)
-    DS_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-    DS_CUDA(cudaEventCreateWithFlags(&built, cudaEventDisableTiming));
+    // streams and events are kept per host thread and device (creating them costs ~0.4 ms per call otherwise)
+    struct StepResources {
+        int device = -1;
+        cudaStream_t st = nullptr, bst[8] = {};
+        cudaEvent_t built = nullptr, ready = nullptr, bev[8] = {};
+    };
+    static thread_local StepResources res;
+    {
+        int dev_now = 0;
+        DS_CUDA(cudaGetDevice(&dev_now));
+        if (res.device != dev_now) {
+            res = StepResources{};          // (resources of another device are left to the driver's teardown)
+            cudaError_t e = cudaStreamCreateWithFlags(&res.st, cudaStreamNonBlocking);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&res.built, cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&res.ready, cudaEventDisableTiming);
+            for (int b = 0; b < 8 && e == cudaSuccess; ++b) {
+                e = cudaStreamCreateWithFlags(&res.bst[b], cudaStreamNonBlocking);
+                if (e == cudaSuccess) e = cudaEventCreateWithFlags(&res.bev[b], cudaEventDisableTiming);
+            }
+            if (e != cudaSuccess) { res = StepResources{}; cleanup(); return cuda_fail(e, "design step streams", __FILE__, __LINE__); }
+            res.device = dev_now;
+        }
+    }
+    st = res.st;
+    built = res.built;
+    ready = res.ready;
     // one device buffer: integrals S | rescaled S | mean,sd 2 | draw sums S | draw means S | mean,var 2 |
     //                    candidate means G*C | candidate M2 G*C | candidate var C | weights max(len,1)
     const size_t nS = (size_t)S, nC = (size_t)std::max<int64_t>(C, 1);
-    const size_t total = 4 * nS + 4 + 2 * (size_t)G * nC + nC + (size_t)std::max<int64_t>(weights_len, 1);
+    const size_t total = 4 * nS + 4 + 2 * (size_t)G * nC + nC + (size_t)std::max<int64_t>(weights_len, 1) + 8 * nS;
     DS_CUDA(cudaMallocAsync((void**)&d_buf, sizeof(double) * total, st));
     double* d_int = d_buf;
     double* d_int_res = d_int + nS;
@@ -945,6 +974,7 @@ int bartint_design_step_dbarts098(const char* const* tree_strings, const double*
     double* d_cm2 = d_cmean + (size_t)G * nC;
     double* d_cvar = d_cm2 + (size_t)G * nC;
     double* d_w = d_cvar + nC;
+    double* d_block_part = d_w + (size_t)std::max<int64_t>(weights_len, 1);       // [<= 8 row blocks][S] per-draw sums
     if (weights != nullptr && want_cand)
         DS_CUDA(cudaMemcpyAsync(d_w, weights, sizeof(double) * (size_t)weights_len, cudaMemcpyHostToDevice, st));
     std::vector<int32_t> counts((size_t)G);
@@ -953,8 +983,15 @@ int bartint_design_step_dbarts098(const char* const* tree_strings, const double*
     std::vector<double> t_cpu;
     auto now_ms = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return 1e3 * (double)ts.tv_sec + 1e-6 * (double)ts.tv_nsec; };
     const double t_begin = now_ms();
+    std::vector<int32_t> edges((size_t)G + 1, 0);
+    for (int k = 1; k <= G; ++k) {       // every chunk at least one draw, the last edge exactly S
+        const int64_t ideal = (int64_t)S * ((int64_t)k * k + 2 * (int64_t)k) / ((int64_t)G * G + 2 * (int64_t)G);
+        edges[(size_t)k] = (int32_t)std::min<int64_t>(std::max<int64_t>(ideal, edges[(size_t)k - 1] + 1), S - (G - k));
+    }
     for (int g = 0; g < G; ++g) {
-        const int32_t s0 = (int32_t)((int64_t)S * g / G), s1 = (int32_t)((int64_t)S * (g + 1) / G);
+        // chunk sizes ramp up (weights g + 1.5): a small first chunk gets the GPU started early, and the host, which
+        // needs less time per draw than the GPU, stays ahead on the larger later ones
+        const int32_t s0 = edges[(size_t)g], s1 = edges[(size_t)g + 1];
         counts[(size_t)g] = s1 - s0;
         bartint_forest* f = nullptr;
         if (timing) t_cpu.push_back(now_ms() - t_begin);
@@ -965,37 +1002,44 @@ int bartint_design_step_dbarts098(const char* const* tree_strings, const double*
         DS_CUDA(cudaEventRecord(built, nullptr));
         DS_CUDA(cudaStreamWaitEvent(st, built, 0));
         if (g == 0 && mc != nullptr) DS_CUDA(staged_submit_rest(mc));   // the first forest is on the bus: now the rest of X
-        bool mc_done = false;
         if (g == 0) {            // the cut points are the same for every chunk: bin once against the first sub-forest
             if (want_cand) DS_RC(bartint_staged_points(f, cand, st, &pc));
             if (want_mc && mc->n_blocks > 1) {
-                // The MC matrix arrives in row blocks: bin each block as it lands and evaluate the FIRST chunk of draws
-                // on it right away (a view of the point set), so the bus transfer hides behind the kernels as well.
+                // The MC matrix arrives in row blocks.  Each block gets its own stream: bin the block when it has landed,
+                // then evaluate chunk after chunk of draws on it (a view of the point set) as the sub-forests become
+                // available.  The GPU always has the ready (block, chunk) pairs to run, so neither the bus transfer nor
+                // the export of later chunks leaves it idle.
                 DS_RC(make_points(f, N, d, st, &pm));
-                const int B = mc->n_blocks;
-                DS_CUDA(cudaMallocAsync((void**)&d_block_part, sizeof(double) * (size_t)B * (size_t)(s1 - s0), st));
-                int used = 0;
-                for (int b = 0; b < B; ++b) {
+                DS_CUDA(cudaEventRecord(ready, st));             // d_buf and the code arrays exist from here on
+                for (int b = 0; b < mc->n_blocks; ++b) {
                     const int64_t r0 = (int64_t)b * mc->block_rows, rows = std::min(mc->block_rows, N - r0);
                     if (rows <= 0) break;
-                    const int64_t rows_padded = (b == B - 1 || r0 + mc->block_rows >= N) ? pm->Npad - r0 : mc->block_rows;
-                    DS_CUDA(cudaStreamWaitEvent(st, mc->block_done[b], 0));
+                    const int64_t rows_padded = (b == mc->n_blocks - 1 || r0 + mc->block_rows >= N) ? pm->Npad - r0 : mc->block_rows;
+                    bst[n_bst] = res.bst[n_bst];
+                    bev[n_bst] = res.bev[n_bst];
+                    cudaStream_t sb = bst[n_bst];
+                    DS_CUDA(cudaStreamWaitEvent(sb, ready, 0));
+                    DS_CUDA(cudaStreamWaitEvent(sb, built, 0));
+                    DS_CUDA(cudaStreamWaitEvent(sb, mc->block_done[b], 0));
                     DS_RC(launch_bin_points(mc->dX + r0, N, rows, d, f->dev.cut_off, f->dev.cut_val, f->max_cuts, f->route,
-                                            pm->codes + r0, pm->Npad, st, rows_padded));
+                                            pm->codes + r0, pm->Npad, sb, rows_padded));
                     if (pm->codes_pm)
-                        DS_RC(launch_repack_codes(pm->codes + r0, pm->Npad, d, pm->codes_pm + r0, st, rows_padded));
-                    bartint_points view = *pm;                       // shallow: same buffers, rows [r0, r0 + rows)
-                    view.codes = pm->codes + r0;
-                    view.codes_pm = pm->codes_pm ? pm->codes_pm + r0 : nullptr;
-                    view.N = rows;
-                    DS_RC(eval_core(f, &view, 0u, 0, s1 - s0, d_block_part + (size_t)used * (size_t)(s1 - s0), nullptr, nullptr,
-                                    nullptr, nullptr, 1.0, 0.0, 1, st));
-                    ++used;
+                        DS_RC(launch_repack_codes(pm->codes + r0, pm->Npad, d, pm->codes_pm + r0, sb, rows_padded));
+                    views[n_bst] = *pm;                              // shallow: same buffers, rows [r0, r0 + rows)
+                    views[n_bst].codes = pm->codes + r0;
+                    views[n_bst].codes_pm = pm->codes_pm ? pm->codes_pm + r0 : nullptr;
+                    views[n_bst].N = rows;
+                    ++n_bst;
                 }
-                DS_RC(launch_reduce_draw_parts(d_block_part, used, s1 - s0, d_sum + s0, st));   // fixed block order
-                mc_done = true;
             } else if (want_mc) {
                 DS_RC(bartint_staged_points(f, mc, st, &pm));
+            }
+        }
+        if (want_mc && n_bst > 0) {
+            for (int b = 0; b < n_bst; ++b) {
+                if (g > 0) DS_CUDA(cudaStreamWaitEvent(bst[b], built, 0));
+                DS_RC(eval_core(f, &views[b], 0u, 0, s1 - s0, d_block_part + (size_t)b * nS + (size_t)s0, nullptr, nullptr,
+                                nullptr, nullptr, 1.0, 0.0, 1, bst[b]));
             }
         }
         if (want_int && s0 < n_int)
@@ -1003,7 +1047,7 @@ int bartint_design_step_dbarts098(const char* const* tree_strings, const double*
         if (want_cand)
             DS_RC(eval_core(f, pc, 0u, 0, s1 - s0, nullptr, d_cmean + (size_t)g * nC, d_cm2 + (size_t)g * nC, nullptr, nullptr,
                             1.0, 0.0, 1, st));
-        if (want_mc && !mc_done)
+        if (want_mc && n_bst == 0)
             DS_RC(eval_core(f, pm, 0u, 0, s1 - s0, d_sum + s0, nullptr, nullptr, nullptr, nullptr, 1.0, 0.0, 1, st));
         if (timing) t_cpu.push_back(now_ms() - t_begin);
     }
@@ -1014,6 +1058,13 @@ int bartint_design_step_dbarts098(const char* const* tree_strings, const double*
         DS_CUDA(cudaMemcpyAsync(d_counts, counts.data(), sizeof(int32_t) * (size_t)G, cudaMemcpyHostToDevice, st));
         DS_RC(launch_merge_shards(d_cmean, d_cm2, G, d_counts, C, scale, y_min, 0, weights ? d_w : nullptr, weights_len,
                                   nullptr, d_cvar, st));
+    }
+    if (want_mc && n_bst > 0) {                                  // join the block streams; blocks added in fixed order
+        for (int b = 0; b < n_bst; ++b) {
+            DS_CUDA(cudaEventRecord(bev[b], bst[b]));
+            DS_CUDA(cudaStreamWaitEvent(st, bev[b], 0));
+        }
+        DS_RC(launch_reduce_draw_parts(d_block_part, n_bst, S, d_sum, st));
     }
     if (want_mc) {
         DS_RC(launch_finalize_draws(d_sum, S, N, scale, y_min, 0, d_dmean, st));
@@ -1027,13 +1078,9 @@ int bartint_design_step_dbarts098(const char* const* tree_strings, const double*
     DS_CUDA(cudaStreamSynchronize(st));
     if (timing) {
         fprintf(stderr, "[bartint] design step: %d chunks, total %.3f ms\n", G, now_ms() - t_begin);
-        for (int g = 0; g < G; ++g) {
-            float k_ms = 0.f, gap = 0.f;
-            if (want_mc) cudaEventElapsedTime(&k_ms, forests[(size_t)g]->ev0[0], forests[(size_t)g]->ev1[0]);
-            if (want_mc && g > 0) cudaEventElapsedTime(&gap, forests[(size_t)g - 1]->ev1[0], forests[(size_t)g]->ev0[0]);
-            fprintf(stderr, "[bartint]   chunk %d: host export %.3f -> %.3f ms, enqueue done %.3f ms; MC kernel %.3f ms, GPU gap before it %.3f ms\n",
-                    g, t_cpu[(size_t)2 * g], t_cpu[(size_t)2 * g + 1], t_cpu[(size_t)2 * g + 1], k_ms, gap);
-        }
+        for (int g = 0; g < G; ++g)
+            fprintf(stderr, "[bartint]   chunk %d: host export + enqueue %.3f -> %.3f ms\n", g, t_cpu[(size_t)2 * g],
+                    t_cpu[(size_t)2 * g + 1]);
     }
     cleanup();
 #undef DS_CUDA
