@@ -581,22 +581,47 @@ int forest_upload(bartint_forest* f) {
                 }
                 gnodes.clear();
             };
-            int bits = NB + 1;   // force a new group at the start of a draw
+            // The trees of a draw may be summed in any order, so they are bin-packed into the groups (largest trees
+            // first, fullest group that still takes the tree) and the draw's trees are PERMUTED: group g covers
+            // permuted positions [group_tree_off[g], group_tree_off[g+1]), tree_perm maps to tree ids.  (Consecutive
+            // greedy packing left ~10 % of the predicate bits unused at cfg 3.)
+            struct TBin { int nodes = 0; std::vector<int32_t> trees; };
+            std::vector<TBin> bins;
+            std::vector<std::pair<int, int32_t>> order;          // (internal nodes, tree)
+            std::vector<int32_t> stumps, walk_trees;
             for (int32_t t = 0; t < f->m; ++t) {
-                const int64_t k = (int64_t)s * f->m + t;
-                internal_nodes(k, tn);
-                const int internal = (int)tn.size();
-                if (internal > NB) {                             // WALK record holding just this tree
-                    close_group();
-                    open_group(k, TK_FLAG_WALK);
-                    bits = NB + 1;
-                    continue;
-                }
-                if (bits + internal > NB) { close_group(); open_group(k, 0u); bits = 0; }
-                gnodes.insert(gnodes.end(), tn.begin(), tn.end());
-                bits += internal;
+                internal_nodes((int64_t)s * f->m + t, tn);
+                if (tn.empty()) stumps.push_back(t);
+                else if ((int)tn.size() > NB) walk_trees.push_back(t);
+                else order.emplace_back((int)tn.size(), t);
             }
-            close_group();
+            std::stable_sort(order.begin(), order.end(), [](const auto& a, const auto& b2) { return a.first > b2.first; });
+            for (const auto& kt : order) {
+                TBin* best = nullptr;
+                for (TBin& b : bins)
+                    if (b.nodes + kt.first <= NB && (best == nullptr || b.nodes > best->nodes)) best = &b;
+                if (best == nullptr) { bins.emplace_back(); best = &bins.back(); }
+                best->nodes += kt.first;
+                best->trees.push_back(kt.second);
+            }
+            int32_t* perm = tree_perm.data() + (size_t)s * f->m;
+            int32_t pos = 0;
+            if (bins.empty() && !stumps.empty()) bins.emplace_back();      // a draw of stumps (and WALK trees) only
+            for (size_t bi = 0; bi < bins.size(); ++bi) {
+                open_group((int64_t)s * f->m + pos, 0u);
+                if (bi == 0)                                      // stumps only add a constant to the table
+                    for (int32_t t : stumps) perm[pos++] = (int32_t)((int64_t)s * f->m + t);
+                for (int32_t t : bins[bi].trees) {
+                    perm[pos++] = (int32_t)((int64_t)s * f->m + t);
+                    internal_nodes((int64_t)s * f->m + t, tn);
+                    gnodes.insert(gnodes.end(), tn.begin(), tn.end());
+                }
+                close_group();
+            }
+            for (int32_t t : walk_trees) {                        // WALK record holding just this tree
+                open_group((int64_t)s * f->m + pos, TK_FLAG_WALK);
+                perm[pos++] = (int32_t)((int64_t)s * f->m + t);
+            }
             hdr.back() |= TK_FLAG_END_DRAW;
             continue;
         }

@@ -479,8 +479,8 @@ template <int NB>
 __global__ void __launch_bounds__(256) table_leaf_kernel(
     const uint8_t* __restrict__ group_rec, const int32_t* __restrict__ draw_group_off,
     const uint2* __restrict__ nodes, const int32_t* __restrict__ tree_off, const uint8_t* __restrict__ node_bit,
-    const uint8_t* __restrict__ codes, int64_t Npad, int64_t N, int m, int draw_begin, int draw_end,
-    int32_t* __restrict__ leaf_out) {
+    const int32_t* __restrict__ tree_perm, const uint8_t* __restrict__ codes, int64_t Npad, int64_t N, int m,
+    int draw_begin, int draw_end, int32_t* __restrict__ leaf_out) {
     const int64_t quad = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int g = draw_group_off[draw_begin] + blockIdx.y;
     if (g >= draw_group_off[draw_end] || quad * 4 >= N) return;
@@ -516,7 +516,7 @@ __global__ void __launch_bounds__(256) table_leaf_kernel(
         const uint32_t idx = kk == 0 ? table_index<NB>(A, 0) : kk == 1 ? table_index<NB>(A, 1)
                            : kk == 2 ? table_index<NB>(A, 2) : table_index<NB>(A, 3);
         for (uint32_t t = 0; t < h.z; ++t) {
-            const int64_t k = (int64_t)h.y + t;
+            const int64_t k = tree_perm[(int64_t)h.y + t];
             int32_t node = tree_off[k];
             uint2 r = nodes[node];
             while ((r.x & 0xFFFFu) != LEAF_VAR) {
@@ -538,8 +538,8 @@ int launch_table_leaf(const bartint_forest* f, const bartint_points* p, int32_t 
 #define LEAF_CASE(NBV)                                                                                              \
     case NBV:                                                                                                       \
         table_leaf_kernel<NBV><<<grid, 256, 0, st>>>(f->dev.group_rec, f->dev.draw_group_off, f->dev.nodes,         \
-                                                     f->dev.tree_off, f->dev.node_bit, p->codes, p->Npad, p->N,     \
-                                                     f->m, draw_begin, draw_end, leaf_out);                         \
+                                                     f->dev.tree_off, f->dev.node_bit, f->dev.tree_perm, p->codes, \
+                                                     p->Npad, p->N, f->m, draw_begin, draw_end, leaf_out);          \
         break;
     switch (f->nb) {
         LEAF_CASE(4) LEAF_CASE(5) LEAF_CASE(6) LEAF_CASE(7) LEAF_CASE(8)
