@@ -670,19 +670,23 @@ int forest_upload(bartint_forest* f) {
             for (const Item& it : items) {
                 Bin* best = nullptr;
                 int best_key = 0;                         // lower is better: widening << 8 | (4 - fill) << 1 | side 2
+                const int exact1 = it.k << 1, exact2 = (it.k << 1) | 1;      // keys of bins this tree would fill exactly
                 if (within(it.regs, m_side1))
                     for (Bin& b : bins1) {
                         if (b.nodes + it.k > 4) continue;
                         const int key = (4 - b.nodes) << 1;
                         if (best == nullptr || key < best_key) { best = &b; best_key = key; }
+                        if (key == exact1) break;                           // nothing beats an exact fit on side 1
                     }
-                for (Bin& b : bins2) {
-                    const unsigned u = b.regs | it.regs;
-                    if (b.nodes + it.k > 4 || !side2_ok(u)) continue;
-                    const int widen = (!pair_ok(u) && pair_ok(b.regs)) ? 1 : 0;
-                    const int key = (widen << 8) | ((4 - b.nodes) << 1) | 1;
-                    if (best == nullptr || key < best_key) { best = &b; best_key = key; }
-                }
+                if (best_key != exact1 || best == nullptr)
+                    for (Bin& b : bins2) {
+                        const unsigned u = b.regs | it.regs;
+                        if (b.nodes + it.k > 4 || !side2_ok(u)) continue;
+                        const int widen = (!pair_ok(u) && pair_ok(b.regs)) ? 1 : 0;
+                        const int key = (widen << 8) | ((4 - b.nodes) << 1) | 1;
+                        if (best == nullptr || key < best_key) { best = &b; best_key = key; }
+                        if (key == exact2) break;                           // best possible key on side 2
+                    }
                 if (best == nullptr) return false;
                 best->nodes += it.k;
                 best->regs |= it.regs;
