@@ -41,11 +41,16 @@ SIGNATURES = {
     "bartint_forest_route": (C.c_int, [C.c_void_p]),
     "bartint_forest_from_wbart": (C.c_int, [C.c_char_p, C.c_int64, C.c_int32, c_int32_p, c_double_p, C.c_double,
                                             handle_p]),
+    "bartint_forest_image_size": (C.c_int, [C.c_void_p, c_int64_p, c_int64_p]),
+    "bartint_forest_pack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
+    "bartint_forest_unpack": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, handle_p]),
     "bartint_forest_info": (C.c_int, [C.c_void_p, c_int64_p]),
     "bartint_forest_export_soa": (C.c_int, [C.c_void_p, c_int64_p, c_int32_p, c_int32_p, c_int32_p, c_int32_p,
                                             c_double_p]),
     "bartint_forest_destroy": (None, [C.c_void_p]),
     "bartint_stage_matrix": (C.c_int, [c_double_p, C.c_int64, C.c_int32, C.c_int, handle_p]),
+    "bartint_finalize_integrals_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bartint_staged_flush": (C.c_int, [C.c_void_p]),
     "bartint_staged_points": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, handle_p]),
     "bartint_staged_free": (None, [C.c_void_p]),
     "bartint_points_from_host": (C.c_int, [C.c_void_p, c_double_p, C.c_int64, C.c_int32, handle_p]),

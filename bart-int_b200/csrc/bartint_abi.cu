@@ -40,7 +40,12 @@ struct DeviceGuard {
     }
 };
 
-static void free_device(DeviceForest& d) {
+static void free_device(DeviceForest& d, unsigned char* image_base = nullptr) {
+    if (image_base != nullptr) {           // an unpacked forest: one allocation holds every array
+        cudaFreeAsync(image_base, nullptr);
+        d = DeviceForest{};
+        return;
+    }
     void* ptrs[] = {d.nodes, d.tree_off, d.tree_leaf_off, d.leaf_mu, d.cut_off, d.cut_val, d.node_bit, d.tree_perm, d.group_tree_off,
                     d.draw_group_off, d.group_rec};
     for (void* q : ptrs)
@@ -233,6 +238,8 @@ int bartint_forest_info(const bartint_forest* f, int64_t info[12]) {
 int bartint_forest_export_soa(const bartint_forest* f, int64_t* tree_node_offset, int32_t* split_var,
                               int32_t* split_cut_idx, int32_t* left, int32_t* right, double* leaf_mu) {
     BI_REQUIRE(f != nullptr, BARTINT_ERR_ARG, "forest is NULL");
+    BI_REQUIRE(f->image_base == nullptr, BARTINT_ERR_UNSUPPORTED,
+               "a forest restored from a device image keeps no host copy of the trees");
     const size_t nn = (size_t)f->n_nodes;
     if (tree_node_offset) memcpy(tree_node_offset, f->tree_off.data(), f->tree_off.size() * sizeof(int64_t));
     if (split_var && nn) memcpy(split_var, f->var.data(), nn * sizeof(int32_t));
@@ -249,7 +256,8 @@ void bartint_forest_destroy(bartint_forest* f) {
         DeviceGuard g(f->device);
         // the buffers are freed in default-stream order: make that stream wait for evaluations on other streams
         if (f->ev_last && f->ev_last_set) cudaStreamWaitEvent(nullptr, f->ev_last, 0);
-        free_device(f->dev);
+        free_device(f->dev, f->image_base);
+        f->image_base = nullptr;
         for (int k = 0; k < 2; ++k) {
             if (f->ev0[k]) cudaEventDestroy(f->ev0[k]);
             if (f->ev1[k]) cudaEventDestroy(f->ev1[k]);
@@ -372,6 +380,13 @@ int bartint_stage_matrix(const double* X, int64_t N, int32_t d, int device, bart
     if (e == cudaSuccess) e = cudaEventRecord(s->done, s->copy_stream);
     if (e != cudaSuccess) { bartint_staged_free(s); return cuda_fail(e, "bartint_stage_matrix", __FILE__, __LINE__); }
     *out = s;
+    return BARTINT_OK;
+}
+
+int bartint_staged_flush(bartint_staged* s) {
+    BI_REQUIRE(s != nullptr, BARTINT_ERR_ARG, "NULL argument");
+    DeviceGuard g(s->device);
+    BI_CUDA(staged_submit_rest(s));
     return BARTINT_OK;
 }
 
@@ -818,6 +833,14 @@ int bartint_exact_integrals(const bartint_forest* f, int32_t measure, const doub
     return rc;
 }
 
+int bartint_finalize_integrals_device(const bartint_forest* f, const double* d_integrals_scaled, int32_t n,
+                                      double* d_rescaled, double* d_mean_sd, void* stream) {
+    BI_REQUIRE(f != nullptr && n >= 1, BARTINT_ERR_ARG, "bad arguments");
+    BI_REQUIRE(d_integrals_scaled != nullptr && d_mean_sd != nullptr, BARTINT_ERR_ARG, "NULL device pointer");
+    DeviceGuard g(f->device);
+    return launch_finalize_integrals(d_integrals_scaled, n, f->y_min, f->y_max, d_rescaled, d_mean_sd, (cudaStream_t)stream);
+}
+
 int bartint_finalize_integrals(const bartint_forest* f, const double* integrals_scaled, int32_t n, double* rescaled_out,
                                double* mean_out, double* sd_out) {
     BI_REQUIRE(f != nullptr && n >= 0, BARTINT_ERR_ARG, "bad arguments");
@@ -860,6 +883,167 @@ int bartint_last_eval_profile(const bartint_forest* f, int32_t with_moments, flo
             BI_CUDA(cudaEventElapsedTime(kernel_ms, f->ev0[slot], f->ev1[slot]));
         }
     }
+    return BARTINT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Device image of a forest: lets one process (one GPU) export a share of the draws and replicate the finished
+// sub-forest to the other ranks with a single NCCL all-gather / broadcast, instead of every rank parsing the whole
+// posterior.  host header = fixed fields + draw_group_off + cut offsets/values; device blob = the device arrays,
+// each padded to 256 B, in the order of kImageArrays.
+// ------------------------------------------------------------------------------------------------------------
+namespace {
+struct ImageHeader {
+    uint32_t magic, version;
+    int32_t S, m, d, max_depth, max_internal, max_cuts, route, table_ok, gather, g_regs, nb, reserved;
+    int64_t n_nodes, n_leaves, n_groups, n_cuts, device_bytes;
+    double y_min, y_max;
+    int64_t bytes[11];       // device array sizes (0 = absent), order of image_arrays()
+};
+constexpr uint32_t kImageMagic = 0x42494E54u;   // "BINT"
+
+inline int64_t pad256(int64_t b) { return (b + 255) / 256 * 256; }
+
+// the device arrays of a forest with their sizes in bytes
+inline void image_arrays(const bartint_forest* f, void* const** ptrs_out, int64_t sizes[11], void** slots[11], DeviceForest* d) {
+    (void)ptrs_out;
+    const int64_t nt = (int64_t)f->S * f->m;
+    slots[0] = (void**)&d->nodes;          sizes[0] = f->n_nodes * 8;
+    slots[1] = (void**)&d->tree_off;       sizes[1] = (nt + 1) * 4;
+    slots[2] = (void**)&d->tree_leaf_off;  sizes[2] = (nt + 1) * 4;
+    slots[3] = (void**)&d->leaf_mu;        sizes[3] = f->n_leaves * 8;
+    slots[4] = (void**)&d->cut_off;        sizes[4] = ((int64_t)f->d + 1) * 4;
+    slots[5] = (void**)&d->cut_val;        sizes[5] = (int64_t)f->cut_val.size() * 8;
+    slots[6] = (void**)&d->node_bit;       sizes[6] = f->table_ok ? f->n_nodes : 0;
+    slots[7] = (void**)&d->tree_perm;      sizes[7] = f->table_ok ? nt * 4 : 0;
+    slots[8] = (void**)&d->group_tree_off; sizes[8] = f->table_ok ? (f->n_groups + 1) * 4 : 0;
+    slots[9] = (void**)&d->draw_group_off; sizes[9] = f->table_ok ? ((int64_t)f->S + 1) * 4 : 0;
+    slots[10] = (void**)&d->group_rec;     sizes[10] = f->table_ok ? f->n_groups * (int64_t)fast_rec_bytes(f) + 16 : 0;
+}
+}  // namespace
+
+int bartint_forest_image_size(const bartint_forest* f, int64_t* host_bytes, int64_t* device_bytes) {
+    BI_REQUIRE(f != nullptr && host_bytes != nullptr && device_bytes != nullptr, BARTINT_ERR_ARG, "NULL argument");
+    int64_t sizes[11];
+    void** slots[11];
+    DeviceForest tmp = f->dev;
+    image_arrays(f, nullptr, sizes, slots, &tmp);
+    int64_t total = 0;
+    for (int k = 0; k < 11; ++k) total += pad256(sizes[k]);
+    *device_bytes = std::max<int64_t>(total, 256);
+    *host_bytes = (int64_t)sizeof(ImageHeader) + ((int64_t)f->S + 1) * 4 + ((int64_t)f->d + 1) * 4 + (int64_t)f->cut_val.size() * 8;
+    return BARTINT_OK;
+}
+
+int bartint_forest_pack(const bartint_forest* f, void* host_header, int64_t host_bytes, void* d_blob, int64_t device_bytes,
+                        void* stream) {
+    BI_REQUIRE(f != nullptr && host_header != nullptr && d_blob != nullptr, BARTINT_ERR_ARG, "NULL argument");
+    int64_t hb = 0, db = 0;
+    int rc = bartint_forest_image_size(f, &hb, &db);
+    if (rc) return rc;
+    BI_REQUIRE(host_bytes >= hb && device_bytes >= db, BARTINT_ERR_ARG, "image buffers too small (need %lld + %lld bytes)",
+               (long long)hb, (long long)db);
+    DeviceGuard g(f->device);
+    ImageHeader h{};
+    h.magic = kImageMagic; h.version = (uint32_t)bartint_version();
+    h.S = f->S; h.m = f->m; h.d = f->d; h.max_depth = f->max_depth; h.max_internal = f->max_internal; h.max_cuts = f->max_cuts;
+    h.route = f->route; h.table_ok = f->table_ok ? 1 : 0; h.gather = f->gather ? 1 : 0; h.g_regs = f->g_regs; h.nb = f->nb;
+    h.n_nodes = f->n_nodes; h.n_leaves = f->n_leaves; h.n_groups = f->n_groups; h.n_cuts = (int64_t)f->cut_val.size();
+    h.device_bytes = db; h.y_min = f->y_min; h.y_max = f->y_max;
+    void** slots[11];
+    DeviceForest tmp = f->dev;
+    image_arrays(f, nullptr, h.bytes, slots, &tmp);
+    unsigned char* hp = (unsigned char*)host_header;
+    memcpy(hp, &h, sizeof(h)); hp += sizeof(h);
+    std::vector<int32_t> dgo((size_t)f->S + 1, 0);
+    if (f->draw_group_off.size() == dgo.size()) dgo = f->draw_group_off;
+    memcpy(hp, dgo.data(), dgo.size() * 4); hp += dgo.size() * 4;
+    memcpy(hp, f->cut_off.data(), ((size_t)f->d + 1) * 4); hp += ((size_t)f->d + 1) * 4;
+    if (!f->cut_val.empty()) memcpy(hp, f->cut_val.data(), f->cut_val.size() * 8);
+    // the forest's uploads ran on the default stream: order the copies after them, then copy on the caller's stream
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaEvent_t ev = nullptr;
+    BI_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    cudaError_t e = cudaEventRecord(ev, nullptr);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(st, ev, 0);
+    int64_t off = 0;
+    for (int k = 0; k < 11 && e == cudaSuccess; ++k) {
+        if (h.bytes[k] > 0)
+            e = cudaMemcpyAsync((unsigned char*)d_blob + off, *slots[k], (size_t)h.bytes[k], cudaMemcpyDeviceToDevice, st);
+        off += pad256(h.bytes[k]);
+    }
+    cudaEventDestroy(ev);
+    if (e != cudaSuccess) return cuda_fail(e, "bartint_forest_pack", __FILE__, __LINE__);
+    return BARTINT_OK;
+}
+
+int bartint_forest_unpack(const void* host_header, int64_t host_bytes, const void* d_blob, int64_t device_bytes, void* stream,
+                          bartint_forest** out) {
+    BI_REQUIRE(out != nullptr, BARTINT_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    BI_REQUIRE(host_header != nullptr && d_blob != nullptr && host_bytes >= (int64_t)sizeof(ImageHeader), BARTINT_ERR_ARG,
+               "bad forest image");
+    ImageHeader h;
+    memcpy(&h, host_header, sizeof(h));
+    BI_REQUIRE(h.magic == kImageMagic && h.version == (uint32_t)bartint_version(), BARTINT_ERR_ARG,
+               "not a forest image of this library version");
+    BI_REQUIRE(h.S >= 0 && h.m >= 0 && h.d >= 0 && h.n_cuts >= 0 && h.device_bytes <= device_bytes, BARTINT_ERR_ARG,
+               "inconsistent forest image");
+    const int64_t need = (int64_t)sizeof(ImageHeader) + ((int64_t)h.S + 1) * 4 + ((int64_t)h.d + 1) * 4 + h.n_cuts * 8;
+    BI_REQUIRE(host_bytes >= need, BARTINT_ERR_ARG, "forest image header truncated");
+    int rc = check_device();
+    if (rc) return rc;
+    bartint_forest* f = new (std::nothrow) bartint_forest();
+    BI_REQUIRE(f != nullptr, BARTINT_ERR_NOMEM, "out of host memory");
+    f->S = h.S; f->m = h.m; f->d = h.d; f->max_depth = h.max_depth; f->max_internal = h.max_internal; f->max_cuts = h.max_cuts;
+    f->route = h.route; f->table_ok = h.table_ok != 0; f->gather = h.gather != 0; f->g_regs = h.g_regs; f->nb = h.nb;
+    f->n_nodes = h.n_nodes; f->n_leaves = h.n_leaves; f->n_groups = h.n_groups; f->y_min = h.y_min; f->y_max = h.y_max;
+    const unsigned char* hp = (const unsigned char*)host_header + sizeof(ImageHeader);
+    f->draw_group_off.resize((size_t)h.S + 1);
+    memcpy(f->draw_group_off.data(), hp, ((size_t)h.S + 1) * 4); hp += ((size_t)h.S + 1) * 4;
+    f->cut_off.resize((size_t)h.d + 1);
+    memcpy(f->cut_off.data(), hp, ((size_t)h.d + 1) * 4); hp += ((size_t)h.d + 1) * 4;
+    f->cut_val.resize((size_t)h.n_cuts);
+    if (h.n_cuts) memcpy(f->cut_val.data(), hp, (size_t)h.n_cuts * 8);
+    cudaError_t e = cudaGetDevice(&f->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (e == cudaSuccess) {                 // same allocator policy as finish_forest: keep freed blocks cached
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, f->device) == cudaSuccess) {
+            uint64_t keep = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        (void)cudaGetLastError();
+    }
+    // one allocation holds every array (image_base); the DeviceForest pointers point into it
+    if (e == cudaSuccess) e = cudaMallocAsync((void**)&f->image_base, (size_t)std::max<int64_t>(h.device_bytes, 256), st);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(f->image_base, d_blob, (size_t)h.device_bytes, cudaMemcpyDeviceToDevice, st);
+    if (e == cudaSuccess) {
+        int64_t sizes[11];
+        void** slots[11];
+        image_arrays(f, nullptr, sizes, slots, &f->dev);
+        int64_t off = 0;
+        for (int k = 0; k < 11; ++k) {
+            if (sizes[k] != h.bytes[k]) { e = cudaErrorInvalidValue; break; }
+            *slots[k] = h.bytes[k] > 0 ? (void*)(f->image_base + off) : nullptr;
+            off += pad256(h.bytes[k]);
+        }
+    }
+    for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
+        e = cudaEventCreate(&f->ev0[k]);
+        if (e == cudaSuccess) e = cudaEventCreate(&f->ev1[k]);
+    }
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&f->ev_last, cudaEventDisableTiming);
+    // later users may run on any stream: the image must be complete before this call returns control to them
+    if (e == cudaSuccess) e = cudaEventRecord(f->ev_last, st);
+    if (e == cudaSuccess) { f->ev_last_set = true; e = cudaStreamSynchronize(st); }
+    if (e != cudaSuccess) {
+        rc = cuda_fail(e, "bartint_forest_unpack", __FILE__, __LINE__);
+        bartint_forest_destroy(f);
+        return rc;
+    }
+    *out = f;
     return BARTINT_OK;
 }
 

@@ -112,6 +112,7 @@ struct bartint_forest {
     int64_t n_groups = 0;
     std::vector<int32_t> draw_group_off;  // host copy, S+1
     bartint::DeviceForest dev;
+    unsigned char* image_base = nullptr;  // forests restored by bartint_forest_unpack: the one allocation behind `dev`
     // profile of the last evaluation
     // slot 0: evaluations producing per-draw sums only; slot 1: evaluations with per-point moments / full output
     cudaEvent_t ev0[2] = {nullptr, nullptr}, ev1[2] = {nullptr, nullptr};

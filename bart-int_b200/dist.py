@@ -131,3 +131,101 @@ def draw_sharded_candidate_var(forest, pts, weights=None, group=None, scaled=Fal
     forest.merge_moments_device(counts, means.data_ptr(), m2s.data_ptr(), pts.N, w_ptr, w_len, 0, var.data_ptr(),
                                 scaled=scaled, stream=st)
     return var
+
+
+# ---------------------------------------------------------------------------------------------
+# draw-sharded EXPORT + replicated forest: every rank parses only its share of the posterior
+# ---------------------------------------------------------------------------------------------
+def replicate_forest(local_forest, group=None, stream=None):
+    """All-gather the device images of the ranks' local sub-forests (bartint_forest_pack / _unpack): returns the list of
+    `world` forests in rank order; entry `rank` is local_forest itself.  MB-sized payload over NVLink instead of every
+    rank exporting the whole posterior on its share of the host cores."""
+    from .forest import Forest
+    rank, world = world_info(group)
+    if world == 1:
+        return [local_forest]
+    dev = torch.device("cuda", torch.cuda.current_device())
+    st = torch.cuda.current_stream().cuda_stream if stream is None else stream
+    hb, db = local_forest.image_size()
+    sizes = all_gather_rows(torch.tensor([hb, db], dtype=torch.int64, device=dev), group).cpu().numpy()
+    max_hb, max_db = int(sizes[:, 0].max()), int(sizes[:, 1].max())
+    blob = torch.empty(max_db, dtype=torch.uint8, device=dev)
+    header = local_forest.pack(blob.data_ptr(), db, stream=st)
+    hdr = torch.zeros(max_hb, dtype=torch.uint8)
+    hdr[:hb] = torch.from_numpy(header)
+    all_hdr = all_gather_rows(hdr.to(dev), group).cpu().numpy()
+    all_blob = all_gather_rows(blob, group)
+    out = []
+    for r in range(world):
+        if r == rank:
+            out.append(local_forest)
+        else:
+            out.append(Forest.unpack(all_hdr[r, :int(sizes[r, 0])], all_blob[r].data_ptr(), int(sizes[r, 1]), stream=st))
+    return out
+
+
+def sharded_design_step(tree_strings, tree_fits, x_train, cut_lists, y_min, y_max, mc_local, candidates, weights=None,
+                        measure="uniform", group=None, n_total=None):
+    """One sequential-design step on `world` ranks from the dbarts state every rank holds (the multi-GPU counterpart of
+    design_step_dbarts):
+      export      draw-sharded: rank r parses draws [lo_r, hi_r) only, then the finished sub-forests are all-gathered
+      integrals   own draws, all-gathered                                       (BARTInt.R:259-262)
+      candidates  own draws on all candidates, (n, mean, M2) all-gathered, Chan merge   (BARTInt.R:312-314)
+      MC points   point-sharded: own rows (StagedMatrix) on ALL draws, per-draw sums all-gathered (bartMean.R:74-82)
+    n_total: the global number of MC rows, if the caller knows it (saves one exchange + host wait).
+    Returns a dict of host arrays like design_step_dbarts (identical on every rank)."""
+    from .forest import Forest, WireStrings
+    rank, world = world_info(group)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    st = torch.cuda.current_stream().cuda_stream
+    wire = tree_strings if isinstance(tree_strings, WireStrings) else WireStrings(tree_strings)
+    S, m = wire.S, wire.m
+    x_train = np.asarray(x_train, np.float64)
+    n = x_train.shape[0]
+    fits = np.asarray(tree_fits, np.float64).reshape(n, m, S)
+    bounds = [shard_range(S, world, r) for r in range(world)]
+    lo, hi = bounds[rank]
+    mc_local.flush()          # this rank's forest upload is ~1 ms away: let the whole matrix travel meanwhile
+    f_loc = Forest.from_dbarts(wire.slice_draws(lo, hi), fits[:, :, lo:hi], x_train, cut_lists, y_min, y_max)
+    # Exchange the sub-forest images FIRST, on an otherwise idle GPU: a collective queued behind the evaluation
+    # kernel cannot start until that kernel's CTAs (resident for its whole duration) leave the SMs -- measured 4-9 ms
+    # for the exchange when it was overlapped with the own-draw evaluation, 0.8 ms alone.
+    forests = replicate_forest(f_loc, group, stream=st)
+    # own draws: exact integrals + candidate moments (small)
+    integ = torch.zeros(S, dtype=torch.float64, device=dev)
+    f_loc.exact_integrals_device(integ[lo:hi].data_ptr(), measure, stream=st)
+    C_ = candidates.N
+    pc = candidates.points(f_loc, stream=st)
+    mean = torch.zeros(C_, dtype=torch.float64, device=dev)
+    m2 = torch.zeros(C_, dtype=torch.float64, device=dev)
+    f_loc.eval_device(pc, d_point_mean=mean.data_ptr(), d_point_m2=m2.data_ptr(), stream=st)
+    # MC points: own rows on every rank's draws (point-sharded)
+    pm = mc_local.points(f_loc, stream=st)
+    sums = torch.empty(S, dtype=torch.float64, device=dev)
+    for r, (a, b) in enumerate(bounds):
+        if b > a:
+            forests[r].eval_device(pm, d_draw_sum=sums[a:b].data_ptr(), stream=st)
+    if n_total is None:       # costs a device->host wait behind the evaluation; pass n_total when it is known
+        n_total = int(all_gather_rows(torch.tensor([pm.N], dtype=torch.int64, device=dev), group).sum().item()) if world > 1 else pm.N
+    total, _ = allreduce_draw_sums(sums, pm.N, group, n_total=n_total)
+    draw_mean = torch.empty(S, dtype=torch.float64, device=dev)
+    mv = torch.empty(2, dtype=torch.float64, device=dev)
+    f_loc.finalize_draws_device(total.data_ptr(), S, n_total, draw_mean.data_ptr(), mv.data_ptr(), stream=st)
+    # candidates: Chan merge of the ranks' moments in rank order
+    counts, means, m2s = gather_moments(mean, m2, hi - lo, group, counts=[b - a for a, b in bounds])
+    var = torch.empty(C_, dtype=torch.float64, device=dev)
+    w = None if weights is None else torch.as_tensor(np.atleast_1d(np.asarray(weights, np.float64)), device=dev)
+    f_loc.merge_moments_device(counts, means.data_ptr(), m2s.data_ptr(), C_, 0 if w is None else w.data_ptr(),
+                               0 if w is None else w.numel(), 0, var.data_ptr(), stream=st)
+    # integrals: each rank filled its own range; the rest is zero, so a rank-ordered sum of the gathered rows is a gather
+    integ_all = ordered_sum(all_gather_rows(integ, group)) if world > 1 else integ
+    integ_res = torch.empty(S, dtype=torch.float64, device=dev)
+    integ_ms = torch.empty(2, dtype=torch.float64, device=dev)
+    f_loc.finalize_integrals_device(integ_all.data_ptr(), S, integ_res.data_ptr(), integ_ms.data_ptr(), stream=st)
+    host = torch.cat([integ_all, integ_ms, var, draw_mean, mv]).cpu().numpy()        # one device->host copy
+    out = {"integrals": host[:S], "integral_mean_sd": host[S:S + 2], "cand_var": host[S + 2:S + 2 + C_],
+           "draw_mean": host[S + 2 + C_:2 * S + 2 + C_], "draw_mean_var": host[2 * S + 2 + C_:]}
+    pm.close(); pc.close()
+    for r, f in enumerate(forests):
+        f.close()
+    return out

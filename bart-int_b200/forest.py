@@ -152,6 +152,17 @@ class WireStrings:
         self.array = (C.c_char_p * max(len(self._enc), 1))(*self._enc)
 
 
+    def slice_draws(self, lo: int, hi: int) -> "WireStrings":
+        """The strings of draws [lo, hi) as a view (no re-encoding): what a rank passes when it exports its share."""
+        v = WireStrings.__new__(WireStrings)
+        v.m, v.S = self.m, hi - lo
+        v._enc = self._enc                                   # keeps the byte strings alive
+        n = max((hi - lo) * self.m, 1)
+        v.array = (C.c_char_p * n).from_address(C.addressof(self.array) + lo * self.m * C.sizeof(C.c_char_p))
+        v._parent = self
+        return v
+
+
 class StagedMatrix:
     """A host matrix on its way to the device (asynchronous copy started at construction), independent of any forest:
     the candidate matrix / fullData exist before the model is fitted, so their transfer can overlap the export."""
@@ -163,6 +174,10 @@ class StagedMatrix:
         h = C.c_void_p()
         _check(_lib.load().bartint_stage_matrix(_p(self._X, C.c_double), self.N, self.d, device, C.byref(h)))
         self._h = h
+
+    def flush(self) -> None:
+        """Put the remaining row blocks on the bus now (by default only the first block travels until a consumer asks)."""
+        _check(_lib.load().bartint_staged_flush(self._h))
 
     def points(self, forest: "Forest", stream: int = 0) -> "Points":
         h = C.c_void_p()
@@ -279,6 +294,31 @@ class Forest:
         f.y_min, f.y_max = float(y_min), float(y_max)
         f._cut_offsets, f._cut_values = cut_offsets, cut_values
         return f
+
+    # ---- device image (replication between ranks) ----
+    def image_size(self) -> tuple[int, int]:
+        """(host header bytes, device blob bytes) of this forest's device image."""
+        hb, db = C.c_int64(0), C.c_int64(0)
+        _check(_lib.load().bartint_forest_image_size(self._h, C.byref(hb), C.byref(db)))
+        return int(hb.value), int(db.value)
+
+    def pack(self, d_blob: int, device_bytes: int, stream: int = 0) -> np.ndarray:
+        """Copy the device arrays into the device buffer at address d_blob (asynchronously on `stream`) and return the
+        host header (uint8 array).  Together they rebuild the forest elsewhere with Forest.unpack."""
+        hb, _ = self.image_size()
+        header = np.zeros(hb, np.uint8)
+        _check(_lib.load().bartint_forest_pack(self._h, header.ctypes.data_as(C.c_void_p), hb, C.c_void_p(d_blob),
+                                               int(device_bytes), C.c_void_p(stream)))
+        return header
+
+    @classmethod
+    def unpack(cls, header: np.ndarray, d_blob: int, device_bytes: int, stream: int = 0) -> "Forest":
+        """Forest on the current device from a (header, device blob) image made by pack() -- possibly on another rank."""
+        header = np.ascontiguousarray(header, np.uint8)
+        h = C.c_void_p()
+        _check(_lib.load().bartint_forest_unpack(header.ctypes.data_as(C.c_void_p), header.nbytes, C.c_void_p(d_blob),
+                                                 int(device_bytes), C.c_void_p(stream), C.byref(h)))
+        return cls(h.value)
 
     def export_soa(self) -> dict:
         n = self.n_nodes
@@ -424,6 +464,12 @@ class Forest:
         _check(_lib.load().bartint_exact_integrals(self._h, _lib.MEASURES[measure], _p(lo_a, C.c_double),
                                                    _p(hi_a, C.c_double), n, _p(out, C.c_double)))
         return out
+
+    def finalize_integrals_device(self, d_integrals: int, n: int, d_rescaled: int, d_mean_sd: int, stream: int = 0) -> None:
+        """BARTInt.R:260-262 on device buffers (asynchronous): rescale, mean, sd."""
+        _check(_lib.load().bartint_finalize_integrals_device(self._h, C.c_void_p(d_integrals), int(n),
+                                                             C.c_void_p(d_rescaled or None), C.c_void_p(d_mean_sd),
+                                                             C.c_void_p(stream)))
 
     def finalize_integrals(self, integrals_scaled):
         x = np.ascontiguousarray(integrals_scaled, np.float64)

@@ -111,6 +111,19 @@ int bartint_forest_route(const bartint_forest* f);
 int bartint_forest_from_wbart(const char* trees_text, int64_t text_len, int32_t d, const int32_t* cut_offsets,
                               const double* cut_values, double offset, bartint_forest** out);
 
+/* Device image of a forest, for replicating it between processes (one process per GPU): each rank exports 1/G of the
+ * draws with bartint_forest_from_dbarts098 on its slice, packs the finished sub-forest, and the images are exchanged
+ * with one NCCL all-gather / broadcast instead of every rank parsing the whole posterior.
+ * pack: host_header (bartint_forest_image_size's host_bytes) is filled at once, the device arrays are copied into
+ * d_blob (device_bytes, a DEVICE pointer) asynchronously on `stream`.  unpack builds a forest on the current device
+ * from such a pair (the blob is copied, not adopted; blocks until the copy is done).  An unpacked forest evaluates,
+ * integrates and reports info like any other; only bartint_forest_export_soa is unsupported (no host copy). */
+int bartint_forest_image_size(const bartint_forest* f, int64_t* host_bytes, int64_t* device_bytes);
+int bartint_forest_pack(const bartint_forest* f, void* host_header, int64_t host_bytes, void* d_blob, int64_t device_bytes,
+                        void* stream);
+int bartint_forest_unpack(const void* host_header, int64_t host_bytes, const void* d_blob, int64_t device_bytes, void* stream,
+                          bartint_forest** out);
+
 /* info[0..11] = S, m, d, n_nodes, n_leaves, max_depth, max_internal_nodes_per_tree,
  *               fast_kernel_ok (0/1), n_groups, table_bits, fast kernel kind (0 none, 1 table, 2 gather),
  *               gather code words per point */
@@ -136,6 +149,7 @@ void bartint_forest_destroy(bartint_forest* f);
  * (bartint_staged_points / bartint_design_step_dbarts098 returned) or freed. */
 typedef struct bartint_staged bartint_staged;
 int bartint_stage_matrix(const double* X, int64_t N, int32_t d, int device, bartint_staged** out);
+int bartint_staged_flush(bartint_staged* s);   /* put the remaining row blocks on the bus now (no forest upload is due soon) */
 int bartint_staged_points(const bartint_forest* f, const bartint_staged* s, void* stream, bartint_points** out);
 void bartint_staged_free(bartint_staged* s);
 
@@ -238,6 +252,9 @@ int bartint_exact_integrals_device(const bartint_forest* f, int32_t measure, con
 
 /* BARTInt.R:260-262 / 290-292:  integrals <- (integrals+0.5)*(ymax-ymin)+ymin; mean; sd (n-1).
  * Runs on the device the forest lives on. rescaled_out may be NULL. */
+/* device-pointer variant (asynchronous on `stream`); d_rescaled may be NULL */
+int bartint_finalize_integrals_device(const bartint_forest* f, const double* d_integrals_scaled, int32_t n,
+                                      double* d_rescaled, double* d_mean_sd, void* stream);
 int bartint_finalize_integrals(const bartint_forest* f, const double* integrals_scaled, int32_t n,
                                double* rescaled_out, double* mean_out, double* sd_out);
 

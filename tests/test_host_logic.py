@@ -65,3 +65,14 @@ def test_adversarial_generators_are_valid_trees():
         nodes = np.diff(ff.tree_offset)
         assert (nodes % 2 == 1).all()
         assert (ff.var < 3).all() and (ff.cut < 20).all()
+
+
+def test_wire_strings_slice_is_a_view():
+    import ctypes as C
+    from bartint_b200 import WireStrings
+    strings = np.array([[f"t{t}s{s}" for s in range(5)] for t in range(3)], dtype=object)      # [m=3, S=5]
+    w = WireStrings(strings)
+    v = w.slice_draws(1, 4)
+    assert (v.m, v.S) == (3, 3)
+    assert [v.array[k] for k in range(9)] == [f"t{t}s{s}".encode() for s in range(1, 4) for t in range(3)]
+    assert C.addressof(v.array) == C.addressof(w.array) + 3 * C.sizeof(C.c_char_p)
