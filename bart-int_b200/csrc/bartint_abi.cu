@@ -293,6 +293,16 @@ static int make_points(const bartint_forest* f, int64_t N, int32_t d, cudaStream
     return BARTINT_OK;
 }
 
+// The one-pass K0 of gather forests fills only the packed records; the feature-major rows are produced the first time
+// a consumer needs them (walk kernel, table kernel, leaf decoding, bartint_points_codes), on that consumer's stream.
+static int ensure_codes(const bartint_points* p, cudaStream_t st) {
+    if (p->codes_valid) return BARTINT_OK;
+    BI_REQUIRE(p->codes != nullptr && p->codes_pm != nullptr, BARTINT_ERR_ARG, "internal: point set has no codes");
+    int rc = launch_unpack_codes(p->codes_pm, p->Npad, p->d, p->codes, st);
+    if (rc == BARTINT_OK) p->codes_valid = true;
+    return rc;
+}
+
 int bartint_points_from_device(const bartint_forest* f, const double* dX, int64_t N, int32_t d, int64_t ld,
                                void* stream, bartint_points** out) {
     BI_REQUIRE(N * d == 0 || dX != nullptr, BARTINT_ERR_ARG, "X is NULL");
@@ -300,13 +310,20 @@ int bartint_points_from_device(const bartint_forest* f, const double* dX, int64_
     int rc = make_points(f, N, d, (cudaStream_t)stream, out);
     if (rc) return rc;
     DeviceGuard g(f->device);
-    rc = launch_bin_points(dX, ld, N, d, f->dev.cut_off, f->dev.cut_val, f->max_cuts, f->route, (*out)->codes,
-                           (*out)->Npad, (cudaStream_t)stream);
-    // (one-pass kernels writing both layouts were tried twice -- one point per thread, then four with a PRMT byte
-    //  transpose -- and were slower at every size (tools/k0_sweep.py: 1.39 vs 1.28 ms at 5e7 points): binning is bound
-    //  by its shared-memory cut-table probes, and the pass over all variables leaves fewer, fatter threads)
-    if (rc == BARTINT_OK && (*out)->codes_pm)
-        rc = launch_repack_codes((*out)->codes, (*out)->Npad, d, (*out)->codes_pm, (cudaStream_t)stream);
+    static const bool split_k0 = [] { const char* e = std::getenv("BARTINT_K0"); return e && std::strcmp(e, "split") == 0; }();
+    if ((*out)->codes_pm && d >= 1 && !split_k0) {
+        // gather forests: one pass, fp64 matrix -> packed records; feature-major rows only on demand (ensure_codes).
+        // (Two earlier one-pass kernels that wrote BOTH layouts lost to bin + repack: while the cut-table probes
+        //  bounded the binning, and because 4 points x all variables per thread made a few waves of long CTAs.)
+        rc = launch_bin_pack_points(dX, ld, N, d, f->dev.cut_off, f->dev.cut_val, f->max_cuts, f->route, (*out)->codes_pm,
+                                    (*out)->Npad, (cudaStream_t)stream);
+        (*out)->codes_valid = false;
+    } else {                                          // table forests, or BARTINT_K0=split (A/B timing): bin, then repack
+        rc = launch_bin_points(dX, ld, N, d, f->dev.cut_off, f->dev.cut_val, f->max_cuts, f->route, (*out)->codes,
+                               (*out)->Npad, (cudaStream_t)stream);
+        if (rc == BARTINT_OK && (*out)->codes_pm)
+            rc = launch_repack_codes((*out)->codes, (*out)->Npad, d, (*out)->codes_pm, (cudaStream_t)stream);
+    }
     if (rc) { bartint_points_destroy(*out); *out = nullptr; }
     return rc;
 }
@@ -455,6 +472,8 @@ int64_t bartint_points_count(const bartint_points* p) { return p ? p->N : -1; }
 int bartint_points_codes(const bartint_points* p, uint8_t* codes_out) {
     BI_REQUIRE(p != nullptr && (codes_out != nullptr || p->N * p->d == 0), BARTINT_ERR_ARG, "NULL argument");
     DeviceGuard g(p->device);
+    int rc = ensure_codes(p, nullptr);
+    if (rc) return rc;
     BI_CUDA(cudaDeviceSynchronize());
     if (p->N > 0 && p->d > 0)
         BI_CUDA(cudaMemcpy2D(codes_out, (size_t)p->N, p->codes, (size_t)p->Npad, (size_t)p->N, (size_t)p->d,
@@ -494,6 +513,10 @@ static int eval_core(const bartint_forest* f, const bartint_points* p, uint32_t 
     const bool want_mom = d_point_mean != nullptr && d_point_m2 != nullptr;
     if (d_leaf != nullptr) flags |= BARTINT_FORCE_WALK;
     EvalPlan plan = make_plan(f, p, flags, draw_begin, draw_end, want_mom, d_full != nullptr);
+    if (!plan.use_gather) {                   // walk / table kernels read the feature-major rows
+        int rc0 = ensure_codes(p, st);
+        if (rc0) return rc0;
+    }
     f->last_used_table[slot] = plan.use_table ? 1 : 0;
     double *draw_part = nullptr, *pt_mean = nullptr, *pt_m2 = nullptr;
     BI_CUDA(cudaMallocAsync((void**)&draw_part, sizeof(double) * (size_t)plan.n_tiles * (size_t)ndraws, st));
@@ -750,8 +773,10 @@ int bartint_leaf_indices(const bartint_forest* f, const bartint_points* p, int32
     int32_t* d_leaf = nullptr;
     BI_CUDA(cudaMallocAsync((void**)&d_leaf, sizeof(int32_t) * (size_t)total, nullptr));
     if (use_table_kernel) {
-        rc = f->gather ? launch_gather_leaf(f, p, draw_begin, draw_end, d_leaf, nullptr)
-                       : launch_table_leaf(f, p, draw_begin, draw_end, d_leaf, nullptr);
+        if (!f->gather) rc = ensure_codes(p, nullptr);
+        if (rc == BARTINT_OK)
+            rc = f->gather ? launch_gather_leaf(f, p, draw_begin, draw_end, d_leaf, nullptr)
+                           : launch_table_leaf(f, p, draw_begin, draw_end, d_leaf, nullptr);
     } else {
         rc = eval_core(f, p, BARTINT_FORCE_WALK, draw_begin, draw_end, nullptr, nullptr, nullptr, d_leaf, nullptr, 1.0,
                        0.0, 1, nullptr);
@@ -1205,11 +1230,16 @@ int bartint_design_step_dbarts098(const char* const* tree_strings, const double*
                     DS_CUDA(cudaStreamWaitEvent(sb, ready, 0));
                     DS_CUDA(cudaStreamWaitEvent(sb, built, 0));
                     DS_CUDA(cudaStreamWaitEvent(sb, mc->block_done[b], 0));
-                    DS_RC(launch_bin_points(mc->dX + r0, N, rows, d, f->dev.cut_off, f->dev.cut_val, f->max_cuts, f->route,
-                                            pm->codes + r0, pm->Npad, sb, rows_padded));
-                    if (pm->codes_pm)
-                        DS_RC(launch_repack_codes(pm->codes + r0, pm->Npad, d, pm->codes_pm + r0, sb, rows_padded));
+                    if (pm->codes_pm) {      // gather forest: one pass to the packed records of this row block
+                        DS_RC(launch_bin_pack_points(mc->dX + r0, N, rows, d, f->dev.cut_off, f->dev.cut_val, f->max_cuts,
+                                                     f->route, pm->codes_pm + r0, rows_padded, sb));
+                        pm->codes_valid = false;
+                    } else {
+                        DS_RC(launch_bin_points(mc->dX + r0, N, rows, d, f->dev.cut_off, f->dev.cut_val, f->max_cuts, f->route,
+                                                pm->codes + r0, pm->Npad, sb, rows_padded));
+                    }
                     views[n_bst] = *pm;                              // shallow: same buffers, rows [r0, r0 + rows)
+                    views[n_bst].codes_valid = true;                 // (views never materialise rows; see below)
                     views[n_bst].codes = pm->codes + r0;
                     views[n_bst].codes_pm = pm->codes_pm ? pm->codes_pm + r0 : nullptr;
                     views[n_bst].N = rows;

@@ -129,6 +129,7 @@ struct bartint_points {
     int32_t d = 0;
     cudaStream_t stream = nullptr;   // stream the code buffer was allocated on (stream-ordered allocator)
     uint8_t* codes = nullptr;  // feature-major: codes[f * Npad + i], zero padded to Npad (multiple of TK_NPAD)
+    mutable bool codes_valid = true;   // false: only codes_pm has been filled (one-pass K0); ensure_codes() fills `codes`
     uint4* codes_pm = nullptr; // point-major packed codes (16 B per point) for the gather kernel; built with the codes
 };
 
@@ -155,6 +156,10 @@ int launch_generate_points(int measure, int64_t N, int64_t first_index, uint64_t
 struct EvalPlan;
 int launch_build_tables(const bartint_forest* f, const uint32_t* d_desc, int desc_words, const uint32_t* d_hdr,
                         const uint32_t* d_split, cudaStream_t st);
+int launch_bin_pack_points(const double* dX, int64_t ld, int64_t N, int32_t d, const int32_t* d_cut_off,
+                           const double* d_cut_val, int max_cuts, int route, uint4* codes_pm, int64_t rows,
+                           cudaStream_t st);
+int launch_unpack_codes(const uint4* codes_pm, int64_t Npad, int d, uint8_t* codes, cudaStream_t st);
 int launch_repack_codes(const uint8_t* codes, int64_t Npad, int d, uint4* codes_pm, cudaStream_t st, int64_t rows = 0);
 int launch_eval_gather(const bartint_forest* f, const bartint_points* p, const EvalPlan& plan, double* draw_part,
                        double* pt_mean, double* pt_m2, double* full_pred, double fp_scale, double fp_y0,

@@ -137,6 +137,131 @@ int launch_bin_points(const double* dX, int64_t ld, int64_t N, int32_t d, const 
 }
 
 // ---------------------------------------------------------------------------------------------
+// K0 for gather forests (d <= 16): one pass from the fp64 matrix straight to the point-major packed records the gather
+// kernel keeps in registers (8 B read per element, 16 B written per point); the feature-major code rows are only
+// materialised on demand (unpack_codes_kernel: walk kernel, leaf decoding, bartint_points_codes).  Persistent grid,
+// ONE point per thread and iteration -- fine-grained on purpose: with fatter threads (4 points x all variables) the
+// kernel is a couple of waves of long CTAs and loses a third of its time to the last, partly filled wave.  All d cut
+// lists sit in shared memory twice: float pairs for the screen and sentinel-padded fp64 rows for the exact path.
+// ---------------------------------------------------------------------------------------------
+template <bool INC, int DMAX>
+__global__ void __launch_bounds__(256) bin_pack_points_kernel(const double* __restrict__ X, int64_t ld, int64_t N, int d,
+                                                              const int32_t* __restrict__ cut_off,
+                                                              const double* __restrict__ cut_val, int cut_stride,
+                                                              uint4* __restrict__ codes_pm, int64_t rows) {
+    extern __shared__ double s_dyn[];                 // d fp64 rows [cut_stride], then d float2 rows [cut_stride]
+    __shared__ double s_c0[16], s_inv[16];            // exact path only
+    __shared__ float4 s_fc[16];                       // per variable: {c0, 1/step, nc (int bits), -} for the fp32 guess
+    float2* s_pairs = reinterpret_cast<float2*>(s_dyn + (size_t)d * cut_stride);
+    // prologue: one warp per variable (8 in flight), so the dependent loads cut_off -> cut_val of the d variables overlap
+    // instead of costing d round trips in front of every CTA (measured: 20 us of a 39 us kernel at 10^6 points)
+    {
+        const int lane = threadIdx.x & 31;
+        for (int j = threadIdx.x >> 5; j < d; j += blockDim.x >> 5) {
+            const int c0i = cut_off[j], nc = cut_off[j + 1] - c0i;
+            double* row = s_dyn + (size_t)j * cut_stride + 1;
+            float2* pr = s_pairs + (size_t)j * cut_stride;
+            for (int k = lane; k < nc; k += 32) row[k] = cut_val[c0i + k];
+            for (int k = lane; k <= nc; k += 32) {
+                const double below = k > 0 ? cut_val[c0i + k - 1] : -INFINITY, here = k < nc ? cut_val[c0i + k] : INFINITY;
+                pr[k] = make_float2(__double2float_ru(below), __double2float_rd(here));
+            }
+            if (lane == 0) {
+                row[-1] = -INFINITY;
+                row[nc] = INFINITY;
+                const double first = nc > 0 ? cut_val[c0i] : 0.0;
+                const double span = nc > 1 ? cut_val[c0i + nc - 1] - first : 0.0;
+                const double inv = span > 0.0 ? (double)(nc - 1) / span : 0.0;
+                s_c0[j] = first;
+                s_inv[j] = inv;
+                s_fc[j] = make_float4((float)first, (float)inv, __int_as_float(nc), 0.f);
+            }
+        }
+    }
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rows; i += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t w[4] = {0u, 0u, 0u, 0u};
+        if (i < N) {
+            double x[DMAX];
+#pragma unroll
+            for (int j = 0; j < DMAX; ++j)                            // all loads first: d x 8 B in flight per thread
+                if (j < d) x[j] = __ldg(X + (int64_t)j * ld + i);
+#pragma unroll
+            for (int j = 0; j < DMAX; ++j)
+                if (j < d) {
+                    // the screen of bin_screened(), with the per-variable constants as one broadcast 16-byte load
+                    const float4 fc = s_fc[j];
+                    const int nc = __float_as_int(fc.z);
+                    const float xn = __double2float_rn(x[j]);
+                    const int k = min(max(__float2int_rd(fmaf(xn - fc.x, fc.y, 1.0f)), 0), nc);
+                    const float2 pr = s_pairs[j * cut_stride + k];
+                    uint32_t code = (uint32_t)k;
+                    if (!(pr.x < xn && xn < pr.y))
+                        code = bin_one<INC>(x[j], s_dyn + (size_t)j * cut_stride + 1, nc, s_c0[j], s_inv[j]);
+                    w[j >> 2] |= code << (8 * (j & 3));
+                }
+        }
+        codes_pm[i] = make_uint4(w[0], w[1], w[2], w[3]);             // rows beyond N: zero records
+    }
+}
+
+int launch_bin_pack_points(const double* dX, int64_t ld, int64_t N, int32_t d, const int32_t* d_cut_off,
+                           const double* d_cut_val, int max_cuts, int route, uint4* codes_pm, int64_t rows,
+                           cudaStream_t st) {
+    if (rows <= 0) return BARTINT_OK;
+    BI_REQUIRE(d >= 1 && d <= 16, BARTINT_ERR_ARG, "internal: packed binning needs 1 <= d <= 16");
+    const int cut_stride = max_cuts + 2;
+    const size_t smem = (size_t)d * cut_stride * (sizeof(double) + sizeof(float2));
+    typedef void (*kern_t)(const double*, int64_t, int64_t, int, const int32_t*, const double*, int, uint4*, int64_t);
+    const bool inc = route == BARTINT_ROUTE_BART;
+    kern_t k = d <= 4    ? (inc ? bin_pack_points_kernel<true, 4> : bin_pack_points_kernel<false, 4>)
+               : d <= 8  ? (inc ? bin_pack_points_kernel<true, 8> : bin_pack_points_kernel<false, 8>)
+               : d <= 12 ? (inc ? bin_pack_points_kernel<true, 12> : bin_pack_points_kernel<false, 12>)
+                         : (inc ? bin_pack_points_kernel<true, 16> : bin_pack_points_kernel<false, 16>);
+    // occupancy and SM count are cached per (kernel, shared-memory size): the queries cost ~15 us of host time, which a
+    // 25 us kernel cannot hide
+    struct Cached { kern_t k = nullptr; size_t smem = 0; int dev = -1, per_sm = 1, n_sm = 148; };
+    static thread_local Cached cache;
+    int dev_now = 0;
+    BI_CUDA(cudaGetDevice(&dev_now));
+    if (cache.k != k || cache.smem != smem || cache.dev != dev_now) {
+        if (smem > 48 * 1024) BI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0, n_sm = 148;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, 256, smem) != cudaSuccess || per_sm < 1) {
+            (void)cudaGetLastError();
+            per_sm = 1;
+        }
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev_now);
+        cache = Cached{k, smem, dev_now, per_sm, n_sm};
+    }
+    const int per_sm = cache.per_sm, n_sm = cache.n_sm;
+    const int64_t want = (rows + 255) / 256;
+    const int64_t grid = std::min<int64_t>(want, (int64_t)n_sm * per_sm);      // persistent: one resident wave
+    k<<<(unsigned)grid, 256, smem, st>>>(dX, ld, N, d, d_cut_off, d_cut_val, cut_stride, codes_pm, rows);
+    count_launch();
+    BI_CUDA(cudaGetLastError());
+    return BARTINT_OK;
+}
+
+// point-major packed records -> feature-major code rows (on demand only; one point per thread)
+__global__ void __launch_bounds__(256) unpack_codes_kernel(const uint4* __restrict__ codes_pm, int64_t Npad, int d,
+                                                           uint8_t* __restrict__ codes) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Npad) return;
+    const uint4 v = codes_pm[i];
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    for (int j = 0; j < d; ++j) codes[(int64_t)j * Npad + i] = (uint8_t)(w[j >> 2] >> (8 * (j & 3)));
+}
+
+int launch_unpack_codes(const uint4* codes_pm, int64_t Npad, int d, uint8_t* codes, cudaStream_t st) {
+    if (Npad == 0 || d == 0) return BARTINT_OK;
+    unpack_codes_kernel<<<(unsigned)((Npad + 255) / 256), 256, 0, st>>>(codes_pm, Npad, d, codes);
+    count_launch();
+    BI_CUDA(cudaGetLastError());
+    return BARTINT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // K0g  generate_points: Monte Carlo points drawn ON THE DEVICE from the integration measure and binned on the fly, so
 // the N x d fp64 matrix never exists in HBM.  Counter-based Philox4x32-10: element (point i,
 // variable j) uses counter (i_lo, i_hi, j, 0) and key (seed_lo, seed_hi) -> the stream does not depend on the launch

@@ -370,12 +370,12 @@ def run_ours(args):
     if not args.points and not args.draws:
         roofline["traffic"] = traffic.get(f"eval_{f0.fast_kernel}_kernel")
     k0 = float(np.median(k0_ms))
-    pm = f0.fast_kernel == "gather"                       # + repack_codes_kernel: codes -> 16 B packed record per point
-    k0_name = "bin_points_kernel+repack_codes_kernel" if pm else "bin_points_kernel"
-    k0_bytes = 9 * N * d + ((N * d + 16 * N) if pm else 0)   # fp64 in, uint8 out (+ re-read codes, packed layout out)
+    pm = f0.fast_kernel == "gather"                       # one pass: fp64 matrix -> 16 B packed record per point
+    k0_name = "bin_pack_points_kernel" if pm else "bin_points_kernel"
+    k0_bytes = (8 * N * d + 16 * N) if pm else 9 * N * d     # fp64 in; packed records (gather) or uint8 rows (table) out
     roofline_k0 = {"kernel": k0_name, "bound": "hbm", "achieved": k0_bytes / (k0 * 1e-3) / 1e9,
                    "peak": hbm_peak, "unit": "GB/s", "frac": k0_bytes / (k0 * 1e-3) / 1e9 / hbm_peak,
-                   "traffic": traffic.get("bin_points_kernel") if not args.points else None, "kernel_ms": k0,
+                   "traffic": traffic.get(k0_name) if not args.points else None, "kernel_ms": k0,
                    "alg_bytes_per_launch": k0_bytes, "peak_source": peak_src,
                    "note": "timed with events around the whole points_from_device call (allocation + launch gap included)"}
 

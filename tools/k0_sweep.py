@@ -55,7 +55,7 @@ def main():
         ms = sorted(ms[2:])
         med = ms[len(ms) // 2]
         packed = f.fast_kernel == "gather"
-        alg = 9 * N * d + (16 * N if packed else 0)
+        alg = (8 * N * d + 16 * N) if packed else 9 * N * d      # gather forests: fp64 in, 16 B packed record out
         out = {"N": N, "d": d, "layout": "feature-major + packed" if packed else "feature-major", "ms_median": med,
                "ms_min": ms[0], "alg_bytes": alg, "gbs": alg / (med * 1e-3) / 1e9,
                "hbm_peak_gbs": peak, "frac": (alg / (med * 1e-3) / 1e9 / peak) if peak else None}
