@@ -3,8 +3,8 @@
 
 For each N the fp64 matrix (N x d column-major) is resident in HBM; the timed region is the points_from_device call
 (stream-ordered allocation + the binning launch) measured with CUDA events, L2 flushed before every repetition.
-Algorithmic bytes: 8 B read per matrix element + 1 B feature-major code (+ 16 B packed record per point for gather
-forests).  Prints one JSON line per N.
+Algorithmic bytes: 8 B read per matrix element + 16 B packed record per point (gather forests) or 1 B feature-major
+code per element (table forests).  Prints one JSON line per N.
 
     python tools/k0_sweep.py [--d 10] [--n 1000000 4000000 12500000 50000000]
 """
@@ -56,7 +56,7 @@ def main():
         med = ms[len(ms) // 2]
         packed = f.fast_kernel == "gather"
         alg = (8 * N * d + 16 * N) if packed else 9 * N * d      # gather forests: fp64 in, 16 B packed record out
-        out = {"N": N, "d": d, "layout": "feature-major + packed" if packed else "feature-major", "ms_median": med,
+        out = {"N": N, "d": d, "layout": "packed records (feature-major rows on demand)" if packed else "feature-major", "ms_median": med,
                "ms_min": ms[0], "alg_bytes": alg, "gbs": alg / (med * 1e-3) / 1e9,
                "hbm_peak_gbs": peak, "frac": (alg / (med * 1e-3) / 1e9 / peak) if peak else None}
         print(json.dumps(out), flush=True)
