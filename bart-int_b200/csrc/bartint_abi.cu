@@ -539,6 +539,10 @@ static int eval_core(const bartint_forest* f, const bartint_points* p, uint32_t 
     if (rc == BARTINT_OK && d_draw_sum != nullptr) {
         rc = launch_reduce_draw_parts(draw_part, plan.n_tiles, ndraws, d_draw_sum, st);
         f->last_launches[slot]++;
+        if (rc == BARTINT_OK && plan.count_mode) {      // + the single-split trees, from 1-D code histograms
+            rc = launch_count_single_splits(f, p, draw_begin, draw_end, d_draw_sum, st);
+            f->last_launches[slot] += 3;
+        }
     }
     if (rc == BARTINT_OK && want_mom && !direct_mom) {
         rc = launch_merge_point_parts(pt_mean, pt_m2, plan.n_chunks, plan.chunk_draws, ndraws, p->N, d_point_mean,
@@ -920,7 +924,7 @@ int bartint_last_eval_profile(const bartint_forest* f, int32_t with_moments, flo
 namespace {
 struct ImageHeader {
     uint32_t magic, version;
-    int32_t S, m, d, max_depth, max_internal, max_cuts, route, table_ok, gather, g_regs, nb, reserved;
+    int32_t S, m, d, max_depth, max_internal, max_cuts, route, table_ok, gather, g_regs, nb, reserved;   // reserved = count_mode
     int64_t n_nodes, n_leaves, n_groups, n_cuts, device_bytes;
     double y_min, y_max;
     int64_t bytes[11];       // device array sizes (0 = absent), order of image_arrays()
@@ -973,6 +977,7 @@ int bartint_forest_pack(const bartint_forest* f, void* host_header, int64_t host
     h.magic = kImageMagic; h.version = (uint32_t)bartint_version();
     h.S = f->S; h.m = f->m; h.d = f->d; h.max_depth = f->max_depth; h.max_internal = f->max_internal; h.max_cuts = f->max_cuts;
     h.route = f->route; h.table_ok = f->table_ok ? 1 : 0; h.gather = f->gather ? 1 : 0; h.g_regs = f->g_regs; h.nb = f->nb;
+    h.reserved = f->count_mode ? 1 : 0;
     h.n_nodes = f->n_nodes; h.n_leaves = f->n_leaves; h.n_groups = f->n_groups; h.n_cuts = (int64_t)f->cut_val.size();
     h.device_bytes = db; h.y_min = f->y_min; h.y_max = f->y_max;
     void** slots[11];
@@ -1022,6 +1027,7 @@ int bartint_forest_unpack(const void* host_header, int64_t host_bytes, const voi
     BI_REQUIRE(f != nullptr, BARTINT_ERR_NOMEM, "out of host memory");
     f->S = h.S; f->m = h.m; f->d = h.d; f->max_depth = h.max_depth; f->max_internal = h.max_internal; f->max_cuts = h.max_cuts;
     f->route = h.route; f->table_ok = h.table_ok != 0; f->gather = h.gather != 0; f->g_regs = h.g_regs; f->nb = h.nb;
+    f->count_mode = h.reserved != 0;
     f->n_nodes = h.n_nodes; f->n_leaves = h.n_leaves; f->n_groups = h.n_groups; f->y_min = h.y_min; f->y_max = h.y_max;
     const unsigned char* hp = (const unsigned char*)host_header + sizeof(ImageHeader);
     f->draw_group_off.resize((size_t)h.S + 1);

@@ -58,6 +58,11 @@ constexpr uint32_t TK_FLAG_WALK = 2u;
 // gather format only: the record holds ONE joint 2^NB table over two gather rounds; unflagged gather records are DUAL
 // (two independent 16-entry tables: trees [first, first+split) -> table 1, the rest -> table 2; header.w = split).
 constexpr uint32_t TK_FLAG_JOINT = 4u;
+// Counting mode (gather format, opt-in BARTINT_COUNT_SPLITS=1): the single-split trees of a draw sit in COUNTABLE DUAL
+// records at the end of the draw; the last record before them carries END_EVAL.  An evaluation that only wants per-draw
+// sums skips the COUNTABLE records, closes the draw at END_EVAL, and gets those trees' sums from 1-D code histograms.
+constexpr uint32_t TK_FLAG_COUNTABLE = 8u;
+constexpr uint32_t TK_FLAG_END_EVAL = 16u;
 __host__ __device__ constexpr int tk_tbl_off(int nb) { return TK_HDR + ((nb * 8 + 15) & ~15); }   // 16 B aligned
 __host__ __device__ constexpr int tk_rec_bytes(int nb) { return tk_tbl_off(nb) + (8 << nb); }       // multiple of 16
 
@@ -107,6 +112,7 @@ struct bartint_forest {
     bool defer_upload_sync = false;    // forest_upload leaves its default-stream work in flight (pipelined design step)
     bool table_ok = false;             // a fast (table or gather) kernel applies
     bool gather = false;               // group records are in the gather format (else table format)
+    bool count_mode = false;           // gather format with COUNTABLE records for the single-split trees
     int g_regs = 0;                    // gather: code words per point
     int nb = 0;
     int64_t n_groups = 0;
@@ -159,6 +165,8 @@ int launch_build_tables(const bartint_forest* f, const uint32_t* d_desc, int des
 int launch_bin_pack_points(const double* dX, int64_t ld, int64_t N, int32_t d, const int32_t* d_cut_off,
                            const double* d_cut_val, int max_cuts, int route, uint4* codes_pm, int64_t rows,
                            cudaStream_t st);
+int launch_count_single_splits(const bartint_forest* f, const bartint_points* p, int32_t draw_begin, int32_t draw_end,
+                               double* d_draw_sum, cudaStream_t st);
 int launch_unpack_codes(const uint4* codes_pm, int64_t Npad, int d, uint8_t* codes, cudaStream_t st);
 int launch_repack_codes(const uint8_t* codes, int64_t Npad, int d, uint4* codes_pm, cudaStream_t st, int64_t rows = 0);
 int launch_eval_gather(const bartint_forest* f, const bartint_points* p, const EvalPlan& plan, double* draw_part,
@@ -177,6 +185,7 @@ struct EvalPlan {
     int tile;          // points per CTA
     bool use_table;    // a fast kernel (table or gather format) is used, else the walk kernel
     bool use_gather;   // ... and it is the gather kernel
+    bool count_mode;   // sums-only evaluation of a counting-mode forest: COUNTABLE records skipped, their trees counted
 };
 EvalPlan make_plan(const bartint_forest* f, const bartint_points* p, uint32_t flags, int32_t draw_begin,
                    int32_t draw_end, bool want_moments, bool want_full);

@@ -515,6 +515,8 @@ int forest_upload(bartint_forest* f) {
     const char* kenv = getenv("BARTINT_KERNEL");
     f->gather = f->table_ok && f->d <= 16 && f->d >= 1 && !(kenv && strcmp(kenv, "table") == 0);
     if (f->gather && f->nb > 5) f->nb = 5;                 // slot weights -(8 << bit) must fit a signed byte
+    const char* cenv = getenv("BARTINT_COUNT_SPLITS");
+    f->count_mode = f->gather && cenv && cenv[0] == '1';    // opt-in: single-split trees counted in sums-only evaluations
     f->g_regs = tg_regs_for(f->d);
     f->n_groups = 0;
     if (!f->table_ok) {
@@ -648,6 +650,7 @@ int forest_upload(bartint_forest* f) {
         std::vector<Bin> bins1, bins2;
         std::vector<int32_t> stumps, joint_trees, walk_trees;
         std::vector<int64_t> tn;
+        std::vector<std::pair<unsigned, int32_t>> singles;       // counting mode: (word mask, tree) of single-split trees
         int dual_nodes = 0;
         for (int32_t t = 0; t < f->m; ++t) {
             internal_nodes((int64_t)s * f->m + t, tn);
@@ -655,6 +658,7 @@ int forest_upload(bartint_forest* f) {
             unsigned regs = 0;
             for (int64_t g : tn) regs |= 1u << (f->var[(size_t)g] >> 2);
             const int k = (int)tn.size();
+            if (f->count_mode && k == 1) { singles.emplace_back(regs, t); continue; }    // counted, not evaluated (sums)
             if (k <= 4 && (within(regs, m_side1) || side2_ok(regs))) {
                 items.push_back(Item{k, regs, (int)within(regs, m_side1) + (int)pair_ok(regs), t});
                 dual_nodes += k;
@@ -819,6 +823,30 @@ int forest_upload(bartint_forest* f) {
             open_group((int64_t)s * f->m + pos, 0u);
             for (int32_t t : stumps) perm[pos++] = (int32_t)((int64_t)s * f->m + t);
             split.back() = (uint32_t)stumps.size();
+        }
+        if (f->count_mode) {
+            // counting mode: everything above is the EVALUATED part of the draw (it must exist, if only as a constant-0
+            // record, to carry END_EVAL); the single-split trees follow in COUNTABLE records -- evaluated like any
+            // DUAL record when per-point results are wanted, skipped and counted when only per-draw sums are.
+            if (hdr.empty()) open_group((int64_t)s * f->m + pos, 0u);
+            hdr.back() |= TK_FLAG_END_EVAL;
+            std::vector<std::pair<unsigned, int32_t>> side_a, side_b;
+            for (const auto& rt : singles) (within(rt.first, m_side1) ? side_a : side_b).push_back(rt);
+            size_t ia = 0, ib = 0;
+            while (ia < side_a.size() || ib < side_b.size()) {
+                Bin b1, b2;
+                while (ia < side_a.size() && b1.nodes < 4) { b1.regs |= side_a[ia].first; b1.trees.push_back(side_a[ia].second); ++b1.nodes; ++ia; }
+                while (ib < side_b.size() && b2.nodes < 4) { b2.regs |= side_b[ib].first; b2.trees.push_back(side_b[ib].second); ++b2.nodes; ++ib; }
+                while (ia < side_a.size() && b2.nodes < 4 && side2_ok(b2.regs | side_a[ia].first)) {   // table 2 also reads words 0/1
+                    b2.regs |= side_a[ia].first; b2.trees.push_back(side_a[ia].second); ++b2.nodes; ++ia;
+                }
+                open_group((int64_t)s * f->m + pos, TK_FLAG_COUNTABLE);
+                uint32_t* gd = &desc[desc.size() - (size_t)DW];
+                const int32_t start = pos;
+                emit_table(b1, 0, gd);
+                split.back() = (uint32_t)(pos - start);
+                emit_table(b2, 1, gd);
+            }
         }
         hdr.back() |= TK_FLAG_END_DRAW;
     }

@@ -395,6 +395,7 @@ EvalPlan make_plan(const bartint_forest* f, const bartint_points* p, uint32_t fl
     const int ndraws = draw_end - draw_begin;
     pl.use_table = f->table_ok && !(flags & BARTINT_FORCE_WALK);
     pl.use_gather = pl.use_table && f->gather && p->codes_pm != nullptr;
+    pl.count_mode = pl.use_gather && f->count_mode && !want_moments && !want_full;
     int resident_per_sm = 8;
     pl.tile = WK_THREADS;
     if (pl.use_gather) {

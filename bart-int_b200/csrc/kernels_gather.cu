@@ -155,14 +155,16 @@ __global__ void __launch_bounds__(TG_THREADS, P > 8 ? 2 : MOMENTS ? 2 : 3) eval_
         const int par = k & 1;
         const int stage_first_draw = draws_done;
         // the stage's group flags as two warp-uniform bit masks
-        unsigned long long walk_mask = 0ull, end_mask = 0ull, joint_mask = 0ull;
+        unsigned long long walk_mask = 0ull, end_mask = 0ull, joint_mask = 0ull, skip_mask = 0ull;
 #pragma unroll
         for (int base = 0; base < GS; base += 32) {
             const int gl = base + lane;
             const uint32_t fl = gl < ng ? *reinterpret_cast<const uint32_t*>(stage + gl * REC) : 0u;
+            const uint32_t end_flag = prm.count_mode ? TK_FLAG_END_EVAL : TK_FLAG_END_DRAW;
             walk_mask |= (unsigned long long)__ballot_sync(0xffffffffu, (fl & TK_FLAG_WALK) != 0u) << base;
-            end_mask |= (unsigned long long)__ballot_sync(0xffffffffu, (fl & TK_FLAG_END_DRAW) != 0u) << base;
+            end_mask |= (unsigned long long)__ballot_sync(0xffffffffu, (fl & end_flag) != 0u) << base;
             joint_mask |= (unsigned long long)__ballot_sync(0xffffffffu, (fl & TK_FLAG_JOINT) != 0u) << base;
+            skip_mask |= (unsigned long long)__ballot_sync(0xffffffffu, prm.count_mode && (fl & TK_FLAG_COUNTABLE) != 0u) << base;
         }
         // DUAL records without a flag (the bulk) run in a tight loop; the next flagged record is found with one ffs
         auto dual_points = [&](auto variant, const uint4& da, uint32_t wB, uint32_t sel_t,
@@ -196,12 +198,13 @@ __global__ void __launch_bounds__(TG_THREADS, P > 8 ? 2 : MOMENTS ? 2 : 3) eval_
         int g = 0;
 #pragma unroll 1
         while (g < ng) {
-            const unsigned long long special = (walk_mask | end_mask | joint_mask) >> g;
+            const unsigned long long special = (walk_mask | end_mask | joint_mask | skip_mask) >> g;
             const int g_stop = special ? min(ng, g + __ffsll((long long)special) - 1) : ng;
 #pragma unroll 1
             for (; g < g_stop; ++g) dual_group(stage + g * REC);
             if (g >= ng) break;
             const unsigned char* rec = stage + g * REC;
+            if ((skip_mask >> g) & 1ull) { ++g; continue; }      // counting mode: this record's trees are counted, not evaluated
             if ((walk_mask >> g) & 1ull) {
                 // rare: a tree that does not fit a group, walked per point from global memory (L1/L2)
                 const int64_t kt = reinterpret_cast<const uint32_t*>(rec)[1];
@@ -356,6 +359,7 @@ int launch_eval_gather(const bartint_forest* f, const bartint_points* p, const E
     prm.fp_scale = fp_scale;
     prm.fp_y0 = fp_y0;
     prm.fp_scaled = fp_scaled;
+    prm.count_mode = plan.count_mode ? 1 : 0;
     size_t smem = 0;
     gather_kernel_t k = gather_kernel_for(f, pt_mean != nullptr, full_pred != nullptr, &smem);
     BI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -6,6 +6,12 @@
 
 namespace bartint {
 
+__device__ __forceinline__ double warp_sum_misc(double v) {        // fixed-order butterfly: deterministic
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
 // ---------------------------------------------------------------------------------------------
 // K0  bin_points: code = #{k : x > cut[j][k]}  (dbarts' integer cut map of x.test).
 // HBM-bound streaming kernel: reads 8 B, writes 1 B per matrix element.  One thread = 4 consecutive
@@ -258,6 +264,83 @@ int launch_unpack_codes(const uint4* codes_pm, int64_t Npad, int d, uint8_t* cod
     unpack_codes_kernel<<<(unsigned)((Npad + 255) / 256), 256, 0, st>>>(codes_pm, Npad, d, codes);
     count_launch();
     BI_CUDA(cudaGetLastError());
+    return BARTINT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Counting mode: per-draw sums of the single-split trees without evaluating them point by point.
+//   sum_i f_tree(x_i) = mu_L * (N - G[v][c]) + mu_R * G[v][c],   G[v][c] = #{i < N : code_i[v] > c}
+// G comes from 1-D histograms of the packed codes (one pass over the point set, shared by all S*m trees).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) hist_codes_kernel(const uint4* __restrict__ codes_pm, int64_t N, int d,
+                                                         unsigned int* __restrict__ hist /* [16][128] */) {
+    __shared__ unsigned int h[16 * 128];
+    for (int k = threadIdx.x; k < 16 * 128; k += blockDim.x) h[k] = 0u;
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint4 v = codes_pm[i];
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        for (int j = 0; j < d; ++j) atomicAdd(&h[j * 128 + ((w[j >> 2] >> (8 * (j & 3))) & 127u)], 1u);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < 16 * 128; k += blockDim.x)
+        if (h[k] != 0u) atomicAdd(&hist[k], h[k]);
+}
+
+// G[v][c] = sum_{code > c} hist[v][code]  (one thread per variable; 128 codes)
+__global__ void suffix_counts_kernel(const unsigned int* __restrict__ hist, int d, long long* __restrict__ G) {
+    const int v = threadIdx.x;
+    if (v >= d) return;
+    long long run = 0;
+    for (int c = 127; c >= 0; --c) {
+        G[v * 128 + c] = run;                 // codes strictly above c
+        run += hist[v * 128 + c];
+    }
+}
+
+// one warp per draw: lanes stride over the draw's trees, fixed-order shuffle reduction, result ADDED to draw_sum
+__global__ void __launch_bounds__(256) count_draw_sums_kernel(const uint2* __restrict__ nodes, const int32_t* __restrict__ tree_off,
+                                                              const int32_t* __restrict__ tree_leaf_off,
+                                                              const double* __restrict__ leaf_mu,
+                                                              const long long* __restrict__ G, long long N, int m,
+                                                              int draw_begin, int draw_end, double* __restrict__ draw_sum) {
+    const int s = draw_begin + (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (s >= draw_end) return;
+    double acc = 0.0;
+    for (int t = lane; t < m; t += 32) {
+        const int64_t k = (int64_t)s * m + t;
+        const int32_t base = tree_off[k];
+        if (tree_off[k + 1] - base != 3) continue;            // exactly one split: root + two leaves
+        const uint2 r = nodes[base];
+        const long long g = G[(r.x & 0xFFFFu) * 128 + (r.x >> 16)];
+        const int32_t lb = tree_leaf_off[k];
+        acc += leaf_mu[lb] * (double)(N - g) + leaf_mu[lb + 1] * (double)g;
+    }
+    acc = warp_sum_misc(acc);
+    if (lane == 0) draw_sum[s - draw_begin] += acc;
+}
+
+int launch_count_single_splits(const bartint_forest* f, const bartint_points* p, int32_t draw_begin, int32_t draw_end,
+                               double* d_draw_sum, cudaStream_t st) {
+    const int ndraws = draw_end - draw_begin;
+    if (ndraws <= 0) return BARTINT_OK;
+    unsigned int* d_hist = nullptr;
+    BI_CUDA(cudaMallocAsync((void**)&d_hist, 16 * 128 * (sizeof(unsigned int) + sizeof(long long)), st));
+    long long* d_G = reinterpret_cast<long long*>(d_hist + 16 * 128);
+    BI_CUDA(cudaMemsetAsync(d_hist, 0, 16 * 128 * sizeof(unsigned int), st));
+    if (p->N > 0) {
+        const int64_t want = (p->N + 255) / 256;
+        hist_codes_kernel<<<(unsigned)std::min<int64_t>(want, 148 * 4), 256, 0, st>>>(p->codes_pm, p->N, p->d, d_hist);
+    }
+    suffix_counts_kernel<<<1, 32, 0, st>>>(d_hist, p->d, d_G);
+    count_draw_sums_kernel<<<(unsigned)((ndraws * 32 + 255) / 256), 256, 0, st>>>(
+        f->dev.nodes, f->dev.tree_off, f->dev.tree_leaf_off, f->dev.leaf_mu, d_G, (long long)p->N, f->m, draw_begin, draw_end,
+        d_draw_sum);
+    count_launch(3);
+    cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(d_hist, st);
+    BI_CUDA(e);
     return BARTINT_OK;
 }
 

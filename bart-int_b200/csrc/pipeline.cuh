@@ -73,6 +73,7 @@ struct TableParams {
     double* full_pred;
     double fp_scale, fp_y0;
     int fp_scaled;
+    int count_mode;                // 1: skip COUNTABLE records, close draws at END_EVAL (sums-only evaluation)
 };
 
 }  // namespace bartint

@@ -10,10 +10,12 @@ from bartint_b200 import Forest, StagedMatrix, WireStrings, design_step_dbarts, 
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["gather", "table"], autouse=True)
+@pytest.fixture(params=["gather", "table", "gather+count"], autouse=True)
 def kernel_kind(request, monkeypatch):
-    monkeypatch.setenv("BARTINT_KERNEL", request.param)
-    return request.param
+    kind, _, count = request.param.partition("+")
+    monkeypatch.setenv("BARTINT_KERNEL", kind)
+    monkeypatch.setenv("BARTINT_COUNT_SPLITS", "1" if count else "0")
+    return kind
 
 
 def _case(S=37, m=11, d=6, n=80, N=5000, C=300, seed=3):

@@ -11,10 +11,12 @@ from bartint_b200 import Forest, synth
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["gather", "table"], autouse=True)
+@pytest.fixture(params=["gather", "table", "gather+count"], autouse=True)
 def kernel_kind(request, monkeypatch):
-    monkeypatch.setenv("BARTINT_KERNEL", request.param)
-    return request.param
+    kind, _, count = request.param.partition("+")
+    monkeypatch.setenv("BARTINT_KERNEL", kind)
+    monkeypatch.setenv("BARTINT_COUNT_SPLITS", "1" if count else "0")
+    return kind
 
 
 def _close(got, want, tol, scale=None):
