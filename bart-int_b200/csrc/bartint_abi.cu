@@ -225,6 +225,51 @@ int bartint_forest_from_soa_routed(int32_t S, int32_t m, int32_t d, const int64_
     return finish_forest(f, out);
 }
 
+int bartint_debug_plan_soa(int32_t S, int32_t m, int32_t d, const int64_t* tree_node_offset, const int32_t* split_var,
+                           const int32_t* split_cut_idx, const int32_t* left, const int32_t* right,
+                           const double* leaf_mu, const int32_t* cut_offsets, const double* cut_values,
+                           int64_t group_capacity, int64_t info[8], uint32_t* walk_nodes, int32_t* tree_leaf_offset,
+                           double* leaf_mu_out, uint8_t* node_bit, int32_t* tree_perm, int32_t* draw_group_offset,
+                           int32_t* group_tree_offset, uint32_t* hdr, uint32_t* split, uint32_t* desc) {
+    BI_REQUIRE(info != nullptr, BARTINT_ERR_ARG, "info is NULL");
+    BI_REQUIRE(S >= 0 && m >= 0, BARTINT_ERR_ARG, "S and m must be >= 0");
+    BI_REQUIRE(tree_node_offset != nullptr, BARTINT_ERR_ARG, "tree_node_offset is NULL");
+    const bool has_nodes = (int64_t)S * m > 0;
+    BI_REQUIRE(!has_nodes || (split_var && split_cut_idx && left && right && leaf_mu), BARTINT_ERR_ARG,
+               "node arrays must not be NULL");
+    int rc = check_cuts(d, cut_offsets, cut_values);
+    if (rc) return rc;
+    bartint_forest f;                       // never uploaded: no device state to release
+    f.S = S; f.m = m; f.d = d;
+    f.cut_off.assign(cut_offsets, cut_offsets + d + 1);
+    f.cut_val.assign(cut_values, cut_values + cut_offsets[d]);
+    if ((rc = canonicalise_soa(S, m, d, tree_node_offset, split_var, split_cut_idx, left, right, leaf_mu, &f))) return rc;
+    if ((rc = forest_finish_host(&f))) return rc;
+    WalkForm W;
+    pack_walk_form(&f, W);
+    FastPlan P;
+    plan_fast_path(&f, W.tree_off, P);
+    info[0] = f.table_ok ? 1 : 0; info[1] = f.gather ? 1 : 0; info[2] = f.nb; info[3] = f.g_regs;
+    info[4] = f.count_mode ? 1 : 0; info[5] = f.n_groups; info[6] = P.DW; info[7] = f.n_leaves;
+    BI_REQUIRE(f.n_groups <= group_capacity, BARTINT_ERR_ARG, "plan has %lld group records, capacity is %lld",
+               (long long)f.n_groups, (long long)group_capacity);
+    BI_REQUIRE(P.DW <= 16, BARTINT_ERR_UNSUPPORTED, "descriptor of %d words", P.DW);
+    if (walk_nodes)
+        for (size_t g = 0; g < W.nodes.size(); ++g) { walk_nodes[2 * g] = W.nodes[g].x; walk_nodes[2 * g + 1] = W.nodes[g].y; }
+    auto copy_out = [](auto* dst, const auto& v) { if (dst && !v.empty()) memcpy(dst, v.data(), v.size() * sizeof(v[0])); };
+    copy_out(tree_leaf_offset, W.leaf_off);
+    copy_out(leaf_mu_out, W.leaf_mu);
+    if (!f.table_ok) return BARTINT_OK;
+    copy_out(node_bit, P.node_bit);
+    copy_out(tree_perm, P.tree_perm);
+    copy_out(draw_group_offset, f.draw_group_off);
+    copy_out(group_tree_offset, P.group_tree_off);
+    copy_out(hdr, P.hdr);
+    copy_out(split, P.split);
+    copy_out(desc, P.desc);
+    return BARTINT_OK;
+}
+
 int bartint_forest_info(const bartint_forest* f, int64_t info[12]) {
     BI_REQUIRE(f != nullptr && info != nullptr, BARTINT_ERR_ARG, "NULL argument");
     info[0] = f->S; info[1] = f->m; info[2] = f->d; info[3] = f->n_nodes; info[4] = f->n_leaves;

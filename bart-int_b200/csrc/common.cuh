@@ -141,9 +141,27 @@ struct bartint_points {
 
 namespace bartint {
 
-// host-side pieces (forest_host.cpp)
+// host-side pieces (forest_host.cu)
 int forest_finish_host(bartint_forest* f);      // validate canonical SoA, compute stats
 int forest_upload(bartint_forest* f);           // build device arrays (+ table groups)
+struct WalkForm {
+    std::vector<uint2> nodes;                 // n_nodes node records (see LEAF_VAR above)
+    std::vector<int32_t> tree_off, leaf_off;  // S*m+1 each: first node / first leaf of every tree
+    std::vector<double> leaf_mu;              // n_leaves, by (tree, leaf ordinal)
+};
+// Fast-path plan of a forest: everything forest_upload sends to the device besides the walk form.  Filled by
+// plan_fast_path on the host (no CUDA call in there: the CPU tests run it through bartint_debug_plan_soa and
+// interpret the records with numpy against the oracle).
+struct FastPlan {
+    int DW = 0;                               // descriptor words per group
+    std::vector<uint8_t> node_bit;            // n_nodes: predicate bit (table format) / slot (gather format) of a node
+    std::vector<int32_t> tree_perm;           // S*m: permuted position -> tree id
+    std::vector<int32_t> group_tree_off;      // n_groups+1: first permuted position of each group
+    std::vector<uint32_t> hdr, split, desc;   // per group: flags, trees in table 1 (DUAL), DW descriptor words
+};
+
+void pack_walk_form(const bartint_forest* f, WalkForm& W);
+void plan_fast_path(bartint_forest* f, const std::vector<int32_t>& tree_off, FastPlan& P);
 int parse_dbarts_forest(const char* const* tree_strings, const double* tree_fits, const double* x_train,
                         int64_t n, int32_t d, const int32_t* cut_offsets, const double* cut_values,
                         int32_t m, int32_t S, bartint_forest* f);

@@ -469,44 +469,11 @@ static int table_bits_from_env() {
     return nb;
 }
 
-int forest_upload(bartint_forest* f) {
-    PhaseTimer pt;
+// Chooses the fast kernel (f->table_ok / gather / nb / g_regs / count_mode), packs the trees of every draw into
+// group records and fills f->n_groups / f->draw_group_off.  tree_off: first node of each tree (int32 copy).
+void plan_fast_path(bartint_forest* f, const std::vector<int32_t>& tree_off, FastPlan& P) {
     const int64_t n_trees = (int64_t)f->S * f->m;
     const int64_t nn = f->n_nodes;
-    std::vector<uint2> nodes((size_t)nn);
-    std::vector<int32_t> tree_off((size_t)n_trees + 1), leaf_off((size_t)n_trees + 1, 0);
-    std::vector<double> leaf_mu((size_t)f->n_leaves);
-    for (int64_t k = 0; k <= n_trees; ++k) tree_off[(size_t)k] = (int32_t)f->tree_off[(size_t)k];
-    // leaf offsets (prefix sum), then fill
-    for (int64_t k = 0; k < n_trees; ++k) {
-        int32_t cnt = tree_off[(size_t)k + 1] - tree_off[(size_t)k];
-        leaf_off[(size_t)k + 1] = leaf_off[(size_t)k] + (cnt + 1) / 2;
-    }
-#pragma omp parallel for schedule(static)
-    for (int64_t k = 0; k < n_trees; ++k) {
-        const int32_t base = tree_off[(size_t)k], cnt = tree_off[(size_t)k + 1] - base;
-        int32_t ord = 0;
-        for (int32_t a = 0; a < cnt; ++a) {
-            const size_t g = (size_t)(base + a);
-            if (f->var[g] >= 0) {
-                nodes[g] = make_uint2((uint32_t)f->var[g] | ((uint32_t)f->cut[g] << 16), (uint32_t)(f->right[g] - a));
-            } else {
-                nodes[g] = make_uint2(LEAF_VAR, (uint32_t)ord);
-                leaf_mu[(size_t)leaf_off[(size_t)k] + ord] = f->mu[g];
-                ++ord;
-            }
-        }
-    }
-    int rc;
-    pt.lap("upload: pack walk form");
-    if ((rc = upload(&f->dev.nodes, nodes))) return rc;
-    if ((rc = upload(&f->dev.tree_off, tree_off))) return rc;
-    if ((rc = upload(&f->dev.tree_leaf_off, leaf_off))) return rc;
-    if ((rc = upload(&f->dev.leaf_mu, leaf_mu))) return rc;
-    if ((rc = upload(&f->dev.cut_off, f->cut_off))) return rc;
-    if ((rc = upload(&f->dev.cut_val, f->cut_val))) return rc;
-
-    pt.lap("upload: H2D walk form");
     // ---- fast-path planning: greedy packing of consecutive trees of a draw into groups of <= NB predicate bits ----
     f->nb = table_bits_from_env();
     // both fast kernels need 7-bit codes (byte-wise compare); the table kernel keeps the code rows of one CTA tile in
@@ -519,13 +486,12 @@ int forest_upload(bartint_forest* f) {
     f->count_mode = f->gather && cenv && cenv[0] == '1';    // opt-in: single-split trees counted in sums-only evaluations
     f->g_regs = tg_regs_for(f->d);
     f->n_groups = 0;
-    if (!f->table_ok) {
-        BI_CUDA(cudaStreamSynchronize(nullptr));
-        return BARTINT_OK;
-    }
+    f->draw_group_off.clear();
+    if (!f->table_ok) return;
     const int NB = f->nb;
-    const int DW = f->gather ? TG_DESC / 4 : 2 * NB;       // descriptor words per group
-    std::vector<uint8_t> node_bit((size_t)nn, 0);
+    const int DW = P.DW = f->gather ? TG_DESC / 4 : 2 * NB;       // descriptor words per group
+    std::vector<uint8_t>& node_bit = P.node_bit;
+    node_bit.assign((size_t)nn, 0);
     // Bit order inside a group: table lookups of lanes whose indices differ only in a HIGH bit hit the same bank pair
     // (a 2^NB x 8 B table wraps the 32 banks 2^(NB-4) times), lookups with equal indices are a broadcast.  The
     // predicates least likely to differ between points -- cuts nearest the edge of their variable's cut grid -- are
@@ -545,7 +511,8 @@ int forest_upload(bartint_forest* f) {
         std::vector<uint32_t> split;           // gather DUAL records: number of trees in table 1
         std::vector<uint32_t> desc;            // DW words per group
     };
-    std::vector<int32_t> tree_perm((size_t)n_trees);           // permuted position -> tree id (identity: table format)
+    std::vector<int32_t>& tree_perm = P.tree_perm;             // permuted position -> tree id (identity: table format)
+    tree_perm.resize((size_t)n_trees);
     for (int64_t k = 0; k < n_trees; ++k) tree_perm[(size_t)k] = (int32_t)k;
     std::vector<DrawPlan> plans((size_t)f->S);
 #pragma omp parallel for schedule(static)
@@ -855,8 +822,12 @@ int forest_upload(bartint_forest* f) {
     for (int32_t s = 0; s < f->S; ++s)
         f->draw_group_off[(size_t)s + 1] = f->draw_group_off[(size_t)s] + (int32_t)plans[(size_t)s].hdr.size();
     const size_t n_groups_total = (size_t)f->draw_group_off[(size_t)f->S];
-    std::vector<int32_t> group_tree_off(n_groups_total);
-    std::vector<uint32_t> hdr(n_groups_total), split(n_groups_total), desc(n_groups_total * (size_t)DW);
+    std::vector<int32_t>& group_tree_off = P.group_tree_off;
+    std::vector<uint32_t>&hdr = P.hdr, &split = P.split, &desc = P.desc;
+    group_tree_off.assign(n_groups_total, 0);
+    hdr.assign(n_groups_total, 0u);
+    split.assign(n_groups_total, 0u);
+    desc.assign(n_groups_total * (size_t)DW, 0u);
 #pragma omp parallel for schedule(static)
     for (int32_t s = 0; s < f->S; ++s) {
         const size_t g0 = (size_t)f->draw_group_off[(size_t)s];
@@ -869,10 +840,72 @@ int forest_upload(bartint_forest* f) {
     f->n_groups = (int64_t)group_tree_off.size();
     group_tree_off.push_back((int32_t)n_trees);
     // group g covers trees [group_tree_off[g], group_tree_off[g+1]) -- groups never span draws
+}
+
+// Walk form of the forest (what eval_walk_kernel, the WALK records and the table builder read): pre-order node
+// records, per-tree node / leaf offsets, leaf values by leaf ordinal.  Host only.
+void pack_walk_form(const bartint_forest* f, WalkForm& W) {
+    const int64_t n_trees = (int64_t)f->S * f->m;
+    const int64_t nn = f->n_nodes;
+    std::vector<uint2>& nodes = W.nodes;
+    std::vector<int32_t>&tree_off = W.tree_off, &leaf_off = W.leaf_off;
+    std::vector<double>& leaf_mu = W.leaf_mu;
+    nodes.resize((size_t)nn);
+    tree_off.resize((size_t)n_trees + 1);
+    leaf_off.assign((size_t)n_trees + 1, 0);
+    leaf_mu.resize((size_t)f->n_leaves);
+    for (int64_t k = 0; k <= n_trees; ++k) tree_off[(size_t)k] = (int32_t)f->tree_off[(size_t)k];
+    // leaf offsets (prefix sum), then fill
+    for (int64_t k = 0; k < n_trees; ++k) {
+        int32_t cnt = tree_off[(size_t)k + 1] - tree_off[(size_t)k];
+        leaf_off[(size_t)k + 1] = leaf_off[(size_t)k] + (cnt + 1) / 2;
+    }
+#pragma omp parallel for schedule(static)
+    for (int64_t k = 0; k < n_trees; ++k) {
+        const int32_t base = tree_off[(size_t)k], cnt = tree_off[(size_t)k + 1] - base;
+        int32_t ord = 0;
+        for (int32_t a = 0; a < cnt; ++a) {
+            const size_t g = (size_t)(base + a);
+            if (f->var[g] >= 0) {
+                nodes[g] = make_uint2((uint32_t)f->var[g] | ((uint32_t)f->cut[g] << 16), (uint32_t)(f->right[g] - a));
+            } else {
+                nodes[g] = make_uint2(LEAF_VAR, (uint32_t)ord);
+                leaf_mu[(size_t)leaf_off[(size_t)k] + ord] = f->mu[g];
+                ++ord;
+            }
+        }
+    }
+}
+
+int forest_upload(bartint_forest* f) {
+    PhaseTimer pt;
+    WalkForm W;
+    pack_walk_form(f, W);
+    const std::vector<uint2>& nodes = W.nodes;
+    const std::vector<int32_t>&tree_off = W.tree_off, &leaf_off = W.leaf_off;
+    const std::vector<double>& leaf_mu = W.leaf_mu;
+    int rc;
+    pt.lap("upload: pack walk form");
+    if ((rc = upload(&f->dev.nodes, nodes))) return rc;
+    if ((rc = upload(&f->dev.tree_off, tree_off))) return rc;
+    if ((rc = upload(&f->dev.tree_leaf_off, leaf_off))) return rc;
+    if ((rc = upload(&f->dev.leaf_mu, leaf_mu))) return rc;
+    if ((rc = upload(&f->dev.cut_off, f->cut_off))) return rc;
+    if ((rc = upload(&f->dev.cut_val, f->cut_val))) return rc;
+
+    pt.lap("upload: H2D walk form");
+    FastPlan P;
+    plan_fast_path(f, tree_off, P);
     pt.lap("upload: group planner");
-    if ((rc = upload(&f->dev.node_bit, node_bit))) return rc;
-    if ((rc = upload(&f->dev.tree_perm, tree_perm))) return rc;
-    if ((rc = upload(&f->dev.group_tree_off, group_tree_off))) return rc;
+    if (!f->table_ok) {
+        BI_CUDA(cudaStreamSynchronize(nullptr));
+        return BARTINT_OK;
+    }
+    const int DW = P.DW;
+    const std::vector<uint32_t>&desc = P.desc, &hdr = P.hdr, &split = P.split;
+    if ((rc = upload(&f->dev.node_bit, P.node_bit))) return rc;
+    if ((rc = upload(&f->dev.tree_perm, P.tree_perm))) return rc;
+    if ((rc = upload(&f->dev.group_tree_off, P.group_tree_off))) return rc;
     if ((rc = upload(&f->dev.draw_group_off, f->draw_group_off))) return rc;
     BI_CUDA(cudaMallocAsync((void**)&f->dev.group_rec, (size_t)f->n_groups * (size_t)fast_rec_bytes(f) + 16, nullptr));
     uint32_t *d_desc = nullptr, *d_hdr = nullptr, *d_split = nullptr;

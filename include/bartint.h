@@ -292,6 +292,28 @@ int bartint_design_step_dbarts098(const char* const* tree_strings, const double*
                                   int32_t measure, int32_t n_draws_integral, int32_t n_chunks, double* integrals_scaled,
                                   double* integral_mean_sd, double* cand_var, double* draw_mean, double* draw_mean_var);
 
+/* ---------------------------------------------------------------------------------------------
+ * Test hook, HOST ONLY (no device is touched, so it runs on a box without a GPU): canonicalises a pre-flattened
+ * forest exactly as bartint_forest_from_soa does and runs the same walk-form packer and group planner that
+ * forest creation runs before uploading, then copies the plan out instead of sending it to the GPU.  The CPU
+ * tests interpret the records with numpy (the PRMT / IDP.4A arithmetic of the gather kernel restated bit by
+ * bit) and compare with the oracle, so the planner -- bin packing, byte selectors, biases, weights, record
+ * flags -- is covered without a GPU.  It is not part of the drop-in surface; nothing in R calls it.
+ *   info[8] = {fast kernel applies, gather format, table bits NB, code words per point R, counting level,
+ *              number of group records, descriptor words per record DW, number of leaves}
+ * Caller-sized outputs: walk_nodes [2 n_nodes] (x, y words of every node record), tree_leaf_offset [S m + 1],
+ * leaf_mu_out [n_leaves = (n_nodes + S m) / 2], node_bit [n_nodes], tree_perm [S m], draw_group_offset [S + 1],
+ * group_tree_offset [group_capacity + 1], hdr / split [group_capacity], desc [16 group_capacity].
+ * group_capacity >= S m + 2 S + 1 always suffices; a smaller one that does not is BARTINT_ERR_ARG.
+ * ------------------------------------------------------------------------------------------- */
+int bartint_debug_plan_soa(int32_t S, int32_t m, int32_t d, const int64_t* tree_node_offset,
+                           const int32_t* split_var, const int32_t* split_cut_idx, const int32_t* left,
+                           const int32_t* right, const double* leaf_mu, const int32_t* cut_offsets,
+                           const double* cut_values, int64_t group_capacity, int64_t info[8], uint32_t* walk_nodes,
+                           int32_t* tree_leaf_offset, double* leaf_mu_out, uint8_t* node_bit, int32_t* tree_perm,
+                           int32_t* draw_group_offset, int32_t* group_tree_offset, uint32_t* hdr, uint32_t* split,
+                           uint32_t* desc);
+
 #ifdef __cplusplus
 }
 #endif

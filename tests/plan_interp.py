@@ -1,0 +1,220 @@
+"""Test infrastructure: a numpy interpreter of the group records the host planner produces.
+
+`debug_plan(ff)` runs the library's real planner on the host (bartint_debug_plan_soa, no device) and returns
+what forest creation would upload.  `interpret(plan, codes, sums_only)` then does, value by value, what the device
+does with it -- build_tables_kernel (kernels_misc.cu), dual_offsets / gather_offset / code_of
+(kernels_gather.cu), pred_mask4 / table_index (kernels_eval.cu) and the record-flag logic of the evaluation loops --
+so the planner's bin packing, byte selectors, biases, slot weights and flags are checked against the oracle
+without a GPU.  It restates the kernels' integer arithmetic; it does not replace the GPU parity tests.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from bartint_b200 import _lib
+
+FLAG_END_DRAW, FLAG_WALK, FLAG_JOINT, FLAG_COUNTABLE, FLAG_END_EVAL = 1, 2, 4, 8, 16
+LEAF_VAR = 0xFFFF
+
+
+def _p(a, ct):
+    return a.ctypes.data_as(C.POINTER(ct))
+
+
+def debug_plan(ff) -> dict:
+    lib = _lib.load()
+    S, m, d = int(ff.S), int(ff.m), int(ff.d)
+    n_trees = S * m
+    toff = np.ascontiguousarray(ff.tree_offset, np.int64)
+    n_nodes = int(toff[-1]) if n_trees else 0
+    cap = n_trees + 2 * S + 1
+    arr = lambda a, t: np.ascontiguousarray(a, t)
+    var, cut, left, right = (arr(getattr(ff, k), np.int32) for k in ("var", "cut", "left", "right"))
+    mu = arr(ff.mu, np.float64)
+    coff, cval = arr(ff.cut_offsets, np.int32), arr(ff.cut_values, np.float64)
+    info = np.zeros(8, np.int64)
+    out = dict(
+        walk_nodes=np.zeros(2 * max(n_nodes, 1), np.uint32), leaf_off=np.zeros(n_trees + 1, np.int32),
+        leaf_mu=np.zeros(max((n_nodes + n_trees) // 2, 1), np.float64), node_bit=np.zeros(max(n_nodes, 1), np.uint8),
+        tree_perm=np.zeros(max(n_trees, 1), np.int32), draw_group_off=np.zeros(S + 1, np.int32),
+        group_tree_off=np.zeros(cap + 1, np.int32), hdr=np.zeros(cap, np.uint32), split=np.zeros(cap, np.uint32),
+        desc=np.zeros(16 * cap, np.uint32))
+    rc = lib.bartint_debug_plan_soa(
+        S, m, d, _p(toff, C.c_int64), _p(var, C.c_int32), _p(cut, C.c_int32), _p(left, C.c_int32), _p(right, C.c_int32),
+        _p(mu, C.c_double), _p(coff, C.c_int32), _p(cval, C.c_double), cap, _p(info, C.c_int64),
+        _p(out["walk_nodes"], C.c_uint32), _p(out["leaf_off"], C.c_int32), _p(out["leaf_mu"], C.c_double),
+        _p(out["node_bit"], C.c_uint8), _p(out["tree_perm"], C.c_int32), _p(out["draw_group_off"], C.c_int32),
+        _p(out["group_tree_off"], C.c_int32), _p(out["hdr"], C.c_uint32), _p(out["split"], C.c_uint32),
+        _p(out["desc"], C.c_uint32))
+    if rc != 0:
+        raise RuntimeError(f"bartint_debug_plan_soa: status {rc}: {lib.bartint_last_error().decode()}")
+    table_ok, gather, nb, regs, level, n_groups, dw, n_leaves = (int(v) for v in info)
+    out.update(S=S, m=m, d=d, table_ok=bool(table_ok), gather=bool(gather), nb=nb, regs=regs, count_level=level,
+               n_groups=n_groups, dw=dw, n_leaves=n_leaves, tree_off=toff.astype(np.int64), n_nodes=n_nodes)
+    out["nodes_x"] = out["walk_nodes"][0::2][:n_nodes]
+    out["nodes_y"] = out["walk_nodes"][1::2][:n_nodes]
+    out["desc"] = out["desc"][:n_groups * dw].reshape(n_groups, dw) if n_groups else np.zeros((0, max(dw, 1)), np.uint32)
+    for k in ("hdr", "split"):
+        out[k] = out[k][:n_groups]
+    out["group_tree_off"] = out["group_tree_off"][:n_groups + 1]
+    return out
+
+
+# ---- the PTX pieces -------------------------------------------------------------------------------------------
+
+def byte_perm(a, b, sel):
+    """__byte_perm(a, b, sel): output byte i = byte (nibble i of sel) of the 8 bytes {a: 0..3, b: 4..7}."""
+    a = np.asarray(a, np.uint64)
+    b = np.asarray(b, np.uint64)
+    pool = a | (b << np.uint64(32))
+    out = np.zeros_like(pool)
+    for i in range(4):
+        nib = (int(sel) >> (4 * i)) & 0xF
+        assert nib < 8, "planner emitted a selector nibble with the sign-replicate bit set"
+        out |= ((pool >> np.uint64(8 * nib)) & np.uint64(0xFF)) << np.uint64(8 * i)
+    return out.astype(np.uint32)
+
+
+def dp4a_sign(v, w, acc):
+    """__dp4a(sign_mask4(v), w, acc): every byte of v with bit 7 set contributes -(signed byte of w)."""
+    v = np.asarray(v, np.uint32)
+    o = np.full(v.shape, acc, np.int64)
+    for i in range(4):
+        wb = (int(w) >> (8 * i)) & 0xFF
+        wb = wb - 256 if wb >= 128 else wb
+        o += np.where((v >> np.uint32(8 * i + 7)) & np.uint32(1), -wb, 0)
+    return o
+
+
+def add32(a, b):
+    return ((np.asarray(a, np.uint64) + np.uint64(int(b))) & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+
+
+def pack_words(codes, regs=4):
+    """codes [N, d] -> point-major packed words [N, 4] (byte j of the 16 = code of variable j), as K0 writes them."""
+    N, d = codes.shape
+    w = np.zeros((N, 4), np.uint32)
+    for j in range(d):
+        w[:, j >> 2] |= codes[:, j].astype(np.uint32) << np.uint32(8 * (j & 3))
+    return w
+
+
+# ---- build_tables_kernel --------------------------------------------------------------------------------------
+
+def _tree_value_for_idx(plan, k, idx):
+    """Leaf value of tree k selected by predicate bits idx (right at a node iff bit node_bit[node] of idx)."""
+    node = int(plan["tree_off"][k])
+    while (int(plan["nodes_x"][node]) & 0xFFFF) != LEAF_VAR:
+        bit = int(plan["node_bit"][node])
+        node += int(plan["nodes_y"][node]) if (idx >> bit) & 1 else 1
+    return plan["leaf_mu"][int(plan["leaf_off"][k]) + int(plan["nodes_y"][node])]
+
+
+def build_table(plan, k0, k1, n_entries):
+    tbl = np.zeros(n_entries)
+    for idx in range(n_entries):
+        s = 0.0
+        for kp in range(k0, k1):
+            s += _tree_value_for_idx(plan, int(plan["tree_perm"][kp]), idx)
+        tbl[idx] = s
+    return tbl
+
+
+def walk_tree(plan, k, codes):
+    """WALK record / walk kernel: per point node walk on codes (right iff code > cut index)."""
+    N = codes.shape[0]
+    base = int(plan["tree_off"][k])
+    node = np.full(N, base, np.int64)
+    for _ in range(int(plan["tree_off"][k + 1]) - base):
+        x = plan["nodes_x"][node].astype(np.int64)
+        internal = (x & 0xFFFF) != LEAF_VAR
+        if not internal.any():
+            break
+        v = np.where(internal, x & 0xFFFF, 0)
+        go_right = codes[np.arange(N), v] > (x >> 16)
+        node = np.where(internal, node + np.where(go_right, plan["nodes_y"][node].astype(np.int64), 1), node)
+    return plan["leaf_mu"][int(plan["leaf_off"][k]) + plan["nodes_y"][node].astype(np.int64)]
+
+
+# ---- the evaluation loop --------------------------------------------------------------------------------------
+
+def record_values(plan, g, codes, words):
+    """Sum over the record's trees of the leaf value of every point, formed the way the kernels form it."""
+    flags, tb, te = int(plan["hdr"][g]), int(plan["group_tree_off"][g]), int(plan["group_tree_off"][g + 1])
+    if flags & FLAG_WALK:
+        assert te - tb == 1
+        return walk_tree(plan, int(plan["tree_perm"][tb]), codes)
+    dsc = [int(v) for v in plan["desc"][g]]
+    R, nb = plan["regs"], plan["nb"]
+    if not plan["gather"]:
+        idx = np.zeros(codes.shape[0], np.int64)
+        for j in range(nb):
+            var, bias = dsc[2 * j], dsc[2 * j + 1] & 0xFF
+            assert dsc[2 * j + 1] == bias * 0x01010101
+            idx |= ((codes[:, var].astype(np.int64) + bias) >= 128).astype(np.int64) << j
+        return build_table(plan, tb, te, 1 << nb)[idx]
+    c = [words[:, r] for r in range(4)]
+    d0, d1, d2, d3, d4, kind, sel_t = dsc[:7]
+    if flags & FLAG_JOINT:
+        gA = byte_perm(c[0], c[1], d0 & 0xFFFF)
+        gB = byte_perm(c[R - 2], c[R - 1], d0 >> 16)
+        o = dp4a_sign(add32(gB, d2), d4, dp4a_sign(add32(gA, d1), d3, 0))
+        assert (o % 8 == 0).all() and (o >= 0).all() and (o < (8 << nb)).all()
+        return build_table(plan, tb, te, 1 << nb)[o // 8]
+    sp = int(plan["split"][g])
+    assert 0 <= sp <= te - tb
+    assert kind in (0, 1, 2)
+    lo = c[0] if (R == 2 or kind == 1) else c[R - 2] if kind == 0 else byte_perm(c[0], c[1], sel_t & 0xFFFF)
+    gA = byte_perm(c[0], c[1], d0 & 0xFFFF)
+    gB = byte_perm(lo, c[R - 1], d0 >> 16)
+    o1 = dp4a_sign(add32(gA, d1), d3, 0)
+    o2 = dp4a_sign(add32(gB, d2), d4, 128)
+    assert (o1 % 8 == 0).all() and (o1 >= 0).all() and (o1 < 128).all()
+    assert (o2 % 8 == 0).all() and (o2 >= 128).all() and (o2 < 256).all()
+    t1 = build_table(plan, tb, tb + sp, 16)
+    t2 = build_table(plan, tb + sp, te, 16)
+    return t1[o1 // 8] + t2[(o2 - 128) // 8]
+
+
+def interpret(plan, codes, sums_only: bool):
+    """(S, N) per-draw tree sums as the evaluation kernel accumulates them.  sums_only on a counting-mode plan skips
+    the COUNTABLE records and closes the draw at END_EVAL (the skipped trees are returned as a list per draw)."""
+    codes = np.asarray(codes, np.int64)
+    words = pack_words(codes) if plan["gather"] else None      # point-major words exist for d <= 16 only
+    S, N = plan["S"], codes.shape[0]
+    out = np.zeros((S, N))
+    skipped = [[] for _ in range(S)]
+    counting = sums_only and plan["count_level"] > 0
+    for s in range(S):
+        g0, g1 = int(plan["draw_group_off"][s]), int(plan["draw_group_off"][s + 1])
+        assert g1 > g0, "every draw needs at least one record"
+        closed = 0
+        for g in range(g0, g1):
+            flags = int(plan["hdr"][g])
+            if counting and flags & FLAG_COUNTABLE:
+                assert closed == 1, "COUNTABLE records must follow the END_EVAL record"
+                tb, te = int(plan["group_tree_off"][g]), int(plan["group_tree_off"][g + 1])
+                skipped[s] += [int(plan["tree_perm"][kp]) for kp in range(tb, te)]
+            else:
+                assert closed == 0, "an evaluated record after the draw was closed"
+                out[s] += record_values(plan, g, codes, words)
+            if flags & (FLAG_END_EVAL if counting else FLAG_END_DRAW):
+                closed += 1
+        assert closed == 1, "a draw must be closed exactly once"
+        assert int(plan["hdr"][g1 - 1]) & FLAG_END_DRAW
+    return out, skipped
+
+
+def check_structure(plan):
+    """Invariants every plan must satisfy whatever the format."""
+    S, m = plan["S"], plan["m"]
+    perm = plan["tree_perm"][:S * m]
+    for s in range(S):
+        assert sorted(perm[s * m:(s + 1) * m]) == list(range(s * m, (s + 1) * m)), "tree_perm must permute within a draw"
+    gto, dgo = plan["group_tree_off"], plan["draw_group_off"]
+    assert (np.diff(gto) >= 0).all() and int(gto[-1]) == S * m
+    assert int(dgo[0]) == 0 and int(dgo[-1]) == plan["n_groups"]
+    for s in range(S):
+        assert int(gto[dgo[s]]) == s * m, "groups never span draws"
