@@ -250,7 +250,7 @@ int bartint_debug_plan_soa(int32_t S, int32_t m, int32_t d, const int64_t* tree_
     FastPlan P;
     plan_fast_path(&f, W.tree_off, P);
     info[0] = f.table_ok ? 1 : 0; info[1] = f.gather ? 1 : 0; info[2] = f.nb; info[3] = f.g_regs;
-    info[4] = f.count_mode ? 1 : 0; info[5] = f.n_groups; info[6] = P.DW; info[7] = f.n_leaves;
+    info[4] = f.count_level; info[5] = f.n_groups; info[6] = P.DW; info[7] = f.n_leaves;
     BI_REQUIRE(f.n_groups <= group_capacity, BARTINT_ERR_ARG, "plan has %lld group records, capacity is %lld",
                (long long)f.n_groups, (long long)group_capacity);
     BI_REQUIRE(P.DW <= 16, BARTINT_ERR_UNSUPPORTED, "descriptor of %d words", P.DW);
@@ -969,7 +969,7 @@ int bartint_last_eval_profile(const bartint_forest* f, int32_t with_moments, flo
 namespace {
 struct ImageHeader {
     uint32_t magic, version;
-    int32_t S, m, d, max_depth, max_internal, max_cuts, route, table_ok, gather, g_regs, nb, reserved;   // reserved = count_mode
+    int32_t S, m, d, max_depth, max_internal, max_cuts, route, table_ok, gather, g_regs, nb, reserved;   // reserved = count_level
     int64_t n_nodes, n_leaves, n_groups, n_cuts, device_bytes;
     double y_min, y_max;
     int64_t bytes[11];       // device array sizes (0 = absent), order of image_arrays()
@@ -1022,7 +1022,7 @@ int bartint_forest_pack(const bartint_forest* f, void* host_header, int64_t host
     h.magic = kImageMagic; h.version = (uint32_t)bartint_version();
     h.S = f->S; h.m = f->m; h.d = f->d; h.max_depth = f->max_depth; h.max_internal = f->max_internal; h.max_cuts = f->max_cuts;
     h.route = f->route; h.table_ok = f->table_ok ? 1 : 0; h.gather = f->gather ? 1 : 0; h.g_regs = f->g_regs; h.nb = f->nb;
-    h.reserved = f->count_mode ? 1 : 0;
+    h.reserved = f->count_level;          // counting level of the records (0: none)
     h.n_nodes = f->n_nodes; h.n_leaves = f->n_leaves; h.n_groups = f->n_groups; h.n_cuts = (int64_t)f->cut_val.size();
     h.device_bytes = db; h.y_min = f->y_min; h.y_max = f->y_max;
     void** slots[11];
@@ -1072,6 +1072,7 @@ int bartint_forest_unpack(const void* host_header, int64_t host_bytes, const voi
     BI_REQUIRE(f != nullptr, BARTINT_ERR_NOMEM, "out of host memory");
     f->S = h.S; f->m = h.m; f->d = h.d; f->max_depth = h.max_depth; f->max_internal = h.max_internal; f->max_cuts = h.max_cuts;
     f->route = h.route; f->table_ok = h.table_ok != 0; f->gather = h.gather != 0; f->g_regs = h.g_regs; f->nb = h.nb;
+    f->count_level = h.reserved;
     f->count_mode = h.reserved != 0;
     f->n_nodes = h.n_nodes; f->n_leaves = h.n_leaves; f->n_groups = h.n_groups; f->y_min = h.y_min; f->y_max = h.y_max;
     const unsigned char* hp = (const unsigned char*)host_header + sizeof(ImageHeader);

@@ -58,9 +58,11 @@ constexpr uint32_t TK_FLAG_WALK = 2u;
 // gather format only: the record holds ONE joint 2^NB table over two gather rounds; unflagged gather records are DUAL
 // (two independent 16-entry tables: trees [first, first+split) -> table 1, the rest -> table 2; header.w = split).
 constexpr uint32_t TK_FLAG_JOINT = 4u;
-// Counting mode (gather format, opt-in BARTINT_COUNT_SPLITS=1): the single-split trees of a draw sit in COUNTABLE DUAL
-// records at the end of the draw; the last record before them carries END_EVAL.  An evaluation that only wants per-draw
-// sums skips the COUNTABLE records, closes the draw at END_EVAL, and gets those trees' sums from 1-D code histograms.
+// Counting mode (gather format, opt-in BARTINT_COUNT_SPLITS=1 or 2): the trees of a draw with at most that many splits
+// (and, for two splits, variables that fit one DUAL table: tg_dual_able) sit in COUNTABLE DUAL records at the end of
+// the draw; the last record before them carries END_EVAL.  An evaluation that only wants per-draw sums skips the
+// COUNTABLE records, closes the draw at END_EVAL, and gets those trees' sums from 1-D / 2-D cumulative code histograms
+// (launch_count_single_splits); an evaluation that wants per-point results treats them like any DUAL record.
 constexpr uint32_t TK_FLAG_COUNTABLE = 8u;
 constexpr uint32_t TK_FLAG_END_EVAL = 16u;
 __host__ __device__ constexpr int tk_tbl_off(int nb) { return TK_HDR + ((nb * 8 + 15) & ~15); }   // 16 B aligned
@@ -77,6 +79,14 @@ constexpr int TG_DESC = 32;
 __host__ __device__ constexpr int tg_tbl_off() { return TK_HDR + TG_DESC; }
 __host__ __device__ constexpr int tg_rec_bytes(int nb) { return tg_tbl_off() + ((8 << nb) < 256 ? 256 : (8 << nb)); }
 __host__ __device__ constexpr int tg_regs_for(int d) { return d <= 8 ? 2 : (d <= 12 ? 3 : 4); }
+// Can a tree whose split variables live in the code words `words` (bit r = word r) sit in one table of a DUAL
+// record?  Table 1 reads words (0,1); table 2 reads (R-2,R-1), (0,R-1) or (0,1,R-1).  With R <= 3 every set of words
+// qualifies; with R = 4 sets containing word 2 together with word 0 or 1 do not.  The planner (which trees may become
+// COUNTABLE) and count_draw_sums_kernel (which trees it adds) must agree, hence one definition for host and device.
+__host__ __device__ constexpr bool tg_dual_able(unsigned words, int R) {
+    const unsigned last = 1u << (R - 1);
+    return (words & ~3u) == 0u || (words & ~((1u << (R - 2)) | last)) == 0u || (words & ~(3u | last)) == 0u;
+}
 
 struct DeviceForest {
     uint2* nodes = nullptr;            // n_nodes
@@ -112,7 +122,8 @@ struct bartint_forest {
     bool defer_upload_sync = false;    // forest_upload leaves its default-stream work in flight (pipelined design step)
     bool table_ok = false;             // a fast (table or gather) kernel applies
     bool gather = false;               // group records are in the gather format (else table format)
-    bool count_mode = false;           // gather format with COUNTABLE records for the single-split trees
+    bool count_mode = false;           // gather format with COUNTABLE records for the trees of <= count_level splits
+    int count_level = 0;               // 1: single-split trees (1-D code histograms); 2: + two-split trees (2-D)
     int g_regs = 0;                    // gather: code words per point
     int nb = 0;
     int64_t n_groups = 0;

@@ -483,7 +483,9 @@ void plan_fast_path(bartint_forest* f, const std::vector<int32_t>& tree_off, Fas
     f->gather = f->table_ok && f->d <= 16 && f->d >= 1 && !(kenv && strcmp(kenv, "table") == 0);
     if (f->gather && f->nb > 5) f->nb = 5;                 // slot weights -(8 << bit) must fit a signed byte
     const char* cenv = getenv("BARTINT_COUNT_SPLITS");
-    f->count_mode = f->gather && cenv && cenv[0] == '1';    // opt-in: single-split trees counted in sums-only evaluations
+    // opt-in: trees of <= 1 (or 2) splits are counted, not evaluated, in sums-only evaluations
+    f->count_level = (f->gather && cenv && (cenv[0] == '1' || cenv[0] == '2')) ? cenv[0] - '0' : 0;
+    f->count_mode = f->count_level > 0;
     f->g_regs = tg_regs_for(f->d);
     f->n_groups = 0;
     f->draw_group_off.clear();
@@ -617,28 +619,32 @@ void plan_fast_path(bartint_forest* f, const std::vector<int32_t>& tree_off, Fas
         std::vector<Bin> bins1, bins2;
         std::vector<int32_t> stumps, joint_trees, walk_trees;
         std::vector<int64_t> tn;
-        std::vector<std::pair<unsigned, int32_t>> singles;       // counting mode: (word mask, tree) of single-split trees
-        int dual_nodes = 0;
+        std::vector<Item> countable;                             // counting mode: trees of <= count_level splits
         for (int32_t t = 0; t < f->m; ++t) {
             internal_nodes((int64_t)s * f->m + t, tn);
             if (tn.empty()) { stumps.push_back(t); continue; }
             unsigned regs = 0;
             for (int64_t g : tn) regs |= 1u << (f->var[(size_t)g] >> 2);
             const int k = (int)tn.size();
-            if (f->count_mode && k == 1) { singles.emplace_back(regs, t); continue; }    // counted, not evaluated (sums)
-            if (k <= 4 && (within(regs, m_side1) || side2_ok(regs))) {
+            const bool dual_able = within(regs, m_side1) || side2_ok(regs);      // == tg_dual_able(regs, R)
+            // counted, not evaluated, when only sums are wanted.  Only trees that fit a DUAL table: an evaluation that
+            // wants per-point results evaluates the COUNTABLE records like any other (a two-split tree on words (0,2)
+            // or (1,2) of a four-word point stays in the evaluated part; count_draw_sums_kernel applies the same test)
+            if (f->count_mode && k <= f->count_level && dual_able) {
+                countable.push_back(Item{k, regs, (int)within(regs, m_side1) + (int)pair_ok(regs), t});
+                continue;
+            }
+            if (k <= 4 && dual_able) {
                 items.push_back(Item{k, regs, (int)within(regs, m_side1) + (int)pair_ok(regs), t});
-                dual_nodes += k;
             } else {
                 (k <= NB ? joint_trees : walk_trees).push_back(t);
             }
         }
-        std::stable_sort(items.begin(), items.end(),
-                         [](const Item& a, const Item& b2) { return a.k != b2.k ? a.k > b2.k : a.flex < b2.flex; });
+        const std::vector<Item>* cur_items = &items;             // the set try_pack / pack_and_emit work on
         auto try_pack = [&](int K) -> bool {
             bins1.assign((size_t)K, Bin{});
             bins2.assign((size_t)K, Bin{});
-            for (const Item& it : items) {
+            for (const Item& it : *cur_items) {
                 Bin* best = nullptr;
                 int best_key = 0;                         // lower is better: widening << 8 | (4 - fill) << 1 | side 2
                 const int exact1 = it.k << 1, exact2 = (it.k << 1) | 1;      // keys of bins this tree would fill exactly
@@ -665,8 +671,6 @@ void plan_fast_path(bartint_forest* f, const std::vector<int32_t>& tree_off, Fas
             }
             return true;
         };
-        int K = (dual_nodes + 7) / 8;
-        while (!try_pack(K)) ++K;                         // K = number of trees always fits
         int32_t* perm = tree_perm.data() + (size_t)s * f->m;
         int32_t pos = 0;                                  // next permuted position inside the draw
         auto emit_table = [&](const Bin& bin, int table, uint32_t* gd) {
@@ -698,33 +702,59 @@ void plan_fast_path(bartint_forest* f, const std::vector<int32_t>& tree_off, Fas
             if (table == 0) { gd[0] |= sel; gd[1] = bias; gd[3] = wgt; }
             else { gd[0] |= sel << 16; gd[2] = bias; gd[4] = wgt; gd[5] = (uint32_t)ps; gd[6] = sel_t; }
         };
-        // emit, sorted by table-2 kind so the kernel's per-record variant branch changes rarely
-        std::vector<int> rec_order;
-        for (int r = 0; r < K; ++r)
-            if (!bins1[(size_t)r].trees.empty() || !bins2[(size_t)r].trees.empty()) rec_order.push_back(r);
-        auto kind_of = [&](int r) {
-            const Bin& b = bins2[(size_t)r];
-            return b.trees.empty() || within(b.regs, m_pair0) ? 0 : within(b.regs, m_pair1) ? 1 : 2;
-        };
-        std::stable_sort(rec_order.begin(), rec_order.end(), [&](int a, int b2) { return kind_of(a) < kind_of(b2); });
-        if (rec_order.empty() && !stumps.empty() && joint_trees.empty() && walk_trees.empty()) {
-            bins1.assign(1, Bin{});
-            bins2.assign(1, Bin{});
-            rec_order.push_back(0);                       // a draw of stumps only: one record holding the constant
-        }
-        for (size_t q = 0; q < rec_order.size(); ++q) {
-            const int r = rec_order[q];
-            open_group((int64_t)s * f->m + pos, 0u);
-            uint32_t* gd = &desc[desc.size() - (size_t)DW];
-            const int32_t start = pos;
-            if (q == 0) {                                 // stumps only add a constant: all into the first table 1
-                for (int32_t t : stumps) perm[pos++] = (int32_t)((int64_t)s * f->m + t);
-                stumps.clear();
+        // pack a set of DUAL-able trees into the fewest records and emit them with the given record flags
+        auto pack_and_emit = [&](std::vector<Item>& set, uint32_t rec_flags, bool evaluated_part) {
+            std::stable_sort(set.begin(), set.end(),
+                             [](const Item& a, const Item& b2) { return a.k != b2.k ? a.k > b2.k : a.flex < b2.flex; });
+            cur_items = &set;
+            int set_nodes = 0;
+            for (const Item& it : set) set_nodes += it.k;
+            // Every tree of the set fits an empty table on its own (that is what put it into the set), so
+            // K = number of trees always succeeds and the search ends there at the latest.
+            const int K_max = std::max<int>(1, (int)set.size());
+            int K = std::min(K_max, std::max(1, (set_nodes + 7) / 8));
+            bool packed = try_pack(K);
+            while (!packed && K < K_max) packed = try_pack(++K);
+            if (!packed) {                                // unreachable by the argument above; never lose a tree
+                K = K_max;
+                bins1.assign((size_t)K, Bin{});
+                bins2.assign((size_t)K, Bin{});
+                for (size_t q = 0; q < set.size(); ++q) {
+                    Bin& b = within(set[q].regs, m_side1) ? bins1[q] : bins2[q];
+                    b.nodes = set[q].k;
+                    b.regs = set[q].regs;
+                    b.trees.push_back(set[q].tree);
+                }
             }
-            emit_table(bins1[(size_t)r], 0, gd);
-            split.back() = (uint32_t)(pos - start);
-            emit_table(bins2[(size_t)r], 1, gd);
-        }
+            // emit, sorted by table-2 kind so the kernel's per-record variant branch changes rarely
+            std::vector<int> rec_order;
+            for (int r = 0; r < K; ++r)
+                if (!bins1[(size_t)r].trees.empty() || !bins2[(size_t)r].trees.empty()) rec_order.push_back(r);
+            auto kind_of = [&](int r) {
+                const Bin& b = bins2[(size_t)r];
+                return b.trees.empty() || within(b.regs, m_pair0) ? 0 : within(b.regs, m_pair1) ? 1 : 2;
+            };
+            std::stable_sort(rec_order.begin(), rec_order.end(), [&](int a, int b2) { return kind_of(a) < kind_of(b2); });
+            if (evaluated_part && rec_order.empty() && !stumps.empty() && joint_trees.empty() && walk_trees.empty()) {
+                bins1.assign(1, Bin{});
+                bins2.assign(1, Bin{});
+                rec_order.push_back(0);                   // a draw of stumps only: one record holding the constant
+            }
+            for (size_t q = 0; q < rec_order.size(); ++q) {
+                const int r = rec_order[q];
+                open_group((int64_t)s * f->m + pos, rec_flags);
+                uint32_t* gd = &desc[desc.size() - (size_t)DW];
+                const int32_t start = pos;
+                if (evaluated_part && q == 0) {           // stumps only add a constant: all into the first table 1
+                    for (int32_t t : stumps) perm[pos++] = (int32_t)((int64_t)s * f->m + t);
+                    stumps.clear();
+                }
+                emit_table(bins1[(size_t)r], 0, gd);
+                split.back() = (uint32_t)(pos - start);
+                emit_table(bins2[(size_t)r], 1, gd);
+            }
+        };
+        pack_and_emit(items, 0u, true);
         // JOINT records: greedy packing of the remaining small trees, two rounds of <= 4 slots, <= NB bits
         std::vector<Slot> gslots;
         int used[2] = {0, 0}, jbits = 0;
@@ -797,23 +827,7 @@ void plan_fast_path(bartint_forest* f, const std::vector<int32_t>& tree_off, Fas
             // DUAL record when per-point results are wanted, skipped and counted when only per-draw sums are.
             if (hdr.empty()) open_group((int64_t)s * f->m + pos, 0u);
             hdr.back() |= TK_FLAG_END_EVAL;
-            std::vector<std::pair<unsigned, int32_t>> side_a, side_b;
-            for (const auto& rt : singles) (within(rt.first, m_side1) ? side_a : side_b).push_back(rt);
-            size_t ia = 0, ib = 0;
-            while (ia < side_a.size() || ib < side_b.size()) {
-                Bin b1, b2;
-                while (ia < side_a.size() && b1.nodes < 4) { b1.regs |= side_a[ia].first; b1.trees.push_back(side_a[ia].second); ++b1.nodes; ++ia; }
-                while (ib < side_b.size() && b2.nodes < 4) { b2.regs |= side_b[ib].first; b2.trees.push_back(side_b[ib].second); ++b2.nodes; ++ib; }
-                while (ia < side_a.size() && b2.nodes < 4 && side2_ok(b2.regs | side_a[ia].first)) {   // table 2 also reads words 0/1
-                    b2.regs |= side_a[ia].first; b2.trees.push_back(side_a[ia].second); ++b2.nodes; ++ia;
-                }
-                open_group((int64_t)s * f->m + pos, TK_FLAG_COUNTABLE);
-                uint32_t* gd = &desc[desc.size() - (size_t)DW];
-                const int32_t start = pos;
-                emit_table(b1, 0, gd);
-                split.back() = (uint32_t)(pos - start);
-                emit_table(b2, 1, gd);
-            }
+            pack_and_emit(countable, TK_FLAG_COUNTABLE, false);
         }
         hdr.back() |= TK_FLAG_END_DRAW;
     }

@@ -298,12 +298,68 @@ __global__ void suffix_counts_kernel(const unsigned int* __restrict__ hist, int 
     }
 }
 
-// one warp per draw: lanes stride over the draw's trees, fixed-order shuffle reduction, result ADDED to draw_sum
+// 2-D histograms for the two-split trees: pair q = (a < b) of variables, hist2[q][code_a][code_b].  One CTA per
+// (pair, slice of the points) with a private 128 x 128 shared-memory histogram, flushed with global atomics.
+__device__ __forceinline__ void pair_of_index(int q, int d, int& a, int& b) {
+    a = 0;
+    while (q >= d - 1 - a) { q -= d - 1 - a; ++a; }
+    b = a + 1 + q;
+}
+__host__ __device__ __forceinline__ int index_of_pair(int a, int b, int d) { return a * d - a * (a + 1) / 2 + (b - a - 1); }
+
+__global__ void __launch_bounds__(256) hist2_codes_kernel(const uint4* __restrict__ codes_pm, int64_t N, int d,
+                                                          unsigned int* __restrict__ hist2 /* [pairs][128][128] */) {
+    extern __shared__ unsigned int h2[];             // 128 x 128
+    for (int k = threadIdx.x; k < 128 * 128; k += blockDim.x) h2[k] = 0u;
+    __syncthreads();
+    int a, b;
+    pair_of_index((int)blockIdx.x, d, a, b);
+    const int64_t per = (N + gridDim.y - 1) / gridDim.y;
+    const int64_t i0 = (int64_t)blockIdx.y * per, i1 = min(N, i0 + per);
+    const uint32_t* __restrict__ words = reinterpret_cast<const uint32_t*>(codes_pm);
+    for (int64_t i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+        const uint32_t ca = (words[4 * i + (a >> 2)] >> (8 * (a & 3))) & 127u;
+        const uint32_t cb = (words[4 * i + (b >> 2)] >> (8 * (b & 3))) & 127u;
+        atomicAdd(&h2[ca * 128 + cb], 1u);
+    }
+    __syncthreads();
+    unsigned int* __restrict__ out = hist2 + (size_t)blockIdx.x * 128 * 128;
+    for (int k = threadIdx.x; k < 128 * 128; k += blockDim.x)
+        if (h2[k] != 0u) atomicAdd(&out[k], h2[k]);
+}
+
+// in place: hist2[q][x][y]  ->  J[q][x][y] = #{code_a > x and code_b > y}   (one CTA of 128 threads per pair)
+__global__ void __launch_bounds__(128) suffix2_counts_kernel(unsigned int* __restrict__ hist2) {
+    extern __shared__ unsigned int h2[];
+    unsigned int* __restrict__ g = hist2 + (size_t)blockIdx.x * 128 * 128;
+    for (int k = threadIdx.x; k < 128 * 128; k += blockDim.x) h2[k] = g[k];
+    __syncthreads();
+    {   // along y, row x = threadIdx.x: E[x][y] = sum_{y' > y} h[x][y']
+        unsigned int* row = h2 + threadIdx.x * 128;
+        unsigned int run = 0;
+        for (int y = 127; y >= 0; --y) { const unsigned int t = row[y]; row[y] = run; run += t; }
+    }
+    __syncthreads();
+    {   // along x, column y = threadIdx.x: J[x][y] = sum_{x' > x} E[x'][y]
+        unsigned int run = 0;
+        for (int x = 127; x >= 0; --x) { const unsigned int t = h2[x * 128 + threadIdx.x]; h2[x * 128 + threadIdx.x] = run; run += t; }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < 128 * 128; k += blockDim.x) g[k] = h2[k];
+}
+
+// one warp per draw: lanes stride over the draw's trees, fixed-order shuffle reduction, result ADDED to draw_sum.
+// Single-split trees (3 nodes) from the 1-D counts G; with level2 also two-split trees (5 nodes):
+//   child on the LEFT  of the root: leaves (LL, LR, R):  n_R = G1,  n_LR = G2 - J,  n_LL = N - G1 - n_LR
+//   child on the RIGHT of the root: leaves (L, RL, RR):  n_L = N - G1,  n_RL = G1 - J,  n_RR = J
+// with G1 = #{code[v1] > c1}, G2 = #{code[v2] > c2}, J = #{both}  (same variable: J = G[v][max(c1, c2)]).
 __global__ void __launch_bounds__(256) count_draw_sums_kernel(const uint2* __restrict__ nodes, const int32_t* __restrict__ tree_off,
                                                               const int32_t* __restrict__ tree_leaf_off,
                                                               const double* __restrict__ leaf_mu,
-                                                              const long long* __restrict__ G, long long N, int m,
-                                                              int draw_begin, int draw_end, double* __restrict__ draw_sum) {
+                                                              const long long* __restrict__ G,
+                                                              const unsigned int* __restrict__ J2, int level2, int d,
+                                                              long long N, int m, int draw_begin, int draw_end,
+                                                              double* __restrict__ draw_sum) {
     const int s = draw_begin + (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
     if (s >= draw_end) return;
@@ -311,11 +367,32 @@ __global__ void __launch_bounds__(256) count_draw_sums_kernel(const uint2* __res
     for (int t = lane; t < m; t += 32) {
         const int64_t k = (int64_t)s * m + t;
         const int32_t base = tree_off[k];
-        if (tree_off[k + 1] - base != 3) continue;            // exactly one split: root + two leaves
-        const uint2 r = nodes[base];
-        const long long g = G[(r.x & 0xFFFFu) * 128 + (r.x >> 16)];
+        const int32_t cnt = tree_off[k + 1] - base;
         const int32_t lb = tree_leaf_off[k];
-        acc += leaf_mu[lb] * (double)(N - g) + leaf_mu[lb + 1] * (double)g;
+        if (cnt == 3) {                                      // exactly one split: root + two leaves
+            const uint2 r = nodes[base];
+            const long long g = G[(r.x & 0xFFFFu) * 128 + (r.x >> 16)];
+            acc += leaf_mu[lb] * (double)(N - g) + leaf_mu[lb + 1] * (double)g;
+        } else if (cnt == 5 && level2) {                     // two splits (J2 exists whenever d >= 2)
+            const uint2 r0 = nodes[base];
+            const uint2 n1 = nodes[base + 1];
+            const bool child_left = (n1.x & 0xFFFFu) != LEAF_VAR;
+            const uint2 ch = child_left ? n1 : nodes[base + r0.y];
+            const int v1 = (int)(r0.x & 0xFFFFu), c1 = (int)(r0.x >> 16), v2 = (int)(ch.x & 0xFFFFu), c2 = (int)(ch.x >> 16);
+            // the planner left this tree in the evaluated part if its two code words fit no DUAL table (d > 12 only)
+            if (!tg_dual_able((1u << (v1 >> 2)) | (1u << (v2 >> 2)), tg_regs_for(d))) continue;
+            const long long g1 = G[v1 * 128 + c1], g2 = G[v2 * 128 + c2];
+            long long j;
+            if (v1 == v2) j = G[v1 * 128 + max(c1, c2)];
+            else if (v1 < v2) j = J2[((size_t)index_of_pair(v1, v2, d) * 128 + c1) * 128 + c2];
+            else j = J2[((size_t)index_of_pair(v2, v1, d) * 128 + c2) * 128 + c1];
+            if (child_left) {
+                const long long n_lr = g2 - j;
+                acc += leaf_mu[lb] * (double)(N - g1 - n_lr) + leaf_mu[lb + 1] * (double)n_lr + leaf_mu[lb + 2] * (double)g1;
+            } else {
+                acc += leaf_mu[lb] * (double)(N - g1) + leaf_mu[lb + 1] * (double)(g1 - j) + leaf_mu[lb + 2] * (double)j;
+            }
+        }
     }
     acc = warp_sum_misc(acc);
     if (lane == 0) draw_sum[s - draw_begin] += acc;
@@ -325,19 +402,36 @@ int launch_count_single_splits(const bartint_forest* f, const bartint_points* p,
                                double* d_draw_sum, cudaStream_t st) {
     const int ndraws = draw_end - draw_begin;
     if (ndraws <= 0) return BARTINT_OK;
+    const int d = p->d;
+    const int pairs = (f->count_level >= 2 && d >= 2) ? d * (d - 1) / 2 : 0;
     unsigned int* d_hist = nullptr;
-    BI_CUDA(cudaMallocAsync((void**)&d_hist, 16 * 128 * (sizeof(unsigned int) + sizeof(long long)), st));
+    const size_t b1 = 16 * 128 * (sizeof(unsigned int) + sizeof(long long));
+    const size_t b2 = (size_t)pairs * 128 * 128 * sizeof(unsigned int);
+    BI_CUDA(cudaMallocAsync((void**)&d_hist, b1 + b2, st));
     long long* d_G = reinterpret_cast<long long*>(d_hist + 16 * 128);
+    unsigned int* d_J2 = pairs ? reinterpret_cast<unsigned int*>(reinterpret_cast<unsigned char*>(d_hist) + b1) : nullptr;
     BI_CUDA(cudaMemsetAsync(d_hist, 0, 16 * 128 * sizeof(unsigned int), st));
+    if (pairs) BI_CUDA(cudaMemsetAsync(d_J2, 0, b2, st));
     if (p->N > 0) {
         const int64_t want = (p->N + 255) / 256;
-        hist_codes_kernel<<<(unsigned)std::min<int64_t>(want, 148 * 4), 256, 0, st>>>(p->codes_pm, p->N, p->d, d_hist);
+        hist_codes_kernel<<<(unsigned)std::min<int64_t>(want, 148 * 4), 256, 0, st>>>(p->codes_pm, p->N, d, d_hist);
+        if (pairs) {
+            static bool attr_set = false;
+            if (!attr_set) {
+                BI_CUDA(cudaFuncSetAttribute(hist2_codes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 128 * 4));
+                BI_CUDA(cudaFuncSetAttribute(suffix2_counts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 128 * 4));
+                attr_set = true;
+            }
+            const int slices = (int)std::max<int64_t>(1, std::min<int64_t>((148 * 3 + pairs - 1) / pairs, (p->N + 4095) / 4096));
+            hist2_codes_kernel<<<dim3((unsigned)pairs, (unsigned)slices), 256, 128 * 128 * 4, st>>>(p->codes_pm, p->N, d, d_J2);
+        }
     }
-    suffix_counts_kernel<<<1, 32, 0, st>>>(d_hist, p->d, d_G);
+    suffix_counts_kernel<<<1, 32, 0, st>>>(d_hist, d, d_G);
+    if (pairs) suffix2_counts_kernel<<<(unsigned)pairs, 128, 128 * 128 * 4, st>>>(d_J2);
     count_draw_sums_kernel<<<(unsigned)((ndraws * 32 + 255) / 256), 256, 0, st>>>(
-        f->dev.nodes, f->dev.tree_off, f->dev.tree_leaf_off, f->dev.leaf_mu, d_G, (long long)p->N, f->m, draw_begin, draw_end,
-        d_draw_sum);
-    count_launch(3);
+        f->dev.nodes, f->dev.tree_off, f->dev.tree_leaf_off, f->dev.leaf_mu, d_G, d_J2, f->count_level >= 2 ? 1 : 0, d,
+        (long long)p->N, f->m, draw_begin, draw_end, d_draw_sum);
+    count_launch(pairs ? 5 : 3);
     cudaError_t e = cudaGetLastError();
     cudaFreeAsync(d_hist, st);
     BI_CUDA(e);

@@ -218,3 +218,66 @@ def check_structure(plan):
     assert int(dgo[0]) == 0 and int(dgo[-1]) == plan["n_groups"]
     for s in range(S):
         assert int(gto[dgo[s]]) == s * m, "groups never span draws"
+
+
+# ---- counting mode: hist_codes / suffix_counts / hist2 / suffix2 / count_draw_sums_kernel ------------------------
+
+def dual_able(words, R):
+    """tg_dual_able (common.cuh)."""
+    last = 1 << (R - 1)
+    return (words & ~3) == 0 or (words & ~((1 << (R - 2)) | last)) == 0 or (words & ~(3 | last)) == 0
+
+
+def count_sums(plan, codes):
+    """Per-draw sums over the points of the trees the counting kernel handles, from cumulative code histograms only
+    (never touching a point again), with the kernel's own rule for which trees those are.  Returns (sums [S], trees
+    counted per draw)."""
+    codes = np.asarray(codes, np.int64)
+    N, d = codes.shape
+    level, R = plan["count_level"], plan["regs"]
+    hist = np.zeros((d, 128), np.int64)
+    for v in range(d):
+        hist[v] = np.bincount(codes[:, v] & 127, minlength=128)
+    G = np.zeros((d, 128), np.int64)                      # G[v][c] = #{code[v] > c}
+    for v in range(d):
+        G[v] = hist[v][::-1].cumsum()[::-1] - hist[v]
+    J2 = {}
+    if level >= 2:
+        for a in range(d):
+            for b in range(a + 1, d):
+                h2 = np.zeros((128, 128), np.int64)
+                np.add.at(h2, (codes[:, a] & 127, codes[:, b] & 127), 1)
+                e = h2[:, ::-1].cumsum(axis=1)[:, ::-1] - h2                   # along y: sum over y' > y
+                J2[(a, b)] = e[::-1].cumsum(axis=0)[::-1] - e                  # along x: sum over x' > x
+    nx, ny, toff, loff, mu = plan["nodes_x"], plan["nodes_y"], plan["tree_off"], plan["leaf_off"], plan["leaf_mu"]
+    S, m = plan["S"], plan["m"]
+    sums, counted = np.zeros(S), [[] for _ in range(S)]
+    for s in range(S):
+        for t in range(m):
+            k = s * m + t
+            base, cnt, lb = int(toff[k]), int(toff[k + 1] - toff[k]), int(loff[k])
+            if cnt == 3:
+                v, c = int(nx[base]) & 0xFFFF, int(nx[base]) >> 16
+                g = int(G[v][c])
+                sums[s] += mu[lb] * float(N - g) + mu[lb + 1] * float(g)
+                counted[s].append(k)
+            elif cnt == 5 and level >= 2:
+                child_left = (int(nx[base + 1]) & 0xFFFF) != LEAF_VAR
+                ch = base + 1 if child_left else base + int(ny[base])
+                v1, c1, v2, c2 = int(nx[base]) & 0xFFFF, int(nx[base]) >> 16, int(nx[ch]) & 0xFFFF, int(nx[ch]) >> 16
+                if not dual_able((1 << (v1 >> 2)) | (1 << (v2 >> 2)), R):
+                    continue
+                g1, g2 = int(G[v1][c1]), int(G[v2][c2])
+                if v1 == v2:
+                    j = int(G[v1][max(c1, c2)])
+                elif v1 < v2:
+                    j = int(J2[(v1, v2)][c1][c2])
+                else:
+                    j = int(J2[(v2, v1)][c2][c1])
+                if child_left:
+                    n_lr = g2 - j
+                    sums[s] += mu[lb] * float(N - g1 - n_lr) + mu[lb + 1] * float(n_lr) + mu[lb + 2] * float(g1)
+                else:
+                    sums[s] += mu[lb] * float(N - g1) + mu[lb + 1] * float(g1 - j) + mu[lb + 2] * float(j)
+                counted[s].append(k)
+    return sums, counted

@@ -6,16 +6,14 @@ import pytest
 from oracle import oracle_np as onp
 from oracle import oracle_c as oc
 from bartint_b200 import Forest, StagedMatrix, WireStrings, design_step_dbarts, synth, BartIntError
+from bartint_testlib import apply_kernel_kind, kernel_kind_params
 
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["gather", "table", "gather+count"], autouse=True)
+@pytest.fixture(params=kernel_kind_params(), autouse=True)
 def kernel_kind(request, monkeypatch):
-    kind, _, count = request.param.partition("+")
-    monkeypatch.setenv("BARTINT_KERNEL", kind)
-    monkeypatch.setenv("BARTINT_COUNT_SPLITS", "1" if count else "0")
-    return kind
+    return apply_kernel_kind(request.param, monkeypatch)
 
 
 def _case(S=37, m=11, d=6, n=80, N=5000, C=300, seed=3):

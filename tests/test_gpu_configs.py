@@ -7,16 +7,14 @@ import pytest
 from oracle import oracle_c as oc
 from oracle import oracle_np as onp
 from bartint_b200 import Forest, synth
+from bartint_testlib import apply_kernel_kind, kernel_kind_params
 
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["gather", "table", "gather+count"], autouse=True)
+@pytest.fixture(params=kernel_kind_params(), autouse=True)
 def kernel_kind(request, monkeypatch):
-    kind, _, count = request.param.partition("+")
-    monkeypatch.setenv("BARTINT_KERNEL", kind)
-    monkeypatch.setenv("BARTINT_COUNT_SPLITS", "1" if count else "0")
-    return kind
+    return apply_kernel_kind(request.param, monkeypatch)
 
 
 def _close(got, want, tol, scale=None):

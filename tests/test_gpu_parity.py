@@ -11,19 +11,16 @@ import pytest
 
 from oracle import oracle_np as onp
 from bartint_b200 import Forest, synth, api
-from bartint_testlib import kat_forest
+from bartint_testlib import apply_kernel_kind, kat_forest, kernel_kind_params
 
 pytestmark = pytest.mark.gpu
 
-@pytest.fixture(params=["gather", "table", "gather+count"], autouse=True)
+@pytest.fixture(params=kernel_kind_params(), autouse=True)
 def kernel_kind(request, monkeypatch):
     """Every parity test runs against both fast kernels: the register-gather kernel (default for d <= 16) and the
     shared-memory table kernel (forced with BARTINT_KERNEL=table; the default for d > 16) -- and against the gather
     kernel in counting mode (BARTINT_COUNT_SPLITS=1: single-split trees' per-draw sums from code histograms)."""
-    kind, _, count = request.param.partition("+")
-    monkeypatch.setenv("BARTINT_KERNEL", kind)
-    monkeypatch.setenv("BARTINT_COUNT_SPLITS", "1" if count else "0")
-    return kind
+    return apply_kernel_kind(request.param, monkeypatch)
 
 
 RTOL = 1e-6            # the north-star tolerance

@@ -35,11 +35,19 @@ def _check_against_oracle(ff, X, codes, monkeypatch, kernel, count):
     np.testing.assert_allclose(got, want, rtol=0, atol=1e-13)
     # sums-only evaluation: COUNTABLE records skipped; their trees are exactly the ones the counting kernel adds
     got, skipped = pi.interpret(plan, codes, sums_only=True)
+    csum, counted = pi.count_sums(plan, codes) if plan["count_level"] else (np.zeros(ff.S), [[] for _ in range(ff.S)])
     nodes = np.diff(np.asarray(ff.tree_offset))
     for s in range(ff.S):
+        # the trees the planner put behind END_EVAL are exactly the trees the counting kernel adds
+        assert sorted(skipped[s]) == sorted(counted[s])
         ks = np.arange(s * ff.m, (s + 1) * ff.m)
-        countable = {int(k) for k in ks if 3 <= nodes[k] <= 1 + 2 * plan["count_level"]}
-        assert set(skipped[s]) == countable
+        small = {int(k) for k in ks if 3 <= nodes[k] <= 1 + 2 * plan["count_level"]}
+        assert set(skipped[s]) <= small
+        if ff.d <= 12:
+            assert set(skipped[s]) == small               # up to three code words every small tree fits a DUAL table
+    # per-draw sums: evaluated records + histogram counts == oracle
+    np.testing.assert_allclose(got.sum(axis=1) + csum, want.sum(axis=1), rtol=1e-12, atol=1e-12)
+    for s in range(ff.S):
         for k in skipped[s]:
             got[s] += pi.walk_tree(plan, k, codes)
     np.testing.assert_allclose(got, want, rtol=0, atol=1e-13)
@@ -47,7 +55,7 @@ def _check_against_oracle(ff, X, codes, monkeypatch, kernel, count):
 
 
 @pytest.mark.parametrize("d", [1, 2, 3, 4, 5, 8, 9, 10, 12, 13, 14, 16])
-@pytest.mark.parametrize("count", [0, 1])
+@pytest.mark.parametrize("count", [0, 1, 2])
 def test_gather_records_reproduce_the_oracle(d, count, monkeypatch):
     ff, X, codes = _case(d, seed=100 + d)
     plan = _check_against_oracle(ff, X, codes, monkeypatch, "gather", count)
@@ -71,8 +79,8 @@ def test_table_bits(bits, monkeypatch):
 
 
 @pytest.mark.parametrize("kind", ["stumps", "left_chain", "right_chain", "same_var", "balanced", "edge_cuts"])
-@pytest.mark.parametrize("d", [3, 11, 16])
-@pytest.mark.parametrize("count", [0, 1])
+@pytest.mark.parametrize("d", [1, 3, 11, 16])
+@pytest.mark.parametrize("count", [0, 1, 2])
 def test_adversarial_shapes(kind, d, count, monkeypatch):
     # deep chains become WALK records, 5-node trees JOINT records, same_var trees put all nodes on one code word
     ff = synth.adversarial_forest(kind, 2, 7, d, numcut=100, seed=d, depth=7)
@@ -137,3 +145,22 @@ def test_capacity_too_small_is_an_error_not_an_overrun():
                                     None, None, None, None)
     assert rc == 1 and b"capacity" in lib.bartint_last_error()
     assert info[5] > 1
+
+
+def test_two_split_trees_on_unpackable_words_stay_evaluated(monkeypatch):
+    """Four code words (13 <= d <= 16): a two-split tree on words (0,2) or (1,2) fits no DUAL table.  It must stay in
+    the evaluated part (the unmerged level-2 patch looped forever here) and must not be counted."""
+    cl = [np.linspace(0, 1, 102)[1:-1]] * 16
+    trees = [(0, 10, 0.1, (9, 20, 0.2, 0.3)),      # words (0,2): not DUAL-able
+             (5, 30, (10, 40, -0.1, -0.2), 0.05),  # words (1,2): not DUAL-able
+             (1, 50, 0.3, (14, 60, 0.1, 0.0)),     # words (0,3): table 2, pair (0,R-1)
+             (8, 70, (13, 5, 0.2, 0.1), -0.3),     # words (2,3): table 2, pair (R-2,R-1)
+             (2, 15, 0.0, (6, 25, 0.4, 0.5)),      # words (0,1): table 1
+             (11, 99, 0.7, 0.8)]                   # single split on word 2
+    ff = synth.forest_from_trees(trees * 3, 3, 6, cl)
+    rng = np.random.default_rng(5)
+    X = rng.random((333, 16))
+    codes = onp.bin_points(X, ff.cut_offsets, ff.cut_values)
+    plan = _check_against_oracle(ff, X, codes, monkeypatch, "gather", 2)
+    _, skipped = pi.interpret(plan, codes, sums_only=True)
+    assert [sorted(k % 6 for k in sk) for sk in skipped] == [[2, 3, 4, 5]] * 3
