@@ -270,6 +270,44 @@ int bartint_debug_plan_soa(int32_t S, int32_t m, int32_t d, const int64_t* tree_
     return BARTINT_OK;
 }
 
+int bartint_debug_export_dbarts098(const char* const* tree_strings, const double* tree_fits, const double* x_train,
+                                   int64_t n, int32_t d, const int32_t* cut_offsets, const double* cut_values,
+                                   int32_t m, int32_t S, int64_t node_capacity, int64_t* n_nodes_out,
+                                   int64_t* tree_node_offset, int32_t* split_var, int32_t* split_cut_idx,
+                                   int32_t* left, int32_t* right, double* leaf_mu) {
+    BI_REQUIRE(n_nodes_out != nullptr, BARTINT_ERR_ARG, "n_nodes_out is NULL");
+    *n_nodes_out = 0;
+    BI_REQUIRE(S >= 0 && m >= 0 && n >= 0, BARTINT_ERR_ARG, "S, m, n must be >= 0");
+    BI_REQUIRE((int64_t)S * m == 0 || tree_strings != nullptr, BARTINT_ERR_ARG, "tree_strings is NULL");
+    BI_REQUIRE((int64_t)S * m * n == 0 || tree_fits != nullptr, BARTINT_ERR_ARG, "tree_fits is NULL");
+    BI_REQUIRE(n * d == 0 || x_train != nullptr, BARTINT_ERR_ARG, "x_train is NULL");
+    int rc = check_cuts(d, cut_offsets, cut_values);
+    if (rc) return rc;
+    bartint_forest f;                       // never uploaded: no device state to release
+    f.S = S; f.m = m; f.d = d;
+    f.cut_off.assign(cut_offsets, cut_offsets + d + 1);
+    f.cut_val.assign(cut_values, cut_values + cut_offsets[d]);
+    if ((rc = parse_dbarts_forest(tree_strings, tree_fits, x_train, n, d, cut_offsets, cut_values, m, S, &f))) return rc;
+    if ((rc = forest_finish_host(&f))) return rc;
+    {
+        WalkForm W;
+        pack_walk_form(&f, W);
+        FastPlan P;
+        plan_fast_path(&f, W.tree_off, P);
+    }
+    *n_nodes_out = f.n_nodes;
+    BI_REQUIRE(f.n_nodes <= node_capacity, BARTINT_ERR_ARG, "forest has %lld nodes, capacity is %lld",
+               (long long)f.n_nodes, (long long)node_capacity);
+    const size_t nn = (size_t)f.n_nodes;
+    if (tree_node_offset) memcpy(tree_node_offset, f.tree_off.data(), f.tree_off.size() * sizeof(int64_t));
+    if (split_var && nn) memcpy(split_var, f.var.data(), nn * sizeof(int32_t));
+    if (split_cut_idx && nn) memcpy(split_cut_idx, f.cut.data(), nn * sizeof(int32_t));
+    if (left && nn) memcpy(left, f.left.data(), nn * sizeof(int32_t));
+    if (right && nn) memcpy(right, f.right.data(), nn * sizeof(int32_t));
+    if (leaf_mu && nn) memcpy(leaf_mu, f.mu.data(), nn * sizeof(double));
+    return BARTINT_OK;
+}
+
 int bartint_forest_info(const bartint_forest* f, int64_t info[12]) {
     BI_REQUIRE(f != nullptr && info != nullptr, BARTINT_ERR_ARG, "NULL argument");
     info[0] = f->S; info[1] = f->m; info[2] = f->d; info[3] = f->n_nodes; info[4] = f->n_leaves;

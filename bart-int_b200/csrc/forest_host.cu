@@ -31,10 +31,10 @@ struct PhaseTimer {
         return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
     }
     PhaseTimer() : on(getenv("BARTINT_TIMING") != nullptr), t0(now()) {}
-    void lap(const char* what) {
+    void lap(const char* what) {                       // "" restarts the clock without printing
         if (!on) return;
         const double t = now();
-        fprintf(stderr, "[bartint] %-28s %8.3f ms\n", what, t - t0);
+        if (what[0]) fprintf(stderr, "[bartint] %-28s %8.3f ms\n", what, t - t0);
         t0 = t;
     }
 };
@@ -156,6 +156,16 @@ int parse_dbarts_forest(const char* const* tree_strings, const double* tree_fits
         const int nc = cut_offsets[j + 1] - cut_offsets[j];
         for (int64_t i = 0; i < n; ++i) codes[(size_t)(j * n + i)] = bin_value(x_train[j * n + i], cuts, nc);
     }
+    // rows of the training matrix ordered by code, per variable (candidate rows for the leaf values below)
+    constexpr int64_t kLeafTries = 8;
+    std::vector<int32_t> order((size_t)(n * d));
+#pragma omp parallel for schedule(static)
+    for (int32_t j = 0; j < d; ++j) {
+        int32_t* o = order.data() + (size_t)j * (size_t)n;
+        const int32_t* cj = codes.data() + (size_t)j * (size_t)n;
+        for (int64_t i = 0; i < n; ++i) o[i] = (int32_t)i;
+        std::stable_sort(o, o + n, [cj](int32_t a, int32_t b) { return cj[a] < cj[b]; });
+    }
     const int64_t nn = bad_tree < 0 ? f->tree_off[(size_t)n_trees] : 0;
     f->var.resize((size_t)nn); f->cut.resize((size_t)nn); f->left.resize((size_t)nn); f->right.resize((size_t)nn);
     f->mu.resize((size_t)nn);
@@ -166,7 +176,13 @@ int parse_dbarts_forest(const char* const* tree_strings, const double* tree_fits
     {
         std::vector<int32_t> pending;
         std::vector<char> have;
-#pragma omp for schedule(static)
+        std::vector<std::pair<double*, const double*>> pend;     // leaf value reads in flight: (destination, source)
+        auto drain = [&pend](size_t keep) {                      // collect all but the `keep` youngest
+            const size_t nd = pend.size() > keep ? pend.size() - keep : 0;
+            for (size_t q = 0; q < nd; ++q) *pend[q].first = *pend[q].second;
+            pend.erase(pend.begin(), pend.begin() + (std::ptrdiff_t)nd);
+        };
+#pragma omp for schedule(static) nowait
         for (int64_t k = 0; k < n_trees; ++k) {
             if (bad_tree >= 0) continue;
             const int64_t base = f->tree_off[(size_t)k];
@@ -194,14 +210,50 @@ int parse_dbarts_forest(const char* const* tree_strings, const double* tree_fits
             // leaf mu = fit of the first training row routed to the leaf (fillPlotInfoForNode, BARTInt.R:125)
             const double* fits = tree_fits + (size_t)k * (size_t)n;   // [obs, tree, sample] column-major
             const int32_t n_leaf = (cnt + 1) / 2;
+            // Which row?  Any row of the leaf carries the leaf's value.  A leaf that is the left (right) child of a
+            // split on variable v holds rows with code[v] <= cut (> cut), so the rows with the smallest (largest)
+            // codes of v are tried first and verified by routing them from the root: one or two short walks and one
+            // read of `fits` per leaf, instead of routing the rows in order until every leaf has turned up (which
+            // also dragged most of the n x m x S fits array through the cache).
             have.assign((size_t)cnt, 0);
             int32_t found = 0;
+            if (pend.size() >= 192) drain(64);
+            if (cnt == 1) {
+                if (n > 0) { __builtin_prefetch(fits); pend.emplace_back(mu, fits); found = 1; }
+            } else {
+                for (int32_t p = 0; p < cnt; ++p) {
+                    if (var[p] < 0) continue;
+                    const int32_t v = var[p], c = cut[p];
+                    const int32_t* ord = order.data() + (size_t)v * (size_t)n;
+                    const int32_t* cv = codes.data() + (size_t)v * (size_t)n;
+                    for (int side = 0; side < 2; ++side) {
+                        const int32_t leaf = side ? right[p] : left[p];
+                        if (var[leaf] >= 0) continue;
+                        for (int64_t t = 0; t < n && t < kLeafTries; ++t) {
+                            const int64_t i = side ? ord[n - 1 - t] : ord[t];
+                            if ((cv[i] > c) != (side == 1)) break;          // no row of this leaf's side is left
+                            int32_t a = 0;
+                            while (var[a] >= 0) a = (codes[(size_t)(var[a] * n + i)] > cut[a]) ? right[a] : left[a];
+                            if (a == leaf) {
+                                // the read of fits[i] is a cache miss (the array is n x m x S doubles, touched once
+                                // per leaf): start it now, collect it later, many misses in flight at once
+                                __builtin_prefetch(fits + i);
+                                pend.emplace_back(mu + a, fits + i);
+                                have[(size_t)a] = 1; ++found;
+                                break;
+                            }
+                        }
+                    }
+                }
+            }
+            // leaves the candidates missed (boxes that are narrow in an earlier split): rows in order
             for (int64_t i = 0; i < n && found < n_leaf; ++i) {
                 int32_t a = 0;
                 while (var[a] >= 0) a = (codes[(size_t)(var[a] * n + i)] > cut[a]) ? right[a] : left[a];
                 if (!have[(size_t)a]) { mu[a] = fits[i]; have[(size_t)a] = 1; ++found; }
             }
         }
+        drain(0);
     }
     pt.lap("exporter: parse + leaf mu");
     if (bad_tree >= 0) {
@@ -471,7 +523,19 @@ static int table_bits_from_env() {
 
 // Chooses the fast kernel (f->table_ok / gather / nb / g_regs / count_mode), packs the trees of every draw into
 // group records and fills f->n_groups / f->draw_group_off.  tree_off: first node of each tree (int32 copy).
+// The trees of one table: a table indexes <= 8 predicate bits and every tree in it has at least one split, so eight
+// slots always suffice (no heap traffic in the packing loops, which run once per draw and candidate K).
+struct TreeList {
+    int32_t v[8];
+    int n = 0;
+    void push_back(int32_t t) { v[n++] = t; }
+    bool empty() const { return n == 0; }
+    const int32_t* begin() const { return v; }
+    const int32_t* end() const { return v + n; }
+};
+
 void plan_fast_path(bartint_forest* f, const std::vector<int32_t>& tree_off, FastPlan& P) {
+    PhaseTimer pt;
     const int64_t n_trees = (int64_t)f->S * f->m;
     const int64_t nn = f->n_nodes;
     // ---- fast-path planning: greedy packing of consecutive trees of a draw into groups of <= NB predicate bits ----
@@ -523,6 +587,10 @@ void plan_fast_path(bartint_forest* f, const std::vector<int32_t>& tree_off, Fas
         std::vector<uint32_t>& hdr = plans[(size_t)s].hdr;
         std::vector<uint32_t>& split = plans[(size_t)s].split;
         std::vector<uint32_t>& desc = plans[(size_t)s].desc;
+        {
+            const size_t guess = (size_t)f->m / 4 + 4;               // a draw's records: one allocation per array
+            group_tree_off.reserve(guess); hdr.reserve(guess); split.reserve(guess); desc.reserve(guess * (size_t)DW);
+        }
         auto open_group = [&](int64_t k, uint32_t flags) {
             group_tree_off.push_back((int32_t)k);
             hdr.push_back(flags);
@@ -538,7 +606,8 @@ void plan_fast_path(bartint_forest* f, const std::vector<int32_t>& tree_off, Fas
 
         if (!f->gather) {
             // ---------------- table format: up to NB nodes per group, any variables ----------------
-            std::vector<int64_t> gnodes, tn;
+            static thread_local std::vector<int64_t> gnodes, tn;
+            gnodes.clear(); tn.clear();
             auto close_group = [&]() {
                 if (gnodes.empty()) return;
                 std::stable_sort(gnodes.begin(), gnodes.end(),
@@ -556,10 +625,12 @@ void plan_fast_path(bartint_forest* f, const std::vector<int32_t>& tree_off, Fas
             // first, fullest group that still takes the tree) and the draw's trees are PERMUTED: group g covers
             // permuted positions [group_tree_off[g], group_tree_off[g+1]), tree_perm maps to tree ids.  (Consecutive
             // greedy packing left ~10 % of the predicate bits unused at cfg 3.)
-            struct TBin { int nodes = 0; std::vector<int32_t> trees; };
-            std::vector<TBin> bins;
-            std::vector<std::pair<int, int32_t>> order;          // (internal nodes, tree)
-            std::vector<int32_t> stumps, walk_trees;
+            struct TBin { int nodes = 0; TreeList trees; };
+            // scratch that lives as long as the (pooled) host thread: no allocation per draw
+            static thread_local std::vector<TBin> bins;
+            static thread_local std::vector<std::pair<int, int32_t>> order;          // (internal nodes, tree)
+            static thread_local std::vector<int32_t> stumps, walk_trees;
+            bins.clear(); order.clear(); stumps.clear(); walk_trees.clear();
             for (int32_t t = 0; t < f->m; ++t) {
                 internal_nodes((int64_t)s * f->m + t, tn);
                 if (tn.empty()) stumps.push_back(t);
@@ -614,12 +685,14 @@ void plan_fast_path(bartint_forest* f, const std::vector<int32_t>& tree_off, Fas
         auto pair_ok = [&](unsigned regs) { return within(regs, m_pair0) || within(regs, m_pair1); };
         auto side2_ok = [&](unsigned regs) { return pair_ok(regs) || within(regs, m_triple); };
         struct Item { int k; unsigned regs; int flex; int32_t tree; };
-        struct Bin { int nodes = 0; unsigned regs = 0; std::vector<int32_t> trees; };
-        std::vector<Item> items;
-        std::vector<Bin> bins1, bins2;
-        std::vector<int32_t> stumps, joint_trees, walk_trees;
-        std::vector<int64_t> tn;
-        std::vector<Item> countable;                             // counting mode: trees of <= count_level splits
+        struct Bin { int nodes = 0; unsigned regs = 0; TreeList trees; };
+        // scratch that lives as long as the (pooled) host thread: no allocation per draw
+        static thread_local std::vector<Item> items;
+        static thread_local std::vector<Bin> bins1, bins2;
+        static thread_local std::vector<int32_t> stumps, joint_trees, walk_trees;
+        static thread_local std::vector<int64_t> tn;
+        static thread_local std::vector<Item> countable;         // counting mode: trees of <= count_level splits
+        items.clear(); stumps.clear(); joint_trees.clear(); walk_trees.clear(); tn.clear(); countable.clear();
         for (int32_t t = 0; t < f->m; ++t) {
             internal_nodes((int64_t)s * f->m + t, tn);
             if (tn.empty()) { stumps.push_back(t); continue; }
@@ -727,7 +800,8 @@ void plan_fast_path(bartint_forest* f, const std::vector<int32_t>& tree_off, Fas
                 }
             }
             // emit, sorted by table-2 kind so the kernel's per-record variant branch changes rarely
-            std::vector<int> rec_order;
+            static thread_local std::vector<int> rec_order;
+            rec_order.clear();
             for (int r = 0; r < K; ++r)
                 if (!bins1[(size_t)r].trees.empty() || !bins2[(size_t)r].trees.empty()) rec_order.push_back(r);
             auto kind_of = [&](int r) {
@@ -756,7 +830,8 @@ void plan_fast_path(bartint_forest* f, const std::vector<int32_t>& tree_off, Fas
         };
         pack_and_emit(items, 0u, true);
         // JOINT records: greedy packing of the remaining small trees, two rounds of <= 4 slots, <= NB bits
-        std::vector<Slot> gslots;
+        static thread_local std::vector<Slot> gslots;
+        gslots.clear();
         int used[2] = {0, 0}, jbits = 0;
         bool jopen = false;
         auto close_joint = [&]() {
@@ -854,11 +929,13 @@ void plan_fast_path(bartint_forest* f, const std::vector<int32_t>& tree_off, Fas
     f->n_groups = (int64_t)group_tree_off.size();
     group_tree_off.push_back((int32_t)n_trees);
     // group g covers trees [group_tree_off[g], group_tree_off[g+1]) -- groups never span draws
+    pt.lap("upload: group planner");
 }
 
 // Walk form of the forest (what eval_walk_kernel, the WALK records and the table builder read): pre-order node
 // records, per-tree node / leaf offsets, leaf values by leaf ordinal.  Host only.
 void pack_walk_form(const bartint_forest* f, WalkForm& W) {
+    PhaseTimer pt;
     const int64_t n_trees = (int64_t)f->S * f->m;
     const int64_t nn = f->n_nodes;
     std::vector<uint2>& nodes = W.nodes;
@@ -889,6 +966,7 @@ void pack_walk_form(const bartint_forest* f, WalkForm& W) {
             }
         }
     }
+    pt.lap("upload: pack walk form");
 }
 
 int forest_upload(bartint_forest* f) {
@@ -899,7 +977,7 @@ int forest_upload(bartint_forest* f) {
     const std::vector<int32_t>&tree_off = W.tree_off, &leaf_off = W.leaf_off;
     const std::vector<double>& leaf_mu = W.leaf_mu;
     int rc;
-    pt.lap("upload: pack walk form");
+    pt.lap("");                                      // restart: pack_walk_form reports its own time
     if ((rc = upload(&f->dev.nodes, nodes))) return rc;
     if ((rc = upload(&f->dev.tree_off, tree_off))) return rc;
     if ((rc = upload(&f->dev.tree_leaf_off, leaf_off))) return rc;
@@ -910,7 +988,7 @@ int forest_upload(bartint_forest* f) {
     pt.lap("upload: H2D walk form");
     FastPlan P;
     plan_fast_path(f, tree_off, P);
-    pt.lap("upload: group planner");
+    pt.lap("");
     if (!f->table_ok) {
         BI_CUDA(cudaStreamSynchronize(nullptr));
         return BARTINT_OK;

@@ -1,0 +1,90 @@
+"""Wrappers of the two HOST-ONLY test hooks of the C ABI (include/bartint.h: bartint_debug_export_dbarts098,
+bartint_debug_plan_soa).  They run the exporter / the group planner exactly as forest creation does but return the
+result instead of uploading it, so they work on a machine without a GPU.  Used by tests/ and tools/ only: nothing
+on the product path calls them."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+def _p(a, ct):
+    return None if a is None else a.ctypes.data_as(C.POINTER(ct))
+
+
+def export_dbarts(wire, tree_fits, x_train, cut_offsets, cut_values, want_arrays: bool = True):
+    """Exporter + validation + walk-form packer + planner on the host.  wire: WireStrings.  Returns (n_nodes, dict of
+    the flattened forest or None)."""
+    lib = _lib.load()
+    x_train = np.asfortranarray(np.asarray(x_train, np.float64))
+    n, d = x_train.shape
+    m, S = wire.m, wire.S
+    fits = np.asfortranarray(np.asarray(tree_fits, np.float64).reshape(n, m, S))
+    coff = np.ascontiguousarray(cut_offsets, np.int32)
+    cval = np.ascontiguousarray(cut_values, np.float64)
+    nn = C.c_int64(0)
+    cap, out = 1 << 62, None
+    if want_arrays:
+        cap = sum(max(2 * s.count(b".") - 1, 0) for s in wire._enc[:m * S]) if hasattr(wire, "_enc") else 0
+        if getattr(wire, "_parent", None) is not None:         # a view: count from the C strings themselves
+            cap = sum(max(2 * (wire.array[k] or b"").count(b".") - 1, 0) for k in range(m * S))
+        out = dict(tree_offset=np.zeros(m * S + 1, np.int64), var=np.zeros(max(cap, 1), np.int32),
+                   cut=np.zeros(max(cap, 1), np.int32), left=np.zeros(max(cap, 1), np.int32),
+                   right=np.zeros(max(cap, 1), np.int32), mu=np.zeros(max(cap, 1), np.float64))
+    o = out or {}
+    rc = lib.bartint_debug_export_dbarts098(
+        C.cast(wire.array, C.c_void_p), _p(fits, C.c_double), _p(x_train, C.c_double), n, d, _p(coff, C.c_int32),
+        _p(cval, C.c_double), m, S, cap, C.byref(nn), _p(o.get("tree_offset"), C.c_int64), _p(o.get("var"), C.c_int32),
+        _p(o.get("cut"), C.c_int32), _p(o.get("left"), C.c_int32), _p(o.get("right"), C.c_int32),
+        _p(o.get("mu"), C.c_double))
+    if rc != 0:
+        from .forest import BartIntError
+        raise BartIntError(rc, lib.bartint_last_error().decode())
+    if out is not None:
+        for k in ("var", "cut", "left", "right", "mu"):
+            out[k] = out[k][:nn.value]
+        out.update(S=S, m=m, d=d)
+    return nn.value, out
+
+
+def plan_soa(ff) -> dict:
+    """The planner's output for a FlatForest: what forest creation would upload for the fast kernels."""
+    lib = _lib.load()
+    S, m, d = int(ff.S), int(ff.m), int(ff.d)
+    n_trees = S * m
+    toff = np.ascontiguousarray(ff.tree_offset, np.int64)
+    n_nodes = int(toff[-1]) if n_trees else 0
+    cap = n_trees + 2 * S + 1
+    var, cut, left, right = (np.ascontiguousarray(getattr(ff, k), np.int32) for k in ("var", "cut", "left", "right"))
+    mu = np.ascontiguousarray(ff.mu, np.float64)
+    coff, cval = np.ascontiguousarray(ff.cut_offsets, np.int32), np.ascontiguousarray(ff.cut_values, np.float64)
+    info = np.zeros(8, np.int64)
+    out = dict(
+        walk_nodes=np.zeros(2 * max(n_nodes, 1), np.uint32), leaf_off=np.zeros(n_trees + 1, np.int32),
+        leaf_mu=np.zeros(max((n_nodes + n_trees) // 2, 1), np.float64), node_bit=np.zeros(max(n_nodes, 1), np.uint8),
+        tree_perm=np.zeros(max(n_trees, 1), np.int32), draw_group_off=np.zeros(S + 1, np.int32),
+        group_tree_off=np.zeros(cap + 1, np.int32), hdr=np.zeros(cap, np.uint32), split=np.zeros(cap, np.uint32),
+        desc=np.zeros(16 * cap, np.uint32))
+    rc = lib.bartint_debug_plan_soa(
+        S, m, d, _p(toff, C.c_int64), _p(var, C.c_int32), _p(cut, C.c_int32), _p(left, C.c_int32), _p(right, C.c_int32),
+        _p(mu, C.c_double), _p(coff, C.c_int32), _p(cval, C.c_double), cap, _p(info, C.c_int64),
+        _p(out["walk_nodes"], C.c_uint32), _p(out["leaf_off"], C.c_int32), _p(out["leaf_mu"], C.c_double),
+        _p(out["node_bit"], C.c_uint8), _p(out["tree_perm"], C.c_int32), _p(out["draw_group_off"], C.c_int32),
+        _p(out["group_tree_off"], C.c_int32), _p(out["hdr"], C.c_uint32), _p(out["split"], C.c_uint32),
+        _p(out["desc"], C.c_uint32))
+    if rc != 0:
+        from .forest import BartIntError
+        raise BartIntError(rc, lib.bartint_last_error().decode())
+    table_ok, gather, nb, regs, level, n_groups, dw, n_leaves = (int(v) for v in info)
+    out.update(S=S, m=m, d=d, table_ok=bool(table_ok), gather=bool(gather), nb=nb, regs=regs, count_level=level,
+               n_groups=n_groups, dw=dw, n_leaves=n_leaves, tree_off=toff.astype(np.int64), n_nodes=n_nodes)
+    out["nodes_x"] = out["walk_nodes"][0::2][:n_nodes]
+    out["nodes_y"] = out["walk_nodes"][1::2][:n_nodes]
+    out["desc"] = out["desc"][:n_groups * dw].reshape(n_groups, dw) if n_groups else np.zeros((0, max(dw, 1)), np.uint32)
+    for k in ("hdr", "split"):
+        out[k] = out[k][:n_groups]
+    out["group_tree_off"] = out["group_tree_off"][:n_groups + 1]
+    return out

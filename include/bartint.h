@@ -314,6 +314,18 @@ int bartint_debug_plan_soa(int32_t S, int32_t m, int32_t d, const int64_t* tree_
                            int32_t* draw_group_offset, int32_t* group_tree_offset, uint32_t* hdr, uint32_t* split,
                            uint32_t* desc);
 
+/* Test hook, HOST ONLY: the exporter of bartint_forest_from_dbarts098 (string parser, leaf values from the saved
+ * fits, canonical pre-order SoA, validation) followed by the walk-form packer and the group planner, i.e. every
+ * host phase of forest creation, without touching a device.  The flattened forest is copied out so the CPU tests
+ * can compare the exporter with the oracle's restatement of getTree() (src/BARTInt.R:92-133); it is also what
+ * tools/exporter_bench.py times.  node_capacity: size of the node arrays (any of which may be NULL);
+ * *n_nodes_out receives the number of nodes; BARTINT_ERR_ARG if that exceeds node_capacity. */
+int bartint_debug_export_dbarts098(const char* const* tree_strings, const double* tree_fits, const double* x_train,
+                                   int64_t n, int32_t d, const int32_t* cut_offsets, const double* cut_values,
+                                   int32_t m, int32_t S, int64_t node_capacity, int64_t* n_nodes_out,
+                                   int64_t* tree_node_offset, int32_t* split_var, int32_t* split_cut_idx,
+                                   int32_t* left, int32_t* right, double* leaf_mu);
+
 #ifdef __cplusplus
 }
 #endif

@@ -9,57 +9,17 @@ without a GPU.  It restates the kernels' integer arithmetic; it does not replace
 """
 from __future__ import annotations
 
-import ctypes as C
-
 import numpy as np
 
-from bartint_b200 import _lib
+from bartint_b200 import hosthooks
 
 FLAG_END_DRAW, FLAG_WALK, FLAG_JOINT, FLAG_COUNTABLE, FLAG_END_EVAL = 1, 2, 4, 8, 16
 LEAF_VAR = 0xFFFF
 
 
-def _p(a, ct):
-    return a.ctypes.data_as(C.POINTER(ct))
-
-
 def debug_plan(ff) -> dict:
-    lib = _lib.load()
-    S, m, d = int(ff.S), int(ff.m), int(ff.d)
-    n_trees = S * m
-    toff = np.ascontiguousarray(ff.tree_offset, np.int64)
-    n_nodes = int(toff[-1]) if n_trees else 0
-    cap = n_trees + 2 * S + 1
-    arr = lambda a, t: np.ascontiguousarray(a, t)
-    var, cut, left, right = (arr(getattr(ff, k), np.int32) for k in ("var", "cut", "left", "right"))
-    mu = arr(ff.mu, np.float64)
-    coff, cval = arr(ff.cut_offsets, np.int32), arr(ff.cut_values, np.float64)
-    info = np.zeros(8, np.int64)
-    out = dict(
-        walk_nodes=np.zeros(2 * max(n_nodes, 1), np.uint32), leaf_off=np.zeros(n_trees + 1, np.int32),
-        leaf_mu=np.zeros(max((n_nodes + n_trees) // 2, 1), np.float64), node_bit=np.zeros(max(n_nodes, 1), np.uint8),
-        tree_perm=np.zeros(max(n_trees, 1), np.int32), draw_group_off=np.zeros(S + 1, np.int32),
-        group_tree_off=np.zeros(cap + 1, np.int32), hdr=np.zeros(cap, np.uint32), split=np.zeros(cap, np.uint32),
-        desc=np.zeros(16 * cap, np.uint32))
-    rc = lib.bartint_debug_plan_soa(
-        S, m, d, _p(toff, C.c_int64), _p(var, C.c_int32), _p(cut, C.c_int32), _p(left, C.c_int32), _p(right, C.c_int32),
-        _p(mu, C.c_double), _p(coff, C.c_int32), _p(cval, C.c_double), cap, _p(info, C.c_int64),
-        _p(out["walk_nodes"], C.c_uint32), _p(out["leaf_off"], C.c_int32), _p(out["leaf_mu"], C.c_double),
-        _p(out["node_bit"], C.c_uint8), _p(out["tree_perm"], C.c_int32), _p(out["draw_group_off"], C.c_int32),
-        _p(out["group_tree_off"], C.c_int32), _p(out["hdr"], C.c_uint32), _p(out["split"], C.c_uint32),
-        _p(out["desc"], C.c_uint32))
-    if rc != 0:
-        raise RuntimeError(f"bartint_debug_plan_soa: status {rc}: {lib.bartint_last_error().decode()}")
-    table_ok, gather, nb, regs, level, n_groups, dw, n_leaves = (int(v) for v in info)
-    out.update(S=S, m=m, d=d, table_ok=bool(table_ok), gather=bool(gather), nb=nb, regs=regs, count_level=level,
-               n_groups=n_groups, dw=dw, n_leaves=n_leaves, tree_off=toff.astype(np.int64), n_nodes=n_nodes)
-    out["nodes_x"] = out["walk_nodes"][0::2][:n_nodes]
-    out["nodes_y"] = out["walk_nodes"][1::2][:n_nodes]
-    out["desc"] = out["desc"][:n_groups * dw].reshape(n_groups, dw) if n_groups else np.zeros((0, max(dw, 1)), np.uint32)
-    for k in ("hdr", "split"):
-        out[k] = out[k][:n_groups]
-    out["group_tree_off"] = out["group_tree_off"][:n_groups + 1]
-    return out
+    """The library's own planner run on the host (bartint_debug_plan_soa through bartint_b200.hosthooks)."""
+    return hosthooks.plan_soa(ff)
 
 
 # ---- the PTX pieces -------------------------------------------------------------------------------------------

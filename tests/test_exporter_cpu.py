@@ -1,0 +1,103 @@
+"""CPU tests of the tree-state exporter (forest_host.cu: parse_dbarts_forest -- the replacement of getTree,
+src/BARTInt.R:92-133) through the host-only hook bartint_debug_export_dbarts098: the flattened forest must equal
+the oracle's restatement node for node, for the prior's trees and for the shapes that stress the leaf-value search
+(deep chains, leaves that share a value, leaves no training row reaches, tiny designs)."""
+import numpy as np
+import pytest
+
+from bartint_b200 import BartIntError, WireStrings, hosthooks, synth
+from oracle import oracle_np as onp
+
+
+def _export(ff, x_train, strings=None, fits=None):
+    s2, f2 = ff.to_dbarts_state(x_train)
+    strings = s2 if strings is None else strings
+    fits = f2 if fits is None else fits
+    nn, got = hosthooks.export_dbarts(WireStrings(strings), fits, x_train, ff.cut_offsets, ff.cut_values)
+    want = onp.forest_from_dbarts(strings, fits, x_train, ff.cut_lists(), ff.y_min, ff.y_max)
+    return nn, got, want
+
+
+def _assert_same(got, want):
+    assert np.array_equal(got["tree_offset"], want["tree_offset"])
+    for k in ("var", "cut", "left", "right"):
+        assert np.array_equal(got[k], want[k]), k
+    leaf = want["var"] < 0
+    assert np.array_equal(got["mu"][leaf], want["mu"][leaf], equal_nan=True)
+
+
+@pytest.mark.parametrize("d,n,seed", [(1, 20, 0), (3, 40, 1), (10, 200, 2), (16, 7, 3), (20, 400, 4)])
+def test_prior_forests_match_the_oracle(d, n, seed):
+    rng = np.random.default_rng(seed)
+    x_train = rng.random((n, d))
+    ff = synth.prior_forest(seed, 6, 25, x_train, synth.genz_gaussian(x_train))
+    nn, got, want = _export(ff, x_train)
+    assert nn == ff.n_nodes
+    _assert_same(got, want)
+    # and the exporter inverts to_dbarts_state: same trees, same leaf values
+    assert np.array_equal(got["var"], ff.var) and np.array_equal(got["cut"], ff.cut)
+    assert np.array_equal(got["mu"][ff.var < 0], ff.mu[ff.var < 0])
+
+
+@pytest.mark.parametrize("kind", ["stumps", "left_chain", "right_chain", "same_var", "balanced", "edge_cuts"])
+def test_adversarial_shapes_including_unreached_leaves(kind):
+    # 30 rows against chains of depth 9: many leaves receive no training row (-> NaN like the oracle) and most of
+    # the others are found only by the fallback scan, not by the candidate rows
+    ff = synth.adversarial_forest(kind, 3, 5, 4, numcut=50, seed=2, depth=9)
+    rng = np.random.default_rng(9)
+    x_train = rng.random((30, 4))
+    _, got, want = _export(ff, x_train)
+    _assert_same(got, want)
+
+
+def test_leaves_sharing_one_value_and_duplicate_rows():
+    cl = [np.linspace(0, 1, 12)[1:-1]] * 2
+    trees = [(0, 4, 0.25, (1, 6, 0.25, 0.25)), (1, 2, (0, 7, -1.0, -1.0), 3.0)]
+    ff = synth.forest_from_trees(trees * 2, 2, 2, cl)
+    x_train = np.array([[0.1, 0.1], [0.1, 0.1], [0.9, 0.9], [0.9, 0.2], [0.45, 0.95], [0.2, 0.7]])
+    _, got, want = _export(ff, x_train)
+    _assert_same(got, want)
+    assert not np.isnan(got["mu"][got["var"] < 0]).any()
+
+
+def test_routing_ties_and_nan_rows():
+    # x == cut goes left, NaN goes left (dbarts' integer cut map: code = #{cuts < x}, NaN -> 0)
+    cl = [np.array([0.25, 0.5, 0.75])]
+    ff = synth.forest_from_trees([(0, 1, 1.0, 2.0)], 1, 1, cl)
+    for x, mu_left_seen in (([[0.5]], True), ([[np.nan]], True), ([[np.nextafter(0.5, 1)]], False)):
+        x_train = np.array(x)
+        fits = np.array([7.0]).reshape(1, 1, 1)
+        _, got, want = _export(ff, x_train, fits=fits)
+        _assert_same(got, want)
+        assert (got["mu"][1] == 7.0) == mu_left_seen and (got["mu"][2] == 7.0) == (not mu_left_seen)
+
+
+def test_no_training_rows():
+    ff = synth.forest_from_trees([(0, 0, 1.0, 2.0), 0.5], 1, 2, [np.array([0.5])])
+    nn, got, _ = _export(ff, np.zeros((0, 1)), fits=np.zeros((0, 2, 1)))
+    assert nn == 4 and np.isnan(got["mu"][got["var"] < 0]).all()
+
+
+@pytest.mark.parametrize("bad", ["", "0 1 .", "0 1 . . .", "0 x . .", "0 1 . . 3", "5 0 . .", "0 99 . .", "-1 0 . ."])
+def test_malformed_strings_are_parse_errors(bad):
+    strings = np.array([[bad]], dtype=object)
+    with pytest.raises(BartIntError) as e:
+        hosthooks.export_dbarts(WireStrings(strings), np.zeros((2, 1, 1)), np.zeros((2, 1)), [0, 3], [0.25, 0.5, 0.75])
+    assert e.value.status == 2
+
+
+def test_thread_count_does_not_change_the_result():
+    from bartint_b200 import _lib
+    rng = np.random.default_rng(5)
+    x_train = rng.random((120, 6))
+    ff = synth.prior_forest(5, 40, 30, x_train)
+    lib = _lib.load()
+    outs = []
+    for t in (1, 3, 8):
+        lib.bartint_set_host_threads(t)
+        outs.append(_export(ff, x_train)[1])
+    lib.bartint_set_host_threads(0)
+    for o in outs[1:]:
+        for k in ("tree_offset", "var", "cut", "left", "right"):
+            assert np.array_equal(o[k], outs[0][k])
+        assert np.array_equal(o["mu"], outs[0]["mu"], equal_nan=True)

@@ -164,3 +164,25 @@ def test_two_split_trees_on_unpackable_words_stay_evaluated(monkeypatch):
     plan = _check_against_oracle(ff, X, codes, monkeypatch, "gather", 2)
     _, skipped = pi.interpret(plan, codes, sums_only=True)
     assert [sorted(k % 6 for k in sk) for sk in skipped] == [[2, 3, 4, 5]] * 3
+
+
+def test_plan_digests_match_the_gpu_verified_build():
+    """tests/golden/plan_digests.json pins what the planner uploads (tools/plan_digest.py: 90 forests x formats x
+    counting levels).  The level-0 digests have not changed since the host-only hook exists (the planner body was moved
+    out of forest_upload verbatim from the build verified on the GPU), and every one of these plans reproduces the
+    oracle through the interpreter above.  A change that alters the digests must be deliberate: re-verify on a GPU,
+    then regenerate the file with `python tools/plan_digest.py > tests/golden/plan_digests.json`."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = {k: v for k, v in os.environ.items() if not k.startswith("BARTINT_")}
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "plan_digest.py")], check=True,
+                         capture_output=True, text=True, env=env).stdout
+    with open(os.path.join(root, "tests", "golden", "plan_digests.json")) as fh:
+        want = json.load(fh)
+    got = json.loads(out)
+    assert sorted(got) == sorted(want)
+    changed = [k for k in want if got[k] != want[k]]
+    assert not changed, f"planner output changed for {changed[:8]} ..."
