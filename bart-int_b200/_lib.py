@@ -80,6 +80,9 @@ SIGNATURES = {
     "bartint_last_eval_profile": (C.c_int, [C.c_void_p, C.c_int32, c_float_p, c_int32_p, c_int32_p]),
     "bartint_kernel_launch_count": (C.c_int64, []),
     # host-only test hooks (exporter / planner output without a device); see tests/plan_interp.py
+    "bartint_debug_export_wbart": (C.c_int, [C.c_char_p, C.c_int64, C.c_int32, c_int32_p, c_double_p, C.c_int64, C.c_int64,
+                                             c_int64_p, c_int64_p, c_int32_p, c_int32_p, c_int32_p, c_int32_p,
+                                             c_double_p]),
     "bartint_debug_export_dbarts098": (C.c_int, [C.c_void_p, c_double_p, c_double_p, C.c_int64, C.c_int32, c_int32_p,
                                                  c_double_p, C.c_int32, C.c_int32, C.c_int64, c_int64_p, c_int64_p,
                                                  c_int32_p, c_int32_p, c_int32_p, c_int32_p, c_double_p]),

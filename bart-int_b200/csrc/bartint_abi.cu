@@ -270,6 +270,53 @@ int bartint_debug_plan_soa(int32_t S, int32_t m, int32_t d, const int64_t* tree_
     return BARTINT_OK;
 }
 
+// shared tail of the two host-only export hooks: the host phases after parsing, then copy the SoA out
+static int debug_finish_and_copy(bartint_forest& f, int64_t tree_capacity, int64_t node_capacity,
+                                 int64_t* tree_node_offset, int32_t* split_var, int32_t* split_cut_idx, int32_t* left,
+                                 int32_t* right, double* leaf_mu) {
+    int rc = forest_finish_host(&f);
+    if (rc) return rc;
+    {
+        WalkForm W;
+        pack_walk_form(&f, W);
+        FastPlan P;
+        plan_fast_path(&f, W.tree_off, P);
+    }
+    BI_REQUIRE(f.n_nodes <= node_capacity && (int64_t)f.S * f.m <= tree_capacity, BARTINT_ERR_ARG,
+               "forest has %lld trees and %lld nodes, capacity is %lld and %lld", (long long)f.S * f.m,
+               (long long)f.n_nodes, (long long)tree_capacity, (long long)node_capacity);
+    const size_t nn = (size_t)f.n_nodes;
+    if (tree_node_offset) memcpy(tree_node_offset, f.tree_off.data(), f.tree_off.size() * sizeof(int64_t));
+    if (split_var && nn) memcpy(split_var, f.var.data(), nn * sizeof(int32_t));
+    if (split_cut_idx && nn) memcpy(split_cut_idx, f.cut.data(), nn * sizeof(int32_t));
+    if (left && nn) memcpy(left, f.left.data(), nn * sizeof(int32_t));
+    if (right && nn) memcpy(right, f.right.data(), nn * sizeof(int32_t));
+    if (leaf_mu && nn) memcpy(leaf_mu, f.mu.data(), nn * sizeof(double));
+    return BARTINT_OK;
+}
+
+int bartint_debug_export_wbart(const char* trees_text, int64_t text_len, int32_t d, const int32_t* cut_offsets,
+                               const double* cut_values, int64_t tree_capacity, int64_t node_capacity,
+                               int64_t dims_out[3], int64_t* tree_node_offset, int32_t* split_var,
+                               int32_t* split_cut_idx, int32_t* left, int32_t* right, double* leaf_mu) {
+    BI_REQUIRE(dims_out != nullptr, BARTINT_ERR_ARG, "dims_out is NULL");
+    dims_out[0] = dims_out[1] = dims_out[2] = 0;
+    BI_REQUIRE(trees_text != nullptr, BARTINT_ERR_ARG, "trees_text is NULL");
+    if (text_len <= 0) text_len = (int64_t)std::strlen(trees_text);
+    BI_REQUIRE(trees_text[text_len] == '\0', BARTINT_ERR_ARG, "trees_text must be NUL terminated at text_len");
+    int rc = check_cuts(d, cut_offsets, cut_values);
+    if (rc) return rc;
+    bartint_forest f;                       // never uploaded: no device state to release
+    f.d = d; f.route = BARTINT_ROUTE_BART;
+    f.cut_off.assign(cut_offsets, cut_offsets + d + 1);
+    f.cut_val.assign(cut_values, cut_values + cut_offsets[d]);
+    if ((rc = parse_wbart_forest(trees_text, text_len, d, &f))) return rc;
+    rc = debug_finish_and_copy(f, tree_capacity, node_capacity, tree_node_offset, split_var, split_cut_idx, left,
+                               right, leaf_mu);
+    dims_out[0] = f.S; dims_out[1] = f.m; dims_out[2] = f.n_nodes;
+    return rc;
+}
+
 int bartint_debug_export_dbarts098(const char* const* tree_strings, const double* tree_fits, const double* x_train,
                                    int64_t n, int32_t d, const int32_t* cut_offsets, const double* cut_values,
                                    int32_t m, int32_t S, int64_t node_capacity, int64_t* n_nodes_out,
@@ -288,24 +335,10 @@ int bartint_debug_export_dbarts098(const char* const* tree_strings, const double
     f.cut_off.assign(cut_offsets, cut_offsets + d + 1);
     f.cut_val.assign(cut_values, cut_values + cut_offsets[d]);
     if ((rc = parse_dbarts_forest(tree_strings, tree_fits, x_train, n, d, cut_offsets, cut_values, m, S, &f))) return rc;
-    if ((rc = forest_finish_host(&f))) return rc;
-    {
-        WalkForm W;
-        pack_walk_form(&f, W);
-        FastPlan P;
-        plan_fast_path(&f, W.tree_off, P);
-    }
+    rc = debug_finish_and_copy(f, (int64_t)S * m, node_capacity, tree_node_offset, split_var, split_cut_idx, left,
+                               right, leaf_mu);
     *n_nodes_out = f.n_nodes;
-    BI_REQUIRE(f.n_nodes <= node_capacity, BARTINT_ERR_ARG, "forest has %lld nodes, capacity is %lld",
-               (long long)f.n_nodes, (long long)node_capacity);
-    const size_t nn = (size_t)f.n_nodes;
-    if (tree_node_offset) memcpy(tree_node_offset, f.tree_off.data(), f.tree_off.size() * sizeof(int64_t));
-    if (split_var && nn) memcpy(split_var, f.var.data(), nn * sizeof(int32_t));
-    if (split_cut_idx && nn) memcpy(split_cut_idx, f.cut.data(), nn * sizeof(int32_t));
-    if (left && nn) memcpy(left, f.left.data(), nn * sizeof(int32_t));
-    if (right && nn) memcpy(right, f.right.data(), nn * sizeof(int32_t));
-    if (leaf_mu && nn) memcpy(leaf_mu, f.mu.data(), nn * sizeof(double));
-    return BARTINT_OK;
+    return rc;
 }
 
 int bartint_forest_info(const bartint_forest* f, int64_t info[12]) {

@@ -50,6 +50,35 @@ def export_dbarts(wire, tree_fits, x_train, cut_offsets, cut_values, want_arrays
     return nn.value, out
 
 
+def export_wbart(trees_text, cut_lists):
+    """Host phases of Forest.from_wbart (BART::wbart `treedraws$trees` text).  Returns the flattened forest."""
+    lib = _lib.load()
+    text = trees_text.encode() if isinstance(trees_text, str) else bytes(trees_text)
+    d = len(cut_lists)
+    coff = np.zeros(d + 1, np.int32)
+    coff[1:] = np.cumsum([len(c) for c in cut_lists])
+    cval = np.ascontiguousarray(np.concatenate([np.asarray(c, np.float64) for c in cut_lists]) if d else np.zeros(0))
+    cap_nodes = text.count(b"\n") + 2                    # one line per node at most
+    cap_trees = cap_nodes
+    dims = np.zeros(3, np.int64)
+    out = dict(tree_offset=np.zeros(cap_trees + 1, np.int64), var=np.zeros(cap_nodes, np.int32),
+               cut=np.zeros(cap_nodes, np.int32), left=np.zeros(cap_nodes, np.int32), right=np.zeros(cap_nodes, np.int32),
+               mu=np.zeros(cap_nodes, np.float64))
+    rc = lib.bartint_debug_export_wbart(text, len(text), d, _p(coff, C.c_int32), _p(cval, C.c_double), cap_trees,
+                                        cap_nodes, _p(dims, C.c_int64), _p(out["tree_offset"], C.c_int64),
+                                        _p(out["var"], C.c_int32), _p(out["cut"], C.c_int32), _p(out["left"], C.c_int32),
+                                        _p(out["right"], C.c_int32), _p(out["mu"], C.c_double))
+    if rc != 0:
+        from .forest import BartIntError
+        raise BartIntError(rc, lib.bartint_last_error().decode())
+    S, m, nn = (int(v) for v in dims)
+    out["tree_offset"] = out["tree_offset"][:S * m + 1]
+    for k in ("var", "cut", "left", "right", "mu"):
+        out[k] = out[k][:nn]
+    out.update(S=S, m=m, d=d)
+    return out
+
+
 def plan_soa(ff) -> dict:
     """The planner's output for a FlatForest: what forest creation would upload for the fast kernels."""
     lib = _lib.load()

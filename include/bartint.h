@@ -326,6 +326,13 @@ int bartint_debug_export_dbarts098(const char* const* tree_strings, const double
                                    int64_t* tree_node_offset, int32_t* split_var, int32_t* split_cut_idx,
                                    int32_t* left, int32_t* right, double* leaf_mu);
 
+/* Test hook, HOST ONLY: the exporter of bartint_forest_from_wbart (text parser, heap ids -> pre-order SoA,
+ * validation) plus the walk-form packer and the planner, without touching a device.  dims_out[3] = {S, m, n_nodes}. */
+int bartint_debug_export_wbart(const char* trees_text, int64_t text_len, int32_t d, const int32_t* cut_offsets,
+                               const double* cut_values, int64_t tree_capacity, int64_t node_capacity,
+                               int64_t dims_out[3], int64_t* tree_node_offset, int32_t* split_var,
+                               int32_t* split_cut_idx, int32_t* left, int32_t* right, double* leaf_mu);
+
 #ifdef __cplusplus
 }
 #endif

@@ -224,3 +224,27 @@ def test_wbart_cpp_parser_verdicts():
         assert _from_wbart_status(bad, KAT_CUTS) == 2, repr(bad)
     assert _from_wbart_status("1 1 3\n1\n1 0 0 1.0\n", KAT_CUTS) == 1                         # p != number of cut lists
     assert _from_wbart_status("1 1\n1\n1 0 0 0.5\n", KAT_CUTS) == 1                            # header one token short -> p mismatch
+
+
+# ---- the C++ exporter on the host (no GPU): bartint_debug_export_wbart against the oracle ----------------------------
+
+@pytest.mark.parametrize("d", [1, 3, 10, 20])
+def test_wbart_cpp_exporter_matches_oracle_on_host(d):
+    from bartint_b200 import hosthooks
+    rng = np.random.default_rng(300 + d)
+    ff = synth.prior_forest(11 + d, 9, 14, rng.random((20 * d, d)), None)
+    for text in (ff.to_wbart_text(), ff.to_wbart_text().replace("\n", "\r\n")):
+        ref = onp.forest_from_wbart(text, ff.cut_lists(), offset=0.0)
+        got = hosthooks.export_wbart(text, ff.cut_lists())
+        assert (got["S"], got["m"], got["d"]) == (ref.S, ref.m, ref.d)
+        for k in ("tree_offset", "var", "cut", "left", "right"):
+            assert np.array_equal(got[k], getattr(ref, k)), k
+        assert np.array_equal(got["mu"], ref.mu)
+
+
+def test_wbart_cpp_exporter_kat_on_host():
+    from bartint_b200 import hosthooks
+    got = hosthooks.export_wbart(KAT_TEXT, KAT_CUTS)
+    ref = onp.forest_from_wbart(KAT_TEXT, KAT_CUTS, offset=KAT_OFFSET)
+    for k in ("tree_offset", "var", "cut", "left", "right", "mu"):
+        assert np.array_equal(got[k], getattr(ref, k)), k
