@@ -163,8 +163,11 @@ int parse_dbarts_forest(const char* const* tree_strings, const double* tree_fits
     for (int32_t j = 0; j < d; ++j) {
         int32_t* o = order.data() + (size_t)j * (size_t)n;
         const int32_t* cj = codes.data() + (size_t)j * (size_t)n;
-        for (int64_t i = 0; i < n; ++i) o[i] = (int32_t)i;
-        std::stable_sort(o, o + n, [cj](int32_t a, int32_t b) { return cj[a] < cj[b]; });
+        const int nc = cut_offsets[j + 1] - cut_offsets[j];          // codes are 0 .. nc: stable counting sort
+        std::vector<int64_t> first((size_t)nc + 2, 0);
+        for (int64_t i = 0; i < n; ++i) ++first[(size_t)cj[i] + 1];
+        for (int c = 0; c <= nc; ++c) first[(size_t)c + 1] += first[(size_t)c];
+        for (int64_t i = 0; i < n; ++i) o[first[(size_t)cj[i]]++] = (int32_t)i;
     }
     const int64_t nn = bad_tree < 0 ? f->tree_off[(size_t)n_trees] : 0;
     f->var.resize((size_t)nn); f->cut.resize((size_t)nn); f->left.resize((size_t)nn); f->right.resize((size_t)nn);

@@ -186,3 +186,26 @@ def test_plan_digests_match_the_gpu_verified_build():
     assert sorted(got) == sorted(want)
     changed = [k for k in want if got[k] != want[k]]
     assert not changed, f"planner output changed for {changed[:8]} ..."
+
+
+def test_randomized_sweep(monkeypatch):
+    """Seeded sweep over d, trees per draw, cut grid sizes, table bits, formats, counting levels and tree shapes."""
+    rng = np.random.default_rng(12345)
+    for it in range(90):
+        d = int(rng.integers(1, 21))
+        m = int(rng.integers(1, 60))
+        S = int(rng.integers(1, 4))
+        numcut = int(rng.choice([1, 2, 5, 100, 127]))
+        kernel = "table" if d > 16 or rng.random() < 0.3 else "gather"
+        count = int(rng.integers(0, 3)) if kernel == "gather" else 0
+        monkeypatch.setenv("BARTINT_TABLE_BITS", str(int(rng.integers(4, 9))))
+        x = rng.random((int(rng.integers(5, 80)), d))
+        kind = rng.choice(["prior", "prior", "prior", "balanced", "same_var", "left_chain", "edge_cuts"])
+        if kind == "prior":
+            ff = synth.prior_forest(int(rng.integers(1 << 30)), S, m, x, numcut=numcut, k=float(rng.choice([2.0, 0.5])))
+        else:
+            ff = synth.adversarial_forest(kind, S, min(m, 12), d, numcut=max(numcut, 2), seed=it,
+                                          depth=int(rng.integers(1, 8)))
+        X = rng.random((97, d))
+        codes = onp.bin_points(X, ff.cut_offsets, ff.cut_values)
+        _check_against_oracle(ff, X, codes, monkeypatch, kernel, count)
