@@ -395,7 +395,10 @@ def run_ours(args):
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "config": config_json(c, {"mc_points_total": n_total,
                                                                        "parallelism": f"points x{world} (MC), draws x{world} (candidates)",
-                                                                       "host_threads_per_rank": host_threads}),
+                                                                       "host_threads_per_rank": host_threads,
+                                                                       # 0 = every tree evaluated point by point (the
+                                                                       # headline); 1 / 2 = opt-in counting mode
+                                                                       "count_splits": int(os.environ.get("BARTINT_COUNT_SPLITS", "0") or 0)}),
         "s_per_sequential_design_step": total_ms / args.steps / 1e3,
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "roofline_k0": roofline_k0,
         "cpu_baseline": cpu,
