@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libbartint_cuda.so")
+# BARTINT_LIB: load another build of the same library instead (a sanitizer build, an older build to compare plans with)
+LIB_PATH = os.environ.get("BARTINT_LIB") or os.path.join(HERE, "libbartint_cuda.so")
 
 c_double_p = C.POINTER(C.c_double)
 c_int32_p = C.POINTER(C.c_int32)
