@@ -416,12 +416,9 @@ int launch_count_single_splits(const bartint_forest* f, const bartint_points* p,
         const int64_t want = (p->N + 255) / 256;
         hist_codes_kernel<<<(unsigned)std::min<int64_t>(want, 148 * 4), 256, 0, st>>>(p->codes_pm, p->N, d, d_hist);
         if (pairs) {
-            static bool attr_set = false;
-            if (!attr_set) {
-                BI_CUDA(cudaFuncSetAttribute(hist2_codes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 128 * 4));
-                BI_CUDA(cudaFuncSetAttribute(suffix2_counts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 128 * 4));
-                attr_set = true;
-            }
+            // per launch, not once per process: the attribute belongs to the current device's copy of the kernel
+            BI_CUDA(cudaFuncSetAttribute(hist2_codes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 128 * 4));
+            BI_CUDA(cudaFuncSetAttribute(suffix2_counts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 128 * 4));
             const int slices = (int)std::max<int64_t>(1, std::min<int64_t>((148 * 3 + pairs - 1) / pairs, (p->N + 4095) / 4096));
             hist2_codes_kernel<<<dim3((unsigned)pairs, (unsigned)slices), 256, 128 * 128 * 4, st>>>(p->codes_pm, p->N, d, d_J2);
         }
