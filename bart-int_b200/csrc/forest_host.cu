@@ -697,11 +697,13 @@ void plan_fast_path(bartint_forest* f, const std::vector<int32_t>& tree_off, Fas
         static thread_local std::vector<Item> countable;         // counting mode: trees of <= count_level splits
         items.clear(); stumps.clear(); joint_trees.clear(); walk_trees.clear(); tn.clear(); countable.clear();
         for (int32_t t = 0; t < f->m; ++t) {
-            internal_nodes((int64_t)s * f->m + t, tn);
-            if (tn.empty()) { stumps.push_back(t); continue; }
+            const int64_t kt = (int64_t)s * f->m + t;
+            const int32_t nb0 = tree_off[(size_t)kt], ne0 = tree_off[(size_t)kt + 1];
+            if (ne0 - nb0 == 1) { stumps.push_back(t); continue; }
             unsigned regs = 0;
-            for (int64_t g : tn) regs |= 1u << (f->var[(size_t)g] >> 2);
-            const int k = (int)tn.size();
+            for (int32_t g = nb0; g < ne0; ++g)
+                if (f->var[(size_t)g] >= 0) regs |= 1u << (f->var[(size_t)g] >> 2);
+            const int k = (ne0 - nb0 - 1) / 2;            // internal nodes of a binary tree with ne0 - nb0 nodes
             const bool dual_able = within(regs, m_side1) || side2_ok(regs);      // == tg_dual_able(regs, R)
             // counted, not evaluated, when only sums are wanted.  Only trees that fit a DUAL table: an evaluation that
             // wants per-point results evaluates the COUNTABLE records like any other (a two-split tree on words (0,2)
@@ -755,11 +757,12 @@ void plan_fast_path(bartint_forest* f, const std::vector<int32_t>& tree_off, Fas
             uint32_t sel = 0, sel_t = 0, bias = 0, wgt = 0;
             int n = 0;
             for (int32_t t : bin.trees) {
-                perm[pos++] = (int32_t)((int64_t)s * f->m + t);
-                internal_nodes((int64_t)s * f->m + t, tn);
-                for (int64_t gi : tn) {
+                const int64_t kt = (int64_t)s * f->m + t;
+                perm[pos++] = (int32_t)kt;
+                for (int32_t gi = tree_off[(size_t)kt], ge = tree_off[(size_t)kt + 1]; gi < ge; ++gi) {
                     const size_t g = (size_t)gi;
                     const int v = f->var[g];
+                    if (v < 0) continue;                  // leaf
                     // byte of variable v inside the table's gather operands (see dual_offsets in kernels_gather.cu)
                     int byte = v;                                                   // table 1: words (0,1)
                     if (ps == 0) byte = v - base1;                                  // words (R-2,R-1)
@@ -780,8 +783,17 @@ void plan_fast_path(bartint_forest* f, const std::vector<int32_t>& tree_off, Fas
         };
         // pack a set of DUAL-able trees into the fewest records and emit them with the given record flags
         auto pack_and_emit = [&](std::vector<Item>& set, uint32_t rec_flags, bool evaluated_part) {
-            std::stable_sort(set.begin(), set.end(),
-                             [](const Item& a, const Item& b2) { return a.k != b2.k ? a.k > b2.k : a.flex < b2.flex; });
+            // stable order: larger trees first, less flexible ones first among equals (insertion sort: <= m items,
+            // no temporary buffer)
+            for (size_t q = 1; q < set.size(); ++q) {
+                const Item it = set[q];
+                size_t r = q;
+                while (r > 0 && (set[r - 1].k != it.k ? set[r - 1].k < it.k : set[r - 1].flex > it.flex)) {
+                    set[r] = set[r - 1];
+                    --r;
+                }
+                set[r] = it;
+            }
             cur_items = &set;
             int set_nodes = 0;
             for (const Item& it : set) set_nodes += it.k;
