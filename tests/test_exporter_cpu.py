@@ -101,3 +101,18 @@ def test_thread_count_does_not_change_the_result():
         for k in ("tree_offset", "var", "cut", "left", "right"):
             assert np.array_equal(o[k], outs[0][k])
         assert np.array_equal(o["mu"], outs[0]["mu"], equal_nan=True)
+
+
+def test_empty_and_degenerate_forests_on_the_host():
+    from bartint_b200 import FlatForest
+    z32 = np.zeros(0, np.int32)
+    ff = FlatForest(0, 5, 2, np.zeros(1, np.int64), z32, z32, z32, z32, np.zeros(0), np.array([0, 1, 2], np.int32),
+                    np.array([0.5, 0.5]), -0.5, 0.5)
+    plan = hosthooks.plan_soa(ff)
+    assert not plan["table_ok"] and plan["n_groups"] == 0                 # no trees: walk kernel territory, nothing planned
+    nn, out = hosthooks.export_dbarts(WireStrings(np.empty((5, 0), dtype=object)), np.zeros((3, 5, 0)), np.zeros((3, 2)),
+                                      [0, 1, 2], [0.5, 0.5])
+    assert nn == 0 and list(out["tree_offset"]) == [0]
+    stumps = synth.forest_from_trees([0.1, 0.2], 1, 2, [])                # d = 0: a forest of constants
+    plan = hosthooks.plan_soa(stumps)
+    assert plan["table_ok"] and not plan["gather"] and plan["n_groups"] == 1
