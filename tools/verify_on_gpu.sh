@@ -11,6 +11,8 @@ echo "== 1. default GPU matrix"
 timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/verify_gpu_default.log 2>&1; echo "exit $?"; tail -3 gpurun_out/verify_gpu_default.log
 echo "== 2. counting level 2 under every GPU parity test"
 BARTINT_TEST_COUNT2=1 timeout 900 python -m pytest tests -m gpu -x -q -k count2 > gpurun_out/verify_gpu_count2.log 2>&1; echo "exit $?"; tail -3 gpurun_out/verify_gpu_count2.log
+echo "== 2b. the R shim end to end through the mock R API"
+BARTINT_TEST_RSHIM_GPU=1 timeout 300 python -m pytest tests/test_r_shim_mock.py -x -q > gpurun_out/verify_rshim.log 2>&1; echo "exit $?"; tail -3 gpurun_out/verify_rshim.log
 echo "== 3. Monte Carlo step at counting levels 0 / 1 / 2 (same box)"
 : > gpurun_out/verify_count_levels.jsonl
 for L in 0 1 2; do
