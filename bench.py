@@ -69,6 +69,16 @@ def cpu_sample_run(ff, X, nthreads, budget_s, oc):
     return ff.S * ff.m * rows / dt, rows, dt
 
 
+def host_cores(oc):
+    """Threads for the CPU arm: every core this process may run on.  Not omp_get_max_threads(): torchrun exports
+    OMP_NUM_THREADS=1 to its workers, which would time the reference on ONE core at N > 1 (only rank 0 runs it, so
+    the whole host is its own)."""
+    try:
+        return max(len(os.sched_getaffinity(0)), oc.max_threads())
+    except AttributeError:
+        return max(os.cpu_count() or 1, oc.max_threads())
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -78,7 +88,7 @@ def run_reference(args):
     c = workload(args)
     x_train, y_train = synth.make_design(CFG)
     ff = synth.prior_forest(2000, c["S"], c["m"], x_train, y_train)
-    nthreads = oc.max_threads()
+    nthreads = host_cores(oc)
     rows = min(c["N"], 20000 * max(1, nthreads // 4))
     X = synth.make_points(CFG, rows)
     Xc = synth.make_points(CFG, c["C"], seed=777)
@@ -383,7 +393,7 @@ def run_ours(args):
     cpu = None
     if not args.no_cpu and world == 1:
         from oracle import oracle_c as oc
-        nthreads = oc.max_threads()
+        nthreads = host_cores(oc)
         rate, rows, secs = cpu_sample_run(flats[0], X_host.numpy().T, nthreads, args.cpu_budget, oc)
         rate1, rows1, _ = cpu_sample_run(flats[0], X_host.numpy().T, 1, min(args.cpu_budget, 5.0), oc)
         cpu = {"value": rate, "unit": UNIT, "cores": nthreads, "kind": "port",
