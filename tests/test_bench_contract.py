@@ -43,3 +43,20 @@ def test_our_arm_line():
     c = j["cpu_baseline"]
     assert c["kind"] == "port" and c["cores"] >= 1 and c["value"] > 0 and isinstance(c["sample"], str)
     assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(j["clocks"])
+
+
+def test_reference_arm_uses_all_cores_under_torchrun_env():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; the reference arm (rank 0 only) must still use the host."""
+    env = dict(os.environ, OMP_NUM_THREADS="1", RANK="0", WORLD_SIZE="2", LOCAL_RANK="0")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                          "--warmup", "0", "--points", "1500", "--draws", "40"], capture_output=True, text=True,
+                         timeout=600, cwd=ROOT, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    j = json.loads([l for l in out.stdout.splitlines() if l.strip()][0])
+    assert j["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0)) and j["n_gpus"] == 2
+    # the other ranks print nothing and exit 0
+    env["RANK"] = "1"
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                          "--warmup", "0", "--points", "1500", "--draws", "40"], capture_output=True, text=True,
+                         timeout=600, cwd=ROOT, env=env)
+    assert out.returncode == 0 and out.stdout.strip() == ""
