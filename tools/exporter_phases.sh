@@ -1,6 +1,7 @@
 #!/bin/bash
 # min over repetitions of each host phase of forest creation: tools/exporter_phases.sh [threads] [reps] [cfg]
-BARTINT_TIMING=1 python /root/repo/tools/exporter_bench.py --threads ${1:-1} --reps ${2:-7} --cfg ${3:-2} 2>&1 | python -c "
+HERE=$(cd "$(dirname "$0")" && pwd)
+BARTINT_TIMING=1 python "$HERE/exporter_bench.py" --threads ${1:-1} --reps ${2:-7} --cfg ${3:-2} 2>&1 | python -c "
 import sys, collections
 m = collections.defaultdict(lambda: 1e9)
 for l in sys.stdin:
