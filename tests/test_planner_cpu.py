@@ -209,3 +209,35 @@ def test_randomized_sweep(monkeypatch):
         X = rng.random((97, d))
         codes = onp.bin_points(X, ff.cut_offsets, ff.cut_values)
         _check_against_oracle(ff, X, codes, monkeypatch, kernel, count)
+
+
+def test_non_preorder_input_is_canonicalised(monkeypatch):
+    """bartint_forest_from_soa accepts any node order (children by index, root first); the library re-lays every tree
+    out in pre-order before planning.  Shuffle the nodes of every tree and compare with the oracle on the shuffled input."""
+    from bartint_b200 import FlatForest
+    rng = np.random.default_rng(21)
+    x = rng.random((50, 9))
+    ff = synth.prior_forest(21, 3, 30, x)
+    off = np.asarray(ff.tree_offset)
+    var, cut, left, right, mu = (np.array(getattr(ff, k)) for k in ("var", "cut", "left", "right", "mu"))
+    for k in range(ff.S * ff.m):
+        a, b = off[k], off[k + 1]
+        cnt = b - a
+        if cnt < 4:
+            continue
+        new_of_old = np.concatenate([[0], 1 + rng.permutation(cnt - 1)])         # root stays first
+        old_of_new = np.argsort(new_of_old)
+        remap = lambda child: np.where(child >= 0, new_of_old[np.maximum(child, 0)], -1)
+        v, c, l, r, u = var[a:b][old_of_new], cut[a:b][old_of_new], left[a:b][old_of_new], right[a:b][old_of_new], mu[a:b][old_of_new]
+        var[a:b], cut[a:b], left[a:b], right[a:b], mu[a:b] = v, c, remap(l), remap(r), u
+    shuffled = FlatForest(ff.S, ff.m, ff.d, off, var, cut, left, right, mu, ff.cut_offsets, ff.cut_values, ff.y_min, ff.y_max)
+    X = rng.random((150, 9))
+    np.testing.assert_allclose(onp.tree_sums(shuffled, X), onp.tree_sums(ff, X), rtol=0, atol=1e-15)   # same forest
+    codes = onp.bin_points(X, ff.cut_offsets, ff.cut_values)
+    monkeypatch.setenv("BARTINT_KERNEL", "gather")
+    monkeypatch.setenv("BARTINT_COUNT_SPLITS", "0")
+    a_plan, b_plan = pi.debug_plan(shuffled), pi.debug_plan(ff)
+    for key in ("hdr", "split", "desc", "tree_perm", "node_bit", "walk_nodes", "leaf_mu"):
+        assert np.array_equal(a_plan[key], b_plan[key]), key                      # identical after canonicalisation
+    got, _ = pi.interpret(a_plan, codes, sums_only=False)
+    np.testing.assert_allclose(got, onp.tree_sums(ff, X), rtol=0, atol=1e-13)
