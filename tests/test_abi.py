@@ -91,3 +91,48 @@ def test_malformed_inputs_rejected_before_touching_the_device():
         Forest.from_dbarts(np.array([["5 1 .."]], dtype=object), np.zeros((2, 1, 1)), rng.random((2, 1)),
                            [np.array([0.3, 0.6])], 0.0, 1.0)
     assert e.value.status == 2
+
+
+def test_corrupted_soa_forests_are_rejected_or_harmless():
+    """Seeded corruption sweep over the pre-flattened input (child indices, variables, cut indices, tree offsets): the
+    library either rejects the forest with a status code or the change was immaterial (a leaf's unused fields, another
+    valid value) -- it never crashes, hangs or plans from a malformed tree.  Host-only hook, no device needed."""
+    import numpy as np
+    from bartint_b200 import BartIntError, FlatForest, hosthooks, synth
+    rng = np.random.default_rng(99)
+    rejected = 0
+    for it in range(400):
+        d, m, S = int(rng.integers(1, 6)), int(rng.integers(1, 6)), int(rng.integers(1, 3))
+        ff = synth.prior_forest(it, S, m, rng.random((20, d)), numcut=int(rng.choice([3, 20, 100])))
+        a = {k: np.array(getattr(ff, k)) for k in ("var", "cut", "left", "right", "mu", "tree_offset")}
+        nn = len(a["var"])
+        j, kind = int(rng.integers(0, nn)), int(rng.integers(0, 6))
+        was_leaf = a["var"][j] < 0
+        if kind == 0:
+            a["left"][j] = int(rng.integers(-5, nn + 5))
+        elif kind == 1:
+            a["right"][j] = int(rng.integers(-5, nn + 5))
+        elif kind == 2:
+            a["var"][j] = int(rng.integers(-3, d + 3))
+        elif kind == 3:
+            a["cut"][j] = int(rng.integers(-3, 300))
+        elif kind == 4:
+            a["tree_offset"][int(rng.integers(1, len(a["tree_offset"])))] += int(rng.choice([-3, -2, -1, 1, 2, 3]))
+        else:
+            a["right"][j] = a["left"][j]
+        bad = FlatForest(S, m, d, a["tree_offset"], a["var"], a["cut"], a["left"], a["right"], a["mu"], ff.cut_offsets,
+                         ff.cut_values, -0.5, 0.5)
+        try:
+            hosthooks.plan_soa(bad)
+        except BartIntError as e:
+            assert e.status in (1, 2, 4)
+            rejected += 1
+            continue
+        # accepted: an internal node must still be a valid split
+        internal = a["var"] >= 0
+        assert (a["var"][internal] < d).all()
+        ncut = np.diff(np.asarray(ff.cut_offsets))
+        assert (a["cut"][internal] >= 0).all() and (a["cut"][internal] < ncut[a["var"][internal]]).all()
+        if kind in (0, 1, 5) and not was_leaf:
+            assert a["left"][j] != a["right"][j]
+    assert rejected > 100
