@@ -116,3 +116,40 @@ def test_empty_and_degenerate_forests_on_the_host():
     stumps = synth.forest_from_trees([0.1, 0.2], 1, 2, [])                # d = 0: a forest of constants
     plan = hosthooks.plan_soa(stumps)
     assert plan["table_ok"] and not plan["gather"] and plan["n_groups"] == 1
+
+
+def test_mutated_tree_strings_never_crash_the_parser():
+    """Seeded byte-level mutations of valid dbarts tree strings (deletions, insertions, digit / dot / space swaps):
+    the exporter either reports a parse error or returns a structurally valid forest."""
+    rng = np.random.default_rng(77)
+    x_train = rng.random((25, 3))
+    ff = synth.prior_forest(77, 4, 6, x_train)
+    strings, fits = ff.to_dbarts_state(x_train)
+    alphabet = list("0123456789 ..  -x")
+    parsed = rejected = 0
+    for it in range(400):
+        s2 = strings.copy()
+        t, s = int(rng.integers(ff.m)), int(rng.integers(ff.S))
+        chars = list(str(s2[t, s]))
+        for _ in range(int(rng.integers(1, 4))):
+            pos = int(rng.integers(0, len(chars) + 1))
+            op = int(rng.integers(3))
+            if op == 0 and chars:
+                del chars[min(pos, len(chars) - 1)]
+            elif op == 1:
+                chars.insert(pos, alphabet[int(rng.integers(len(alphabet)))])
+            elif chars:
+                chars[min(pos, len(chars) - 1)] = alphabet[int(rng.integers(len(alphabet)))]
+        s2[t, s] = "".join(chars)
+        try:
+            nn, got = hosthooks.export_dbarts(WireStrings(s2), fits, x_train, ff.cut_offsets, ff.cut_values)
+        except BartIntError as e:
+            assert e.status == 2, e
+            rejected += 1
+            continue
+        parsed += 1
+        off = got["tree_offset"]
+        assert off[-1] == nn and ((np.diff(off) % 2) == 1).all()
+        internal = got["var"] >= 0
+        assert (got["var"][internal] < ff.d).all() and (got["left"][internal] > 0).all() and (got["right"][internal] > 0).all()
+    assert rejected > 100 and parsed > 10
