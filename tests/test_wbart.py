@@ -248,3 +248,38 @@ def test_wbart_cpp_exporter_kat_on_host():
     ref = onp.forest_from_wbart(KAT_TEXT, KAT_CUTS, offset=KAT_OFFSET)
     for k in ("tree_offset", "var", "cut", "left", "right", "mu"):
         assert np.array_equal(got[k], getattr(ref, k)), k
+
+
+def test_mutated_wbart_text_never_crashes_the_parser():
+    """Seeded byte-level mutations of a valid treedraws text: a parse / argument error or a structurally valid forest."""
+    from bartint_b200 import BartIntError, hosthooks
+    rng = np.random.default_rng(55)
+    ff = synth.prior_forest(55, 3, 5, rng.random((30, 3)), None)
+    text = ff.to_wbart_text()
+    alphabet = list("0123456789 \n\n.-e+x\r")
+    parsed = rejected = 0
+    for it in range(400):
+        chars = list(text)
+        for _ in range(int(rng.integers(1, 4))):
+            pos = int(rng.integers(0, len(chars)))
+            op = int(rng.integers(4))
+            if op == 0:
+                del chars[pos]
+            elif op == 1:
+                chars.insert(pos, alphabet[int(rng.integers(len(alphabet)))])
+            elif op == 2:
+                chars[pos] = alphabet[int(rng.integers(len(alphabet)))]
+            else:
+                del chars[pos:pos + int(rng.integers(1, 40))]              # a truncated / spliced file
+        try:
+            got = hosthooks.export_wbart("".join(chars), ff.cut_lists())
+        except BartIntError as e:
+            assert e.status in (1, 2), e
+            rejected += 1
+            continue
+        parsed += 1
+        off = got["tree_offset"]
+        assert len(off) == got["S"] * got["m"] + 1 and ((np.diff(off) % 2) == 1).all()
+        internal = got["var"] >= 0
+        assert (got["var"][internal] < ff.d).all()
+    assert rejected > 100 and parsed > 10
