@@ -153,3 +153,29 @@ def test_mutated_tree_strings_never_crash_the_parser():
         internal = got["var"] >= 0
         assert (got["var"][internal] < ff.d).all() and (got["left"][internal] > 0).all() and (got["right"][internal] > 0).all()
     assert rejected > 100 and parsed > 10
+
+
+def test_draw_slices_export_to_the_matching_part_of_the_forest():
+    """dist.sharded_design_step lets rank r export only draws [lo_r, hi_r): a WireStrings view plus the matching slab of
+    savedTreeFits.  The pieces must be exactly the corresponding trees of the whole export."""
+    rng = np.random.default_rng(31)
+    x_train = rng.random((40, 5))
+    ff = synth.prior_forest(31, 11, 7, x_train)
+    strings, fits = ff.to_dbarts_state(x_train)
+    fits = np.asfortranarray(np.asarray(fits))
+    wire = WireStrings(strings)
+    _, whole = hosthooks.export_dbarts(wire, fits, x_train, ff.cut_offsets, ff.cut_values)
+    off = whole["tree_offset"]
+    from bartint_b200.dist import shard_range
+    covered = 0
+    for rank in range(4):
+        lo, hi = shard_range(ff.S, 4, rank)
+        _, part = hosthooks.export_dbarts(wire.slice_draws(lo, hi), fits[:, :, lo:hi], x_train, ff.cut_offsets,
+                                          ff.cut_values)
+        a, b = off[lo * ff.m], off[hi * ff.m]
+        assert np.array_equal(part["tree_offset"], off[lo * ff.m:hi * ff.m + 1] - a)
+        for k in ("var", "cut", "left", "right"):
+            assert np.array_equal(part[k], whole[k][a:b]), k
+        assert np.array_equal(part["mu"], whole["mu"][a:b], equal_nan=True)
+        covered += hi - lo
+    assert covered == ff.S
