@@ -400,6 +400,22 @@ def run_ours(args):
                "sample": f"{rows} of {N} MC points x all {S} draws x {m} trees ({secs:.1f} s), OpenMP over draws",
                "single_thread_value": rate1}
 
+    # ---- the step's results against the CPU oracle's values for the same seeded inputs at FULL size ----
+    # (tests/golden/bench_cfg2_expected.json, made by tools/bench_expected_cpu.py with oracle/oracle_c.c; the exact
+    #  integrals and the chosen candidate do not depend on the number of ranks, the Monte Carlo mean does)
+    check = {"integral_mean": float(d_int_ms[0].item()), "integral_sd": float(d_int_ms[1].item()),
+             "mc_mean": float(results["mean_var"][0].item()), "argmax_candidate": int(torch.argmax(results["var"]).item())}
+    golden_verdict = None
+    if not args.points and not args.draws:
+        try:
+            gold = json.load(open(os.path.join(ROOT, "tests", "golden", "bench_cfg2_expected.json")))["forests"]
+            want = gold[str(2000 + (args.steps - 1) % len(forests))]
+            keys = ["integral_mean", "integral_sd", "argmax_candidate"] + (["mc_mean"] if world == 1 else [])
+            worst = max(abs(check[k] - want[k]) / max(abs(want[k]), 1e-300) for k in keys)
+            golden_verdict = {"keys": keys, "max_rel_diff": worst, "agree_1e-9": bool(worst <= 1e-9)}
+        except Exception as e:                      # a missing golden file must not cost the bench line
+            golden_verdict = {"error": repr(e)}
+
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -412,9 +428,7 @@ def run_ours(args):
         "s_per_sequential_design_step": total_ms / args.steps / 1e3,
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "roofline_k0": roofline_k0,
         "cpu_baseline": cpu,
-        "results_check": {"integral_mean": float(d_int_ms[0].item()), "integral_sd": float(d_int_ms[1].item()),
-                          "mc_mean": float(results["mean_var"][0].item()),
-                          "argmax_candidate": int(torch.argmax(results["var"]).item())},
+        "results_check": dict(check, vs_cpu_oracle_full_size=golden_verdict),
     }
     emit(json.dumps(out))
     if world > 1:
