@@ -722,19 +722,22 @@ void plan_fast_path(bartint_forest* f, const std::vector<int32_t>& tree_off, Fas
         auto try_pack = [&](int K) -> bool {
             bins1.assign((size_t)K, Bin{});
             bins2.assign((size_t)K, Bin{});
+            size_t lo1 = 0, lo2 = 0;                      // bins before these are full: never looked at again
             for (const Item& it : *cur_items) {
                 Bin* best = nullptr;
                 int best_key = 0;                         // lower is better: widening << 8 | (4 - fill) << 1 | side 2
                 const int exact1 = it.k << 1, exact2 = (it.k << 1) | 1;      // keys of bins this tree would fill exactly
                 if (within(it.regs, m_side1))
-                    for (Bin& b : bins1) {
+                    for (size_t q = lo1; q < (size_t)K; ++q) {
+                        Bin& b = bins1[q];
                         if (b.nodes + it.k > 4) continue;
                         const int key = (4 - b.nodes) << 1;
                         if (best == nullptr || key < best_key) { best = &b; best_key = key; }
                         if (key == exact1) break;                           // nothing beats an exact fit on side 1
                     }
                 if (best_key != exact1 || best == nullptr)
-                    for (Bin& b : bins2) {
+                    for (size_t q = lo2; q < (size_t)K; ++q) {
+                        Bin& b = bins2[q];
                         const unsigned u = b.regs | it.regs;
                         if (b.nodes + it.k > 4 || !side2_ok(u)) continue;
                         const int widen = (!pair_ok(u) && pair_ok(b.regs)) ? 1 : 0;
@@ -746,6 +749,8 @@ void plan_fast_path(bartint_forest* f, const std::vector<int32_t>& tree_off, Fas
                 best->nodes += it.k;
                 best->regs |= it.regs;
                 best->trees.push_back(it.tree);
+                while (lo1 < (size_t)K && bins1[lo1].nodes >= 4) ++lo1;
+                while (lo2 < (size_t)K && bins2[lo2].nodes >= 4) ++lo2;
             }
             return true;
         };
