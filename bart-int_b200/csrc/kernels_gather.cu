@@ -89,7 +89,10 @@ size_t tg_smem_bytes() {
            (TK_NSTAGE + 1) * sizeof(uint64_t);
 }
 
-template <int NB, int R, bool MOMENTS, bool FULL, int P = TG_P>
+// COUNT = true is the sums-only evaluation of a counting-mode forest (skip COUNTABLE records, close draws at END_EVAL).
+// It is a compile-time variant so that the default kernel carries no trace of it: with the mode tested at run time
+// inside the stage loop the 16-point body spilled (STACK 32 -> 48, round-1 regression 5.56 -> 6.18 ms at cfg 2).
+template <int NB, int R, bool MOMENTS, bool FULL, int P = TG_P, bool COUNT = false>
 __global__ void __launch_bounds__(TG_THREADS, P > 8 ? 2 : MOMENTS ? 2 : 3) eval_gather_kernel(const TableParams prm) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int T = TG_THREADS, TILE = TG_THREADS * P;
@@ -160,11 +163,11 @@ __global__ void __launch_bounds__(TG_THREADS, P > 8 ? 2 : MOMENTS ? 2 : 3) eval_
         for (int base = 0; base < GS; base += 32) {
             const int gl = base + lane;
             const uint32_t fl = gl < ng ? *reinterpret_cast<const uint32_t*>(stage + gl * REC) : 0u;
-            const uint32_t end_flag = prm.count_mode ? TK_FLAG_END_EVAL : TK_FLAG_END_DRAW;
+            constexpr uint32_t end_flag = COUNT ? TK_FLAG_END_EVAL : TK_FLAG_END_DRAW;
             walk_mask |= (unsigned long long)__ballot_sync(0xffffffffu, (fl & TK_FLAG_WALK) != 0u) << base;
             end_mask |= (unsigned long long)__ballot_sync(0xffffffffu, (fl & end_flag) != 0u) << base;
             joint_mask |= (unsigned long long)__ballot_sync(0xffffffffu, (fl & TK_FLAG_JOINT) != 0u) << base;
-            skip_mask |= (unsigned long long)__ballot_sync(0xffffffffu, prm.count_mode && (fl & TK_FLAG_COUNTABLE) != 0u) << base;
+            if (COUNT) skip_mask |= (unsigned long long)__ballot_sync(0xffffffffu, (fl & TK_FLAG_COUNTABLE) != 0u) << base;
         }
         // DUAL records without a flag (the bulk) run in a tight loop; the next flagged record is found with one ffs
         auto dual_points = [&](auto variant, const uint4& da, uint32_t wB, uint32_t sel_t,
@@ -198,13 +201,13 @@ __global__ void __launch_bounds__(TG_THREADS, P > 8 ? 2 : MOMENTS ? 2 : 3) eval_
         int g = 0;
 #pragma unroll 1
         while (g < ng) {
-            const unsigned long long special = (walk_mask | end_mask | joint_mask | skip_mask) >> g;
+            const unsigned long long special = (COUNT ? (walk_mask | end_mask | joint_mask | skip_mask) : (walk_mask | end_mask | joint_mask)) >> g;
             const int g_stop = special ? min(ng, g + __ffsll((long long)special) - 1) : ng;
 #pragma unroll 1
             for (; g < g_stop; ++g) dual_group(stage + g * REC);
             if (g >= ng) break;
             const unsigned char* rec = stage + g * REC;
-            if ((skip_mask >> g) & 1ull) { ++g; continue; }      // counting mode: this record's trees are counted, not evaluated
+            if (COUNT && ((skip_mask >> g) & 1ull)) { ++g; continue; }      // this record's trees are counted, not evaluated
             if ((walk_mask >> g) & 1ull) {
                 // rare: a tree that does not fit a group, walked per point from global memory (L1/L2)
                 const int64_t kt = reinterpret_cast<const uint32_t*>(rec)[1];
@@ -296,32 +299,34 @@ int gather_tile(bool mom, bool full) { return TG_THREADS * gather_points_per_thr
 typedef void (*gather_kernel_t)(const TableParams);
 
 template <int NB, int R>
-static gather_kernel_t pick_gather(bool mom, bool full) {
+static gather_kernel_t pick_gather(bool mom, bool full, bool count) {
     if (mom && full) return eval_gather_kernel<NB, R, true, true>;
     if (mom) return eval_gather_kernel<NB, R, true, false>;
     if (full) return eval_gather_kernel<NB, R, false, true>;
-    if (gather_points_per_thread(mom, full) == 16) return eval_gather_kernel<NB, R, false, false, 16>;
-    return eval_gather_kernel<NB, R, false, false>;
+    if (gather_points_per_thread(mom, full) == 16)
+        return count ? eval_gather_kernel<NB, R, false, false, 16, true> : eval_gather_kernel<NB, R, false, false, 16>;
+    return count ? eval_gather_kernel<NB, R, false, false, TG_P, true> : eval_gather_kernel<NB, R, false, false>;
 }
 
 template <int NB>
-static gather_kernel_t pick_gather_r(int regs, bool mom, bool full) {
+static gather_kernel_t pick_gather_r(int regs, bool mom, bool full, bool count) {
     switch (regs) {
-        case 2: return pick_gather<NB, 2>(mom, full);
-        case 3: return pick_gather<NB, 3>(mom, full);
-        default: return pick_gather<NB, 4>(mom, full);
+        case 2: return pick_gather<NB, 2>(mom, full, count);
+        case 3: return pick_gather<NB, 3>(mom, full, count);
+        default: return pick_gather<NB, 4>(mom, full, count);
     }
 }
 
-static gather_kernel_t gather_kernel_for(const bartint_forest* f, bool mom, bool full, size_t* smem) {
-    if (f->nb == 4) { *smem = tg_smem_bytes<4>(); return pick_gather_r<4>(f->g_regs, mom, full); }
+// count: the sums-only evaluation of a counting-mode forest (EvalPlan::count_mode); never with mom / full
+static gather_kernel_t gather_kernel_for(const bartint_forest* f, bool mom, bool full, bool count, size_t* smem) {
+    if (f->nb == 4) { *smem = tg_smem_bytes<4>(); return pick_gather_r<4>(f->g_regs, mom, full, count); }
     *smem = tg_smem_bytes<5>();
-    return pick_gather_r<5>(f->g_regs, mom, full);
+    return pick_gather_r<5>(f->g_regs, mom, full, count);
 }
 
 int gather_resident_ctas(const bartint_forest* f, bool mom, bool full) {
     size_t smem = 0;
-    gather_kernel_t k = gather_kernel_for(f, mom, full, &smem);
+    gather_kernel_t k = gather_kernel_for(f, mom, full, f->count_mode && !mom && !full, &smem);
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int nblk = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, k, TG_THREADS, smem) != cudaSuccess || nblk < 1) {
@@ -361,7 +366,7 @@ int launch_eval_gather(const bartint_forest* f, const bartint_points* p, const E
     prm.fp_scaled = fp_scaled;
     prm.count_mode = plan.count_mode ? 1 : 0;
     size_t smem = 0;
-    gather_kernel_t k = gather_kernel_for(f, pt_mean != nullptr, full_pred != nullptr, &smem);
+    gather_kernel_t k = gather_kernel_for(f, pt_mean != nullptr, full_pred != nullptr, plan.count_mode, &smem);
     BI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)plan.n_tiles, (unsigned)plan.n_chunks);
     k<<<grid, TG_THREADS, smem, st>>>(prm);

@@ -1,5 +1,6 @@
 """GPU parity at the shapes of the BASELINE configs: >= 1e6 (draw, tree, point) leaf triples bit-equal
-to the oracle, and small instances of cfg 1 (d=1), cfg 2, cfg 4 (gaussian-measure points) and cfg 5 (survey-shaped
+to the oracle, and small instances of cfg 1 (d=1), cfg 2, cfg 3 (d=20, 200 trees per draw: the kernels for more
+than 16 variables), cfg 4 (gaussian-measure points) and cfg 5 (survey-shaped
 integer features with per-candidate variance) against the C restatement of the reference arithmetic."""
 import numpy as np
 import pytest
@@ -46,7 +47,7 @@ def test_leaf_indices_two_million_triples():
     pts.close(); f.close()
 
 
-@pytest.mark.parametrize("cfg,S,N", [(1, 200, 100), (2, 60, 20000), (4, 40, 20000), (5, 50, 6000)])
+@pytest.mark.parametrize("cfg,S,N", [(1, 200, 100), (2, 60, 20000), (3, 20, 5000), (4, 40, 20000), (5, 50, 6000)])
 def test_config_shapes_small(cfg, S, N):
     c = synth.CONFIGS[cfg]
     x_train, y_train = synth.make_design(cfg, scale=0.2 if cfg == 4 else 1.0)
