@@ -22,6 +22,7 @@ handle_p = C.POINTER(C.c_void_p)
 # name -> (restype, argtypes); kept in one table so tests can check every symbol of the header
 SIGNATURES = {
     "bartint_version": (C.c_int, []),
+    "bartint_forest_bitslice_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "bartint_last_error": (C.c_char_p, []),
     "bartint_device_count": (C.c_int, [c_int32_p]),
     "bartint_set_device": (C.c_int, [C.c_int]),
@@ -96,6 +97,7 @@ SIGNATURES = {
 
 BARTINT_SCALED_UNITS = 0x1
 BARTINT_FORCE_WALK = 0x2
+BARTINT_NO_BITSLICE = 0x4
 MEASURES = {"uniform": 0, "gaussian": 1, "exponential": 2, "gaussian_correct": 3}
 STATUS_NAMES = {0: "OK", 1: "ERR_ARG", 2: "ERR_PARSE", 3: "ERR_CUDA", 4: "ERR_UNSUPPORTED", 5: "ERR_NOMEM",
                 6: "ERR_NODEVICE"}

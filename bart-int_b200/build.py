@@ -15,7 +15,8 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libbartint_cuda.so")
 SYNTH_LIB = os.path.join(HERE, "libbartint_synth.so")
 
-CUDA_SOURCES = ["bartint_abi.cu", "forest_host.cu", "kernels_eval.cu", "kernels_gather.cu", "kernels_misc.cu"]
+CUDA_SOURCES = ["bartint_abi.cu", "forest_host.cu", "kernels_eval.cu", "kernels_gather.cu", "kernels_bitslice.cu",
+                "kernels_misc.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC,-fopenmp,-O3", "-shared", "-lgomp",

@@ -41,7 +41,9 @@ struct DeviceGuard {
 };
 
 static void free_device(DeviceForest& d, unsigned char* image_base = nullptr) {
-    if (image_base != nullptr) {           // an unpacked forest: one allocation holds every array
+    for (void* q : {(void*)d.bs_pool, (void*)d.bs_slice_hdr, (void*)d.bs_base})     // never part of an image
+        if (q) cudaFreeAsync(q, nullptr);
+    if (image_base != nullptr) {           // an unpacked forest: one allocation holds every other array
         cudaFreeAsync(image_base, nullptr);
         d = DeviceForest{};
         return;
@@ -104,7 +106,7 @@ using namespace bartint;
 
 extern "C" {
 
-int bartint_version(void) { return 100; }
+int bartint_version(void) { return 200; }
 
 int64_t bartint_kernel_launch_count(void) { return (int64_t)bartint::launch_count(); }
 
@@ -348,6 +350,15 @@ int bartint_forest_info(const bartint_forest* f, int64_t info[12]) {
     info[9] = f->nb;
     info[10] = f->table_ok ? (f->gather ? 2 : 1) : 0;
     info[11] = f->gather ? f->g_regs : 0;
+    return BARTINT_OK;
+}
+
+int bartint_forest_bitslice_info(const bartint_forest* f, int64_t info[8]) {
+    BI_REQUIRE(f != nullptr && info != nullptr, BARTINT_ERR_ARG, "NULL argument");
+    for (int k = 0; k < 8; ++k) info[k] = 0;
+    if (!f->bs_ok) return BARTINT_OK;
+    info[0] = 1; info[1] = f->bs_ncuts; info[2] = f->bs_ch; info[3] = f->bs_rows; info[4] = f->bs_anc; info[5] = f->bs_q;
+    info[6] = bs_pool_bytes(f); info[7] = (int64_t)(f->bs_ncuts + 1) * (f->bs_ch * 16 + 4);
     return BARTINT_OK;
 }
 
@@ -629,11 +640,11 @@ static int eval_core(const bartint_forest* f, const bartint_points* p, uint32_t 
     const bool want_mom = d_point_mean != nullptr && d_point_m2 != nullptr;
     if (d_leaf != nullptr) flags |= BARTINT_FORCE_WALK;
     EvalPlan plan = make_plan(f, p, flags, draw_begin, draw_end, want_mom, d_full != nullptr);
-    if (!plan.use_gather) {                   // walk / table kernels read the feature-major rows
+    if (plan.use_bitslice ? p->codes_pm == nullptr : !plan.use_gather) {   // walk / table kernels read the feature-major rows
         int rc0 = ensure_codes(p, st);
         if (rc0) return rc0;
     }
-    f->last_used_table[slot] = plan.use_table ? 1 : 0;
+    f->last_used_table[slot] = plan.use_bitslice ? 2 : plan.use_table ? 1 : 0;
     double *draw_part = nullptr, *pt_mean = nullptr, *pt_m2 = nullptr;
     BI_CUDA(cudaMallocAsync((void**)&draw_part, sizeof(double) * (size_t)plan.n_tiles * (size_t)ndraws, st));
     const bool direct_mom = want_mom && plan.n_chunks == 1;   // single chunk: the kernel writes the final moments
@@ -646,13 +657,17 @@ static int eval_core(const bartint_forest* f, const bartint_points* p, uint32_t 
         }
     }
     BI_CUDA(cudaEventRecord(f->ev0[slot], st));
-    int rc = plan.use_gather ? launch_eval_gather(f, p, plan, draw_part, pt_mean, pt_m2, d_full, fp_scale, fp_y0, fp_scaled, st)
+    int rc = plan.use_bitslice ? launch_eval_bitslice(f, p, plan, draw_part, st)
+             : plan.use_gather ? launch_eval_gather(f, p, plan, draw_part, pt_mean, pt_m2, d_full, fp_scale, fp_y0, fp_scaled, st)
              : plan.use_table ? launch_eval_table(f, p, plan, draw_part, pt_mean, pt_m2, d_full, fp_scale, fp_y0, fp_scaled, st)
                               : launch_eval_walk(f, p, plan, draw_part, pt_mean, pt_m2, d_leaf, d_full, fp_scale, fp_y0, fp_scaled, st);
     BI_CUDA(cudaEventRecord(f->ev1[slot], st));
     f->last_timed[slot] = true;
     f->last_launches[slot] = 1;
-    if (rc == BARTINT_OK && d_draw_sum != nullptr) {
+    if (rc == BARTINT_OK && d_draw_sum != nullptr && plan.use_bitslice) {
+        rc = launch_bs_reduce(f, draw_part, plan.n_tiles, draw_begin, ndraws, p->N, d_draw_sum, st);
+        f->last_launches[slot]++;
+    } else if (rc == BARTINT_OK && d_draw_sum != nullptr) {
         rc = launch_reduce_draw_parts(draw_part, plan.n_tiles, ndraws, d_draw_sum, st);
         f->last_launches[slot]++;
         if (rc == BARTINT_OK && plan.count_mode) {      // + the single-split trees, from 1-D code histograms
@@ -1044,6 +1059,8 @@ struct ImageHeader {
     int64_t n_nodes, n_leaves, n_groups, n_cuts, device_bytes;
     double y_min, y_max;
     int64_t bytes[11];       // device array sizes (0 = absent), order of image_arrays()
+    int32_t draw_internal_max, pad0;     // inputs of bs_configure: the bit-sliced form is rebuilt on the device
+    double max_abs_mu;
 };
 constexpr uint32_t kImageMagic = 0x42494E54u;   // "BINT"
 
@@ -1096,6 +1113,7 @@ int bartint_forest_pack(const bartint_forest* f, void* host_header, int64_t host
     h.reserved = f->count_level;          // counting level of the records (0: none)
     h.n_nodes = f->n_nodes; h.n_leaves = f->n_leaves; h.n_groups = f->n_groups; h.n_cuts = (int64_t)f->cut_val.size();
     h.device_bytes = db; h.y_min = f->y_min; h.y_max = f->y_max;
+    h.draw_internal_max = f->draw_internal_max; h.max_abs_mu = f->max_abs_mu;
     void** slots[11];
     DeviceForest tmp = f->dev;
     image_arrays(f, nullptr, h.bytes, slots, &tmp);
@@ -1177,6 +1195,12 @@ int bartint_forest_unpack(const void* host_header, int64_t host_bytes, const voi
             *slots[k] = h.bytes[k] > 0 ? (void*)(f->image_base + off) : nullptr;
             off += pad256(h.bytes[k]);
         }
+    }
+    if (e == cudaSuccess) {                 // the bit-sliced form is not in the image: rebuild it from the walk form
+        f->draw_internal_max = h.draw_internal_max;
+        f->max_abs_mu = h.max_abs_mu;
+        bs_configure(f);
+        if (launch_build_bitslice(f, st) != BARTINT_OK) e = cudaErrorUnknown;
     }
     for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
         e = cudaEventCreate(&f->ev0[k]);

@@ -101,6 +101,10 @@ struct DeviceForest {
     int32_t* group_tree_off = nullptr; // n_groups+1: first (permuted) tree position of each group
     int32_t* draw_group_off = nullptr; // S+1: first group of each draw
     uint8_t* group_rec = nullptr;      // n_groups * tk_rec_bytes(nb)
+    // bit-sliced form (kernels_bitslice.cu), built on the device from the walk form; never part of a forest image
+    unsigned char* bs_pool = nullptr;  // ELL rows of the internal nodes, one block per slice of 32 draws
+    int4* bs_slice_hdr = nullptr;      // per slice: rows of class A, B, C and the deepest C node
+    double* bs_base = nullptr;         // S: sum over the draw's trees of the leftmost leaf value
 };
 
 }  // namespace bartint
@@ -127,6 +131,12 @@ struct bartint_forest {
     int g_regs = 0;                    // gather: code words per point
     int nb = 0;
     int64_t n_groups = 0;
+    // bit-sliced sums-only kernel (bs_configure): applies / predicate rows / 128-point chunks per tile / longest draw
+    // (internal nodes) / ancestor planes / fixed-point exponent of the leaf differences
+    bool bs_ok = false;
+    int32_t bs_ncuts = 0, bs_ch = 0, bs_rows = 0, bs_anc = 0, bs_q = 0;
+    int32_t draw_internal_max = 0;     // most internal nodes in one draw
+    double max_abs_mu = 0.0;           // largest |leaf value|
     std::vector<int32_t> draw_group_off;  // host copy, S+1
     bartint::DeviceForest dev;
     unsigned char* image_base = nullptr;  // forests restored by bartint_forest_unpack: the one allocation behind `dev`
@@ -203,6 +213,14 @@ int launch_eval_gather(const bartint_forest* f, const bartint_points* p, const E
                        int fp_scaled, cudaStream_t st);
 int launch_gather_leaf(const bartint_forest* f, const bartint_points* p, int32_t draw_begin, int32_t draw_end,
                        int32_t* leaf_out, cudaStream_t st);
+void bs_configure(bartint_forest* f);                        // host: does the bit-sliced kernel apply, table sizes
+int launch_build_bitslice(bartint_forest* f, cudaStream_t st);   // device: walk form -> ELL rows
+int bs_tile(const bartint_forest* f);
+int64_t bs_pool_bytes(const bartint_forest* f);
+int launch_eval_bitslice(const bartint_forest* f, const bartint_points* p, const EvalPlan& plan, double* draw_part,
+                         cudaStream_t st);
+int launch_bs_reduce(const bartint_forest* f, const double* draw_part, int n_tiles, int32_t draw_begin, int ndraws,
+                     int64_t N, double* draw_sum, cudaStream_t st);
 int gather_tile(bool mom, bool full);
 int gather_resident_ctas(const bartint_forest* f, bool mom, bool full);   // occupancy query for make_plan
 inline int fast_rec_bytes(const bartint_forest* f) { return f->gather ? tg_rec_bytes(f->nb) : tk_rec_bytes(f->nb); }
@@ -210,8 +228,9 @@ inline int fast_tbl_off(const bartint_forest* f) { return f->gather ? tg_tbl_off
 
 struct EvalPlan {
     int32_t draw_begin, draw_end;
-    int n_tiles, n_chunks, chunk_draws;
+    int n_tiles, n_chunks, chunk_draws;   // (bit-sliced kernel: chunk_draws counts slices of 32 draws)
     int tile;          // points per CTA
+    bool use_bitslice; // sums-only evaluation by the bit-sliced kernel (kernels_bitslice.cu)
     bool use_table;    // a fast kernel (table or gather format) is used, else the walk kernel
     bool use_gather;   // ... and it is the gather kernel
     bool count_mode;   // sums-only evaluation of a counting-mode forest: COUNTABLE records skipped, their trees counted

@@ -503,6 +503,24 @@ int forest_finish_host(bartint_forest* f) {
     f->n_leaves = n_leaves;
     f->max_depth = max_depth;
     f->max_internal = max_internal;
+    // for the bit-sliced kernel: the longest draw and the largest |leaf value| (fixed-point scale)
+    int32_t draw_internal_max = 0;
+    double max_abs_mu = 0.0;
+    bool mu_finite = true;
+#pragma omp parallel for schedule(static) reduction(max : draw_internal_max, max_abs_mu) reduction(&& : mu_finite)
+    for (int32_t s = 0; s < f->S; ++s) {
+        const int64_t g0 = f->tree_off[(size_t)s * (size_t)f->m], g1 = f->tree_off[(size_t)(s + 1) * (size_t)f->m];
+        draw_internal_max = std::max(draw_internal_max, (int32_t)((g1 - g0 - f->m) / 2));
+        for (int64_t g = g0; g < g1; ++g)
+            if (f->var[(size_t)g] < 0) {
+                const double a = std::fabs(f->mu[(size_t)g]);
+                if (!(a <= 1.7e308)) mu_finite = false;
+                else max_abs_mu = std::max(max_abs_mu, a);
+            }
+    }
+    f->draw_internal_max = draw_internal_max;
+    f->max_abs_mu = mu_finite ? max_abs_mu : INFINITY;
+    bs_configure(f);
     pt.lap("validate + stats");
     return BARTINT_OK;
 }
@@ -1005,6 +1023,7 @@ int forest_upload(bartint_forest* f) {
     if ((rc = upload(&f->dev.cut_off, f->cut_off))) return rc;
     if ((rc = upload(&f->dev.cut_val, f->cut_val))) return rc;
 
+    if ((rc = launch_build_bitslice(f, nullptr))) return rc;
     pt.lap("upload: H2D walk form");
     FastPlan P;
     plan_fast_path(f, tree_off, P);

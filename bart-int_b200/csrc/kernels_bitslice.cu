@@ -1,0 +1,479 @@
+// K1b  per-draw sums by BIT-SLICED evaluation:  rowMeans(predict(model, X))  without per-point work per tree.
+//
+// Replaces, for evaluations that only want the per-draw sums (the Monte Carlo integral of BASELINE configs 2-4 and
+// the survey estimator, src/survey_design/bartMean.R:74-82 `rowMeans(pred)`), the per-point table lookups of the
+// gather / table kernels.  Identity used (pre-order trees, L(a) = value of the leftmost leaf below node a):
+//
+//     f_t(x) = L(root) + sum over internal nodes a of  [x reaches a  and  goes right at a] * (L(right(a)) - L(a))
+//
+// "goes right at a" is the predicate  code_v(x) > cut  and "reaches a" is the AND of the ancestors' predicates (negated
+// for ancestors left through their left child).  For a tile of T points every predicate (variable v, cut c) is ONE
+// bit vector M[v,c] of T bits, built once per CTA in shared memory from the points' uint8 cut codes.  A node then
+// costs a few 128-bit loads, AND and POPC for the whole tile instead of one lookup per point, and
+//
+//     sum_{i in tile} f_t(x_i) = T * L(root) + sum_a delta_a * popc( AND of ancestor literals & M[v_a, c_a] ).
+//
+// delta_a is held as a 64-bit FIXED-POINT number (scale 2^Q chosen from max |mu|) and the products are accumulated in
+// 64-bit integers, so the sum over the nodes of a draw and the points of a tile is exact and independent of the
+// order in which nodes are visited; one rounding happens when the tile's total is converted to fp64.
+//
+// Work layout ("lanes are draws"): the nodes of 32 consecutive draws (a SLICE) are stored as ELL rows -- row k holds
+// the k-th node of each of the 32 draws, 16 bytes per lane -- so a warp reads a row with one coalesced LDG.128, every
+// lane accumulates the sum of ITS draw in registers, and no cross-lane reduction or atomics are needed.  Three node
+// classes per slice, each padded to the slice's longest draw with delta = 0 entries:
+//     A  root nodes            popc(M[v,c]) over the tile comes from a per-tile count table P[v,c]   (1 LDS.32)
+//     B  children of the root  popc((M[parent] ^ pol) & M[own])                                   (2 x CH LDS.128)
+//     C  depth >= 2            own mask ANDed with every ancestor literal (ancestor planes, u32 per entry)
+// Shared-memory rows are CH x 16 bytes (CH x 128 points); lane q reads the chunks in the order c ^ (q & 7), so the
+// eight lanes of an LDS.128 phase always hit eight different 16-byte bank groups whatever rows they address.
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+
+#include "pipeline.cuh"
+
+namespace bartint {
+
+constexpr int BS_THREADS = 512;                 // 16 warps, one CTA per SM (the mask table fills shared memory)
+constexpr int BS_NWARP = BS_THREADS / 32;
+constexpr size_t BS_SMEM_MAX = 227 * 1024;
+
+// ---------------------------------------------------------------------------------------------
+// device builder: walk form -> ELL rows (run once per forest, right after the upload)
+// ---------------------------------------------------------------------------------------------
+struct BsLayout {
+    int64_t slice_bytes;
+    int32_t off_a, off_b, off_c, off_anc;      // byte offsets of the class blocks inside a slice
+    int32_t cap_c;                              // rows of the C block (stride of an ancestor plane)
+    int32_t anc_planes;
+    int32_t row_bytes;                          // CH * 16
+    int32_t ones_off;                           // byte offset of the all-ones mask row (row index n_cuts)
+};
+
+static BsLayout bs_layout_of(const bartint_forest* f) {
+    BsLayout L{};
+    const int cap_a = std::max(f->m, 1), cap_b = std::max(std::min(2 * f->m, f->bs_rows), 1), cap_c = std::max(f->bs_rows, 1);
+    L.anc_planes = f->bs_anc;
+    L.cap_c = cap_c;
+    L.off_a = 0;
+    L.off_b = L.off_a + 512 * cap_a;
+    L.off_c = L.off_b + 512 * cap_b;
+    L.off_anc = L.off_c + 512 * cap_c;
+    L.slice_bytes = (int64_t)L.off_anc + 128ll * L.anc_planes * cap_c;
+    L.row_bytes = f->bs_ch * 16;
+    L.ones_off = f->bs_ncuts * L.row_bytes;
+    return L;
+}
+
+// one pass over a tree in pre-order; calls emit(depth, node index a, leaves seen before a, path) for every internal node
+template <typename Emit>
+__device__ __forceinline__ void bs_walk_tree(const uint2* __restrict__ nd, int cnt, const int32_t* __restrict__ cut_off,
+                                             int row_bytes, Emit emit) {
+    uint32_t path[64];      // per depth: byte offset of the ancestor's mask row | negated << 31
+    int pend[64];           // depths of the ancestors whose right subtree is still to come
+    int np = 0, depth = 0, leaves = 0;
+    for (int a = 0; a < cnt; ++a) {
+        const uint2 r = nd[a];
+        const uint32_t var = r.x & 0xFFFFu;
+        if (var != LEAF_VAR) {
+            const uint32_t vc = (uint32_t)cut_off[var] + (r.x >> 16);
+            emit(depth, a, leaves, r.y, vc, path);
+            if (depth < 64) {
+                path[depth] = (vc * (uint32_t)row_bytes) | 0x80000000u;     // the left subtree comes next: literal negated
+                pend[np++] = depth;
+            }
+            ++depth;
+        } else {
+            ++leaves;
+            if (np > 0) {
+                const int dp = pend[--np];
+                path[dp] &= 0x7FFFFFFFu;                                    // now in that ancestor's right subtree
+                depth = dp + 1;
+            }
+        }
+    }
+}
+
+// counts per tree: x = root nodes (0/1), y = depth-1 nodes, z = deeper nodes, w = largest depth of a C node
+__global__ void __launch_bounds__(128) bs_count_kernel(const uint2* __restrict__ nodes, const int32_t* __restrict__ tree_off,
+                                                       const int32_t* __restrict__ cut_off, int64_t n_trees,
+                                                       ushort4* __restrict__ tree_cnt) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_trees) return;
+    int ca = 0, cb = 0, cc = 0, dmax = 0;
+    bs_walk_tree(nodes + tree_off[k], tree_off[k + 1] - tree_off[k], cut_off, 16,
+                 [&](int depth, int, int, uint32_t, uint32_t, const uint32_t*) {
+                     if (depth == 0) ++ca;
+                     else if (depth == 1) ++cb;
+                     else { ++cc; dmax = max(dmax, depth); }
+                 });
+    tree_cnt[k] = make_ushort4((unsigned short)ca, (unsigned short)cb, (unsigned short)cc, (unsigned short)dmax);
+}
+
+// one warp per slice, one lane per draw: first rows of every tree inside its draw's column, the slice's row counts
+// (the longest draw), and base[s] = sum_t L(root_t)
+__global__ void __launch_bounds__(128) bs_layout_kernel(const ushort4* __restrict__ tree_cnt, const int32_t* __restrict__ tree_leaf_off,
+                                                        const double* __restrict__ leaf_mu, int S, int m,
+                                                        ushort4* __restrict__ tree_row, int4* __restrict__ slice_hdr,
+                                                        double* __restrict__ base) {
+    const int sl = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (sl * 32 >= S) return;
+    const int s = sl * 32 + lane;
+    int ra = 0, rb = 0, rc = 0, dmax = 0;
+    double b = 0.0;
+    if (s < S) {
+        for (int t = 0; t < m; ++t) {
+            const int64_t k = (int64_t)s * m + t;
+            const ushort4 c = tree_cnt[k];
+            tree_row[k] = make_ushort4((unsigned short)ra, (unsigned short)rb, (unsigned short)rc, 0);
+            ra += c.x; rb += c.y; rc += c.z;
+            dmax = max(dmax, (int)c.w);
+            b += leaf_mu[tree_leaf_off[k]];                 // leaf ordinal 0 = the leftmost leaf
+        }
+        base[s] = b;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        ra = max(ra, __shfl_xor_sync(0xffffffffu, ra, o));
+        rb = max(rb, __shfl_xor_sync(0xffffffffu, rb, o));
+        rc = max(rc, __shfl_xor_sync(0xffffffffu, rc, o));
+        dmax = max(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+    }
+    if (lane == 0) slice_hdr[sl] = make_int4(ra, rb, rc, dmax);
+}
+
+__global__ void __launch_bounds__(128) bs_fill_kernel(const uint2* __restrict__ nodes, const int32_t* __restrict__ tree_off,
+                                                      const int32_t* __restrict__ tree_leaf_off, const double* __restrict__ leaf_mu,
+                                                      const int32_t* __restrict__ cut_off, int64_t n_trees, int m,
+                                                      const ushort4* __restrict__ tree_row, BsLayout L, double fx_scale,
+                                                      unsigned char* __restrict__ pool) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_trees) return;
+    const int s = (int)(k / m), lane = s & 31;
+    unsigned char* __restrict__ sp = pool + (int64_t)(s >> 5) * L.slice_bytes;
+    const ushort4 r0 = tree_row[k];
+    int ra = r0.x, rb = r0.y, rc = r0.z;
+    const double* __restrict__ mu = leaf_mu + tree_leaf_off[k];
+    bs_walk_tree(nodes + tree_off[k], tree_off[k + 1] - tree_off[k], cut_off, L.row_bytes,
+                 [&](int depth, int, int leaves, uint32_t roff, uint32_t vc, const uint32_t* path) {
+                     // leaves before the right child = leaves before a + leaves of the left subtree (roff - 1 nodes)
+                     const double delta = mu[leaves + (int)(roff >> 1)] - mu[leaves];
+                     const long long fx = __double2ll_rn(delta * fx_scale);
+                     const uint32_t lo = (uint32_t)(unsigned long long)fx, hi = (uint32_t)((unsigned long long)fx >> 32);
+                     if (depth == 0) {
+                         reinterpret_cast<uint4*>(sp + L.off_a)[ra * 32 + lane] = make_uint4(lo, hi, vc, 0u);
+                         ++ra;
+                     } else if (depth == 1) {
+                         reinterpret_cast<uint4*>(sp + L.off_b)[rb * 32 + lane] =
+                             make_uint4(lo, hi, path[0], vc * (uint32_t)L.row_bytes);
+                         ++rb;
+                     } else {
+                         reinterpret_cast<uint4*>(sp + L.off_c)[rc * 32 + lane] =
+                             make_uint4(lo, hi, vc * (uint32_t)L.row_bytes, (uint32_t)depth);
+                         uint32_t* __restrict__ anc = reinterpret_cast<uint32_t*>(sp + L.off_anc);
+                         for (int a = 0; a < L.anc_planes; ++a)
+                             anc[((int64_t)a * L.cap_c + rc) * 32 + lane] = a < depth ? path[a] : (uint32_t)L.ones_off;
+                         ++rc;
+                     }
+                 });
+}
+
+// Decides whether the bit-sliced kernel applies to the forest and sizes its tables (host; no CUDA call).
+//   bs_ncuts  total number of cut points = number of predicate rows
+//   bs_ch     128-point chunks per tile: the largest of 8 / 4 / 2 whose mask table fits shared memory
+//   bs_rows   longest draw (internal nodes), bs_anc = ancestor planes = deepest internal node
+void bs_configure(bartint_forest* f) {
+    f->bs_ok = false;
+    const char* e = getenv("BARTINT_BITSLICE");
+    if (e && e[0] == '0') return;
+    if (f->S < 1 || f->m < 1 || f->d < 1) return;
+    const int64_t ncuts = f->cut_off[(size_t)f->d];
+    if (ncuts < 1 || f->max_depth < 1 || f->max_depth > 33) return;     // (no split anywhere: nothing to slice)
+    if (f->draw_internal_max < 1 || f->draw_internal_max >= 65535 || f->m >= 65535) return;
+    int ch = 0;
+    for (int c : {8, 4, 2})
+        if ((size_t)(ncuts + 1) * (size_t)(c * 16 + 4) + 64 <= BS_SMEM_MAX) { ch = c; break; }
+    if (ch == 0 || (ncuts + 1) * (int64_t)ch * 16 >= (int64_t)1 << 31) return;
+    f->bs_ncuts = (int32_t)ncuts;
+    f->bs_ch = ch;
+    f->bs_rows = f->draw_internal_max;
+    f->bs_anc = std::max(2, f->max_depth - 1);
+    // fixed point: |delta| <= 2 max|mu| < 2^(e+1)  ->  |delta * 2^Q| < 2^61 with Q = 60 - e
+    const double dmax = 2.0 * f->max_abs_mu;
+    int ex = 0;
+    if (dmax > 0.0 && std::isfinite(dmax)) ex = std::ilogb(dmax);
+    else if (!std::isfinite(dmax)) return;                               // NaN / Inf leaf values: keep the fp64 kernels
+    f->bs_q = 60 - ex;
+    if (f->bs_q > 1000 || f->bs_q < -900) return;
+    f->bs_ok = true;
+}
+
+int launch_build_bitslice(bartint_forest* f, cudaStream_t st) {
+    if (!f->bs_ok) return BARTINT_OK;
+    const BsLayout L = bs_layout_of(f);
+    const int64_t n_trees = (int64_t)f->S * f->m;
+    const int n_slices = (f->S + 31) / 32;
+    const size_t pool_bytes = (size_t)L.slice_bytes * (size_t)n_slices;
+    ushort4 *tree_cnt = nullptr, *tree_row = nullptr;
+    BI_CUDA(cudaMallocAsync((void**)&f->dev.bs_pool, pool_bytes, st));
+    BI_CUDA(cudaMallocAsync((void**)&f->dev.bs_slice_hdr, sizeof(int4) * (size_t)n_slices, st));
+    BI_CUDA(cudaMallocAsync((void**)&f->dev.bs_base, sizeof(double) * (size_t)f->S, st));
+    BI_CUDA(cudaMallocAsync((void**)&tree_cnt, sizeof(ushort4) * (size_t)n_trees, st));
+    BI_CUDA(cudaMallocAsync((void**)&tree_row, sizeof(ushort4) * (size_t)n_trees, st));
+    BI_CUDA(cudaMemsetAsync(f->dev.bs_pool, 0, pool_bytes, st));
+    const unsigned gt = (unsigned)((n_trees + 127) / 128);
+    bs_count_kernel<<<gt, 128, 0, st>>>(f->dev.nodes, f->dev.tree_off, f->dev.cut_off, n_trees, tree_cnt);
+    bs_layout_kernel<<<(unsigned)((n_slices * 32 + 127) / 128), 128, 0, st>>>(tree_cnt, f->dev.tree_leaf_off, f->dev.leaf_mu,
+                                                                             f->S, f->m, tree_row, f->dev.bs_slice_hdr,
+                                                                             f->dev.bs_base);
+    bs_fill_kernel<<<gt, 128, 0, st>>>(f->dev.nodes, f->dev.tree_off, f->dev.tree_leaf_off, f->dev.leaf_mu, f->dev.cut_off,
+                                       n_trees, f->m, tree_row, L, std::ldexp(1.0, f->bs_q), f->dev.bs_pool);
+    count_launch(3);
+    cudaFreeAsync(tree_cnt, st);
+    cudaFreeAsync(tree_row, st);
+    BI_CUDA(cudaGetLastError());
+    return BARTINT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// the evaluation kernel
+// ---------------------------------------------------------------------------------------------
+struct BsParams {
+    const unsigned char* pool;
+    const int4* slice_hdr;
+    BsLayout L;
+    const uint4* codes_pm;      // point-major packed codes (gather forests), or null
+    const uint8_t* codes;       // feature-major code rows
+    int64_t Npad, N;
+    const int32_t* cut_off;
+    int d, ncuts;
+    int draw_begin, draw_end;
+    int slice_begin, slice_end, chunk_slices;
+    double inv_scale;           // 2^-Q
+    double* draw_part;          // [n_tiles][draw_end - draw_begin]
+};
+
+__device__ __forceinline__ int popc4(const uint4& v) { return __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w); }
+
+template <int CH>
+__global__ void __launch_bounds__(BS_THREADS, 1) eval_bitslice_kernel(const BsParams prm) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int ROWB = CH * 16;           // bytes per predicate row
+    constexpr int WORDS = CH * 4;           // 32-point words per row
+    constexpr int TILE = CH * 128;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_rows = prm.ncuts + 1;
+    unsigned char* const s_mask = smem;                                             // [n_rows][ROWB]
+    uint32_t* const s_cnt = reinterpret_cast<uint32_t*>(smem + (size_t)n_rows * ROWB);   // [n_rows] popcount of a row
+    const int64_t tile_base = (int64_t)blockIdx.x * TILE;
+
+    // ---- 0. clear the table; the last row is the all-ones literal of unused ancestor slots ----
+    {
+        uint4* t4 = reinterpret_cast<uint4*>(s_mask);
+        const int n16 = prm.ncuts * CH;
+        for (int i = tid; i < n16; i += BS_THREADS) t4[i] = make_uint4(0u, 0u, 0u, 0u);
+        for (int i = tid; i < CH; i += BS_THREADS) t4[n16 + i] = make_uint4(~0u, ~0u, ~0u, ~0u);
+    }
+    __syncthreads();
+    // ---- 1. one-hot rows: row (v, c) word w gets the lanes of sub-tile w whose code of v equals c + 1 ----
+    for (int sub = warp; sub < WORDS; sub += BS_NWARP) {
+        const int64_t i = tile_base + (int64_t)sub * 32 + lane;
+        const bool in = i < prm.N;                    // padding rows count as code 0 (never right of any cut)
+        uint32_t* const col = reinterpret_cast<uint32_t*>(s_mask) + sub;
+        if (prm.codes_pm != nullptr) {
+            const uint4 v = in ? __ldg(&prm.codes_pm[i]) : make_uint4(0u, 0u, 0u, 0u);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                if (j < prm.d) {
+                    const uint32_t c = (w[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+                    const uint32_t mm = __match_any_sync(0xffffffffu, c);
+                    if (c != 0u && lane == __ffs((int)mm) - 1) col[(size_t)(__ldg(&prm.cut_off[j]) + (int)c - 1) * WORDS] = mm;
+                }
+            }
+        } else {
+            for (int j = 0; j < prm.d; ++j) {
+                const uint32_t c = in ? (uint32_t)__ldg(&prm.codes[(int64_t)j * prm.Npad + i]) : 0u;
+                const uint32_t mm = __match_any_sync(0xffffffffu, c);
+                if (c != 0u && lane == __ffs((int)mm) - 1) col[(size_t)(__ldg(&prm.cut_off[j]) + (int)c - 1) * WORDS] = mm;
+            }
+        }
+    }
+    __syncthreads();
+    // ---- 2. suffix OR down every variable's rows: M[v, c] = points with code > c; WORDS threads per variable ----
+    for (int v = tid / WORDS; v < prm.d; v += BS_THREADS / WORDS) {
+        const int w = tid % WORDS;
+        const int r0 = __ldg(&prm.cut_off[v]), r1 = __ldg(&prm.cut_off[v + 1]);
+        uint32_t* const col = reinterpret_cast<uint32_t*>(s_mask) + w;
+        uint32_t m = 0u;
+        for (int r = r1 - 1; r >= r0; --r) {
+            m |= col[(size_t)r * WORDS];
+            col[(size_t)r * WORDS] = m;
+        }
+    }
+    __syncthreads();
+    // chunk order of this lane: the 8 lanes of an LDS.128 phase read 8 different bank groups
+    uint32_t rot[CH];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) rot[c] = (uint32_t)((c ^ (lane & (CH - 1))) * 16);
+    // ---- 3. per-row popcounts over the tile (class A reads these instead of the masks) ----
+    for (int r = tid; r < n_rows; r += BS_THREADS) {
+        const unsigned char* row = s_mask + (size_t)r * ROWB;
+        int cnt = 0;
+#pragma unroll
+        for (int c = 0; c < CH; ++c) cnt += popc4(*reinterpret_cast<const uint4*>(row + rot[c]));
+        s_cnt[r] = (uint32_t)cnt;
+    }
+    __syncthreads();
+
+    // ---- 4. the slices of this CTA's draw chunk, one warp per slice, one lane per draw ----
+    const int ndraws = prm.draw_end - prm.draw_begin;
+    const int sl0 = prm.slice_begin + blockIdx.y * prm.chunk_slices;
+    const int sl1 = min(sl0 + prm.chunk_slices, prm.slice_end);
+    for (int sl = sl0 + warp; sl < sl1; sl += BS_NWARP) {
+        const int4 hdr = __ldg(&prm.slice_hdr[sl]);
+        const unsigned char* __restrict__ sp = prm.pool + (int64_t)sl * prm.L.slice_bytes;
+        unsigned long long acc0 = 0ull;      // sum of (low 32 bits of delta) * count
+        long long acc1 = 0ll;                // sum of (high 32 bits of delta, signed) * count
+        // class A
+        {
+            const uint4* __restrict__ rows = reinterpret_cast<const uint4*>(sp + prm.L.off_a) + lane;
+            uint4 e = hdr.x > 0 ? __ldg(rows) : make_uint4(0u, 0u, 0u, 0u);
+            for (int k = 0; k < hdr.x; ++k) {
+                const uint4 cur = e;
+                if (k + 1 < hdr.x) e = __ldg(rows + (size_t)(k + 1) * 32);
+                const uint32_t cnt = s_cnt[cur.z];
+                acc0 += (unsigned long long)cur.x * cnt;
+                acc1 += (long long)(int)cur.y * (long long)cnt;
+            }
+        }
+        // class B
+        {
+            const uint4* __restrict__ rows = reinterpret_cast<const uint4*>(sp + prm.L.off_b) + lane;
+            uint4 e = hdr.y > 0 ? __ldg(rows) : make_uint4(0u, 0u, 0u, 0u);
+            for (int k = 0; k < hdr.y; ++k) {
+                const uint4 cur = e;
+                if (k + 1 < hdr.y) e = __ldg(rows + (size_t)(k + 1) * 32);
+                const uint32_t pm = (uint32_t)((int)cur.z >> 31);
+                const unsigned char* ap = s_mask + (cur.z & 0x7FFFFFFFu);
+                const unsigned char* aj = s_mask + cur.w;
+                int cnt = 0;
+#pragma unroll
+                for (int c = 0; c < CH; ++c) {
+                    const uint4 mp = *reinterpret_cast<const uint4*>(ap + rot[c]);
+                    const uint4 mj = *reinterpret_cast<const uint4*>(aj + rot[c]);
+                    cnt += __popc((mp.x ^ pm) & mj.x) + __popc((mp.y ^ pm) & mj.y) + __popc((mp.z ^ pm) & mj.z) +
+                           __popc((mp.w ^ pm) & mj.w);
+                }
+                acc0 += (unsigned long long)cur.x * (uint32_t)cnt;
+                acc1 += (long long)(int)cur.y * (long long)cnt;
+            }
+        }
+        // class C
+        if (hdr.z > 0) {
+            const uint4* __restrict__ rows = reinterpret_cast<const uint4*>(sp + prm.L.off_c) + lane;
+            const uint32_t* __restrict__ anc = reinterpret_cast<const uint32_t*>(sp + prm.L.off_anc) + lane;
+            for (int k = 0; k < hdr.z; ++k) {
+                const uint4 cur = __ldg(rows + (size_t)k * 32);
+                uint4 r[CH];
+                const unsigned char* aj = s_mask + cur.z;
+#pragma unroll
+                for (int c = 0; c < CH; ++c) r[c] = *reinterpret_cast<const uint4*>(aj + rot[c]);
+                for (int a = 0; a < hdr.w; ++a) {
+                    const uint32_t w = __ldg(anc + ((size_t)a * prm.L.cap_c + k) * 32);
+                    const uint32_t pm = (uint32_t)((int)w >> 31);
+                    const unsigned char* ap = s_mask + (w & 0x7FFFFFFFu);
+#pragma unroll
+                    for (int c = 0; c < CH; ++c) {
+                        const uint4 mp = *reinterpret_cast<const uint4*>(ap + rot[c]);
+                        r[c].x &= mp.x ^ pm; r[c].y &= mp.y ^ pm; r[c].z &= mp.z ^ pm; r[c].w &= mp.w ^ pm;
+                    }
+                }
+                int cnt = 0;
+#pragma unroll
+                for (int c = 0; c < CH; ++c) cnt += popc4(r[c]);
+                acc0 += (unsigned long long)cur.x * (uint32_t)cnt;
+                acc1 += (long long)(int)cur.y * (long long)cnt;
+            }
+        }
+        const int s = sl * 32 + lane;
+        if (s >= prm.draw_begin && s < prm.draw_end)
+            prm.draw_part[(int64_t)blockIdx.x * ndraws + (s - prm.draw_begin)] =
+                ((double)acc1 * 4294967296.0 + (double)acc0) * prm.inv_scale;
+    }
+}
+
+size_t bs_smem_bytes(const bartint_forest* f) { return (size_t)(f->bs_ncuts + 1) * (size_t)(f->bs_ch * 16 + 4); }
+int bs_tile(const bartint_forest* f) { return f->bs_ch * 128; }
+int64_t bs_pool_bytes(const bartint_forest* f) { return f->bs_ok ? bs_layout_of(f).slice_bytes * ((f->S + 31) / 32) : 0; }
+
+typedef void (*bs_kernel_t)(const BsParams);
+static bs_kernel_t bs_kernel_for(int ch) {
+    return ch == 8 ? eval_bitslice_kernel<8> : ch == 4 ? eval_bitslice_kernel<4> : eval_bitslice_kernel<2>;
+}
+
+int launch_eval_bitslice(const bartint_forest* f, const bartint_points* p, const EvalPlan& plan, double* draw_part,
+                         cudaStream_t st) {
+    BI_REQUIRE(f->bs_ok && f->dev.bs_pool != nullptr, BARTINT_ERR_ARG, "internal: forest has no bit-sliced form");
+    BI_REQUIRE(plan.tile == bs_tile(f), BARTINT_ERR_ARG, "internal: plan/launch tile mismatch");
+    BsParams prm{};
+    prm.pool = f->dev.bs_pool;
+    prm.slice_hdr = f->dev.bs_slice_hdr;
+    prm.L = bs_layout_of(f);
+    prm.codes_pm = p->codes_pm;
+    prm.codes = p->codes;
+    prm.Npad = p->Npad;
+    prm.N = p->N;
+    prm.cut_off = f->dev.cut_off;
+    prm.d = f->d;
+    prm.ncuts = f->bs_ncuts;
+    prm.draw_begin = plan.draw_begin;
+    prm.draw_end = plan.draw_end;
+    prm.slice_begin = plan.draw_begin / 32;
+    prm.slice_end = (plan.draw_end + 31) / 32;
+    prm.chunk_slices = plan.chunk_draws;          // (in slices for this kernel)
+    prm.inv_scale = std::ldexp(1.0, -f->bs_q);
+    prm.draw_part = draw_part;
+    const size_t smem = bs_smem_bytes(f);
+    bs_kernel_t k = bs_kernel_for(f->bs_ch);
+    BI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)plan.n_tiles, (unsigned)plan.n_chunks);
+    k<<<grid, BS_THREADS, smem, st>>>(prm);
+    count_launch();
+    BI_CUDA(cudaGetLastError());
+    return BARTINT_OK;
+}
+
+// draw_sum[s] = sum over tiles of draw_part[tile][s]  +  N * base[s]   (tiles added in fixed order, 8 interleaved
+// partial sums like reduce_draw_parts_kernel; base = sum over the draw's trees of the leftmost leaf value)
+__global__ void __launch_bounds__(256) bs_reduce_kernel(const double* __restrict__ part, int n_tiles, int ndraws,
+                                                        const double* __restrict__ base, double n_points,
+                                                        double* __restrict__ out) {
+    __shared__ double s_part[8][33];
+    const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
+    const int s = blockIdx.x * 32 + x;
+    double acc = 0.0;
+    if (s < ndraws)
+        for (int t = y; t < n_tiles; t += 8) acc += part[(int64_t)t * ndraws + s];
+    s_part[y][x] = acc;
+    __syncthreads();
+    if (y == 0 && s < ndraws) {
+        double tot = s_part[0][x];
+#pragma unroll
+        for (int k = 1; k < 8; ++k) tot += s_part[k][x];
+        out[s] = tot + n_points * base[s];
+    }
+}
+
+int launch_bs_reduce(const bartint_forest* f, const double* draw_part, int n_tiles, int32_t draw_begin, int ndraws,
+                     int64_t N, double* draw_sum, cudaStream_t st) {
+    if (ndraws == 0) return BARTINT_OK;
+    bs_reduce_kernel<<<(ndraws + 31) / 32, 256, 0, st>>>(draw_part, n_tiles, ndraws, f->dev.bs_base + draw_begin, (double)N,
+                                                         draw_sum);
+    count_launch();
+    BI_CUDA(cudaGetLastError());
+    return BARTINT_OK;
+}
+
+}  // namespace bartint

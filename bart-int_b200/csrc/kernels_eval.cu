@@ -393,6 +393,21 @@ EvalPlan make_plan(const bartint_forest* f, const bartint_points* p, uint32_t fl
     pl.draw_begin = draw_begin;
     pl.draw_end = draw_end;
     const int ndraws = draw_end - draw_begin;
+    pl.use_bitslice = f->bs_ok && f->dev.bs_pool != nullptr && !want_moments && !want_full &&
+                      !(flags & (BARTINT_FORCE_WALK | BARTINT_NO_BITSLICE));
+    if (pl.use_bitslice) {
+        // CTA = one tile of points x a run of slices (32 draws each), one warp per slice.  Every CTA rebuilds the
+        // tile's mask table, so the draws are only split when there are too few tiles to occupy the SMs.
+        pl.tile = bs_tile(f);
+        pl.n_tiles = (int)std::max<int64_t>((p->N + pl.tile - 1) / pl.tile, 1);
+        int n_sm = 148;
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, f->device);
+        const int n_slices = (draw_end + 31) / 32 - draw_begin / 32;
+        int chunks = std::max(1, std::min(n_slices, (n_sm + pl.n_tiles - 1) / pl.n_tiles));
+        pl.chunk_draws = (n_slices + chunks - 1) / chunks;                       // slices per CTA
+        pl.n_chunks = (n_slices + pl.chunk_draws - 1) / pl.chunk_draws;
+        return pl;
+    }
     pl.use_table = f->table_ok && !(flags & BARTINT_FORCE_WALK);
     pl.use_gather = pl.use_table && f->gather && p->codes_pm != nullptr;
     pl.count_mode = pl.use_gather && f->count_mode && !want_moments && !want_full;

@@ -234,6 +234,11 @@ class Forest:
         self.table_kernel_ok = bool(tk)                                  # a fast kernel (table or gather) applies
         self.fast_kernel = {0: "none", 1: "table", 2: "gather"}[kind]
         self.route = int(_lib.load().bartint_forest_route(self._h))
+        bs = (C.c_int64 * 8)()
+        _check(_lib.load().bartint_forest_bitslice_info(self._h, bs))
+        # the bit-sliced sums-only kernel: applies, predicate rows, points per tile, longest draw, fixed-point exponent
+        self.bitslice_ok, self.bitslice_rows, self.bitslice_tile = bool(bs[0]), int(bs[1]), int(bs[2]) * 128
+        self.bitslice_info = [int(v) for v in bs]
         self.y_min = self.y_max = None
 
     # ---- constructors ----
@@ -359,7 +364,7 @@ class Forest:
 
     # ---- evaluation ----
     def eval(self, pts, weights=None, want=("draw_mean", "point_mean", "point_var"), scaled=False, draws=None,
-             force_walk=False) -> dict:
+             force_walk=False, no_bitslice=False) -> dict:
         """predict + colVars*weights + rowMeans (+ the full S x N matrix when asked), fused on the device.
 
         `pts` is either a Points handle (codes resident in HBM) or a host matrix (N x d): the latter goes through the
@@ -387,7 +392,8 @@ class Forest:
         w = None
         if weights is not None:
             w = np.ascontiguousarray(np.asarray(weights, np.float64).ravel())
-        flags = (_lib.BARTINT_SCALED_UNITS if scaled else 0) | (_lib.BARTINT_FORCE_WALK if force_walk else 0)
+        flags = ((_lib.BARTINT_SCALED_UNITS if scaled else 0) | (_lib.BARTINT_FORCE_WALK if force_walk else 0) |
+                 (_lib.BARTINT_NO_BITSLICE if no_bitslice else 0))
         outs = (_p(out.get("draw_mean"), C.c_double), _p(out.get("point_mean"), C.c_double),
                 _p(out.get("point_var"), C.c_double), _p(out.get("full_pred"), C.c_double))
         wargs = (_p(w, C.c_double), 0 if w is None else w.size)
@@ -405,11 +411,12 @@ class Forest:
                 pts.close()
 
     def eval_device(self, pts: Points, d_draw_sum: int = 0, d_point_mean: int = 0, d_point_m2: int = 0, draws=None,
-                    stream: int = 0, force_walk: bool = False) -> None:
+                    stream: int = 0, force_walk: bool = False, no_bitslice: bool = False) -> None:
         """Asynchronous evaluation writing raw scaled-unit partials to device addresses (0 = not wanted)."""
         lo, hi = (0, self.S) if draws is None else draws
+        flags = (_lib.BARTINT_FORCE_WALK if force_walk else 0) | (_lib.BARTINT_NO_BITSLICE if no_bitslice else 0)
         _check(_lib.load().bartint_eval_points_device(
-            self._h, pts._h, _lib.BARTINT_FORCE_WALK if force_walk else 0, lo, hi, C.c_void_p(d_draw_sum or None),
+            self._h, pts._h, flags, lo, hi, C.c_void_p(d_draw_sum or None),
             C.c_void_p(d_point_mean or None), C.c_void_p(d_point_m2 or None), C.c_void_p(stream)))
 
     def merge_moments_device(self, shard_draws, d_mean: int, d_m2: int, N: int, d_weights: int, weights_len: int,
@@ -438,7 +445,8 @@ class Forest:
         """Timing of the last evaluation of the given kind (per-draw sums only / with per-point outputs)."""
         ms, nl, tk = C.c_float(), C.c_int32(), C.c_int32()
         _check(_lib.load().bartint_last_eval_profile(self._h, int(with_moments), C.byref(ms), C.byref(nl), C.byref(tk)))
-        return {"kernel_ms": ms.value, "launches": nl.value, "table_kernel": bool(tk.value)}
+        return {"kernel_ms": ms.value, "launches": nl.value, "table_kernel": tk.value == 1,
+                "kernel": {0: "walk", 1: self.fast_kernel, 2: "bitslice"}.get(tk.value, "?")}
 
     def leaf_indices(self, pts, draws=None, use_table_kernel=False) -> np.ndarray:
         """Leaf ordinals, shape (ndraws*m, N), row t + (s - lo)*m."""

@@ -53,6 +53,7 @@ typedef enum {
 /* flags for bartint_eval* */
 #define BARTINT_SCALED_UNITS 0x1u  /* outputs stay in dbarts scaled units (no y rescale)            */
 #define BARTINT_FORCE_WALK   0x2u  /* use the generic node-walk kernel even if the table kernel fits */
+#define BARTINT_NO_BITSLICE  0x4u  /* per-draw sums through the per-point kernels, not the bit-sliced one (A/B timing) */
 
 int bartint_version(void);
 const char* bartint_last_error(void);
@@ -128,6 +129,11 @@ int bartint_forest_unpack(const void* host_header, int64_t host_bytes, const voi
  *               fast_kernel_ok (0/1), n_groups, table_bits, fast kernel kind (0 none, 1 table, 2 gather),
  *               gather code words per point */
 int bartint_forest_info(const bartint_forest* f, int64_t info[12]);
+/* The bit-sliced sums-only kernel (kernels_bitslice.cu; used by every evaluation that asks for per-draw sums only):
+ * info[0..7] = applies (0/1), predicate rows (= total number of cut points), 128-point chunks per tile, longest draw
+ *              (internal nodes), ancestor planes, fixed-point exponent Q of the leaf differences, bytes of the node
+ *              rows in HBM, shared memory per CTA */
+int bartint_forest_bitslice_info(const bartint_forest* f, int64_t info[8]);
 /* read the canonical (pre-order) flattening back; arrays sized from info[3] */
 int bartint_forest_export_soa(const bartint_forest* f, int64_t* tree_node_offset, int32_t* split_var,
                               int32_t* split_cut_idx, int32_t* left, int32_t* right, double* leaf_mu);
@@ -261,7 +267,8 @@ int bartint_finalize_integrals(const bartint_forest* f, const double* integrals_
 /* Timing of the last evaluation on this forest: milliseconds spent in the evaluation kernel (CUDA events on
  * the launching stream), kernels launched, and which kernel ran.  Two slots are kept: with_moments = 0 for the
  * last evaluation that produced per-draw sums only, 1 for the last one with per-point moments / full / leaf
- * output.  Blocks until that kernel has finished. */
+ * output.  Blocks until that kernel has finished.  *used_table_kernel: 0 node-walk kernel, 1 table / gather kernel,
+ * 2 bit-sliced kernel. */
 int bartint_last_eval_profile(const bartint_forest* f, int32_t with_moments, float* kernel_ms, int32_t* n_launches,
                               int32_t* used_table_kernel);
 

@@ -5,21 +5,20 @@ import numpy as np
 
 
 def kernel_kind_params():
-    """Kernel configurations every GPU parity test runs under: the register-gather kernel (default for d <= 16), the
-    shared-memory table kernel (BARTINT_KERNEL=table; the default for d > 16) and the gather kernel in counting mode
-    (BARTINT_COUNT_SPLITS=1: per-draw sums of the single-split trees from 1-D code histograms).  Level 2 of the
-    counting mode (two-split trees from 2-D histograms) was merged after the round's GPU budget was spent: its
-    planner is covered on CPU (test_planner_cpu.py), its kernels join the GPU matrix with BARTINT_TEST_COUNT2=1."""
-    kinds = ["gather", "table", "gather+count1"]
-    if os.environ.get("BARTINT_TEST_COUNT2") == "1":
-        kinds.append("gather+count2")
-    return kinds
+    """Kernel configurations every GPU parity test runs under.  Per-point outputs (moments, the full matrix, leaf
+    ordinals) come from the register-gather kernel (default for d <= 16) or the shared-memory table kernel
+    (BARTINT_KERNEL=table; the default for d > 16); evaluations that want per-draw sums only go through the bit-sliced
+    kernel unless it is switched off ("+nobs": BARTINT_BITSLICE=0, sums from the per-point kernels).  The counting
+    modes of the gather kernel (BARTINT_COUNT_SPLITS=1 / 2: per-draw sums of the one- and two-split trees from 1-D /
+    2-D cumulative code histograms) only exist without the bit-sliced kernel."""
+    return ["gather", "table", "gather+nobs", "table+nobs", "gather+count1", "gather+count2"]
 
 
 def apply_kernel_kind(param, monkeypatch):
-    kind, _, count = param.partition("+")
+    kind, _, opt = param.partition("+")
     monkeypatch.setenv("BARTINT_KERNEL", kind)
-    monkeypatch.setenv("BARTINT_COUNT_SPLITS", count[-1] if count else "0")
+    monkeypatch.setenv("BARTINT_COUNT_SPLITS", opt[-1] if opt.startswith("count") else "0")
+    monkeypatch.setenv("BARTINT_BITSLICE", "0" if opt else "1")
     return kind
 
 
