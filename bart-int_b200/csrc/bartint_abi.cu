@@ -41,7 +41,7 @@ struct DeviceGuard {
 };
 
 static void free_device(DeviceForest& d, unsigned char* image_base = nullptr) {
-    for (void* q : {(void*)d.bs_pool, (void*)d.bs_slice_hdr, (void*)d.bs_base})     // never part of an image
+    for (void* q : {(void*)d.bs_pool, (void*)d.bs_slice_hdr, (void*)d.bs_base, (void*)d.bs_slot_draw})     // never part of an image
         if (q) cudaFreeAsync(q, nullptr);
     if (image_base != nullptr) {           // an unpacked forest: one allocation holds every other array
         cudaFreeAsync(image_base, nullptr);

@@ -103,7 +103,8 @@ struct DeviceForest {
     uint8_t* group_rec = nullptr;      // n_groups * tk_rec_bytes(nb)
     // bit-sliced form (kernels_bitslice.cu), built on the device from the walk form; never part of a forest image
     unsigned char* bs_pool = nullptr;  // ELL rows of the internal nodes, one block per slice of 32 draws
-    int4* bs_slice_hdr = nullptr;      // per slice: rows of class A, B, C and the deepest C node
+    int4* bs_slice_hdr = nullptr;      // per slice, two words: rows of class A, B, C2, C3 | rows of D, deepest D node
+    int32_t* bs_slot_draw = nullptr;   // slot (slice * 32 + lane) -> draw, -1 = empty (draws are sorted by row counts)
     double* bs_base = nullptr;         // S: sum over the draw's trees of the leftmost leaf value
 };
 

@@ -19,11 +19,13 @@
 //
 // Work layout ("lanes are draws"): the nodes of 32 consecutive draws (a SLICE) are stored as ELL rows -- row k holds
 // the k-th node of each of the 32 draws, 16 bytes per lane -- so a warp reads a row with one coalesced LDG.128, every
-// lane accumulates the sum of ITS draw in registers, and no cross-lane reduction or atomics are needed.  Three node
-// classes per slice, each padded to the slice's longest draw with delta = 0 entries:
+// lane accumulates the sum of ITS draw in registers, and no cross-lane reduction or atomics are needed.  Node classes
+// by depth, each padded to the slice's longest draw with delta = 0 entries (draws are assigned to slices in the order
+// of their row counts, so the padding is small):
 //     A  root nodes            popc(M[v,c]) over the tile comes from a per-tile count table P[v,c]   (1 LDS.32)
 //     B  children of the root  popc((M[parent] ^ pol) & M[own])                                   (2 x CH LDS.128)
-//     C  depth >= 2            own mask ANDed with every ancestor literal (ancestor planes, u32 per entry)
+//     C2, C3  depth 2 and 3    own mask ANDed with 2 / 3 ancestor literals, all references packed in the entry
+//     D  depth >= 4            ancestor references in separate planes (rare)
 // Shared-memory rows are CH x 16 bytes (CH x 128 points); lane q reads the chunks in the order c ^ (q & 7), so the
 // eight lanes of an LDS.128 phase always hit eight different 16-byte bank groups whatever rows they address.
 #include <algorithm>
@@ -38,39 +40,59 @@ namespace bartint {
 constexpr int BS_THREADS = 512;                 // 16 warps, one CTA per SM (the mask table fills shared memory)
 constexpr int BS_NWARP = BS_THREADS / 32;
 constexpr size_t BS_SMEM_MAX = 227 * 1024;
+constexpr int BS_SORT_MAX = 16384;              // draws are ordered by cost (rank sort, O(S^2)) up to this many
 
 // ---------------------------------------------------------------------------------------------
 // device builder: walk form -> ELL rows (run once per forest, right after the upload)
 // ---------------------------------------------------------------------------------------------
+// Node classes by depth.  A, B, C2, C3 entries are 16 bytes: {delta lo, delta hi, refs, refs}; D entries (depth >= 4,
+// rare) keep their ancestors in separate planes of one u32 per entry.
+//   A   z = predicate row
+//   B   z = parent byte offset | negated << 31,  w = own byte offset
+//   C2/C3  z = own | anc0 << 14 | neg0 << 28 | neg1 << 29 | neg2 << 30,  w = anc1 | anc2 << 14   (offsets in 16-byte units)
+//   D   z = own byte offset, w = depth;  plane a: ancestor a's byte offset | negated << 31 (all-ones row beyond depth)
+enum { BS_A = 0, BS_B = 1, BS_C2 = 2, BS_C3 = 3, BS_D = 4, BS_NCLS = 5 };
+
 struct BsLayout {
     int64_t slice_bytes;
-    int32_t off_a, off_b, off_c, off_anc;      // byte offsets of the class blocks inside a slice
-    int32_t cap_c;                              // rows of the C block (stride of an ancestor plane)
+    int32_t off[BS_NCLS];                       // byte offsets of the class blocks inside a slice
+    int32_t off_anc;                            // ancestor planes of class D
+    int32_t cap_d;                              // rows of the D block (stride of an ancestor plane)
     int32_t anc_planes;
     int32_t row_bytes;                          // CH * 16
     int32_t ones_off;                           // byte offset of the all-ones mask row (row index n_cuts)
 };
 
+static inline int ru(int x, int q) { return (std::max(x, 1) + q - 1) / q * q; }
+
 static BsLayout bs_layout_of(const bartint_forest* f) {
     BsLayout L{};
-    const int cap_a = std::max(f->m, 1), cap_b = std::max(std::min(2 * f->m, f->bs_rows), 1), cap_c = std::max(f->bs_rows, 1);
+    const int m = f->m, R = f->bs_rows;
+    // row capacities: a draw has at most min(2^k m, R) nodes at depth k; rounded up to the prefetch group of the class
+    const int cap[BS_NCLS] = {ru(m, 8), ru(std::min(2 * m, R), 4), ru(std::min(4 * m, R), 4), ru(std::min(8 * m, R), 4),
+                              f->max_depth > 4 ? ru(R, 2) : 2};
+    int o = 0;
+    for (int c = 0; c < BS_NCLS; ++c) { L.off[c] = o; o += 512 * cap[c]; }
+    L.off_anc = o;
+    L.cap_d = cap[BS_D];
     L.anc_planes = f->bs_anc;
-    L.cap_c = cap_c;
-    L.off_a = 0;
-    L.off_b = L.off_a + 512 * cap_a;
-    L.off_c = L.off_b + 512 * cap_b;
-    L.off_anc = L.off_c + 512 * cap_c;
-    L.slice_bytes = (int64_t)L.off_anc + 128ll * L.anc_planes * cap_c;
+    L.slice_bytes = (int64_t)o + 128ll * L.anc_planes * L.cap_d;
     L.row_bytes = f->bs_ch * 16;
     L.ones_off = f->bs_ncuts * L.row_bytes;
     return L;
 }
 
-// one pass over a tree in pre-order; calls emit(depth, node index a, leaves seen before a, path) for every internal node
+struct BsCnt { unsigned short n[BS_NCLS], dmax, pad0, pad1; };     // 16 bytes
+static_assert(sizeof(BsCnt) == 16, "BsCnt is stored as one 16-byte word");
+
+__device__ __forceinline__ int bs_class_of(int depth) { return depth < 4 ? depth : BS_D; }
+
+// one pass over a tree in pre-order; calls emit(depth, leaves seen before the node, right-child offset, predicate
+// row, path) for every internal node.  path[k] = byte offset of the depth-k ancestor's row | negated << 31.
 template <typename Emit>
 __device__ __forceinline__ void bs_walk_tree(const uint2* __restrict__ nd, int cnt, const int32_t* __restrict__ cut_off,
                                              int row_bytes, Emit emit) {
-    uint32_t path[64];      // per depth: byte offset of the ancestor's mask row | negated << 31
+    uint32_t path[64];
     int pend[64];           // depths of the ancestors whose right subtree is still to come
     int np = 0, depth = 0, leaves = 0;
     for (int a = 0; a < cnt; ++a) {
@@ -78,7 +100,7 @@ __device__ __forceinline__ void bs_walk_tree(const uint2* __restrict__ nd, int c
         const uint32_t var = r.x & 0xFFFFu;
         if (var != LEAF_VAR) {
             const uint32_t vc = (uint32_t)cut_off[var] + (r.x >> 16);
-            emit(depth, a, leaves, r.y, vc, path);
+            emit(depth, leaves, r.y, vc, path);
             if (depth < 64) {
                 path[depth] = (vc * (uint32_t)row_bytes) | 0x80000000u;     // the left subtree comes next: literal negated
                 pend[np++] = depth;
@@ -95,94 +117,159 @@ __device__ __forceinline__ void bs_walk_tree(const uint2* __restrict__ nd, int c
     }
 }
 
-// counts per tree: x = root nodes (0/1), y = depth-1 nodes, z = deeper nodes, w = largest depth of a C node
 __global__ void __launch_bounds__(128) bs_count_kernel(const uint2* __restrict__ nodes, const int32_t* __restrict__ tree_off,
                                                        const int32_t* __restrict__ cut_off, int64_t n_trees,
-                                                       ushort4* __restrict__ tree_cnt) {
+                                                       BsCnt* __restrict__ tree_cnt) {
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n_trees) return;
-    int ca = 0, cb = 0, cc = 0, dmax = 0;
+    int n[BS_NCLS] = {0, 0, 0, 0, 0}, dmax = 0;
     bs_walk_tree(nodes + tree_off[k], tree_off[k + 1] - tree_off[k], cut_off, 16,
-                 [&](int depth, int, int, uint32_t, uint32_t, const uint32_t*) {
-                     if (depth == 0) ++ca;
-                     else if (depth == 1) ++cb;
-                     else { ++cc; dmax = max(dmax, depth); }
+                 [&](int depth, int, uint32_t, uint32_t, const uint32_t*) {
+                     const int c = bs_class_of(depth);
+#pragma unroll
+                     for (int q = 0; q < BS_NCLS; ++q) n[q] += (q == c);
+                     if (c == BS_D) dmax = max(dmax, depth);
                  });
-    tree_cnt[k] = make_ushort4((unsigned short)ca, (unsigned short)cb, (unsigned short)cc, (unsigned short)dmax);
+    BsCnt out{};
+#pragma unroll
+    for (int q = 0; q < BS_NCLS; ++q) out.n[q] = (unsigned short)n[q];
+    out.dmax = (unsigned short)dmax;
+    tree_cnt[k] = out;
 }
 
-// one warp per slice, one lane per draw: first rows of every tree inside its draw's column, the slice's row counts
-// (the longest draw), and base[s] = sum_t L(root_t)
-__global__ void __launch_bounds__(128) bs_layout_kernel(const ushort4* __restrict__ tree_cnt, const int32_t* __restrict__ tree_leaf_off,
-                                                        const double* __restrict__ leaf_mu, int S, int m,
-                                                        ushort4* __restrict__ tree_row, int4* __restrict__ slice_hdr,
-                                                        double* __restrict__ base) {
-    const int sl = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
-    if (sl * 32 >= S) return;
-    const int s = sl * 32 + lane;
-    int ra = 0, rb = 0, rc = 0, dmax = 0;
+// one thread per draw: first row of every tree inside its draw's column (per class), the draw's totals, its sort
+// key (draws with similar row counts share a slice, so little of a slice is padding) and base[s] = sum_t L(root_t)
+__global__ void __launch_bounds__(128) bs_draw_kernel(const BsCnt* __restrict__ tree_cnt, const int32_t* __restrict__ tree_leaf_off,
+                                                      const double* __restrict__ leaf_mu, int S, int m,
+                                                      BsCnt* __restrict__ tree_row, BsCnt* __restrict__ draw_tot,
+                                                      unsigned long long* __restrict__ key, double* __restrict__ base) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    int r[BS_NCLS] = {0, 0, 0, 0, 0}, dmax = 0;
     double b = 0.0;
-    if (s < S) {
-        for (int t = 0; t < m; ++t) {
-            const int64_t k = (int64_t)s * m + t;
-            const ushort4 c = tree_cnt[k];
-            tree_row[k] = make_ushort4((unsigned short)ra, (unsigned short)rb, (unsigned short)rc, 0);
-            ra += c.x; rb += c.y; rc += c.z;
-            dmax = max(dmax, (int)c.w);
-            b += leaf_mu[tree_leaf_off[k]];                 // leaf ordinal 0 = the leftmost leaf
+    for (int t = 0; t < m; ++t) {
+        const int64_t k = (int64_t)s * m + t;
+        const BsCnt c = tree_cnt[k];
+        BsCnt row{};
+#pragma unroll
+        for (int q = 0; q < BS_NCLS; ++q) { row.n[q] = (unsigned short)r[q]; r[q] += c.n[q]; }
+        tree_row[k] = row;
+        dmax = max(dmax, (int)c.dmax);
+        b += leaf_mu[tree_leaf_off[k]];                 // leaf ordinal 0 = the leftmost leaf
+    }
+    BsCnt tot{};
+#pragma unroll
+    for (int q = 0; q < BS_NCLS; ++q) tot.n[q] = (unsigned short)r[q];
+    tot.dmax = (unsigned short)dmax;
+    draw_tot[s] = tot;
+    base[s] = b;
+    // the mask loads a draw costs (B 2, C2 3, C3 4, D ~6 per node); ties broken by the parts, then by the draw index
+    const unsigned long long cost = 2ull * r[BS_B] + 3ull * r[BS_C2] + 4ull * r[BS_C3] + 6ull * r[BS_D];
+    key[s] = (cost << 40) | ((unsigned long long)min(r[BS_B], 4095) << 28) | ((unsigned long long)min(r[BS_C2], 4095) << 16) |
+             (unsigned long long)(s & 0xFFFF);
+}
+
+// rank of every draw by key: its slot (slice = slot / 32, lane = slot % 32).  sorted == 0: identity.
+__global__ void __launch_bounds__(256) bs_rank_kernel(const unsigned long long* __restrict__ key, int S, int sorted,
+                                                      int32_t* __restrict__ draw_slot, int32_t* __restrict__ slot_draw) {
+    __shared__ unsigned long long s_key[256];
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long mine = s < S ? key[s] : 0ull;
+    int rank = s;
+    if (sorted) {
+        rank = 0;
+        for (int j0 = 0; j0 < S; j0 += 256) {
+            __syncthreads();
+            s_key[threadIdx.x] = j0 + (int)threadIdx.x < S ? key[j0 + threadIdx.x] : ~0ull;
+            __syncthreads();
+            const int nj = min(256, S - j0);
+            for (int j = 0; j < nj; ++j) {
+                const unsigned long long o = s_key[j];
+                rank += (o < mine) || (o == mine && j0 + j < s);
+            }
         }
-        base[s] = b;
+    }
+    if (s < S) { draw_slot[s] = rank; slot_draw[rank] = s; }
+}
+
+// one warp per slice: the slice's row counts = the longest of its 32 draws
+__global__ void __launch_bounds__(128) bs_hdr_kernel(const BsCnt* __restrict__ draw_tot, const int32_t* __restrict__ slot_draw,
+                                                     int n_slices, int4* __restrict__ slice_hdr) {
+    const int sl = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (sl >= n_slices) return;
+    const int s = slot_draw[sl * 32 + lane];
+    int v[BS_NCLS + 1] = {0, 0, 0, 0, 0, 0};
+    if (s >= 0) {
+        const BsCnt t = draw_tot[s];
+#pragma unroll
+        for (int q = 0; q < BS_NCLS; ++q) v[q] = t.n[q];
+        v[BS_NCLS] = t.dmax;
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        ra = max(ra, __shfl_xor_sync(0xffffffffu, ra, o));
-        rb = max(rb, __shfl_xor_sync(0xffffffffu, rb, o));
-        rc = max(rc, __shfl_xor_sync(0xffffffffu, rc, o));
-        dmax = max(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+    for (int q = 0; q <= BS_NCLS; ++q)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[q] = max(v[q], __shfl_xor_sync(0xffffffffu, v[q], o));
+    if (lane == 0) {
+        slice_hdr[2 * sl] = make_int4(v[0], v[1], v[2], v[3]);
+        slice_hdr[2 * sl + 1] = make_int4(v[4], v[5], 0, 0);
     }
-    if (lane == 0) slice_hdr[sl] = make_int4(ra, rb, rc, dmax);
 }
 
 __global__ void __launch_bounds__(128) bs_fill_kernel(const uint2* __restrict__ nodes, const int32_t* __restrict__ tree_off,
                                                       const int32_t* __restrict__ tree_leaf_off, const double* __restrict__ leaf_mu,
                                                       const int32_t* __restrict__ cut_off, int64_t n_trees, int m,
-                                                      const ushort4* __restrict__ tree_row, BsLayout L, double fx_scale,
-                                                      unsigned char* __restrict__ pool) {
+                                                      const BsCnt* __restrict__ tree_row, const int32_t* __restrict__ draw_slot,
+                                                      BsLayout L, double fx_scale, unsigned char* __restrict__ pool) {
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n_trees) return;
-    const int s = (int)(k / m), lane = s & 31;
-    unsigned char* __restrict__ sp = pool + (int64_t)(s >> 5) * L.slice_bytes;
-    const ushort4 r0 = tree_row[k];
-    int ra = r0.x, rb = r0.y, rc = r0.z;
+    const int slot = draw_slot[k / m], lane = slot & 31;
+    unsigned char* __restrict__ sp = pool + (int64_t)(slot >> 5) * L.slice_bytes;
+    const BsCnt r0 = tree_row[k];
+    int row[BS_NCLS];
+#pragma unroll
+    for (int q = 0; q < BS_NCLS; ++q) row[q] = r0.n[q];
     const double* __restrict__ mu = leaf_mu + tree_leaf_off[k];
+    const uint32_t rb = (uint32_t)L.row_bytes;
     bs_walk_tree(nodes + tree_off[k], tree_off[k + 1] - tree_off[k], cut_off, L.row_bytes,
-                 [&](int depth, int, int leaves, uint32_t roff, uint32_t vc, const uint32_t* path) {
-                     // leaves before the right child = leaves before a + leaves of the left subtree (roff - 1 nodes)
+                 [&](int depth, int leaves, uint32_t roff, uint32_t vc, const uint32_t* path) {
+                     // leaves before the right child = leaves before the node + leaves of its left subtree (roff - 1 nodes)
                      const double delta = mu[leaves + (int)(roff >> 1)] - mu[leaves];
                      const long long fx = __double2ll_rn(delta * fx_scale);
                      const uint32_t lo = (uint32_t)(unsigned long long)fx, hi = (uint32_t)((unsigned long long)fx >> 32);
-                     if (depth == 0) {
-                         reinterpret_cast<uint4*>(sp + L.off_a)[ra * 32 + lane] = make_uint4(lo, hi, vc, 0u);
-                         ++ra;
-                     } else if (depth == 1) {
-                         reinterpret_cast<uint4*>(sp + L.off_b)[rb * 32 + lane] =
-                             make_uint4(lo, hi, path[0], vc * (uint32_t)L.row_bytes);
-                         ++rb;
+                     const int c = bs_class_of(depth);
+                     uint4 e = make_uint4(lo, hi, 0u, 0u);
+                     if (c == BS_A) {
+                         e.z = vc;
+                     } else if (c == BS_B) {
+                         e.z = path[0];
+                         e.w = vc * rb;
+                     } else if (c == BS_C2 || c == BS_C3) {
+                         const uint32_t u = rb >> 4;                        // 16-byte units per row
+                         e.z = vc * u | ((path[0] & 0x7FFFFFFFu) >> 4) << 14 | (path[0] >> 31) << 28 | (path[1] >> 31) << 29;
+                         e.w = (path[1] & 0x7FFFFFFFu) >> 4;
+                         if (c == BS_C3) {
+                             e.z |= (path[2] >> 31) << 30;
+                             e.w |= ((path[2] & 0x7FFFFFFFu) >> 4) << 14;
+                         }
                      } else {
-                         reinterpret_cast<uint4*>(sp + L.off_c)[rc * 32 + lane] =
-                             make_uint4(lo, hi, vc * (uint32_t)L.row_bytes, (uint32_t)depth);
+                         e.z = vc * rb;
+                         e.w = (uint32_t)depth;
                          uint32_t* __restrict__ anc = reinterpret_cast<uint32_t*>(sp + L.off_anc);
                          for (int a = 0; a < L.anc_planes; ++a)
-                             anc[((int64_t)a * L.cap_c + rc) * 32 + lane] = a < depth ? path[a] : (uint32_t)L.ones_off;
-                         ++rc;
+                             anc[((int64_t)a * L.cap_d + row[BS_D]) * 32 + lane] = a < depth ? path[a] : (uint32_t)L.ones_off;
                      }
+                     int rr = 0;
+#pragma unroll
+                     for (int q = 0; q < BS_NCLS; ++q)
+                         if (q == c) { rr = row[q]; row[q] = rr + 1; }
+                     reinterpret_cast<uint4*>(sp + L.off[c])[rr * 32 + lane] = e;
                  });
 }
 
 // Decides whether the bit-sliced kernel applies to the forest and sizes its tables (host; no CUDA call).
 //   bs_ncuts  total number of cut points = number of predicate rows
 //   bs_ch     128-point chunks per tile: the largest of 8 / 4 / 2 whose mask table fits shared memory
-//   bs_rows   longest draw (internal nodes), bs_anc = ancestor planes = deepest internal node
+//   bs_rows   longest draw (internal nodes), bs_anc = ancestor planes of class D = deepest internal node
 void bs_configure(bartint_forest* f) {
     f->bs_ok = false;
     const char* e = getenv("BARTINT_BITSLICE");
@@ -190,15 +277,15 @@ void bs_configure(bartint_forest* f) {
     if (f->S < 1 || f->m < 1 || f->d < 1) return;
     const int64_t ncuts = f->cut_off[(size_t)f->d];
     if (ncuts < 1 || f->max_depth < 1 || f->max_depth > 33) return;     // (no split anywhere: nothing to slice)
-    if (f->draw_internal_max < 1 || f->draw_internal_max >= 65535 || f->m >= 65535) return;
+    if (f->draw_internal_max < 1 || f->draw_internal_max >= 65535 || f->m >= 8000) return;
     int ch = 0;
     for (int c : {8, 4, 2})
         if ((size_t)(ncuts + 1) * (size_t)(c * 16 + 4) + 64 <= BS_SMEM_MAX) { ch = c; break; }
-    if (ch == 0 || (ncuts + 1) * (int64_t)ch * 16 >= (int64_t)1 << 31) return;
+    if (ch == 0 || (ncuts + 1) * (int64_t)ch >= 1 << 14) return;         // row offsets are 14-bit counts of 16 bytes
     f->bs_ncuts = (int32_t)ncuts;
     f->bs_ch = ch;
     f->bs_rows = f->draw_internal_max;
-    f->bs_anc = std::max(2, f->max_depth - 1);
+    f->bs_anc = std::max(4, f->max_depth - 1);
     // fixed point: |delta| <= 2 max|mu| < 2^(e+1)  ->  |delta * 2^Q| < 2^61 with Q = 60 - e
     const double dmax = 2.0 * f->max_abs_mu;
     int ex = 0;
@@ -215,23 +302,32 @@ int launch_build_bitslice(bartint_forest* f, cudaStream_t st) {
     const int64_t n_trees = (int64_t)f->S * f->m;
     const int n_slices = (f->S + 31) / 32;
     const size_t pool_bytes = (size_t)L.slice_bytes * (size_t)n_slices;
-    ushort4 *tree_cnt = nullptr, *tree_row = nullptr;
+    BsCnt *tree_cnt = nullptr, *tree_row = nullptr, *draw_tot = nullptr;
+    unsigned long long* key = nullptr;
+    int32_t* draw_slot = nullptr;
     BI_CUDA(cudaMallocAsync((void**)&f->dev.bs_pool, pool_bytes, st));
-    BI_CUDA(cudaMallocAsync((void**)&f->dev.bs_slice_hdr, sizeof(int4) * (size_t)n_slices, st));
+    BI_CUDA(cudaMallocAsync((void**)&f->dev.bs_slice_hdr, 2 * sizeof(int4) * (size_t)n_slices, st));
     BI_CUDA(cudaMallocAsync((void**)&f->dev.bs_base, sizeof(double) * (size_t)f->S, st));
-    BI_CUDA(cudaMallocAsync((void**)&tree_cnt, sizeof(ushort4) * (size_t)n_trees, st));
-    BI_CUDA(cudaMallocAsync((void**)&tree_row, sizeof(ushort4) * (size_t)n_trees, st));
+    BI_CUDA(cudaMallocAsync((void**)&f->dev.bs_slot_draw, sizeof(int32_t) * 32 * (size_t)n_slices, st));
+    BI_CUDA(cudaMallocAsync((void**)&tree_cnt, sizeof(BsCnt) * (size_t)n_trees, st));
+    BI_CUDA(cudaMallocAsync((void**)&tree_row, sizeof(BsCnt) * (size_t)n_trees, st));
+    BI_CUDA(cudaMallocAsync((void**)&draw_tot, sizeof(BsCnt) * (size_t)f->S, st));
+    BI_CUDA(cudaMallocAsync((void**)&key, sizeof(unsigned long long) * (size_t)f->S, st));
+    BI_CUDA(cudaMallocAsync((void**)&draw_slot, sizeof(int32_t) * (size_t)f->S, st));
     BI_CUDA(cudaMemsetAsync(f->dev.bs_pool, 0, pool_bytes, st));
+    BI_CUDA(cudaMemsetAsync(f->dev.bs_slot_draw, 0xFF, sizeof(int32_t) * 32 * (size_t)n_slices, st));   // -1: empty slot
     const unsigned gt = (unsigned)((n_trees + 127) / 128);
     bs_count_kernel<<<gt, 128, 0, st>>>(f->dev.nodes, f->dev.tree_off, f->dev.cut_off, n_trees, tree_cnt);
-    bs_layout_kernel<<<(unsigned)((n_slices * 32 + 127) / 128), 128, 0, st>>>(tree_cnt, f->dev.tree_leaf_off, f->dev.leaf_mu,
-                                                                             f->S, f->m, tree_row, f->dev.bs_slice_hdr,
-                                                                             f->dev.bs_base);
+    bs_draw_kernel<<<(unsigned)((f->S + 127) / 128), 128, 0, st>>>(tree_cnt, f->dev.tree_leaf_off, f->dev.leaf_mu, f->S, f->m,
+                                                                  tree_row, draw_tot, key, f->dev.bs_base);
+    bs_rank_kernel<<<(unsigned)((f->S + 255) / 256), 256, 0, st>>>(key, f->S, f->S <= BS_SORT_MAX ? 1 : 0, draw_slot,
+                                                                  f->dev.bs_slot_draw);
+    bs_hdr_kernel<<<(unsigned)((n_slices * 32 + 127) / 128), 128, 0, st>>>(draw_tot, f->dev.bs_slot_draw, n_slices,
+                                                                          f->dev.bs_slice_hdr);
     bs_fill_kernel<<<gt, 128, 0, st>>>(f->dev.nodes, f->dev.tree_off, f->dev.tree_leaf_off, f->dev.leaf_mu, f->dev.cut_off,
-                                       n_trees, f->m, tree_row, L, std::ldexp(1.0, f->bs_q), f->dev.bs_pool);
-    count_launch(3);
-    cudaFreeAsync(tree_cnt, st);
-    cudaFreeAsync(tree_row, st);
+                                       n_trees, f->m, tree_row, draw_slot, L, std::ldexp(1.0, f->bs_q), f->dev.bs_pool);
+    count_launch(5);
+    for (void* q : {(void*)tree_cnt, (void*)tree_row, (void*)draw_tot, (void*)key, (void*)draw_slot}) cudaFreeAsync(q, st);
     BI_CUDA(cudaGetLastError());
     return BARTINT_OK;
 }
@@ -242,6 +338,7 @@ int launch_build_bitslice(bartint_forest* f, cudaStream_t st) {
 struct BsParams {
     const unsigned char* pool;
     const int4* slice_hdr;
+    const int32_t* slot_draw;
     BsLayout L;
     const uint4* codes_pm;      // point-major packed codes (gather forests), or null
     const uint8_t* codes;       // feature-major code rows
@@ -249,12 +346,36 @@ struct BsParams {
     const int32_t* cut_off;
     int d, ncuts;
     int draw_begin, draw_end;
-    int slice_begin, slice_end, chunk_slices;
+    int n_slices, chunk_slices;
     double inv_scale;           // 2^-Q
     double* draw_part;          // [n_tiles][draw_end - draw_begin]
 };
 
 __device__ __forceinline__ int popc4(const uint4& v) { return __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w); }
+__device__ __forceinline__ uint4 lds16(const unsigned char* p) { return *reinterpret_cast<const uint4*>(p); }
+
+// Rows [0, n) of one class, G at a time: the loads of the next group are in flight while this one is processed (the
+// row blocks are padded to a multiple of G with zero entries, so a group may always be loaded whole).
+template <int G, typename F>
+__device__ __forceinline__ void bs_rows(const uint4* __restrict__ rows, int n, F body) {
+    uint4 nxt[G];
+    if (n > 0) {
+#pragma unroll
+        for (int j = 0; j < G; ++j) nxt[j] = __ldg(rows + (size_t)j * 32);
+    }
+    for (int k0 = 0; k0 < n; k0 += G) {
+        uint4 cur[G];
+#pragma unroll
+        for (int j = 0; j < G; ++j) cur[j] = nxt[j];
+        if (k0 + G < n) {
+#pragma unroll
+            for (int j = 0; j < G; ++j) nxt[j] = __ldg(rows + (size_t)(k0 + G + j) * 32);
+        }
+#pragma unroll
+        for (int j = 0; j < G; ++j)
+            if (k0 + j < n) body(cur[j]);
+    }
+}
 
 template <int CH>
 __global__ void __launch_bounds__(BS_THREADS, 1) eval_bitslice_kernel(const BsParams prm) {
@@ -322,83 +443,98 @@ __global__ void __launch_bounds__(BS_THREADS, 1) eval_bitslice_kernel(const BsPa
         const unsigned char* row = s_mask + (size_t)r * ROWB;
         int cnt = 0;
 #pragma unroll
-        for (int c = 0; c < CH; ++c) cnt += popc4(*reinterpret_cast<const uint4*>(row + rot[c]));
+        for (int c = 0; c < CH; ++c) cnt += popc4(lds16(row + rot[c]));
         s_cnt[r] = (uint32_t)cnt;
     }
     __syncthreads();
 
-    // ---- 4. the slices of this CTA's draw chunk, one warp per slice, one lane per draw ----
+    // ---- 4. the slices of this CTA's chunk, one warp per slice, one lane per draw ----
     const int ndraws = prm.draw_end - prm.draw_begin;
-    const int sl0 = prm.slice_begin + blockIdx.y * prm.chunk_slices;
-    const int sl1 = min(sl0 + prm.chunk_slices, prm.slice_end);
+    const int sl0 = blockIdx.y * prm.chunk_slices;
+    const int sl1 = min(sl0 + prm.chunk_slices, prm.n_slices);
     for (int sl = sl0 + warp; sl < sl1; sl += BS_NWARP) {
-        const int4 hdr = __ldg(&prm.slice_hdr[sl]);
+        const int s = __ldg(&prm.slot_draw[sl * 32 + lane]);
+        const bool wanted = s >= prm.draw_begin && s < prm.draw_end;
+        if (!__any_sync(0xffffffffu, wanted)) continue;
+        const int4 h0 = __ldg(&prm.slice_hdr[2 * sl]), h1 = __ldg(&prm.slice_hdr[2 * sl + 1]);
         const unsigned char* __restrict__ sp = prm.pool + (int64_t)sl * prm.L.slice_bytes;
         unsigned long long acc0 = 0ull;      // sum of (low 32 bits of delta) * count
         long long acc1 = 0ll;                // sum of (high 32 bits of delta, signed) * count
-        // class A
-        {
-            const uint4* __restrict__ rows = reinterpret_cast<const uint4*>(sp + prm.L.off_a) + lane;
-            uint4 e = hdr.x > 0 ? __ldg(rows) : make_uint4(0u, 0u, 0u, 0u);
-            for (int k = 0; k < hdr.x; ++k) {
-                const uint4 cur = e;
-                if (k + 1 < hdr.x) e = __ldg(rows + (size_t)(k + 1) * 32);
-                const uint32_t cnt = s_cnt[cur.z];
-                acc0 += (unsigned long long)cur.x * cnt;
-                acc1 += (long long)(int)cur.y * (long long)cnt;
-            }
-        }
-        // class B
-        {
-            const uint4* __restrict__ rows = reinterpret_cast<const uint4*>(sp + prm.L.off_b) + lane;
-            uint4 e = hdr.y > 0 ? __ldg(rows) : make_uint4(0u, 0u, 0u, 0u);
-            for (int k = 0; k < hdr.y; ++k) {
-                const uint4 cur = e;
-                if (k + 1 < hdr.y) e = __ldg(rows + (size_t)(k + 1) * 32);
-                const uint32_t pm = (uint32_t)((int)cur.z >> 31);
-                const unsigned char* ap = s_mask + (cur.z & 0x7FFFFFFFu);
-                const unsigned char* aj = s_mask + cur.w;
-                int cnt = 0;
+        auto add = [&](const uint4& e, int cnt) {
+            acc0 += (unsigned long long)e.x * (uint32_t)cnt;
+            acc1 += (long long)(int)e.y * (long long)cnt;
+        };
+        bs_rows<8>(reinterpret_cast<const uint4*>(sp + prm.L.off[BS_A]) + lane, h0.x,
+                   [&](const uint4& e) { add(e, (int)s_cnt[e.z]); });
+        bs_rows<4>(reinterpret_cast<const uint4*>(sp + prm.L.off[BS_B]) + lane, h0.y, [&](const uint4& e) {
+            const uint32_t pm = (uint32_t)((int)e.z >> 31);
+            const unsigned char* ap = s_mask + (e.z & 0x7FFFFFFFu);
+            const unsigned char* aj = s_mask + e.w;
+            int cnt = 0;
 #pragma unroll
-                for (int c = 0; c < CH; ++c) {
-                    const uint4 mp = *reinterpret_cast<const uint4*>(ap + rot[c]);
-                    const uint4 mj = *reinterpret_cast<const uint4*>(aj + rot[c]);
-                    cnt += __popc((mp.x ^ pm) & mj.x) + __popc((mp.y ^ pm) & mj.y) + __popc((mp.z ^ pm) & mj.z) +
-                           __popc((mp.w ^ pm) & mj.w);
-                }
-                acc0 += (unsigned long long)cur.x * (uint32_t)cnt;
-                acc1 += (long long)(int)cur.y * (long long)cnt;
+            for (int c = 0; c < CH; ++c) {
+                const uint4 mp = lds16(ap + rot[c]), mj = lds16(aj + rot[c]);
+                cnt += __popc((mp.x ^ pm) & mj.x) + __popc((mp.y ^ pm) & mj.y) + __popc((mp.z ^ pm) & mj.z) +
+                       __popc((mp.w ^ pm) & mj.w);
             }
-        }
-        // class C
-        if (hdr.z > 0) {
-            const uint4* __restrict__ rows = reinterpret_cast<const uint4*>(sp + prm.L.off_c) + lane;
+            add(e, cnt);
+        });
+        bs_rows<4>(reinterpret_cast<const uint4*>(sp + prm.L.off[BS_C2]) + lane, h0.z, [&](const uint4& e) {
+            const unsigned char* aj = s_mask + ((e.z & 0x3FFFu) << 4);
+            const unsigned char* a0 = s_mask + (((e.z >> 14) & 0x3FFFu) << 4);
+            const unsigned char* a1 = s_mask + ((e.w & 0x3FFFu) << 4);
+            const uint32_t p0 = (uint32_t)((int)(e.z << 3) >> 31), p1 = (uint32_t)((int)(e.z << 2) >> 31);
+            int cnt = 0;
+#pragma unroll
+            for (int c = 0; c < CH; ++c) {
+                const uint4 mj = lds16(aj + rot[c]), m0 = lds16(a0 + rot[c]), m1 = lds16(a1 + rot[c]);
+                cnt += __popc((m0.x ^ p0) & (m1.x ^ p1) & mj.x) + __popc((m0.y ^ p0) & (m1.y ^ p1) & mj.y) +
+                       __popc((m0.z ^ p0) & (m1.z ^ p1) & mj.z) + __popc((m0.w ^ p0) & (m1.w ^ p1) & mj.w);
+            }
+            add(e, cnt);
+        });
+        bs_rows<2>(reinterpret_cast<const uint4*>(sp + prm.L.off[BS_C3]) + lane, h0.w, [&](const uint4& e) {
+            const unsigned char* aj = s_mask + ((e.z & 0x3FFFu) << 4);
+            const unsigned char* a0 = s_mask + (((e.z >> 14) & 0x3FFFu) << 4);
+            const unsigned char* a1 = s_mask + ((e.w & 0x3FFFu) << 4);
+            const unsigned char* a2 = s_mask + (((e.w >> 14) & 0x3FFFu) << 4);
+            const uint32_t p0 = (uint32_t)((int)(e.z << 3) >> 31), p1 = (uint32_t)((int)(e.z << 2) >> 31),
+                           p2 = (uint32_t)((int)(e.z << 1) >> 31);
+            int cnt = 0;
+#pragma unroll
+            for (int c = 0; c < CH; ++c) {
+                const uint4 mj = lds16(aj + rot[c]), m0 = lds16(a0 + rot[c]), m1 = lds16(a1 + rot[c]), m2 = lds16(a2 + rot[c]);
+                cnt += __popc((m0.x ^ p0) & (m1.x ^ p1) & (m2.x ^ p2) & mj.x) + __popc((m0.y ^ p0) & (m1.y ^ p1) & (m2.y ^ p2) & mj.y) +
+                       __popc((m0.z ^ p0) & (m1.z ^ p1) & (m2.z ^ p2) & mj.z) + __popc((m0.w ^ p0) & (m1.w ^ p1) & (m2.w ^ p2) & mj.w);
+            }
+            add(e, cnt);
+        });
+        if (h1.x > 0) {      // class D: depth >= 4, ancestors in planes (rare)
+            const uint4* __restrict__ rows = reinterpret_cast<const uint4*>(sp + prm.L.off[BS_D]) + lane;
             const uint32_t* __restrict__ anc = reinterpret_cast<const uint32_t*>(sp + prm.L.off_anc) + lane;
-            for (int k = 0; k < hdr.z; ++k) {
-                const uint4 cur = __ldg(rows + (size_t)k * 32);
+            for (int k = 0; k < h1.x; ++k) {
+                const uint4 e = __ldg(rows + (size_t)k * 32);
                 uint4 r[CH];
-                const unsigned char* aj = s_mask + cur.z;
+                const unsigned char* aj = s_mask + e.z;
 #pragma unroll
-                for (int c = 0; c < CH; ++c) r[c] = *reinterpret_cast<const uint4*>(aj + rot[c]);
-                for (int a = 0; a < hdr.w; ++a) {
-                    const uint32_t w = __ldg(anc + ((size_t)a * prm.L.cap_c + k) * 32);
+                for (int c = 0; c < CH; ++c) r[c] = lds16(aj + rot[c]);
+                for (int a = 0; a < h1.y; ++a) {
+                    const uint32_t w = __ldg(anc + ((size_t)a * prm.L.cap_d + k) * 32);
                     const uint32_t pm = (uint32_t)((int)w >> 31);
                     const unsigned char* ap = s_mask + (w & 0x7FFFFFFFu);
 #pragma unroll
                     for (int c = 0; c < CH; ++c) {
-                        const uint4 mp = *reinterpret_cast<const uint4*>(ap + rot[c]);
+                        const uint4 mp = lds16(ap + rot[c]);
                         r[c].x &= mp.x ^ pm; r[c].y &= mp.y ^ pm; r[c].z &= mp.z ^ pm; r[c].w &= mp.w ^ pm;
                     }
                 }
                 int cnt = 0;
 #pragma unroll
                 for (int c = 0; c < CH; ++c) cnt += popc4(r[c]);
-                acc0 += (unsigned long long)cur.x * (uint32_t)cnt;
-                acc1 += (long long)(int)cur.y * (long long)cnt;
+                add(e, cnt);
             }
         }
-        const int s = sl * 32 + lane;
-        if (s >= prm.draw_begin && s < prm.draw_end)
+        if (wanted)
             prm.draw_part[(int64_t)blockIdx.x * ndraws + (s - prm.draw_begin)] =
                 ((double)acc1 * 4294967296.0 + (double)acc0) * prm.inv_scale;
     }
@@ -420,6 +556,7 @@ int launch_eval_bitslice(const bartint_forest* f, const bartint_points* p, const
     BsParams prm{};
     prm.pool = f->dev.bs_pool;
     prm.slice_hdr = f->dev.bs_slice_hdr;
+    prm.slot_draw = f->dev.bs_slot_draw;
     prm.L = bs_layout_of(f);
     prm.codes_pm = p->codes_pm;
     prm.codes = p->codes;
@@ -430,8 +567,7 @@ int launch_eval_bitslice(const bartint_forest* f, const bartint_points* p, const
     prm.ncuts = f->bs_ncuts;
     prm.draw_begin = plan.draw_begin;
     prm.draw_end = plan.draw_end;
-    prm.slice_begin = plan.draw_begin / 32;
-    prm.slice_end = (plan.draw_end + 31) / 32;
+    prm.n_slices = (f->S + 31) / 32;
     prm.chunk_slices = plan.chunk_draws;          // (in slices for this kernel)
     prm.inv_scale = std::ldexp(1.0, -f->bs_q);
     prm.draw_part = draw_part;

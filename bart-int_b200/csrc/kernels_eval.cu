@@ -402,7 +402,7 @@ EvalPlan make_plan(const bartint_forest* f, const bartint_points* p, uint32_t fl
         pl.n_tiles = (int)std::max<int64_t>((p->N + pl.tile - 1) / pl.tile, 1);
         int n_sm = 148;
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, f->device);
-        const int n_slices = (draw_end + 31) / 32 - draw_begin / 32;
+        const int n_slices = (f->S + 31) / 32;        // (draws are permuted over the slices: every slice is visited)
         int chunks = std::max(1, std::min(n_slices, (n_sm + pl.n_tiles - 1) / pl.n_tiles));
         pl.chunk_draws = (n_slices + chunks - 1) / chunks;                       // slices per CTA
         pl.n_chunks = (n_slices + pl.chunk_draws - 1) / pl.chunk_draws;
