@@ -163,10 +163,12 @@ __global__ void __launch_bounds__(128) bs_draw_kernel(const BsCnt* __restrict__ 
     tot.dmax = (unsigned short)dmax;
     draw_tot[s] = tot;
     base[s] = b;
-    // the mask loads a draw costs (B 2, C2 3, C3 4, D ~6 per node); ties broken by the parts, then by the draw index
-    const unsigned long long cost = 2ull * r[BS_B] + 3ull * r[BS_C2] + 4ull * r[BS_C3] + 6ull * r[BS_D];
-    key[s] = (cost << 40) | ((unsigned long long)min(r[BS_B], 4095) << 28) | ((unsigned long long)min(r[BS_C2], 4095) << 16) |
-             (unsigned long long)(s & 0xFFFF);
+    // Slices take the draws in key order and every class is padded to the slice's longest draw, so draws that share a
+    // slice should have similar counts: the rare deep classes first (draws with D / C3 nodes together), then the B
+    // count (pairs of values, so the C2 count still sorts inside a bucket), then C2, C3; ties by the draw index.
+    const auto f12 = [](int v) { return (unsigned long long)min(v, 4095); };
+    key[s] = ((unsigned long long)(r[BS_D] > 0) << 63) | ((unsigned long long)(r[BS_C3] > 0) << 62) | (f12(r[BS_B] >> 1) << 48) |
+             (f12(r[BS_C2]) << 36) | (f12(r[BS_C3]) << 24) | (f12(r[BS_D]) << 16) | (unsigned long long)(s & 0xFFFF);
 }
 
 // rank of every draw by key: its slot (slice = slot / 32, lane = slot % 32).  sorted == 0: identity.
@@ -389,50 +391,39 @@ __global__ void __launch_bounds__(BS_THREADS, 1) eval_bitslice_kernel(const BsPa
     uint32_t* const s_cnt = reinterpret_cast<uint32_t*>(smem + (size_t)n_rows * ROWB);   // [n_rows] popcount of a row
     const int64_t tile_base = (int64_t)blockIdx.x * TILE;
 
-    // ---- 0. clear the table; the last row is the all-ones literal of unused ancestor slots ----
-    {
-        uint4* t4 = reinterpret_cast<uint4*>(s_mask);
-        const int n16 = prm.ncuts * CH;
-        for (int i = tid; i < n16; i += BS_THREADS) t4[i] = make_uint4(0u, 0u, 0u, 0u);
-        for (int i = tid; i < CH; i += BS_THREADS) t4[n16 + i] = make_uint4(~0u, ~0u, ~0u, ~0u);
-    }
-    __syncthreads();
-    // ---- 1. one-hot rows: row (v, c) word w gets the lanes of sub-tile w whose code of v equals c + 1 ----
-    for (int sub = warp; sub < WORDS; sub += BS_NWARP) {
-        const int64_t i = tile_base + (int64_t)sub * 32 + lane;
-        const bool in = i < prm.N;                    // padding rows count as code 0 (never right of any cut)
-        uint32_t* const col = reinterpret_cast<uint32_t*>(s_mask) + sub;
+    // ---- 0-2. the mask table.  Column w (32 points) of variable j's rows belongs to ONE thread: it clears the column,
+    // sets bit i of row (j, code - 1) for each of its 32 points (plain read-modify-write, no other thread touches the
+    // column), then ORs the rows downwards: M[j, c] = points with code > c.  Lanes hold consecutive columns, so every
+    // access is bank-conflict free, and no barrier is needed until the table is complete. ----
+    for (int item = tid; item < prm.d * WORDS; item += BS_THREADS) {
+        const int j = item / WORDS, w = item % WORDS;
+        const int r0 = __ldg(&prm.cut_off[j]), r1 = __ldg(&prm.cut_off[j + 1]);
+        uint32_t* const col = reinterpret_cast<uint32_t*>(s_mask) + w;
+        for (int r = r0; r < r1; ++r) col[(size_t)r * WORDS] = 0u;
+        const int64_t i0 = tile_base + (int64_t)w * 32;
         if (prm.codes_pm != nullptr) {
-            const uint4 v = in ? __ldg(&prm.codes_pm[i]) : make_uint4(0u, 0u, 0u, 0u);
-            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                if (j < prm.d) {
-                    const uint32_t c = (w[j >> 2] >> (8 * (j & 3))) & 0xFFu;
-                    const uint32_t mm = __match_any_sync(0xffffffffu, c);
-                    if (c != 0u && lane == __ffs((int)mm) - 1) col[(size_t)(__ldg(&prm.cut_off[j]) + (int)c - 1) * WORDS] = mm;
-                }
+            const unsigned char* src = reinterpret_cast<const unsigned char*>(prm.codes_pm) + j;   // byte j of each 16-byte record
+#pragma unroll 4
+            for (int i = 0; i < 32; ++i) {
+                const uint32_t c = i0 + i < prm.N ? (uint32_t)__ldg(src + (i0 + i) * 16) : 0u;
+                if (c != 0u) col[(size_t)(r0 + (int)c - 1) * WORDS] |= 1u << i;
             }
         } else {
-            for (int j = 0; j < prm.d; ++j) {
-                const uint32_t c = in ? (uint32_t)__ldg(&prm.codes[(int64_t)j * prm.Npad + i]) : 0u;
-                const uint32_t mm = __match_any_sync(0xffffffffu, c);
-                if (c != 0u && lane == __ffs((int)mm) - 1) col[(size_t)(__ldg(&prm.cut_off[j]) + (int)c - 1) * WORDS] = mm;
+            const uint8_t* src = prm.codes + (int64_t)j * prm.Npad;
+#pragma unroll 4
+            for (int i = 0; i < 32; ++i) {
+                const uint32_t c = i0 + i < prm.N ? (uint32_t)__ldg(src + i0 + i) : 0u;
+                if (c != 0u) col[(size_t)(r0 + (int)c - 1) * WORDS] |= 1u << i;
             }
         }
-    }
-    __syncthreads();
-    // ---- 2. suffix OR down every variable's rows: M[v, c] = points with code > c; WORDS threads per variable ----
-    for (int v = tid / WORDS; v < prm.d; v += BS_THREADS / WORDS) {
-        const int w = tid % WORDS;
-        const int r0 = __ldg(&prm.cut_off[v]), r1 = __ldg(&prm.cut_off[v + 1]);
-        uint32_t* const col = reinterpret_cast<uint32_t*>(s_mask) + w;
         uint32_t m = 0u;
         for (int r = r1 - 1; r >= r0; --r) {
             m |= col[(size_t)r * WORDS];
             col[(size_t)r * WORDS] = m;
         }
     }
+    for (int i = tid; i < WORDS; i += BS_THREADS)          // the all-ones literal of unused ancestor slots
+        reinterpret_cast<uint32_t*>(s_mask)[(size_t)prm.ncuts * WORDS + i] = ~0u;
     __syncthreads();
     // chunk order of this lane: the 8 lanes of an LDS.128 phase read 8 different bank groups
     uint32_t rot[CH];
