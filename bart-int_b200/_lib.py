@@ -26,6 +26,10 @@ SIGNATURES = {
     "bartint_last_error": (C.c_char_p, []),
     "bartint_device_count": (C.c_int, [c_int32_p]),
     "bartint_set_device": (C.c_int, [C.c_int]),
+    "bartint_init": (C.c_int, [C.c_int]),
+    "bartint_group_size": (C.c_int, []),
+    "bartint_group_exchange": (C.c_char_p, []),
+    "bartint_shutdown": (None, []),
     "bartint_forest_from_dbarts098": (C.c_int, [C.POINTER(C.c_char_p), c_double_p, c_double_p, C.c_int64, C.c_int32,
                                                 c_int32_p, c_double_p, C.c_double, C.c_double, C.c_int32, C.c_int32,
                                                 handle_p]),
@@ -98,6 +102,7 @@ SIGNATURES = {
 BARTINT_SCALED_UNITS = 0x1
 BARTINT_FORCE_WALK = 0x2
 BARTINT_NO_BITSLICE = 0x4
+BARTINT_DEVICE_GROUP = -1
 MEASURES = {"uniform": 0, "gaussian": 1, "exponential": 2, "gaussian_correct": 3}
 STATUS_NAMES = {0: "OK", 1: "ERR_ARG", 2: "ERR_PARSE", 3: "ERR_CUDA", 4: "ERR_UNSUPPORTED", 5: "ERR_NOMEM",
                 6: "ERR_NODEVICE"}

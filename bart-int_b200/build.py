@@ -16,10 +16,10 @@ LIB = os.path.join(HERE, "libbartint_cuda.so")
 SYNTH_LIB = os.path.join(HERE, "libbartint_synth.so")
 
 CUDA_SOURCES = ["bartint_abi.cu", "forest_host.cu", "kernels_eval.cu", "kernels_gather.cu", "kernels_bitslice.cu",
-                "kernels_misc.cu"]
+                "kernels_misc.cu", "group.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-    "-Xcompiler", "-fPIC,-fopenmp,-O3", "-shared", "-lgomp",
+    "-Xcompiler", "-fPIC,-fopenmp,-O3,-pthread", "-shared", "-lgomp", "-ldl",
 ]
 
 

@@ -4,6 +4,7 @@
 #include <ctime>
 #include <cstdio>
 #include <limits>
+#include <memory>
 #include <new>
 
 #ifdef _OPENMP
@@ -455,31 +456,11 @@ int bartint_points_from_device(const bartint_forest* f, const double* dX, int64_
     return rc;
 }
 
-struct bartint_staged {
-    int device = 0;
-    int64_t N = 0;
-    int32_t d = 0;
-    double* dX = nullptr;
-    cudaStream_t copy_stream = nullptr;
-    cudaEvent_t done = nullptr;
-    // large matrices travel in row blocks (multiples of 4096 rows), each with its own event, so a consumer can start
-    // on the first rows while the rest is still on the bus (bartint_design_step_dbarts098)
-    int n_blocks = 1;
-    int64_t block_rows = 0;
-    cudaEvent_t block_done[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    // Only block 0 is put on the bus at once: copies queue FIFO on the copy engine, and the first forest upload of a
-    // design step must not wait behind the whole matrix.  The other blocks are submitted by staged_submit_rest()
-    // (first consumer, or the design step right after its first forest upload).  The host matrix stays caller-owned
-    // and must remain valid until the staged matrix has been consumed or freed.
-    const double* host_X = nullptr;
-    int submitted = 1;
-};
-
 static cudaError_t staged_submit_block(bartint_staged* s, int b) {
     const int64_t r0 = (int64_t)b * s->block_rows, rows = std::min(s->block_rows, s->N - r0);
     cudaError_t e = cudaSuccess;
     if (rows > 0)
-        e = cudaMemcpy2DAsync(s->dX + r0, sizeof(double) * (size_t)s->N, s->host_X + r0, sizeof(double) * (size_t)s->N,
+        e = cudaMemcpy2DAsync(s->dX + r0, sizeof(double) * (size_t)s->N, s->host_X + r0, sizeof(double) * (size_t)s->host_ld,
                               sizeof(double) * (size_t)rows, (size_t)s->d, cudaMemcpyHostToDevice, s->copy_stream);
     if (e == cudaSuccess) e = cudaEventRecord(s->block_done[b], s->copy_stream);
     return e;
@@ -495,16 +476,12 @@ static cudaError_t staged_submit_rest(const bartint_staged* cs) {
     return e;
 }
 
-int bartint_stage_matrix(const double* X, int64_t N, int32_t d, int device, bartint_staged** out) {
-    BI_REQUIRE(out != nullptr, BARTINT_ERR_ARG, "out is NULL");
-    *out = nullptr;
-    BI_REQUIRE(N >= 0 && d >= 0 && (N * d == 0 || X != nullptr), BARTINT_ERR_ARG, "X is NULL or bad shape");
-    int rc = check_device();
-    if (rc) return rc;
+// rows [0, N) of a column-major host matrix with leading dimension ld, staged on `device`
+static int stage_rows(const double* X, int64_t N, int64_t ld, int32_t d, int device, bartint_staged** out) {
     DeviceGuard g(device);
     bartint_staged* s = new (std::nothrow) bartint_staged();
     BI_REQUIRE(s != nullptr, BARTINT_ERR_NOMEM, "out of host memory");
-    s->device = device; s->N = N; s->d = d;
+    s->device = device; s->N = N; s->d = d; s->host_ld = ld;
     cudaError_t e = cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->done, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMallocAsync((void**)&s->dX, sizeof(double) * (size_t)std::max<int64_t>(N * d, 1), s->copy_stream);
@@ -517,8 +494,11 @@ int bartint_stage_matrix(const double* X, int64_t N, int32_t d, int device, bart
                 e = cudaEventCreateWithFlags(&s->block_done[b], cudaEventDisableTiming);
             if (e == cudaSuccess) e = staged_submit_block(s, 0);
             s->submitted = 1;
-        } else {
+        } else if (ld == N) {
             e = cudaMemcpyAsync(s->dX, X, sizeof(double) * (size_t)(N * d), cudaMemcpyHostToDevice, s->copy_stream);
+        } else {
+            e = cudaMemcpy2DAsync(s->dX, sizeof(double) * (size_t)N, X, sizeof(double) * (size_t)ld, sizeof(double) * (size_t)N,
+                                  (size_t)d, cudaMemcpyHostToDevice, s->copy_stream);
         }
     }
     if (e == cudaSuccess) e = cudaEventRecord(s->done, s->copy_stream);
@@ -527,8 +507,44 @@ int bartint_stage_matrix(const double* X, int64_t N, int32_t d, int device, bart
     return BARTINT_OK;
 }
 
+int bartint_stage_matrix(const double* X, int64_t N, int32_t d, int device, bartint_staged** out) {
+    BI_REQUIRE(out != nullptr, BARTINT_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    BI_REQUIRE(N >= 0 && d >= 0 && (N * d == 0 || X != nullptr), BARTINT_ERR_ARG, "X is NULL or bad shape");
+    int rc = check_device();
+    if (rc) return rc;
+    if (device != BARTINT_DEVICE_GROUP) return stage_rows(X, N, N, d, device, out);
+    // the device group: contiguous row shards (multiples of 1024 rows), shard g staged on member g by its own thread
+    const int G = group_size();
+    bartint_staged* box = new (std::nothrow) bartint_staged();
+    BI_REQUIRE(box != nullptr, BARTINT_ERR_NOMEM, "out of host memory");
+    box->device = group_device(0); box->N = N; box->d = d; box->n_blocks = 0;
+    box->shards.assign((size_t)G, nullptr);
+    box->shard_lo.assign((size_t)G + 1, N);
+    const int64_t per = ((N + G - 1) / G + 1023) / 1024 * 1024;
+    for (int g = 0; g <= G; ++g) box->shard_lo[(size_t)g] = std::min<int64_t>(N, (int64_t)g * per);
+    for (int g = 1; g < G; ++g) {
+        const int64_t lo = box->shard_lo[(size_t)g], rows = box->shard_lo[(size_t)g + 1] - lo;
+        bartint_staged** slot = &box->shards[(size_t)g];
+        group_post(g, [=] { return stage_rows(X + lo, rows, N, d, group_device(g), slot); });
+    }
+    rc = stage_rows(X, box->shard_lo[1], N, d, group_device(0), &box->shards[0]);
+    const int rc2 = group_wait();
+    if (rc == BARTINT_OK) rc = rc2;
+    if (rc != BARTINT_OK) { bartint_staged_free(box); return rc; }
+    *out = box;
+    return BARTINT_OK;
+}
+
 int bartint_staged_flush(bartint_staged* s) {
     BI_REQUIRE(s != nullptr, BARTINT_ERR_ARG, "NULL argument");
+    if (!s->shards.empty()) {
+        for (bartint_staged* sh : s->shards) {
+            int rc = bartint_staged_flush(sh);
+            if (rc) return rc;
+        }
+        return BARTINT_OK;
+    }
     DeviceGuard g(s->device);
     BI_CUDA(staged_submit_rest(s));
     return BARTINT_OK;
@@ -536,6 +552,7 @@ int bartint_staged_flush(bartint_staged* s) {
 
 int bartint_staged_points(const bartint_forest* f, const bartint_staged* s, void* stream, bartint_points** out) {
     BI_REQUIRE(f != nullptr && s != nullptr && out != nullptr, BARTINT_ERR_ARG, "NULL argument");
+    BI_REQUIRE(s->shards.empty(), BARTINT_ERR_UNSUPPORTED, "a matrix staged on the device group is consumed by bartint_design_step_dbarts098 / bartint_eval_staged");
     BI_REQUIRE(s->device == f->device, BARTINT_ERR_ARG, "matrix was staged on another device than the forest's");
     DeviceGuard g(f->device);
     BI_CUDA(staged_submit_rest(s));
@@ -545,6 +562,17 @@ int bartint_staged_points(const bartint_forest* f, const bartint_staged* s, void
 
 void bartint_staged_free(bartint_staged* s) {
     if (s == nullptr) return;
+    if (!s->shards.empty()) {              // a group container: every shard is released by its member's thread
+        for (size_t g = 1; g < s->shards.size(); ++g) {
+            bartint_staged* sh = s->shards[g];
+            if (sh && (int)g < group_size()) group_post((int)g, [sh] { bartint_staged_free(sh); return (int)BARTINT_OK; });
+            else bartint_staged_free(sh);
+        }
+        bartint_staged_free(s->shards[0]);
+        group_wait();
+        delete s;
+        return;
+    }
     {
         DeviceGuard g(s->device);
         if (s->copy_stream) cudaStreamSynchronize(s->copy_stream);
@@ -1141,8 +1169,9 @@ int bartint_forest_pack(const bartint_forest* f, void* host_header, int64_t host
     return BARTINT_OK;
 }
 
-int bartint_forest_unpack(const void* host_header, int64_t host_bytes, const void* d_blob, int64_t device_bytes, void* stream,
-                          bartint_forest** out) {
+// src_device >= 0: the blob lives on that (peer) device and is pulled over NVLink; wait: block until the image is complete
+static int forest_from_image(const void* host_header, int64_t host_bytes, const void* d_blob, int src_device,
+                             int64_t device_bytes, cudaStream_t st, bool wait, bartint_forest** out) {
     BI_REQUIRE(out != nullptr, BARTINT_ERR_ARG, "out is NULL");
     *out = nullptr;
     BI_REQUIRE(host_header != nullptr && d_blob != nullptr && host_bytes >= (int64_t)sizeof(ImageHeader), BARTINT_ERR_ARG,
@@ -1172,7 +1201,6 @@ int bartint_forest_unpack(const void* host_header, int64_t host_bytes, const voi
     f->cut_val.resize((size_t)h.n_cuts);
     if (h.n_cuts) memcpy(f->cut_val.data(), hp, (size_t)h.n_cuts * 8);
     cudaError_t e = cudaGetDevice(&f->device);
-    cudaStream_t st = (cudaStream_t)stream;
     if (e == cudaSuccess) {                 // same allocator policy as finish_forest: keep freed blocks cached
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, f->device) == cudaSuccess) {
@@ -1184,7 +1212,9 @@ int bartint_forest_unpack(const void* host_header, int64_t host_bytes, const voi
     // one allocation holds every array (image_base); the DeviceForest pointers point into it
     if (e == cudaSuccess) e = cudaMallocAsync((void**)&f->image_base, (size_t)std::max<int64_t>(h.device_bytes, 256), st);
     if (e == cudaSuccess)
-        e = cudaMemcpyAsync(f->image_base, d_blob, (size_t)h.device_bytes, cudaMemcpyDeviceToDevice, st);
+        e = src_device >= 0 && src_device != f->device
+                ? cudaMemcpyPeerAsync(f->image_base, f->device, d_blob, src_device, (size_t)h.device_bytes, st)
+                : cudaMemcpyAsync(f->image_base, d_blob, (size_t)h.device_bytes, cudaMemcpyDeviceToDevice, st);
     if (e == cudaSuccess) {
         int64_t sizes[11];
         void** slots[11];
@@ -1209,7 +1239,7 @@ int bartint_forest_unpack(const void* host_header, int64_t host_bytes, const voi
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&f->ev_last, cudaEventDisableTiming);
     // later users may run on any stream: the image must be complete before this call returns control to them
     if (e == cudaSuccess) e = cudaEventRecord(f->ev_last, st);
-    if (e == cudaSuccess) { f->ev_last_set = true; e = cudaStreamSynchronize(st); }
+    if (e == cudaSuccess) { f->ev_last_set = true; if (wait) e = cudaStreamSynchronize(st); }
     if (e != cudaSuccess) {
         rc = cuda_fail(e, "bartint_forest_unpack", __FILE__, __LINE__);
         bartint_forest_destroy(f);
@@ -1217,6 +1247,11 @@ int bartint_forest_unpack(const void* host_header, int64_t host_bytes, const voi
     }
     *out = f;
     return BARTINT_OK;
+}
+
+int bartint_forest_unpack(const void* host_header, int64_t host_bytes, const void* d_blob, int64_t device_bytes, void* stream,
+                          bartint_forest** out) {
+    return forest_from_image(host_header, host_bytes, d_blob, -1, device_bytes, (cudaStream_t)stream, true, out);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -1227,14 +1262,21 @@ int bartint_forest_unpack(const void* host_header, int64_t host_bytes, const voi
 // ------------------------------------------------------------------------------------------------------------
 int bartint_design_step_dbarts098(const char* const* tree_strings, const double* tree_fits, const double* x_train,
                                   int64_t n, int32_t d, const int32_t* cut_offsets, const double* cut_values,
-                                  double y_min, double y_max, int32_t m, int32_t S, const bartint_staged* mc,
+                                  double y_min, double y_max, int32_t m, int32_t S, const bartint_staged* mc_arg,
                                   const bartint_staged* cand, const double* weights, int64_t weights_len,
                                   int32_t measure, int32_t n_draws_integral, int32_t n_chunks, double* integrals_scaled,
                                   double* integral_mean_sd, double* cand_var, double* draw_mean, double* draw_mean_var) {
     BI_REQUIRE(S >= 1 && m >= 1, BARTINT_ERR_ARG, "S and m must be >= 1");
     BI_REQUIRE(tree_strings != nullptr && tree_fits != nullptr, BARTINT_ERR_ARG, "NULL dbarts state");
     BI_REQUIRE(measure >= 0 && measure <= 3, BARTINT_ERR_ARG, "unknown measure %d", measure);
-    BI_REQUIRE(mc == nullptr || mc->d == d, BARTINT_ERR_ARG, "MC point matrix has %d columns, the model %d", mc ? mc->d : 0, d);
+    BI_REQUIRE(mc_arg == nullptr || mc_arg->d == d, BARTINT_ERR_ARG, "MC point matrix has %d columns, the model %d", mc_arg ? mc_arg->d : 0, d);
+    // a matrix staged on the device group: member 0 (this thread) works on shard 0 exactly like the one-GPU path, the
+    // other members get every chunk's forest image and evaluate their own rows (see the chunk loop)
+    const bool grouped = mc_arg != nullptr && !mc_arg->shards.empty();
+    const int GM = grouped ? (int)mc_arg->shards.size() : 1;
+    BI_REQUIRE(!grouped || GM == group_size(), BARTINT_ERR_ARG, "the MC matrix was staged on a device group of %d, the group now has %d", GM, group_size());
+    const bartint_staged* mc = grouped ? mc_arg->shards[0] : mc_arg;
+    const int64_t N_total = mc_arg ? mc_arg->N : 0;
     BI_REQUIRE(cand == nullptr || cand->d == d, BARTINT_ERR_ARG, "candidate matrix has %d columns, the model %d", cand ? cand->d : 0, d);
     BI_REQUIRE(mc == nullptr || cand == nullptr || mc->device == cand->device, BARTINT_ERR_ARG, "matrices staged on different devices");
     const int64_t C = cand ? cand->N : 0, N = mc ? mc->N : 0;
@@ -1253,7 +1295,8 @@ int bartint_design_step_dbarts098(const char* const* tree_strings, const double*
     const int n_int = (n_draws_integral <= 0 || n_draws_integral > S) ? S : n_draws_integral;
     const bool want_int = integrals_scaled != nullptr || integral_mean_sd != nullptr;
     const bool want_cand = cand_var != nullptr && C > 0;
-    const bool want_mc = (draw_mean != nullptr || draw_mean_var != nullptr) && N > 0;
+    const bool want_mc = (draw_mean != nullptr || draw_mean_var != nullptr) && N_total > 0;
+    const bool multi = grouped && GM > 1 && want_mc;
 
     cudaStream_t st = nullptr;
     cudaEvent_t built = nullptr;
@@ -1266,7 +1309,33 @@ int bartint_design_step_dbarts098(const char* const* tree_strings, const double*
     cudaEvent_t ready = nullptr;
     bartint_points views[8];
     int n_bst = 0;
+    // the other group members: their chunk forests, point shard, per-draw sums (complete over their rows) and the
+    // receive buffer of the exchange; touched only by the member's worker thread until group_wait()
+    struct Member {
+        std::vector<bartint_forest*> forests;
+        bartint_points* pm = nullptr;
+        double *d_sum = nullptr, *d_gath = nullptr;
+    };
+    std::vector<Member> members((size_t)GM);
+    std::vector<void*> blobs;                 // forest images on member 0, one per chunk
+    std::vector<cudaEvent_t> packed_ev;
     auto cleanup = [&]() {
+        if (multi) {
+            group_wait();
+            for (int g = 1; g < GM; ++g) {
+                Member* M = &members[(size_t)g];
+                group_post(g, [M, g] {
+                    cudaStreamSynchronize(group_stream(g));
+                    for (bartint_forest* f : M->forests) bartint_forest_destroy(f);
+                    if (M->pm) bartint_points_destroy(M->pm);
+                    if (M->d_sum) cudaFreeAsync(M->d_sum, group_stream(g));
+                    if (M->d_gath) cudaFreeAsync(M->d_gath, group_stream(g));
+                    (void)cudaGetLastError();
+                    return (int)BARTINT_OK;
+                });
+            }
+            group_wait();
+        }
         for (int b = 0; b < 8; ++b)
             if (bst[b]) cudaStreamSynchronize(bst[b]);
         if (st) cudaStreamSynchronize(st);
@@ -1276,6 +1345,8 @@ int bartint_design_step_dbarts098(const char* const* tree_strings, const double*
         if (pc) bartint_points_destroy(pc);
         if (d_buf) cudaFreeAsync(d_buf, nullptr);
         if (d_counts) cudaFreeAsync(d_counts, nullptr);
+        for (void* b : blobs) cudaFreeAsync(b, nullptr);
+        for (cudaEvent_t ev : packed_ev) cudaEventDestroy(ev);
         for (bartint_forest* f : forests) bartint_forest_destroy(f);
         (void)cudaGetLastError();
     };
@@ -1318,7 +1389,8 @@ int bartint_design_step_dbarts098(const char* const* tree_strings, const double*
     // one device buffer: integrals S | rescaled S | mean,sd 2 | draw sums S | draw means S | mean,var 2 |
     //                    candidate means G*C | candidate M2 G*C | candidate var C | weights max(len,1)
     const size_t nS = (size_t)S, nC = (size_t)std::max<int64_t>(C, 1);
-    const size_t total = 4 * nS + 4 + 2 * (size_t)G * nC + nC + (size_t)std::max<int64_t>(weights_len, 1) + 8 * nS;
+    const size_t total = 4 * nS + 4 + 2 * (size_t)G * nC + nC + (size_t)std::max<int64_t>(weights_len, 1) + 8 * nS +
+                         (size_t)(GM + 1) * nS;
     DS_CUDA(cudaMallocAsync((void**)&d_buf, sizeof(double) * total, st));
     double* d_int = d_buf;
     double* d_int_res = d_int + nS;
@@ -1331,6 +1403,8 @@ int bartint_design_step_dbarts098(const char* const* tree_strings, const double*
     double* d_cvar = d_cm2 + (size_t)G * nC;
     double* d_w = d_cvar + nC;
     double* d_block_part = d_w + (size_t)std::max<int64_t>(weights_len, 1);       // [<= 8 row blocks][S] per-draw sums
+    double* d_gath = d_block_part + 8 * nS;                                       // [GM][S] the members' per-draw sums
+    double* d_sum_local = d_gath + (size_t)GM * nS;                               // member 0's own rows (group runs)
     if (weights != nullptr && want_cand)
         DS_CUDA(cudaMemcpyAsync(d_w, weights, sizeof(double) * (size_t)weights_len, cudaMemcpyHostToDevice, st));
     std::vector<int32_t> counts((size_t)G);
@@ -1358,9 +1432,45 @@ int bartint_design_step_dbarts098(const char* const* tree_strings, const double*
         DS_CUDA(cudaEventRecord(built, nullptr));
         DS_CUDA(cudaStreamWaitEvent(st, built, 0));
         if (g == 0 && mc != nullptr) DS_CUDA(staged_submit_rest(mc));   // the first forest is on the bus: now the rest of X
+        if (multi) {
+            // the chunk's forest image for the other members: packed behind the uploads on the default stream, pulled
+            // by every member over NVLink on its own stream, evaluated on the member's rows by its worker thread
+            int64_t hb = 0, db = 0;
+            DS_RC(bartint_forest_image_size(f, &hb, &db));
+            auto hdr = std::make_shared<std::vector<unsigned char>>((size_t)hb);
+            void* blob = nullptr;
+            DS_CUDA(cudaMallocAsync(&blob, (size_t)db, nullptr));
+            blobs.push_back(blob);
+            DS_RC(bartint_forest_pack(f, hdr->data(), hb, blob, db, nullptr));
+            cudaEvent_t pev = nullptr;
+            DS_CUDA(cudaEventCreateWithFlags(&pev, cudaEventDisableTiming));
+            packed_ev.push_back(pev);
+            DS_CUDA(cudaEventRecord(pev, nullptr));
+            const int dev0 = f->device;
+            for (int k = 1; k < GM; ++k) {
+                Member* M = &members[(size_t)k];
+                const bartint_staged* shard = mc_arg->shards[(size_t)k];
+                group_post(k, [=] {
+                    cudaStream_t ws = group_stream(k);
+                    BI_CUDA(cudaStreamWaitEvent(ws, pev, 0));
+                    bartint_forest* fk = nullptr;
+                    int r = forest_from_image(hdr->data(), hb, blob, dev0, db, ws, false, &fk);
+                    if (r) return r;
+                    M->forests.push_back(fk);
+                    if (M->d_sum == nullptr) {
+                        BI_CUDA(cudaMallocAsync((void**)&M->d_sum, sizeof(double) * (size_t)S, ws));
+                        BI_CUDA(cudaMallocAsync((void**)&M->d_gath, sizeof(double) * (size_t)S * (size_t)GM, ws));
+                        BI_CUDA(cudaMemsetAsync(M->d_sum, 0, sizeof(double) * (size_t)S, ws));
+                        if (shard->N > 0 && (r = bartint_staged_points(fk, shard, ws, &M->pm))) return r;
+                    }
+                    if (M->pm == nullptr) return (int)BARTINT_OK;          // an empty shard contributes zeros
+                    return eval_core(fk, M->pm, 0u, 0, s1 - s0, M->d_sum + s0, nullptr, nullptr, nullptr, nullptr, 1.0, 0.0, 1, ws);
+                });
+            }
+        }
         if (g == 0) {            // the cut points are the same for every chunk: bin once against the first sub-forest
             if (want_cand) DS_RC(bartint_staged_points(f, cand, st, &pc));
-            if (want_mc && mc->n_blocks > 1) {
+            if (want_mc && N > 0 && mc->n_blocks > 1) {
                 // The MC matrix arrives in row blocks.  Each block gets its own stream: bin the block when it has landed,
                 // then evaluate chunk after chunk of draws on it (a view of the point set) as the sub-forests become
                 // available.  The GPU always has the ready (block, chunk) pairs to run, so neither the bus transfer nor
@@ -1392,7 +1502,7 @@ int bartint_design_step_dbarts098(const char* const* tree_strings, const double*
                     views[n_bst].N = rows;
                     ++n_bst;
                 }
-            } else if (want_mc) {
+            } else if (want_mc && N > 0) {
                 DS_RC(bartint_staged_points(f, mc, st, &pm));
             }
         }
@@ -1408,7 +1518,7 @@ int bartint_design_step_dbarts098(const char* const* tree_strings, const double*
         if (want_cand)
             DS_RC(eval_core(f, pc, 0u, 0, s1 - s0, nullptr, d_cmean + (size_t)g * nC, d_cm2 + (size_t)g * nC, nullptr, nullptr,
                             1.0, 0.0, 1, st));
-        if (want_mc && n_bst == 0)
+        if (want_mc && n_bst == 0 && pm != nullptr)
             DS_RC(eval_core(f, pm, 0u, 0, s1 - s0, d_sum + s0, nullptr, nullptr, nullptr, nullptr, 1.0, 0.0, 1, st));
         if (timing) t_cpu.push_back(now_ms() - t_begin);
     }
@@ -1427,8 +1537,21 @@ int bartint_design_step_dbarts098(const char* const* tree_strings, const double*
         }
         DS_RC(launch_reduce_draw_parts(d_block_part, n_bst, S, d_sum, st));
     }
+    if (multi) {
+        // one exchange per call: every member's per-draw sums over its rows -> all members (ncclAllGather on the
+        // compute streams), added in member order on member 0
+        DS_RC(group_wait());
+        if (pm == nullptr) DS_CUDA(cudaMemsetAsync(d_sum, 0, sizeof(double) * nS, st));
+        DS_CUDA(cudaMemcpyAsync(d_sum_local, d_sum, sizeof(double) * nS, cudaMemcpyDeviceToDevice, st));
+        std::vector<double*> send((size_t)GM), recv((size_t)GM);
+        std::vector<cudaStream_t> streams((size_t)GM);
+        send[0] = d_sum_local; recv[0] = d_gath; streams[0] = st;
+        for (int k = 1; k < GM; ++k) { send[(size_t)k] = members[(size_t)k].d_sum; recv[(size_t)k] = members[(size_t)k].d_gath; streams[(size_t)k] = group_stream(k); }
+        DS_RC(group_allgather(send.data(), recv.data(), nS, streams.data()));
+        DS_RC(launch_reduce_draw_parts(d_gath, GM, S, d_sum, st));
+    }
     if (want_mc) {
-        DS_RC(launch_finalize_draws(d_sum, S, N, scale, y_min, 0, d_dmean, st));
+        DS_RC(launch_finalize_draws(d_sum, S, N_total, scale, y_min, 0, d_dmean, st));
         DS_RC(launch_draw_summary(d_dmean, S, d_mv, st));
     }
     if (integrals_scaled) DS_CUDA(cudaMemcpyAsync(integrals_scaled, d_int, sizeof(double) * (size_t)n_int, cudaMemcpyDeviceToHost, st));

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -161,6 +162,32 @@ struct bartint_points {
     uint4* codes_pm = nullptr; // point-major packed codes (16 B per point) for the gather kernel; built with the codes
 };
 
+struct bartint_staged {
+    int device = 0;
+    int64_t N = 0;
+    int32_t d = 0;
+    double* dX = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t done = nullptr;
+    // large matrices travel in row blocks (multiples of 4096 rows), each with its own event, so a consumer can start
+    // on the first rows while the rest is still on the bus (bartint_design_step_dbarts098)
+    int n_blocks = 1;
+    int64_t block_rows = 0;
+    cudaEvent_t block_done[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    // Only block 0 is put on the bus at once: copies queue FIFO on the copy engine, and the first forest upload of a
+    // design step must not wait behind the whole matrix.  The other blocks are submitted by staged_submit_rest()
+    // (first consumer, or the design step right after its first forest upload).  The host matrix stays caller-owned
+    // and must remain valid until the staged matrix has been consumed or freed.
+    const double* host_X = nullptr;
+    int64_t host_ld = 0;             // leading dimension of host_X (rows of the caller's matrix; > N for a row shard)
+    int submitted = 1;
+    // A matrix staged on the DEVICE GROUP (bartint_stage_matrix with device = BARTINT_DEVICE_GROUP): contiguous row
+    // shards, shard g on group member g.  The container itself holds no device memory.
+    std::vector<bartint_staged*> shards;
+    std::vector<int64_t> shard_lo;   // first row of every shard, then N
+};
+
+
 namespace bartint {
 
 // host-side pieces (forest_host.cu)
@@ -191,6 +218,19 @@ int parse_wbart_forest(const char* text, int64_t len, int32_t d, bartint_forest*
 int canonicalise_soa(int32_t S, int32_t m, int32_t d, const int64_t* tree_node_offset, const int32_t* split_var,
                      const int32_t* split_cut_idx, const int32_t* left, const int32_t* right,
                      const double* leaf_mu, bartint_forest* f);
+
+// device group (group.cu): single-process multi-GPU.  Member 0 is driven by the calling thread; every other member
+// has a worker thread (its device current, one non-blocking stream) that runs posted tasks in order.
+int group_size();                                   // 1 when bartint_init has not been called
+int group_device(int g);
+bool group_has(int device);                         // is `device` member 0 of the group
+cudaStream_t group_stream(int g);                   // member g's worker stream (g >= 1)
+void group_post(int g, std::function<int()> fn);    // g >= 1; fn returns a bartint_status
+int group_wait();                                   // all posted tasks done; first error (message copied to this thread)
+// all-gather of `count` doubles per member: recv[g] receives G x count (member-major) on member g.  Enqueued on
+// streams[g]; NCCL (ncclAllGather, one group call) between distinct GPUs, peer copies in the same-device test mode.
+int group_allgather(double* const* send, double* const* recv, size_t count, cudaStream_t const* streams);
+const char* group_exchange_name();
 
 // kernel launchers (kernels_*.cu)
 int launch_bin_points(const double* dX, int64_t ld, int64_t N, int32_t d, const int32_t* d_cut_off,

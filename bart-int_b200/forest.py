@@ -163,11 +163,33 @@ class WireStrings:
         return v
 
 
+def init_group(n_gpus: int = 0) -> int:
+    """bartint_init: open the single-process device group over n_gpus devices (0 = all).  Returns its size."""
+    _check(_lib.load().bartint_init(int(n_gpus)))
+    return int(_lib.load().bartint_group_size())
+
+
+def group_size() -> int:
+    return int(_lib.load().bartint_group_size())
+
+
+def group_exchange() -> str:
+    return _lib.load().bartint_group_exchange().decode()
+
+
+def shutdown_group() -> None:
+    _lib.load().bartint_shutdown()
+
+
 class StagedMatrix:
     """A host matrix on its way to the device (asynchronous copy started at construction), independent of any forest:
     the candidate matrix / fullData exist before the model is fitted, so their transfer can overlap the export."""
 
     def __init__(self, X, device: int = 0):
+        """device: a CUDA device index, or "group" / -1 for the device group opened by `init_group` (row shards, one
+        per member)."""
+        if device == "group":
+            device = _lib.BARTINT_DEVICE_GROUP
         X = np.asarray(X, np.float64)
         self._X = np.asfortranarray(X)          # keep the host buffer alive until the copy has been consumed
         self.N, self.d = self._X.shape

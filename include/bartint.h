@@ -59,6 +59,21 @@ int bartint_version(void);
 const char* bartint_last_error(void);
 int bartint_device_count(int* n_out);
 int bartint_set_device(int device);       /* forests/points are created on the current device */
+
+/* ---------------------------------------------------------------------------------------------
+ * Device group: all GPUs of the box behind ONE caller (the reference's callers are a single R process,
+ * src/BARTInt.R:259-262, 312-314; src/survey_design/bartMean.R:74-82).  bartint_init(n) opens a group over devices
+ * 0..n-1 (n <= 0: every visible device): peer access, one worker thread and stream per member, one NCCL communicator
+ * per member (ncclCommInitAll; libnccl.so.2 is loaded with dlopen).  A matrix staged with device = BARTINT_DEVICE_GROUP
+ * is split into contiguous row shards, one per member, and bartint_design_step_dbarts098 given such a matrix
+ * exports the posterior once (all host threads), replicates every chunk's forest image to the other members with
+ * peer copies over NVLink, evaluates each member's rows there, and combines the members' per-draw sums with one
+ * ncclAllGather + member-ordered sum on the compute streams.  Not thread safe: one caller at a time (R is).
+ * bartint_group_exchange(): the name of the exchange in use (for reports). */
+int bartint_init(int n_gpus);
+int bartint_group_size(void);             /* 1 before bartint_init */
+const char* bartint_group_exchange(void);
+void bartint_shutdown(void);
 /* Host threads used by the exporter / group planner (OpenMP).  n <= 0: one per host core.  Returns the number in
  * effect.  Launchers that pin OMP_NUM_THREADS=1 per rank (torchrun) make the exporter serial unless this is called;
  * a multi-rank host should pass cores / ranks-per-node. */
@@ -154,6 +169,7 @@ void bartint_forest_destroy(bartint_forest* f);
  * when the first consumer asks for the data.  X therefore has to stay valid until the staged matrix has been consumed
  * (bartint_staged_points / bartint_design_step_dbarts098 returned) or freed. */
 typedef struct bartint_staged bartint_staged;
+#define BARTINT_DEVICE_GROUP (-1)   /* stage on the device group of bartint_init: contiguous row shards, one per member */
 int bartint_stage_matrix(const double* X, int64_t N, int32_t d, int device, bartint_staged** out);
 int bartint_staged_flush(bartint_staged* s);   /* put the remaining row blocks on the bus now (no forest upload is due soon) */
 int bartint_staged_points(const bartint_forest* f, const bartint_staged* s, void* stream, bartint_points** out);

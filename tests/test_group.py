@@ -1,0 +1,82 @@
+"""The single-process device group behind the C ABI (bartint_init, include/bartint.h): one call drives every GPU of
+the box, which is what the reference's one R process can reach (src/BARTInt.R:259-262, 312-314; bartMean.R:74-82).
+The k-member result of bartint_design_step_dbarts098 must equal the one-GPU result.  On a box with one GPU the
+group is opened over the same device several times (BARTINT_GROUP_DEVICES, peer-copy exchange); with >= 2 GPUs the
+members are distinct devices and the exchange is ncclAllGather."""
+import os
+
+import numpy as np
+import pytest
+
+import bartint_b200 as bi
+from bartint_b200 import StagedMatrix, design_step_dbarts, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _n_gpus():
+    import ctypes as C
+    from bartint_b200 import _lib
+    n = C.c_int32(0)
+    _lib.load().bartint_device_count(C.byref(n))
+    return n.value
+
+
+def _case(S=96, m=12, d=4, N=70_001, C=64, seed=3):
+    rng = np.random.default_rng(seed)
+    x_train = rng.random((50, d))
+    y = synth.genz_gaussian(x_train)
+    ff = synth.prior_forest(seed, S, m, x_train, y)
+    strings, fits = ff.to_dbarts_state(x_train)
+    return ff, x_train, strings, fits, rng.random((N, d)), rng.random((C, d))
+
+
+def _step(case, device, n_chunks=0):
+    ff, x_train, strings, fits, X, Xc = case
+    sx, sxc = StagedMatrix(X, device), StagedMatrix(Xc, 0)
+    try:
+        return design_step_dbarts(strings, fits, x_train, ff.cut_lists(), ff.y_min, ff.y_max, mc=sx, candidates=sxc,
+                                  weights=1.0, measure="uniform", n_chunks=n_chunks)
+    finally:
+        sx.close(); sxc.close()
+
+
+def _same(a, b, tol=1e-12):
+    for k in ("integrals", "integral_mean_sd", "cand_var", "draw_mean", "draw_mean_var"):
+        s = max(float(np.max(np.abs(a[k]))), 1e-300)
+        assert np.max(np.abs(np.asarray(a[k]) - np.asarray(b[k]))) <= tol * s, k
+
+
+@pytest.mark.parametrize("members", [1, 2, 3])
+def test_group_on_one_device_equals_single(members, monkeypatch):
+    """Members on the SAME device (test mode): worker threads, image replication, sharded staging and the
+    member-ordered exchange are exercised on a one-GPU box."""
+    case = _case()
+    want = _step(case, 0)
+    monkeypatch.setenv("BARTINT_GROUP_DEVICES", ",".join(["0"] * members))
+    try:
+        assert bi.init_group(members) == members
+        for n_chunks in (0, 1, 3):
+            got = _step(case, "group", n_chunks)
+            _same(got, want)
+        # a matrix with fewer rows than members x 1024: trailing members hold empty shards
+        small = _case(N=1500)
+        _same(_step(small, "group"), _step(small, 0))
+    finally:
+        bi.shutdown_group()
+    assert bi.group_size() == 1
+
+
+@pytest.mark.skipif(_n_gpus() < 2, reason="needs >= 2 GPUs")
+def test_group_over_all_gpus_equals_single():
+    case = _case(S=200, m=20, d=6, N=300_007, C=100, seed=8)
+    want = _step(case, 0)
+    try:
+        g = bi.init_group(0)
+        assert g == _n_gpus() and "ncclAllGather" in bi.group_exchange()
+        for _ in range(2):
+            _same(_step(case, "group"), want)
+        assert bi.init_group(2) == 2          # re-opening with another size replaces the group
+        _same(_step(case, "group"), want)
+    finally:
+        bi.shutdown_group()
