@@ -354,12 +354,27 @@ int bartint_forest_info(const bartint_forest* f, int64_t info[12]) {
     return BARTINT_OK;
 }
 
-int bartint_forest_bitslice_info(const bartint_forest* f, int64_t info[8]) {
+int bartint_forest_bitslice_info(const bartint_forest* f, int64_t info[16]) {
     BI_REQUIRE(f != nullptr && info != nullptr, BARTINT_ERR_ARG, "NULL argument");
-    for (int k = 0; k < 8; ++k) info[k] = 0;
+    for (int k = 0; k < 16; ++k) info[k] = 0;
     if (!f->bs_ok) return BARTINT_OK;
     info[0] = 1; info[1] = f->bs_ncuts; info[2] = f->bs_ch; info[3] = f->bs_rows; info[4] = f->bs_anc; info[5] = f->bs_q;
     info[6] = bs_pool_bytes(f); info[7] = (int64_t)(f->bs_ncuts + 1) * (f->bs_ch * 16 + 4);
+    for (int k = 0; k < 5; ++k) info[8 + k] = f->bs_class_nodes[k];
+    info[13] = f->bs_refs_total;
+    info[15] = (f->S + 31) / 32;
+    if (f->dev.bs_slice_hdr != nullptr) {         // what the slices actually load: every class padded to its longest draw
+        DeviceGuard g(f->device);
+        std::vector<int32_t> hdr((size_t)info[15] * 8);
+        BI_CUDA(cudaDeviceSynchronize());
+        BI_CUDA(cudaMemcpy(hdr.data(), f->dev.bs_slice_hdr, hdr.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        int64_t padded = 0;
+        for (int64_t sl = 0; sl < info[15]; ++sl) {
+            const int32_t* h = &hdr[(size_t)sl * 8];
+            padded += 32ll * (2ll * h[1] + 3ll * h[2] + 4ll * h[3] + (int64_t)h[4] * (1 + h[5]));
+        }
+        info[14] = padded;
+    }
     return BARTINT_OK;
 }
 

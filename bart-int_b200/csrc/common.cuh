@@ -139,6 +139,8 @@ struct bartint_forest {
     int32_t bs_ncuts = 0, bs_ch = 0, bs_rows = 0, bs_anc = 0, bs_q = 0;
     int32_t draw_internal_max = 0;     // most internal nodes in one draw
     double max_abs_mu = 0.0;           // largest |leaf value|
+    int64_t bs_class_nodes[5] = {0, 0, 0, 0, 0};   // internal nodes at depth 0, 1, 2, 3, >= 4 (0 for unpacked images)
+    int64_t bs_refs_total = 0;         // mask rows referenced by the nodes of depth >= 1 (depth + 1 each)
     std::vector<int32_t> draw_group_off;  // host copy, S+1
     bartint::DeviceForest dev;
     unsigned char* image_base = nullptr;  // forests restored by bartint_forest_unpack: the one allocation behind `dev`

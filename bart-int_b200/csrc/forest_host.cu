@@ -477,7 +477,10 @@ int forest_finish_host(bartint_forest* f) {
     int64_t n_leaves = 0;
     int32_t max_depth = 0, max_internal = 0;
     int bad = 0;
-#pragma omp parallel for schedule(static) reduction(+ : n_leaves) reduction(max : max_depth, max_internal)
+    // internal nodes by depth class (0, 1, 2, 3, >= 4) and the mask rows they reference in the bit-sliced kernel
+    // (depth + 1 for depth >= 1): the kernel's shared-memory floor, reported by bartint_forest_bitslice_info
+    int64_t cls0 = 0, cls1 = 0, cls2 = 0, cls3 = 0, cls4 = 0, refs = 0;
+#pragma omp parallel for schedule(static) reduction(+ : n_leaves, cls0, cls1, cls2, cls3, cls4, refs) reduction(max : max_depth, max_internal)
     for (int64_t k = 0; k < n_trees; ++k) {
         const int64_t base = f->tree_off[(size_t)k];
         const int32_t cnt = (int32_t)(f->tree_off[(size_t)k + 1] - base);
@@ -487,6 +490,9 @@ int forest_finish_host(bartint_forest* f) {
         for (int32_t a = 0; a < cnt; ++a) {
             if (f->var[(size_t)(base + a)] >= 0) {
                 ++internal;
+                const int32_t dp = depth[(size_t)a];
+                if (dp == 0) ++cls0; else if (dp == 1) ++cls1; else if (dp == 2) ++cls2; else if (dp == 3) ++cls3; else ++cls4;
+                if (dp >= 1) refs += dp + 1;
                 int32_t v = f->var[(size_t)(base + a)], c = f->cut[(size_t)(base + a)];
                 if (c < 0 || c >= f->cut_off[(size_t)v + 1] - f->cut_off[(size_t)v]) bad = 1;
                 depth[(size_t)f->left[(size_t)(base + a)]] = depth[(size_t)a] + 1;
@@ -503,6 +509,8 @@ int forest_finish_host(bartint_forest* f) {
     f->n_leaves = n_leaves;
     f->max_depth = max_depth;
     f->max_internal = max_internal;
+    f->bs_class_nodes[0] = cls0; f->bs_class_nodes[1] = cls1; f->bs_class_nodes[2] = cls2; f->bs_class_nodes[3] = cls3;
+    f->bs_class_nodes[4] = cls4; f->bs_refs_total = refs;
     // for the bit-sliced kernel: the longest draw and the largest |leaf value| (fixed-point scale)
     int32_t draw_internal_max = 0;
     double max_abs_mu = 0.0;

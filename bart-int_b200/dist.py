@@ -100,12 +100,12 @@ def chan_merge_np(counts, means, m2s):
 # ---------------------------------------------------------------------------------------------
 # production wrappers (CUDA tensors + libbartint_cuda)
 # ---------------------------------------------------------------------------------------------
-def point_sharded_draw_means(forest, pts_local, group=None, scaled=False, stream=None, n_total=None):
+def point_sharded_draw_means(forest, pts_local, group=None, scaled=False, stream=None, n_total=None, no_bitslice=False):
     """rowMeans(predict(model, X)) with X's rows sharded across ranks.  Returns (draw_mean[S], mean_var[2]) on device."""
     dev = torch.device("cuda", torch.cuda.current_device())
     st = torch.cuda.current_stream().cuda_stream if stream is None else stream
     sums = torch.empty(forest.S, dtype=torch.float64, device=dev)
-    forest.eval_device(pts_local, d_draw_sum=sums.data_ptr(), stream=st)
+    forest.eval_device(pts_local, d_draw_sum=sums.data_ptr(), stream=st, no_bitslice=no_bitslice)
     total, n_total = allreduce_draw_sums(sums, pts_local.N, group, n_total)
     out = torch.empty(forest.S, dtype=torch.float64, device=dev)
     mv = torch.empty(2, dtype=torch.float64, device=dev)

@@ -256,7 +256,7 @@ class Forest:
         self.table_kernel_ok = bool(tk)                                  # a fast kernel (table or gather) applies
         self.fast_kernel = {0: "none", 1: "table", 2: "gather"}[kind]
         self.route = int(_lib.load().bartint_forest_route(self._h))
-        bs = (C.c_int64 * 8)()
+        bs = (C.c_int64 * 16)()
         _check(_lib.load().bartint_forest_bitslice_info(self._h, bs))
         # the bit-sliced sums-only kernel: applies, predicate rows, points per tile, longest draw, fixed-point exponent
         self.bitslice_ok, self.bitslice_rows, self.bitslice_tile = bool(bs[0]), int(bs[1]), int(bs[2]) * 128

@@ -145,10 +145,14 @@ int bartint_forest_unpack(const void* host_header, int64_t host_bytes, const voi
  *               gather code words per point */
 int bartint_forest_info(const bartint_forest* f, int64_t info[12]);
 /* The bit-sliced sums-only kernel (kernels_bitslice.cu; used by every evaluation that asks for per-draw sums only):
- * info[0..7] = applies (0/1), predicate rows (= total number of cut points), 128-point chunks per tile, longest draw
- *              (internal nodes), ancestor planes, fixed-point exponent Q of the leaf differences, bytes of the node
- *              rows in HBM, shared memory per CTA */
-int bartint_forest_bitslice_info(const bartint_forest* f, int64_t info[8]);
+ * info[0..7]  = applies (0/1), predicate rows (= total number of cut points), 128-point chunks per tile, longest draw
+ *               (internal nodes), ancestor planes, fixed-point exponent Q of the leaf differences, bytes of the node
+ *               rows in HBM, shared memory per CTA;
+ * info[8..12] = internal nodes at depth 0, 1, 2, 3, >= 4;  info[13] = mask rows referenced by the nodes of depth >= 1
+ *               (depth + 1 each: the kernel's shared-memory floor is info[13] * chunks / 8 wavefronts per tile);
+ * info[14]    = the same count over the padded slice rows (what the kernel loads); info[15] = slices of 32 draws.
+ * Blocks until the forest's build has finished. */
+int bartint_forest_bitslice_info(const bartint_forest* f, int64_t info[16]);
 /* read the canonical (pre-order) flattening back; arrays sized from info[3] */
 int bartint_forest_export_soa(const bartint_forest* f, int64_t* tree_node_offset, int32_t* split_var,
                               int32_t* split_cut_idx, int32_t* left, int32_t* right, double* leaf_mu);
