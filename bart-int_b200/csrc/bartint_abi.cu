@@ -142,7 +142,7 @@ int bartint_set_device(int device) {
 static int forest_from_dbarts_impl(const char* const* tree_strings, const double* tree_fits, const double* x_train,
                                    int64_t n, int32_t d, const int32_t* cut_offsets, const double* cut_values,
                                    double y_min, double y_max, int32_t m, int32_t S, bool defer_upload_sync,
-                                   bartint_forest** out);
+                                   bartint_forest** out, bool no_fast_plan = false);
 
 int bartint_forest_from_dbarts098(const char* const* tree_strings, const double* tree_fits, const double* x_train,
                                   int64_t n, int32_t d, const int32_t* cut_offsets, const double* cut_values,
@@ -154,7 +154,7 @@ int bartint_forest_from_dbarts098(const char* const* tree_strings, const double*
 static int forest_from_dbarts_impl(const char* const* tree_strings, const double* tree_fits, const double* x_train,
                                    int64_t n, int32_t d, const int32_t* cut_offsets, const double* cut_values,
                                    double y_min, double y_max, int32_t m, int32_t S, bool defer_upload_sync,
-                                   bartint_forest** out) {
+                                   bartint_forest** out, bool no_fast_plan) {
     BI_REQUIRE(out != nullptr, BARTINT_ERR_ARG, "out is NULL");
     *out = nullptr;
     BI_REQUIRE(S >= 0 && m >= 0 && n >= 0, BARTINT_ERR_ARG, "S, m, n must be >= 0");
@@ -167,6 +167,7 @@ static int forest_from_dbarts_impl(const char* const* tree_strings, const double
     BI_REQUIRE(f != nullptr, BARTINT_ERR_NOMEM, "out of host memory");
     f->S = S; f->m = m; f->d = d; f->y_min = y_min; f->y_max = y_max;
     f->defer_upload_sync = defer_upload_sync;
+    f->no_fast_plan = no_fast_plan;
     f->cut_off.assign(cut_offsets, cut_offsets + d + 1);
     f->cut_val.assign(cut_values, cut_values + cut_offsets[d]);
     rc = parse_dbarts_forest(tree_strings, tree_fits, x_train, n, d, cut_offsets, cut_values, m, S, f);
@@ -1305,13 +1306,19 @@ int bartint_design_step_dbarts098(const char* const* tree_strings, const double*
     BI_CUDA(cudaGetDevice(&cur));
     DeviceGuard guard(device >= 0 ? device : cur);
 
-    int G = n_chunks > 0 ? n_chunks : (S >= 256 ? 4 : 1);
+    // (two chunks: the host export of the second half overlaps the first half's upload, build and evaluation; with the
+    //  bit-sliced kernel the evaluation is short and more chunks only add per-chunk host work -- tools/step_chunks.py)
+    int G = n_chunks > 0 ? n_chunks : (S >= 256 ? 2 : 1);
     G = std::min(G, S);
     const int n_int = (n_draws_integral <= 0 || n_draws_integral > S) ? S : n_draws_integral;
     const bool want_int = integrals_scaled != nullptr || integral_mean_sd != nullptr;
     const bool want_cand = cand_var != nullptr && C > 0;
     const bool want_mc = (draw_mean != nullptr || draw_mean_var != nullptr) && N_total > 0;
     const bool multi = grouped && GM > 1 && want_mc;
+    // Few candidates: their per-point moments come from the node-walk kernel and the per-draw sums of the MC points from
+    // the bit-sliced kernel, so the group planner, the record upload and the table build are skipped altogether.
+    static const bool force_plan = [] { const char* e = std::getenv("BARTINT_STEP_PLAN"); return e && e[0] == '1'; }();
+    const bool light = C <= 2048 && !force_plan;
 
     cudaStream_t st = nullptr;
     cudaEvent_t built = nullptr;
@@ -1441,7 +1448,7 @@ int bartint_design_step_dbarts098(const char* const* tree_strings, const double*
         bartint_forest* f = nullptr;
         if (timing) t_cpu.push_back(now_ms() - t_begin);
         DS_RC(forest_from_dbarts_impl(tree_strings + (size_t)s0 * (size_t)m, tree_fits + (size_t)s0 * (size_t)m * (size_t)n,
-                                      x_train, n, d, cut_offsets, cut_values, y_min, y_max, m, s1 - s0, true, &f));
+                                      x_train, n, d, cut_offsets, cut_values, y_min, y_max, m, s1 - s0, true, &f, light));
         forests.push_back(f);
         // the sub-forest's copies and table build are still in flight on the default stream: order `st` after them
         DS_CUDA(cudaEventRecord(built, nullptr));

@@ -126,6 +126,8 @@ struct bartint_forest {
     std::vector<double> cut_val;
     // table path
     bool defer_upload_sync = false;    // forest_upload leaves its default-stream work in flight (pipelined design step)
+    bool no_fast_plan = false;         // skip the table / gather records (design step with few candidates: the bit-sliced
+                                       // kernel gives the per-draw sums, the walk kernel the few per-point results)
     bool table_ok = false;             // a fast (table or gather) kernel applies
     bool gather = false;               // group records are in the gather format (else table format)
     bool count_mode = false;           // gather format with COUNTABLE records for the trees of <= count_level splits

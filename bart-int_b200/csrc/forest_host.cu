@@ -1034,9 +1034,11 @@ int forest_upload(bartint_forest* f) {
     if ((rc = launch_build_bitslice(f, nullptr))) return rc;
     pt.lap("upload: H2D walk form");
     FastPlan P;
-    plan_fast_path(f, tree_off, P);
+    if (f->no_fast_plan) f->table_ok = false;
+    else plan_fast_path(f, tree_off, P);
     pt.lap("");
     if (!f->table_ok) {
+        if (f->defer_upload_sync) return BARTINT_OK;
         BI_CUDA(cudaStreamSynchronize(nullptr));
         return BARTINT_OK;
     }

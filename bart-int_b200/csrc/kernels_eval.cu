@@ -436,7 +436,8 @@ EvalPlan make_plan(const bartint_forest* f, const bartint_points* p, uint32_t fl
     const int resident = n_sm * resident_per_sm;
     int best_chunks = 1;
     double best_eff = -1.0;
-    const int max_chunks = std::max(1, std::min(ndraws, pl.use_table ? 96 : 16));
+    // (the walk kernel with a handful of tiles -- the candidates of a design step -- needs the draws for parallelism)
+    const int max_chunks = std::max(1, std::min(ndraws, pl.use_table || pl.n_tiles <= 16 ? 96 : 16));
     for (int c = 1; c <= max_chunks; ++c) {
         const int cd = (ndraws + c - 1) / c;
         const int real_c = (ndraws + cd - 1) / cd;
@@ -444,7 +445,8 @@ EvalPlan make_plan(const bartint_forest* f, const bartint_points* p, uint32_t fl
         if (cd < 4 && c > 1) continue;
         const double waves = (double)pl.n_tiles * c / resident;
         // each extra chunk re-loads the tile's codes and re-fills the pipeline: mild preference for few chunks
-        const double eff = waves / std::ceil(waves) - 0.002 * c;
+        // (a grid smaller than one wave: every extra chunk simply puts more SMs to work)
+        const double eff = waves <= 1.0 ? waves : waves / std::ceil(waves) - 0.002 * c;
         if (eff > best_eff + 1e-9) { best_eff = eff; best_chunks = c; }
     }
     pl.n_chunks = best_chunks;
