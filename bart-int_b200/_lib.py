@@ -85,18 +85,6 @@ SIGNATURES = {
     "bartint_finalize_integrals": (C.c_int, [C.c_void_p, c_double_p, C.c_int32, c_double_p, c_double_p, c_double_p]),
     "bartint_last_eval_profile": (C.c_int, [C.c_void_p, C.c_int32, c_float_p, c_int32_p, c_int32_p]),
     "bartint_kernel_launch_count": (C.c_int64, []),
-    # host-only test hooks (exporter / planner output without a device); see tests/plan_interp.py
-    "bartint_debug_export_wbart": (C.c_int, [C.c_char_p, C.c_int64, C.c_int32, c_int32_p, c_double_p, C.c_int64, C.c_int64,
-                                             c_int64_p, c_int64_p, c_int32_p, c_int32_p, c_int32_p, c_int32_p,
-                                             c_double_p]),
-    "bartint_debug_export_dbarts098": (C.c_int, [C.c_void_p, c_double_p, c_double_p, C.c_int64, C.c_int32, c_int32_p,
-                                                 c_double_p, C.c_int32, C.c_int32, C.c_int64, c_int64_p, c_int64_p,
-                                                 c_int32_p, c_int32_p, c_int32_p, c_int32_p, c_double_p]),
-    "bartint_debug_plan_soa": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, c_int64_p, c_int32_p, c_int32_p, c_int32_p,
-                                         c_int32_p, c_double_p, c_int32_p, c_double_p, C.c_int64, c_int64_p,
-                                         C.POINTER(C.c_uint32), c_int32_p, c_double_p, c_uint8_p, c_int32_p, c_int32_p,
-                                         c_int32_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
-                                         C.POINTER(C.c_uint32)]),
 }
 
 BARTINT_SCALED_UNITS = 0x1

@@ -19,6 +19,7 @@ CUDA_SOURCES = ["bartint_abi.cu", "forest_host.cu", "kernels_eval.cu", "kernels_
                 "kernels_misc.cu", "group.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+    "-DBARTINT_TEST_HOOKS",       # host-only hooks of include/bartint_test_hooks.h (the CPU test-suite needs them)
     "-Xcompiler", "-fPIC,-fopenmp,-O3,-pthread", "-shared", "-lgomp", "-ldl",
 ]
 
@@ -40,7 +41,8 @@ def _stale(target: str, sources: list[str]) -> bool:
 def build_cuda(force: bool = False, verbose: bool = False, extra: list[str] | None = None) -> str:
     srcs = [os.path.join(CSRC, s) for s in CUDA_SOURCES]
     deps = srcs + [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "pipeline.cuh"),
-                   os.path.join(HERE, "..", "include", "bartint.h")]
+                   os.path.join(HERE, "..", "include", "bartint.h"),
+                   os.path.join(HERE, "..", "include", "bartint_test_hooks.h")]
     if force or _stale(LIB, deps):
         cmd = [_nvcc(), *NVCC_FLAGS, *(extra or []), "-o", LIB, *srcs]
         if verbose:

@@ -12,6 +12,9 @@
 #endif
 
 #include "common.cuh"
+#ifdef BARTINT_TEST_HOOKS
+#include "../../include/bartint_test_hooks.h"
+#endif
 
 namespace bartint {
 const char* get_error();
@@ -229,6 +232,7 @@ int bartint_forest_from_soa_routed(int32_t S, int32_t m, int32_t d, const int64_
     return finish_forest(f, out);
 }
 
+#ifdef BARTINT_TEST_HOOKS      // include/bartint_test_hooks.h
 int bartint_debug_plan_soa(int32_t S, int32_t m, int32_t d, const int64_t* tree_node_offset, const int32_t* split_var,
                            const int32_t* split_cut_idx, const int32_t* left, const int32_t* right,
                            const double* leaf_mu, const int32_t* cut_offsets, const double* cut_values,
@@ -344,6 +348,8 @@ int bartint_debug_export_dbarts098(const char* const* tree_strings, const double
     *n_nodes_out = f.n_nodes;
     return rc;
 }
+
+#endif  // BARTINT_TEST_HOOKS
 
 int bartint_forest_info(const bartint_forest* f, int64_t info[12]) {
     BI_REQUIRE(f != nullptr && info != nullptr, BARTINT_ERR_ARG, "NULL argument");

@@ -1,5 +1,5 @@
-"""Wrappers of the two HOST-ONLY test hooks of the C ABI (include/bartint.h: bartint_debug_export_dbarts098,
-bartint_debug_plan_soa).  They run the exporter / the group planner exactly as forest creation does but return the
+"""Wrappers of the HOST-ONLY test hooks (include/bartint_test_hooks.h: bartint_debug_export_dbarts098,
+bartint_debug_export_wbart, bartint_debug_plan_soa; compiled in with -DBARTINT_TEST_HOOKS).  They run the exporter / the group planner exactly as forest creation does but return the
 result instead of uploading it, so they work on a machine without a GPU.  Used by tests/ and tools/ only: nothing
 on the product path calls them."""
 from __future__ import annotations
@@ -8,7 +8,32 @@ import ctypes as C
 
 import numpy as np
 
-from . import _lib
+from bartint_b200 import _lib
+from bartint_b200._lib import c_double_p, c_int32_p, c_int64_p, c_uint8_p
+
+# name -> (restype, argtypes) of the hooks; applied to the loaded library on first use (the product binding table
+# bartint_b200/_lib.py covers include/bartint.h only)
+HOOK_SIGNATURES = {
+    "bartint_debug_export_wbart": (C.c_int, [C.c_char_p, C.c_int64, C.c_int32, c_int32_p, c_double_p, C.c_int64, C.c_int64,
+                                             c_int64_p, c_int64_p, c_int32_p, c_int32_p, c_int32_p, c_int32_p,
+                                             c_double_p]),
+    "bartint_debug_export_dbarts098": (C.c_int, [C.c_void_p, c_double_p, c_double_p, C.c_int64, C.c_int32, c_int32_p,
+                                                 c_double_p, C.c_int32, C.c_int32, C.c_int64, c_int64_p, c_int64_p,
+                                                 c_int32_p, c_int32_p, c_int32_p, c_int32_p, c_double_p]),
+    "bartint_debug_plan_soa": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, c_int64_p, c_int32_p, c_int32_p, c_int32_p,
+                                         c_int32_p, c_double_p, c_int32_p, c_double_p, C.c_int64, c_int64_p,
+                                         C.POINTER(C.c_uint32), c_int32_p, c_double_p, c_uint8_p, c_int32_p, c_int32_p,
+                                         c_int32_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
+                                         C.POINTER(C.c_uint32)]),
+}
+
+
+def _load():
+    lib = _lib.load()
+    for name, (res, args) in HOOK_SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    return lib
 
 
 def _p(a, ct):
@@ -18,7 +43,7 @@ def _p(a, ct):
 def export_dbarts(wire, tree_fits, x_train, cut_offsets, cut_values, want_arrays: bool = True):
     """Exporter + validation + walk-form packer + planner on the host.  wire: WireStrings.  Returns (n_nodes, dict of
     the flattened forest or None)."""
-    lib = _lib.load()
+    lib = _load()
     x_train = np.asfortranarray(np.asarray(x_train, np.float64))
     n, d = x_train.shape
     m, S = wire.m, wire.S
@@ -41,7 +66,7 @@ def export_dbarts(wire, tree_fits, x_train, cut_offsets, cut_values, want_arrays
         _p(o.get("cut"), C.c_int32), _p(o.get("left"), C.c_int32), _p(o.get("right"), C.c_int32),
         _p(o.get("mu"), C.c_double))
     if rc != 0:
-        from .forest import BartIntError
+        from bartint_b200.forest import BartIntError
         raise BartIntError(rc, lib.bartint_last_error().decode())
     if out is not None:
         for k in ("var", "cut", "left", "right", "mu"):
@@ -52,7 +77,7 @@ def export_dbarts(wire, tree_fits, x_train, cut_offsets, cut_values, want_arrays
 
 def export_wbart(trees_text, cut_lists):
     """Host phases of Forest.from_wbart (BART::wbart `treedraws$trees` text).  Returns the flattened forest."""
-    lib = _lib.load()
+    lib = _load()
     text = trees_text.encode() if isinstance(trees_text, str) else bytes(trees_text)
     d = len(cut_lists)
     coff = np.zeros(d + 1, np.int32)
@@ -69,7 +94,7 @@ def export_wbart(trees_text, cut_lists):
                                         _p(out["var"], C.c_int32), _p(out["cut"], C.c_int32), _p(out["left"], C.c_int32),
                                         _p(out["right"], C.c_int32), _p(out["mu"], C.c_double))
     if rc != 0:
-        from .forest import BartIntError
+        from bartint_b200.forest import BartIntError
         raise BartIntError(rc, lib.bartint_last_error().decode())
     S, m, nn = (int(v) for v in dims)
     out["tree_offset"] = out["tree_offset"][:S * m + 1]
@@ -81,7 +106,7 @@ def export_wbart(trees_text, cut_lists):
 
 def plan_soa(ff) -> dict:
     """The planner's output for a FlatForest: what forest creation would upload for the fast kernels."""
-    lib = _lib.load()
+    lib = _load()
     S, m, d = int(ff.S), int(ff.m), int(ff.d)
     n_trees = S * m
     toff = np.ascontiguousarray(ff.tree_offset, np.int64)
@@ -105,7 +130,7 @@ def plan_soa(ff) -> dict:
         _p(out["group_tree_off"], C.c_int32), _p(out["hdr"], C.c_uint32), _p(out["split"], C.c_uint32),
         _p(out["desc"], C.c_uint32))
     if rc != 0:
-        from .forest import BartIntError
+        from bartint_b200.forest import BartIntError
         raise BartIntError(rc, lib.bartint_last_error().decode())
     table_ok, gather, nb, regs, level, n_groups, dw, n_leaves = (int(v) for v in info)
     out.update(S=S, m=m, d=d, table_ok=bool(table_ok), gather=bool(gather), nb=nb, regs=regs, count_level=level,

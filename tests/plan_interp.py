@@ -11,7 +11,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from bartint_b200 import hosthooks
+import hosthooks
 
 FLAG_END_DRAW, FLAG_WALK, FLAG_JOINT, FLAG_COUNTABLE, FLAG_END_EVAL = 1, 2, 4, 8, 16
 LEAF_VAR = 0xFFFF

@@ -13,8 +13,8 @@ from bartint_testlib import has_gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def header_functions():
-    src = open(os.path.join(ROOT, "include", "bartint.h")).read()
+def header_functions(name="bartint.h"):
+    src = open(os.path.join(ROOT, "include", name)).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     return sorted(set(re.findall(r"\b(bartint_[a-z0-9_]+)\s*\(", src)))
 
@@ -27,6 +27,11 @@ def test_library_exports_every_header_symbol():
         assert hasattr(lib, name), f"{name} declared in include/bartint.h but not exported"
     # and the python binding table covers exactly the header
     assert sorted(_lib.SIGNATURES) == names
+    # the host-only test hooks live in their own header (and build flag), outside the drop-in surface
+    import hosthooks
+    hooks = header_functions("bartint_test_hooks.h")
+    assert hooks and all(h.startswith("bartint_debug_") for h in hooks) and not any("debug" in n for n in names)
+    assert sorted(hosthooks.HOOK_SIGNATURES) == hooks and all(hasattr(lib, h) for h in hooks)
 
 
 def test_version_and_error_string():
@@ -98,7 +103,8 @@ def test_corrupted_soa_forests_are_rejected_or_harmless():
     library either rejects the forest with a status code or the change was immaterial (a leaf's unused fields, another
     valid value) -- it never crashes, hangs or plans from a malformed tree.  Host-only hook, no device needed."""
     import numpy as np
-    from bartint_b200 import BartIntError, FlatForest, hosthooks, synth
+    import hosthooks
+    from bartint_b200 import BartIntError, FlatForest, synth
     rng = np.random.default_rng(99)
     rejected = 0
     for it in range(400):

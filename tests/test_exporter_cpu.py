@@ -5,7 +5,8 @@ the oracle's restatement node for node, for the prior's trees and for the shapes
 import numpy as np
 import pytest
 
-from bartint_b200 import BartIntError, WireStrings, hosthooks, synth
+import hosthooks
+from bartint_b200 import BartIntError, WireStrings, synth
 from oracle import oracle_np as onp
 
 

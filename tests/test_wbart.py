@@ -230,7 +230,7 @@ def test_wbart_cpp_parser_verdicts():
 
 @pytest.mark.parametrize("d", [1, 3, 10, 20])
 def test_wbart_cpp_exporter_matches_oracle_on_host(d):
-    from bartint_b200 import hosthooks
+    import hosthooks
     rng = np.random.default_rng(300 + d)
     ff = synth.prior_forest(11 + d, 9, 14, rng.random((20 * d, d)), None)
     for text in (ff.to_wbart_text(), ff.to_wbart_text().replace("\n", "\r\n")):
@@ -243,7 +243,7 @@ def test_wbart_cpp_exporter_matches_oracle_on_host(d):
 
 
 def test_wbart_cpp_exporter_kat_on_host():
-    from bartint_b200 import hosthooks
+    import hosthooks
     got = hosthooks.export_wbart(KAT_TEXT, KAT_CUTS)
     ref = onp.forest_from_wbart(KAT_TEXT, KAT_CUTS, offset=KAT_OFFSET)
     for k in ("tree_offset", "var", "cut", "left", "right", "mu"):
@@ -252,7 +252,8 @@ def test_wbart_cpp_exporter_kat_on_host():
 
 def test_mutated_wbart_text_never_crashes_the_parser():
     """Seeded byte-level mutations of a valid treedraws text: a parse / argument error or a structurally valid forest."""
-    from bartint_b200 import BartIntError, hosthooks
+    import hosthooks
+    from bartint_b200 import BartIntError
     rng = np.random.default_rng(55)
     ff = synth.prior_forest(55, 3, 5, rng.random((30, 3)), None)
     text = ff.to_wbart_text()

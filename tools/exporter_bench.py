@@ -14,7 +14,9 @@ import time
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from bartint_b200 import WireStrings, _lib, hosthooks, synth  # noqa: E402
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+import hosthooks  # noqa: E402   (tests/hosthooks.py: the host-only hooks of include/bartint_test_hooks.h)
+from bartint_b200 import WireStrings, _lib, synth  # noqa: E402
 
 
 def main():
