@@ -207,6 +207,32 @@ int bartint_forest_from_wbart(const char* trees_text, int64_t text_len, int32_t 
 
 int bartint_forest_route(const bartint_forest* f) { return f ? f->route : -1; }
 
+int bartint_forest_from_value_splits(int32_t S, int32_t m, int32_t d, const int64_t* tree_node_offset,
+                                     const int32_t* split_var, const double* value, const int32_t* left,
+                                     const int32_t* right, int32_t route, double leaf_scale, double offset,
+                                     bartint_forest** out) {
+    BI_REQUIRE(out != nullptr, BARTINT_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    BI_REQUIRE(route == BARTINT_ROUTE_DBARTS || route == BARTINT_ROUTE_BART, BARTINT_ERR_ARG, "unknown routing rule %d", route);
+    BI_REQUIRE(S >= 0 && m >= 0 && d >= 0, BARTINT_ERR_ARG, "S, m and d must be >= 0");
+    BI_REQUIRE(tree_node_offset != nullptr, BARTINT_ERR_ARG, "tree_node_offset is NULL");
+    BI_REQUIRE((int64_t)S * m == 0 || (split_var && value), BARTINT_ERR_ARG, "node arrays must not be NULL");
+    BI_REQUIRE((left == nullptr) == (right == nullptr), BARTINT_ERR_ARG, "left and right must both be given or both be NULL");
+    bartint_forest* f = new (std::nothrow) bartint_forest();
+    BI_REQUIRE(f != nullptr, BARTINT_ERR_NOMEM, "out of host memory");
+    f->S = S; f->m = m; f->d = d; f->y_min = offset - 0.5; f->y_max = offset + 0.5; f->route = route;
+    int rc = value_splits_to_soa(S, m, d, tree_node_offset, split_var, value, left, right, leaf_scale, f);
+    if (rc) { delete f; return rc; }
+    return finish_forest(f, out);
+}
+
+int bartint_forest_cutpoints(const bartint_forest* f, int32_t* cut_offsets, double* cut_values) {
+    BI_REQUIRE(f != nullptr, BARTINT_ERR_ARG, "forest is NULL");
+    if (cut_offsets) memcpy(cut_offsets, f->cut_off.data(), f->cut_off.size() * sizeof(int32_t));
+    if (cut_values && !f->cut_val.empty()) memcpy(cut_values, f->cut_val.data(), f->cut_val.size() * sizeof(double));
+    return BARTINT_OK;
+}
+
 int bartint_forest_from_soa_routed(int32_t S, int32_t m, int32_t d, const int64_t* tree_node_offset,
                                    const int32_t* split_var, const int32_t* split_cut_idx, const int32_t* left,
                                    const int32_t* right, const double* leaf_mu, const int32_t* cut_offsets,
@@ -323,6 +349,23 @@ int bartint_debug_export_wbart(const char* trees_text, int64_t text_len, int32_t
                                right, leaf_mu);
     dims_out[0] = f.S; dims_out[1] = f.m; dims_out[2] = f.n_nodes;
     return rc;
+}
+
+int bartint_debug_export_value_splits(int32_t S, int32_t m, int32_t d, const int64_t* tree_node_offset,
+                                      const int32_t* split_var, const double* value, const int32_t* left,
+                                      const int32_t* right, double leaf_scale, int64_t* tree_node_offset_out,
+                                      int32_t* var_out, int32_t* cut_out, int32_t* left_out, int32_t* right_out,
+                                      double* leaf_mu_out, int32_t* cut_offsets_out, double* cut_values_out) {
+    BI_REQUIRE(tree_node_offset != nullptr && (int64_t)S * m >= 0, BARTINT_ERR_ARG, "bad arguments");
+    BI_REQUIRE((left == nullptr) == (right == nullptr), BARTINT_ERR_ARG, "left and right must both be given or both be NULL");
+    bartint_forest f;                       // never uploaded: no device state to release
+    f.S = S; f.m = m; f.d = d;
+    int rc = value_splits_to_soa(S, m, d, tree_node_offset, split_var, value, left, right, leaf_scale, &f);
+    if (rc) return rc;
+    if (cut_offsets_out) memcpy(cut_offsets_out, f.cut_off.data(), f.cut_off.size() * sizeof(int32_t));
+    if (cut_values_out && !f.cut_val.empty()) memcpy(cut_values_out, f.cut_val.data(), f.cut_val.size() * sizeof(double));
+    return debug_finish_and_copy(f, (int64_t)S * m, tree_node_offset[(int64_t)S * m], tree_node_offset_out, var_out, cut_out,
+                                 left_out, right_out, leaf_mu_out);
 }
 
 int bartint_debug_export_dbarts098(const char* const* tree_strings, const double* tree_fits, const double* x_train,
@@ -514,8 +557,11 @@ static int stage_rows(const double* X, int64_t N, int64_t ld, int32_t d, int dev
             s->host_X = X;
             for (int b = 0; b < s->n_blocks && e == cudaSuccess; ++b)
                 e = cudaEventCreateWithFlags(&s->block_done[b], cudaEventDisableTiming);
+            // two of the four blocks travel at once (about as long as the export of the first draw chunk takes); the
+            // rest follows the first forest upload, which must not queue behind the whole matrix on the copy engine
             if (e == cudaSuccess) e = staged_submit_block(s, 0);
-            s->submitted = 1;
+            if (e == cudaSuccess) e = staged_submit_block(s, 1);
+            s->submitted = 2;
         } else if (ld == N) {
             e = cudaMemcpyAsync(s->dX, X, sizeof(double) * (size_t)(N * d), cudaMemcpyHostToDevice, s->copy_stream);
         } else {
@@ -548,7 +594,13 @@ int bartint_stage_matrix(const double* X, int64_t N, int32_t d, int device, bart
     for (int g = 1; g < G; ++g) {
         const int64_t lo = box->shard_lo[(size_t)g], rows = box->shard_lo[(size_t)g + 1] - lo;
         bartint_staged** slot = &box->shards[(size_t)g];
-        group_post(g, [=] { return stage_rows(X + lo, rows, N, d, group_device(g), slot); });
+        // (the members other than 0 receive their forests over NVLink, not over the bus: nothing has to overtake the
+        //  matrix on their copy engines, so the whole shard is put on the bus at once)
+        group_post(g, [=] {
+            int r = stage_rows(X + lo, rows, N, d, group_device(g), slot);
+            if (r == BARTINT_OK && *slot != nullptr && staged_submit_rest(*slot) != cudaSuccess) r = BARTINT_ERR_CUDA;
+            return r;
+        });
     }
     rc = stage_rows(X, box->shard_lo[1], N, d, group_device(0), &box->shards[0]);
     const int rc2 = group_wait();

@@ -219,6 +219,8 @@ int parse_dbarts_forest(const char* const* tree_strings, const double* tree_fits
                         int64_t n, int32_t d, const int32_t* cut_offsets, const double* cut_values,
                         int32_t m, int32_t S, bartint_forest* f);
 int parse_wbart_forest(const char* text, int64_t len, int32_t d, bartint_forest* f);
+int value_splits_to_soa(int32_t S, int32_t m, int32_t d, const int64_t* off, const int32_t* var, const double* value,
+                        const int32_t* left, const int32_t* right, double leaf_scale, bartint_forest* f);
 int canonicalise_soa(int32_t S, int32_t m, int32_t d, const int64_t* tree_node_offset, const int32_t* split_var,
                      const int32_t* split_cut_idx, const int32_t* left, const int32_t* right,
                      const double* leaf_mu, bartint_forest* f);

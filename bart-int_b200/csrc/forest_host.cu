@@ -458,6 +458,80 @@ int canonicalise_soa(int32_t S, int32_t m, int32_t d, const int64_t* off, const 
     return BARTINT_OK;
 }
 
+// Forests whose splits are given as VALUES (dbarts >= 0.9-9 `fit$getTrees()` / `extract(fit, "trees")` data frames,
+// bartMachine's raw node data): the cut-point lists are built from the split values themselves -- per variable the
+// sorted distinct values used anywhere in the posterior -- so routing on the resulting codes is exact for the
+// package's own comparison (x <= c or x < c) whatever grid the package drew its cuts from.  left / right may be NULL:
+// the nodes of a tree are then in pre-order (a node's left child is the next node).  Leaf values are multiplied by
+// leaf_scale.  Fills f's canonical SoA and cut lists.
+int value_splits_to_soa(int32_t S, int32_t m, int32_t d, const int64_t* off, const int32_t* var, const double* value,
+                        const int32_t* left, const int32_t* right, double leaf_scale, bartint_forest* f) {
+    const int64_t n_trees = (int64_t)S * m;
+    BI_REQUIRE(off[0] == 0, BARTINT_ERR_ARG, "tree_node_offset[0] must be 0");
+    for (int64_t k = 0; k < n_trees; ++k)
+        BI_REQUIRE(off[k + 1] > off[k], BARTINT_ERR_ARG, "tree %lld has no nodes", (long long)k);
+    const int64_t nn = off[n_trees];
+    // 1. per variable: sorted distinct split values
+    std::vector<std::vector<double>> cuts((size_t)d);
+    for (int64_t g = 0; g < nn; ++g) {
+        if (var[g] < 0) continue;
+        BI_REQUIRE(var[g] < d, BARTINT_ERR_ARG, "node %lld splits on variable %d but the model has %d", (long long)g, var[g], d);
+        BI_REQUIRE(value[g] == value[g], BARTINT_ERR_ARG, "node %lld has a NaN split value", (long long)g);
+        cuts[(size_t)var[g]].push_back(value[g]);
+    }
+    f->cut_off.assign((size_t)d + 1, 0);
+    f->cut_val.clear();
+    for (int32_t j = 0; j < d; ++j) {
+        std::vector<double>& c = cuts[(size_t)j];
+        std::sort(c.begin(), c.end());
+        c.erase(std::unique(c.begin(), c.end()), c.end());
+        BI_REQUIRE(c.size() <= 255, BARTINT_ERR_UNSUPPORTED,
+                   "variable %d is split at %zu distinct values; codes are uint8 (at most 255 cut points per variable)", j, c.size());
+        f->cut_val.insert(f->cut_val.end(), c.begin(), c.end());
+        f->cut_off[(size_t)j + 1] = (int32_t)f->cut_val.size();
+    }
+    // 2. children (explicit, or implied by pre-order) and cut indices
+    std::vector<int32_t> cut((size_t)nn, 0), lft, rgt;
+    std::vector<double> mu((size_t)nn, 0.0);
+    const bool implied = left == nullptr || right == nullptr;
+    if (implied) { lft.assign((size_t)nn, -1); rgt.assign((size_t)nn, -1); }
+    int bad = 0;
+#pragma omp parallel for schedule(static)
+    for (int64_t k = 0; k < n_trees; ++k) {
+        const int64_t base = off[k];
+        const int32_t cnt = (int32_t)(off[k + 1] - base);
+        if (implied) {                      // pre-order: the right child of a node follows its whole left subtree
+            std::vector<int32_t> pend;      // internal nodes waiting for their right child
+            for (int32_t a = 0; a < cnt; ++a) {
+                if (var[base + a] >= 0) {
+                    if (a + 1 >= cnt) { bad = 1; break; }
+                    lft[(size_t)(base + a)] = a + 1;
+                    pend.push_back(a);
+                } else if (!pend.empty()) {
+                    if (a + 1 >= cnt) { bad = 1; break; }
+                    rgt[(size_t)(base + pend.back())] = a + 1;
+                    pend.pop_back();
+                } else if (a + 1 != cnt) {
+                    bad = 1;                // nodes after the tree is complete
+                    break;
+                }
+            }
+            if (!pend.empty()) bad = 1;
+        }
+        for (int32_t a = 0; a < cnt; ++a) {
+            const int64_t g = base + a;
+            if (var[g] >= 0) {
+                const std::vector<double>& c = cuts[(size_t)var[g]];
+                cut[(size_t)g] = (int32_t)(std::lower_bound(c.begin(), c.end(), value[g]) - c.begin());
+            } else {
+                mu[(size_t)g] = leaf_scale * value[g];
+            }
+        }
+    }
+    BI_REQUIRE(!bad, BARTINT_ERR_ARG, "node arrays are not complete binary trees in pre-order");
+    return canonicalise_soa(S, m, d, off, var, cut.data(), implied ? lft.data() : left, implied ? rgt.data() : right, mu.data(), f);
+}
+
 int forest_finish_host(bartint_forest* f) {
     PhaseTimer pt;
     const int64_t n_trees = (int64_t)f->S * f->m;

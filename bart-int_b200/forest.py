@@ -295,6 +295,32 @@ class Forest:
         return f
 
     @classmethod
+    def from_value_splits(cls, S, m, d, tree_offset, var, value, left=None, right=None, route=0, leaf_scale=1.0,
+                          offset=0.0) -> "Forest":
+        """Exporter for trees given with split VALUES (dbarts >= 0.9-9 ``fit$getTrees()``, bartMachine raw node data):
+        var[g] = -1 marks a leaf, value[g] is the split value or the leaf prediction; left/right None = pre-order."""
+        toff = np.ascontiguousarray(tree_offset, np.int64)
+        var = np.ascontiguousarray(var, np.int32)
+        value = np.ascontiguousarray(value, np.float64)
+        lft = None if left is None else np.ascontiguousarray(left, np.int32)
+        rgt = None if right is None else np.ascontiguousarray(right, np.int32)
+        h = C.c_void_p()
+        _check(_lib.load().bartint_forest_from_value_splits(int(S), int(m), int(d), _p(toff, C.c_int64), _p(var, C.c_int32),
+                                                            _p(value, C.c_double), _p(lft, C.c_int32), _p(rgt, C.c_int32),
+                                                            int(route), float(leaf_scale), float(offset), C.byref(h)))
+        f = cls(h.value)
+        f.y_min, f.y_max = float(offset) - 0.5, float(offset) + 0.5
+        return f
+
+    def cutpoints(self):
+        """The forest's cut-point lists (one ascending array per variable)."""
+        off = np.zeros(self.d + 1, np.int32)
+        _check(_lib.load().bartint_forest_cutpoints(self._h, _p(off, C.c_int32), None))
+        val = np.zeros(max(int(off[-1]), 1))
+        _check(_lib.load().bartint_forest_cutpoints(self._h, _p(off, C.c_int32), _p(val, C.c_double)))
+        return [val[off[j]:off[j + 1]].copy() for j in range(self.d)]
+
+    @classmethod
     def from_dbarts(cls, tree_strings, tree_fits, x_train, cut_lists, y_min, y_max) -> "Forest":
         """Exporter: dbarts 0.9-8 saved state -> HBM forest (getTree, BARTInt.R:92-133, for all trees).
 

@@ -118,6 +118,25 @@ int bartint_forest_from_soa_routed(int32_t S, int32_t m, int32_t d, const int64_
                                    bartint_forest** out);
 int bartint_forest_route(const bartint_forest* f);
 
+/* Exporter for packages that expose their trees with split VALUES instead of cut indices:
+ *   dbarts >= 0.9-9   fit$getTrees() / extract(fit, "trees"): one row per node in pre-order, columns sample, tree, var
+ *                     (-1 = leaf), value (split value | leaf prediction); the string format of 0.9-8 that
+ *                     getTree() (src/BARTInt.R:92-133) parses no longer exists there (README.md:102-106);
+ *   bartMachine       extract_raw_node_data(): nested nodes with splitAttributeM, splitValue, y_pred (README.md:202).
+ * value[g] is the split value of an internal node and the leaf prediction of a leaf (split_var[g] = -1).  left/right
+ * are node indices relative to the tree's first node, or both NULL when the nodes of every tree are in pre-order.
+ * The cut-point lists become, per variable, the sorted distinct split values of the posterior (at most 255 each);
+ * bartint_forest_cutpoints reads them back.  predict = offset + leaf_scale * sum_t leaf value; route as below
+ * (bartMachine and dbarts: left iff x <= split).  The R side checks (leaf_scale, offset) against the package's own
+ * predict() on a few rows when the forest is built (bart-int_b200/R/bartint.R). */
+int bartint_forest_from_value_splits(int32_t S, int32_t m, int32_t d, const int64_t* tree_node_offset,
+                                     const int32_t* split_var, const double* value, const int32_t* left,
+                                     const int32_t* right, int32_t route, double leaf_scale, double offset,
+                                     bartint_forest** out);
+/* cut_offsets [d + 1], cut_values [cut_offsets[d]] of a forest (either may be NULL); sizes from a first call with
+ * cut_values = NULL. */
+int bartint_forest_cutpoints(const bartint_forest* f, int32_t* cut_offsets, double* cut_values);
+
 /* Exporter for BART::wbart / pbart fits (the reference's README.md:202 invites swapping
  * the BART package).  trees_text = fit$treedraws$trees, a NUL-terminated string: "ndpost ntree p\n", then draw by
  * draw and tree by tree a line with the node count followed by one line "nid var cut theta" per node (heap node ids:

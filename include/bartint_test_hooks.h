@@ -55,6 +55,16 @@ int bartint_debug_export_wbart(const char* trees_text, int64_t text_len, int32_t
                                int64_t dims_out[3], int64_t* tree_node_offset, int32_t* split_var,
                                int32_t* split_cut_idx, int32_t* left, int32_t* right, double* leaf_mu);
 
+/* Test hook, HOST ONLY: the value-split exporter of bartint_forest_from_value_splits (cut-point lists from the distinct
+ * split values, cut indices, pre-order children) plus the host phases of forest creation, without touching a device.
+ * Outputs sized by the caller: node arrays [tree_node_offset[S m]], cut_offsets_out [d + 1], cut_values_out [number of
+ * internal nodes] (an upper bound). */
+int bartint_debug_export_value_splits(int32_t S, int32_t m, int32_t d, const int64_t* tree_node_offset,
+                                      const int32_t* split_var, const double* value, const int32_t* left,
+                                      const int32_t* right, double leaf_scale, int64_t* tree_node_offset_out,
+                                      int32_t* var_out, int32_t* cut_out, int32_t* left_out, int32_t* right_out,
+                                      double* leaf_mu_out, int32_t* cut_offsets_out, double* cut_values_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -543,6 +543,53 @@ def forest_from_wbart(trees_text, cut_lists, offset=0.0):
                            y_min=float(offset) - 0.5, y_max=float(offset) + 0.5, route=ROUTE_BART)
 
 
+def forest_from_value_splits(S, m, d, tree_offset, var, value, left=None, right=None, route=ROUTE_DBARTS, leaf_scale=1.0,
+                             offset=0.0):
+    """Flat forest from trees whose splits are VALUES [dbarts-mem / bartMachine-mem] -- what newer BART packages hand
+    out instead of the dbarts 0.9-8 tree strings that getTree() (src/BARTInt.R:92-133) parses:
+
+      dbarts >= 0.9-9   ``fit$getTrees()``: data frame, one row per node in pre-order, columns sample, tree, n,
+                        var (-1 = leaf), value (split value | leaf prediction);
+      bartMachine       ``extract_raw_node_data``: nested nodes (splitAttributeM, splitValue, y_pred, left, right).
+
+    A point goes left iff x <= split value (route 0; dbarts and bartMachine) or x < split value (route 1).  The cut
+    lists are, per variable, the sorted distinct split values, so "x > value" <=> "code > index of value".
+    predict = offset + leaf_scale * sum_t leaf value, written with the dbarts rescale by ymin = offset - 0.5.
+    left/right None: nodes are in pre-order (left child = next node, right child after the left subtree)."""
+    tree_offset = np.asarray(tree_offset, np.int64)
+    var = np.asarray(var, np.int32)
+    value = np.asarray(value, np.float64)
+    nn = int(tree_offset[-1])
+    cut_lists = [np.unique(value[(var == j)]) for j in range(d)]
+    if left is None:
+        left = np.full(nn, -1, np.int32)
+        right = np.full(nn, -1, np.int32)
+        for k in range(S * m):
+            b, e = int(tree_offset[k]), int(tree_offset[k + 1])
+            pend = []
+            for a in range(e - b):
+                if var[b + a] >= 0:
+                    left[b + a] = a + 1
+                    pend.append(a)
+                elif pend:
+                    right[b + pend.pop()] = a + 1
+            if pend or any(right[b + a] >= e - b or left[b + a] >= e - b for a in range(e - b)):
+                raise ValueError("tree %d is not a complete binary tree in pre-order" % k)
+    cut = np.zeros(nn, np.int32)
+    mu = np.zeros(nn)
+    for g in range(nn):
+        if var[g] >= 0:
+            cut[g] = int(np.searchsorted(cut_lists[var[g]], value[g]))
+        else:
+            mu[g] = leaf_scale * value[g]
+    cut_offsets = np.zeros(d + 1, np.int32)
+    cut_offsets[1:] = np.cumsum([len(c) for c in cut_lists])
+    cut_values = np.concatenate(cut_lists) if d else np.zeros(0)
+    return SimpleNamespace(S=S, m=m, d=d, tree_offset=tree_offset, var=var, cut=cut, left=np.asarray(left, np.int32),
+                           right=np.asarray(right, np.int32), mu=mu, cut_offsets=cut_offsets, cut_values=cut_values,
+                           y_min=float(offset) - 0.5, y_max=float(offset) + 0.5, route=int(route))
+
+
 def wbart_trees_text(forest) -> str:
     """Inverse of forest_from_wbart: writes a flat forest in the treedraws$trees text format (heap node ids, nodes in
     pre-order as tree::getnodes lists them; theta of internal nodes written as 0)."""

@@ -25,6 +25,9 @@ HOOK_SIGNATURES = {
                                          C.POINTER(C.c_uint32), c_int32_p, c_double_p, c_uint8_p, c_int32_p, c_int32_p,
                                          c_int32_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
                                          C.POINTER(C.c_uint32)]),
+    "bartint_debug_export_value_splits": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, c_int64_p, c_int32_p, c_double_p, c_int32_p,
+                                                    c_int32_p, C.c_double, c_int64_p, c_int32_p, c_int32_p, c_int32_p, c_int32_p,
+                                                    c_double_p, c_int32_p, c_double_p]),
 }
 
 
@@ -141,4 +144,30 @@ def plan_soa(ff) -> dict:
     for k in ("hdr", "split"):
         out[k] = out[k][:n_groups]
     out["group_tree_off"] = out["group_tree_off"][:n_groups + 1]
+    return out
+
+
+def export_value_splits(S, m, d, tree_offset, var, value, left=None, right=None, leaf_scale=1.0) -> dict:
+    """The value-split exporter on the host: canonical pre-order SoA with cut indices + the cut lists it built."""
+    lib = _load()
+    toff = np.ascontiguousarray(tree_offset, np.int64)
+    var = np.ascontiguousarray(var, np.int32)
+    value = np.ascontiguousarray(value, np.float64)
+    lft = None if left is None else np.ascontiguousarray(left, np.int32)
+    rgt = None if right is None else np.ascontiguousarray(right, np.int32)
+    nn = int(toff[-1])
+    out = dict(tree_offset=np.zeros(S * m + 1, np.int64), var=np.zeros(max(nn, 1), np.int32), cut=np.zeros(max(nn, 1), np.int32),
+               left=np.zeros(max(nn, 1), np.int32), right=np.zeros(max(nn, 1), np.int32), mu=np.zeros(max(nn, 1)),
+               cut_offsets=np.zeros(d + 1, np.int32), cut_values=np.zeros(max(nn, 1)))
+    rc = lib.bartint_debug_export_value_splits(S, m, d, _p(toff, C.c_int64), _p(var, C.c_int32), _p(value, C.c_double),
+                                               _p(lft, C.c_int32), _p(rgt, C.c_int32), float(leaf_scale),
+                                               _p(out["tree_offset"], C.c_int64), _p(out["var"], C.c_int32), _p(out["cut"], C.c_int32),
+                                               _p(out["left"], C.c_int32), _p(out["right"], C.c_int32), _p(out["mu"], C.c_double),
+                                               _p(out["cut_offsets"], C.c_int32), _p(out["cut_values"], C.c_double))
+    if rc != 0:
+        from bartint_b200.forest import BartIntError
+        raise BartIntError(rc, lib.bartint_last_error().decode())
+    for k in ("var", "cut", "left", "right", "mu"):
+        out[k] = out[k][:nn]
+    out["cut_values"] = out["cut_values"][:int(out["cut_offsets"][-1])]
     return out
