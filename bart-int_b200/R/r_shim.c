@@ -59,9 +59,12 @@ SEXP bartint_R_forest(SEXP trees, SEXP fits, SEXP x, SEXP cuts, SEXP ymin, SEXP 
 }
 
 /* .Call("bartint_R_forest_wbart", fit$treedraws$trees (chr 1), fit$treedraws$cutpoints (list of p numeric),
- *       fit$offset)  -> external pointer.   For fits made with BART::wbart / pbart instead of dbarts
- * (the reference's README.md:202 invites swapping the BART package); routing follows tree::bn (left iff x < cut). */
-SEXP bartint_R_forest_wbart(SEXP trees, SEXP cuts, SEXP offset) {
+ *       fit$offset, fit$mu, fit$binaryOffset)  -> external pointer.   For fits made with the BART package instead of
+ * dbarts (the reference's README.md:202 invites swapping the BART package); routing follows tree::bn (left iff
+ * x < cut).  The centring constant predict() adds is fit$mu for wbart, fit$offset for gbart and fit$binaryOffset for
+ * pbart [BART-mem]: the first of the three that is not NULL is used, and it is an error if all are -- silently
+ * assuming 0 would shift every prediction, draw mean and integral by mean(y.train). */
+SEXP bartint_R_forest_wbart(SEXP trees, SEXP cuts, SEXP offset, SEXP mu, SEXP binary_offset) {
     const int d = (int)XLENGTH(cuts);
     int32_t* off = (int32_t*)R_alloc((size_t)d + 1, sizeof(int32_t));
     off[0] = 0;
@@ -71,12 +74,61 @@ SEXP bartint_R_forest_wbart(SEXP trees, SEXP cuts, SEXP offset) {
         const double* c = REAL(VECTOR_ELT(cuts, j));
         for (int k = 0; k < off[j + 1] - off[j]; ++k) vals[off[j] + k] = c[k];
     }
+    SEXP centre = !Rf_isNull(offset) ? offset : !Rf_isNull(mu) ? mu : binary_offset;
+    if (Rf_isNull(centre)) Rf_error("bartint: the fit has none of $offset, $mu, $binaryOffset: cannot tell what predict() adds to the tree sums");
     bartint_forest* f = NULL;
-    check(bartint_forest_from_wbart(CHAR(STRING_ELT(trees, 0)), 0, d, off, vals, Rf_asReal(offset), &f));
+    check(bartint_forest_from_wbart(CHAR(STRING_ELT(trees, 0)), 0, d, off, vals, Rf_asReal(centre), &f));
     SEXP ptr = PROTECT(R_MakeExternalPtr(f, R_NilValue, R_NilValue));
     R_RegisterCFinalizerEx(ptr, forest_finalizer, TRUE);
     UNPROTECT(1);
     return ptr;
+}
+
+/* .Call("bartint_R_forest_values", S, m, d, tree_node_offset (dbl S*m+1), var (int, -1 = leaf, 0-based), value (dbl),
+ *       left, right (int or NULL: pre-order), route, leaf_scale, offset)  -> external pointer.
+ * Trees exported with split VALUES: dbarts >= 0.9-9 fit$getTrees(), bartMachine::extract_raw_node_data (README.md:
+ * 102-106, :202); see bartint_forest_from_value_splits. */
+SEXP bartint_R_forest_values(SEXP S, SEXP m, SEXP d, SEXP offs, SEXP var, SEXP value, SEXP left, SEXP right, SEXP route,
+                             SEXP leaf_scale, SEXP offset) {
+    const R_xlen_t nt = XLENGTH(offs);
+    int64_t* off = (int64_t*)R_alloc((size_t)nt, sizeof(int64_t));
+    for (R_xlen_t k = 0; k < nt; ++k) off[k] = (int64_t)REAL(offs)[k];
+    if (nt != (R_xlen_t)Rf_asInteger(S) * Rf_asInteger(m) + 1 || off[nt - 1] != (int64_t)XLENGTH(var) || XLENGTH(var) != XLENGTH(value))
+        Rf_error("bartint: tree offsets, var and value do not describe S * m trees");
+    const int has_children = !Rf_isNull(left) && !Rf_isNull(right);
+    bartint_forest* f = NULL;
+    check(bartint_forest_from_value_splits(Rf_asInteger(S), Rf_asInteger(m), Rf_asInteger(d), off, INTEGER(var), REAL(value),
+                                           has_children ? INTEGER(left) : NULL, has_children ? INTEGER(right) : NULL,
+                                           Rf_asInteger(route), Rf_asReal(leaf_scale), Rf_asReal(offset), &f));
+    SEXP ptr = PROTECT(R_MakeExternalPtr(f, R_NilValue, R_NilValue));
+    R_RegisterCFinalizerEx(ptr, forest_finalizer, TRUE);
+    UNPROTECT(1);
+    return ptr;
+}
+
+/* bartint_init(n_gpus): open the device group (all GPUs behind this one R process).  Returns the group size. */
+SEXP bartint_R_init(SEXP n_gpus) {
+    check(bartint_init(Rf_asInteger(n_gpus)));
+    return Rf_ScalarInteger(bartint_group_size());
+}
+
+/* release a forest handle now (the finalizer then finds it cleared) */
+SEXP bartint_R_release(SEXP ptr) {
+    forest_finalizer(ptr);
+    return R_NilValue;
+}
+
+/* order(values, decreasing = TRUE)[1:k], 0-based (-1 once the non-NaN values are exhausted) */
+SEXP bartint_R_topk(SEXP values, SEXP k) {
+    const int kk = Rf_asInteger(k);
+    SEXP out = PROTECT(Rf_allocVector(INTSXP, kk > 0 ? kk : 0));
+    if (kk > 0) {
+        int64_t* idx = (int64_t*)R_alloc((size_t)kk, sizeof(int64_t));
+        check(bartint_topk(REAL(values), (int64_t)XLENGTH(values), kk, idx, NULL));
+        for (int r = 0; r < kk; ++r) INTEGER(out)[r] = (int)idx[r];
+    }
+    UNPROTECT(1);
+    return out;
 }
 
 /* sampleIntegrals(model, dim, measure): src/BARTInt.R:204-223.  n_draws_used <= 0 -> all draws. */
@@ -135,7 +187,9 @@ SEXP bartint_R_design_step(SEXP trees, SEXP fits, SEXP x, SEXP cuts, SEXP ymin, 
         const double* c = REAL(VECTOR_ELT(cuts, j));
         for (int k = 0; k < off[j + 1] - off[j]; ++k) vals[off[j] + k] = c[k];
     }
-    int device = 0;
+    const int device = 0;
+    /* after bartint_init() the rows of X are sharded over every GPU of the group (one call still drives them all) */
+    const int x_device = bartint_group_size() > 1 ? BARTINT_DEVICE_GROUP : device;
     bartint_staged *sc = NULL, *sx = NULL;
     int64_t C = 0;
     if (!Rf_isNull(cand)) {
@@ -143,7 +197,7 @@ SEXP bartint_R_design_step(SEXP trees, SEXP fits, SEXP x, SEXP cuts, SEXP ymin, 
         check(bartint_stage_matrix(REAL(cand), C, d, device, &sc));
     }
     if (!Rf_isNull(X)) {
-        const int rc = bartint_stage_matrix(REAL(X), INTEGER(Rf_getAttrib(X, R_DimSymbol))[0], d, device, &sx);
+        const int rc = bartint_stage_matrix(REAL(X), INTEGER(Rf_getAttrib(X, R_DimSymbol))[0], d, x_device, &sx);
         if (rc != BARTINT_OK) { bartint_staged_free(sc); check(rc); }
     }
     int n_int = Rf_asInteger(n_draws_integral);

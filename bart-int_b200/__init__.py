@@ -11,8 +11,8 @@ Layout
   R/               the .Call shim sources a BART-Int maintainer adds (not buildable here: no R)
 """
 from .forest import (FlatForest, Forest, Points, StagedMatrix, WireStrings, BartIntError,  # noqa: F401
-                     design_step_dbarts, init_group, group_size, group_exchange, shutdown_group)
+                     design_step_dbarts, init_group, group_size, group_exchange, shutdown_group, topk)
 from . import api, synth  # noqa: F401
 
 __all__ = ["FlatForest", "Forest", "Points", "StagedMatrix", "WireStrings", "BartIntError", "design_step_dbarts", "init_group",
-           "group_size", "group_exchange", "shutdown_group", "api", "synth"]
+           "group_size", "group_exchange", "shutdown_group", "topk", "api", "synth"]

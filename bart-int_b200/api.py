@@ -156,18 +156,41 @@ def r_sample_one(v: np.ndarray, rng) -> int:
     return int(v[rng.integers(0, v.size)])
 
 
-def _candidates(measure: str, dim: int, n: int, rng):
-    """BARTInt.R:299-309: candidate set and weights (weights quirks B4 kept: uniform -> 1)."""
+def _candidates(measure: str, dim: int, n: int, rng, refcompat: bool = True):
+    """BARTInt.R:299-309: candidate set and weights.
+
+    refcompat=True returns the weights OBJECT the reference builds, quirks included; `_pick` applies
+    R's recycling to it:
+      gaussian     `dtnorm(candidateSet, ...)` is a C x d MATRIX, not a length-C vector;
+      exponential  `colMeans(dexp(candidateSet))` has length d, not C.
+    refcompat=False returns the per-candidate density (product over the coordinates), length C -- what the paper's text
+    describes."""
     X = synth.sample_measure(rng, measure, n, dim)
     if measure == "uniform":
         return X, np.ones(1)
     if measure == "gaussian":
-        # dtnorm(candidateSet, mean=0.5, lower=0, upper=1) is a C x d MATRIX in the reference; only its first
-        # column lines up with var by recycling when d == 1.  Use the per-candidate density product.
         from scipy.special import ndtr
         dens = np.exp(-0.5 * (X - 0.5) ** 2) / math.sqrt(2 * math.pi) / (ndtr(0.5) - ndtr(-0.5))
-        return X, dens.prod(axis=1)
-    return X, np.full(1, float(np.exp(-X).mean()))
+        return X, (dens if refcompat else dens.prod(axis=1))
+    return X, (np.exp(-X).mean(axis=0) if refcompat else np.exp(-X.sum(axis=1)))
+
+
+def _pick(var_unweighted: np.ndarray, weights: np.ndarray, rng) -> int:
+    """`var <- colVars(fValues) * weights; index <- sample(which(var == max(var)), 1)` (BARTInt.R:314-315) with R's
+    recycling of whatever shape `weights` has; returns the 1-based index R would use in `candidateSet[index, ]`.
+
+    length 1 or C: plain product.  Length d (exponential quirk): weights[i mod d].  C x d matrix (gaussian quirk): the
+    product is a C x d matrix (var recycled down the columns) and `which` returns LINEAR indices into it; an index
+    beyond C makes `candidateSet[index, ]` fail in R ("subscript out of bounds") -- here the candidate of that row is
+    taken instead, which is what R picks whenever it does not fail."""
+    C_ = var_unweighted.size
+    w = np.asarray(weights, np.float64)
+    if w.ndim == 2:                                   # C x d, column-major linear indices like R
+        prod = (var_unweighted[:, None] * w).ravel(order="F")
+    else:
+        prod = var_unweighted * np.resize(w, C_)
+    lin = r_sample_one(np.nonzero(prod == prod.max())[0] + 1, rng)       # quirk B2 inside
+    return (lin - 1) % C_ + 1
 
 
 def BARTInt(dim, trainX, trainY, numNewTraining, FUN, sequential, measure, save_posterior=False,
@@ -199,8 +222,8 @@ def BARTInt(dim, trainX, trainY, numNewTraining, FUN, sequential, measure, save_
             continue
         candidateSet, weights = _candidates(measure, dim, 100, rng)              # :299-309
         if sequential:
-            var = bartint_candidate_var(model, candidateSet, weights)            # :312-314
-            index = r_sample_one(np.nonzero(var == var.max())[0] + 1, rng)       # :315 (quirk B2)
+            var = bartint_candidate_var(model, candidateSet, 1.0)                # :312-314 (colVars; the weights follow)
+            index = _pick(var, weights, rng)                                     # :314-315 (quirks B2, B4)
         else:
             index = int(rng.integers(1, 101))                                    # :318
         value = float(np.asarray(FUN(candidateSet[index - 1:index, :])).ravel()[0])   # :320

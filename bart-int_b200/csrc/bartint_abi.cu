@@ -824,6 +824,31 @@ int bartint_argmax_ties_device(const double* d_values, int64_t n, int64_t* d_out
     return launch_argmax_ties(d_values, n, d_out, (cudaStream_t)stream);
 }
 
+int bartint_topk_device(const double* d_values, int64_t n, int32_t k, int64_t* d_index_out, double* d_value_out, void* stream) {
+    BI_REQUIRE(k >= 0 && n >= 0 && (n == 0 || d_values != nullptr) && (k == 0 || d_index_out != nullptr), BARTINT_ERR_ARG, "bad arguments");
+    return launch_topk(d_values, n, k, d_index_out, d_value_out, (cudaStream_t)stream);
+}
+
+int bartint_topk(const double* values, int64_t n, int32_t k, int64_t* index_out, double* value_out) {
+    BI_REQUIRE(k >= 0 && n >= 0 && (n == 0 || values != nullptr) && (k == 0 || index_out != nullptr), BARTINT_ERR_ARG, "bad arguments");
+    int rc = check_device();
+    if (rc) return rc;
+    if (k == 0) return BARTINT_OK;
+    double* d_v = nullptr;
+    BI_CUDA(cudaMallocAsync((void**)&d_v, sizeof(double) * (size_t)(std::max<int64_t>(n, 1) + k) + sizeof(int64_t) * (size_t)k, nullptr));
+    double* d_val = d_v + std::max<int64_t>(n, 1);
+    int64_t* d_idx = reinterpret_cast<int64_t*>(d_val + k);
+    cudaError_t e = n ? cudaMemcpyAsync(d_v, values, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, nullptr) : cudaSuccess;
+    rc = e == cudaSuccess ? launch_topk(d_v, n, k, d_idx, d_val, nullptr) : cuda_fail(e, "bartint_topk", __FILE__, __LINE__);
+    if (rc == BARTINT_OK) {
+        e = cudaMemcpy(index_out, d_idx, sizeof(int64_t) * (size_t)k, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && value_out) e = cudaMemcpy(value_out, d_val, sizeof(double) * (size_t)k, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = cuda_fail(e, "bartint_topk", __FILE__, __LINE__);
+    }
+    cudaFreeAsync(d_v, nullptr);
+    return rc;
+}
+
 int bartint_eval_points(const bartint_forest* f, const bartint_points* p, uint32_t flags, int32_t draw_begin,
                         int32_t draw_end, const double* weights, int64_t weights_len, double* draw_mean,
                         double* point_mean, double* point_var, double* full_pred) {

@@ -305,6 +305,7 @@ int launch_finalize_draws(const double* draw_sum, int ndraws, int64_t N, double 
 int launch_exact_integrals(const bartint_forest* f, int measure, const double* d_lo, const double* d_hi,
                            int n_draws, double* d_out, cudaStream_t st);
 int launch_argmax_ties(const double* d_v, int64_t n, int64_t* d_out, cudaStream_t st);
+int launch_topk(const double* d_v, int64_t n, int k, int64_t* d_idx, double* d_val, cudaStream_t st);
 int launch_draw_summary(const double* d_draw_mean, int ndraws, double* d_mean_var, cudaStream_t st);
 int launch_finalize_integrals(const double* d_in, int n, double y_min, double y_max, double* d_rescaled,
                               double* d_mean_sd, cudaStream_t st);

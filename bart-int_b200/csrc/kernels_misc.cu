@@ -968,6 +968,70 @@ int launch_argmax_ties(const double* d_v, int64_t n, int64_t* d_out, cudaStream_
     return BARTINT_OK;
 }
 
+// Batch design: the k candidates of largest posterior variance, i.e. order(var, decreasing =
+// TRUE)[1:k] with ties in index order and NaN last -- the selection src/BARTInt.R:315,387 / bartMean.R:51 make for k = 1.
+// One CTA; every thread keeps the best not-yet-taken element of its strided share in registers, a round is one
+// block-wide arg-max (value, then lower index), and only the winner's owner rescans its share.
+__global__ void __launch_bounds__(1024) topk_kernel(const double* __restrict__ v, int64_t n, int k, int64_t* __restrict__ idx_out,
+                                                    double* __restrict__ val_out) {
+    __shared__ double s_val[32];
+    __shared__ long long s_idx[32];
+    __shared__ long long s_win;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    double taken_v = INFINITY;        // the last element of this thread's share that was output (share order: value desc, index asc)
+    long long taken_i = -1;
+    double best = -INFINITY;
+    long long bi = -1;
+    auto rescan = [&]() {             // best element of the share that comes AFTER (taken_v, taken_i) in the output order
+        best = -INFINITY; bi = -1;
+        for (int64_t i = t; i < n; i += 1024) {
+            const double x = v[i];
+            if (x != x) continue;                                                   // NaN: never selected
+            const bool after = x < taken_v || (x == taken_v && (long long)i > taken_i);
+            if (after && (bi < 0 || x > best)) { best = x; bi = i; }                // first maximum = lowest index
+        }
+    };
+    rescan();
+    for (int r = 0; r < k; ++r) {
+        double bv = best;
+        long long bx = bi;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const long long ox = __shfl_xor_sync(0xffffffffu, bx, o);
+            if (ox >= 0 && (bx < 0 || ov > bv || (ov == bv && ox < bx))) { bv = ov; bx = ox; }
+        }
+        if (lane == 0) { s_val[warp] = bv; s_idx[warp] = bx; }
+        __syncthreads();
+        if (warp == 0) {
+            bv = s_val[lane]; bx = s_idx[lane];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const long long ox = __shfl_xor_sync(0xffffffffu, bx, o);
+                if (ox >= 0 && (bx < 0 || ov > bv || (ov == bv && ox < bx))) { bv = ov; bx = ox; }
+            }
+            if (lane == 0) {
+                s_win = bx;
+                idx_out[r] = bx;
+                if (val_out) val_out[r] = bx >= 0 ? bv : NAN;
+            }
+        }
+        __syncthreads();
+        const long long win = s_win;
+        if (win >= 0 && win == bi) { taken_v = best; taken_i = bi; rescan(); }
+        __syncthreads();
+    }
+}
+
+int launch_topk(const double* d_v, int64_t n, int k, int64_t* d_idx, double* d_val, cudaStream_t st) {
+    if (k <= 0) return BARTINT_OK;
+    topk_kernel<<<1, 1024, 0, st>>>(d_v, n, k, d_idx, d_val);
+    count_launch();
+    BI_CUDA(cudaGetLastError());
+    return BARTINT_OK;
+}
+
 int launch_finalize_integrals(const double* d_in, int n, double y_min, double y_max, double* d_rescaled,
                               double* d_mean_sd, cudaStream_t st) {
     finalize_integrals_kernel<<<1, 256, 0, st>>>(d_in, n, y_min, y_max, d_rescaled, d_mean_sd);

@@ -165,7 +165,7 @@ def replicate_forest(local_forest, group=None, stream=None):
 
 
 def sharded_design_step(tree_strings, tree_fits, x_train, cut_lists, y_min, y_max, mc_local, candidates, weights=None,
-                        measure="uniform", group=None, n_total=None):
+                        measure="uniform", group=None, n_total=None, n_draws_integral=None):
     """One sequential-design step on `world` ranks from the dbarts state every rank holds (the multi-GPU counterpart of
     design_step_dbarts):
       export      draw-sharded: rank r parses draws [lo_r, hi_r) only, then the finished sub-forests are all-gathered
@@ -173,6 +173,8 @@ def sharded_design_step(tree_strings, tree_fits, x_train, cut_lists, y_min, y_ma
       candidates  own draws on all candidates, (n, mean, M2) all-gathered, Chan merge   (BARTInt.R:312-314)
       MC points   point-sharded: own rows (StagedMatrix) on ALL draws, per-draw sums all-gathered (bartMean.R:74-82)
     n_total: the global number of MC rows, if the caller knows it (saves one exchange + host wait).
+    n_draws_integral: integrate only the first so many draws (the reference's quirk B1: min(ntree, S), BARTInt.R:216);
+    None = all draws.  Mean and sd are then taken over those draws, like bartint_design_step_dbarts098.
     Returns a dict of host arrays like design_step_dbarts (identical on every rank)."""
     from .forest import Forest, WireStrings
     rank, world = world_info(group)
@@ -192,8 +194,10 @@ def sharded_design_step(tree_strings, tree_fits, x_train, cut_lists, y_min, y_ma
     # for the exchange when it was overlapped with the own-draw evaluation, 0.8 ms alone.
     forests = replicate_forest(f_loc, group, stream=st)
     # own draws: exact integrals + candidate moments (small)
+    n_int = S if not n_draws_integral else max(1, min(int(n_draws_integral), S))
     integ = torch.zeros(S, dtype=torch.float64, device=dev)
-    f_loc.exact_integrals_device(integ[lo:hi].data_ptr(), measure, stream=st)
+    if min(hi, n_int) > lo:          # this rank's draws inside the integrated range
+        f_loc.exact_integrals_device(integ[lo:hi].data_ptr(), measure, n_draws_used=min(hi, n_int) - lo, stream=st)
     C_ = candidates.N
     pc = candidates.points(f_loc, stream=st)
     mean = torch.zeros(C_, dtype=torch.float64, device=dev)
@@ -221,9 +225,9 @@ def sharded_design_step(tree_strings, tree_fits, x_train, cut_lists, y_min, y_ma
     integ_all = ordered_sum(all_gather_rows(integ, group)) if world > 1 else integ
     integ_res = torch.empty(S, dtype=torch.float64, device=dev)
     integ_ms = torch.empty(2, dtype=torch.float64, device=dev)
-    f_loc.finalize_integrals_device(integ_all.data_ptr(), S, integ_res.data_ptr(), integ_ms.data_ptr(), stream=st)
+    f_loc.finalize_integrals_device(integ_all.data_ptr(), n_int, integ_res.data_ptr(), integ_ms.data_ptr(), stream=st)
     host = torch.cat([integ_all, integ_ms, var, draw_mean, mv]).cpu().numpy()        # one device->host copy
-    out = {"integrals": host[:S], "integral_mean_sd": host[S:S + 2], "cand_var": host[S + 2:S + 2 + C_],
+    out = {"integrals": host[:n_int], "integral_mean_sd": host[S:S + 2], "cand_var": host[S + 2:S + 2 + C_],
            "draw_mean": host[S + 2 + C_:2 * S + 2 + C_], "draw_mean_var": host[2 * S + 2 + C_:]}
     pm.close(); pc.close()
     for r, f in enumerate(forests):

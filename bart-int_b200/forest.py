@@ -163,6 +163,16 @@ class WireStrings:
         return v
 
 
+def topk(values, k: int):
+    """order(values, decreasing=TRUE)[1:k] on the device (0-based indices; ties in index order, NaN never selected):
+    the batch version of the reference's `which(var == max(var))` pick (BARTInt.R:315,387)."""
+    v = np.ascontiguousarray(np.asarray(values, np.float64).ravel())
+    idx = np.zeros(max(k, 1), np.int64)
+    val = np.zeros(max(k, 1))
+    _check(_lib.load().bartint_topk(_p(v, C.c_double), v.size, int(k), _p(idx, C.c_int64), _p(val, C.c_double)))
+    return idx[:k], val[:k]
+
+
 def init_group(n_gpus: int = 0) -> int:
     """bartint_init: open the single-process device group over n_gpus devices (0 = all).  Returns its size."""
     _check(_lib.load().bartint_init(int(n_gpus)))

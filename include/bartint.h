@@ -259,6 +259,13 @@ int bartint_finalize_draws_device(const bartint_forest* f, uint32_t flags, const
  * break -- and R's sample(scalar) quirk, SURVEY App. B2 -- stay with the caller. */
 int bartint_argmax_ties_device(const double* d_values, int64_t n, int64_t* d_out, void* stream);
 
+/* Batch design: the k candidates of largest value, order(values, decreasing = TRUE)[1:k] with
+ * ties in index order and NaN never selected -- for k = 1 the first element of which(var == max(var)) (src/BARTInt.R:
+ * 315,387; bartMean.R:51).  index_out[r] = 0-based index of the r-th largest (-1 once the non-NaN values are exhausted),
+ * value_out (may be NULL) its value.  _device: device pointers, asynchronous on `stream`. */
+int bartint_topk_device(const double* d_values, int64_t n, int32_t k, int64_t* d_index_out, double* d_value_out, void* stream);
+int bartint_topk(const double* values, int64_t n, int32_t k, int64_t* index_out, double* value_out);
+
 /* Chan merge of G draw-shards' per-point moments (device pointers, shard-major [g*N + i]);
  * then  var = M2/(n-1) * scale^2 * weight  and  mean = y0 + scale*(0.5 + mean)  with
  * scale = y_max - y_min, y0 = y_min (or scale = 1, y0 = -0.5 for BARTINT_SCALED_UNITS).     */

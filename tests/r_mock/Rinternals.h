@@ -41,6 +41,7 @@ int Rf_asInteger(SEXP x);
 Rboolean Rf_isNull(SEXP x);
 SEXP Rf_allocVector(unsigned int type, R_xlen_t n);
 SEXP Rf_allocMatrix(unsigned int type, int nrow, int ncol);
+SEXP Rf_ScalarInteger(int v);
 SEXP R_MakeExternalPtr(void* p, SEXP tag, SEXP prot);
 void* R_ExternalPtrAddr(SEXP s);
 void R_ClearExternalPtr(SEXP s);

@@ -116,6 +116,12 @@ SEXP Rf_allocMatrix(unsigned int type, int nrow, int ncol) {
     INTEGER(s->dim)[1] = ncol;
     return s;
 }
+
+SEXP Rf_ScalarInteger(int v) {
+    SEXP s = Rf_allocVector(INTSXP, 1);
+    INTEGER(s)[0] = v;
+    return s;
+}
 SEXP R_MakeExternalPtr(void* p, SEXP tag, SEXP prot) {
     (void)tag; (void)prot;
     SEXP s = new_sexp(EXTPTRSXP, 1, 0);
@@ -180,7 +186,10 @@ SEXP mock_call(dotcall_t fn, int nargs, SEXP* a) {
     error_target = &here;
     if (setjmp(here) == 0) {
         switch (nargs) {
+            case 1: result = fn(a[0]); break;
+            case 2: result = fn(a[0], a[1]); break;
             case 3: result = fn(a[0], a[1], a[2]); break;
+            case 5: result = fn(a[0], a[1], a[2], a[3], a[4]); break;
             case 4: result = fn(a[0], a[1], a[2], a[3]); break;
             case 6: result = fn(a[0], a[1], a[2], a[3], a[4], a[5]); break;
             case 11: result = fn(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10]); break;

@@ -123,3 +123,21 @@ def test_design_step_row_block_path(N):
     scale = ff.y_max - ff.y_min
     assert np.max(np.abs(out["draw_mean"] - ref)) <= 1e-12 * scale
     assert np.max(np.abs(out["draw_mean"] - sep)) <= 1e-13 * scale
+
+
+@pytest.mark.gpu
+def test_topk_batch_selection():
+    """order(var, decreasing = TRUE)[1:k] on the device: ties in index order, NaN never selected, k beyond the data -> -1."""
+    from bartint_b200 import topk
+    rng = np.random.default_rng(0)
+    for n, k in [(100, 1), (100, 7), (5000, 64), (200_000, 20), (3, 5)]:
+        v = np.round(rng.random(n), 2)                 # many ties
+        if n > 10:
+            v[rng.integers(0, n, 5)] = np.nan
+        idx, val = topk(v, k)
+        order = sorted((i for i in range(n) if v[i] == v[i]), key=lambda i: (-v[i], i))
+        want = (order + [-1] * k)[:k]
+        assert list(idx) == want, (n, k)
+        assert all((val[r] == v[want[r]]) if want[r] >= 0 else np.isnan(val[r]) for r in range(k))
+    assert list(topk(np.array([np.nan, np.nan]), 2)[0]) == [-1, -1]
+    assert len(topk(np.zeros(4), 0)[0]) == 0

@@ -76,3 +76,30 @@ def test_wire_strings_slice_is_a_view():
     assert (v.m, v.S) == (3, 3)
     assert [v.array[k] for k in range(9)] == [f"t{t}s{s}".encode() for s in range(1, 4) for t in range(3)]
     assert C.addressof(v.array) == C.addressof(w.array) + 3 * C.sizeof(C.c_char_p)
+
+
+def test_candidate_pick_follows_r_recycling():
+    """BARTInt.R:305,308,314-315: `colVars(fValues) * weights` with weights that are not length C."""
+    from bartint_b200 import api
+    rng = np.random.default_rng(0)
+    C_, d = 100, 3
+    var = rng.random(C_)
+    # exponential: length-d weights recycled over the candidates -> weight of candidate i is w[i mod d]
+    w = np.array([1.0, 5.0, 0.1])
+    want = int(np.argmax(var * np.array([w[i % d] for i in range(C_)]))) + 1
+    assert api._pick(var, w, np.random.default_rng(1)) == want
+    # gaussian: C x d matrix; R's product is C x d with var down the columns, which() gives column-major linear indices
+    W = rng.random((C_, d))
+    prod = np.array([[var[i] * W[i, j] for j in range(d)] for i in range(C_)])
+    lin = int(np.argmax(prod.ravel(order="F")))            # 0-based linear index
+    assert api._pick(var, W, np.random.default_rng(1)) == lin % C_ + 1
+    # scalar / length-C weights: the plain product
+    assert api._pick(var, np.ones(1), np.random.default_rng(1)) == int(np.argmax(var)) + 1
+    wc = rng.random(C_)
+    assert api._pick(var, wc, np.random.default_rng(1)) == int(np.argmax(var * wc)) + 1
+    # the weights objects _candidates builds have the reference's shapes
+    X, wg = api._candidates("gaussian", d, C_, np.random.default_rng(2))
+    assert wg.shape == (C_, d)
+    X, we = api._candidates("exponential", d, C_, np.random.default_rng(2))
+    assert we.shape == (d,) and np.allclose(we, np.exp(-X).mean(axis=0))
+    assert api._candidates("exponential", d, C_, np.random.default_rng(2), refcompat=False)[1].shape == (C_,)

@@ -153,25 +153,65 @@ def test_wbart_binding(rmock):
     ff = synth.prior_forest(4, 3, 5, rng.random((30, 2)), None)
     text = ff.to_wbart_text()
     cuts = rmock.list_of_reals(ff.cut_lists())
+    nil = rmock.lib.mock_nil()
+    trees = lambda t: rmock.strings(np.array([t], dtype=object))
     with pytest.raises(RuntimeError, match="node count|treedraws|tree 0"):
-        rmock.call("bartint_R_forest_wbart", rmock.strings(np.array(["1 1 2\nx\n"], dtype=object)), cuts,
-                   rmock.real([0.0], dim=False))
+        rmock.call("bartint_R_forest_wbart", trees("1 1 2\nx\n"), cuts, rmock.real([0.0], dim=False), nil, nil)
     with pytest.raises(RuntimeError, match="p = 2 but d = 1"):
-        rmock.call("bartint_R_forest_wbart", rmock.strings(np.array([text], dtype=object)),
-                   rmock.list_of_reals(ff.cut_lists()[:1]), rmock.real([0.0], dim=False))
+        rmock.call("bartint_R_forest_wbart", trees(text), rmock.list_of_reals(ff.cut_lists()[:1]),
+                   rmock.real([0.0], dim=False), nil, nil)
+    # a plain wbart fit has $mu and no $offset (gbart: $offset, pbart: $binaryOffset); none of them is an error, never 0
+    with pytest.raises(RuntimeError, match="none of .offset, .mu, .binaryOffset"):
+        rmock.call("bartint_R_forest_wbart", trees(text), cuts, nil, nil, nil)
+    for args in ((rmock.real([1.5], dim=False), nil, nil), (nil, rmock.real([1.5], dim=False), nil),
+                 (nil, nil, rmock.real([1.5], dim=False))):
+        if has_gpu():
+            h = rmock.call("bartint_R_forest_wbart", trees(text), cuts, *args)
+            X = rng.random((40, 2))
+            out = rmock.call("bartint_R_eval", h, rmock.real(X), nil, rmock.integer(4))
+            full = rmock.to_numpy(rmock.lib.VECTOR_ELT(out, 2))
+            want = onp.predict(onp.forest_from_wbart(text, ff.cut_lists(), 1.5), X)        # offset + sum of leaf values
+            np.testing.assert_allclose(full, want, rtol=0, atol=1e-12)
+            rmock.lib.mock_finalize(h)
+        else:
+            with pytest.raises(RuntimeError, match="(device|CUDA)"):
+                rmock.call("bartint_R_forest_wbart", trees(text), cuts, *args)
+
+
+def test_value_split_binding(rmock):
+    """bartint_R_forest_values: the marshalling of a getTrees()-style export (double offsets, 0-based var, pre-order)."""
+    off = rmock.real([0.0, 3.0, 4.0], dim=False)
+    var = np.array([0, -1, -1, -1], np.int32)
+    val = rmock.real([0.4, -1.0, 2.0, 0.25], dim=False)
+    ivec = lambda a: rmock.lib.mock_int(np.ascontiguousarray(a, np.int32).ctypes.data_as(C.POINTER(C.c_int)), len(a))
+    nil = rmock.lib.mock_nil()
+    args = lambda S, v: (rmock.integer(S), rmock.integer(2 // S), rmock.integer(1), off, ivec(v), val, nil, nil, rmock.integer(0),
+                         rmock.real([1.0], dim=False), rmock.real([10.0], dim=False))
+    with pytest.raises(RuntimeError, match="do not describe S . m trees"):
+        rmock.call("bartint_R_forest_values", rmock.integer(3), rmock.integer(1), rmock.integer(1), off, ivec(var), val, nil, nil,
+                   rmock.integer(0), rmock.real([1.0], dim=False), rmock.real([0.0], dim=False))
+    with pytest.raises(RuntimeError, match="variable 3"):
+        rmock.call("bartint_R_forest_values", *args(1, np.array([3, -1, -1, -1], np.int32)))
     if has_gpu():
-        h = rmock.call("bartint_R_forest_wbart", rmock.strings(np.array([text], dtype=object)), cuts,
-                       rmock.real([1.5], dim=False))
-        rmock.lib.mock_finalize(h)
+        h = rmock.call("bartint_R_forest_values", *args(1, var))
+        X = np.array([[0.4], [0.41], [0.0]])
+        out = rmock.call("bartint_R_eval", h, rmock.real(X), nil, rmock.integer(4))
+        full = rmock.to_numpy(rmock.lib.VECTOR_ELT(out, 2))
+        np.testing.assert_allclose(full, [[10.0 - 1.0 + 0.25, 10.0 + 2.0 + 0.25, 10.0 - 1.0 + 0.25]], atol=1e-13)   # left iff x <= 0.4
+        k = rmock.call("bartint_R_topk", rmock.real([0.1, 0.7, 0.7, np.nan], dim=False), rmock.integer(3))
+        assert list(np.ctypeslib.as_array(C.cast(rmock.lib.mock_real_ptr(k), C.POINTER(C.c_int)), shape=(3,))) == [1, 2, 0]
+        rmock.call("bartint_R_release", h)
+        with pytest.raises(RuntimeError, match="already released"):
+            rmock.call("bartint_R_eval", h, rmock.real(X), nil, rmock.integer(4))
+        assert rmock.lib.mock_type(rmock.call("bartint_R_init", rmock.integer(1))) == 13          # INTSXP: the group size
     else:
         with pytest.raises(RuntimeError, match="(device|CUDA)"):
-            rmock.call("bartint_R_forest_wbart", rmock.strings(np.array([text], dtype=object)), cuts,
-                       rmock.real([1.5], dim=False))
+            rmock.call("bartint_R_forest_values", *args(1, var))
+        with pytest.raises(RuntimeError, match="(device|CUDA)"):
+            rmock.call("bartint_R_init", rmock.integer(0))
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("BARTINT_TEST_RSHIM_GPU") != "1",
-                    reason="written after the round's GPU budget was spent; enable with BARTINT_TEST_RSHIM_GPU=1")
 def test_shim_end_to_end_against_the_oracle(rmock):
     ff, x_train, strings, fits = _state(seed=8, S=12, m=9, d=4, n=60)
     rng = np.random.default_rng(1)
