@@ -78,9 +78,11 @@ def test_wire_strings_slice_is_a_view():
     assert C.addressof(v.array) == C.addressof(w.array) + 3 * C.sizeof(C.c_char_p)
 
 
-def test_candidate_pick_follows_r_recycling():
-    """BARTInt.R:305,308,314-315: `colVars(fValues) * weights` with weights that are not length C."""
+def test_candidate_pick_follows_r_recycling(monkeypatch):
+    """BARTInt.R:305,308,314-315: `colVars(fValues) * weights` with weights that are not length C.
+    (R's sample(scalar) quirk B2, which _pick keeps, is switched off here so that the recycling alone is visible.)"""
     from bartint_b200 import api
+    monkeypatch.setattr(api, "r_sample_one", lambda v, rng: int(np.asarray(v)[0]))
     rng = np.random.default_rng(0)
     C_, d = 100, 3
     var = rng.random(C_)
