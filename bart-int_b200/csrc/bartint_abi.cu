@@ -800,6 +800,17 @@ int bartint_eval_points_device(const bartint_forest* f, const bartint_points* p,
                      1, (cudaStream_t)stream);
 }
 
+int bartint_eval_points_full_device(const bartint_forest* f, const bartint_points* p, uint32_t flags, int32_t draw_begin,
+                                    int32_t draw_end, double* d_full_pred, void* stream) {
+    int rc = check_range(f, p, draw_begin, draw_end);
+    if (rc) return rc;
+    BI_REQUIRE(d_full_pred != nullptr || (int64_t)(draw_end - draw_begin) * p->N == 0, BARTINT_ERR_ARG, "d_full_pred is NULL");
+    DeviceGuard g(f->device);
+    const int scaled = (flags & BARTINT_SCALED_UNITS) ? 1 : 0;
+    return eval_core(f, p, flags, draw_begin, draw_end, nullptr, nullptr, nullptr, nullptr, d_full_pred, f->y_max - f->y_min,
+                     f->y_min, scaled, (cudaStream_t)stream);
+}
+
 int bartint_merge_moments_device(const bartint_forest* f, uint32_t flags, int32_t G, const int32_t* shard_draws,
                                  const double* d_mean, const double* d_m2, int64_t N, const double* d_weights,
                                  int64_t weights_len, double* d_point_mean_out, double* d_point_var_out, void* stream) {

@@ -93,7 +93,7 @@ size_t tg_smem_bytes() {
 // It is a compile-time variant so that the default kernel carries no trace of it: with the mode tested at run time
 // inside the stage loop the 16-point body spilled (STACK 32 -> 48, round-1 regression 5.56 -> 6.18 ms at cfg 2).
 template <int NB, int R, bool MOMENTS, bool FULL, int P = TG_P, bool COUNT = false>
-__global__ void __launch_bounds__(TG_THREADS, P > 8 ? 2 : MOMENTS ? 2 : 3) eval_gather_kernel(const TableParams prm) {
+__global__ void __launch_bounds__(TG_THREADS, P > 8 ? 2 : (MOMENTS || FULL) ? 2 : 3) eval_gather_kernel(const TableParams prm) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int T = TG_THREADS, TILE = TG_THREADS * P;
     constexpr int REC = tg_rec_bytes(NB);
@@ -144,6 +144,14 @@ __global__ void __launch_bounds__(TG_THREADS, P > 8 ? 2 : MOMENTS ? 2 : 3) eval_
 
     double acc[P];
     double piv[MOMENTS ? P : 1], S1[MOMENTS ? P : 1], S2[MOMENTS ? P : 1];
+    // FULL (the S x N matrix of predict(), draws contiguous per point in R's layout): the draws of the current group of
+    // four rows wait in registers (slot = row mod 4, statically indexed) and leave as ONE aligned 32-byte sector per
+    // point -- two 16-byte stores -- whenever the draw index reaches a multiple of four; a warp that stored one
+    // double per draw touched 32 sectors for 256 bytes of payload.  Ragged heads / tails of a draw chunk and row
+    // counts that are not a multiple of four fall back to scalar stores.
+    double fq[FULL ? P : 1][4];
+    int fq_n = 0;                                              // values waiting (uniform across the CTA)
+    const bool fq_vec = FULL && (ndraws & 3) == 0 && (reinterpret_cast<uintptr_t>(prm.full_pred) & 31) == 0;
 #pragma unroll
     for (int p = 0; p < P; ++p) acc[p] = 0.0;
 #pragma unroll
@@ -243,12 +251,34 @@ __global__ void __launch_bounds__(TG_THREADS, P > 8 ? 2 : MOMENTS ? 2 : 3) eval_
                         S1[p] += dlt;
                         S2[p] = fma(dlt, dlt, S2[p]);
                     }
-                    if (FULL) {
-                        if ((vmask >> p) & 1u) {
-                            const int64_t i = tile_base + (int64_t)p * T + tid;
-                            prm.full_pred[(int64_t)(s - prm.draw_begin) + (int64_t)ndraws * i] =
-                                prm.fp_scaled ? fv : prm.fp_scale * (fv + 0.5) + prm.fp_y0;
+                    if (FULL) {                                       // slot = row mod 4 (warp-uniform, static indices)
+                        const double fo = prm.fp_scaled ? fv : prm.fp_scale * (fv + 0.5) + prm.fp_y0;
+                        const int slot = (s - prm.draw_begin) & 3;
+                        if (slot == 0) fq[p][0] = fo;
+                        else if (slot == 1) fq[p][1] = fo;
+                        else if (slot == 2) fq[p][2] = fo;
+                        else fq[p][3] = fo;
+                    }
+                }
+                if (FULL) {
+                    ++fq_n;
+                    const int row = s - prm.draw_begin, slot = row & 3;       // row of the newest value
+                    if (slot == 3 || s + 1 == s1) {                           // a sector is complete, or the chunk ends
+#pragma unroll
+                        for (int p = 0; p < P; ++p) {
+                            if ((vmask >> p) & 1u) {
+                                double* dst = prm.full_pred + (int64_t)ndraws * (tile_base + (int64_t)p * T + tid) + (row - slot);
+                                if (fq_n == 4 && fq_vec) {                    // (fq_n == 4 implies slot == 3)
+                                    *reinterpret_cast<double2*>(dst) = make_double2(fq[p][0], fq[p][1]);
+                                    *reinterpret_cast<double2*>(dst + 2) = make_double2(fq[p][2], fq[p][3]);
+                                } else {
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j)
+                                        if (j <= slot && j > slot - fq_n) dst[j] = fq[p][j];
+                                }
+                            }
                         }
+                        fq_n = 0;
                     }
                 }
                 dsum = warp_sum(dsum);

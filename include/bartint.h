@@ -247,6 +247,11 @@ int bartint_eval_points_device(const bartint_forest* f, const bartint_points* p,
                                double* d_draw_sum, double* d_point_mean, double* d_point_m2,
                                void* stream);
 
+/* predict(model, X) kept ON THE DEVICE: d_full_pred [(draw_end - draw_begin) x N] column-major, rows = draws (R's layout
+ * of the S x N matrix, BARTInt.R:312,380; bartMean.R:47,74), original units unless BARTINT_SCALED_UNITS.  Asynchronous. */
+int bartint_eval_points_full_device(const bartint_forest* f, const bartint_points* p, uint32_t flags,
+                                    int32_t draw_begin, int32_t draw_end, double* d_full_pred, void* stream);
+
 /* rowMeans + the survey estimator's summary (bartMean.R:76,80,82), asynchronous, device pointers:
  *   d_draw_mean[ndraws] = rowMeans(pred) = (ymax-ymin)*(d_draw_sum/n_points + 0.5) + ymin
  *   d_mean_var[2]       = { mean(pred), sum((rowMeans - mean)^2)/(ndraws-1) }   (a VARIANCE, quirk B6)

@@ -452,3 +452,22 @@ def test_staged_matrix_path(small_case):
     out = f.eval(pts, want=("draw_mean",))
     _assert_close(out["draw_mean"], onp.row_means(onp.predict(ff, X)), 1e-13, scale=ff.y_max - ff.y_min)
     pts.close(); st.close(); f.close()
+
+
+@pytest.mark.parametrize("S,draws", [(12, None), (12, (4, 12)), (13, None), (12, (3, 11)), (40, (1, 38)), (64, None)])
+def test_full_matrix_writer_alignment_cases(S, draws):
+    """predict()'s S x N matrix (BARTInt.R:312,380; bartMean.R:47,74): the gather kernel stores four draws of a point as one
+    32-byte sector when the row count is a multiple of four, scalars otherwise and at ragged chunk ends; every case must
+    be the same matrix, equal to the oracle's."""
+    rng = np.random.default_rng(S)
+    x_train = rng.random((40, 4))
+    ff = synth.prior_forest(S, S, 8, x_train, synth.genz_gaussian(x_train))
+    X = rng.random((4099, 4))
+    P = onp.predict(ff, X)
+    f = Forest.from_soa(ff)
+    lo, hi = draws if draws else (0, S)
+    out = f.eval(X, want=("full_pred", "draw_mean"), draws=draws)
+    _assert_close(out["full_pred"], P[lo:hi], 1e-13, scale=ff.y_max - ff.y_min)
+    walk = f.eval(X, want=("full_pred",), draws=draws, force_walk=True)["full_pred"]
+    _assert_close(out["full_pred"], walk, 1e-13, scale=ff.y_max - ff.y_min)
+    f.close()
