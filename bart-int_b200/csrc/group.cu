@@ -13,6 +13,9 @@
 // (tens of microseconds each) then run on different host threads instead of queueing behind one another.
 // NCCL is loaded with dlopen: a box without it can still use one GPU.
 #include <dlfcn.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 #include <condition_variable>
 #include <cstdlib>
@@ -300,6 +303,11 @@ int bartint_init(int n_gpus) {
     }
     cudaSetDevice(devices[0]);
     g_group = g.release();
+#ifdef _OPENMP
+    // the members' worker threads need cores of their own: the exporter's OpenMP team spin-waits between its parallel
+    // regions, and a team as large as the machine leaves the workers waiting for a scheduler quantum (milliseconds)
+    if (G > 1) omp_set_num_threads(std::max(1, std::min(omp_get_max_threads(), omp_get_num_procs() - (G - 1))));
+#endif
     return BARTINT_OK;
 }
 

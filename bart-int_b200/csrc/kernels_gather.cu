@@ -254,10 +254,8 @@ __global__ void __launch_bounds__(TG_THREADS, P > 8 ? 2 : (MOMENTS || FULL) ? 2 
                     if (FULL) {                                       // slot = row mod 4 (warp-uniform, static indices)
                         const double fo = prm.fp_scaled ? fv : prm.fp_scale * (fv + 0.5) + prm.fp_y0;
                         const int slot = (s - prm.draw_begin) & 3;
-                        if (slot == 0) fq[p][0] = fo;
-                        else if (slot == 1) fq[p][1] = fo;
-                        else if (slot == 2) fq[p][2] = fo;
-                        else fq[p][3] = fo;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) fq[p][j] = slot == j ? fo : fq[p][j];     // selects: fq stays in registers
                     }
                 }
                 if (FULL) {
@@ -321,6 +319,7 @@ __global__ void __launch_bounds__(TG_THREADS, P > 8 ? 2 : (MOMENTS || FULL) ? 2 
 // the full matrix are wanted (their extra accumulators do not fit 16 points).  BARTINT_GATHER_P=8 forces 8.
 int gather_points_per_thread(bool mom, bool full) {
     static const bool p8 = [] { const char* e = std::getenv("BARTINT_GATHER_P"); return e && std::atoi(e) == 8; }();
+    if (mom && full) return 4;        // moments + the four-row store buffer: 8 points would spill 200 bytes per thread
     return (!p8 && !mom && !full) ? 16 : TG_P;
 }
 int gather_tile(bool mom, bool full) { return TG_THREADS * gather_points_per_thread(mom, full); }
@@ -330,7 +329,7 @@ typedef void (*gather_kernel_t)(const TableParams);
 
 template <int NB, int R>
 static gather_kernel_t pick_gather(bool mom, bool full, bool count) {
-    if (mom && full) return eval_gather_kernel<NB, R, true, true>;
+    if (mom && full) return eval_gather_kernel<NB, R, true, true, 4>;
     if (mom) return eval_gather_kernel<NB, R, true, false>;
     if (full) return eval_gather_kernel<NB, R, false, true>;
     if (gather_points_per_thread(mom, full) == 16)

@@ -434,7 +434,7 @@ def run_ours(args):
                 Xall = X_host
             Xn, Xcn = Xall.numpy().T, Xc_host.numpy().T        # N x d views, column-major (pinned)
             if world > 1:
-                assert bi.init_group(world) == world
+                assert bi.init_group(world) == world      # (keeps world - 1 cores free of exporter threads for its workers)
             target = "group" if world > 1 else local_rank
             e2e_steps = max(1, min(args.steps, 20))
             times, worst = [], 0.0

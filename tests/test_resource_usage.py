@@ -1,0 +1,41 @@
+"""Register / stack budget of the hot kernel instantiations, read from the built library with `cuobjdump -res-usage`
+(works without a GPU).  The round-1 verdict found an 11 % slowdown of the gather kernel that was visible here first: the
+16-point sums-only instantiation had grown from a 32-byte to a 48-byte stack frame.  profiles/r2/res_usage.txt keeps the
+listing of the shipped build."""
+import os
+import re
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "bart-int_b200", "libbartint_cuda.so")
+
+
+def res_usage():
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(exe):
+        pytest.skip("cuobjdump not available")
+    txt = subprocess.run([exe, "-res-usage", LIB], capture_output=True, text=True, check=True).stdout
+    out = {}
+    for name, reg, stack in re.findall(r"Function (\S+):\s*\n\s*REG:(\d+) STACK:(\d+)", txt):
+        out[name] = (int(reg), int(stack))
+    return out
+
+
+def test_hot_instantiations_keep_their_budget():
+    use = res_usage()
+    assert len(use) > 30
+    find = lambda pat: [(k, v) for k, v in use.items() if re.search(pat, k)]
+    # eval_gather_kernel<5, 3, MOMENTS=0, FULL=0, P=16, COUNT=0>: the per-point sums kernel of cfg 2 (2 CTAs x 128 registers)
+    (name, (reg, stack)), = find(r"eval_gather_kernelILi5ELi3ELb0ELb0ELi16ELb0E")
+    assert reg <= 128 and stack <= 32, (name, reg, stack)
+    # the predict()-matrix instantiation keeps its four-row store buffer in registers
+    (name, (reg, stack)), = find(r"eval_gather_kernelILi5ELi3ELb0ELb1ELi8ELb0E")
+    assert reg <= 128 and stack <= 16, (name, reg, stack)
+    # the bit-sliced kernel: no local memory in any tile shape, 512 threads x 128 registers = one CTA per SM
+    bs = find(r"eval_bitslice_kernelILi[248]E")
+    assert len(bs) == 3
+    for name, (reg, stack) in bs:
+        assert reg <= 128 and stack == 0, (name, reg, stack)
