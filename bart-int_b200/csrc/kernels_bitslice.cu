@@ -38,7 +38,6 @@
 namespace bartint {
 
 constexpr int BS_THREADS = 512;                 // 16 warps, one CTA per SM (the mask table fills shared memory)
-constexpr int BS_NWARP = BS_THREADS / 32;
 constexpr size_t BS_SMEM_MAX = 227 * 1024;
 constexpr int BS_SORT_MAX = 16384;              // draws are ordered by cost (rank sort, O(S^2)) up to this many
 
@@ -354,6 +353,22 @@ struct BsParams {
 };
 
 __device__ __forceinline__ int popc4(const uint4& v) { return __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w); }
+
+// Population count of a long run of words with fewer POPC: POPC runs on the quarter-rate XU pipe (one warp instruction
+// per 8 clocks and SM sub-partition), which a row pair of class B would keep exactly as busy as the shared-memory pipe
+// (32 POPC per 64 wavefronts).  A carry-save adder over two words and the running `ones` word costs two LOP3 on the ALU
+// pipe and replaces two POPC by one (of the carries, weight 2): per 4 words 4 LOP3 + 2 POPC instead of 4 POPC.
+struct PopAcc {
+    uint32_t ones = 0u;
+    int twos = 0;                           // number of set bits seen in carry words (each counts twice)
+    __device__ __forceinline__ void add2(uint32_t a, uint32_t b) {
+        const uint32_t carry = (a & b) | (ones & (a ^ b));      // majority(ones, a, b): one LOP3
+        ones ^= a ^ b;                                          // one LOP3
+        twos += __popc(carry);
+    }
+    __device__ __forceinline__ void add4(uint32_t a, uint32_t b, uint32_t c, uint32_t d) { add2(a, b); add2(c, d); }
+    __device__ __forceinline__ int total() const { return 2 * twos + __popc(ones); }
+};
 __device__ __forceinline__ uint4 lds16(const unsigned char* p) { return *reinterpret_cast<const uint4*>(p); }
 
 // Rows [0, n) of one class, G at a time: the loads of the next group are in flight while this one is processed (the
@@ -385,10 +400,12 @@ __global__ void __launch_bounds__(BS_THREADS, 1) eval_bitslice_kernel(const BsPa
     constexpr int ROWB = CH * 16;           // bytes per predicate row
     constexpr int WORDS = CH * 4;           // 32-point words per row
     constexpr int TILE = CH * 128;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int n_rows = prm.ncuts + 1;
     unsigned char* const s_mask = smem;                                             // [n_rows][ROWB]
     uint32_t* const s_cnt = reinterpret_cast<uint32_t*>(smem + (size_t)n_rows * ROWB);   // [n_rows] popcount of a row
+    int* const s_next = reinterpret_cast<int*>(s_cnt + n_rows);                          // slice counter of phase 4
+    if (tid == 0) *s_next = 0;
     const int64_t tile_base = (int64_t)blockIdx.x * TILE;
 
     // ---- 0-2. the mask table.  Column w (32 points) of variable j's rows belongs to ONE thread: it clears the column,
@@ -439,11 +456,20 @@ __global__ void __launch_bounds__(BS_THREADS, 1) eval_bitslice_kernel(const BsPa
     }
     __syncthreads();
 
-    // ---- 4. the slices of this CTA's chunk, one warp per slice, one lane per draw ----
+    // ---- 4. the slices of this CTA's chunk, one warp per slice, one lane per draw.  Slices are sorted by cost
+    // (ascending), so the warps take them from a shared counter starting with the most expensive one: with a fixed
+    // assignment warp 15 got the two longest of the 32 slices and the CTA waited for it with an idle data pipe
+    // (0.50 -> 0.47 ms at cfg 2).  Splitting a slice into quarter units with an integer combine in shared memory was
+    // tried and lost (0.51 ms): every unit pays the L2 round trip of its first row group again. ----
     const int ndraws = prm.draw_end - prm.draw_begin;
     const int sl0 = blockIdx.y * prm.chunk_slices;
     const int sl1 = min(sl0 + prm.chunk_slices, prm.n_slices);
-    for (int sl = sl0 + warp; sl < sl1; sl += BS_NWARP) {
+    for (;;) {
+        int take = 0;
+        if (lane == 0) take = atomicAdd(s_next, 1);
+        take = __shfl_sync(0xffffffffu, take, 0);
+        const int sl = sl1 - 1 - take;
+        if (sl < sl0) break;
         const int s = __ldg(&prm.slot_draw[sl * 32 + lane]);
         const bool wanted = s >= prm.draw_begin && s < prm.draw_end;
         if (!__any_sync(0xffffffffu, wanted)) continue;
@@ -461,14 +487,13 @@ __global__ void __launch_bounds__(BS_THREADS, 1) eval_bitslice_kernel(const BsPa
             const uint32_t pm = (uint32_t)((int)e.z >> 31);
             const unsigned char* ap = s_mask + (e.z & 0x7FFFFFFFu);
             const unsigned char* aj = s_mask + e.w;
-            int cnt = 0;
+            PopAcc pa;
 #pragma unroll
             for (int c = 0; c < CH; ++c) {
                 const uint4 mp = lds16(ap + rot[c]), mj = lds16(aj + rot[c]);
-                cnt += __popc((mp.x ^ pm) & mj.x) + __popc((mp.y ^ pm) & mj.y) + __popc((mp.z ^ pm) & mj.z) +
-                       __popc((mp.w ^ pm) & mj.w);
+                pa.add4((mp.x ^ pm) & mj.x, (mp.y ^ pm) & mj.y, (mp.z ^ pm) & mj.z, (mp.w ^ pm) & mj.w);
             }
-            add(e, cnt);
+            add(e, pa.total());
         });
         bs_rows<4>(reinterpret_cast<const uint4*>(sp + prm.L.off[BS_C2]) + lane, h0.z, [&](const uint4& e) {
             const unsigned char* aj = s_mask + ((e.z & 0x3FFFu) << 4);
@@ -531,7 +556,7 @@ __global__ void __launch_bounds__(BS_THREADS, 1) eval_bitslice_kernel(const BsPa
     }
 }
 
-size_t bs_smem_bytes(const bartint_forest* f) { return (size_t)(f->bs_ncuts + 1) * (size_t)(f->bs_ch * 16 + 4); }
+size_t bs_smem_bytes(const bartint_forest* f) { return (size_t)(f->bs_ncuts + 1) * (size_t)(f->bs_ch * 16 + 4) + 16; }
 int bs_tile(const bartint_forest* f) { return f->bs_ch * 128; }
 int64_t bs_pool_bytes(const bartint_forest* f) { return f->bs_ok ? bs_layout_of(f).slice_bytes * ((f->S + 31) / 32) : 0; }
 
