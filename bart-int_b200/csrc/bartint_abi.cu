@@ -282,7 +282,7 @@ int bartint_debug_plan_soa(int32_t S, int32_t m, int32_t d, const int64_t* tree_
     WalkForm W;
     pack_walk_form(&f, W);
     FastPlan P;
-    plan_fast_path(&f, W.tree_off, P);
+    plan_fast_path(&f, W.tree_off.data(), P);
     info[0] = f.table_ok ? 1 : 0; info[1] = f.gather ? 1 : 0; info[2] = f.nb; info[3] = f.g_regs;
     info[4] = f.count_level; info[5] = f.n_groups; info[6] = P.DW; info[7] = f.n_leaves;
     BI_REQUIRE(f.n_groups <= group_capacity, BARTINT_ERR_ARG, "plan has %lld group records, capacity is %lld",
@@ -314,7 +314,7 @@ static int debug_finish_and_copy(bartint_forest& f, int64_t tree_capacity, int64
         WalkForm W;
         pack_walk_form(&f, W);
         FastPlan P;
-        plan_fast_path(&f, W.tree_off, P);
+        plan_fast_path(&f, W.tree_off.data(), P);
     }
     BI_REQUIRE(f.n_nodes <= node_capacity && (int64_t)f.S * f.m <= tree_capacity, BARTINT_ERR_ARG,
                "forest has %lld trees and %lld nodes, capacity is %lld and %lld", (long long)f.S * f.m,
@@ -1530,13 +1530,17 @@ int bartint_design_step_dbarts098(const char* const* tree_strings, const double*
     auto now_ms = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return 1e3 * (double)ts.tv_sec + 1e-6 * (double)ts.tv_nsec; };
     const double t_begin = now_ms();
     std::vector<int32_t> edges((size_t)G + 1, 0);
+    // Chunk sizes: the host export is the critical path and the evaluation of the LAST chunk is the tail nothing can
+    // hide, so the chunks shrink towards the end (weights G + 0.5 - g; BARTINT_STEP_FIRST = percent of the draws in the
+    // first chunk overrides it for two chunks).  (Round 1, with a 5.6 ms evaluation behind a 2 ms export, ramped UP.)
+    static const int first_pct = [] { const char* e = std::getenv("BARTINT_STEP_FIRST"); return e ? atoi(e) : 0; }();
     for (int k = 1; k <= G; ++k) {       // every chunk at least one draw, the last edge exactly S
-        const int64_t ideal = (int64_t)S * ((int64_t)k * k + 2 * (int64_t)k) / ((int64_t)G * G + 2 * (int64_t)G);
+        // sum_{g<k} (G + 0.5 - g) = k (2G + 2 - k) / 2   of   G (G + 2) / 2
+        int64_t ideal = (int64_t)S * ((int64_t)k * (2 * G + 2 - k)) / ((int64_t)G * (G + 2));
+        if (G == 2 && k == 1 && first_pct > 0 && first_pct < 100) ideal = (int64_t)S * first_pct / 100;
         edges[(size_t)k] = (int32_t)std::min<int64_t>(std::max<int64_t>(ideal, edges[(size_t)k - 1] + 1), S - (G - k));
     }
     for (int g = 0; g < G; ++g) {
-        // chunk sizes ramp up (weights g + 1.5): a small first chunk gets the GPU started early, and the host, which
-        // needs less time per draw than the GPU, stays ahead on the larger later ones
         const int32_t s0 = edges[(size_t)g], s1 = edges[(size_t)g + 1];
         counts[(size_t)g] = s1 - s0;
         bartint_forest* f = nullptr;

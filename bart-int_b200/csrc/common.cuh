@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <functional>
+#include <new>
 #include <string>
 #include <vector>
 
@@ -197,10 +198,31 @@ namespace bartint {
 // host-side pieces (forest_host.cu)
 int forest_finish_host(bartint_forest* f);      // validate canonical SoA, compute stats
 int forest_upload(bartint_forest* f);           // build device arrays (+ table groups)
+// Staging memory of the walk form: page-locked blocks from a per-thread cache, so that the host->device copies of a
+// forest upload are true DMA transfers that return at once (from pageable vectors cudaMemcpyAsync stages and waits:
+// 0.25-0.35 ms per draw chunk of a design step).  A block released while its copy may still be in flight is tagged with
+// an event on the upload stream and not handed out again before that event has completed.  Without a CUDA device (the
+// host-only test hooks) the blocks are plain heap memory.  Elements are default-initialised (no zero fill).
+void* pinned_stage_alloc(size_t bytes);
+void pinned_stage_free(void* p, size_t bytes);
+template <typename T>
+struct StageAlloc {
+    using value_type = T;
+    StageAlloc() = default;
+    template <typename U> StageAlloc(const StageAlloc<U>&) {}
+    T* allocate(size_t n) { return static_cast<T*>(pinned_stage_alloc(n * sizeof(T))); }
+    void deallocate(T* p, size_t n) { pinned_stage_free(p, n * sizeof(T)); }
+    template <typename U> void construct(U*) {}                                   // default-init: no zero fill
+    template <typename U, typename... A> void construct(U* p, A&&... a) { ::new ((void*)p) U(static_cast<A&&>(a)...); }
+    template <typename U> bool operator==(const StageAlloc<U>&) const { return true; }
+    template <typename U> bool operator!=(const StageAlloc<U>&) const { return false; }
+};
+template <typename T> using StageVec = std::vector<T, StageAlloc<T>>;
+
 struct WalkForm {
-    std::vector<uint2> nodes;                 // n_nodes node records (see LEAF_VAR above)
-    std::vector<int32_t> tree_off, leaf_off;  // S*m+1 each: first node / first leaf of every tree
-    std::vector<double> leaf_mu;              // n_leaves, by (tree, leaf ordinal)
+    StageVec<uint2> nodes;                    // n_nodes node records (see LEAF_VAR above)
+    StageVec<int32_t> tree_off, leaf_off;     // S*m+1 each: first node / first leaf of every tree
+    StageVec<double> leaf_mu;                 // n_leaves, by (tree, leaf ordinal)
 };
 // Fast-path plan of a forest: everything forest_upload sends to the device besides the walk form.  Filled by
 // plan_fast_path on the host (no CUDA call in there: the CPU tests run it through bartint_debug_plan_soa and
@@ -214,7 +236,7 @@ struct FastPlan {
 };
 
 void pack_walk_form(const bartint_forest* f, WalkForm& W);
-void plan_fast_path(bartint_forest* f, const std::vector<int32_t>& tree_off, FastPlan& P);
+void plan_fast_path(bartint_forest* f, const int32_t* tree_off, FastPlan& P);
 int parse_dbarts_forest(const char* const* tree_strings, const double* tree_fits, const double* x_train,
                         int64_t n, int32_t d, const int32_t* cut_offsets, const double* cut_values,
                         int32_t m, int32_t S, bartint_forest* f);

@@ -607,8 +607,81 @@ int forest_finish_host(bartint_forest* f) {
     return BARTINT_OK;
 }
 
-template <typename T>
-static int upload(T** dptr, const std::vector<T>& h) {
+// ---- page-locked staging blocks (see StageAlloc in common.cuh) ----
+namespace {
+struct StageBlock { void* p; size_t bytes; bool pinned; cudaEvent_t busy; };
+struct StageCache {
+    std::vector<StageBlock> free_blocks;
+    ~StageCache() {
+        for (StageBlock& b : free_blocks) {
+            if (b.busy) { cudaEventSynchronize(b.busy); cudaEventDestroy(b.busy); }
+            if (b.pinned) cudaFreeHost(b.p); else free(b.p);
+        }
+        (void)cudaGetLastError();
+    }
+};
+thread_local StageCache g_stage;
+std::atomic<int> g_stage_pinned{-1};      // -1 unknown, 0 no device (heap), 1 page-locked
+constexpr size_t kStageHeader = 64;       // room in front of the user pointer for {bytes, pinned}
+}  // namespace
+
+void* pinned_stage_alloc(size_t bytes) {
+    const size_t need = ((std::max<size_t>(bytes, 1) + 4095) & ~(size_t)4095) + kStageHeader;
+    // a cached block that is large enough and whose last copy has completed
+    for (size_t k = 0; k < g_stage.free_blocks.size(); ++k) {
+        StageBlock& b = g_stage.free_blocks[k];
+        if (b.bytes < need || b.bytes > 4 * need + (1u << 20)) continue;
+        if (b.busy) {
+            if (cudaEventQuery(b.busy) != cudaSuccess) { (void)cudaGetLastError(); continue; }
+            cudaEventDestroy(b.busy);
+            b.busy = nullptr;
+        }
+        StageBlock got = b;
+        g_stage.free_blocks.erase(g_stage.free_blocks.begin() + (std::ptrdiff_t)k);
+        size_t* hdr = static_cast<size_t*>(got.p);
+        hdr[0] = got.bytes; hdr[1] = got.pinned ? 1 : 0;
+        return static_cast<char*>(got.p) + kStageHeader;
+    }
+    void* p = nullptr;
+    bool pinned = false;
+    if (g_stage_pinned.load() != 0) {
+        int n_dev = 0;
+        if (g_stage_pinned.load() < 0) g_stage_pinned.store(cudaGetDeviceCount(&n_dev) == cudaSuccess && n_dev > 0 ? 1 : 0);
+        (void)cudaGetLastError();
+        if (g_stage_pinned.load() == 1 && cudaHostAlloc(&p, need, cudaHostAllocPortable) == cudaSuccess) pinned = true;
+        else { (void)cudaGetLastError(); p = nullptr; }
+    }
+    if (!p) p = malloc(need);
+    if (!p) throw std::bad_alloc();
+    size_t* hdr = static_cast<size_t*>(p);
+    hdr[0] = need; hdr[1] = pinned ? 1 : 0;
+    return static_cast<char*>(p) + kStageHeader;
+}
+
+void pinned_stage_free(void* user, size_t) {
+    if (!user) return;
+    void* p = static_cast<char*>(user) - kStageHeader;
+    const size_t* hdr = static_cast<const size_t*>(p);
+    StageBlock b{p, hdr[0], hdr[1] != 0, nullptr};
+    if (b.pinned) {      // a copy out of this block may still be queued on the upload (default) stream
+        if (cudaEventCreateWithFlags(&b.busy, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventRecord(b.busy, nullptr) != cudaSuccess) {
+            (void)cudaGetLastError();
+            cudaStreamSynchronize(nullptr);
+            if (b.busy) { cudaEventDestroy(b.busy); b.busy = nullptr; }
+        }
+    }
+    if (g_stage.free_blocks.size() >= 32) {          // bound the cache: drop the oldest block
+        StageBlock old = g_stage.free_blocks.front();
+        g_stage.free_blocks.erase(g_stage.free_blocks.begin());
+        if (old.busy) { cudaEventSynchronize(old.busy); cudaEventDestroy(old.busy); }
+        if (old.pinned) cudaFreeHost(old.p); else free(old.p);
+    }
+    g_stage.free_blocks.push_back(b);
+}
+
+template <typename T, typename A>
+static int upload(T** dptr, const std::vector<T, A>& h) {
     size_t bytes = std::max<size_t>(h.size(), 1) * sizeof(T);
     // stream-ordered allocator on the default stream: cached blocks make a per-step forest rebuild cheap
     BI_CUDA(cudaMallocAsync((void**)dptr, bytes, nullptr));
@@ -637,7 +710,7 @@ struct TreeList {
     const int32_t* end() const { return v + n; }
 };
 
-void plan_fast_path(bartint_forest* f, const std::vector<int32_t>& tree_off, FastPlan& P) {
+void plan_fast_path(bartint_forest* f, const int32_t* tree_off, FastPlan& P) {
     PhaseTimer pt;
     const int64_t n_trees = (int64_t)f->S * f->m;
     const int64_t nn = f->n_nodes;
@@ -1058,9 +1131,9 @@ void pack_walk_form(const bartint_forest* f, WalkForm& W) {
     PhaseTimer pt;
     const int64_t n_trees = (int64_t)f->S * f->m;
     const int64_t nn = f->n_nodes;
-    std::vector<uint2>& nodes = W.nodes;
-    std::vector<int32_t>&tree_off = W.tree_off, &leaf_off = W.leaf_off;
-    std::vector<double>& leaf_mu = W.leaf_mu;
+    StageVec<uint2>& nodes = W.nodes;
+    StageVec<int32_t>&tree_off = W.tree_off, &leaf_off = W.leaf_off;
+    StageVec<double>& leaf_mu = W.leaf_mu;
     nodes.resize((size_t)nn);
     tree_off.resize((size_t)n_trees + 1);
     leaf_off.assign((size_t)n_trees + 1, 0);
@@ -1093,9 +1166,9 @@ int forest_upload(bartint_forest* f) {
     PhaseTimer pt;
     WalkForm W;
     pack_walk_form(f, W);
-    const std::vector<uint2>& nodes = W.nodes;
-    const std::vector<int32_t>&tree_off = W.tree_off, &leaf_off = W.leaf_off;
-    const std::vector<double>& leaf_mu = W.leaf_mu;
+    const StageVec<uint2>& nodes = W.nodes;
+    const StageVec<int32_t>&tree_off = W.tree_off, &leaf_off = W.leaf_off;
+    const StageVec<double>& leaf_mu = W.leaf_mu;
     int rc;
     pt.lap("");                                      // restart: pack_walk_form reports its own time
     if ((rc = upload(&f->dev.nodes, nodes))) return rc;
@@ -1109,7 +1182,7 @@ int forest_upload(bartint_forest* f) {
     pt.lap("upload: H2D walk form");
     FastPlan P;
     if (f->no_fast_plan) f->table_ok = false;
-    else plan_fast_path(f, tree_off, P);
+    else plan_fast_path(f, tree_off.data(), P);
     pt.lap("");
     if (!f->table_ok) {
         if (f->defer_upload_sync) return BARTINT_OK;
