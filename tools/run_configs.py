@@ -72,7 +72,7 @@ def run(cfg, scale):
     rel = float(((s_tab - s_walk).abs() / s_walk.abs().clamp_min(1e-3 * n_sub)).max())
     out = {"cfg": cfg, "workload": c["name"], "S": S, "m": m, "d": d, "points": N, "tree_evals": S * m * N,
            "ms": min(times), "kernel_ms": min(kms), "evals_per_s": S * m * N / (min(times) * 1e-3),
-           "table_kernel": prof["table_kernel"], "moments": want_mom, "max_internal_nodes": f.max_internal,
+           "kernel": prof.get("kernel"), "table_kernel": prof["table_kernel"], "moments": want_mom, "max_internal_nodes": f.max_internal,
            "groups": f.n_groups, "table_bits": f.table_bits, "table_vs_walk_rel_err": rel,
            "forest_gen_s": t_gen, "forest_upload_s": t_upload}
     if c["measure"] == "uniform":
