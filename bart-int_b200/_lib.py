@@ -48,6 +48,7 @@ SIGNATURES = {
                                                    c_int32_p, C.c_int32, C.c_double, C.c_double, handle_p]),
     "bartint_forest_cutpoints": (C.c_int, [C.c_void_p, c_int32_p, c_double_p]),
     "bartint_eval_points_full_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "bartint_sum_rows_device": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "bartint_topk_device": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "bartint_topk": (C.c_int, [c_double_p, C.c_int64, C.c_int32, c_int64_p, c_double_p]),
     "bartint_forest_route": (C.c_int, [C.c_void_p]),

@@ -409,7 +409,7 @@ int bartint_forest_bitslice_info(const bartint_forest* f, int64_t info[16]) {
     for (int k = 0; k < 16; ++k) info[k] = 0;
     if (!f->bs_ok) return BARTINT_OK;
     info[0] = 1; info[1] = f->bs_ncuts; info[2] = f->bs_ch; info[3] = f->bs_rows; info[4] = f->bs_anc; info[5] = f->bs_q;
-    info[6] = bs_pool_bytes(f); info[7] = (int64_t)(f->bs_ncuts + 1) * (f->bs_ch * 16 + 4);
+    info[6] = bs_pool_bytes(f); info[7] = (int64_t)bs_smem_bytes(f);
     for (int k = 0; k < 5; ++k) info[8 + k] = f->bs_class_nodes[k];
     info[13] = f->bs_refs_total;
     info[15] = (f->S + 31) / 32;
@@ -828,6 +828,11 @@ int bartint_merge_moments_device(const bartint_forest* f, uint32_t flags, int32_
                                  weights_len, d_point_mean_out, d_point_var_out, st);
     cudaFreeAsync(d_counts, st);
     return rc;
+}
+
+int bartint_sum_rows_device(const double* d_rows, int32_t n_rows, int32_t n, double* d_out, void* stream) {
+    BI_REQUIRE(n_rows >= 1 && n >= 0 && (n == 0 || (d_rows != nullptr && d_out != nullptr)), BARTINT_ERR_ARG, "bad arguments");
+    return launch_reduce_draw_parts(d_rows, n_rows, n, d_out, (cudaStream_t)stream);
 }
 
 int bartint_argmax_ties_device(const double* d_values, int64_t n, int64_t* d_out, void* stream) {

@@ -286,6 +286,7 @@ void bs_configure(bartint_forest* f);                        // host: does the b
 int launch_build_bitslice(bartint_forest* f, cudaStream_t st);   // device: walk form -> ELL rows
 int bs_tile(const bartint_forest* f);
 int64_t bs_pool_bytes(const bartint_forest* f);
+size_t bs_smem_bytes(const bartint_forest* f);
 int launch_eval_bitslice(const bartint_forest* f, const bartint_points* p, const EvalPlan& plan, double* draw_part,
                          cudaStream_t st);
 int launch_bs_reduce(const bartint_forest* f, const double* draw_part, int n_tiles, int32_t draw_begin, int ndraws,

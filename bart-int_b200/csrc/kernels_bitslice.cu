@@ -281,7 +281,7 @@ void bs_configure(bartint_forest* f) {
     if (f->draw_internal_max < 1 || f->draw_internal_max >= 65535 || f->m >= 8000) return;
     int ch = 0;
     for (int c : {8, 4, 2})
-        if ((size_t)(ncuts + 1) * (size_t)(c * 16 + 4) + 64 <= BS_SMEM_MAX) { ch = c; break; }
+        if ((size_t)(ncuts + 1) * (size_t)(c * 16 + 4) + 64 + (size_t)f->d * (size_t)c * 128 <= BS_SMEM_MAX) { ch = c; break; }
     if (ch == 0 || (ncuts + 1) * (int64_t)ch >= 1 << 14) return;         // row offsets are 14-bit counts of 16 bytes
     f->bs_ncuts = (int32_t)ncuts;
     f->bs_ch = ch;
@@ -352,6 +352,9 @@ struct BsParams {
     double* draw_part;          // [n_tiles][draw_end - draw_begin]
 };
 
+// shared-memory layout of the evaluation kernel: [mask rows][row counts][slice counter][staged codes d x TILE]
+__host__ __device__ inline size_t bs_stage_off(int n_rows, int rowb) { return (((size_t)n_rows * (size_t)(rowb + 4) + 16 + 15) & ~(size_t)15); }
+
 __device__ __forceinline__ int popc4(const uint4& v) { return __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w); }
 
 // Population count of a long run of words with fewer POPC: POPC runs on the quarter-rate XU pipe (one warp instruction
@@ -412,26 +415,44 @@ __global__ void __launch_bounds__(BS_THREADS, 1) eval_bitslice_kernel(const BsPa
     // sets bit i of row (j, code - 1) for each of its 32 points (plain read-modify-write, no other thread touches the
     // column), then ORs the rows downwards: M[j, c] = points with code > c.  Lanes hold consecutive columns, so every
     // access is bank-conflict free, and no barrier is needed until the table is complete. ----
+    // (the tile's codes are first staged feature-major in shared memory with coalesced loads: a thread then needs two
+    //  LDS.128 for the 32 codes of its column instead of 32 strided byte loads from global memory)
+    unsigned char* const s_codes = smem + bs_stage_off(n_rows, ROWB);                  // [d][TILE]
+    if (prm.codes_pm != nullptr) {
+        for (int pt = tid; pt < TILE; pt += BS_THREADS) {
+            const int64_t i = tile_base + pt;
+            const uint4 v = i < prm.N ? __ldg(&prm.codes_pm[i]) : make_uint4(0u, 0u, 0u, 0u);
+            const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if (j < prm.d) s_codes[j * TILE + pt] = (unsigned char)(wv[j >> 2] >> (8 * (j & 3)));
+        }
+    } else {
+        for (int q = tid; q < prm.d * (TILE / 4); q += BS_THREADS) {                   // 4 points per thread and step
+            const int j = q / (TILE / 4), p4 = (q % (TILE / 4)) * 4;
+            const int64_t i = tile_base + p4;                                          // rows are padded to 4096: i + 3 < Npad
+            uint32_t c4 = i < prm.Npad ? __ldg(reinterpret_cast<const uint32_t*>(prm.codes + (int64_t)j * prm.Npad + i)) : 0u;
+            if (i + 3 >= prm.N) {                                                      // padding rows count as code 0
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+                    if (i + b >= prm.N) c4 &= ~(0xFFu << (8 * b));
+            }
+            *reinterpret_cast<uint32_t*>(s_codes + j * TILE + p4) = c4;
+        }
+    }
+    __syncthreads();
     for (int item = tid; item < prm.d * WORDS; item += BS_THREADS) {
         const int j = item / WORDS, w = item % WORDS;
         const int r0 = __ldg(&prm.cut_off[j]), r1 = __ldg(&prm.cut_off[j + 1]);
         uint32_t* const col = reinterpret_cast<uint32_t*>(s_mask) + w;
         for (int r = r0; r < r1; ++r) col[(size_t)r * WORDS] = 0u;
-        const int64_t i0 = tile_base + (int64_t)w * 32;
-        if (prm.codes_pm != nullptr) {
-            const unsigned char* src = reinterpret_cast<const unsigned char*>(prm.codes_pm) + j;   // byte j of each 16-byte record
-#pragma unroll 4
-            for (int i = 0; i < 32; ++i) {
-                const uint32_t c = i0 + i < prm.N ? (uint32_t)__ldg(src + (i0 + i) * 16) : 0u;
-                if (c != 0u) col[(size_t)(r0 + (int)c - 1) * WORDS] |= 1u << i;
-            }
-        } else {
-            const uint8_t* src = prm.codes + (int64_t)j * prm.Npad;
-#pragma unroll 4
-            for (int i = 0; i < 32; ++i) {
-                const uint32_t c = i0 + i < prm.N ? (uint32_t)__ldg(src + i0 + i) : 0u;
-                if (c != 0u) col[(size_t)(r0 + (int)c - 1) * WORDS] |= 1u << i;
-            }
+        const uint4 ca = *reinterpret_cast<const uint4*>(s_codes + j * TILE + w * 32);
+        const uint4 cb = *reinterpret_cast<const uint4*>(s_codes + j * TILE + w * 32 + 16);
+        const uint32_t cw[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const uint32_t c = (cw[i >> 2] >> (8 * (i & 3))) & 0xFFu;
+            if (c != 0u) col[(size_t)(r0 + (int)c - 1) * WORDS] |= 1u << i;
         }
         uint32_t m = 0u;
         for (int r = r1 - 1; r >= r0; --r) {
@@ -556,7 +577,9 @@ __global__ void __launch_bounds__(BS_THREADS, 1) eval_bitslice_kernel(const BsPa
     }
 }
 
-size_t bs_smem_bytes(const bartint_forest* f) { return (size_t)(f->bs_ncuts + 1) * (size_t)(f->bs_ch * 16 + 4) + 16; }
+size_t bs_smem_bytes(const bartint_forest* f) {
+    return bs_stage_off(f->bs_ncuts + 1, f->bs_ch * 16) + (size_t)f->d * (size_t)f->bs_ch * 128;
+}
 int bs_tile(const bartint_forest* f) { return f->bs_ch * 128; }
 int64_t bs_pool_bytes(const bartint_forest* f) { return f->bs_ok ? bs_layout_of(f).slice_bytes * ((f->S + 31) / 32) : 0; }
 
@@ -597,33 +620,50 @@ int launch_eval_bitslice(const bartint_forest* f, const bartint_points* p, const
     return BARTINT_OK;
 }
 
-// draw_sum[s] = sum over tiles of draw_part[tile][s]  +  N * base[s]   (tiles added in fixed order, 8 interleaved
-// partial sums like reduce_draw_parts_kernel; base = sum over the draw's trees of the leftmost leaf value)
+// draw_sum[s] = sum over tiles of draw_part[tile][s]  +  N * base[s]   (base = sum over the draw's trees of the
+// leftmost leaf value).  The tiles are added in a fixed order that depends only on their number: blocks of
+// BS_RED_BLOCK tiles (grid.y), inside a block 8 interleaved partial sums like reduce_draw_parts_kernel; a second launch
+// of the same kernel adds the blocks' sums when there is more than one (cfg 4: 97 656 tiles x 2000 draws = 1.56 GB of
+// partials, which 63 CTAs walking all tiles read at a fraction of the HBM rate).
+constexpr int BS_RED_BLOCK = 1024;
 __global__ void __launch_bounds__(256) bs_reduce_kernel(const double* __restrict__ part, int n_tiles, int ndraws,
                                                         const double* __restrict__ base, double n_points,
                                                         double* __restrict__ out) {
     __shared__ double s_part[8][33];
     const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
     const int s = blockIdx.x * 32 + x;
+    const int t0 = blockIdx.y * BS_RED_BLOCK, t1 = min(t0 + BS_RED_BLOCK, n_tiles);
     double acc = 0.0;
     if (s < ndraws)
-        for (int t = y; t < n_tiles; t += 8) acc += part[(int64_t)t * ndraws + s];
+        for (int t = t0 + y; t < t1; t += 8) acc += part[(int64_t)t * ndraws + s];
     s_part[y][x] = acc;
     __syncthreads();
     if (y == 0 && s < ndraws) {
         double tot = s_part[0][x];
 #pragma unroll
         for (int k = 1; k < 8; ++k) tot += s_part[k][x];
-        out[s] = tot + n_points * base[s];
+        out[(int64_t)blockIdx.y * ndraws + s] = base != nullptr ? tot + n_points * base[s] : tot;
     }
 }
 
 int launch_bs_reduce(const bartint_forest* f, const double* draw_part, int n_tiles, int32_t draw_begin, int ndraws,
                      int64_t N, double* draw_sum, cudaStream_t st) {
     if (ndraws == 0) return BARTINT_OK;
-    bs_reduce_kernel<<<(ndraws + 31) / 32, 256, 0, st>>>(draw_part, n_tiles, ndraws, f->dev.bs_base + draw_begin, (double)N,
-                                                         draw_sum);
-    count_launch();
+    const double* base = f->dev.bs_base + draw_begin;
+    const int n_blocks = (n_tiles + BS_RED_BLOCK - 1) / BS_RED_BLOCK;
+    if (n_blocks <= 1) {
+        bs_reduce_kernel<<<(ndraws + 31) / 32, 256, 0, st>>>(draw_part, n_tiles, ndraws, base, (double)N, draw_sum);
+        count_launch();
+    } else {
+        BI_REQUIRE(n_blocks <= BS_RED_BLOCK, BARTINT_ERR_UNSUPPORTED, "more than %d tiles in one evaluation", BS_RED_BLOCK * BS_RED_BLOCK);
+        double* tmp = nullptr;
+        BI_CUDA(cudaMallocAsync((void**)&tmp, sizeof(double) * (size_t)n_blocks * (size_t)ndraws, st));
+        bs_reduce_kernel<<<dim3((unsigned)((ndraws + 31) / 32), (unsigned)n_blocks), 256, 0, st>>>(draw_part, n_tiles, ndraws, nullptr,
+                                                                                                   0.0, tmp);
+        bs_reduce_kernel<<<(ndraws + 31) / 32, 256, 0, st>>>(tmp, n_blocks, ndraws, base, (double)N, draw_sum);
+        count_launch(2);
+        cudaFreeAsync(tmp, st);
+    }
     BI_CUDA(cudaGetLastError());
     return BARTINT_OK;
 }

@@ -43,8 +43,17 @@ def all_gather_rows(t: torch.Tensor, group=None) -> torch.Tensor:
     return out
 
 
-def ordered_sum(rows: torch.Tensor) -> torch.Tensor:
-    """Sum over dim 0 in index order (deterministic, identical on every rank)."""
+def ordered_sum(rows: torch.Tensor, stream=None) -> torch.Tensor:
+    """Sum over dim 0 in a fixed order (deterministic, identical on every rank).  CUDA tensors: ONE launch of the
+    library's fixed-order row reduction (bartint_sum_rows_device) instead of world - 1 elementwise kernels."""
+    if rows.is_cuda and rows.dtype == torch.float64 and rows.dim() == 2 and rows.is_contiguous():
+        from . import _lib
+        out = torch.empty(rows.shape[1], dtype=torch.float64, device=rows.device)
+        st = torch.cuda.current_stream().cuda_stream if stream is None else stream
+        rc = _lib.load().bartint_sum_rows_device(rows.data_ptr(), rows.shape[0], rows.shape[1], out.data_ptr(), st)
+        if rc != 0:
+            raise RuntimeError(_lib.load().bartint_last_error().decode())
+        return out
     acc = rows[0].clone()
     for r in range(1, rows.shape[0]):
         acc += rows[r]
@@ -68,9 +77,9 @@ def allreduce_draw_sums(local_sums: torch.Tensor, n_local: int, group=None, n_to
 
 
 def gather_moments(local_mean: torch.Tensor, local_m2: torch.Tensor, n_local_draws: int, group=None, counts=None):
-    """Draw-sharded exchange: (draw counts per rank, means [world, C], M2s [world, C])."""
-    means = all_gather_rows(local_mean, group)
-    m2s = all_gather_rows(local_m2, group)
+    """Draw-sharded exchange: (draw counts per rank, means [world, C], M2s [world, C]) -- one all-gather for both."""
+    both = all_gather_rows(torch.stack([local_mean, local_m2]), group)          # [world, 2, C]
+    means, m2s = both[:, 0].contiguous(), both[:, 1].contiguous()
     if counts is None:
         c = all_gather_rows(torch.tensor([n_local_draws], dtype=torch.int32, device=local_mean.device), group)
         counts = c.flatten().cpu().numpy().astype(np.int32)          # device->host sync; pass counts to avoid it

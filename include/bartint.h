@@ -259,6 +259,11 @@ int bartint_eval_points_full_device(const bartint_forest* f, const bartint_point
 int bartint_finalize_draws_device(const bartint_forest* f, uint32_t flags, const double* d_draw_sum, int32_t ndraws,
                                   int64_t n_points, double* d_draw_mean, double* d_mean_var, void* stream);
 
+/* out[i] = sum over r of d_rows[r * n + i], the rows added in a fixed order (rows 0, 8, 16, .. then 1, 9, .. like the tile
+ * reduction of the evaluation kernels) so that every rank of a point-sharded evaluation gets bit-identical totals from
+ * the all-gathered per-draw partial sums.  Asynchronous on `stream`. */
+int bartint_sum_rows_device(const double* d_rows, int32_t n_rows, int32_t n, double* d_out, void* stream);
+
 /* which(var == max(var)) on the device (src/BARTInt.R:315,387; bartMean.R:51): d_out[0] = 0-based index of the
  * first maximum, d_out[1] = number of elements equal to it; {-1, 0} if any value is NaN or n == 0.  The random tie
  * break -- and R's sample(scalar) quirk, SURVEY App. B2 -- stay with the caller. */
