@@ -146,6 +146,8 @@ static int forest_from_dbarts_impl(const char* const* tree_strings, const double
                                    int64_t n, int32_t d, const int32_t* cut_offsets, const double* cut_values,
                                    double y_min, double y_max, int32_t m, int32_t S, bool defer_upload_sync,
                                    bartint_forest** out, bool no_fast_plan = false);
+static int forest_from_image(const void* host_header, int64_t host_bytes, const void* d_blob, int src_device,
+                             int64_t device_bytes, cudaStream_t st, bool wait, bartint_forest** out);
 
 int bartint_forest_from_dbarts098(const char* const* tree_strings, const double* tree_fits, const double* x_train,
                                   int64_t n, int32_t d, const int32_t* cut_offsets, const double* cut_values,
@@ -445,6 +447,9 @@ int bartint_forest_export_soa(const bartint_forest* f, int64_t* tree_node_offset
 
 void bartint_forest_destroy(bartint_forest* f) {
     if (f == nullptr) return;
+    for (bartint_forest* r : f->replicas)          // copies on the other members of the device group
+        if (r && r != f) bartint_forest_destroy(r);
+    f->replicas.clear();
     {
         DeviceGuard g(f->device);
         // the buffers are freed in default-stream order: make that stream wait for evaluations on other streams
@@ -934,58 +939,51 @@ int bartint_eval_points(const bartint_forest* f, const bartint_points* p, uint32
     return BARTINT_OK;
 }
 
-// One-shot host-buffer evaluation.  Large matrices are processed as a pipeline over row blocks: the host->device copy
-// of block k+1 (copy stream) overlaps the binning + evaluation of block k (compute stream); per-block draw sums are
-// added in block order, per-point outputs land at their offsets.  Results do not depend on the block count up to the
-// fp64 summation order of the per-draw sums (fixed by N alone).
-int bartint_eval(const bartint_forest* f, const double* X, int64_t N, int32_t d, uint32_t flags, const double* weights,
-                 int64_t weights_len, double* draw_mean, double* point_mean, double* point_var, double* full_pred) {
-    BI_REQUIRE(f != nullptr, BARTINT_ERR_ARG, "forest is NULL");
-    BI_REQUIRE(N >= 0 && (N * d == 0 || X != nullptr), BARTINT_ERR_ARG, "X is NULL or N < 0");
-    BI_REQUIRE(d == f->d, BARTINT_ERR_ARG, "point matrix has %d columns but the forest was fit on %d variables", d, f->d);
-    constexpr int64_t kMinPipelined = 1 << 18;
-    if (N < kMinPipelined || full_pred != nullptr || f->S == 0) {      // small / full-matrix requests: single shot
-        bartint_points* p = nullptr;
-        int rc = bartint_points_from_host(f, X, N, d, &p);
-        if (rc) return rc;
-        rc = bartint_eval_points(f, p, flags, 0, f->S, weights, weights_len, draw_mean, point_mean, point_var, full_pred);
-        bartint_points_destroy(p);
-        return rc;
-    }
-    BI_REQUIRE(weights == nullptr || weights_len == 1 || weights_len == N, BARTINT_ERR_ARG,
-               "weights must have length 1 or N");
+// One shard of a host-buffer evaluation on ONE device (the forest's): rows [0, N) of a column-major matrix with
+// leading dimension ld, processed as a pipeline over row blocks -- the host->device copy of block k+1 (copy stream)
+// overlaps the binning + evaluation of block k (compute stream); per-block draw sums are added in block order,
+// per-point outputs (and the S x N matrix, block by block) land at their offsets.  d_sum_keep != NULL: leave the scaled
+// per-draw sums of these rows there (device, S doubles) for a cross-device exchange instead of finalising draw_mean.
+// Blocks until its streams are done.
+static int eval_shard(const bartint_forest* f, const double* X, int64_t N, int64_t ld, int32_t d, uint32_t flags,
+                      const double* weights, int64_t weights_len, double* d_sum_keep, double* draw_mean, double* point_mean,
+                      double* point_var, double* full_pred) {
     DeviceGuard g(f->device);
     const int S = f->S;
     const int scaled = (flags & BARTINT_SCALED_UNITS) ? 1 : 0;
     const double scale = f->y_max - f->y_min, y0 = f->y_min;
     const bool want_mom = point_mean != nullptr || point_var != nullptr;
+    const bool want_full = full_pred != nullptr && S > 0;
     const int K = 4;                                                   // row blocks
-    const int64_t blk = (((N + K - 1) / K + TK_NPAD - 1) / TK_NPAD) * TK_NPAD;
-    const int nblk = (int)((N + blk - 1) / blk);
+    int64_t blk = (((N + K - 1) / K + TK_NPAD - 1) / TK_NPAD) * TK_NPAD;
+    if (want_full) blk = std::min<int64_t>(blk, std::max<int64_t>(TK_NPAD, ((int64_t)1 << 27) / std::max(S, 1) / TK_NPAD * TK_NPAD));   // <= 1 GiB per block buffer
+    const int nblk = (int)std::max<int64_t>((N + blk - 1) / blk, 1);
     cudaStream_t cs = nullptr, xs = nullptr;       // compute, copy
     cudaEvent_t copied[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr};
-    double *dX[2] = {nullptr, nullptr}, *d_sums = nullptr, *d_sum = nullptr, *d_out = nullptr, *d_mean = nullptr,
-           *d_m2 = nullptr, *d_omean = nullptr, *d_ovar = nullptr, *d_w = nullptr;
+    double *dX[2] = {nullptr, nullptr}, *dF[2] = {nullptr, nullptr}, *d_sums = nullptr, *d_sum = nullptr, *d_out = nullptr,
+           *d_mean = nullptr, *d_m2 = nullptr, *d_omean = nullptr, *d_ovar = nullptr, *d_w = nullptr;
     int32_t* d_cnt = nullptr;
     bartint_points* pts[2] = {nullptr, nullptr};
     int rc = BARTINT_OK;
     cudaError_t e = cudaSuccess;
     auto ok = [&](cudaError_t err) { if (e == cudaSuccess && err != cudaSuccess) e = err; return e == cudaSuccess; };
+    const size_t n1 = (size_t)std::max<int64_t>(N, 1), s1 = (size_t)std::max(S, 1);
     ok(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
     ok(cudaStreamCreateWithFlags(&xs, cudaStreamNonBlocking));
     for (int k = 0; k < 2; ++k) {
         ok(cudaEventCreateWithFlags(&copied[k], cudaEventDisableTiming));
         ok(cudaEventCreateWithFlags(&consumed[k], cudaEventDisableTiming));
-        ok(cudaMallocAsync((void**)&dX[k], sizeof(double) * (size_t)blk * (size_t)d, cs));
+        ok(cudaMallocAsync((void**)&dX[k], sizeof(double) * (size_t)blk * (size_t)std::max(d, 1), cs));
+        if (want_full) ok(cudaMallocAsync((void**)&dF[k], sizeof(double) * (size_t)blk * s1, cs));
     }
-    ok(cudaMallocAsync((void**)&d_sums, sizeof(double) * (size_t)nblk * (size_t)S, cs));
-    ok(cudaMallocAsync((void**)&d_sum, sizeof(double) * (size_t)S, cs));
-    ok(cudaMallocAsync((void**)&d_out, sizeof(double) * (size_t)S, cs));
+    ok(cudaMallocAsync((void**)&d_sums, sizeof(double) * (size_t)nblk * s1, cs));
+    ok(cudaMallocAsync((void**)&d_sum, sizeof(double) * s1, cs));
+    ok(cudaMallocAsync((void**)&d_out, sizeof(double) * s1, cs));
     if (want_mom) {
-        ok(cudaMallocAsync((void**)&d_mean, sizeof(double) * (size_t)N, cs));
-        ok(cudaMallocAsync((void**)&d_m2, sizeof(double) * (size_t)N, cs));
-        ok(cudaMallocAsync((void**)&d_omean, sizeof(double) * (size_t)N, cs));
-        ok(cudaMallocAsync((void**)&d_ovar, sizeof(double) * (size_t)N, cs));
+        ok(cudaMallocAsync((void**)&d_mean, sizeof(double) * n1, cs));
+        ok(cudaMallocAsync((void**)&d_m2, sizeof(double) * n1, cs));
+        ok(cudaMallocAsync((void**)&d_omean, sizeof(double) * n1, cs));
+        ok(cudaMallocAsync((void**)&d_ovar, sizeof(double) * n1, cs));
         ok(cudaMallocAsync((void**)&d_cnt, sizeof(int32_t), cs));
         if (weights != nullptr) {
             ok(cudaMallocAsync((void**)&d_w, sizeof(double) * (size_t)weights_len, cs));
@@ -994,11 +992,11 @@ int bartint_eval(const bartint_forest* f, const double* X, int64_t N, int32_t d,
         ok(cudaMemcpyAsync(d_cnt, &S, sizeof(int32_t), cudaMemcpyHostToDevice, cs));
     }
     ok(cudaStreamSynchronize(cs));                 // buffers exist before the copy stream touches them
-    for (int k = 0; k < nblk && e == cudaSuccess && rc == BARTINT_OK; ++k) {
+    for (int k = 0; k < nblk && e == cudaSuccess && rc == BARTINT_OK && N > 0; ++k) {
         const int b = k & 1;
         const int64_t r0 = (int64_t)k * blk, rows = std::min<int64_t>(blk, N - r0);
         if (k >= 2) ok(cudaStreamWaitEvent(xs, consumed[b], 0));       // block k-2 has been binned out of dX[b]
-        ok(cudaMemcpy2DAsync(dX[b], sizeof(double) * (size_t)rows, X + r0, sizeof(double) * (size_t)N,
+        ok(cudaMemcpy2DAsync(dX[b], sizeof(double) * (size_t)rows, X + r0, sizeof(double) * (size_t)ld,
                              sizeof(double) * (size_t)rows, (size_t)d, cudaMemcpyHostToDevice, xs));
         ok(cudaEventRecord(copied[b], xs));
         ok(cudaStreamWaitEvent(cs, copied[b], 0));
@@ -1007,24 +1005,30 @@ int bartint_eval(const bartint_forest* f, const double* X, int64_t N, int32_t d,
         rc = bartint_points_from_device(f, dX[b], rows, d, rows, cs, &pts[b]);
         ok(cudaEventRecord(consumed[b], cs));
         if (rc == BARTINT_OK)
-            rc = eval_core(f, pts[b], flags, 0, S, d_sums + (size_t)k * S, want_mom ? d_mean + r0 : nullptr,
-                           want_mom ? d_m2 + r0 : nullptr, nullptr, nullptr, scale, y0, scaled, cs);
+            rc = eval_core(f, pts[b], flags, 0, S, d_sums + (size_t)k * s1, want_mom ? d_mean + r0 : nullptr,
+                           want_mom ? d_m2 + r0 : nullptr, nullptr, want_full ? dF[b] : nullptr, scale, y0, scaled, cs);
+        if (rc == BARTINT_OK && want_full)          // the block's S x rows slab is contiguous in R's layout
+            ok(cudaMemcpyAsync(full_pred + (size_t)S * (size_t)r0, dF[b], sizeof(double) * (size_t)S * (size_t)rows,
+                               cudaMemcpyDeviceToHost, cs));
     }
-    if (e == cudaSuccess && rc == BARTINT_OK) rc = launch_reduce_draw_parts(d_sums, nblk, S, d_sum, cs);
-    if (e == cudaSuccess && rc == BARTINT_OK && draw_mean != nullptr)
+    if (e == cudaSuccess && rc == BARTINT_OK && N == 0) ok(cudaMemsetAsync(d_sums, 0, sizeof(double) * s1, cs));
+    if (e == cudaSuccess && rc == BARTINT_OK && S > 0)
+        rc = launch_reduce_draw_parts(d_sums, N > 0 ? nblk : 1, S, d_sum_keep ? d_sum_keep : d_sum, cs);
+    if (e == cudaSuccess && rc == BARTINT_OK && draw_mean != nullptr && d_sum_keep == nullptr && S > 0)
         rc = launch_finalize_draws(d_sum, S, N, scale, y0, scaled, d_out, cs);
-    if (e == cudaSuccess && rc == BARTINT_OK && want_mom)
+    if (e == cudaSuccess && rc == BARTINT_OK && want_mom && N > 0)
         rc = launch_merge_shards(d_mean, d_m2, 1, d_cnt, N, scale, y0, scaled, d_w, weights_len, d_omean, d_ovar, cs);
     if (e == cudaSuccess && rc == BARTINT_OK) {
-        if (draw_mean) ok(cudaMemcpyAsync(draw_mean, d_out, sizeof(double) * (size_t)S, cudaMemcpyDeviceToHost, cs));
-        if (point_mean) ok(cudaMemcpyAsync(point_mean, d_omean, sizeof(double) * (size_t)N, cudaMemcpyDeviceToHost, cs));
-        if (point_var) ok(cudaMemcpyAsync(point_var, d_ovar, sizeof(double) * (size_t)N, cudaMemcpyDeviceToHost, cs));
+        if (draw_mean && d_sum_keep == nullptr && S > 0) ok(cudaMemcpyAsync(draw_mean, d_out, sizeof(double) * (size_t)S, cudaMemcpyDeviceToHost, cs));
+        if (point_mean && N > 0) ok(cudaMemcpyAsync(point_mean, d_omean, sizeof(double) * (size_t)N, cudaMemcpyDeviceToHost, cs));
+        if (point_var && N > 0) ok(cudaMemcpyAsync(point_var, d_ovar, sizeof(double) * (size_t)N, cudaMemcpyDeviceToHost, cs));
     }
     if (cs) ok(cudaStreamSynchronize(cs));
     if (xs) cudaStreamSynchronize(xs);
     for (int k = 0; k < 2; ++k) {
         if (pts[k]) bartint_points_destroy(pts[k]);
         if (dX[k]) cudaFreeAsync(dX[k], cs);
+        if (dF[k]) cudaFreeAsync(dF[k], cs);
         if (copied[k]) cudaEventDestroy(copied[k]);
         if (consumed[k]) cudaEventDestroy(consumed[k]);
     }
@@ -1035,6 +1039,130 @@ int bartint_eval(const bartint_forest* f, const double* X, int64_t N, int32_t d,
     if (cs) { cudaStreamSynchronize(cs); cudaStreamDestroy(cs); }
     if (xs) cudaStreamDestroy(xs);
     if (rc == BARTINT_OK && e != cudaSuccess) rc = cuda_fail(e, "bartint_eval pipeline", __FILE__, __LINE__);
+    return rc;
+}
+
+// Copies of a forest on the other members of the device group (built on first use, kept with the forest): the image
+// is packed once on the forest's device and pulled by every member over NVLink.
+static int ensure_replicas(const bartint_forest* cf) {
+    bartint_forest* f = const_cast<bartint_forest*>(cf);          // the replica list is a cache (one caller at a time)
+    const int G = group_size();
+    if ((int)f->replicas.size() == G && f->replica_generation == group_generation()) return BARTINT_OK;
+    for (bartint_forest* r : f->replicas)
+        if (r && r != f) bartint_forest_destroy(r);
+    f->replicas.assign((size_t)G, nullptr);
+    f->replicas[0] = f;
+    f->replica_generation = group_generation();
+    if (G == 1) return BARTINT_OK;
+    DeviceGuard g(f->device);
+    int64_t hb = 0, db = 0;
+    int rc = bartint_forest_image_size(f, &hb, &db);
+    if (rc) return rc;
+    auto hdr = std::make_shared<std::vector<unsigned char>>((size_t)hb);
+    void* blob = nullptr;
+    BI_CUDA(cudaMallocAsync(&blob, (size_t)db, nullptr));
+    rc = bartint_forest_pack(f, hdr->data(), hb, blob, db, nullptr);
+    cudaEvent_t pev = nullptr;
+    if (rc == BARTINT_OK && (cudaEventCreateWithFlags(&pev, cudaEventDisableTiming) != cudaSuccess || cudaEventRecord(pev, nullptr) != cudaSuccess))
+        rc = cuda_fail(cudaGetLastError(), "replicate forest", __FILE__, __LINE__);
+    if (rc == BARTINT_OK) {
+        const int dev0 = f->device;
+        for (int k = 1; k < G; ++k) {
+            bartint_forest** slot = &f->replicas[(size_t)k];
+            group_post(k, [=] {
+                cudaStream_t ws = group_stream(k);
+                BI_CUDA(cudaStreamWaitEvent(ws, pev, 0));
+                return forest_from_image(hdr->data(), hb, blob, dev0, db, ws, true, slot);
+            });
+        }
+        rc = group_wait();
+    }
+    if (pev) cudaEventDestroy(pev);
+    cudaFreeAsync(blob, nullptr);
+    return rc;
+}
+
+// One-shot host-buffer evaluation (the R entry points predict / bartint_candidate_var / bartint_draw_means end here).
+// With a device group (bartint_init) and a matrix of at least 2^16 rows per member the rows are sharded over the
+// members: every member evaluates its rows on its replica of the forest, per-point outputs go straight to their place
+// in the caller's arrays, and the per-draw sums are all-gathered and added in member order.
+int bartint_eval(const bartint_forest* f, const double* X, int64_t N, int32_t d, uint32_t flags, const double* weights,
+                 int64_t weights_len, double* draw_mean, double* point_mean, double* point_var, double* full_pred) {
+    BI_REQUIRE(f != nullptr, BARTINT_ERR_ARG, "forest is NULL");
+    BI_REQUIRE(N >= 0 && (N * d == 0 || X != nullptr), BARTINT_ERR_ARG, "X is NULL or N < 0");
+    BI_REQUIRE(d == f->d, BARTINT_ERR_ARG, "point matrix has %d columns but the forest was fit on %d variables", d, f->d);
+    constexpr int64_t kMinPipelined = 1 << 18;
+    const int G = group_size();
+    const char* gm = std::getenv("BARTINT_GROUP_MIN_ROWS");          // rows per member below which one GPU does it all
+    const int64_t group_min = gm ? (int64_t)atoll(gm) : (int64_t)1 << 16;
+    const bool grouped = G > 1 && group_has(f->device) && f->S > 0 && N >= group_min * G && f->image_base == nullptr;
+    if (!grouped && (N < kMinPipelined || full_pred != nullptr || f->S == 0)) {      // small / full-matrix requests: single shot
+        bartint_points* p = nullptr;
+        int rc = bartint_points_from_host(f, X, N, d, &p);
+        if (rc) return rc;
+        rc = bartint_eval_points(f, p, flags, 0, f->S, weights, weights_len, draw_mean, point_mean, point_var, full_pred);
+        bartint_points_destroy(p);
+        return rc;
+    }
+    BI_REQUIRE(weights == nullptr || weights_len == 1 || weights_len == N, BARTINT_ERR_ARG,
+               "weights must have length 1 or N");
+    if (!grouped) return eval_shard(f, X, N, N, d, flags, weights, weights_len, nullptr, draw_mean, point_mean, point_var, nullptr);
+
+    int rc = ensure_replicas(f);
+    if (rc) return rc;
+    const int S = f->S;
+    const int64_t per = ((N + G - 1) / G + 1023) / 1024 * 1024;
+    std::vector<double*> d_sum((size_t)G, nullptr), d_gath((size_t)G, nullptr);
+    DeviceGuard guard(f->device);
+    cudaStream_t st0 = nullptr;
+    BI_CUDA(cudaStreamCreateWithFlags(&st0, cudaStreamNonBlocking));
+    auto shard = [=, &d_sum, &d_gath](int k, cudaStream_t ws) -> int {
+        const int64_t lo = std::min<int64_t>(N, (int64_t)k * per), rows = std::min<int64_t>(N, (int64_t)(k + 1) * per) - lo;
+        BI_CUDA(cudaMallocAsync((void**)&d_sum[(size_t)k], sizeof(double) * (size_t)S, ws));
+        BI_CUDA(cudaMallocAsync((void**)&d_gath[(size_t)k], sizeof(double) * (size_t)S * (size_t)G, ws));
+        BI_CUDA(cudaStreamSynchronize(ws));
+        const bool wvec = weights != nullptr && weights_len == N;
+        return eval_shard(f->replicas[(size_t)k], X + lo, rows, N, d, flags, wvec ? weights + lo : weights, wvec ? rows : weights_len,
+                          d_sum[(size_t)k], nullptr, point_mean ? point_mean + lo : nullptr, point_var ? point_var + lo : nullptr,
+                          full_pred ? full_pred + (size_t)S * (size_t)lo : nullptr);
+    };
+    for (int k = 1; k < G; ++k) group_post(k, [=] { return shard(k, group_stream(k)); });
+    rc = shard(0, st0);
+    const int rc2 = group_wait();
+    if (rc == BARTINT_OK) rc = rc2;
+    double *d_tot = nullptr, *d_out = nullptr;
+    if (rc == BARTINT_OK && draw_mean != nullptr) {
+        std::vector<cudaStream_t> streams((size_t)G);
+        streams[0] = st0;
+        for (int k = 1; k < G; ++k) streams[(size_t)k] = group_stream(k);
+        rc = group_allgather(d_sum.data(), d_gath.data(), (size_t)S, streams.data());
+        cudaError_t e = cudaMallocAsync((void**)&d_tot, sizeof(double) * 2 * (size_t)S, st0);
+        if (rc == BARTINT_OK && e != cudaSuccess) rc = cuda_fail(e, "bartint_eval group", __FILE__, __LINE__);
+        d_out = d_tot ? d_tot + S : nullptr;
+        if (rc == BARTINT_OK) rc = launch_reduce_draw_parts(d_gath[0], G, S, d_tot, st0);
+        if (rc == BARTINT_OK)
+            rc = launch_finalize_draws(d_tot, S, N, f->y_max - f->y_min, f->y_min, (flags & BARTINT_SCALED_UNITS) ? 1 : 0, d_out, st0);
+        if (rc == BARTINT_OK) {
+            e = cudaMemcpyAsync(draw_mean, d_out, sizeof(double) * (size_t)S, cudaMemcpyDeviceToHost, st0);
+            if (e != cudaSuccess) rc = cuda_fail(e, "bartint_eval group", __FILE__, __LINE__);
+        }
+    }
+    cudaStreamSynchronize(st0);
+    for (int k = 1; k < G; ++k) {
+        double *a = d_sum[(size_t)k], *b = d_gath[(size_t)k];
+        group_post(k, [=] {
+            cudaStreamSynchronize(group_stream(k));
+            if (a) cudaFreeAsync(a, group_stream(k));
+            if (b) cudaFreeAsync(b, group_stream(k));
+            return (int)BARTINT_OK;
+        });
+    }
+    group_wait();
+    if (d_sum[0]) cudaFreeAsync(d_sum[0], st0);
+    if (d_gath[0]) cudaFreeAsync(d_gath[0], st0);
+    if (d_tot) cudaFreeAsync(d_tot, st0);
+    cudaStreamSynchronize(st0);
+    cudaStreamDestroy(st0);
     return rc;
 }
 

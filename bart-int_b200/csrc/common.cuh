@@ -146,6 +146,10 @@ struct bartint_forest {
     int64_t bs_refs_total = 0;         // mask rows referenced by the nodes of depth >= 1 (depth + 1 each)
     std::vector<int32_t> draw_group_off;  // host copy, S+1
     bartint::DeviceForest dev;
+    // replicas on the members of the device group (bartint_eval on a group; [0] = this forest), and the generation of
+    // the group they were built for
+    std::vector<bartint_forest*> replicas;
+    int replica_generation = -1;
     unsigned char* image_base = nullptr;  // forests restored by bartint_forest_unpack: the one allocation behind `dev`
     // profile of the last evaluation
     // slot 0: evaluations producing per-draw sums only; slot 1: evaluations with per-point moments / full output
@@ -250,6 +254,7 @@ int canonicalise_soa(int32_t S, int32_t m, int32_t d, const int64_t* tree_node_o
 // device group (group.cu): single-process multi-GPU.  Member 0 is driven by the calling thread; every other member
 // has a worker thread (its device current, one non-blocking stream) that runs posted tasks in order.
 int group_size();                                   // 1 when bartint_init has not been called
+int group_generation();                             // changes with every bartint_init / bartint_shutdown
 int group_device(int g);
 bool group_has(int device);                         // is `device` member 0 of the group
 cudaStream_t group_stream(int g);                   // member g's worker stream (g >= 1)

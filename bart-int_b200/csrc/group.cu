@@ -111,6 +111,7 @@ struct Group {
 
 std::mutex g_mu;
 Group* g_group = nullptr;
+int g_generation = 0;
 NcclApi g_nccl;
 
 void destroy_group(Group* g) {
@@ -133,6 +134,7 @@ void destroy_group(Group* g) {
 }  // namespace
 
 int group_size() { return g_group ? (int)g_group->devices.size() : 1; }
+int group_generation() { return g_generation; }
 int group_device(int g) { return g_group ? g_group->devices[(size_t)g] : 0; }
 bool group_has(int device) { return g_group != nullptr && g_group->devices[0] == device; }
 cudaStream_t group_stream(int g) { return g_group && g >= 1 ? g_group->workers[(size_t)g]->st : nullptr; }
@@ -303,6 +305,7 @@ int bartint_init(int n_gpus) {
     }
     cudaSetDevice(devices[0]);
     g_group = g.release();
+    ++g_generation;
 #ifdef _OPENMP
     // the members' worker threads need cores of their own: the exporter's OpenMP team spin-waits between its parallel
     // regions, and a team as large as the machine leaves the workers waiting for a scheduler quantum (milliseconds)
@@ -321,6 +324,7 @@ void bartint_shutdown(void) {
     group_wait();
     destroy_group(g_group);
     g_group = nullptr;
+    ++g_generation;
 }
 
 }  // extern "C"

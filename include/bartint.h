@@ -68,7 +68,8 @@ int bartint_set_device(int device);       /* forests/points are created on the c
  * is split into contiguous row shards, one per member, and bartint_design_step_dbarts098 given such a matrix
  * exports the posterior once (all host threads), replicates every chunk's forest image to the other members with
  * peer copies over NVLink, evaluates each member's rows there, and combines the members' per-draw sums with one
- * ncclAllGather + member-ordered sum on the compute streams.  Not thread safe: one caller at a time (R is).
+ * ncclAllGather + member-ordered sum on the compute streams; bartint_eval shards the rows of its host matrix the same
+ * way.  Not thread safe: one caller at a time (R is).
  * bartint_group_exchange(): the name of the exchange in use (for reports). */
 int bartint_init(int n_gpus);
 int bartint_group_size(void);             /* 1 before bartint_init */
@@ -232,7 +233,11 @@ int bartint_eval_points(const bartint_forest* f, const bartint_points* p, uint32
                         const double* weights, int64_t weights_len,
                         double* draw_mean, double* point_mean, double* point_var, double* full_pred);
 
-/* one-shot convenience: bin + evaluate all draws */
+/* one-shot convenience: bin + evaluate all draws (what the R entry points predict / bartint_candidate_var /
+ * bartint_draw_means call).  With a device group (bartint_init) and at least 2^16 rows per member (BARTINT_GROUP_MIN_ROWS)
+ * the rows are sharded over the GPUs: every member evaluates its rows on its own replica of the forest (pulled once over
+ * NVLink and kept with the forest), per-point outputs and the slabs of full_pred go straight to their place in the
+ * caller's arrays, the per-draw sums are all-gathered (ncclAllGather) and added in member order. */
 int bartint_eval(const bartint_forest* f, const double* X, int64_t N, int32_t d, uint32_t flags,
                  const double* weights, int64_t weights_len,
                  double* draw_mean, double* point_mean, double* point_var, double* full_pred);

@@ -80,3 +80,43 @@ def test_group_over_all_gpus_equals_single():
         _same(_step(case, "group"), want)
     finally:
         bi.shutdown_group()
+
+
+def _eval_case(seed=5, S=70, m=9, d=4, N=9000):
+    rng = np.random.default_rng(seed)
+    x_train = rng.random((40, d))
+    ff = synth.prior_forest(seed, S, m, x_train, synth.genz_gaussian(x_train))
+    return ff, rng.random((N, d)), rng.random(N)
+
+
+def _eval_all(ff, X, w):
+    """predict / colVars * weights / rowMeans through the one-shot host entry point (what the R shim calls)"""
+    from bartint_b200 import Forest
+    f = Forest.from_soa(ff)
+    try:
+        a = f.eval(X, weights=w, want=("draw_mean", "point_mean", "point_var"))
+        b = f.eval(X, want=("draw_mean",))
+        c = f.eval(X, want=("full_pred", "draw_mean"))
+        return a, b, c
+    finally:
+        f.close()
+
+
+@pytest.mark.parametrize("members", [2, 3])
+def test_group_eval_equals_single(members, monkeypatch):
+    """bartint_eval on the device group: rows sharded over the members (forest replicas pulled from member 0), per-point
+    outputs written in place, per-draw sums exchanged -- equal to the one-GPU call."""
+    ff, X, w = _eval_case()
+    want = _eval_all(ff, X, w)
+    monkeypatch.setenv("BARTINT_GROUP_DEVICES", ",".join(["0"] * members) if _n_gpus() < members else ",".join(map(str, range(members))))
+    monkeypatch.setenv("BARTINT_GROUP_MIN_ROWS", "1024")
+    try:
+        assert bi.init_group(members) == members
+        for rep in range(2):                      # the second pass reuses the cached replicas
+            got = _eval_all(ff, X, w)
+            for g, wnt in zip(got, want):
+                for k in wnt:
+                    scale = max(float(np.max(np.abs(wnt[k]))), 1e-300)
+                    assert np.max(np.abs(g[k] - wnt[k])) <= 1e-12 * scale, k
+    finally:
+        bi.shutdown_group()
