@@ -59,8 +59,8 @@ static void free_device(DeviceForest& d, unsigned char* image_base = nullptr) {
     d = DeviceForest{};
 }
 
-static int finish_forest(bartint_forest* f, bartint_forest** out) {
-    int rc = forest_finish_host(f);
+static int finish_forest(bartint_forest* f, bartint_forest** out, WalkForm* prebuilt = nullptr) {
+    int rc = prebuilt ? BARTINT_OK : forest_finish_host(f);      // (a prebuilt walk form comes with its statistics)
     if (rc == BARTINT_OK) rc = check_device();
     if (rc == BARTINT_OK) {
         cudaError_t e = cudaGetDevice(&f->device);
@@ -75,7 +75,7 @@ static int finish_forest(bartint_forest* f, bartint_forest** out) {
             cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
         }
         (void)cudaGetLastError();
-        rc = forest_upload(f);
+        rc = forest_upload(f, prebuilt);
     }
     if (rc == BARTINT_OK) {
         cudaError_t e = cudaSuccess;
@@ -175,6 +175,13 @@ static int forest_from_dbarts_impl(const char* const* tree_strings, const double
     f->no_fast_plan = no_fast_plan;
     f->cut_off.assign(cut_offsets, cut_offsets + d + 1);
     f->cut_val.assign(cut_values, cut_values + cut_offsets[d]);
+    static const bool fused = [] { const char* e = std::getenv("BARTINT_FUSED_EXPORT"); return !(e && e[0] == '0'); }();
+    if (no_fast_plan && fused) {      // the design step with few candidates: strings -> walk form in one pass
+        WalkForm W;
+        rc = parse_dbarts_walk(tree_strings, tree_fits, x_train, n, d, cut_offsets, cut_values, m, S, f, W);
+        if (rc) { delete f; return rc; }
+        return finish_forest(f, out, &W);
+    }
     rc = parse_dbarts_forest(tree_strings, tree_fits, x_train, n, d, cut_offsets, cut_values, m, S, f);
     if (rc) { delete f; return rc; }
     return finish_forest(f, out);
@@ -353,6 +360,34 @@ int bartint_debug_export_wbart(const char* trees_text, int64_t text_len, int32_t
     return rc;
 }
 
+int bartint_debug_export_dbarts098_walk(const char* const* tree_strings, const double* tree_fits, const double* x_train,
+                                        int64_t n, int32_t d, const int32_t* cut_offsets, const double* cut_values,
+                                        int32_t m, int32_t S, int64_t node_capacity, int64_t stats[8], uint32_t* walk_nodes,
+                                        int32_t* tree_node_offset, int32_t* tree_leaf_offset, double* leaf_mu) {
+    BI_REQUIRE(stats != nullptr, BARTINT_ERR_ARG, "stats is NULL");
+    for (int k = 0; k < 8; ++k) stats[k] = 0;
+    BI_REQUIRE(S >= 0 && m >= 0 && n >= 0, BARTINT_ERR_ARG, "S, m, n must be >= 0");
+    BI_REQUIRE((int64_t)S * m == 0 || tree_strings != nullptr, BARTINT_ERR_ARG, "tree_strings is NULL");
+    int rc = check_cuts(d, cut_offsets, cut_values);
+    if (rc) return rc;
+    bartint_forest f;                       // never uploaded: no device state to release
+    f.S = S; f.m = m; f.d = d;
+    f.cut_off.assign(cut_offsets, cut_offsets + d + 1);
+    f.cut_val.assign(cut_values, cut_values + cut_offsets[d]);
+    WalkForm W;
+    if ((rc = parse_dbarts_walk(tree_strings, tree_fits, x_train, n, d, cut_offsets, cut_values, m, S, &f, W))) return rc;
+    stats[0] = f.n_nodes; stats[1] = f.n_leaves; stats[2] = f.max_depth; stats[3] = f.max_internal;
+    stats[4] = f.draw_internal_max; stats[5] = f.bs_refs_total; stats[6] = f.bs_ok ? 1 : 0; stats[7] = f.bs_class_nodes[0];
+    BI_REQUIRE(f.n_nodes <= node_capacity, BARTINT_ERR_ARG, "forest has %lld nodes, capacity is %lld", (long long)f.n_nodes,
+               (long long)node_capacity);
+    if (walk_nodes)
+        for (size_t g = 0; g < W.nodes.size(); ++g) { walk_nodes[2 * g] = W.nodes[g].x; walk_nodes[2 * g + 1] = W.nodes[g].y; }
+    if (tree_node_offset) memcpy(tree_node_offset, W.tree_off.data(), W.tree_off.size() * sizeof(int32_t));
+    if (tree_leaf_offset) memcpy(tree_leaf_offset, W.leaf_off.data(), W.leaf_off.size() * sizeof(int32_t));
+    if (leaf_mu && !W.leaf_mu.empty()) memcpy(leaf_mu, W.leaf_mu.data(), W.leaf_mu.size() * sizeof(double));
+    return BARTINT_OK;
+}
+
 int bartint_debug_export_value_splits(int32_t S, int32_t m, int32_t d, const int64_t* tree_node_offset,
                                       const int32_t* split_var, const double* value, const int32_t* left,
                                       const int32_t* right, double leaf_scale, int64_t* tree_node_offset_out,
@@ -433,7 +468,7 @@ int bartint_forest_bitslice_info(const bartint_forest* f, int64_t info[16]) {
 int bartint_forest_export_soa(const bartint_forest* f, int64_t* tree_node_offset, int32_t* split_var,
                               int32_t* split_cut_idx, int32_t* left, int32_t* right, double* leaf_mu) {
     BI_REQUIRE(f != nullptr, BARTINT_ERR_ARG, "forest is NULL");
-    BI_REQUIRE(f->image_base == nullptr, BARTINT_ERR_UNSUPPORTED,
+    BI_REQUIRE(f->image_base == nullptr && !f->walk_only, BARTINT_ERR_UNSUPPORTED,
                "a forest restored from a device image keeps no host copy of the trees");
     const size_t nn = (size_t)f->n_nodes;
     if (tree_node_offset) memcpy(tree_node_offset, f->tree_off.data(), f->tree_off.size() * sizeof(int64_t));
@@ -546,14 +581,31 @@ static cudaError_t staged_submit_rest(const bartint_staged* cs) {
     return e;
 }
 
+// The copy stream and the events of a staged matrix are recycled per host thread and device: creating a stream and five
+// events costs ~0.1 ms per matrix, twice per sequential-design step.
+namespace {
+struct StageRes { int device; cudaStream_t st; cudaEvent_t done; cudaEvent_t blk[8]; };
+thread_local std::vector<StageRes> g_stage_res;
+}  // namespace
+
 // rows [0, N) of a column-major host matrix with leading dimension ld, staged on `device`
 static int stage_rows(const double* X, int64_t N, int64_t ld, int32_t d, int device, bartint_staged** out) {
     DeviceGuard g(device);
     bartint_staged* s = new (std::nothrow) bartint_staged();
     BI_REQUIRE(s != nullptr, BARTINT_ERR_NOMEM, "out of host memory");
     s->device = device; s->N = N; s->d = d; s->host_ld = ld;
-    cudaError_t e = cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->done, cudaEventDisableTiming);
+    cudaError_t e = cudaSuccess;
+    for (size_t k = 0; k < g_stage_res.size(); ++k)
+        if (g_stage_res[k].device == device) {                    // a recycled stream + events of this thread and device
+            s->copy_stream = g_stage_res[k].st; s->done = g_stage_res[k].done;
+            for (int b = 0; b < 8; ++b) s->block_done[b] = g_stage_res[k].blk[b];
+            g_stage_res.erase(g_stage_res.begin() + (std::ptrdiff_t)k);
+            break;
+        }
+    if (s->copy_stream == nullptr) {
+        e = cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->done, cudaEventDisableTiming);
+    }
     if (e == cudaSuccess) e = cudaMallocAsync((void**)&s->dX, sizeof(double) * (size_t)std::max<int64_t>(N * d, 1), s->copy_stream);
     if (e == cudaSuccess && N * d > 0) {
         if (N >= (int64_t)1 << 18) {      // 4 row blocks: column-major, so each block is a d-row 2-D copy
@@ -561,12 +613,12 @@ static int stage_rows(const double* X, int64_t N, int64_t ld, int32_t d, int dev
             s->block_rows = ((N + 3) / 4 + TK_NPAD - 1) / TK_NPAD * TK_NPAD;
             s->host_X = X;
             for (int b = 0; b < s->n_blocks && e == cudaSuccess; ++b)
-                e = cudaEventCreateWithFlags(&s->block_done[b], cudaEventDisableTiming);
+                if (s->block_done[b] == nullptr) e = cudaEventCreateWithFlags(&s->block_done[b], cudaEventDisableTiming);
             // two of the four blocks travel at once (about as long as the export of the first draw chunk takes); the
             // rest follows the first forest upload, which must not queue behind the whole matrix on the copy engine
-            if (e == cudaSuccess) e = staged_submit_block(s, 0);
-            if (e == cudaSuccess) e = staged_submit_block(s, 1);
-            s->submitted = 2;
+            static const int upfront = [] { const char* e2 = std::getenv("BARTINT_STAGE_UPFRONT"); int v = e2 ? atoi(e2) : 2; return v < 1 ? 1 : v > 4 ? 4 : v; }();
+            for (int b = 0; b < upfront && e == cudaSuccess; ++b) e = staged_submit_block(s, b);
+            s->submitted = upfront;
         } else if (ld == N) {
             e = cudaMemcpyAsync(s->dX, X, sizeof(double) * (size_t)(N * d), cudaMemcpyHostToDevice, s->copy_stream);
         } else {
@@ -656,10 +708,16 @@ void bartint_staged_free(bartint_staged* s) {
         DeviceGuard g(s->device);
         if (s->copy_stream) cudaStreamSynchronize(s->copy_stream);
         if (s->dX) cudaFree(s->dX);            // synchronous: a consumer stream may still be binning from it
-        if (s->done) cudaEventDestroy(s->done);
-        for (cudaEvent_t ev : s->block_done)
-            if (ev) cudaEventDestroy(ev);
-        if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
+        if (s->copy_stream && s->done && g_stage_res.size() < 16) {      // keep the stream and the events for the next matrix
+            StageRes r{s->device, s->copy_stream, s->done, {}};
+            for (int b = 0; b < 8; ++b) r.blk[b] = s->block_done[b];
+            g_stage_res.push_back(r);
+        } else {
+            if (s->done) cudaEventDestroy(s->done);
+            for (cudaEvent_t ev : s->block_done)
+                if (ev) cudaEventDestroy(ev);
+            if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
+        }
         (void)cudaGetLastError();
     }
     delete s;
@@ -1533,9 +1591,13 @@ int bartint_design_step_dbarts098(const char* const* tree_strings, const double*
     BI_CUDA(cudaGetDevice(&cur));
     DeviceGuard guard(device >= 0 ? device : cur);
 
-    // (two chunks: the host export of the second half overlaps the first half's upload, build and evaluation; with the
-    //  bit-sliced kernel the evaluation is short and more chunks only add per-chunk host work -- tools/step_chunks.py)
-    int G = n_chunks > 0 ? n_chunks : (S >= 256 ? 2 : 1);
+    // Draw chunks: with the one-pass exporter and the bit-sliced kernel a whole cfg-2 posterior is exported in about a
+    // millisecond and evaluated in half of one, so pipelining chunks against each other no longer pays for its
+    // per-chunk host work (tools/step_chunks.py, tools/step_sweep.py: 1 chunk 1.9-2.1 ms, 2 chunks 2.2-2.5 ms); with
+    // many candidates (group records and per-point kernels, round-1 regime) two chunks still overlap export and evaluation.
+    static const int env_chunks = [] { const char* e = std::getenv("BARTINT_STEP_CHUNKS"); return e ? atoi(e) : 0; }();
+    const bool few_cand = (cand ? cand->N : 0) <= 2048;
+    int G = n_chunks > 0 ? n_chunks : env_chunks > 0 ? env_chunks : (S >= 256 && !(few_cand && (int64_t)S * m <= 200000) ? 2 : 1);
     G = std::min(G, S);
     const int n_int = (n_draws_integral <= 0 || n_draws_integral > S) ? S : n_draws_integral;
     const bool want_int = integrals_scaled != nullptr || integral_mean_sd != nullptr;

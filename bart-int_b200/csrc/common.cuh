@@ -127,6 +127,7 @@ struct bartint_forest {
     std::vector<double> cut_val;
     // table path
     bool defer_upload_sync = false;    // forest_upload leaves its default-stream work in flight (pipelined design step)
+    bool walk_only = false;            // built by parse_dbarts_walk: walk form only, no canonical host SoA (design step)
     bool no_fast_plan = false;         // skip the table / gather records (design step with few candidates: the bit-sliced
                                        // kernel gives the per-draw sums, the walk kernel the few per-point results)
     bool table_ok = false;             // a fast (table or gather) kernel applies
@@ -201,7 +202,8 @@ namespace bartint {
 
 // host-side pieces (forest_host.cu)
 int forest_finish_host(bartint_forest* f);      // validate canonical SoA, compute stats
-int forest_upload(bartint_forest* f);           // build device arrays (+ table groups)
+struct WalkForm;
+int forest_upload(bartint_forest* f, WalkForm* prebuilt = nullptr);   // build device arrays (+ table groups)
 // Staging memory of the walk form: page-locked blocks from a per-thread cache, so that the host->device copies of a
 // forest upload are true DMA transfers that return at once (from pageable vectors cudaMemcpyAsync stages and waits:
 // 0.25-0.35 ms per draw chunk of a design step).  A block released while its copy may still be in flight is tagged with
@@ -244,6 +246,9 @@ void plan_fast_path(bartint_forest* f, const int32_t* tree_off, FastPlan& P);
 int parse_dbarts_forest(const char* const* tree_strings, const double* tree_fits, const double* x_train,
                         int64_t n, int32_t d, const int32_t* cut_offsets, const double* cut_values,
                         int32_t m, int32_t S, bartint_forest* f);
+int parse_dbarts_walk(const char* const* tree_strings, const double* tree_fits, const double* x_train, int64_t n, int32_t d,
+                      const int32_t* cut_offsets, const double* cut_values, int32_t m, int32_t S, bartint_forest* f,
+                      WalkForm& W);
 int parse_wbart_forest(const char* text, int64_t len, int32_t d, bartint_forest* f);
 int value_splits_to_soa(int32_t S, int32_t m, int32_t d, const int64_t* off, const int32_t* var, const double* value,
                         const int32_t* left, const int32_t* right, double leaf_scale, bartint_forest* f);

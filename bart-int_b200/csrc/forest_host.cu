@@ -63,6 +63,8 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
 // Accepts any run of spaces between tokens (the reference tokeniser inserts one after every '.').
 // Appends the tree's nodes in pre-order; child indices are relative to the tree's first node.
 // ---------------------------------------------------------------------------------------------
+static int forest_check_cuts(bartint_forest* f);      // defined with forest_finish_host
+
 static bool parse_int(const char*& p, int32_t& out) {
     while (*p == ' ') ++p;
     if (*p < '0' || *p > '9') return false;
@@ -268,6 +270,198 @@ int parse_dbarts_forest(const char* const* tree_strings, const double* tree_fits
         set_error("tree string references a variable or cut index outside the cut-point table");
         return BARTINT_ERR_PARSE;
     }
+    return BARTINT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// The exporter of the fused design step: dbarts 0.9-8 strings + fits -> WALK FORM in one pass.  The trees of a design
+// step are evaluated (bit-sliced sums, node-walk moments, exact integrals) and thrown away, so the canonical SoA that
+// parse_dbarts_forest fills, forest_finish_host re-reads for its statistics and pack_walk_form re-reads to pack never
+// needs to exist: every tree is parsed into a small thread-local scratch, validated, measured (depth classes, leaves)
+// and written straight into the page-locked walk form; the leaf values are collected through the same prefetch queue.
+// Same grammar, same checks and the same leaf-value rule (getTree, src/BARTInt.R:92-133) as parse_dbarts_forest; the
+// GPU parity tests of the design step compare the two paths.
+// ---------------------------------------------------------------------------------------------
+int parse_dbarts_walk(const char* const* tree_strings, const double* tree_fits, const double* x_train, int64_t n, int32_t d,
+                      const int32_t* cut_offsets, const double* cut_values, int32_t m, int32_t S, bartint_forest* f,
+                      WalkForm& W) {
+    const int64_t n_trees = (int64_t)S * m;
+    PhaseTimer pt;
+    int rc = forest_check_cuts(f);
+    if (rc) return rc;
+    W.tree_off.resize((size_t)n_trees + 1);
+    W.leaf_off.resize((size_t)n_trees + 1);
+    int64_t bad_tree = -1;
+    std::vector<int32_t> n_leaf((size_t)n_trees);
+#pragma omp parallel for schedule(static)
+    for (int64_t k = 0; k < n_trees; ++k) {
+        int32_t dots = 0;
+        if (tree_strings[k] != nullptr)
+            for (const char* p = tree_strings[k]; *p; ++p) dots += (*p == '.');
+        if (dots == 0) {
+#pragma omp critical
+            bad_tree = k;
+        }
+        n_leaf[(size_t)k] = dots;
+    }
+    if (bad_tree >= 0) {
+        set_error("malformed dbarts tree string at tree %lld (draw %lld)", (long long)(bad_tree % m), (long long)(bad_tree / m));
+        return BARTINT_ERR_PARSE;
+    }
+    int64_t nn = 0, nl = 0;
+    int32_t draw_internal_max = 0;
+    for (int32_t s = 0; s < S; ++s) {
+        int64_t internal = 0;
+        for (int32_t t = 0; t < m; ++t) {
+            const size_t k = (size_t)s * (size_t)m + (size_t)t;
+            W.tree_off[k] = (int32_t)nn; W.leaf_off[k] = (int32_t)nl;
+            nn += 2 * (int64_t)n_leaf[k] - 1; nl += n_leaf[k];
+            internal += n_leaf[k] - 1;
+        }
+        draw_internal_max = std::max<int64_t>(draw_internal_max, internal);
+    }
+    BI_REQUIRE(nn < (int64_t)1 << 31, BARTINT_ERR_UNSUPPORTED, "forest has more than 2^31 nodes");
+    W.tree_off[(size_t)n_trees] = (int32_t)nn; W.leaf_off[(size_t)n_trees] = (int32_t)nl;
+    W.nodes.resize((size_t)nn);
+    W.leaf_mu.resize((size_t)nl);
+    // integer cut map of the training matrix and its rows ordered by code (see parse_dbarts_forest)
+    std::vector<int32_t> codes((size_t)(n * d)), order((size_t)(n * d));
+#pragma omp parallel for schedule(static)
+    for (int32_t j = 0; j < d; ++j) {
+        const double* cuts = cut_values + cut_offsets[j];
+        const int nc = cut_offsets[j + 1] - cut_offsets[j];
+        int32_t* cj = codes.data() + (size_t)j * (size_t)n;
+        for (int64_t i = 0; i < n; ++i) cj[i] = bin_value(x_train[j * n + i], cuts, nc);
+        int32_t* o = order.data() + (size_t)j * (size_t)n;
+        std::vector<int64_t> first((size_t)nc + 2, 0);
+        for (int64_t i = 0; i < n; ++i) ++first[(size_t)cj[i] + 1];
+        for (int c = 0; c <= nc; ++c) first[(size_t)c + 1] += first[(size_t)c];
+        for (int64_t i = 0; i < n; ++i) o[first[(size_t)cj[i]]++] = (int32_t)i;
+    }
+    pt.lap("exporter: count + cut map");
+    constexpr int64_t kLeafTries = 8;
+    int bad_ref = 0;
+    int32_t max_depth = 0, max_internal = 0;
+    int64_t cls0 = 0, cls1 = 0, cls2 = 0, cls3 = 0, cls4 = 0, refs = 0;
+#pragma omp parallel reduction(max : max_depth, max_internal) reduction(+ : cls0, cls1, cls2, cls3, cls4, refs)
+    {
+        std::vector<int32_t> pending, var, cut, left, right, depth, ord_of;
+        std::vector<char> have;
+        std::vector<std::pair<double*, const double*>> pend;     // leaf value reads in flight: (destination, source)
+        auto drain = [&pend](size_t keep) {
+            const size_t nd = pend.size() > keep ? pend.size() - keep : 0;
+            for (size_t q = 0; q < nd; ++q) *pend[q].first = *pend[q].second;
+            pend.erase(pend.begin(), pend.begin() + (std::ptrdiff_t)nd);
+        };
+#pragma omp for schedule(static) nowait
+        for (int64_t k = 0; k < n_trees; ++k) {
+            if (bad_tree >= 0) continue;
+            const int32_t cnt = 2 * n_leaf[(size_t)k] - 1;
+            if ((int32_t)var.size() < cnt) {
+                var.resize((size_t)cnt); cut.resize((size_t)cnt); left.resize((size_t)cnt); right.resize((size_t)cnt);
+                depth.resize((size_t)cnt); ord_of.resize((size_t)cnt);
+            }
+            if (parse_tree_string(tree_strings[k], cnt, var.data(), cut.data(), left.data(), right.data(), pending) != BARTINT_OK) {
+#pragma omp critical
+                bad_tree = k;
+                continue;
+            }
+            uint2* nodes = W.nodes.data() + W.tree_off[(size_t)k];
+            double* mu = W.leaf_mu.data() + W.leaf_off[(size_t)k];
+            bool ok = true;
+            int32_t ord = 0, internal = 0;
+            depth[0] = 0;
+            for (int32_t a = 0; a < cnt; ++a) {
+                if (var[(size_t)a] >= 0) {
+                    const int32_t v = var[(size_t)a], c = cut[(size_t)a];
+                    if (v >= d || c >= cut_offsets[v + 1] - cut_offsets[v]) { ok = false; break; }
+                    nodes[a] = make_uint2((uint32_t)v | ((uint32_t)c << 16), (uint32_t)(right[(size_t)a] - a));
+                    const int32_t dp = depth[(size_t)a];
+                    depth[(size_t)left[(size_t)a]] = dp + 1; depth[(size_t)right[(size_t)a]] = dp + 1;
+                    ++internal;
+                    if (dp == 0) ++cls0; else if (dp == 1) ++cls1; else if (dp == 2) ++cls2; else if (dp == 3) ++cls3; else ++cls4;
+                    if (dp >= 1) refs += dp + 1;
+                } else {
+                    nodes[a] = make_uint2(LEAF_VAR, (uint32_t)ord);
+                    ord_of[(size_t)a] = ord;
+                    mu[ord] = std::numeric_limits<double>::quiet_NaN();
+                    ++ord;
+                }
+                max_depth = std::max(max_depth, depth[(size_t)a]);
+            }
+            if (!ok) {
+#pragma omp atomic write
+                bad_ref = 1;
+                continue;
+            }
+            max_internal = std::max(max_internal, internal);
+            // leaf mu = fit of a training row routed to the leaf (fillPlotInfoForNode, BARTInt.R:125); candidate rows
+            // from the per-variable code order, verified by routing them from the root (see parse_dbarts_forest)
+            const double* fits = tree_fits + (size_t)k * (size_t)n;
+            const int32_t nlf = (cnt + 1) / 2;
+            have.assign((size_t)cnt, 0);
+            int32_t found = 0;
+            if (pend.size() >= 192) drain(64);
+            if (cnt == 1) {
+                if (n > 0) { __builtin_prefetch(fits); pend.emplace_back(mu, fits); found = 1; }
+            } else {
+                for (int32_t p = 0; p < cnt; ++p) {
+                    if (var[(size_t)p] < 0) continue;
+                    const int32_t v = var[(size_t)p], c = cut[(size_t)p];
+                    const int32_t* o = order.data() + (size_t)v * (size_t)n;
+                    const int32_t* cv = codes.data() + (size_t)v * (size_t)n;
+                    for (int side = 0; side < 2; ++side) {
+                        const int32_t leaf = side ? right[(size_t)p] : left[(size_t)p];
+                        if (var[(size_t)leaf] >= 0) continue;
+                        for (int64_t t = 0; t < n && t < kLeafTries; ++t) {
+                            const int64_t i = side ? o[n - 1 - t] : o[t];
+                            if ((cv[i] > c) != (side == 1)) break;
+                            int32_t a = 0;
+                            while (var[(size_t)a] >= 0)
+                                a = (codes[(size_t)(var[(size_t)a] * n + i)] > cut[(size_t)a]) ? right[(size_t)a] : left[(size_t)a];
+                            if (a == leaf) {
+                                __builtin_prefetch(fits + i);
+                                pend.emplace_back(mu + ord_of[(size_t)a], fits + i);
+                                have[(size_t)a] = 1; ++found;
+                                break;
+                            }
+                        }
+                    }
+                }
+            }
+            for (int64_t i = 0; i < n && found < nlf; ++i) {        // leaves the candidates missed: rows in order
+                int32_t a = 0;
+                while (var[(size_t)a] >= 0)
+                    a = (codes[(size_t)(var[(size_t)a] * n + i)] > cut[(size_t)a]) ? right[(size_t)a] : left[(size_t)a];
+                if (!have[(size_t)a]) { mu[ord_of[(size_t)a]] = fits[i]; have[(size_t)a] = 1; ++found; }
+            }
+        }
+        drain(0);
+    }
+    if (bad_tree >= 0) {
+        set_error("malformed dbarts tree string at tree %lld (draw %lld)", (long long)(bad_tree % m), (long long)(bad_tree / m));
+        return BARTINT_ERR_PARSE;
+    }
+    if (bad_ref) {
+        set_error("tree string references a variable or cut index outside the cut-point table");
+        return BARTINT_ERR_PARSE;
+    }
+    double max_abs_mu = 0.0;
+    bool mu_finite = true;
+#pragma omp parallel for schedule(static) reduction(max : max_abs_mu) reduction(&& : mu_finite)
+    for (int64_t g = 0; g < nl; ++g) {
+        const double a = std::fabs(W.leaf_mu[(size_t)g]);
+        if (!(a <= 1.7e308)) mu_finite = false;
+        else max_abs_mu = std::max(max_abs_mu, a);
+    }
+    f->n_nodes = nn; f->n_leaves = nl; f->max_depth = max_depth; f->max_internal = max_internal;
+    f->bs_class_nodes[0] = cls0; f->bs_class_nodes[1] = cls1; f->bs_class_nodes[2] = cls2; f->bs_class_nodes[3] = cls3;
+    f->bs_class_nodes[4] = cls4; f->bs_refs_total = refs;
+    f->draw_internal_max = draw_internal_max;
+    f->max_abs_mu = mu_finite ? max_abs_mu : INFINITY;
+    f->walk_only = true;
+    bs_configure(f);
+    pt.lap("exporter: parse + leaf mu + walk form");
     return BARTINT_OK;
 }
 
@@ -532,11 +726,21 @@ int value_splits_to_soa(int32_t S, int32_t m, int32_t d, const int64_t* off, con
     return canonicalise_soa(S, m, d, off, var, cut.data(), implied ? lft.data() : left, implied ? rgt.data() : right, mu.data(), f);
 }
 
+static int forest_check_cuts(bartint_forest* f);
+static int forest_finish_host_trees(bartint_forest* f, PhaseTimer& pt);
+
 int forest_finish_host(bartint_forest* f) {
     PhaseTimer pt;
     const int64_t n_trees = (int64_t)f->S * f->m;
     f->n_nodes = f->tree_off[(size_t)n_trees];
     BI_REQUIRE(f->n_nodes < (int64_t)1 << 31, BARTINT_ERR_UNSUPPORTED, "forest has more than 2^31 nodes");
+    int rc_cuts = forest_check_cuts(f);
+    if (rc_cuts) return rc_cuts;
+    return forest_finish_host_trees(f, pt);
+}
+
+// cut-point lists: ascending, at most 255 per variable (codes are uint8); fills f->max_cuts
+static int forest_check_cuts(bartint_forest* f) {
     f->max_cuts = 0;
     for (int32_t j = 0; j < f->d; ++j) {
         int nc = f->cut_off[(size_t)j + 1] - f->cut_off[(size_t)j];
@@ -548,6 +752,11 @@ int forest_finish_host(bartint_forest* f) {
     }
     BI_REQUIRE(f->max_cuts <= 255, BARTINT_ERR_UNSUPPORTED, "more than 255 cut points for one variable (codes are uint8)");
     BI_REQUIRE(f->d < 65535, BARTINT_ERR_UNSUPPORTED, "more than 65534 variables");
+    return BARTINT_OK;
+}
+
+static int forest_finish_host_trees(bartint_forest* f, PhaseTimer& pt) {
+    const int64_t n_trees = (int64_t)f->S * f->m;
     int64_t n_leaves = 0;
     int32_t max_depth = 0, max_internal = 0;
     int bad = 0;
@@ -627,17 +836,23 @@ constexpr size_t kStageHeader = 64;       // room in front of the user pointer f
 
 void* pinned_stage_alloc(size_t bytes) {
     const size_t need = ((std::max<size_t>(bytes, 1) + 4095) & ~(size_t)4095) + kStageHeader;
-    // a cached block that is large enough and whose last copy has completed
+    // the SMALLEST cached block that is large enough and whose last copy has completed (first fit let a 100 KB request
+    // take the 700 KB block the next request needed, which then cost a cudaHostAlloc in every step)
+    int best = -1;
     for (size_t k = 0; k < g_stage.free_blocks.size(); ++k) {
         StageBlock& b = g_stage.free_blocks[k];
         if (b.bytes < need || b.bytes > 4 * need + (1u << 20)) continue;
+        if (best >= 0 && g_stage.free_blocks[(size_t)best].bytes <= b.bytes) continue;
         if (b.busy) {
             if (cudaEventQuery(b.busy) != cudaSuccess) { (void)cudaGetLastError(); continue; }
             cudaEventDestroy(b.busy);
             b.busy = nullptr;
         }
-        StageBlock got = b;
-        g_stage.free_blocks.erase(g_stage.free_blocks.begin() + (std::ptrdiff_t)k);
+        best = (int)k;
+    }
+    if (best >= 0) {
+        StageBlock got = g_stage.free_blocks[(size_t)best];
+        g_stage.free_blocks.erase(g_stage.free_blocks.begin() + best);
         size_t* hdr = static_cast<size_t*>(got.p);
         hdr[0] = got.bytes; hdr[1] = got.pinned ? 1 : 0;
         return static_cast<char*>(got.p) + kStageHeader;
@@ -1162,10 +1377,11 @@ void pack_walk_form(const bartint_forest* f, WalkForm& W) {
     pt.lap("upload: pack walk form");
 }
 
-int forest_upload(bartint_forest* f) {
+int forest_upload(bartint_forest* f, WalkForm* prebuilt) {
     PhaseTimer pt;
-    WalkForm W;
-    pack_walk_form(f, W);
+    WalkForm W_local;
+    WalkForm& W = prebuilt ? *prebuilt : W_local;
+    if (!prebuilt) pack_walk_form(f, W);
     const StageVec<uint2>& nodes = W.nodes;
     const StageVec<int32_t>&tree_off = W.tree_off, &leaf_off = W.leaf_off;
     const StageVec<double>& leaf_mu = W.leaf_mu;
@@ -1181,7 +1397,7 @@ int forest_upload(bartint_forest* f) {
     if ((rc = launch_build_bitslice(f, nullptr))) return rc;
     pt.lap("upload: H2D walk form");
     FastPlan P;
-    if (f->no_fast_plan) f->table_ok = false;
+    if (f->no_fast_plan || f->walk_only) f->table_ok = false;
     else plan_fast_path(f, tree_off.data(), P);
     pt.lap("");
     if (!f->table_ok) {

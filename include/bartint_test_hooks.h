@@ -55,6 +55,15 @@ int bartint_debug_export_wbart(const char* trees_text, int64_t text_len, int32_t
                                int64_t dims_out[3], int64_t* tree_node_offset, int32_t* split_var,
                                int32_t* split_cut_idx, int32_t* left, int32_t* right, double* leaf_mu);
 
+/* Test hook, HOST ONLY: the one-pass exporter of the fused design step (parse_dbarts_walk: dbarts 0.9-8 strings + fits ->
+ * walk form, no canonical SoA in between).  stats[8] = {nodes, leaves, max depth, max internal nodes per tree, most
+ * internal nodes in one draw, mask-row references of the nodes at depth >= 1, bit-sliced kernel applies, root splits}.
+ * walk_nodes [2 node_capacity] (x, y words), tree_node_offset / tree_leaf_offset [S m + 1], leaf_mu [leaves]. */
+int bartint_debug_export_dbarts098_walk(const char* const* tree_strings, const double* tree_fits, const double* x_train,
+                                        int64_t n, int32_t d, const int32_t* cut_offsets, const double* cut_values,
+                                        int32_t m, int32_t S, int64_t node_capacity, int64_t stats[8], uint32_t* walk_nodes,
+                                        int32_t* tree_node_offset, int32_t* tree_leaf_offset, double* leaf_mu);
+
 /* Test hook, HOST ONLY: the value-split exporter of bartint_forest_from_value_splits (cut-point lists from the distinct
  * split values, cut indices, pre-order children) plus the host phases of forest creation, without touching a device.
  * Outputs sized by the caller: node arrays [tree_node_offset[S m]], cut_offsets_out [d + 1], cut_values_out [number of

@@ -25,6 +25,9 @@ HOOK_SIGNATURES = {
                                          C.POINTER(C.c_uint32), c_int32_p, c_double_p, c_uint8_p, c_int32_p, c_int32_p,
                                          c_int32_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
                                          C.POINTER(C.c_uint32)]),
+    "bartint_debug_export_dbarts098_walk": (C.c_int, [C.c_void_p, c_double_p, c_double_p, C.c_int64, C.c_int32, c_int32_p, c_double_p,
+                                                      C.c_int32, C.c_int32, C.c_int64, c_int64_p, C.POINTER(C.c_uint32), c_int32_p,
+                                                      c_int32_p, c_double_p]),
     "bartint_debug_export_value_splits": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, c_int64_p, c_int32_p, c_double_p, c_int32_p,
                                                     c_int32_p, C.c_double, c_int64_p, c_int32_p, c_int32_p, c_int32_p, c_int32_p,
                                                     c_double_p, c_int32_p, c_double_p]),
@@ -170,4 +173,30 @@ def export_value_splits(S, m, d, tree_offset, var, value, left=None, right=None,
     for k in ("var", "cut", "left", "right", "mu"):
         out[k] = out[k][:nn]
     out["cut_values"] = out["cut_values"][:int(out["cut_offsets"][-1])]
+    return out
+
+
+def export_dbarts_walk(wire, tree_fits, x_train, cut_offsets, cut_values, node_capacity) -> dict:
+    """The one-pass exporter of the fused design step on the host: walk form + statistics."""
+    lib = _load()
+    x_train = np.asfortranarray(np.asarray(x_train, np.float64))
+    n, d = x_train.shape
+    m, S = wire.m, wire.S
+    fits = np.asfortranarray(np.asarray(tree_fits, np.float64).reshape(n, m, S))
+    coff = np.ascontiguousarray(cut_offsets, np.int32)
+    cval = np.ascontiguousarray(cut_values, np.float64)
+    stats = np.zeros(8, np.int64)
+    cap = max(int(node_capacity), 1)
+    out = dict(walk_nodes=np.zeros(2 * cap, np.uint32), tree_off=np.zeros(m * S + 1, np.int32),
+               leaf_off=np.zeros(m * S + 1, np.int32), leaf_mu=np.zeros(cap, np.float64))
+    rc = lib.bartint_debug_export_dbarts098_walk(wire.array, _p(fits, C.c_double), _p(x_train, C.c_double), n, d,
+                                                 _p(coff, C.c_int32), _p(cval, C.c_double), m, S, cap, _p(stats, C.c_int64),
+                                                 _p(out["walk_nodes"], C.c_uint32), _p(out["tree_off"], C.c_int32),
+                                                 _p(out["leaf_off"], C.c_int32), _p(out["leaf_mu"], C.c_double))
+    if rc != 0:
+        from bartint_b200.forest import BartIntError
+        raise BartIntError(rc, lib.bartint_last_error().decode())
+    out["stats"] = stats
+    out["walk_nodes"] = out["walk_nodes"][:2 * int(stats[0])]
+    out["leaf_mu"] = out["leaf_mu"][:int(stats[1])]
     return out

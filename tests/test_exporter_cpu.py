@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 import hosthooks
-from bartint_b200 import BartIntError, WireStrings, synth
+from bartint_b200 import BartIntError, FlatForest, WireStrings, synth
 from oracle import oracle_np as onp
 
 
@@ -180,3 +180,34 @@ def test_draw_slices_export_to_the_matching_part_of_the_forest():
         assert np.array_equal(part["mu"], whole["mu"][a:b], equal_nan=True)
         covered += hi - lo
     assert covered == ff.S
+
+
+@pytest.mark.parametrize("seed,S,m,d,n", [(1, 6, 5, 3, 40), (2, 33, 50, 10, 200), (3, 4, 7, 1, 21), (4, 3, 9, 20, 60)])
+def test_one_pass_walk_exporter_equals_two_pass(seed, S, m, d, n):
+    """The fused design step parses dbarts strings straight into the walk form (parse_dbarts_walk); it must produce
+    exactly what the exporter + validation + walk-form packer produce: node words, leaf offsets, leaf values (getTree's
+    rule, BARTInt.R:92-133) and the statistics the bit-sliced kernel is sized from."""
+    rng = np.random.default_rng(seed)
+    x_train = rng.random((n, d))
+    ff = synth.prior_forest(seed, S, m, x_train, synth.genz_gaussian(x_train))
+    strings, fits = ff.to_dbarts_state(x_train)
+    wire = WireStrings(strings)
+    nn, two = hosthooks.export_dbarts(wire, fits, x_train, ff.cut_offsets, ff.cut_values)
+    flat = FlatForest(S, m, d, two["tree_offset"], two["var"], two["cut"], two["left"], two["right"], two["mu"],
+                      ff.cut_offsets, ff.cut_values, ff.y_min, ff.y_max)
+    plan = hosthooks.plan_soa(flat)
+    one = hosthooks.export_dbarts_walk(wire, fits, x_train, ff.cut_offsets, ff.cut_values, nn)
+    assert int(one["stats"][0]) == nn and int(one["stats"][1]) == (nn + S * m) // 2
+    assert np.array_equal(one["walk_nodes"], plan["walk_nodes"][:2 * nn])
+    assert np.array_equal(one["tree_off"], two["tree_offset"].astype(np.int32))
+    assert np.array_equal(one["leaf_off"], plan["leaf_off"])
+    assert np.array_equal(one["leaf_mu"], plan["leaf_mu"][:len(one["leaf_mu"])], equal_nan=True)
+    internal = two["var"] >= 0
+    per_draw = [int(internal[two["tree_offset"][s * m]:two["tree_offset"][(s + 1) * m]].sum()) for s in range(S)]
+    assert int(one["stats"][4]) == max(per_draw)
+    # malformed strings fail the same way
+    bad = strings.copy()
+    bad[0, 0] = "0 1 . "
+    with pytest.raises(BartIntError) as e:
+        hosthooks.export_dbarts_walk(WireStrings(bad), fits, x_train, ff.cut_offsets, ff.cut_values, nn)
+    assert e.value.status == 2
