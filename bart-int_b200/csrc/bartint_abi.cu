@@ -450,18 +450,7 @@ int bartint_forest_bitslice_info(const bartint_forest* f, int64_t info[16]) {
     for (int k = 0; k < 5; ++k) info[8 + k] = f->bs_class_nodes[k];
     info[13] = f->bs_refs_total;
     info[15] = (f->S + 31) / 32;
-    if (f->dev.bs_slice_hdr != nullptr) {         // what the slices actually load: every class padded to its longest draw
-        DeviceGuard g(f->device);
-        std::vector<int32_t> hdr((size_t)info[15] * 8);
-        BI_CUDA(cudaDeviceSynchronize());
-        BI_CUDA(cudaMemcpy(hdr.data(), f->dev.bs_slice_hdr, hdr.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
-        int64_t padded = 0;
-        for (int64_t sl = 0; sl < info[15]; ++sl) {
-            const int32_t* h = &hdr[(size_t)sl * 8];
-            padded += 32ll * (2ll * h[1] + 3ll * h[2] + 4ll * h[3] + (int64_t)h[4] * (1 + h[5]));
-        }
-        info[14] = padded;
-    }
+    { DeviceGuard g(f->device); info[14] = bs_padded_refs(f); }      // what the slices load: every class padded per slice
     return BARTINT_OK;
 }
 
@@ -811,7 +800,7 @@ static int eval_core(const bartint_forest* f, const bartint_points* p, uint32_t 
     }
     f->last_used_table[slot] = plan.use_bitslice ? 2 : plan.use_table ? 1 : 0;
     double *draw_part = nullptr, *pt_mean = nullptr, *pt_m2 = nullptr;
-    BI_CUDA(cudaMallocAsync((void**)&draw_part, sizeof(double) * (size_t)plan.n_tiles * (size_t)ndraws, st));
+    BI_CUDA(cudaMallocAsync((void**)&draw_part, sizeof(double) * (size_t)plan.n_tiles * (size_t)(plan.use_bitslice ? plan.chunk_draws : 1) * (size_t)ndraws, st));
     const bool direct_mom = want_mom && plan.n_chunks == 1;   // single chunk: the kernel writes the final moments
     if (want_mom) {
         if (direct_mom) { pt_mean = d_point_mean; pt_m2 = d_point_m2; }
@@ -830,7 +819,7 @@ static int eval_core(const bartint_forest* f, const bartint_points* p, uint32_t 
     f->last_timed[slot] = true;
     f->last_launches[slot] = 1;
     if (rc == BARTINT_OK && d_draw_sum != nullptr && plan.use_bitslice) {
-        rc = launch_bs_reduce(f, draw_part, plan.n_tiles, draw_begin, ndraws, p->N, d_draw_sum, st);
+        rc = launch_bs_reduce(f, draw_part, plan.n_tiles * plan.chunk_draws, draw_begin, ndraws, p->N, d_draw_sum, st);
         f->last_launches[slot]++;
     } else if (rc == BARTINT_OK && d_draw_sum != nullptr) {
         rc = launch_reduce_draw_parts(draw_part, plan.n_tiles, ndraws, d_draw_sum, st);

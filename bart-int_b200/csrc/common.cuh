@@ -105,8 +105,8 @@ struct DeviceForest {
     uint8_t* group_rec = nullptr;      // n_groups * tk_rec_bytes(nb)
     // bit-sliced form (kernels_bitslice.cu), built on the device from the walk form; never part of a forest image
     unsigned char* bs_pool = nullptr;  // ELL rows of the internal nodes, one block per slice of 32 draws
-    int4* bs_slice_hdr = nullptr;      // per slice, two words: rows of class A, B, C2, C3 | rows of D, deepest D node
-    int32_t* bs_slot_draw = nullptr;   // slot (slice * 32 + lane) -> draw, -1 = empty (draws are sorted by row counts)
+    int2* bs_slice_hdr = nullptr;      // [class][slice]: rows, deepest node (class D)
+    int32_t* bs_slot_draw = nullptr;   // [class][slice * 32 + lane] -> draw, -1 = empty (per class: draws sorted by row count)
     double* bs_base = nullptr;         // S: sum over the draw's trees of the leftmost leaf value
 };
 
@@ -140,7 +140,7 @@ struct bartint_forest {
     // bit-sliced sums-only kernel (bs_configure): applies / predicate rows / 128-point chunks per tile / longest draw
     // (internal nodes) / ancestor planes / fixed-point exponent of the leaf differences
     bool bs_ok = false;
-    int32_t bs_ncuts = 0, bs_ch = 0, bs_rows = 0, bs_anc = 0, bs_q = 0;
+    int32_t bs_ncuts = 0, bs_ch = 0, bs_rows = 0, bs_anc = 0, bs_q = 0, bs_perm = 0;
     int32_t draw_internal_max = 0;     // most internal nodes in one draw
     double max_abs_mu = 0.0;           // largest |leaf value|
     int64_t bs_class_nodes[5] = {0, 0, 0, 0, 0};   // internal nodes at depth 0, 1, 2, 3, >= 4 (0 for unpacked images)
@@ -297,6 +297,7 @@ int launch_build_bitslice(bartint_forest* f, cudaStream_t st);   // device: walk
 int bs_tile(const bartint_forest* f);
 int64_t bs_pool_bytes(const bartint_forest* f);
 size_t bs_smem_bytes(const bartint_forest* f);
+int64_t bs_padded_refs(const bartint_forest* f);
 int launch_eval_bitslice(const bartint_forest* f, const bartint_points* p, const EvalPlan& plan, double* draw_part,
                          cudaStream_t st);
 int launch_bs_reduce(const bartint_forest* f, const double* draw_part, int n_tiles, int32_t draw_begin, int ndraws,

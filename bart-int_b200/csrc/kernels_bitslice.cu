@@ -52,14 +52,21 @@ constexpr int BS_SORT_MAX = 16384;              // draws are ordered by cost (ra
 //   D   z = own byte offset, w = depth;  plane a: ancestor a's byte offset | negated << 31 (all-ones row beyond depth)
 enum { BS_A = 0, BS_B = 1, BS_C2 = 2, BS_C3 = 3, BS_D = 4, BS_NCLS = 5 };
 
+constexpr int BS_PERM = 1024;                   // draws are permuted inside blocks of this many (32 slices of 32) ...
+constexpr int BS_PERM_SMALL = 256;              // ... or of this many when the masks leave no room for 1024 accumulators
+
+// Every class has its OWN assignment of draws to slices (draws sorted by the class's row count inside a block of BS_PERM
+// draws), so a slice pads to the longest of 32 draws with nearly equal counts.  Pool = one block per class:
+// [slice][row][lane] entries of 16 bytes; class D additionally [slice][plane][row][lane] u32 ancestor references.
 struct BsLayout {
-    int64_t slice_bytes;
-    int32_t off[BS_NCLS];                       // byte offsets of the class blocks inside a slice
-    int32_t off_anc;                            // ancestor planes of class D
-    int32_t cap_d;                              // rows of the D block (stride of an ancestor plane)
+    int64_t cls_off[BS_NCLS];                   // byte offset of the class block in the pool
+    int32_t cap[BS_NCLS];                       // rows per slice of the class
+    int64_t anc_off;                            // ancestor planes of class D
     int32_t anc_planes;
+    int32_t n_slices;
     int32_t row_bytes;                          // CH * 16
     int32_t ones_off;                           // byte offset of the all-ones mask row (row index n_cuts)
+    int64_t total_bytes;
 };
 
 static inline int ru(int x, int q) { return (std::max(x, 1) + q - 1) / q * q; }
@@ -70,12 +77,13 @@ static BsLayout bs_layout_of(const bartint_forest* f) {
     // row capacities: a draw has at most min(2^k m, R) nodes at depth k; rounded up to the prefetch group of the class
     const int cap[BS_NCLS] = {ru(m, 8), ru(std::min(2 * m, R), 4), ru(std::min(4 * m, R), 4), ru(std::min(8 * m, R), 4),
                               f->max_depth > 4 ? ru(R, 2) : 2};
-    int o = 0;
-    for (int c = 0; c < BS_NCLS; ++c) { L.off[c] = o; o += 512 * cap[c]; }
-    L.off_anc = o;
-    L.cap_d = cap[BS_D];
+    L.n_slices = (f->S + 31) / 32;
+    int64_t o = 0;
+    for (int c = 0; c < BS_NCLS; ++c) { L.cls_off[c] = o; L.cap[c] = cap[c]; o += 512ll * cap[c] * L.n_slices; }
+    L.anc_off = o;
     L.anc_planes = f->bs_anc;
-    L.slice_bytes = (int64_t)o + 128ll * L.anc_planes * L.cap_d;
+    o += 128ll * L.anc_planes * cap[BS_D] * L.n_slices;
+    L.total_bytes = o;
     L.row_bytes = f->bs_ch * 16;
     L.ones_off = f->bs_ncuts * L.row_bytes;
     return L;
@@ -136,8 +144,8 @@ __global__ void __launch_bounds__(128) bs_count_kernel(const uint2* __restrict__
     tree_cnt[k] = out;
 }
 
-// one thread per draw: first row of every tree inside its draw's column (per class), the draw's totals, its sort
-// key (draws with similar row counts share a slice, so little of a slice is padding) and base[s] = sum_t L(root_t)
+// one thread per draw: first row of every tree inside its draw's column (per class), the draw's totals, one sort key per
+// class (row count, then the draw index) and base[s] = sum_t L(root_t)
 __global__ void __launch_bounds__(128) bs_draw_kernel(const BsCnt* __restrict__ tree_cnt, const int32_t* __restrict__ tree_leaf_off,
                                                       const double* __restrict__ leaf_mu, int S, int m,
                                                       BsCnt* __restrict__ tree_row, BsCnt* __restrict__ draw_tot,
@@ -162,69 +170,69 @@ __global__ void __launch_bounds__(128) bs_draw_kernel(const BsCnt* __restrict__ 
     tot.dmax = (unsigned short)dmax;
     draw_tot[s] = tot;
     base[s] = b;
-    // Slices take the draws in key order and every class is padded to the slice's longest draw, so draws that share a
-    // slice should have similar counts: the rare deep classes first (draws with D / C3 nodes together), then the B
-    // count (pairs of values, so the C2 count still sorts inside a bucket), then C2, C3; ties by the draw index.
-    const auto f12 = [](int v) { return (unsigned long long)min(v, 4095); };
-    key[s] = ((unsigned long long)(r[BS_D] > 0) << 63) | ((unsigned long long)(r[BS_C3] > 0) << 62) | (f12(r[BS_B] >> 1) << 48) |
-             (f12(r[BS_C2]) << 36) | (f12(r[BS_C3]) << 24) | (f12(r[BS_D]) << 16) | (unsigned long long)(s & 0xFFFF);
+#pragma unroll
+    for (int q = 0; q < BS_NCLS; ++q)
+        key[(size_t)q * S + s] = ((unsigned long long)r[q] << 32) | ((unsigned long long)(q == BS_D ? dmax : 0) << 20) |
+                                 (unsigned long long)(s & 0xFFFFF);
 }
 
-// rank of every draw by key: its slot (slice = slot / 32, lane = slot % 32).  sorted == 0: identity.
-__global__ void __launch_bounds__(256) bs_rank_kernel(const unsigned long long* __restrict__ key, int S, int sorted,
-                                                      int32_t* __restrict__ draw_slot, int32_t* __restrict__ slot_draw) {
+// Slot of every draw in every class (blockIdx.y = class): its rank by key among the draws of its block of BS_PERM draws;
+// slice = slot / 32, lane = slot % 32.
+__global__ void __launch_bounds__(256) bs_rank_kernel(const unsigned long long* __restrict__ key, int S,
+                                                      int32_t* __restrict__ draw_slot, int32_t* __restrict__ slot_draw, int n_slots, int perm) {
     __shared__ unsigned long long s_key[256];
+    const int c = blockIdx.y;
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    const unsigned long long mine = s < S ? key[s] : 0ull;
-    int rank = s;
-    if (sorted) {
-        rank = 0;
-        for (int j0 = 0; j0 < S; j0 += 256) {
-            __syncthreads();
-            s_key[threadIdx.x] = j0 + (int)threadIdx.x < S ? key[j0 + threadIdx.x] : ~0ull;
-            __syncthreads();
-            const int nj = min(256, S - j0);
-            for (int j = 0; j < nj; ++j) {
-                const unsigned long long o = s_key[j];
-                rank += (o < mine) || (o == mine && j0 + j < s);
-            }
-        }
+    const unsigned long long* kc = key + (size_t)c * S;
+    const unsigned long long mine = s < S ? kc[s] : 0ull;
+    // (a thread block never straddles two permutation blocks: perm is a multiple of 256)
+    const int b0 = (blockIdx.x * blockDim.x) / perm * perm, b1 = min(b0 + perm, S);
+    int rank = 0;
+    for (int j0 = b0; j0 < b1; j0 += 256) {
+        __syncthreads();
+        s_key[threadIdx.x] = j0 + (int)threadIdx.x < b1 ? kc[j0 + threadIdx.x] : ~0ull;
+        __syncthreads();
+        const int nj = min(256, b1 - j0);
+        for (int j = 0; j < nj; ++j) rank += s_key[j] < mine;          // keys are distinct (the draw index is part of them)
     }
-    if (s < S) { draw_slot[s] = rank; slot_draw[rank] = s; }
+    if (s < S) {
+        draw_slot[(size_t)c * S + s] = b0 + rank;
+        slot_draw[(size_t)c * n_slots + b0 + rank] = s;
+    }
 }
 
-// one warp per slice: the slice's row counts = the longest of its 32 draws
+// one warp per (class, slice): the slice's row count = the longest of its 32 draws (class D: also its deepest node)
 __global__ void __launch_bounds__(128) bs_hdr_kernel(const BsCnt* __restrict__ draw_tot, const int32_t* __restrict__ slot_draw,
-                                                     int n_slices, int4* __restrict__ slice_hdr) {
-    const int sl = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
-    if (sl >= n_slices) return;
-    const int s = slot_draw[sl * 32 + lane];
-    int v[BS_NCLS + 1] = {0, 0, 0, 0, 0, 0};
+                                                     int n_slices, int2* __restrict__ slice_hdr) {
+    const int w = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (w >= BS_NCLS * n_slices) return;
+    const int c = w / n_slices;
+    const int s = slot_draw[(size_t)w * 32 + lane];           // [class][slice][lane]
+    int rows = 0, dmax = 0;
     if (s >= 0) {
         const BsCnt t = draw_tot[s];
-#pragma unroll
-        for (int q = 0; q < BS_NCLS; ++q) v[q] = t.n[q];
-        v[BS_NCLS] = t.dmax;
+        rows = t.n[c];
+        dmax = c == BS_D ? t.dmax : 0;
     }
 #pragma unroll
-    for (int q = 0; q <= BS_NCLS; ++q)
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v[q] = max(v[q], __shfl_xor_sync(0xffffffffu, v[q], o));
-    if (lane == 0) {
-        slice_hdr[2 * sl] = make_int4(v[0], v[1], v[2], v[3]);
-        slice_hdr[2 * sl + 1] = make_int4(v[4], v[5], 0, 0);
+    for (int o = 16; o > 0; o >>= 1) {
+        rows = max(rows, __shfl_xor_sync(0xffffffffu, rows, o));
+        dmax = max(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
     }
+    if (lane == 0) slice_hdr[w] = make_int2(rows, dmax);
 }
 
 __global__ void __launch_bounds__(128) bs_fill_kernel(const uint2* __restrict__ nodes, const int32_t* __restrict__ tree_off,
                                                       const int32_t* __restrict__ tree_leaf_off, const double* __restrict__ leaf_mu,
-                                                      const int32_t* __restrict__ cut_off, int64_t n_trees, int m,
+                                                      const int32_t* __restrict__ cut_off, int64_t n_trees, int m, int S,
                                                       const BsCnt* __restrict__ tree_row, const int32_t* __restrict__ draw_slot,
                                                       BsLayout L, double fx_scale, unsigned char* __restrict__ pool) {
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n_trees) return;
-    const int slot = draw_slot[k / m], lane = slot & 31;
-    unsigned char* __restrict__ sp = pool + (int64_t)(slot >> 5) * L.slice_bytes;
+    const int s_draw = (int)(k / m);
+    int slot[BS_NCLS];
+#pragma unroll
+    for (int q = 0; q < BS_NCLS; ++q) slot[q] = draw_slot[(size_t)q * S + s_draw];
     const BsCnt r0 = tree_row[k];
     int row[BS_NCLS];
 #pragma unroll
@@ -255,15 +263,17 @@ __global__ void __launch_bounds__(128) bs_fill_kernel(const uint2* __restrict__ 
                      } else {
                          e.z = vc * rb;
                          e.w = (uint32_t)depth;
-                         uint32_t* __restrict__ anc = reinterpret_cast<uint32_t*>(sp + L.off_anc);
+                         uint32_t* __restrict__ anc = reinterpret_cast<uint32_t*>(pool + L.anc_off) +
+                                                      (int64_t)(slot[BS_D] >> 5) * L.anc_planes * L.cap[BS_D] * 32 + (slot[BS_D] & 31);
                          for (int a = 0; a < L.anc_planes; ++a)
-                             anc[((int64_t)a * L.cap_d + row[BS_D]) * 32 + lane] = a < depth ? path[a] : (uint32_t)L.ones_off;
+                             anc[((int64_t)a * L.cap[BS_D] + row[BS_D]) * 32] = a < depth ? path[a] : (uint32_t)L.ones_off;
                      }
-                     int rr = 0;
+                     int rr = 0, sl = 0, cap = 1;
+                     int64_t off = 0;
 #pragma unroll
                      for (int q = 0; q < BS_NCLS; ++q)
-                         if (q == c) { rr = row[q]; row[q] = rr + 1; }
-                     reinterpret_cast<uint4*>(sp + L.off[c])[rr * 32 + lane] = e;
+                         if (q == c) { rr = row[q]; row[q] = rr + 1; sl = slot[q]; cap = L.cap[q]; off = L.cls_off[q]; }
+                     reinterpret_cast<uint4*>(pool + off)[((int64_t)(sl >> 5) * cap + rr) * 32 + (sl & 31)] = e;
                  });
 }
 
@@ -279,12 +289,18 @@ void bs_configure(bartint_forest* f) {
     const int64_t ncuts = f->cut_off[(size_t)f->d];
     if (ncuts < 1 || f->max_depth < 1 || f->max_depth > 33) return;     // (no split anywhere: nothing to slice)
     if (f->draw_internal_max < 1 || f->draw_internal_max >= 65535 || f->m >= 8000) return;
-    int ch = 0;
-    for (int c : {8, 4, 2})
-        if ((size_t)(ncuts + 1) * (size_t)(c * 16 + 4) + 64 + (size_t)f->d * (size_t)c * 128 <= BS_SMEM_MAX) { ch = c; break; }
+    int ch = 0, perm = 0;
+    for (int c : {8, 4, 2}) {                          // the widest tile that fits, then the largest permutation block
+        for (int p : {BS_PERM, BS_PERM_SMALL})
+            if ((size_t)(ncuts + 1) * (size_t)(c * 16 + 4) + 64 + (size_t)f->d * (size_t)c * 128 + (size_t)p * 26 + 2048 <= BS_SMEM_MAX) {
+                ch = c; perm = p; break;
+            }
+        if (ch) break;
+    }
     if (ch == 0 || (ncuts + 1) * (int64_t)ch >= 1 << 14) return;         // row offsets are 14-bit counts of 16 bytes
     f->bs_ncuts = (int32_t)ncuts;
     f->bs_ch = ch;
+    f->bs_perm = perm;
     f->bs_rows = f->draw_internal_max;
     f->bs_anc = std::max(4, f->max_depth - 1);
     // fixed point: |delta| <= 2 max|mu| < 2^(e+1)  ->  |delta * 2^Q| < 2^61 with Q = 60 - e
@@ -301,36 +317,56 @@ int launch_build_bitslice(bartint_forest* f, cudaStream_t st) {
     if (!f->bs_ok) return BARTINT_OK;
     const BsLayout L = bs_layout_of(f);
     const int64_t n_trees = (int64_t)f->S * f->m;
-    const int n_slices = (f->S + 31) / 32;
-    const size_t pool_bytes = (size_t)L.slice_bytes * (size_t)n_slices;
+    const int n_slices = L.n_slices, n_slots = n_slices * 32;
+    const size_t pool_bytes = (size_t)L.total_bytes;
     BsCnt *tree_cnt = nullptr, *tree_row = nullptr, *draw_tot = nullptr;
     unsigned long long* key = nullptr;
     int32_t* draw_slot = nullptr;
     BI_CUDA(cudaMallocAsync((void**)&f->dev.bs_pool, pool_bytes, st));
-    BI_CUDA(cudaMallocAsync((void**)&f->dev.bs_slice_hdr, 2 * sizeof(int4) * (size_t)n_slices, st));
+    BI_CUDA(cudaMallocAsync((void**)&f->dev.bs_slice_hdr, sizeof(int2) * (size_t)BS_NCLS * (size_t)n_slices, st));
     BI_CUDA(cudaMallocAsync((void**)&f->dev.bs_base, sizeof(double) * (size_t)f->S, st));
-    BI_CUDA(cudaMallocAsync((void**)&f->dev.bs_slot_draw, sizeof(int32_t) * 32 * (size_t)n_slices, st));
+    BI_CUDA(cudaMallocAsync((void**)&f->dev.bs_slot_draw, sizeof(int32_t) * (size_t)BS_NCLS * (size_t)n_slots, st));
     BI_CUDA(cudaMallocAsync((void**)&tree_cnt, sizeof(BsCnt) * (size_t)n_trees, st));
     BI_CUDA(cudaMallocAsync((void**)&tree_row, sizeof(BsCnt) * (size_t)n_trees, st));
     BI_CUDA(cudaMallocAsync((void**)&draw_tot, sizeof(BsCnt) * (size_t)f->S, st));
-    BI_CUDA(cudaMallocAsync((void**)&key, sizeof(unsigned long long) * (size_t)f->S, st));
-    BI_CUDA(cudaMallocAsync((void**)&draw_slot, sizeof(int32_t) * (size_t)f->S, st));
+    BI_CUDA(cudaMallocAsync((void**)&key, sizeof(unsigned long long) * (size_t)BS_NCLS * (size_t)f->S, st));
+    BI_CUDA(cudaMallocAsync((void**)&draw_slot, sizeof(int32_t) * (size_t)BS_NCLS * (size_t)f->S, st));
     BI_CUDA(cudaMemsetAsync(f->dev.bs_pool, 0, pool_bytes, st));
-    BI_CUDA(cudaMemsetAsync(f->dev.bs_slot_draw, 0xFF, sizeof(int32_t) * 32 * (size_t)n_slices, st));   // -1: empty slot
+    BI_CUDA(cudaMemsetAsync(f->dev.bs_slot_draw, 0xFF, sizeof(int32_t) * (size_t)BS_NCLS * (size_t)n_slots, st));   // -1: empty slot
     const unsigned gt = (unsigned)((n_trees + 127) / 128);
     bs_count_kernel<<<gt, 128, 0, st>>>(f->dev.nodes, f->dev.tree_off, f->dev.cut_off, n_trees, tree_cnt);
     bs_draw_kernel<<<(unsigned)((f->S + 127) / 128), 128, 0, st>>>(tree_cnt, f->dev.tree_leaf_off, f->dev.leaf_mu, f->S, f->m,
                                                                   tree_row, draw_tot, key, f->dev.bs_base);
-    bs_rank_kernel<<<(unsigned)((f->S + 255) / 256), 256, 0, st>>>(key, f->S, f->S <= BS_SORT_MAX ? 1 : 0, draw_slot,
-                                                                  f->dev.bs_slot_draw);
-    bs_hdr_kernel<<<(unsigned)((n_slices * 32 + 127) / 128), 128, 0, st>>>(draw_tot, f->dev.bs_slot_draw, n_slices,
-                                                                          f->dev.bs_slice_hdr);
+    bs_rank_kernel<<<dim3((unsigned)((f->S + 255) / 256), BS_NCLS), 256, 0, st>>>(key, f->S, draw_slot, f->dev.bs_slot_draw, n_slots, f->bs_perm);
+    bs_hdr_kernel<<<(unsigned)((BS_NCLS * n_slices * 32 + 127) / 128), 128, 0, st>>>(draw_tot, f->dev.bs_slot_draw, n_slices,
+                                                                                      f->dev.bs_slice_hdr);
     bs_fill_kernel<<<gt, 128, 0, st>>>(f->dev.nodes, f->dev.tree_off, f->dev.tree_leaf_off, f->dev.leaf_mu, f->dev.cut_off,
-                                       n_trees, f->m, tree_row, draw_slot, L, std::ldexp(1.0, f->bs_q), f->dev.bs_pool);
+                                       n_trees, f->m, f->S, tree_row, draw_slot, L, std::ldexp(1.0, f->bs_q), f->dev.bs_pool);
     count_launch(5);
     for (void* q : {(void*)tree_cnt, (void*)tree_row, (void*)draw_tot, (void*)key, (void*)draw_slot}) cudaFreeAsync(q, st);
     BI_CUDA(cudaGetLastError());
     return BARTINT_OK;
+}
+
+// what the slices load, in mask-row references (for bartint_forest_bitslice_info): every class padded to the longest
+// draw of each of its slices.  Reads the slice headers back (blocks).
+int64_t bs_padded_refs(const bartint_forest* f) {
+    if (!f->bs_ok || f->dev.bs_slice_hdr == nullptr) return 0;
+    const int n_slices = (f->S + 31) / 32;
+    std::vector<int2> hdr((size_t)BS_NCLS * (size_t)n_slices);
+    if (cudaDeviceSynchronize() != cudaSuccess ||
+        cudaMemcpy(hdr.data(), f->dev.bs_slice_hdr, hdr.size() * sizeof(int2), cudaMemcpyDeviceToHost) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    int64_t padded = 0;
+    const int refs[BS_NCLS] = {0, 2, 3, 4, 1};
+    for (int c = 1; c < BS_NCLS; ++c)
+        for (int sl = 0; sl < n_slices; ++sl) {
+            const int2 h = hdr[(size_t)c * n_slices + sl];
+            padded += 32ll * h.x * (refs[c] + (c == BS_D ? h.y : 0));
+        }
+    return padded;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -338,8 +374,8 @@ int launch_build_bitslice(bartint_forest* f, cudaStream_t st) {
 // ---------------------------------------------------------------------------------------------
 struct BsParams {
     const unsigned char* pool;
-    const int4* slice_hdr;
-    const int32_t* slot_draw;
+    const int2* slice_hdr;      // [class][slice]: rows, deepest node (class D)
+    const int32_t* slot_draw;   // [class][slice * 32 + lane] -> draw or -1
     BsLayout L;
     const uint4* codes_pm;      // point-major packed codes (gather forests), or null
     const uint8_t* codes;       // feature-major code rows
@@ -347,13 +383,13 @@ struct BsParams {
     const int32_t* cut_off;
     int d, ncuts;
     int draw_begin, draw_end;
-    int n_slices, chunk_slices;
+    int n_slices, unit_chunks, perm;  // grid.y = permutation blocks x unit_chunks; perm = draws per block
     double inv_scale;           // 2^-Q
     double* draw_part;          // [n_tiles][draw_end - draw_begin]
 };
 
 // shared-memory layout of the evaluation kernel: [mask rows][row counts][slice counter][staged codes d x TILE]
-__host__ __device__ inline size_t bs_stage_off(int n_rows, int rowb) { return (((size_t)n_rows * (size_t)(rowb + 4) + 16 + 15) & ~(size_t)15); }
+__host__ __device__ inline size_t bs_stage_off(int n_rows, int rowb) { return (((size_t)n_rows * (size_t)(rowb + 4) + 32 + 15) & ~(size_t)15); }
 
 __device__ __forceinline__ int popc4(const uint4& v) { return __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w); }
 
@@ -373,27 +409,28 @@ struct PopAcc {
     __device__ __forceinline__ int total() const { return 2 * twos + __popc(ones); }
 };
 __device__ __forceinline__ uint4 lds16(const unsigned char* p) { return *reinterpret_cast<const uint4*>(p); }
+// 16 bytes at offset a ^ x of the CTA's shared memory.  A lane reads the chunks of a mask row in the order k ^ (lane % CH): the 8
+// lanes of an LDS.128 phase then hit 8 different bank groups.  Rows are aligned to their own size, so with
+// a = row + 16 * (lane % CH) chunk k ^ (lane % CH) is at a ^ (16 k): one LOP3 with an immediate, no table of offsets.
+#define lds16x(a, x) (*reinterpret_cast<const uint4*>(smem + ((a) ^ (uint32_t)(x))))
 
 // Rows [0, n) of one class, G at a time: the loads of the next group are in flight while this one is processed (the
 // row blocks are padded to a multiple of G with zero entries, so a group may always be loaded whole).
 template <int G, typename F>
 __device__ __forceinline__ void bs_rows(const uint4* __restrict__ rows, int n, F body) {
-    uint4 nxt[G];
+    uint4 w[G];
     if (n > 0) {
 #pragma unroll
-        for (int j = 0; j < G; ++j) nxt[j] = __ldg(rows + (size_t)j * 32);
+        for (int j = 0; j < G; ++j) w[j] = __ldg(rows + (size_t)j * 32);
     }
     for (int k0 = 0; k0 < n; k0 += G) {
-        uint4 cur[G];
+        const bool more = k0 + G < n;
 #pragma unroll
-        for (int j = 0; j < G; ++j) cur[j] = nxt[j];
-        if (k0 + G < n) {
-#pragma unroll
-            for (int j = 0; j < G; ++j) nxt[j] = __ldg(rows + (size_t)(k0 + G + j) * 32);
+        for (int j = 0; j < G; ++j) {
+            const uint4 e = w[j];                  // entry k0 + j; its register slot takes entry k0 + G + j at once
+            if (more) w[j] = __ldg(rows + (size_t)(k0 + G + j) * 32);
+            if (k0 + j < n) body(e);
         }
-#pragma unroll
-        for (int j = 0; j < G; ++j)
-            if (k0 + j < n) body(cur[j]);
     }
 }
 
@@ -418,6 +455,8 @@ __global__ void __launch_bounds__(BS_THREADS, 1) eval_bitslice_kernel(const BsPa
     // (the tile's codes are first staged feature-major in shared memory with coalesced loads: a thread then needs two
     //  LDS.128 for the 32 codes of its column instead of 32 strided byte loads from global memory)
     unsigned char* const s_codes = smem + bs_stage_off(n_rows, ROWB);                  // [d][TILE]
+    unsigned long long* const s_acc =                                                   // [perm][2] integer accumulators
+        reinterpret_cast<unsigned long long*>(smem + ((bs_stage_off(n_rows, ROWB) + (size_t)prm.d * TILE + 15) & ~(size_t)15));
     if (prm.codes_pm != nullptr) {
         for (int pt = tid; pt < TILE; pt += BS_THREADS) {
             const int64_t i = tile_base + pt;
@@ -464,124 +503,179 @@ __global__ void __launch_bounds__(BS_THREADS, 1) eval_bitslice_kernel(const BsPa
         reinterpret_cast<uint32_t*>(s_mask)[(size_t)prm.ncuts * WORDS + i] = ~0u;
     __syncthreads();
     // chunk order of this lane: the 8 lanes of an LDS.128 phase read 8 different bank groups
-    uint32_t rot[CH];
-#pragma unroll
-    for (int c = 0; c < CH; ++c) rot[c] = (uint32_t)((c ^ (lane & (CH - 1))) * 16);
+    const uint32_t mb = (uint32_t)(lane & (CH - 1)) * 16u;          // (the mask table starts at offset 0, 128-byte aligned)
     // ---- 3. per-row popcounts over the tile (class A reads these instead of the masks) ----
     for (int r = tid; r < n_rows; r += BS_THREADS) {
-        const unsigned char* row = s_mask + (size_t)r * ROWB;
+        const uint32_t row = mb + (uint32_t)r * ROWB;
         int cnt = 0;
 #pragma unroll
-        for (int c = 0; c < CH; ++c) cnt += popc4(lds16(row + rot[c]));
+        for (int c = 0; c < CH; ++c) cnt += popc4(lds16x(row, c * 16));
         s_cnt[r] = (uint32_t)cnt;
     }
     __syncthreads();
 
-    // ---- 4. the slices of this CTA's chunk, one warp per slice, one lane per draw.  Slices are sorted by cost
-    // (ascending), so the warps take them from a shared counter starting with the most expensive one: with a fixed
-    // assignment warp 15 got the two longest of the 32 slices and the CTA waited for it with an idle data pipe
-    // (0.50 -> 0.47 ms at cfg 2).  Splitting a slice into quarter units with an integer combine in shared memory was
-    // tried and lost (0.51 ms): every unit pays the L2 round trip of its first row group again. ----
-    const int ndraws = prm.draw_end - prm.draw_begin;
-    const int sl0 = blockIdx.y * prm.chunk_slices;
-    const int sl1 = min(sl0 + prm.chunk_slices, prm.n_slices);
+    // ---- 4. the rows.  A WORK UNIT is one (class, slice): 32 draws with (nearly) the same number of rows of that class,
+    // one lane per draw.  The warps take the units of this CTA's permutation block from a shared counter -- the classes
+    // in the order B, C2, C3, D, A and the slices of a class from the longest down -- and add the lane's exact integer
+    // sums to its draw's accumulators in shared memory (64-bit integer atomics: the order of arrival does not matter).
+    // Each class sorts the draws on its own, so a slice pads only to the longest of 32 nearly equal draws; with one
+    // common assignment of draws to slices the classes padded 7.8e7 wavefronts for 5.9e7 needed at cfg 2. ----
+    // CTA constants of the unit loop live in shared memory and are re-read where needed: the loop bodies need every
+    // register for mask words in flight (128 per thread at 512 threads)
+    volatile int* const s_ctl = s_next + 1;             // [0] first slice, [1] slices, [2] units, [3] unit chunk
+    if (tid == 0) {
+        const int pblock = prm.draw_begin / prm.perm + blockIdx.y / prm.unit_chunks;
+        const int a = pblock * (prm.perm / 32), b = min(a + prm.perm / 32, prm.n_slices);
+        s_ctl[0] = a; s_ctl[1] = b - a; s_ctl[2] = BS_NCLS * (b - a); s_ctl[3] = blockIdx.y % prm.unit_chunks;
+    }
+    __syncthreads();
+    {
+        const int sl0 = s_ctl[0], nsl = s_ctl[1], draw0 = sl0 * 32;
+        for (int i = tid; i < nsl * 64; i += BS_THREADS) s_acc[i] = 0ull;
+        // the units' slice headers and slot -> draw maps, staged once: a unit would otherwise start with two dependent L2
+        // round trips, and a CTA runs up to 5 x 32 of them
+        int2* const s_hdr = reinterpret_cast<int2*>(s_acc + prm.perm * 2);                  // [class][slice of the block]
+        uint16_t* const s_slot = reinterpret_cast<uint16_t*>(s_hdr + BS_NCLS * (prm.perm / 32));   // [class][slot] -> draw - draw0
+        for (int i = tid; i < BS_NCLS * nsl; i += BS_THREADS)
+            s_hdr[i] = __ldg(&prm.slice_hdr[(size_t)(i / nsl) * prm.n_slices + sl0 + i % nsl]);
+        for (int i = tid; i < BS_NCLS * nsl * 32; i += BS_THREADS) {
+            const int sd = __ldg(&prm.slot_draw[(size_t)(i / (nsl * 32)) * prm.n_slices * 32 + draw0 + i % (nsl * 32)]);
+            s_slot[i] = sd < 0 ? (uint16_t)0xFFFFu : (uint16_t)(sd - draw0);
+        }
+    }
+    __syncthreads();
     for (;;) {
         int take = 0;
         if (lane == 0) take = atomicAdd(s_next, 1);
         take = __shfl_sync(0xffffffffu, take, 0);
-        const int sl = sl1 - 1 - take;
-        if (sl < sl0) break;
-        const int s = __ldg(&prm.slot_draw[sl * 32 + lane]);
-        const bool wanted = s >= prm.draw_begin && s < prm.draw_end;
-        if (!__any_sync(0xffffffffu, wanted)) continue;
-        const int4 h0 = __ldg(&prm.slice_hdr[2 * sl]), h1 = __ldg(&prm.slice_hdr[2 * sl + 1]);
-        const unsigned char* __restrict__ sp = prm.pool + (int64_t)sl * prm.L.slice_bytes;
+        int u = take * prm.unit_chunks + s_ctl[3];                 // this CTA's share of the units
+        if (u >= s_ctl[2]) break;
+        // units in the order (slice rank descending; B, C2, C3, D, A of that rank): at any moment the warps work on a
+        // mix of classes -- class A uses no mask rows, and a CTA whose warps all run A units leaves the data pipe idle
+        const int ci = u % BS_NCLS;
+        const int c = ci == 4 ? BS_A : ci + 1;
+        int2 hd;
+        int sl;
+        {
+            const int nsl = s_ctl[1];
+            const int idx = c * nsl + nsl - 1 - u / BS_NCLS;
+            const int2* s_hdr = reinterpret_cast<const int2*>(s_acc + prm.perm * 2);
+            const uint16_t* s_slot = reinterpret_cast<const uint16_t*>(s_hdr + BS_NCLS * (prm.perm / 32));
+            const int so = s_slot[idx * 32 + lane];
+            sl = s_ctl[0] + nsl - 1 - u / BS_NCLS;
+            const int s = so == 0xFFFF ? -1 : s_ctl[0] * 32 + so;
+            if (!__any_sync(0xffffffffu, s >= prm.draw_begin && s < prm.draw_end)) continue;
+            hd = s_hdr[idx];
+        }
+        if (hd.x == 0) continue;
+        const uint4* __restrict__ rows =
+            reinterpret_cast<const uint4*>(prm.pool + prm.L.cls_off[c]) + (size_t)sl * prm.L.cap[c] * 32 + lane;
         unsigned long long acc0 = 0ull;      // sum of (low 32 bits of delta) * count
         long long acc1 = 0ll;                // sum of (high 32 bits of delta, signed) * count
         auto add = [&](const uint4& e, int cnt) {
             acc0 += (unsigned long long)e.x * (uint32_t)cnt;
             acc1 += (long long)(int)e.y * (long long)cnt;
         };
-        bs_rows<8>(reinterpret_cast<const uint4*>(sp + prm.L.off[BS_A]) + lane, h0.x,
-                   [&](const uint4& e) { add(e, (int)s_cnt[e.z]); });
-        bs_rows<4>(reinterpret_cast<const uint4*>(sp + prm.L.off[BS_B]) + lane, h0.y, [&](const uint4& e) {
-            const uint32_t pm = (uint32_t)((int)e.z >> 31);
-            const unsigned char* ap = s_mask + (e.z & 0x7FFFFFFFu);
-            const unsigned char* aj = s_mask + e.w;
-            PopAcc pa;
+        if (c == BS_A) {
+            bs_rows<8>(rows, hd.x, [&](const uint4& e) { add(e, (int)s_cnt[e.z]); });
+        } else if (c == BS_B) {
+            bs_rows<2>(rows, hd.x, [&](const uint4& e) {
+                const uint32_t pm = (uint32_t)((int)e.z >> 31);
+                const uint32_t ap = mb + (e.z & 0x7FFFFFFFu), aj = mb + e.w;
+                PopAcc pa;
 #pragma unroll
-            for (int c = 0; c < CH; ++c) {
-                const uint4 mp = lds16(ap + rot[c]), mj = lds16(aj + rot[c]);
-                pa.add4((mp.x ^ pm) & mj.x, (mp.y ^ pm) & mj.y, (mp.z ^ pm) & mj.z, (mp.w ^ pm) & mj.w);
-            }
-            add(e, pa.total());
-        });
-        bs_rows<4>(reinterpret_cast<const uint4*>(sp + prm.L.off[BS_C2]) + lane, h0.z, [&](const uint4& e) {
-            const unsigned char* aj = s_mask + ((e.z & 0x3FFFu) << 4);
-            const unsigned char* a0 = s_mask + (((e.z >> 14) & 0x3FFFu) << 4);
-            const unsigned char* a1 = s_mask + ((e.w & 0x3FFFu) << 4);
-            const uint32_t p0 = (uint32_t)((int)(e.z << 3) >> 31), p1 = (uint32_t)((int)(e.z << 2) >> 31);
-            int cnt = 0;
+                for (int k = 0; k < CH; ++k) {
+                    const uint4 mp = lds16x(ap, k * 16), mj = lds16x(aj, k * 16);
+                    pa.add4((mp.x ^ pm) & mj.x, (mp.y ^ pm) & mj.y, (mp.z ^ pm) & mj.z, (mp.w ^ pm) & mj.w);
+                }
+                add(e, pa.total());
+            });
+        } else if (c == BS_C2) {
+            bs_rows<4>(rows, hd.x, [&](const uint4& e) {
+                const uint32_t aj = mb + ((e.z & 0x3FFFu) << 4), a0 = mb + (((e.z >> 14) & 0x3FFFu) << 4),
+                               a1 = mb + ((e.w & 0x3FFFu) << 4);
+                const uint32_t p0 = (uint32_t)((int)(e.z << 3) >> 31), p1 = (uint32_t)((int)(e.z << 2) >> 31);
+                int cnt = 0;
 #pragma unroll
-            for (int c = 0; c < CH; ++c) {
-                const uint4 mj = lds16(aj + rot[c]), m0 = lds16(a0 + rot[c]), m1 = lds16(a1 + rot[c]);
-                cnt += __popc((m0.x ^ p0) & (m1.x ^ p1) & mj.x) + __popc((m0.y ^ p0) & (m1.y ^ p1) & mj.y) +
-                       __popc((m0.z ^ p0) & (m1.z ^ p1) & mj.z) + __popc((m0.w ^ p0) & (m1.w ^ p1) & mj.w);
-            }
-            add(e, cnt);
-        });
-        bs_rows<2>(reinterpret_cast<const uint4*>(sp + prm.L.off[BS_C3]) + lane, h0.w, [&](const uint4& e) {
-            const unsigned char* aj = s_mask + ((e.z & 0x3FFFu) << 4);
-            const unsigned char* a0 = s_mask + (((e.z >> 14) & 0x3FFFu) << 4);
-            const unsigned char* a1 = s_mask + ((e.w & 0x3FFFu) << 4);
-            const unsigned char* a2 = s_mask + (((e.w >> 14) & 0x3FFFu) << 4);
-            const uint32_t p0 = (uint32_t)((int)(e.z << 3) >> 31), p1 = (uint32_t)((int)(e.z << 2) >> 31),
-                           p2 = (uint32_t)((int)(e.z << 1) >> 31);
-            int cnt = 0;
+                for (int k = 0; k < CH; ++k) {
+                    const uint4 mj = lds16x(aj, k * 16), m0 = lds16x(a0, k * 16), m1 = lds16x(a1, k * 16);
+                    cnt += __popc((m0.x ^ p0) & (m1.x ^ p1) & mj.x) + __popc((m0.y ^ p0) & (m1.y ^ p1) & mj.y) +
+                           __popc((m0.z ^ p0) & (m1.z ^ p1) & mj.z) + __popc((m0.w ^ p0) & (m1.w ^ p1) & mj.w);
+                }
+                add(e, cnt);
+            });
+        } else if (c == BS_C3) {
+            bs_rows<2>(rows, hd.x, [&](const uint4& e) {
+                const uint32_t aj = mb + ((e.z & 0x3FFFu) << 4), a0 = mb + (((e.z >> 14) & 0x3FFFu) << 4),
+                               a1 = mb + ((e.w & 0x3FFFu) << 4), a2 = mb + (((e.w >> 14) & 0x3FFFu) << 4);
+                const uint32_t p0 = (uint32_t)((int)(e.z << 3) >> 31), p1 = (uint32_t)((int)(e.z << 2) >> 31),
+                               p2 = (uint32_t)((int)(e.z << 1) >> 31);
+                int cnt = 0;
 #pragma unroll
-            for (int c = 0; c < CH; ++c) {
-                const uint4 mj = lds16(aj + rot[c]), m0 = lds16(a0 + rot[c]), m1 = lds16(a1 + rot[c]), m2 = lds16(a2 + rot[c]);
-                cnt += __popc((m0.x ^ p0) & (m1.x ^ p1) & (m2.x ^ p2) & mj.x) + __popc((m0.y ^ p0) & (m1.y ^ p1) & (m2.y ^ p2) & mj.y) +
-                       __popc((m0.z ^ p0) & (m1.z ^ p1) & (m2.z ^ p2) & mj.z) + __popc((m0.w ^ p0) & (m1.w ^ p1) & (m2.w ^ p2) & mj.w);
-            }
-            add(e, cnt);
-        });
-        if (h1.x > 0) {      // class D: depth >= 4, ancestors in planes (rare)
-            const uint4* __restrict__ rows = reinterpret_cast<const uint4*>(sp + prm.L.off[BS_D]) + lane;
-            const uint32_t* __restrict__ anc = reinterpret_cast<const uint32_t*>(sp + prm.L.off_anc) + lane;
-            for (int k = 0; k < h1.x; ++k) {
+                for (int k = 0; k < CH; ++k) {
+                    const uint4 mj = lds16x(aj, k * 16), m0 = lds16x(a0, k * 16), m1 = lds16x(a1, k * 16), m2 = lds16x(a2, k * 16);
+                    cnt += __popc((m0.x ^ p0) & (m1.x ^ p1) & (m2.x ^ p2) & mj.x) + __popc((m0.y ^ p0) & (m1.y ^ p1) & (m2.y ^ p2) & mj.y) +
+                           __popc((m0.z ^ p0) & (m1.z ^ p1) & (m2.z ^ p2) & mj.z) + __popc((m0.w ^ p0) & (m1.w ^ p1) & (m2.w ^ p2) & mj.w);
+                }
+                add(e, cnt);
+            });
+        } else {      // class D: depth >= 4, ancestors in planes (rare)
+            const uint32_t* __restrict__ anc = reinterpret_cast<const uint32_t*>(prm.pool + prm.L.anc_off) +
+                                               (size_t)sl * prm.L.anc_planes * prm.L.cap[BS_D] * 32 + lane;
+            for (int k = 0; k < hd.x; ++k) {
                 const uint4 e = __ldg(rows + (size_t)k * 32);
                 uint4 r[CH];
-                const unsigned char* aj = s_mask + e.z;
+                const uint32_t aj = mb + e.z;
 #pragma unroll
-                for (int c = 0; c < CH; ++c) r[c] = lds16(aj + rot[c]);
-                for (int a = 0; a < h1.y; ++a) {
-                    const uint32_t w = __ldg(anc + ((size_t)a * prm.L.cap_d + k) * 32);
+                for (int q = 0; q < CH; ++q) r[q] = lds16x(aj, q * 16);
+                for (int a = 0; a < hd.y; ++a) {
+                    const uint32_t w = __ldg(anc + ((size_t)a * prm.L.cap[BS_D] + k) * 32);
                     const uint32_t pm = (uint32_t)((int)w >> 31);
-                    const unsigned char* ap = s_mask + (w & 0x7FFFFFFFu);
+                    const uint32_t ap = mb + (w & 0x7FFFFFFFu);
 #pragma unroll
-                    for (int c = 0; c < CH; ++c) {
-                        const uint4 mp = lds16(ap + rot[c]);
-                        r[c].x &= mp.x ^ pm; r[c].y &= mp.y ^ pm; r[c].z &= mp.z ^ pm; r[c].w &= mp.w ^ pm;
+                    for (int q = 0; q < CH; ++q) {
+                        const uint4 mp = lds16x(ap, q * 16);
+                        r[q].x &= mp.x ^ pm; r[q].y &= mp.y ^ pm; r[q].z &= mp.z ^ pm; r[q].w &= mp.w ^ pm;
                     }
                 }
                 int cnt = 0;
 #pragma unroll
-                for (int c = 0; c < CH; ++c) cnt += popc4(r[c]);
+                for (int q = 0; q < CH; ++q) cnt += popc4(r[q]);
                 add(e, cnt);
             }
         }
-        if (wanted)
-            prm.draw_part[(int64_t)blockIdx.x * ndraws + (s - prm.draw_begin)] =
-                ((double)acc1 * 4294967296.0 + (double)acc0) * prm.inv_scale;
+        // the unit's draw slot again (nothing derived from u was kept in registers across the rows)
+        asm volatile("" : "+r"(u));
+        {
+            const int nsl = s_ctl[1], cj = u % BS_NCLS;
+            const int idx = (cj == 4 ? BS_A : cj + 1) * nsl + nsl - 1 - u / BS_NCLS;
+            const uint16_t* s_slot = reinterpret_cast<const uint16_t*>(s_acc + prm.perm * 2 + BS_NCLS * (prm.perm / 32));
+            const int so = s_slot[idx * 32 + lane];
+            if (so != 0xFFFF) {
+                atomicAdd(&s_acc[so * 2], acc0);
+                atomicAdd(&s_acc[so * 2 + 1], (unsigned long long)acc1);
+            }
+        }
+    }
+    __syncthreads();
+    {
+        const int nsl = s_ctl[1], draw0 = s_ctl[0] * 32, uchunk = s_ctl[3];
+        const int ndraws = prm.draw_end - prm.draw_begin;
+        for (int i = threadIdx.x; i < nsl * 32; i += BS_THREADS) {
+            const int s = draw0 + i;
+            if (s >= prm.draw_begin && s < prm.draw_end)
+                prm.draw_part[((int64_t)blockIdx.x * prm.unit_chunks + uchunk) * ndraws + (s - prm.draw_begin)] =
+                    ((double)(long long)s_acc[2 * i + 1] * 4294967296.0 + (double)s_acc[2 * i]) * prm.inv_scale;
+        }
     }
 }
 
 size_t bs_smem_bytes(const bartint_forest* f) {
-    return bs_stage_off(f->bs_ncuts + 1, f->bs_ch * 16) + (size_t)f->d * (size_t)f->bs_ch * 128;
+    return ((bs_stage_off(f->bs_ncuts + 1, f->bs_ch * 16) + (size_t)f->d * (size_t)f->bs_ch * 128 + 15) & ~(size_t)15) +
+           (size_t)f->bs_perm * 16 + (size_t)BS_NCLS * (f->bs_perm / 32) * 8 + (size_t)BS_NCLS * f->bs_perm * 2;
 }
 int bs_tile(const bartint_forest* f) { return f->bs_ch * 128; }
-int64_t bs_pool_bytes(const bartint_forest* f) { return f->bs_ok ? bs_layout_of(f).slice_bytes * ((f->S + 31) / 32) : 0; }
+int64_t bs_pool_bytes(const bartint_forest* f) { return f->bs_ok ? bs_layout_of(f).total_bytes : 0; }
 
 typedef void (*bs_kernel_t)(const BsParams);
 static bs_kernel_t bs_kernel_for(int ch) {
@@ -607,7 +701,8 @@ int launch_eval_bitslice(const bartint_forest* f, const bartint_points* p, const
     prm.draw_begin = plan.draw_begin;
     prm.draw_end = plan.draw_end;
     prm.n_slices = (f->S + 31) / 32;
-    prm.chunk_slices = plan.chunk_draws;          // (in slices for this kernel)
+    prm.perm = f->bs_perm;
+    prm.unit_chunks = plan.chunk_draws;           // (unit chunks per permutation block for this kernel)
     prm.inv_scale = std::ldexp(1.0, -f->bs_q);
     prm.draw_part = draw_part;
     const size_t smem = bs_smem_bytes(f);

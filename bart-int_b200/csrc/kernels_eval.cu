@@ -396,16 +396,17 @@ EvalPlan make_plan(const bartint_forest* f, const bartint_points* p, uint32_t fl
     pl.use_bitslice = f->bs_ok && f->dev.bs_pool != nullptr && !want_moments && !want_full &&
                       !(flags & (BARTINT_FORCE_WALK | BARTINT_NO_BITSLICE));
     if (pl.use_bitslice) {
-        // CTA = one tile of points x a run of slices (32 draws each), one warp per slice.  Every CTA rebuilds the
-        // tile's mask table, so the draws are only split when there are too few tiles to occupy the SMs.
+        // CTA = one tile of points x one permutation block of draws (f->bs_perm) x a share of that block's work units.  Every
+        // CTA rebuilds the tile's mask table, so the units are only split when there are too few tiles to occupy the SMs.
         pl.tile = bs_tile(f);
         pl.n_tiles = (int)std::max<int64_t>((p->N + pl.tile - 1) / pl.tile, 1);
         int n_sm = 148;
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, f->device);
-        const int n_slices = (f->S + 31) / 32;        // (draws are permuted over the slices: every slice is visited)
-        int chunks = std::max(1, std::min(n_slices, (n_sm + pl.n_tiles - 1) / pl.n_tiles));
-        pl.chunk_draws = (n_slices + chunks - 1) / chunks;                       // slices per CTA
-        pl.n_chunks = (n_slices + pl.chunk_draws - 1) / pl.chunk_draws;
+        const int n_pblocks = (draw_end - 1) / f->bs_perm - draw_begin / f->bs_perm + 1;     // blocks the draw range touches
+        const int units = 5 * std::min((f->S + 31) / 32, f->bs_perm / 32);
+        int uc = std::max(1, std::min(units / 16, (n_sm + pl.n_tiles * n_pblocks - 1) / (pl.n_tiles * n_pblocks)));
+        pl.chunk_draws = uc;                                                     // unit chunks per permutation block
+        pl.n_chunks = n_pblocks * uc;
         return pl;
     }
     pl.use_table = f->table_ok && !(flags & BARTINT_FORCE_WALK);

@@ -107,6 +107,27 @@ def test_draw_subranges_and_point_sources():
     pts.close(); f.close()
 
 
+@pytest.mark.parametrize("d,numcut,S,m,N,chunks", [
+    (4, 100, 1100, 6, 2500, 8),       # two permutation blocks of 1024 draws
+    (3, 60, 2500, 3, 1300, 8),        # three blocks, the last one partial
+    (12, 255, 300, 5, 1500, 4),       # masks leave room for 256 accumulators only: blocks of 256 draws
+])
+def test_permutation_blocks(d, numcut, S, m, N, chunks):
+    """Each class sorts the draws inside blocks of 1024 (or 256) draws; a CTA owns one block.  Draw ranges that start or
+    end inside a block, or cover a block none of whose slices is wanted, must give the same per-draw means."""
+    rng = np.random.default_rng(77 + S)
+    x_train = rng.random((max(5 * d, 30), d))
+    ff = synth.prior_forest(5 + d, S, m, x_train, synth.genz_gaussian(x_train), numcut=numcut)
+    X = rng.random((N, d))
+    f = Forest.from_soa(ff)
+    assert f.bitslice_ok and f.bitslice_tile == 128 * chunks, f.bitslice_info
+    f.close()
+    _check(ff, X)
+    for draws in [(0, 256), (255, 257), (S - 40, S), (200, S - 1), (1023, min(1025, S))]:
+        if draws[1] <= S and draws[0] < draws[1]:
+            _check(ff, X, draws=draws)
+
+
 def test_leaf_value_scales():
     """The fixed-point scale follows max |mu|: tiny, huge and mixed-magnitude leaf values keep ~1e-16 relative accuracy."""
     rng = np.random.default_rng(2)
