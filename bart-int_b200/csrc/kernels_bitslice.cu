@@ -721,22 +721,34 @@ int launch_eval_bitslice(const bartint_forest* f, const bartint_points* p, const
 // of the same kernel adds the blocks' sums when there is more than one (cfg 4: 97 656 tiles x 2000 draws = 1.56 GB of
 // partials, which 63 CTAs walking all tiles read at a fraction of the HBM rate).
 constexpr int BS_RED_BLOCK = 1024;
-__global__ void __launch_bounds__(256) bs_reduce_kernel(const double* __restrict__ part, int n_tiles, int ndraws,
-                                                        const double* __restrict__ base, double n_points,
-                                                        double* __restrict__ out) {
-    __shared__ double s_part[8][33];
-    const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
-    const int s = blockIdx.x * 32 + x;
+__global__ void __launch_bounds__(1024) bs_reduce_kernel(const double* __restrict__ part, int n_tiles, int ndraws,
+                                                         const double* __restrict__ base, double n_points,
+                                                         double* __restrict__ out) {
+    // 8 draws x 128 tile lanes per CTA: a thread adds every 128th tile of its draw (8 loads for 1024 tiles, all in
+    // flight at once; 8 lanes read one 64-byte piece of a row), then the partial sums are combined in a fixed order
+    __shared__ double s_part[128][9];
+    __shared__ double s_mid[8][9];
+    const int x = threadIdx.x & 7, y = threadIdx.x >> 3;
+    const int s = blockIdx.x * 8 + x;
     const int t0 = blockIdx.y * BS_RED_BLOCK, t1 = min(t0 + BS_RED_BLOCK, n_tiles);
     double acc = 0.0;
-    if (s < ndraws)
-        for (int t = t0 + y; t < t1; t += 8) acc += part[(int64_t)t * ndraws + s];
+    if (s < ndraws) {
+#pragma unroll 8
+        for (int t = t0 + y; t < t1; t += 128) acc += part[(int64_t)t * ndraws + s];
+    }
     s_part[y][x] = acc;
     __syncthreads();
-    if (y == 0 && s < ndraws) {
-        double tot = s_part[0][x];
+    if (threadIdx.x < 64) {
+        double tot = 0.0;
 #pragma unroll
-        for (int k = 1; k < 8; ++k) tot += s_part[k][x];
+        for (int k = 0; k < 16; ++k) tot += s_part[y * 16 + k][x];
+        s_mid[y][x] = tot;
+    }
+    __syncthreads();
+    if (threadIdx.x < 8 && s < ndraws) {
+        double tot = s_mid[0][x];
+#pragma unroll
+        for (int k = 1; k < 8; ++k) tot += s_mid[k][x];
         out[(int64_t)blockIdx.y * ndraws + s] = base != nullptr ? tot + n_points * base[s] : tot;
     }
 }
@@ -747,15 +759,15 @@ int launch_bs_reduce(const bartint_forest* f, const double* draw_part, int n_til
     const double* base = f->dev.bs_base + draw_begin;
     const int n_blocks = (n_tiles + BS_RED_BLOCK - 1) / BS_RED_BLOCK;
     if (n_blocks <= 1) {
-        bs_reduce_kernel<<<(ndraws + 31) / 32, 256, 0, st>>>(draw_part, n_tiles, ndraws, base, (double)N, draw_sum);
+        bs_reduce_kernel<<<(ndraws + 7) / 8, 1024, 0, st>>>(draw_part, n_tiles, ndraws, base, (double)N, draw_sum);
         count_launch();
     } else {
         BI_REQUIRE(n_blocks <= BS_RED_BLOCK, BARTINT_ERR_UNSUPPORTED, "more than %d tiles in one evaluation", BS_RED_BLOCK * BS_RED_BLOCK);
         double* tmp = nullptr;
         BI_CUDA(cudaMallocAsync((void**)&tmp, sizeof(double) * (size_t)n_blocks * (size_t)ndraws, st));
-        bs_reduce_kernel<<<dim3((unsigned)((ndraws + 31) / 32), (unsigned)n_blocks), 256, 0, st>>>(draw_part, n_tiles, ndraws, nullptr,
+        bs_reduce_kernel<<<dim3((unsigned)((ndraws + 7) / 8), (unsigned)n_blocks), 1024, 0, st>>>(draw_part, n_tiles, ndraws, nullptr,
                                                                                                    0.0, tmp);
-        bs_reduce_kernel<<<(ndraws + 31) / 32, 256, 0, st>>>(tmp, n_blocks, ndraws, base, (double)N, draw_sum);
+        bs_reduce_kernel<<<(ndraws + 7) / 8, 1024, 0, st>>>(tmp, n_blocks, ndraws, base, (double)N, draw_sum);
         count_launch(2);
         cudaFreeAsync(tmp, st);
     }
