@@ -17,16 +17,18 @@
 // 64-bit integers, so the sum over the nodes of a draw and the points of a tile is exact and independent of the
 // order in which nodes are visited; one rounding happens when the tile's total is converted to fp64.
 //
-// Work layout ("lanes are draws"): the nodes of 32 consecutive draws (a SLICE) are stored as ELL rows -- row k holds
-// the k-th node of each of the 32 draws, 16 bytes per lane -- so a warp reads a row with one coalesced LDG.128, every
-// lane accumulates the sum of ITS draw in registers, and no cross-lane reduction or atomics are needed.  Node classes
-// by depth, each padded to the slice's longest draw with delta = 0 entries (draws are assigned to slices in the order
-// of their row counts, so the padding is small):
+// Work layout ("lanes are draws"): the nodes of a draw are split into CLASSES by depth, and per class the nodes of 32
+// draws (a SLICE of that class) are stored as ELL rows -- row k holds the k-th node of each of the 32 draws, 16 bytes per
+// lane -- so a warp reads a row with one coalesced LDG.128 and every lane accumulates the sum of ITS draw in registers.
+// A slice is padded to its longest draw with delta = 0 entries; each class assigns the draws to its slices on its own,
+// in the order of that class's row counts (inside permutation blocks of 1024 draws), so the padding stays small.  A warp's
+// work unit is one (class, slice); at its end every lane adds its two 64-bit integers to its draw's accumulators in
+// shared memory (integer atomics: exact, so the order does not matter).
 //     A  root nodes            popc(M[v,c]) over the tile comes from a per-tile count table P[v,c]   (1 LDS.32)
 //     B  children of the root  popc((M[parent] ^ pol) & M[own])                                   (2 x CH LDS.128)
 //     C2, C3  depth 2 and 3    own mask ANDed with 2 / 3 ancestor literals, all references packed in the entry
 //     D  depth >= 4            ancestor references in separate planes (rare)
-// Shared-memory rows are CH x 16 bytes (CH x 128 points); lane q reads the chunks in the order c ^ (q & 7), so the
+// Shared-memory rows are CH x 16 bytes (CH x 128 points); lane q reads the chunks in the order k ^ (q % CH), so the
 // eight lanes of an LDS.128 phase always hit eight different 16-byte bank groups whatever rows they address.
 #include <algorithm>
 #include <cmath>
@@ -39,7 +41,6 @@ namespace bartint {
 
 constexpr int BS_THREADS = 512;                 // 16 warps, one CTA per SM (the mask table fills shared memory)
 constexpr size_t BS_SMEM_MAX = 227 * 1024;
-constexpr int BS_SORT_MAX = 16384;              // draws are ordered by cost (rank sort, O(S^2)) up to this many
 
 // ---------------------------------------------------------------------------------------------
 // device builder: walk form -> ELL rows (run once per forest, right after the upload)
