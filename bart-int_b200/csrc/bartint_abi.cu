@@ -550,6 +550,23 @@ int bartint_points_from_device(const bartint_forest* f, const double* dX, int64_
     return rc;
 }
 
+// BARTINT_TIMING=2: wall-clock stamps of GPU progress (host callbacks on the streams; CLOCK_MONOTONIC ms modulo 10^5, the
+// clock Python's time.monotonic() reads), for the timeline of a design step across the members of a device group.
+namespace {
+struct Stamp { int k; int b; const char* what; };
+bool stamps_on() { static const bool on = [] { const char* e = std::getenv("BARTINT_TIMING"); return e && e[0] == '2'; }(); return on; }
+void CUDART_CB stamp_cb(void* p) {
+    Stamp* s = static_cast<Stamp*>(p);
+    timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
+    const double t = std::fmod(1e3 * (double)ts.tv_sec + 1e-6 * (double)ts.tv_nsec, 1e5);
+    fprintf(stderr, "[bartint-stamp] %.3f device %d: %s %d\n", t, s->k, s->what, s->b);
+    delete s;
+}
+void stamp(cudaStream_t st, int k, const char* what, int b = 0) {
+    if (stamps_on()) cudaLaunchHostFunc(st, stamp_cb, new Stamp{k, b, what});
+}
+}  // namespace
+
 static cudaError_t staged_submit_block(bartint_staged* s, int b) {
     const int64_t r0 = (int64_t)b * s->block_rows, rows = std::min(s->block_rows, s->N - r0);
     cudaError_t e = cudaSuccess;
@@ -557,6 +574,7 @@ static cudaError_t staged_submit_block(bartint_staged* s, int b) {
         e = cudaMemcpy2DAsync(s->dX + r0, sizeof(double) * (size_t)s->N, s->host_X + r0, sizeof(double) * (size_t)s->host_ld,
                               sizeof(double) * (size_t)rows, (size_t)s->d, cudaMemcpyHostToDevice, s->copy_stream);
     if (e == cudaSuccess) e = cudaEventRecord(s->block_done[b], s->copy_stream);
+    stamp(s->copy_stream, s->device, "X block landed", b);
     return e;
 }
 
@@ -1615,10 +1633,17 @@ int bartint_design_step_dbarts098(const char* const* tree_strings, const double*
         std::vector<bartint_forest*> forests;
         bartint_points* pm = nullptr;
         double *d_sum = nullptr, *d_gath = nullptr;
+        // a shard that arrives in row blocks is binned and evaluated block by block, like member 0's own rows: when the
+        // last block lands only that block's work is left, not the whole shard's
+        bartint_points views[8];
+        int n_views = 0;
+        double* d_block_part = nullptr;       // [n_views][S]
+        cudaEvent_t done_ev = nullptr;        // the member's row of member 0's gather buffer has been written
     };
     std::vector<Member> members((size_t)GM);
     std::vector<void*> blobs;                 // forest images on member 0, one per chunk
     std::vector<cudaEvent_t> packed_ev;
+    cudaEvent_t arena_ev = nullptr;           // member 0's result buffer exists (recorded on its stream)
     auto cleanup = [&]() {
         if (multi) {
             group_wait();
@@ -1630,6 +1655,8 @@ int bartint_design_step_dbarts098(const char* const* tree_strings, const double*
                     if (M->pm) bartint_points_destroy(M->pm);
                     if (M->d_sum) cudaFreeAsync(M->d_sum, group_stream(g));
                     if (M->d_gath) cudaFreeAsync(M->d_gath, group_stream(g));
+                    if (M->d_block_part) cudaFreeAsync(M->d_block_part, group_stream(g));
+                    if (M->done_ev) cudaEventDestroy(M->done_ev);
                     (void)cudaGetLastError();
                     return (int)BARTINT_OK;
                 });
@@ -1647,6 +1674,7 @@ int bartint_design_step_dbarts098(const char* const* tree_strings, const double*
         if (d_counts) cudaFreeAsync(d_counts, nullptr);
         for (void* b : blobs) cudaFreeAsync(b, nullptr);
         for (cudaEvent_t ev : packed_ev) cudaEventDestroy(ev);
+        if (arena_ev) cudaEventDestroy(arena_ev);
         for (bartint_forest* f : forests) bartint_forest_destroy(f);
         (void)cudaGetLastError();
     };
@@ -1692,6 +1720,10 @@ int bartint_design_step_dbarts098(const char* const* tree_strings, const double*
     const size_t total = 4 * nS + 4 + 2 * (size_t)G * nC + nC + (size_t)std::max<int64_t>(weights_len, 1) + 8 * nS +
                          (size_t)(GM + 1) * nS;
     DS_CUDA(cudaMallocAsync((void**)&d_buf, sizeof(double) * total, st));
+    if (multi) {          // the other members write into this buffer: their streams wait until it exists
+        DS_CUDA(cudaEventCreateWithFlags(&arena_ev, cudaEventDisableTiming));
+        DS_CUDA(cudaEventRecord(arena_ev, st));
+    }
     double* d_int = d_buf;
     double* d_int_res = d_int + nS;
     double* d_int_ms = d_int_res + nS;
@@ -1734,6 +1766,7 @@ int bartint_design_step_dbarts098(const char* const* tree_strings, const double*
         forests.push_back(f);
         // the sub-forest's copies and table build are still in flight on the default stream: order `st` after them
         DS_CUDA(cudaEventRecord(built, nullptr));
+        stamp(nullptr, f->device, "forest built, chunk", g);
         DS_CUDA(cudaStreamWaitEvent(st, built, 0));
         if (g == 0 && mc != nullptr) DS_CUDA(staged_submit_rest(mc));   // the first forest is on the bus: now the rest of X
         if (multi) {
@@ -1760,15 +1793,56 @@ int bartint_design_step_dbarts098(const char* const* tree_strings, const double*
                     bartint_forest* fk = nullptr;
                     int r = forest_from_image(hdr->data(), hb, blob, dev0, db, ws, false, &fk);
                     if (r) return r;
+                    stamp(ws, group_device(k), "forest image + bit-sliced rows ready, chunk", g);
                     M->forests.push_back(fk);
                     if (M->d_sum == nullptr) {
                         BI_CUDA(cudaMallocAsync((void**)&M->d_sum, sizeof(double) * (size_t)S, ws));
                         BI_CUDA(cudaMallocAsync((void**)&M->d_gath, sizeof(double) * (size_t)S * (size_t)GM, ws));
                         BI_CUDA(cudaMemsetAsync(M->d_sum, 0, sizeof(double) * (size_t)S, ws));
+                        if (shard->N > 0 && shard->n_blocks > 1) {
+                            if ((r = make_points(fk, shard->N, shard->d, ws, &M->pm))) return r;
+                            BI_CUDA(cudaMallocAsync((void**)&M->d_block_part, sizeof(double) * (size_t)S * (size_t)shard->n_blocks, ws));
+                            for (int b = 0; b < shard->n_blocks; ++b) {
+                                const int64_t r0 = (int64_t)b * shard->block_rows, rows = std::min(shard->block_rows, shard->N - r0);
+                                if (rows <= 0) break;
+                                const int64_t rows_padded = (b == shard->n_blocks - 1 || r0 + shard->block_rows >= shard->N)
+                                                                ? M->pm->Npad - r0 : shard->block_rows;
+                                BI_CUDA(cudaStreamWaitEvent(ws, shard->block_done[b], 0));
+                                if (M->pm->codes_pm) {
+                                    if ((r = launch_bin_pack_points(shard->dX + r0, shard->N, rows, shard->d, fk->dev.cut_off, fk->dev.cut_val,
+                                                                    fk->max_cuts, fk->route, M->pm->codes_pm + r0, rows_padded, ws))) return r;
+                                    M->pm->codes_valid = false;
+                                } else if ((r = launch_bin_points(shard->dX + r0, shard->N, rows, shard->d, fk->dev.cut_off, fk->dev.cut_val,
+                                                                  fk->max_cuts, fk->route, M->pm->codes + r0, M->pm->Npad, ws, rows_padded))) {
+                                    return r;
+                                }
+                                bartint_points& v = M->views[M->n_views];
+                                v = *M->pm;                                   // shallow: same buffers, rows [r0, r0 + rows)
+                                v.codes_valid = true;
+                                v.codes = M->pm->codes + r0;
+                                v.codes_pm = M->pm->codes_pm ? M->pm->codes_pm + r0 : nullptr;
+                                v.N = rows;
+                                ++M->n_views;
+                                // (first chunk: evaluate this block before waiting for the next one)
+                                if ((r = eval_core(fk, &v, 0u, 0, s1 - s0, M->d_block_part + (size_t)(M->n_views - 1) * (size_t)S + (size_t)s0,
+                                                   nullptr, nullptr, nullptr, nullptr, 1.0, 0.0, 1, ws))) return r;
+                                stamp(ws, group_device(k), "shard block evaluated", b);
+                            }
+                            return (int)BARTINT_OK;
+                        }
                         if (shard->N > 0 && (r = bartint_staged_points(fk, shard, ws, &M->pm))) return r;
                     }
                     if (M->pm == nullptr) return (int)BARTINT_OK;          // an empty shard contributes zeros
-                    return eval_core(fk, M->pm, 0u, 0, s1 - s0, M->d_sum + s0, nullptr, nullptr, nullptr, nullptr, 1.0, 0.0, 1, ws);
+                    if (M->n_views > 0) {
+                        for (int b = 0; b < M->n_views; ++b)
+                            if ((r = eval_core(fk, &M->views[b], 0u, 0, s1 - s0, M->d_block_part + (size_t)b * (size_t)S + (size_t)s0,
+                                               nullptr, nullptr, nullptr, nullptr, 1.0, 0.0, 1, ws))) return r;
+                        return (int)BARTINT_OK;
+                    }
+                    stamp(ws, group_device(k), "shard binned, chunk", g);
+                    r = eval_core(fk, M->pm, 0u, 0, s1 - s0, M->d_sum + s0, nullptr, nullptr, nullptr, nullptr, 1.0, 0.0, 1, ws);
+                    stamp(ws, group_device(k), "shard evaluated, chunk", g);
+                    return r;
                 });
             }
         }
@@ -1815,6 +1889,7 @@ int bartint_design_step_dbarts098(const char* const* tree_strings, const double*
                 if (g > 0) DS_CUDA(cudaStreamWaitEvent(bst[b], built, 0));
                 DS_RC(eval_core(f, &views[b], 0u, 0, s1 - s0, d_block_part + (size_t)b * nS + (size_t)s0, nullptr, nullptr,
                                 nullptr, nullptr, 1.0, 0.0, 1, bst[b]));
+                stamp(bst[b], f->device, "block evaluated", b);
             }
         }
         if (want_int && s0 < n_int)
@@ -1842,16 +1917,46 @@ int bartint_design_step_dbarts098(const char* const* tree_strings, const double*
         DS_RC(launch_reduce_draw_parts(d_block_part, n_bst, S, d_sum, st));
     }
     if (multi) {
-        // one exchange per call: every member's per-draw sums over its rows -> all members (ncclAllGather on the
-        // compute streams), added in member order on member 0
+        // one exchange per call: every member's per-draw sums over its rows -> member 0, added there in member order.
+        // Default: every member WRITES its row of member 0's gather buffer over NVLink peer memory -- the kernel that adds
+        // the member's row blocks stores its result there directly -- and member 0's stream waits for one event per
+        // member.  BARTINT_GROUP_EXCHANGE=nccl (or no peer access): ncclAllGather on the compute streams.
+        const bool peer = group_peer_writes();
+        const int dev0 = group_device(0);
+        for (int k = 1; k < GM; ++k) {
+            Member* M = &members[(size_t)k];
+            group_post(k, [=] {           // (runs after the member's chunk jobs: one queue per member)
+                cudaStream_t ws = group_stream(k);
+                double* dst = peer ? d_gath + (size_t)k * nS : M->d_sum;
+                if (peer) BI_CUDA(cudaStreamWaitEvent(ws, arena_ev, 0));          // the buffer exists on member 0
+                if (M->n_views > 0) {
+                    int r = launch_reduce_draw_parts(M->d_block_part, M->n_views, S, dst, ws);
+                    if (r) return r;
+                } else if (peer) {
+                    BI_CUDA(cudaMemcpyPeerAsync(dst, dev0, M->d_sum, group_device(k), sizeof(double) * nS, ws));
+                }
+                if (peer) {
+                    if (M->done_ev == nullptr) BI_CUDA(cudaEventCreateWithFlags(&M->done_ev, cudaEventDisableTiming));
+                    BI_CUDA(cudaEventRecord(M->done_ev, ws));
+                }
+                return (int)BARTINT_OK;
+            });
+        }
         DS_RC(group_wait());
         if (pm == nullptr) DS_CUDA(cudaMemsetAsync(d_sum, 0, sizeof(double) * nS, st));
-        DS_CUDA(cudaMemcpyAsync(d_sum_local, d_sum, sizeof(double) * nS, cudaMemcpyDeviceToDevice, st));
-        std::vector<double*> send((size_t)GM), recv((size_t)GM);
-        std::vector<cudaStream_t> streams((size_t)GM);
-        send[0] = d_sum_local; recv[0] = d_gath; streams[0] = st;
-        for (int k = 1; k < GM; ++k) { send[(size_t)k] = members[(size_t)k].d_sum; recv[(size_t)k] = members[(size_t)k].d_gath; streams[(size_t)k] = group_stream(k); }
-        DS_RC(group_allgather(send.data(), recv.data(), nS, streams.data()));
+        stamp(st, group_device(0), "member 0 ready for the exchange");
+        if (peer) {
+            DS_CUDA(cudaMemcpyAsync(d_gath, d_sum, sizeof(double) * nS, cudaMemcpyDeviceToDevice, st));
+            for (int k = 1; k < GM; ++k) DS_CUDA(cudaStreamWaitEvent(st, members[(size_t)k].done_ev, 0));
+        } else {
+            DS_CUDA(cudaMemcpyAsync(d_sum_local, d_sum, sizeof(double) * nS, cudaMemcpyDeviceToDevice, st));
+            std::vector<double*> send((size_t)GM), recv((size_t)GM);
+            std::vector<cudaStream_t> streams((size_t)GM);
+            send[0] = d_sum_local; recv[0] = d_gath; streams[0] = st;
+            for (int k = 1; k < GM; ++k) { send[(size_t)k] = members[(size_t)k].d_sum; recv[(size_t)k] = members[(size_t)k].d_gath; streams[(size_t)k] = group_stream(k); }
+            DS_RC(group_allgather(send.data(), recv.data(), nS, streams.data()));
+        }
+        stamp(st, group_device(0), "exchange done");
         DS_RC(launch_reduce_draw_parts(d_gath, GM, S, d_sum, st));
     }
     if (want_mc) {
@@ -1864,6 +1969,11 @@ int bartint_design_step_dbarts098(const char* const* tree_strings, const double*
     if (want_mc && draw_mean) DS_CUDA(cudaMemcpyAsync(draw_mean, d_dmean, sizeof(double) * nS, cudaMemcpyDeviceToHost, st));
     if (want_mc && draw_mean_var) DS_CUDA(cudaMemcpyAsync(draw_mean_var, d_mv, sizeof(double) * 2, cudaMemcpyDeviceToHost, st));
     DS_CUDA(cudaStreamSynchronize(st));
+    if (stamps_on()) {
+        timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
+        fprintf(stderr, "[bartint-stamp] %.3f host: step begin\n[bartint-stamp] %.3f host: results on the host\n", std::fmod(t_begin, 1e5),
+                std::fmod(1e3 * (double)ts.tv_sec + 1e-6 * (double)ts.tv_nsec, 1e5));
+    }
     if (timing) {
         fprintf(stderr, "[bartint] design step: %d chunks, total %.3f ms\n", G, now_ms() - t_begin);
         for (int g = 0; g < G; ++g)

@@ -262,6 +262,7 @@ int group_size();                                   // 1 when bartint_init has n
 int group_generation();                             // changes with every bartint_init / bartint_shutdown
 int group_device(int g);
 bool group_has(int device);                         // is `device` member 0 of the group
+bool group_peer_writes();                           // gather-to-root by peer stores (NVLink) instead of the NCCL exchange
 cudaStream_t group_stream(int g);                   // member g's worker stream (g >= 1)
 void group_post(int g, std::function<int()> fn);    // g >= 1; fn returns a bartint_status
 int group_wait();                                   // all posted tasks done; first error (message copied to this thread)

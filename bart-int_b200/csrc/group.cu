@@ -107,6 +107,7 @@ struct Group {
     std::vector<std::unique_ptr<Worker>> workers;   // [0] unused (member 0 = the calling thread)
     std::vector<ncclComm_t> comms;
     bool nccl = false;
+    bool peer_to_root = true;                       // every member can store into member 0's memory
 };
 
 std::mutex g_mu;
@@ -138,8 +139,17 @@ int group_generation() { return g_generation; }
 int group_device(int g) { return g_group ? g_group->devices[(size_t)g] : 0; }
 bool group_has(int device) { return g_group != nullptr && g_group->devices[0] == device; }
 cudaStream_t group_stream(int g) { return g_group && g >= 1 ? g_group->workers[(size_t)g]->st : nullptr; }
+// The members can store into member 0's memory (NVLink peer access, or the same device in test mode) and the NCCL
+// exchange has not been asked for: the design step's gather-to-root is then done with peer writes.
+bool group_peer_writes() {
+    const char* e = getenv("BARTINT_GROUP_EXCHANGE");          // read per call: the tests switch it
+    const bool want_nccl = e && strcmp(e, "nccl") == 0;
+    return g_group != nullptr && g_group->peer_to_root && !(want_nccl && g_group->nccl);
+}
 const char* group_exchange_name() {
     return !g_group || g_group->devices.size() < 2 ? "none (one device)"
+           : group_peer_writes() ? "peer writes of the per-draw partial sums into member 0's buffer (NVLink; ncclAllGather with "
+                                   "BARTINT_GROUP_EXCHANGE=nccl and in bartint_eval) + member-ordered sum"
            : g_group->nccl ? "ncclAllGather of the per-draw partial sums + member-ordered sum"
                            : "peer copies of the per-draw partial sums + member-ordered sum (same-device test mode)";
 }
@@ -262,7 +272,7 @@ int bartint_init(int n_gpus) {
             if (devices[(size_t)a] == devices[(size_t)b]) continue;
             int can = 0;
             cudaDeviceCanAccessPeer(&can, devices[(size_t)a], devices[(size_t)b]);
-            if (!can) continue;
+            if (!can) { if (b == 0) g->peer_to_root = false; continue; }
             cudaError_t pe = cudaDeviceEnablePeerAccess(devices[(size_t)b], 0);
             if (pe != cudaSuccess) (void)cudaGetLastError();                   // already enabled
             if (pool) {

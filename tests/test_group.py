@@ -67,15 +67,38 @@ def test_group_on_one_device_equals_single(members, monkeypatch):
     assert bi.group_size() == 1
 
 
-@pytest.mark.skipif(_n_gpus() < 2, reason="needs >= 2 GPUs")
-def test_group_over_all_gpus_equals_single():
-    case = _case(S=200, m=20, d=6, N=300_007, C=100, seed=8)
+def test_group_shards_in_row_blocks(monkeypatch):
+    """Shards of >= 2^18 rows arrive in four row blocks; every member bins and evaluates its shard block by block (the
+    last member's shard is shorter and ragged), for one and for several chunks of draws."""
+    case = _case(S=40, m=8, d=3, N=2 * 300_032 + 270_001, C=16, seed=11)
     want = _step(case, 0)
+    monkeypatch.setenv("BARTINT_GROUP_DEVICES", "0,0,0")
+    try:
+        assert bi.init_group(3) == 3
+        for n_chunks in (0, 1, 3):
+            _same(_step(case, "group", n_chunks), want)
+    finally:
+        bi.shutdown_group()
+
+
+@pytest.mark.skipif(_n_gpus() < 2, reason="needs >= 2 GPUs")
+def test_group_over_all_gpus_equals_single(monkeypatch):
+    case = _case(S=200, m=20, d=6, N=300_007, C=100, seed=8)
+    big = _case(S=64, m=10, d=4, N=_n_gpus() * 270_336 - 5, C=32, seed=9)      # shards that arrive in row blocks
+    want, want_big = _step(case, 0), _step(big, 0)
     try:
         g = bi.init_group(0)
-        assert g == _n_gpus() and "ncclAllGather" in bi.group_exchange()
+        assert g == _n_gpus()
+        # the gather-to-root of the step: peer stores into member 0's buffer (default) and the NCCL exchange
+        assert bi.group_exchange().startswith("peer writes")
         for _ in range(2):
             _same(_step(case, "group"), want)
+        _same(_step(big, "group"), want_big)
+        monkeypatch.setenv("BARTINT_GROUP_EXCHANGE", "nccl")
+        assert bi.group_exchange().startswith("ncclAllGather")
+        _same(_step(case, "group"), want)
+        _same(_step(big, "group", 2), want_big)
+        monkeypatch.delenv("BARTINT_GROUP_EXCHANGE")
         assert bi.init_group(2) == 2          # re-opening with another size replaces the group
         _same(_step(case, "group"), want)
     finally:
