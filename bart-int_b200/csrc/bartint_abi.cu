@@ -1519,10 +1519,18 @@ static int forest_from_image(const void* host_header, int64_t host_bytes, const 
     }
     // one allocation holds every array (image_base); the DeviceForest pointers point into it
     if (e == cudaSuccess) e = cudaMallocAsync((void**)&f->image_base, (size_t)std::max<int64_t>(h.device_bytes, 256), st);
-    if (e == cudaSuccess)
-        e = src_device >= 0 && src_device != f->device
-                ? cudaMemcpyPeerAsync(f->image_base, f->device, d_blob, src_device, (size_t)h.device_bytes, st)
-                : cudaMemcpyAsync(f->image_base, d_blob, (size_t)h.device_bytes, cudaMemcpyDeviceToDevice, st);
+    if (e == cudaSuccess) {
+        // Inside a device group the image is pulled over NVLink by a KERNEL of this device: a copy-engine transfer
+        // (cudaMemcpyPeerAsync) queued behind the member's own host-to-device matrix blocks and arrived when the
+        // whole shard had landed -- the forest was the last thing a member received (8 GPUs: 1.4 ms of the step).
+        if (src_device >= 0 && group_size() > 1 && group_peer_reads() && src_device == group_device(0)) {
+            if (launch_copy_bytes(f->image_base, d_blob, h.device_bytes, st) != BARTINT_OK) e = cudaErrorUnknown;
+        } else {
+            e = src_device >= 0 && src_device != f->device
+                    ? cudaMemcpyPeerAsync(f->image_base, f->device, d_blob, src_device, (size_t)h.device_bytes, st)
+                    : cudaMemcpyAsync(f->image_base, d_blob, (size_t)h.device_bytes, cudaMemcpyDeviceToDevice, st);
+        }
+    }
     if (e == cudaSuccess) {
         int64_t sizes[11];
         void** slots[11];
@@ -1943,6 +1951,7 @@ int bartint_design_step_dbarts098(const char* const* tree_strings, const double*
             });
         }
         DS_RC(group_wait());
+        if (timing) fprintf(stderr, "[bartint]   members' work enqueued by their threads at %.3f ms\n", now_ms() - t_begin);
         if (pm == nullptr) DS_CUDA(cudaMemsetAsync(d_sum, 0, sizeof(double) * nS, st));
         stamp(st, group_device(0), "member 0 ready for the exchange");
         if (peer) {

@@ -262,6 +262,7 @@ int group_size();                                   // 1 when bartint_init has n
 int group_generation();                             // changes with every bartint_init / bartint_shutdown
 int group_device(int g);
 bool group_has(int device);                         // is `device` member 0 of the group
+bool group_peer_reads();                            // every member can load from member 0's memory (peer access is on)
 bool group_peer_writes();                           // gather-to-root by peer stores (NVLink) instead of the NCCL exchange
 cudaStream_t group_stream(int g);                   // member g's worker stream (g >= 1)
 void group_post(int g, std::function<int()> fn);    // g >= 1; fn returns a bartint_status
@@ -330,6 +331,9 @@ int launch_eval_table(const bartint_forest* f, const bartint_points* p, const Ev
 int launch_table_leaf(const bartint_forest* f, const bartint_points* p, int32_t draw_begin, int32_t draw_end,
                       int32_t* leaf_out, cudaStream_t st);
 int launch_reduce_draw_parts(const double* draw_part, int n_tiles, int ndraws, double* draw_sum, cudaStream_t st);
+// dst[0, bytes) = src[0, bytes) by an SM kernel (16-byte words; src may be peer memory): no copy engine is involved, so
+// the copy cannot queue behind a host-to-device transfer in flight on the destination
+int launch_copy_bytes(void* dst, const void* src, int64_t bytes, cudaStream_t st);
 int launch_merge_point_parts(const double* pt_mean, const double* pt_m2, int n_chunks, int chunk_draws, int ndraws,
                              int64_t N, double* mean_out, double* m2_out, cudaStream_t st);
 int launch_merge_shards(const double* mean, const double* m2, int G, const int32_t* d_counts, int64_t N,

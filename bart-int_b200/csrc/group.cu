@@ -141,6 +141,7 @@ bool group_has(int device) { return g_group != nullptr && g_group->devices[0] ==
 cudaStream_t group_stream(int g) { return g_group && g >= 1 ? g_group->workers[(size_t)g]->st : nullptr; }
 // The members can store into member 0's memory (NVLink peer access, or the same device in test mode) and the NCCL
 // exchange has not been asked for: the design step's gather-to-root is then done with peer writes.
+bool group_peer_reads() { return g_group != nullptr && g_group->peer_to_root; }
 bool group_peer_writes() {
     const char* e = getenv("BARTINT_GROUP_EXCHANGE");          // read per call: the tests switch it
     const bool want_nccl = e && strcmp(e, "nccl") == 0;

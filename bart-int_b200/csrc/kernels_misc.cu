@@ -602,6 +602,25 @@ __global__ void __launch_bounds__(256) reduce_draw_parts_kernel(const double* __
     }
 }
 
+__global__ void __launch_bounds__(256) copy_bytes_kernel(uint4* __restrict__ dst, const uint4* __restrict__ src, int64_t n16,
+                                                         unsigned char* dst_tail, const unsigned char* src_tail, int tail) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) dst[i] = src[i];
+    if (blockIdx.x == 0 && (int)threadIdx.x < tail) dst_tail[threadIdx.x] = src_tail[threadIdx.x];
+}
+
+int launch_copy_bytes(void* dst, const void* src, int64_t bytes, cudaStream_t st) {
+    if (bytes <= 0) return BARTINT_OK;
+    BI_REQUIRE(((uintptr_t)dst & 15) == 0 && ((uintptr_t)src & 15) == 0, BARTINT_ERR_ARG, "internal: unaligned device copy");
+    const int64_t n16 = bytes / 16;
+    const int blocks = (int)std::min<int64_t>(std::max<int64_t>((n16 + 255) / 256, 1), 148 * 8);
+    copy_bytes_kernel<<<blocks, 256, 0, st>>>((uint4*)dst, (const uint4*)src, n16, (unsigned char*)dst + n16 * 16,
+                                              (const unsigned char*)src + n16 * 16, (int)(bytes - n16 * 16));
+    count_launch();
+    BI_CUDA(cudaGetLastError());
+    return BARTINT_OK;
+}
+
 int launch_reduce_draw_parts(const double* draw_part, int n_tiles, int ndraws, double* draw_sum, cudaStream_t st) {
     if (ndraws == 0) return BARTINT_OK;
     reduce_draw_parts_kernel<<<(ndraws + 31) / 32, 256, 0, st>>>(draw_part, n_tiles, ndraws, draw_sum);

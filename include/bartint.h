@@ -66,10 +66,11 @@ int bartint_set_device(int device);       /* forests/points are created on the c
  * 0..n-1 (n <= 0: every visible device): peer access, one worker thread and stream per member, one NCCL communicator
  * per member (ncclCommInitAll; libnccl.so.2 is loaded with dlopen).  A matrix staged with device = BARTINT_DEVICE_GROUP
  * is split into contiguous row shards, one per member, and bartint_design_step_dbarts098 given such a matrix
- * exports the posterior once (all host threads), replicates every chunk's forest image to the other members with
- * peer copies over NVLink, evaluates each member's rows there, and combines the members' per-draw sums with one
- * ncclAllGather + member-ordered sum on the compute streams; bartint_eval shards the rows of its host matrix the same
- * way.  Not thread safe: one caller at a time (R is).
+ * exports the posterior once (all host threads), replicates every chunk's forest image to the other members over
+ * NVLink, evaluates each member's rows there row block by row block, and gathers the members' per-draw sums on member 0
+ * (peer stores into its buffer; ncclAllGather on the compute streams with BARTINT_GROUP_EXCHANGE=nccl or without peer
+ * access) for the member-ordered sum; bartint_eval shards the rows of its host matrix the same way and exchanges with
+ * ncclAllGather.  Not thread safe: one caller at a time (R is).
  * bartint_group_exchange(): the name of the exchange in use (for reports). */
 int bartint_init(int n_gpus);
 int bartint_group_size(void);             /* 1 before bartint_init */
