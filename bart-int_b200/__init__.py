@@ -12,7 +12,7 @@ Layout
 """
 from .forest import (FlatForest, Forest, Points, StagedMatrix, WireStrings, BartIntError,  # noqa: F401
                      design_step_dbarts, init_group, group_size, group_exchange, shutdown_group, topk)
-from . import api, hostmem, synth  # noqa: F401
+from . import api, synth  # noqa: F401
 
 __all__ = ["FlatForest", "Forest", "Points", "StagedMatrix", "WireStrings", "BartIntError", "design_step_dbarts", "init_group",
            "group_size", "group_exchange", "shutdown_group", "topk", "api", "synth"]

@@ -1,4 +1,4 @@
-"""Host-side placement of a page-locked point matrix on a multi-socket box (Linux; used by bench.py and tools/).
+"""Host-side placement of a page-locked point matrix on a multi-socket box (Linux; used by tools/numa_probe.py).
 
 One process drives all GPUs (bartint_init), so one host matrix feeds 8 copy engines at once.  Pages that live on the
 socket a GPU hangs off are read by its DMA engine without crossing the inter-socket link; `numa_local_pinned_matrix`

@@ -8,7 +8,9 @@ sys.path.insert(0, ROOT)
 import numpy as np
 import torch
 import bartint_b200 as bi
-from bartint_b200 import StagedMatrix, WireStrings, design_step_dbarts, synth, hostmem
+from bartint_b200 import StagedMatrix, WireStrings, design_step_dbarts, synth
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+import hostmem
 
 G = torch.cuda.device_count()
 out = {"gpus": G, "cores": len(os.sched_getaffinity(0)), "numa_nodes": hostmem.numa_nodes(),
