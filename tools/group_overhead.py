@@ -34,6 +34,25 @@ def run(target):
     return round(1e3 * float(np.median(ts[4:])), 3), round(1e3 * float(min(ts[4:])), 3), o["draw_mean"]
 
 
+# the bare bus transfer of the same shards (d column pieces per GPU, all GPUs at once)
+if len(set(os.environ.get("BARTINT_GROUP_DEVICES", "0,1").split(","))) > 1 and torch.cuda.device_count() >= G:
+    Xt = torch.from_numpy(X.T)
+    devb = [torch.empty((Xt.shape[0], n_each), dtype=torch.float64, device=f"cuda:{g}") for g in range(G)]
+    strm = [torch.cuda.Stream(device=g) for g in range(G)]
+    ts = []
+    for rep in range(5):
+        for g in range(G):
+            torch.cuda.synchronize(g)
+        t0 = time.perf_counter()
+        for j in range(Xt.shape[0]):
+            for g in range(G):
+                with torch.cuda.stream(strm[g]):
+                    devb[g][j].copy_(Xt[j, g * n_each:(g + 1) * n_each], non_blocking=True)
+        for g in range(G):
+            strm[g].synchronize()
+        ts.append(time.perf_counter() - t0)
+    out["bare_h2d_of_the_shards_ms"] = round(1e3 * float(np.median(ts[1:])), 3)
+    del devb
 os.environ["BARTINT_GROUP_MIN_ROWS"] = "1"
 a = run(0)
 out["one_device_ms (median, min)"] = a[:2]

@@ -27,7 +27,7 @@ import bartint_b200 as bi
 from bartint_b200 import StagedMatrix, WireStrings, design_step_dbarts, synth
 
 G = torch.cuda.device_count() if len(sys.argv) < 2 else int(sys.argv[1])
-N, d = 1_000_000, 10
+N, d = (int(sys.argv[2]) if len(sys.argv) > 2 else 1_000_000), 10
 c = synth.CONFIGS[2]
 x_train, y_train = synth.make_design(2)
 ff = synth.prior_forest(2000, c["S"], c["m"], x_train, y_train)
