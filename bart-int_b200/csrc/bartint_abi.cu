@@ -615,9 +615,12 @@ static int stage_rows(const double* X, int64_t N, int64_t ld, int32_t d, int dev
     }
     if (e == cudaSuccess) e = cudaMallocAsync((void**)&s->dX, sizeof(double) * (size_t)std::max<int64_t>(N * d, 1), s->copy_stream);
     if (e == cudaSuccess && N * d > 0) {
-        if (N >= (int64_t)1 << 18) {      // 4 row blocks: column-major, so each block is a d-row 2-D copy
-            s->n_blocks = 4;
-            s->block_rows = ((N + 3) / 4 + TK_NPAD - 1) / TK_NPAD * TK_NPAD;
+        if (N >= (int64_t)1 << 18) {      // 4 row blocks (8 from 160 MB): column-major, so each block is a d-row 2-D copy
+            // (the evaluation of the LAST block is the tail no transfer hides, and the first forest upload queues behind
+            //  the block in flight on the copy engine: 8*10^6 x 10 rows in four 160 MB blocks had 0.9 ms and 3 ms of those)
+            const int nb = N * (int64_t)d * 8 >= ((int64_t)160 << 20) ? 8 : 4;
+            s->n_blocks = nb;
+            s->block_rows = ((N + nb - 1) / nb + TK_NPAD - 1) / TK_NPAD * TK_NPAD;
             s->host_X = X;
             for (int b = 0; b < s->n_blocks && e == cudaSuccess; ++b)
                 if (s->block_done[b] == nullptr) e = cudaEventCreateWithFlags(&s->block_done[b], cudaEventDisableTiming);

@@ -93,3 +93,25 @@ def test_full_size_properties(cfg2_full):
     assert np.max(np.abs(full.mean(axis=0) - red["point_mean"])) <= 1e-12 * max(scale, 1.0)
     assert np.max(np.abs(full.var(axis=0, ddof=1) - red["point_var"])) <= 1e-10 * max(scale * scale, 1.0)
     f.close()
+
+
+def test_large_host_matrix_arrives_in_eight_row_blocks():
+    """A host matrix of 160 MB or more is staged in eight row blocks (four below that): the fused step on 2.2 * 10^6 rows
+    equals the separate calls on a point handle."""
+    rng = np.random.default_rng(21)
+    x_train = rng.random((60, 10))
+    ff = synth.prior_forest(77, 48, 12, x_train, synth.genz_gaussian(x_train))
+    X = np.asfortranarray(rng.random((2_200_003, 10)))
+    Xc = rng.random((50, 10))
+    strings, fits = ff.to_dbarts_state(x_train)
+    sx, sxc = StagedMatrix(X), StagedMatrix(np.asfortranarray(Xc))
+    o = design_step_dbarts(strings, fits, x_train, ff.cut_lists(), ff.y_min, ff.y_max, mc=sx, candidates=sxc, weights=1.0)
+    sx.close(); sxc.close()
+    f = Forest.from_soa(ff)
+    pts = f.points(X)
+    want = f.eval(pts, want=("draw_mean",))["draw_mean"]
+    pts.close()
+    scale = ff.y_max - ff.y_min
+    assert np.max(np.abs(o["draw_mean"] - want)) <= 1e-13 * max(scale, 1.0)
+    assert np.max(np.abs(o["cand_var"] - f.eval(Xc, want=("point_var",))["point_var"])) <= 1e-10 * max(scale * scale, 1.0)
+    f.close()
